@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native AAURoverEnv-v0 non-physics MDP hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port), host cores
+
+Headline metric (BASELINE.json): height-scan rays/s on cfg-2 -- 4096 envs x 961 rays per GPU on the synthetic
+200 m x 200 m / 2,000,000-triangle terrain.  A "step" is one height-scan pass over one batch of synthetic poses.
+The same run also measures the fused non-physics step (cfg-3 at N=1, cfg-5 = 8192 envs/GPU + the NCCL
+episode-statistics all-reduce under torchrun) and reports it under "extra".
+
+Timing: CUDA events on the launching stream around every timed step, L2 flushed (256 MiB write) between steps and
+excluded from the timed region, max over ranks.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TERRAIN = dict(size_m=200.0, grid_res=0.2, seed=0)
+SCAN_ENVS_PER_GPU = 4096  # cfg-2
+STEP_ENVS_1GPU = 16384  # cfg-3
+STEP_ENVS_PER_GPU_MULTI = 8192  # cfg-5
+N_RAYS = 961
+TERRAIN_BYTES = 36.0e6  # compulsory mesh footprint (12.0 MB vertices + 24.0 MB indices)
+POSE_SETS = 8
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(kernel: str):
+    """DRAM bytes per launch from the committed ncu capture (profiles/ncu_summary.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons of one GPU while the timed region runs (pynvml, ~20 ms period)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            log("clock sampling unavailable:", e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def build_world(need_tables_for: int | None, device):
+    """Synthetic terrain + scan grid (+ resample tables for `need_tables_for` envs)."""
+    from isaac_rover_orbit_b200 import ops
+    from isaac_rover_orbit_b200 import terrain as TR
+
+    t0 = time.time()
+    v, f = TR.make_synthetic_terrain(**TERRAIN)
+    grid = ops.ScanGridHandle.from_mesh(v, f, device)
+    log(f"terrain {v.shape[0]} verts / {f.shape[0]} tris, scan grid {grid.grid.nbytes() / 1e6:.1f} MB "
+        f"({time.time() - t0:.1f}s)")
+    tables = None
+    if need_tables_for:
+        t0 = time.time()
+        tables = TR.build_terrain_tables(v, f, need_tables_for, build_device=device)
+        log(f"terrain tables {tuple(tables.heightmap.shape)} ({time.time() - t0:.1f}s)")
+    return v, f, grid, tables
+
+
+def time_steps(fn, steps, warmup, flush, stream):
+    """fn(i) enqueues one step; returns per-step milliseconds (CUDA events, flush excluded)."""
+    for i in range(warmup):
+        flush()
+        fn(i)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        flush()
+        ev[i][0].record(stream)
+        fn(warmup + i)
+        ev[i][1].record(stream)
+    torch.cuda.synchronize()
+    return np.array([a.elapsed_time(b) for a, b in ev])
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the product path has no CPU fallback); "
+                           "use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from isaac_rover_orbit_b200 import ops, synthetic
+    from isaac_rover_orbit_b200.config import RoverEnvCfg
+    from isaac_rover_orbit_b200.dist import EpisodeStats
+
+    n_scan = SCAN_ENVS_PER_GPU
+    n_step = STEP_ENVS_1GPU if world == 1 else STEP_ENVS_PER_GPU_MULTI
+    v, f, grid, tables = build_world(n_step, dev)
+    vt = torch.from_numpy(v)
+    cfg = RoverEnvCfg(num_envs=n_step)
+    rays = ops.grid_pattern().to(dev)
+    stream = torch.cuda.current_stream(dev)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def flush():
+        flush_buf.fill_(1)
+
+    # ------------------------------------------------------------------ headline: height scan (cfg-2 per GPU)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    poses = [synthetic.make_poses(n_scan, gen, vt, TERRAIN["size_m"], TERRAIN["grid_res"]) for _ in range(POSE_SETS)]
+    poses_d = [(p.to(dev), q.to(dev)) for p, q in poses]
+    out = torch.empty(n_scan, N_RAYS, device=dev)
+
+    def scan_step(i):
+        p, q = poses_d[i % POSE_SETS]
+        ops.height_scan(p, q, rays, grid, out=out, variant=args.variant)
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clocks:
+        ms = time_steps(scan_step, args.steps, args.warmup, flush, stream)
+        # keep the GPU busy long enough for >= a few clock samples
+        t_end = time.time() + 0.3
+        while time.time() < t_end:
+            scan_step(0)
+        torch.cuda.synchronize()
+    total_ms = torch.tensor([ms.sum()], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    rays_total = n_scan * N_RAYS * args.steps * world
+    value = rays_total / (total_ms * 1e-3)
+    t_launch = float(ms.mean()) * 1e-3
+    alg_bytes = 4.0 * n_scan * N_RAYS + 28.0 * n_scan + TERRAIN_BYTES
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / t_launch / 1e9
+    kname = "height_scan_direct_kernel" if args.variant == 0 else "height_scan_staged_kernel"
+
+    # ------------------------------------------------------------------ e2e: host buffers through the public API
+    pin = [(p.pin_memory(), q.pin_memory()) for p, q in poses]
+    host_out = torch.empty(n_scan, N_RAYS).pin_memory()
+    p_d, q_d = torch.empty(n_scan, 3, device=dev), torch.empty(n_scan, 4, device=dev)
+
+    def e2e_step(i):
+        p, q = pin[i % POSE_SETS]
+        p_d.copy_(p, non_blocking=True)
+        q_d.copy_(q, non_blocking=True)
+        ops.height_scan(p_d, q_d, rays, grid, out=out, variant=args.variant)
+        host_out.copy_(out, non_blocking=True)
+
+    e2e_steps = max(min(args.steps, 200), 3)
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+        torch.cuda.synchronize()  # the caller reads the heights of step i before issuing step i+1
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = n_scan * N_RAYS * e2e_steps * world / float(e2e_t.item())
+
+    # ------------------------------------------------------------------ extra: fused non-physics step
+    extra = {}
+    try:
+        buf = ops.MdpBuffers.allocate(n_step, dev)
+        params = ops.mdp_params(cfg)
+        th = ops.TerrainTablesHandle(tables.heightmap, tables.safe_mask, tables.offset_xy, tables.spawn_table,
+                                     tables.resolution, dev)
+        gen2 = torch.Generator().manual_seed(99 + rank)
+        sets = [synthetic.make_step(n_step, gen2, vt, TERRAIN["size_m"], TERRAIN["grid_res"],
+                                    cfg.num_contact_bodies, cfg.target_rounds).to(dev) for _ in range(4)]
+        pc, hc, ep = synthetic.init_commands(n_step, gen2, sets[0].root_pos_w.cpu())
+        buf.pos_cmd_w.copy_(pc)
+        buf.heading_cmd_w.copy_(hc)
+        buf.episode_length_buf.copy_(ep)
+        buf.env_origins.copy_(sets[0].root_pos_w)
+        buf.time_left.fill_(150.0)
+        obs = torch.zeros(n_step, 4 + N_RAYS, device=dev)
+        stats = EpisodeStats(buf, world)
+
+        def full_step(i):
+            s = sets[i % 4]  # the synthetic "physics" hands over root state + contact forces of this step
+            ops.mdp_pre_step(buf, params, s.actions, s.force_matrix_w)
+            ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
+                              s.theta_u, obs)
+            ops.height_scan(s.root_pos_w, s.root_quat_w, rays, grid, out=obs[:, 4:], variant=args.variant)
+            if world > 1:
+                stats.all_reduce_async()
+
+        def mdp_only(i):
+            s = sets[i % 4]
+            ops.mdp_pre_step(buf, params, s.actions, s.force_matrix_w)
+            ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
+                              s.theta_u, obs)
+
+        ksteps = max(min(args.steps, 200), 3)
+        ms_full = time_steps(full_step, ksteps, 3, flush, stream)
+        ms_mdp = time_steps(mdp_only, ksteps, 3, flush, stream)
+        buf.stats.zero_()
+        mdp_only(0)
+        torch.cuda.synchronize()
+        resets_per_step = float(buf.stats[13].item())
+        tf = torch.tensor([ms_full.sum(), ms_mdp.sum()], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        full_bytes = n_step * (414.0 + 4.0 * N_RAYS) + TERRAIN_BYTES
+        extra = {
+            "fused_step": {
+                "workload": f"cfg-{'3' if world == 1 else '5'}: {n_step} envs/GPU, pre_step + post_step + height scan"
+                            + (" + NCCL episode-stat all-reduce" if world > 1 else ""),
+                "env_steps_per_s": n_step * world * ksteps / (float(tf[0]) * 1e-3),
+                "ms_per_step": float(tf[0]) / ksteps,
+                "gpu_launches_per_step": 3,
+                "roofline_frac_hbm": full_bytes / (float(tf[0]) / ksteps * 1e-3) / 1e9 / peak,
+                "resets_in_one_step": resets_per_step,
+            },
+            "mdp_only": {
+                "env_steps_per_s": n_step * world * ksteps / (float(tf[1]) * 1e-3),
+                "ms_per_step": float(tf[1]) / ksteps,
+                "roofline_frac_hbm": n_step * 414.0 / (float(tf[1]) / ksteps * 1e-3) / 1e9 / peak,
+                "note": "two launches over 414 B/env: launch-latency bound at this N (SURVEY.md 8d)",
+            },
+        }
+    except Exception as e:  # the headline number must survive a failure of the extra measurements
+        extra = {"error": f"{type(e).__name__}: {e}"}
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference(v, f, steps=3, warmup=1, n_envs=256)
+
+    if rank == 0:
+        line = {
+            "metric": "height_scan_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg-2 height-scan raycast only: 4096 envs x 961 rays per GPU, synthetic 200 m x "
+                                   "200 m Mars-like terrain, 2,000,000 triangles",
+                       "envs_per_gpu": n_scan, "rays_per_env": N_RAYS, "kernel_variant": args.variant,
+                       "l2": "flushed between timed steps (256 MiB write, outside the timed region)",
+                       "pose_sets": POSE_SETS},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_scan * 28,
+                    "d2h_bytes_per_step": n_scan * N_RAYS * 4, "steps": e2e_steps,
+                    "how": "pinned host poses -> H2D -> rover_height_scan -> D2H heights, synchronised per step"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": recorded_traffic(kname),
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_us": t_launch * 1e6},
+            "cpu_baseline": cpu,
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_reference(v, f, steps, warmup, n_envs):
+    """The reference's CPU path for the height scan, restated (oracle port): torch pose->ray transform
+    (ORBIT RayCaster) + BVH/watertight closest hit (warp mesh_query_ray) + height_scan_rover, all host threads."""
+    from isaac_rover_orbit_b200 import synthetic
+    from oracle import raycast as oracle_raycast
+    from oracle import step as OS
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t0 = time.time()
+    mesh = oracle_raycast.Mesh(v, f)
+    log(f"oracle BVH over {len(f)} triangles ({time.time() - t0:.1f}s)")
+    gen = torch.Generator().manual_seed(4321)
+    vt = torch.from_numpy(v)
+    sets = [synthetic.make_poses(n_envs, gen, vt, TERRAIN["size_m"], TERRAIN["grid_res"]) for _ in range(4)]
+    for i in range(warmup):
+        OS.height_scan(*sets[i % 4], mesh)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        OS.height_scan(*sets[i % 4], mesh)
+    dt = time.perf_counter() - t0
+    return {"value": n_envs * N_RAYS * steps / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} steps x {n_envs} envs x {N_RAYS} rays on the same 2,000,000-triangle terrain "
+                      f"(oracle/: torch ray transform + C BVH raycast with OpenMP)",
+            "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from isaac_rover_orbit_b200 import terrain as TR
+
+    v, f = TR.make_synthetic_terrain(**TERRAIN)
+    n_envs = 256
+    cpu = cpu_reference(v, f, steps=max(args.steps, 1), warmup=max(args.warmup, 1), n_envs=n_envs)
+    line = {
+        "impl": "reference", "metric": "height_scan_rays_per_s", "value": cpu["value"], "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg-2 height-scan raycast only: 4096 envs x 961 rays per GPU, synthetic 200 m x "
+                               "200 m Mars-like terrain, 2,000,000 triangles",
+                   "sample": f"each step = {n_envs} envs x {N_RAYS} rays of that workload (bounded CPU sample)"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("ROVER_SCAN_VARIANT", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,169 @@
+/* rover_b200.h -- C ABI of the B200-native non-physics MDP hot path of AAURoverEnv-v0.
+ *
+ * The reference (abmoRobotics/isaac_rover_orbit) is pure Python on top of ORBIT / warp / skrl and has NO
+ * FFI of its own; the boundary it offers is ORBIT's manager-term plugin API.  This
+ * library sits UNDER those Python callables: each entry point below names the reference interface
+ * (file:line under the reference root) whose per-step work it replaces.  The Python mirror of the
+ * manager-term API that calls these lives in isaac_rover_orbit_b200/ (ctypes).
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory (cudaMalloc / torch CUDA tensor .data_ptr()) unless it says "host";
+ *   - tensors are dense row-major fp32 unless stated; quaternions are (w, x, y, z);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it, nothing synchronises;
+ *   - every function returns 0 on success, non-zero on error; rover_last_error() gives the message
+ *     (thread-local).  No function falls back to a CPU path.
+ */
+#ifndef ROVER_B200_H
+#define ROVER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ROVER_B200_ABI_VERSION 1
+#define ROVER_MAX_LEVELS 12
+#define ROVER_NUM_REWARD_TERMS 7
+#define ROVER_NUM_TERMINATION_TERMS 4
+#define ROVER_STATS_LEN 16
+
+int rover_abi_version(void);
+const char* rover_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Height scan.  Replaces ORBIT RayCaster._update_buffers_impl -> raycast_mesh -> warp mesh_query_ray
+ * (third-party; wired at rover_envs/envs/navigation/rover_env_cfg.py:78-86) fused with
+ * height_scan_rover (rover_envs/envs/navigation/mdp/observations.py:35-45).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct RoverScanLevel {
+    float ox, oy;        /* grid origin of this level                                   */
+    float cell;          /* cell size (level-0 size * 2^level)                           */
+    float inv_cell;      /* 1 / cell, the value the builder used                         */
+    int32_t ncx, ncy;    /* grid extent                                                  */
+    int32_t start_offset;/* offset of this level's (ncx*ncy+1) entries inside cell_start */
+    int32_t reserved;
+} RoverScanLevel;
+
+typedef struct RoverScanGrid {
+    int32_t n_levels;
+    int32_t span;                 /* a ray in cell (i,j) tests homes (i-span..i, j-span..j)  */
+    RoverScanLevel level[ROVER_MAX_LEVELS];
+    const int32_t* cell_start;    /* record index ranges per home cell, all levels concatenated */
+    const float* records;         /* n_records x 12 floats, 16-byte aligned                   */
+    int32_t n_records;
+    int32_t reserved;
+} RoverScanGrid;
+
+/* pos_w [n_envs,3], quat_w [n_envs,4]: sensor (body) pose, sensor.data.pos_w / quat_w.
+ * ray_starts_local [n_rays,3]: ORBIT RayCaster.ray_starts (grid_pattern + offset.pos), env frame.
+ * out_heights [n_envs,n_rays]: pos_w.z - hit.z - base_offset; a miss (no hit with 0 <= t < max_dist) is -inf.
+ * out_hits_w [n_envs,n_rays,3] (optional, may be NULL): sensor.data.ray_hits_w, +inf on a miss.
+ * variant: 0 = direct (global-memory) kernel, 1 = shared-memory staged kernel. */
+int rover_height_scan(const float* pos_w, const float* quat_w, int32_t n_envs, const float* ray_starts_local,
+                      int32_t n_rays, const RoverScanGrid* grid /* host */, float max_distance, float base_offset,
+                      float* out_heights, int32_t out_stride, float* out_hits_w, int32_t variant, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused MDP step.  Replaces, in one launch:
+ *   AckermannAction2.process_actions/apply_actions/ackermann  rover_envs/mdp/actions/ackermann_actions.py:226-322
+ *   ORBIT ActionManager.process_action (prev_action <- action <- new)
+ *   episode_length_buf += 1                                    entrypoints/rover_env.py:79
+ *   time_out / is_success / far_from_target / collision        mdp/terminations.py:14-64 (+ ORBIT mdp.time_out)
+ *   the seven reward terms, weight * dt, episodic sums         mdp/rewards.py:14-137 (+ ORBIT RewardManager.compute)
+ * It reads the PREVIOUS step's pos_cmd_b, as the reference's step ordering does (rover_env.py:82-86).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct RoverMdpParams {
+    /* actions_cfg.py:20, robots/aau_rover/env_cfg.py:21-31 */
+    float scale_lin, scale_ang, offset_lin, offset_ang;
+    float wheelbase_length, middle_wheel_distance, rear_and_front_wheel_distance, wheel_radius;
+    float min_radius;            /* (float)(middle_wheel_distance * 0.8) evaluated in double, ackermann_actions.py:264 */
+    /* rover_env_cfg.py:128-163 */
+    float weight[ROVER_NUM_REWARD_TERMS];
+    float reached_threshold, far_threshold;
+    float step_dt;               /* sim.dt * decimation (rover_env_cfg.py:269-270) */
+    int32_t max_episode_length;  /* ceil(episode_length_s / step_dt) */
+    /* rover_env_cfg.py:104-112 */
+    float obs_distance_scale, obs_heading_scale;
+    /* terrain_importer.py:132, rover_env_cfg.py:191-200, randomizations.py:12 */
+    float target_distance, resampling_time, heading_lo, heading_hi, spawn_z_offset;
+    int32_t num_bodies;          /* contact-sensor bodies B: force_matrix_w is [n_envs, B, 1, 3] */
+} RoverMdpParams;
+
+typedef struct RoverMdpState {     /* persistent manager state, mutated in place */
+    float* action;                 /* [N,2] action_manager.action                        */
+    float* prev_action;            /* [N,2] action_manager.prev_action                   */
+    float* pos_cmd_w;              /* [N,3] TerrainBasedPositionCommand.pos_command_w    */
+    float* heading_cmd_w;          /* [N]                                                */
+    float* pos_cmd_b;              /* [N,3] .command                                     */
+    float* heading_cmd_b;          /* [N]                                                */
+    float* time_left;              /* [N]   CommandTerm.time_left                        */
+    int64_t* command_counter;      /* [N]                                                */
+    int64_t* episode_length_buf;   /* [N]   env.episode_length_buf (int64 like ORBIT)    */
+    float* episode_sums;           /* [N,7] RewardManager._episode_sums                  */
+    float* env_origins;            /* [N,3] terrain.env_origins                          */
+    float* err_pos;                /* [N]   metrics["error_pos"]                         */
+    float* err_heading;            /* [N]   metrics["error_heading"]                     */
+} RoverMdpState;
+
+typedef struct RoverMdpOut {
+    float* processed_actions;      /* [N,2] */
+    float* joint_pos;              /* [N,4] steering targets  [FL,RL,RR,FR] */
+    float* joint_vel;              /* [N,6] drive targets     [ML,FL,RL,RR,MR,FR] */
+    float* reward;                 /* [N]   */
+    float* term_rewards;           /* [N,7] weight*value*dt per term */
+    uint8_t* terminated;           /* [N]   */
+    uint8_t* truncated;            /* [N]   */
+    uint8_t* term_flags;           /* [N,4] time_limit,is_success,far_from_target,collision */
+    uint8_t* reset_flags;          /* [N]   terminated | truncated */
+    int32_t* block_reset_counts;   /* [ceil(N/ROVER_MDP_BLOCK)] resets per thread block (rank scan input) */
+} RoverMdpOut;
+
+#define ROVER_MDP_BLOCK 256
+
+/* new_actions [N,2]; force_matrix_w [N,B,1,3] (contact_sensor.data.force_matrix_w). */
+int rover_mdp_pre_step(const float* new_actions, const float* force_matrix_w, int32_t n_envs,
+                       const RoverMdpParams* params /* host */, const RoverMdpState* state /* host struct */,
+                       const RoverMdpOut* out /* host struct */, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Reset + command update + observation head.  Replaces, in one launch (rows a-4..a-6, a-22..a-28):
+ *   reset_root_state_rover                        mdp/randomizations.py:12-39
+ *   ORBIT manager .reset(ids) combine rules       (action/reward/command/termination), episode stats
+ *   TerrainBasedPositionCommand._resample_command utils/terrains/terrain_importer.py:74-95
+ *   RoverTerrainImporter.sample_new_targets       :134-175 (rejection loop, bounded to n_rounds)
+ *   TerrainManager.check_if_target_is_valid       utils/terrains/terrain_utils.py:202-223
+ *   HeightmapManager.get_height_at                :62-84
+ *   CommandTerm.compute: _update_metrics, time_left, _update_command  terrain_importer.py:97-106
+ *   last_action / distance / angle observations   mdp/observations.py:15-32, rover_env_cfg.py:103-112
+ * Random variates are inputs so that oracle and kernel consume identical numbers:
+ *   spawn_perm[j] (int64) = spawn row of the j-th reset env (ascending env id);
+ *   yaw_u[N], heading_u[N], theta_u[N, n_rounds] = uniform [0,1) variates indexed by env id.
+ * root_pos_w / root_quat_w are updated in place for reset envs (write_root_pose_to_sim).
+ * stats [ROVER_STATS_LEN] f32 is ACCUMULATED (atomicAdd): 7 reward sums, 4 termination counts, err_pos sum,
+ * err_heading sum, number of resets, rounds-exhausted count, time-resample count.  The reduction is
+ * deterministic (per-block partials in `scratch`, summed in block order by the last block to finish).
+ * obs [N, obs_stride]: columns 0..3 are written (actions(2), distance*0.11, angle/pi).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct RoverTerrainTables {
+    const float* heightmap;       /* [H,W] */
+    const uint8_t* safe_mask;     /* [H,W] 1 = rock/unsafe */
+    int32_t height, width;        /* H, W */
+    float offset_x, offset_y;     /* (min_x, min_y) added (sic) to xy/res, terrain_utils.py:75 */
+    float resolution;             /* 0.05 */
+    const float* spawn_table;     /* [n_spawns,3] */
+    int32_t n_spawns;
+    int32_t reserved;
+} RoverTerrainTables;
+
+int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_t n_envs, const RoverMdpParams* params,
+                        const RoverMdpState* state, const RoverMdpOut* out, const RoverTerrainTables* tables,
+                        const int64_t* spawn_perm, const float* yaw_u, const float* heading_u, const float* theta_u,
+                        int32_t n_rounds, int64_t* out_spawn_index /* [N], -1 if not reset */, float* stats,
+                        float* scratch /* [ceil(N/ROVER_MDP_BLOCK)*ROVER_STATS_LEN + 1] f32, zeroed once */,
+                        float* obs, int32_t obs_stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROVER_B200_H */

@@ -1,0 +1,130 @@
+"""ctypes binding of ``librover_b200.so`` (the C ABI declared in ``include/rover_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no fallback: if the
+library or a symbol is missing, or a call returns non-zero, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librover_b200.so")
+
+MAX_LEVELS = 12
+NUM_REWARD_TERMS = 7
+NUM_TERMINATION_TERMS = 4
+STATS_LEN = 16
+MDP_BLOCK = 256
+ABI_VERSION = 1
+
+SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_mdp_pre_step", "rover_mdp_post_step")
+
+
+class ScanLevel(C.Structure):
+    _fields_ = [("ox", C.c_float), ("oy", C.c_float), ("cell", C.c_float), ("inv_cell", C.c_float),
+                ("ncx", C.c_int32), ("ncy", C.c_int32), ("start_offset", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ScanGrid(C.Structure):
+    _fields_ = [("n_levels", C.c_int32), ("span", C.c_int32), ("level", ScanLevel * MAX_LEVELS),
+                ("cell_start", C.c_void_p), ("records", C.c_void_p), ("n_records", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class MdpParams(C.Structure):
+    _fields_ = [("scale_lin", C.c_float), ("scale_ang", C.c_float), ("offset_lin", C.c_float),
+                ("offset_ang", C.c_float), ("wheelbase_length", C.c_float), ("middle_wheel_distance", C.c_float),
+                ("rear_and_front_wheel_distance", C.c_float), ("wheel_radius", C.c_float), ("min_radius", C.c_float),
+                ("weight", C.c_float * NUM_REWARD_TERMS), ("reached_threshold", C.c_float),
+                ("far_threshold", C.c_float), ("step_dt", C.c_float), ("max_episode_length", C.c_int32),
+                ("obs_distance_scale", C.c_float), ("obs_heading_scale", C.c_float), ("target_distance", C.c_float),
+                ("resampling_time", C.c_float), ("heading_lo", C.c_float), ("heading_hi", C.c_float),
+                ("spawn_z_offset", C.c_float), ("num_bodies", C.c_int32)]
+
+
+_STATE_FIELDS = ("action", "prev_action", "pos_cmd_w", "heading_cmd_w", "pos_cmd_b", "heading_cmd_b", "time_left",
+                 "command_counter", "episode_length_buf", "episode_sums", "env_origins", "err_pos", "err_heading")
+_OUT_FIELDS = ("processed_actions", "joint_pos", "joint_vel", "reward", "term_rewards", "terminated", "truncated",
+               "term_flags", "reset_flags", "block_reset_counts")
+
+
+class MdpState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _STATE_FIELDS]
+
+
+class MdpOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _OUT_FIELDS]
+
+
+class TerrainTables(C.Structure):
+    _fields_ = [("heightmap", C.c_void_p), ("safe_mask", C.c_void_p), ("height", C.c_int32), ("width", C.c_int32),
+                ("offset_x", C.c_float), ("offset_y", C.c_float), ("resolution", C.c_float),
+                ("spawn_table", C.c_void_p), ("n_spawns", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PolicyWeights(C.Structure):
+    _fields_ = [("w", C.c_void_p * 6), ("b", C.c_void_p * 6), ("in_dim", C.c_int32 * 6), ("out_dim", C.c_int32 * 6)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library once; verify the ABI version and that every declared symbol is exported."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python __graft_entry__.py` (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    missing = [s for s in SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise RuntimeError(f"librover_b200.so does not export {missing}")
+    lib.rover_abi_version.restype = C.c_int
+    lib.rover_last_error.restype = C.c_char_p
+    if lib.rover_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"librover_b200.so ABI {lib.rover_abi_version()} != expected {ABI_VERSION}")
+    vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+    lib.rover_height_scan.restype = C.c_int
+    lib.rover_height_scan.argtypes = [vp, vp, i32, vp, i32, C.POINTER(ScanGrid), f32, f32, vp, i32, vp, i32, vp]
+    lib.rover_mdp_pre_step.restype = C.c_int
+    lib.rover_mdp_pre_step.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut), vp]
+    lib.rover_mdp_post_step.restype = C.c_int
+    lib.rover_mdp_post_step.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
+                                        C.POINTER(TerrainTables), vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError("rover_b200: " + load().rover_last_error().decode(errors="replace"))
+
+
+def require_cuda(*tensors: torch.Tensor) -> torch.device:
+    """Every tensor must live on the same CUDA device and be contiguous -- no silent copies, no CPU path."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("rover_b200 kernels need CUDA tensors; there is no CPU fallback")
+        if not t.is_contiguous():
+            raise RuntimeError("rover_b200 kernels need contiguous tensors")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {t.device} vs {dev}")
+    return dev
+
+
+def ptr(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

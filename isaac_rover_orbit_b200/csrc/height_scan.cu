@@ -1,0 +1,129 @@
+// Height-scan raycaster for vertical rays over the multi-level home grid (see scan_grid.py).
+//
+// Replaces ORBIT RayCaster._update_buffers_impl -> raycast_mesh -> warp mesh_query_ray (third-party, wired at
+// rover_envs/envs/navigation/rover_env_cfg.py:78-86) fused with height_scan_rover
+// (rover_envs/envs/navigation/mdp/observations.py:35-45).  One CTA per environment:
+//   * the yaw-only sensor frame is computed once per CTA in the reference's fp32 operation order
+//     (ORBIT yaw_quat / quat_apply) with contraction disabled, so ray origins match the
+//     reference bit for bit up to libm differences in atan2f/sinf/cosf;
+//   * every thread walks its rays through the home grid: for each level, the (span+1)^2 home cells whose
+//     triangles can cover the ray's cell; a record test is 8 FMAs (3 edge functions + plane);
+//   * closest hit along (0,0,-1) == highest z with 0 <= Z - z < max_distance;
+//   * heights are written coalesced (consecutive threads = consecutive rays of one env).
+#include "scan_common.cuh"
+
+namespace rover {
+
+// highest covered z below the ray origin, or -inf
+__device__ __forceinline__ float cast_down(const ScanGridDev& g, float X, float Y, float Z, float max_d) {
+    float best = -INFINITY;
+    for (int l = 0; l < g.n_levels; ++l) {
+        const ScanLevelDev& L = g.level[l];
+        const int i = cell_of(X, L.ox, L.inv_cell);
+        const int j = cell_of(Y, L.oy, L.inv_cell);
+        const int j0 = max(j - g.span, 0), j1 = min(j, L.ncy - 1);
+        const int i0 = max(i - g.span, 0), i1 = min(i, L.ncx - 1);
+        for (int jj = j0; jj <= j1; ++jj) {
+            const float ly = __fsub_rn(Y, __fadd_rn(L.oy, __fmul_rn((float)jj, L.cell)));
+            const int* __restrict__ row = g.cell_start + L.start_offset + jj * L.ncx;
+            for (int ii = i0; ii <= i1; ++ii) {
+                const float lx = __fsub_rn(X, __fadd_rn(L.ox, __fmul_rn((float)ii, L.cell)));
+                const int b = __ldg(row + ii), e = __ldg(row + ii + 1);
+                for (int r = b; r < e; ++r) {
+                    const float4 r0 = __ldg(g.rec + 3 * r);
+                    const float4 r1 = __ldg(g.rec + 3 * r + 1);
+                    const float4 r2 = __ldg(g.rec + 3 * r + 2);
+                    test_record(r0, r1, r2, lx, ly, Z, max_d, best);
+                }
+            }
+        }
+    }
+    return best;
+}
+
+constexpr int kScanThreads = 256;
+
+__global__ void __launch_bounds__(kScanThreads)
+height_scan_direct_kernel(const float* __restrict__ pos_w, const float* __restrict__ quat_w,
+                          const float* __restrict__ ray_local, int n_rays, const __grid_constant__ ScanGridDev g,
+                          float max_d, float base_offset, float* __restrict__ out, int out_stride,
+                          float* __restrict__ hits) {
+    const int env = blockIdx.x;
+    __shared__ SensorFrame frame_s;
+    if (threadIdx.x == 0) frame_s = make_frame(pos_w + 3 * (size_t)env, quat_w + 4 * (size_t)env);
+    __syncthreads();
+    const SensorFrame f = frame_s;
+    for (int r = threadIdx.x; r < n_rays; r += kScanThreads) {
+        const float vx = __ldg(ray_local + 3 * r), vy = __ldg(ray_local + 3 * r + 1), vz = __ldg(ray_local + 3 * r + 2);
+        float X, Y, Z;
+        ray_origin(f, vx, vy, vz, X, Y, Z);
+        const float zhit = cast_down(g, X, Y, Z, max_d);
+        float h = -INFINITY, hx = INFINITY, hy = INFINITY, hz = INFINITY;
+        if (zhit != -INFINITY) {
+            // reference rounding chain: t -> hit.z = Z + t*(-1) -> (pos.z - hit.z) - offset
+            const float t = __fsub_rn(Z, zhit);
+            hz = __fsub_rn(Z, t);
+            hx = X;
+            hy = Y;
+            h = __fsub_rn(__fsub_rn(f.pz, hz), base_offset);
+        }
+        out[(size_t)env * out_stride + r] = h;
+        if (hits) {
+            float* p = hits + ((size_t)env * n_rays + r) * 3;
+            p[0] = hx;
+            p[1] = hy;
+            p[2] = hz;
+        }
+    }
+}
+
+static int make_dev_grid(const RoverScanGrid* grid, ScanGridDev& g) {
+    ROVER_CHECK(grid != nullptr, "rover_height_scan: grid is NULL");
+    ROVER_CHECK(grid->n_levels >= 1 && grid->n_levels <= ROVER_MAX_LEVELS, "rover_height_scan: bad n_levels %d",
+                grid->n_levels);
+    ROVER_CHECK(grid->span >= 0 && grid->span <= 3, "rover_height_scan: bad span %d", grid->span);
+    ROVER_CHECK(grid->cell_start != nullptr, "rover_height_scan: cell_start is NULL");
+    ROVER_CHECK(grid->records != nullptr || grid->n_records == 0, "rover_height_scan: records is NULL");
+    ROVER_CHECK((reinterpret_cast<uintptr_t>(grid->records) & 15) == 0, "rover_height_scan: records not 16B aligned");
+    g.n_levels = grid->n_levels;
+    g.span = grid->span;
+    for (int l = 0; l < grid->n_levels; ++l) {
+        const RoverScanLevel& s = grid->level[l];
+        ROVER_CHECK(s.ncx > 0 && s.ncy > 0 && s.cell > 0.f, "rover_height_scan: bad level %d", l);
+        g.level[l] = {s.ox, s.oy, s.cell, s.inv_cell, s.ncx, s.ncy, s.start_offset, 0};
+    }
+    g.cell_start = grid->cell_start;
+    g.rec = reinterpret_cast<const float4*>(grid->records);
+    return 0;
+}
+
+int launch_height_scan_staged(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local, int n_rays,
+                              const ScanGridDev& g, float max_d, float base_offset, float* out, int out_stride,
+                              float* hits, cudaStream_t stream);  // height_scan_staged.cu
+
+}  // namespace rover
+
+extern "C" int rover_height_scan(const float* pos_w, const float* quat_w, int32_t n_envs,
+                                 const float* ray_starts_local, int32_t n_rays, const RoverScanGrid* grid,
+                                 float max_distance, float base_offset, float* out_heights, int32_t out_stride,
+                                 float* out_hits_w, int32_t variant, void* stream) {
+    using namespace rover;
+    ROVER_CHECK(n_envs >= 0 && n_rays >= 0, "rover_height_scan: negative sizes");
+    if (n_envs == 0 || n_rays == 0) return 0;
+    ROVER_CHECK(pos_w && quat_w && ray_starts_local && out_heights, "rover_height_scan: NULL tensor");
+    ROVER_CHECK(out_stride >= n_rays, "rover_height_scan: out_stride %d < n_rays %d", out_stride, n_rays);
+    ScanGridDev g;
+    if (int rc = make_dev_grid(grid, g)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (variant == 0) {
+        height_scan_direct_kernel<<<n_envs, kScanThreads, 0, s>>>(pos_w, quat_w, ray_starts_local, n_rays, g,
+                                                                   max_distance, base_offset, out_heights, out_stride,
+                                                                   out_hits_w);
+        return check_launch("height_scan_direct_kernel");
+    }
+    if (variant == 1) {
+        return launch_height_scan_staged(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, max_distance,
+                                         base_offset, out_heights, out_stride, out_hits_w, s);
+    }
+    return fail("rover_height_scan: unknown variant %d", variant);
+}

@@ -1,0 +1,449 @@
+// Fused non-physics MDP step of AAURoverEnv-v0: two launches around the (external) physics state.
+//
+//   mdp_pre_step_kernel   one thread per env: action manager shift, AckermannAction2 kinematics, counters,
+//                         the 4 terminations, the 7 weighted rewards + episodic sums, reset flags.
+//   mdp_post_step_kernel  one thread per env: rank of each reset env (block prefix + warp scan), spawn/yaw
+//                         reset, manager resets + episode statistics, bounded target rejection sampling on the
+//                         valid-location mask, heightmap lookup, command metrics / update, observation head.
+//
+// Reference lines restated (relative to the reference root):
+//   rover_envs/mdp/actions/ackermann_actions.py:226-322        rover_envs/envs/navigation/mdp/rewards.py:14-137
+//   rover_envs/envs/navigation/mdp/terminations.py:14-64        .../mdp/observations.py:15-32
+//   .../mdp/randomizations.py:12-39                             .../utils/terrains/terrain_importer.py:74-175
+//   .../utils/terrains/terrain_utils.py:62-84, 202-223          .../entrypoints/rover_env.py:61-102 (ordering)
+// plus the ORBIT manager combine rules and math helpers of SURVEY.md Appendix A.1/A.2.
+// fp32 arithmetic follows the reference's operation order; contraction is disabled (__f*_rn) wherever a
+// value is compared against a threshold or truncated to an index.
+#include "common.cuh"
+
+namespace rover {
+
+__device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+// torch.remainder(a, 2pi) followed by the (a > pi) fold  (ORBIT wrap_to_pi, A.1)
+__device__ __forceinline__ float wrap_to_pi(float a) {
+    const float two_pi = 6.2831855f, pi = 3.1415927f;
+    float m = fmodf(a, two_pi);
+    if (m != 0.f && m < 0.f) m = __fadd_rn(m, two_pi);
+    if (m > pi) m = __fsub_rn(m, two_pi);
+    return m;
+}
+
+struct YawQuat {
+    float cw, sz;
+};
+
+// ORBIT yaw_quat (A.1)
+__device__ __forceinline__ YawQuat yaw_quat(float w, float x, float y, float z) {
+    const float siny = __fmul_rn(2.f, __fadd_rn(__fmul_rn(w, z), __fmul_rn(x, y)));
+    const float cosy = __fsub_rn(1.f, __fmul_rn(2.f, __fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z))));
+    const float half = __fdiv_rn(atan2f(siny, cosy), 2.f);
+    const float s = sinf(half), c = cosf(half);
+    const float n = fmaxf(sqrtf(__fadd_rn(__fmul_rn(c, c), __fmul_rn(s, s))), 1e-9f);
+    return {__fdiv_rn(c, n), __fdiv_rn(s, n)};
+}
+
+// ORBIT ArticulationData.heading_w (A.1): atan2 of the rotated x axis
+__device__ __forceinline__ float heading_w(float w, float x, float y, float z) {
+    const float ty = __fmul_rn(z, 2.f), tz = __fmul_rn(-y, 2.f);  // t = 2 * (xyz x (1,0,0)) = (0, 2z, -2y)
+    const float cx = __fsub_rn(__fmul_rn(y, tz), __fmul_rn(z, ty));
+    const float cy = __fsub_rn(0.f, __fmul_rn(x, tz));  // z*t.x - x*t.z with t.x = 0
+    const float fx = __fadd_rn(1.f, cx);
+    const float fy = __fadd_rn(__fmul_rn(w, ty), cy);
+    return atan2f(fy, fx);
+}
+
+__device__ __forceinline__ float norm2(float x, float y) {
+    return sqrtf(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
+}
+
+// contact_sensor force_matrix_w [B,1,3] of one env: L2 norm over bodies per axis, summed over axes, > 1
+__device__ __forceinline__ bool collision_active(const float* __restrict__ f, int num_bodies) {
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int b = 0; b < num_bodies; ++b) {
+        const float x = __ldg(f + 3 * b), y = __ldg(f + 3 * b + 1), z = __ldg(f + 3 * b + 2);
+        sx = __fadd_rn(sx, __fmul_rn(x, x));
+        sy = __fadd_rn(sy, __fmul_rn(y, y));
+        sz = __fadd_rn(sz, __fmul_rn(z, z));
+    }
+    return __fadd_rn(__fadd_rn(sqrtf(sx), sqrtf(sy)), sqrtf(sz)) > 1.f;
+}
+
+__global__ void __launch_bounds__(ROVER_MDP_BLOCK)
+mdp_pre_step_kernel(const float* __restrict__ new_actions, const float* __restrict__ force, int n,
+                    const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
+                    const __grid_constant__ RoverMdpOut O) {
+    const int i = blockIdx.x * ROVER_MDP_BLOCK + threadIdx.x;
+    bool reset = false;
+    if (i < n) {
+        // ---- ActionManager.process_action: prev <- action <- new; term.process_actions (ackermann_actions.py:226-229)
+        const float2 a_old = reinterpret_cast<const float2*>(S.action)[i];
+        const float2 a = reinterpret_cast<const float2*>(new_actions)[i];
+        reinterpret_cast<float2*>(S.prev_action)[i] = a_old;
+        reinterpret_cast<float2*>(S.action)[i] = a;
+        const float lin_p = __fadd_rn(__fmul_rn(a.x, P.scale_lin), P.offset_lin);
+        const float ang_p = __fadd_rn(__fmul_rn(a.y, P.scale_ang), P.offset_ang);
+        reinterpret_cast<float2*>(O.processed_actions)[i] = make_float2(lin_p, ang_p);
+
+        // ---- AckermannAction2.ackermann (ackermann_actions.py:238-322)
+        {
+            float dir = sgnf(lin_p);
+            const float turn = sgnf(ang_p);
+            if (dir == 0.f) dir = 1.f;                                                  // :255
+            const float v = fabsf(lin_p), w = fabsf(ang_p);
+            const bool moving = (w != 0.f) || (v != 0.f);                               // :262
+            float R = moving ? __fdiv_rn(v, w) : INFINITY;                              // :265-266 (x/0 = inf)
+            const float r_min = P.min_radius;                                           // :264
+            if (R < r_min) R = r_min;                                                   // :267
+            const float half_mw = P.middle_wheel_distance / 2.f, half_fr = P.rear_and_front_wheel_distance / 2.f;
+            const float r_ml = __fsub_rn(R, half_mw), r_mr = __fadd_rn(R, half_mw);     // :271-272
+            const float r_l = __fsub_rn(R, half_fr), r_r = __fadd_rn(R, half_fr);       // :273-276
+            const bool point = R < P.middle_wheel_distance;                             // :278
+            const float spin = __fmul_rn(__fadd_rn(v, 1.f), turn);
+            const float v_l = point ? -spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_l, w), dir);
+            const float v_r = point ? spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_r, w), dir);
+            const float v_ml = point ? -spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_ml, w), dir);
+            const float v_mr = point ? spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_mr, w), dir);
+            const float ack = __fmul_rn(atan2f(P.wheelbase_length, r_l), turn);         // :305 (FL radius for all)
+            const float q = 0.78539816339744830962f;
+            float* jv = O.joint_vel + 6 * (size_t)i;                                    // [ML,FL,RL,RR,MR,FR] :316
+            jv[0] = __fdiv_rn(v_ml, P.wheel_radius);
+            jv[1] = __fdiv_rn(v_l, P.wheel_radius);
+            jv[2] = __fdiv_rn(v_l, P.wheel_radius);
+            jv[3] = __fdiv_rn(v_r, P.wheel_radius);
+            jv[4] = __fdiv_rn(v_mr, P.wheel_radius);
+            jv[5] = __fdiv_rn(v_r, P.wheel_radius);
+            reinterpret_cast<float4*>(O.joint_pos)[i] =                                 // [FL,RL,RR,FR] :317
+                make_float4(point ? -q : ack, point ? q : ack, point ? -q : ack, point ? q : ack);
+        }
+
+        // ---- counters (rover_env.py:79)
+        const long long ep = S.episode_length_buf[i] + 1;
+        S.episode_length_buf[i] = ep;
+
+        // ---- shared quantities of the PREVIOUS command (rover_env.py:82-86 run before the command update)
+        const float bx = S.pos_cmd_b[3 * (size_t)i], by = S.pos_cmd_b[3 * (size_t)i + 1];
+        const float d = norm2(bx, by);
+        const float ang = atan2f(by, bx);
+        const bool coll = collision_active(force + (size_t)i * P.num_bodies * 3, P.num_bodies);
+        const float max_len = (float)P.max_episode_length;
+
+        // ---- terminations (terminations.py:14-64, ORBIT mdp.time_out)
+        const bool t_out = ep >= (long long)P.max_episode_length;
+        const bool t_succ = d < P.reached_threshold;
+        const bool t_far = d > P.far_threshold;
+        const bool terminated = t_succ || t_far || coll;
+        reset = t_out || terminated;
+        O.terminated[i] = terminated;
+        O.truncated[i] = t_out;
+        reinterpret_cast<uchar4*>(O.term_flags)[i] = make_uchar4(t_out, t_succ, t_far, coll);
+        O.reset_flags[i] = reset;
+
+        // ---- rewards (rewards.py:14-137), RewardManager: value * weight * dt, summed in declaration order
+        float val[ROVER_NUM_REWARD_TERMS];
+        val[0] = __fdiv_rn(__fdiv_rn(1.f, __fadd_rn(1.f, __fmul_rn(__fmul_rn(0.11f, d), d))), max_len);
+        val[1] = t_succ ? __fdiv_rn((float)((long long)P.max_episode_length - ep), max_len) : 0.f;
+        {
+            const float d_lin = __fmul_rn(__fsub_rn(a.y, a_old.y), 3.f);
+            const float d_ang = __fmul_rn(__fsub_rn(a.x, a_old.x), 3.f);
+            float p_ang = (d_ang > 0.05f) ? __fmul_rn(d_ang, d_ang) : 0.f;
+            float p_lin = (d_lin > 0.05f) ? __fmul_rn(d_lin, d_lin) : 0.f;
+            p_ang = __fmul_rn(p_ang, p_ang);
+            p_lin = __fmul_rn(p_lin, p_lin);
+            val[2] = __fdiv_rn(__fadd_rn(p_ang, p_lin), max_len);
+        }
+        val[3] = (fabsf(ang) > 2.f) ? __fdiv_rn(fabsf(ang), max_len) : 0.f;
+        val[4] = (a.x < 0.f) ? (float)(1.0 / (double)P.max_episode_length) : 0.f;
+        val[5] = coll ? 1.f : 0.f;
+        val[6] = t_far ? 1.f : 0.f;
+        float total = 0.f;
+        float* sums = S.episode_sums + ROVER_NUM_REWARD_TERMS * (size_t)i;
+        float* tr = O.term_rewards + ROVER_NUM_REWARD_TERMS * (size_t)i;
+#pragma unroll
+        for (int k = 0; k < ROVER_NUM_REWARD_TERMS; ++k) {
+            const float c = __fmul_rn(__fmul_rn(val[k], P.weight[k]), P.step_dt);
+            total = __fadd_rn(total, c);
+            sums[k] = __fadd_rn(sums[k], c);
+            tr[k] = c;
+        }
+        O.reward[i] = total;
+    }
+    const int cnt = __syncthreads_count(reset);
+    if (threadIdx.x == 0) O.block_reset_counts[blockIdx.x] = cnt;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+
+struct Tables {
+    const float* __restrict__ heightmap;
+    const uint8_t* __restrict__ safe_mask;
+    int H, W;
+    float offx, offy, res;
+    const float* __restrict__ spawn;
+    int n_spawns;
+};
+
+// terrain_utils.py:75-81 / :211-218: cell = trunc(xy / res + (min_x, min_y)), clamped (offset ADDED, sic)
+__device__ __forceinline__ void terrain_cell(const Tables& T, float x, float y, int& col, int& row) {
+    const float sx = __fadd_rn(__fdiv_rn(x, T.res), T.offx);
+    const float sy = __fadd_rn(__fdiv_rn(y, T.res), T.offy);
+    const long long cx = (long long)fminf(fmaxf(sx, -1.0e18f), 1.0e18f);  // .long(): truncation toward zero
+    const long long cy = (long long)fminf(fmaxf(sy, -1.0e18f), 1.0e18f);
+    col = (int)min(max(cx, 0LL), (long long)(T.W - 1));
+    row = (int)min(max(cy, 0LL), (long long)(T.H - 1));
+}
+
+// CommandTerm._resample + _resample_command + sample_new_targets (terrain_importer.py:74-95, 134-175)
+__device__ __forceinline__ bool resample_command(int i, const RoverMdpParams& P, const RoverMdpState& S, const Tables& T,
+                                                 float ox, float oy, const float* __restrict__ theta_u, int n_rounds,
+                                                 float heading_u, float& cx, float& cy, float& cz, float& chead) {
+    const float pi_f = 3.1415927f;  // torch.pi as fp32; the reference computes rand * 2 * pi left to right
+    float x = 0.f, y = 0.f;
+    int col = 0, row = 0;
+    bool bad = true;
+    for (int r = 0; r < n_rounds && bad; ++r) {
+        const float th = __fmul_rn(__fmul_rn(__ldg(theta_u + (size_t)i * n_rounds + r), 2.f), pi_f);  // :169
+        x = __fadd_rn(__fmul_rn(cosf(th), P.target_distance), ox);                                        // :172
+        y = __fadd_rn(__fmul_rn(sinf(th), P.target_distance), oy);                                        // :173
+        terrain_cell(T, x, y, col, row);
+        bad = __ldg(T.safe_mask + (size_t)row * T.W + col) == 1;                                          // :220
+    }
+    cx = x;
+    cy = y;
+    cz = __ldg(T.heightmap + (size_t)row * T.W + col);                       // :154 (+ default_root_state z = 0)
+    chead = __fadd_rn(__fmul_rn(heading_u, __fsub_rn(P.heading_hi, P.heading_lo)), P.heading_lo);  // uniform_(lo, hi)
+    S.time_left[i] = P.resampling_time;
+    return bad;
+}
+
+constexpr int kStats = ROVER_STATS_LEN;
+
+__global__ void __launch_bounds__(ROVER_MDP_BLOCK)
+mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_quat_w, int n,
+                     const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
+                     const __grid_constant__ RoverMdpOut O, const __grid_constant__ Tables T,
+                     const long long* __restrict__ spawn_perm, const float* __restrict__ yaw_u,
+                     const float* __restrict__ heading_u, const float* __restrict__ theta_u, int n_rounds,
+                     long long* __restrict__ out_spawn_index, float* __restrict__ block_stats,
+                     unsigned int* __restrict__ done_counter, float* __restrict__ stats, float* __restrict__ obs,
+                     int obs_stride) {
+    __shared__ int warp_cnt[ROVER_MDP_BLOCK / 32];
+    __shared__ int block_base;
+    __shared__ float red[ROVER_MDP_BLOCK / 32][kStats];
+    __shared__ bool is_last;
+    const int i = blockIdx.x * ROVER_MDP_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool valid = i < n;
+    const bool reset = valid && O.reset_flags[i] != 0;
+
+    // ---- rank of this env among the reset envs in ascending env order (== reset_buf.nonzero() order)
+    if (wid == 0) {
+        int acc = 0;
+        for (int b = lane; b < (int)blockIdx.x; b += 32) acc += O.block_reset_counts[b];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) block_base = acc;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, reset);
+    if (lane == 0) warp_cnt[wid] = __popc(ballot);
+    __syncthreads();
+    int rank = block_base + __popc(ballot & ((1u << lane) - 1u));
+    for (int w = 0; w < wid; ++w) rank += warp_cnt[w];
+
+    float st[kStats];
+#pragma unroll
+    for (int k = 0; k < kStats; ++k) st[k] = 0.f;
+
+    if (valid) {
+        float px = root_pos_w[3 * (size_t)i], py = root_pos_w[3 * (size_t)i + 1], pz = root_pos_w[3 * (size_t)i + 2];
+        float4 q = reinterpret_cast<float4*>(root_quat_w)[i];  // (w,x,y,z)
+        float cwx = S.pos_cmd_w[3 * (size_t)i], cwy = S.pos_cmd_w[3 * (size_t)i + 1], cwz = S.pos_cmd_w[3 * (size_t)i + 2];
+        float chead = S.heading_cmd_w[i];
+        float2 act = reinterpret_cast<float2*>(S.action)[i];
+        float time_left = S.time_left[i];
+        long long spawn_idx = -1;
+        bool cmd_dirty = false;
+
+        if (reset) {
+            // -- reset_root_state_rover (randomizations.py:12-39)
+            spawn_idx = __ldg(spawn_perm + rank);
+            const float* sp = T.spawn + 3 * (size_t)spawn_idx;
+            px = __ldg(sp);
+            py = __ldg(sp + 1);
+            pz = __fadd_rn(__ldg(sp + 2), P.spawn_z_offset);
+            const float angle = __fmul_rn(__fmul_rn(__ldg(yaw_u + i), 2.f), 3.1415927f);
+            const float half = __fdiv_rn(angle, 2.f);
+            q = make_float4(cosf(half), 0.f, 0.f, sinf(half));
+            S.env_origins[3 * (size_t)i] = px;
+            S.env_origins[3 * (size_t)i + 1] = py;
+            S.env_origins[3 * (size_t)i + 2] = pz;
+            root_pos_w[3 * (size_t)i] = px;
+            root_pos_w[3 * (size_t)i + 1] = py;
+            root_pos_w[3 * (size_t)i + 2] = pz;
+            reinterpret_cast<float4*>(root_quat_w)[i] = q;
+            // -- ActionManager.reset
+            act = make_float2(0.f, 0.f);
+            reinterpret_cast<float2*>(S.action)[i] = act;
+            reinterpret_cast<float2*>(S.prev_action)[i] = act;
+            // -- RewardManager.reset: episodic sums of reset envs -> stats, then zero
+            float* sums = S.episode_sums + ROVER_NUM_REWARD_TERMS * (size_t)i;
+#pragma unroll
+            for (int k = 0; k < ROVER_NUM_REWARD_TERMS; ++k) {
+                st[k] = sums[k];
+                sums[k] = 0.f;
+            }
+            // -- TerminationManager.reset: per-term counts
+            const uchar4 tf = reinterpret_cast<const uchar4*>(O.term_flags)[i];
+            st[7] = tf.x;
+            st[8] = tf.y;
+            st[9] = tf.z;
+            st[10] = tf.w;
+            // -- CommandTerm.reset: metrics -> stats, zero, counter = 0, then _resample (counter += 1)
+            st[11] = S.err_pos[i];
+            st[12] = S.err_heading[i];
+            st[13] = 1.f;
+            const bool exhausted = resample_command(i, P, S, T, px, py, theta_u, n_rounds, __ldg(heading_u + i), cwx,
+                                                    cwy, cwz, chead);
+            st[14] = exhausted ? 1.f : 0.f;
+            S.command_counter[i] = 1;
+            time_left = P.resampling_time;
+            cmd_dirty = true;
+            S.episode_length_buf[i] = 0;
+        }
+        if (out_spawn_index) out_spawn_index[i] = spawn_idx;
+
+        // -- CommandManager.compute(dt): metrics, time_left, time-based resample, _update_command
+        const float ex = __fsub_rn(cwx, px), ey = __fsub_rn(cwy, py), ez = __fsub_rn(cwz, pz);
+        const float hw = heading_w(q.x, q.y, q.z, q.w);
+        S.err_pos[i] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
+        S.err_heading[i] = fabsf(wrap_to_pi(__fsub_rn(chead, hw)));
+        time_left = __fsub_rn(time_left, P.step_dt);
+        if (time_left <= 0.f) {
+            const float ox = S.env_origins[3 * (size_t)i], oy = S.env_origins[3 * (size_t)i + 1];
+            const bool exhausted = resample_command(i, P, S, T, ox, oy, theta_u, n_rounds, __ldg(heading_u + i), cwx,
+                                                    cwy, cwz, chead);
+            st[14] += exhausted ? 1.f : 0.f;
+            st[15] = 1.f;
+            S.command_counter[i] += 1;
+            time_left = P.resampling_time;
+            cmd_dirty = true;
+        }
+        S.time_left[i] = time_left;
+        if (cmd_dirty) {
+            S.pos_cmd_w[3 * (size_t)i] = cwx;
+            S.pos_cmd_w[3 * (size_t)i + 1] = cwy;
+            S.pos_cmd_w[3 * (size_t)i + 2] = cwz;
+            S.heading_cmd_w[i] = chead;
+        }
+        // _update_command (terrain_importer.py:97-101): quat_rotate_inverse(yaw_quat(q), target - root)
+        const float vx = __fsub_rn(cwx, px), vy = __fsub_rn(cwy, py), vz = __fsub_rn(cwz, pz);
+        const YawQuat yq = yaw_quat(q.x, q.y, q.z, q.w);
+        const float k = __fsub_rn(__fmul_rn(2.f, __fmul_rn(yq.cw, yq.cw)), 1.f);
+        const float b_x = __fmul_rn(__fmul_rn(-__fmul_rn(yq.sz, vy), yq.cw), 2.f);
+        const float b_y = __fmul_rn(__fmul_rn(__fmul_rn(yq.sz, vx), yq.cw), 2.f);
+        const float dot = __fmul_rn(yq.sz, vz);
+        const float c_z = __fmul_rn(__fmul_rn(yq.sz, dot), 2.f);
+        const float pbx = __fsub_rn(__fmul_rn(vx, k), b_x);
+        const float pby = __fsub_rn(__fmul_rn(vy, k), b_y);
+        const float pbz = __fadd_rn(__fmul_rn(vz, k), c_z);
+        S.pos_cmd_b[3 * (size_t)i] = pbx;
+        S.pos_cmd_b[3 * (size_t)i + 1] = pby;
+        S.pos_cmd_b[3 * (size_t)i + 2] = pbz;
+        S.heading_cmd_b[i] = wrap_to_pi(__fsub_rn(chead, hw));
+
+        // -- observation head (rover_env_cfg.py:103-112): last_action, distance * 0.11, angle / pi
+        if (obs) {
+            float* o = obs + (size_t)i * obs_stride;
+            o[0] = act.x;
+            o[1] = act.y;
+            o[2] = __fmul_rn(norm2(pbx, pby), P.obs_distance_scale);
+            o[3] = __fmul_rn(atan2f(pby, pbx), P.obs_heading_scale);
+        }
+    }
+
+    // ---- deterministic episode statistics: warp shuffle -> block -> last block sums the partials in order
+#pragma unroll
+    for (int k = 0; k < kStats; ++k) {
+        float v = st[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) red[wid][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kStats) {
+        float v = 0.f;
+        for (int w = 0; w < ROVER_MDP_BLOCK / 32; ++w) v += red[w][threadIdx.x];
+        block_stats[(size_t)blockIdx.x * kStats + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last && threadIdx.x < kStats) {
+        float v = 0.f;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(block_stats + (size_t)b * kStats + threadIdx.x);
+        stats[threadIdx.x] += v;
+        if (threadIdx.x == 0) *done_counter = 0u;  // re-arm for the next launch
+    }
+}
+
+}  // namespace rover
+
+static int check_state(const RoverMdpState* s, const RoverMdpOut* o) {
+    using namespace rover;
+    ROVER_CHECK(s && o, "rover_mdp: NULL state/out struct");
+    ROVER_CHECK(s->action && s->prev_action && s->pos_cmd_w && s->heading_cmd_w && s->pos_cmd_b && s->heading_cmd_b &&
+                    s->time_left && s->command_counter && s->episode_length_buf && s->episode_sums && s->env_origins &&
+                    s->err_pos && s->err_heading,
+                "rover_mdp: NULL pointer in RoverMdpState");
+    ROVER_CHECK(o->processed_actions && o->joint_pos && o->joint_vel && o->reward && o->term_rewards && o->terminated &&
+                    o->truncated && o->term_flags && o->reset_flags && o->block_reset_counts,
+                "rover_mdp: NULL pointer in RoverMdpOut");
+    ROVER_CHECK((reinterpret_cast<uintptr_t>(o->joint_pos) & 15) == 0, "rover_mdp: joint_pos not 16B aligned");
+    return 0;
+}
+
+extern "C" int rover_mdp_pre_step(const float* new_actions, const float* force_matrix_w, int32_t n_envs,
+                                  const RoverMdpParams* params, const RoverMdpState* state, const RoverMdpOut* out,
+                                  void* stream) {
+    using namespace rover;
+    ROVER_CHECK(n_envs >= 0, "rover_mdp_pre_step: negative n_envs");
+    if (n_envs == 0) return 0;
+    ROVER_CHECK(new_actions && force_matrix_w && params, "rover_mdp_pre_step: NULL argument");
+    ROVER_CHECK(params->num_bodies >= 0 && params->max_episode_length > 0, "rover_mdp_pre_step: bad params");
+    if (int rc = check_state(state, out)) return rc;
+    const int blocks = (n_envs + ROVER_MDP_BLOCK - 1) / ROVER_MDP_BLOCK;
+    mdp_pre_step_kernel<<<blocks, ROVER_MDP_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(
+        new_actions, force_matrix_w, n_envs, *params, *state, *out);
+    return check_launch("mdp_pre_step_kernel");
+}
+
+extern "C" int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_t n_envs, const RoverMdpParams* params,
+                                   const RoverMdpState* state, const RoverMdpOut* out,
+                                   const RoverTerrainTables* tables, const int64_t* spawn_perm, const float* yaw_u,
+                                   const float* heading_u, const float* theta_u, int32_t n_rounds,
+                                   int64_t* out_spawn_index, float* stats, float* scratch, float* obs,
+                                   int32_t obs_stride, void* stream) {
+    using namespace rover;
+    ROVER_CHECK(n_envs >= 0, "rover_mdp_post_step: negative n_envs");
+    if (n_envs == 0) return 0;
+    ROVER_CHECK(root_pos_w && root_quat_w && params && tables && spawn_perm && yaw_u && heading_u && theta_u && stats &&
+                    scratch,
+                "rover_mdp_post_step: NULL argument");
+    ROVER_CHECK(n_rounds >= 1, "rover_mdp_post_step: n_rounds must be >= 1");
+    ROVER_CHECK(tables->heightmap && tables->safe_mask && tables->spawn_table && tables->height > 0 &&
+                    tables->width > 0 && tables->n_spawns > 0 && tables->resolution > 0.f,
+                "rover_mdp_post_step: bad terrain tables");
+    ROVER_CHECK((reinterpret_cast<uintptr_t>(root_quat_w) & 15) == 0, "rover_mdp_post_step: root_quat_w not 16B aligned");
+    ROVER_CHECK(obs == nullptr || obs_stride >= 4, "rover_mdp_post_step: obs_stride < 4");
+    if (int rc = check_state(state, out)) return rc;
+    Tables T{tables->heightmap, tables->safe_mask, tables->height,   tables->width,   tables->offset_x,
+             tables->offset_y,  tables->resolution, tables->spawn_table, tables->n_spawns};
+    const int blocks = (n_envs + ROVER_MDP_BLOCK - 1) / ROVER_MDP_BLOCK;
+    // scratch layout: [blocks * 16] block partials, then one uint32 completion counter (zero-initialised by caller)
+    float* block_stats = scratch;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + (size_t)blocks * ROVER_STATS_LEN);
+    mdp_post_step_kernel<<<blocks, ROVER_MDP_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(
+        root_pos_w, root_quat_w, n_envs, *params, *state, *out, T, reinterpret_cast<const long long*>(spawn_perm),
+        yaw_u, heading_u, theta_u, n_rounds, reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats,
+        obs, obs_stride);
+    return check_launch("mdp_post_step_kernel");
+}

@@ -1,0 +1,77 @@
+"""Env sharding and the one collective on the path: the episode-statistics reduction.
+
+The reference is single-process / single-GPU; every MDP term is per-env, so environments
+shard across ranks with no data-path exchange.  The only cross-env quantities are the logging
+statistics the ORBIT managers' ``reset()`` produce (``extras["log"]``, consumed at rover_envs/utils/skrl_utils.py:
+139-142): per-term episodic reward means, termination counts and command metrics over the envs that reset.
+Each rank's fused post-step kernel accumulates the SUMS and the COUNT into one 16-float vector; ranks combine
+them with a single ``all_reduce(SUM)`` (NCCL over NVLink on GPUs, gloo in the CPU tests) and divide afterwards
+-- sum / count, not a mean of means.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .config import REWARD_TERMS, TERMINATION_TERMS
+
+STATS_LEN = 16
+IDX_ERR_POS, IDX_ERR_HEADING, IDX_NUM_RESETS, IDX_EXHAUSTED, IDX_TIME_RESAMPLES = 11, 12, 13, 14, 15
+
+
+def shard_range(num_envs: int, rank: int, world: int) -> tuple:
+    """Block partition of the env axis: rank r owns [r*N/G, (r+1)*N/G) (remainder spread over the first ranks)."""
+    base, rem = divmod(num_envs, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def spawn_rows(num_envs_local: int, rank: int) -> tuple:
+    """Rows of the global spawn table a rank draws from: 2*N_local rows, disjoint between ranks, so that the
+    without-replacement draw of mdp/randomizations.py:22 stays shard-local."""
+    return 2 * num_envs_local * rank, 2 * num_envs_local * (rank + 1)
+
+
+def episode_log(stats: torch.Tensor, episode_length_s: float = 150.0) -> dict:
+    """``extras["log"]`` from a (globally reduced) statistics vector, as the ORBIT managers build it."""
+    s = stats.detach().double().cpu()
+    k = max(float(s[IDX_NUM_RESETS]), 1.0)
+    log = {f"Episode Reward/{name}": float(s[i]) / k / episode_length_s for i, name in enumerate(REWARD_TERMS)}
+    log.update({f"Episode Termination/{name}": int(round(float(s[7 + i]))) for i, name in enumerate(TERMINATION_TERMS)})
+    log["Metrics/target_pose/error_pos"] = float(s[IDX_ERR_POS]) / k
+    log["Metrics/target_pose/error_heading"] = float(s[IDX_ERR_HEADING]) / k
+    log["num_resets"] = int(round(float(s[IDX_NUM_RESETS])))
+    return log
+
+
+class EpisodeStats:
+    """Owns the hand-off of the per-rank statistics vector to the collective.
+
+    ``all_reduce_async`` snapshots ``buf.stats`` into a staging vector, clears the accumulator for the next
+    interval and starts the all-reduce without blocking the compute stream; ``result`` waits for it.
+    """
+
+    def __init__(self, buf, world_size: int | None = None, group=None):
+        self.stats = buf.stats if hasattr(buf, "stats") else buf
+        self.group = group
+        self.world = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        self.staging = torch.zeros_like(self.stats)
+        self._work = None
+
+    def all_reduce_async(self):
+        if self._work is not None:
+            self._work.wait()
+        self.staging.copy_(self.stats)
+        self.stats.zero_()
+        if self.world > 1:
+            self._work = dist.all_reduce(self.staging, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return self
+
+    def result(self) -> torch.Tensor:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return self.staging
+
+    def log(self, episode_length_s: float = 150.0) -> dict:
+        return episode_log(self.result(), episode_length_s)

@@ -1,0 +1,232 @@
+"""Thin Python operators over the C ABI (``include/rover_b200.h``): tensors in, tensors out, current stream.
+
+No operator has a CPU or eager-PyTorch fallback: CUDA tensors are required and a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import RoverEnvCfg
+from .scan_grid import ScanGrid, build_scan_grid
+
+
+# ------------------------------------------------------------------------------------------------------
+# height scan
+# ------------------------------------------------------------------------------------------------------
+class ScanGridHandle:
+    """Device-resident home grid + the host struct the launcher reads (``RoverScanGrid``)."""
+
+    def __init__(self, grid: ScanGrid, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ScanGridHandle needs a CUDA device; there is no CPU fallback")
+        self.grid = grid
+        self.cell_start = grid.cell_start.to(self.device).contiguous()
+        self.records = grid.records.to(self.device).contiguous()
+        if grid.n_records == 0:
+            self.records = torch.zeros(1, 12, device=self.device)
+        s = _lib.ScanGrid()
+        s.n_levels = len(grid.levels)
+        s.span = grid.span
+        for i, lv in enumerate(grid.levels):
+            s.level[i] = _lib.ScanLevel(lv.ox, lv.oy, lv.cell, lv.inv_cell, lv.ncx, lv.ncy, lv.start_offset, 0)
+        s.cell_start = self.cell_start.data_ptr()
+        s.records = self.records.data_ptr()
+        s.n_records = grid.n_records
+        self.struct = s
+
+    @classmethod
+    def from_mesh(cls, vertices, faces, device, cell_size=None) -> "ScanGridHandle":
+        v = vertices.detach().cpu().numpy() if isinstance(vertices, torch.Tensor) else np.asarray(vertices)
+        f = faces.detach().cpu().numpy() if isinstance(faces, torch.Tensor) else np.asarray(faces)
+        return cls(build_scan_grid(v, f, cell_size=cell_size), device)
+
+
+def grid_pattern(resolution: float = 0.1, size=(3.0, 3.0), offset_pos=(0.0, 0.0, 10.0)) -> torch.Tensor:
+    """Local ray starts ``[R,3]`` = ORBIT ``grid_pattern`` + ``RayCasterCfg.offset.pos``.
+    x varies fastest: ray ``r = iy * nx + ix``."""
+    x = torch.arange(start=-size[0] / 2, end=size[0] / 2 + 1.0e-9, step=resolution)
+    y = torch.arange(start=-size[1] / 2, end=size[1] / 2 + 1.0e-9, step=resolution)
+    gx, gy = torch.meshgrid(x, y, indexing="xy")
+    starts = torch.zeros(gx.numel(), 3, dtype=torch.float32)
+    starts[:, 0] = gx.flatten()
+    starts[:, 1] = gy.flatten()
+    return starts + torch.tensor(offset_pos, dtype=torch.float32)
+
+
+def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, ray_starts_local: torch.Tensor, grid: ScanGridHandle,
+                max_distance: float = 100.0, base_offset: float = 0.26878, out: torch.Tensor | None = None,
+                return_hits: bool = False, variant: int = 0):
+    """``height_scan_rover`` over the CUDA raycaster.  ``out`` may be a ``[N, >=R]`` row-strided view (e.g. the
+    scan columns of the observation buffer).  Returns heights ``[N,R]`` (and ``ray_hits_w [N,R,3]``)."""
+    dev = _lib.require_cuda(pos_w, quat_w, ray_starts_local)
+    n, r = pos_w.shape[0], ray_starts_local.shape[0]
+    if pos_w.dtype != torch.float32 or quat_w.dtype != torch.float32 or ray_starts_local.dtype != torch.float32:
+        raise RuntimeError("height_scan: fp32 tensors required")
+    if pos_w.shape != (n, 3) or quat_w.shape != (n, 4) or ray_starts_local.shape != (r, 3):
+        raise RuntimeError("height_scan: bad shapes")
+    if grid.device != dev:
+        raise RuntimeError("height_scan: grid lives on another device")
+    if out is None:
+        out = torch.empty(n, r, dtype=torch.float32, device=dev)
+    elif out.dtype != torch.float32 or out.shape != (n, r) or out.stride(1) != 1 or out.device != dev:
+        raise RuntimeError("height_scan: out must be fp32 [N,R] with unit inner stride")
+    hits = torch.empty(n, r, 3, dtype=torch.float32, device=dev) if return_hits else None
+    _lib.check(_lib.load().rover_height_scan(
+        _lib.ptr(pos_w), _lib.ptr(quat_w), n, _lib.ptr(ray_starts_local), r, C.byref(grid.struct),
+        float(max_distance), float(base_offset), C.c_void_p(out.data_ptr()), int(out.stride(0)) if n > 0 else r,
+        _lib.ptr(hits), int(variant), _lib.current_stream(dev)))
+    return (out, hits) if return_hits else out
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused MDP step
+# ------------------------------------------------------------------------------------------------------
+def mdp_params(cfg: RoverEnvCfg) -> _lib.MdpParams:
+    a = cfg.actions
+    p = _lib.MdpParams()
+    p.scale_lin, p.scale_ang = a.scale
+    p.offset_lin, p.offset_ang = a.offsets()
+    p.wheelbase_length = a.wheelbase_length
+    p.middle_wheel_distance = a.middle_wheel_distance
+    p.rear_and_front_wheel_distance = a.rear_and_front_wheel_distance
+    p.wheel_radius = a.wheel_radius
+    p.min_radius = a.middle_wheel_distance * 0.8  # evaluated in double, then fp32 (ackermann_actions.py:264)
+    for i, w in enumerate(cfg.rewards.weights):
+        p.weight[i] = w
+    p.reached_threshold = cfg.rewards.reached_threshold
+    p.far_threshold = cfg.rewards.far_threshold
+    p.step_dt = cfg.step_dt
+    p.max_episode_length = cfg.max_episode_length
+    p.obs_distance_scale = cfg.obs_distance_scale
+    p.obs_heading_scale = cfg.obs_heading_scale
+    p.target_distance = cfg.commands.target_distance
+    p.resampling_time = cfg.commands.resampling_time_range[0]
+    p.heading_lo, p.heading_hi = cfg.commands.heading_range
+    p.spawn_z_offset = cfg.spawn_z_offset
+    p.num_bodies = cfg.num_contact_bodies
+    return p
+
+
+@dataclass
+class MdpBuffers:
+    """Persistent manager state + per-step outputs of the fused kernels, all on one CUDA device."""
+
+    n: int
+    device: torch.device
+    # state (names follow the reference objects they belong to)
+    action: torch.Tensor
+    prev_action: torch.Tensor
+    pos_cmd_w: torch.Tensor
+    heading_cmd_w: torch.Tensor
+    pos_cmd_b: torch.Tensor
+    heading_cmd_b: torch.Tensor
+    time_left: torch.Tensor
+    command_counter: torch.Tensor
+    episode_length_buf: torch.Tensor
+    episode_sums: torch.Tensor
+    env_origins: torch.Tensor
+    err_pos: torch.Tensor
+    err_heading: torch.Tensor
+    # outputs
+    processed_actions: torch.Tensor
+    joint_pos: torch.Tensor
+    joint_vel: torch.Tensor
+    reward: torch.Tensor
+    term_rewards: torch.Tensor
+    terminated: torch.Tensor
+    truncated: torch.Tensor
+    term_flags: torch.Tensor
+    reset_flags: torch.Tensor
+    block_reset_counts: torch.Tensor
+    spawn_index: torch.Tensor
+    stats: torch.Tensor
+    scratch: torch.Tensor
+
+    @staticmethod
+    def allocate(n: int, device) -> "MdpBuffers":
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("MdpBuffers need a CUDA device; there is no CPU fallback")
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)  # noqa: E731
+        i64 = lambda *s: torch.zeros(*s, dtype=torch.int64, device=device)  # noqa: E731
+        u8 = lambda *s: torch.zeros(*s, dtype=torch.uint8, device=device)  # noqa: E731
+        blocks = (n + _lib.MDP_BLOCK - 1) // _lib.MDP_BLOCK
+        return MdpBuffers(
+            n, device, f(n, 2), f(n, 2), f(n, 3), f(n), f(n, 3), f(n), f(n), i64(n), i64(n), f(n, 7), f(n, 3), f(n),
+            f(n), f(n, 2), f(n, 4), f(n, 6), f(n), f(n, 7), u8(n), u8(n), u8(n, 4), u8(n),
+            torch.zeros(max(blocks, 1), dtype=torch.int32, device=device), torch.full((n,), -1, dtype=torch.int64,
+                                                                                      device=device),
+            f(_lib.STATS_LEN), f(max(blocks, 1) * _lib.STATS_LEN + 1))
+
+    def state_struct(self) -> _lib.MdpState:
+        return _lib.MdpState(*[getattr(self, k).data_ptr() for k in _lib._STATE_FIELDS])
+
+    def out_struct(self) -> _lib.MdpOut:
+        return _lib.MdpOut(*[getattr(self, k).data_ptr() for k in _lib._OUT_FIELDS])
+
+
+class TerrainTablesHandle:
+    """Device tables + host struct (``RoverTerrainTables``) for the resample path."""
+
+    def __init__(self, heightmap, safe_mask, offset_xy, spawn_table, resolution, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("TerrainTablesHandle needs a CUDA device; there is no CPU fallback")
+        self.heightmap = heightmap.to(self.device, torch.float32).contiguous()
+        mask = safe_mask.reshape(safe_mask.shape[0], safe_mask.shape[1])
+        self.safe_mask = mask.to(self.device, torch.uint8).contiguous()
+        self.spawn_table = spawn_table.to(self.device, torch.float32).contiguous()
+        off = [float(v) for v in offset_xy]
+        self.struct = _lib.TerrainTables(self.heightmap.data_ptr(), self.safe_mask.data_ptr(),
+                                         self.heightmap.shape[0], self.heightmap.shape[1], off[0], off[1],
+                                         float(resolution), self.spawn_table.data_ptr(), self.spawn_table.shape[0], 0)
+        if self.safe_mask.shape != self.heightmap.shape:
+            raise RuntimeError("safe_mask and heightmap shapes differ")
+
+
+def mdp_pre_step(buf: MdpBuffers, params: _lib.MdpParams, actions: torch.Tensor, force_matrix_w: torch.Tensor):
+    """Action shift + Ackermann + counters + terminations + rewards (one launch, in place on ``buf``)."""
+    dev = _lib.require_cuda(actions, force_matrix_w)
+    if dev != buf.device:
+        raise RuntimeError("mdp_pre_step: inputs on another device than the buffers")
+    if actions.shape != (buf.n, 2) or actions.dtype != torch.float32:
+        raise RuntimeError("mdp_pre_step: actions must be fp32 [N,2]")
+    if force_matrix_w.dtype != torch.float32 or force_matrix_w.numel() != buf.n * params.num_bodies * 3:
+        raise RuntimeError("mdp_pre_step: force_matrix_w must be fp32 [N,B,1,3]")
+    st, out = buf.state_struct(), buf.out_struct()
+    _lib.check(_lib.load().rover_mdp_pre_step(_lib.ptr(actions), _lib.ptr(force_matrix_w), buf.n, C.byref(params),
+                                               C.byref(st), C.byref(out), _lib.current_stream(dev)))
+
+
+def mdp_post_step(buf: MdpBuffers, params: _lib.MdpParams, tables: TerrainTablesHandle, root_pos_w: torch.Tensor,
+                  root_quat_w: torch.Tensor, spawn_perm: torch.Tensor, yaw_u: torch.Tensor, heading_u: torch.Tensor,
+                  theta_u: torch.Tensor, obs: torch.Tensor | None = None):
+    """Reset / resample / command update / observation head (one launch).  ``root_*`` are updated in place
+    for the reset envs; ``buf.stats`` is accumulated; ``buf.spawn_index`` holds the spawn rows used (-1 else)."""
+    dev = _lib.require_cuda(root_pos_w, root_quat_w, spawn_perm, yaw_u, heading_u, theta_u)
+    if dev != buf.device or tables.device != dev:
+        raise RuntimeError("mdp_post_step: tensors on different devices")
+    n = buf.n
+    if root_pos_w.shape != (n, 3) or root_quat_w.shape != (n, 4):
+        raise RuntimeError("mdp_post_step: bad root state shapes")
+    if spawn_perm.dtype != torch.int64 or spawn_perm.numel() < n:
+        raise RuntimeError("mdp_post_step: spawn_perm must be int64 with at least N entries")
+    if theta_u.dim() != 2 or theta_u.shape[0] != n or yaw_u.shape != (n,) or heading_u.shape != (n,):
+        raise RuntimeError("mdp_post_step: variates must be yaw_u[N], heading_u[N], theta_u[N,R]")
+    obs_ptr, obs_stride = None, 0
+    if obs is not None:
+        if obs.dtype != torch.float32 or obs.shape[0] != n or obs.stride(1) != 1 or obs.shape[1] < 4:
+            raise RuntimeError("mdp_post_step: obs must be fp32 [N,>=4] with unit inner stride")
+        obs_ptr, obs_stride = C.c_void_p(obs.data_ptr()), int(obs.stride(0))
+    st, out = buf.state_struct(), buf.out_struct()
+    _lib.check(_lib.load().rover_mdp_post_step(
+        _lib.ptr(root_pos_w), _lib.ptr(root_quat_w), n, C.byref(params), C.byref(st), C.byref(out),
+        C.byref(tables.struct), _lib.ptr(spawn_perm), _lib.ptr(yaw_u), _lib.ptr(heading_u), _lib.ptr(theta_u),
+        int(theta_u.shape[1]), _lib.ptr(buf.spawn_index), _lib.ptr(buf.stats), _lib.ptr(buf.scratch), obs_ptr,
+        obs_stride, _lib.current_stream(dev)))

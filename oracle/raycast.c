@@ -173,13 +173,18 @@ static int ray_tri_watertight(const float org[3], const float dir[3], const floa
     return 1;
 }
 
-static inline int ray_aabb(const float org[3], const float rcp[3], const float lo[3], const float hi[3], float tmax) {
+static inline int ray_aabb(const float org[3], const float dir[3], const float rcp[3], const float lo[3],
+                           const float hi[3], float tmax) {
     float t0 = 0.0f, t1 = tmax;
     for (int k = 0; k < 3; ++k) {
+        if (dir[k] == 0.0f) {
+            /* axis-parallel ray: inside the (closed) slab or not; avoids the 0 * inf = NaN of the slab form */
+            if (org[k] < lo[k] || org[k] > hi[k]) return 0;
+            continue;
+        }
         float a = (lo[k] - org[k]) * rcp[k];
         float b = (hi[k] - org[k]) * rcp[k];
         float n = fminf(a, b), f = fmaxf(a, b);
-        /* NaN (0 * inf) compares false: slab ignored, which is the conservative choice */
         if (n > t0) t0 = n;
         if (f < t1) t1 = f;
     }
@@ -208,7 +213,7 @@ static void cast_one(const Mesh *m, const float org[3], const float dir[3], floa
         stack[sp++] = 0;
         while (sp > 0) {
             const Node *nd = &m->nodes[stack[--sp]];
-            if (!ray_aabb(org, rcp, nd->lo, nd->hi, best)) continue;
+            if (!ray_aabb(org, dir, rcp, nd->lo, nd->hi, best)) continue;
             if (nd->count > 0) {
                 for (int i = nd->left; i < nd->left + nd->count; ++i) {
                     int fi = m->prim[i];

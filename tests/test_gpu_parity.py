@@ -1,0 +1,272 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C ABI against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): bit-exact hit / termination masks and resampled indices; 1e-5 relative
+for float rewards, actions and ray distances.  A ray distance is t ~ 10 m, so heights are compared with
+``atol = 1e-5 * t`` (1e-4 m).  Threshold-exact masks are compared on the envs whose compared quantity is not
+within a few ulp of the threshold (CPU libm and CUDA atan2f/sinf/cosf differ in the last ulp).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from isaac_rover_orbit_b200 import ops, synthetic
+from isaac_rover_orbit_b200 import terrain as TR
+from isaac_rover_orbit_b200.config import RoverEnvCfg
+
+pytestmark = pytest.mark.gpu
+
+SIZE, RES = 48.0, 0.2
+
+
+@pytest.fixture(scope="module")
+def world(cuda_device):
+    from oracle import raycast as oracle_raycast
+
+    v, f = TR.make_synthetic_terrain(SIZE, RES, seed=3)
+    n = 256
+    tables = TR.build_terrain_tables(v, f, n)
+    return dict(v=v, f=f, n=n, tables=tables, mesh=oracle_raycast.Mesh(v, f),
+                grid=ops.ScanGridHandle.from_mesh(v, f, cuda_device), dev=cuda_device,
+                rays=ops.grid_pattern())
+
+
+def _scan_compare(h_gpu, h_ref, t_ref=10.0):
+    h_gpu = h_gpu.cpu()
+    assert torch.equal(torch.isinf(h_gpu), torch.isinf(h_ref)), "hit mask must be bit-exact"
+    fin = ~torch.isinf(h_ref)
+    assert (h_gpu[~fin] == -float("inf")).all()
+    if fin.any():
+        err = (h_gpu[fin] - h_ref[fin]).abs().max().item()
+        assert err <= 1e-5 * max(t_ref, 1.0), f"height error {err}"
+
+
+@pytest.mark.parametrize("variant", [0])
+def test_height_scan_vs_oracle_small_terrain(world, variant):
+    from oracle import step as OS
+
+    gen = torch.Generator().manual_seed(11)
+    n = world["n"]
+    pos, quat = synthetic.make_poses(n, gen, torch.from_numpy(world["v"]), SIZE, RES, margin=0.5)
+    # rays leaving the mesh (misses), exact axis-aligned yaw on grid lines (rays on edges / vertices)
+    pos[:4, :2] = torch.tensor([[0.3, 0.3], [47.9, 20.0], [24.0, -0.7], [10.0, 10.2]])
+    quat[4:8] = torch.tensor([[1.0, 0, 0, 0], [0.70710678, 0, 0, 0.70710678], [0.0, 0, 0, 1.0], [1.0, 0, 0, 0]])
+    pos[4:8, :2] = torch.tensor([[10.0, 10.0], [20.2, 30.0], [5.0, 5.0], [40.1, 40.1]])
+    dev = world["dev"]
+    h, hits = ops.height_scan(pos.to(dev), quat.to(dev), world["rays"].to(dev), world["grid"], return_hits=True,
+                              variant=variant)
+    h_ref, hits_ref = OS.height_scan(pos, quat, world["mesh"])
+    assert torch.isinf(h_ref).any() and (~torch.isinf(h_ref)).any()
+    _scan_compare(h, h_ref)
+    hits = hits.cpu()
+    miss = torch.isinf(hits_ref[..., 2])
+    assert torch.equal(torch.isinf(hits).all(-1), miss)
+    torch.testing.assert_close(hits[~miss], hits_ref[~miss], rtol=1e-6, atol=1e-4)
+
+
+def test_height_scan_analytic_plane(cuda_device):
+    """Independent of the oracle: on the plane z = 0.3x - 0.2y + 1 the scan equals body_z - z(x,y) - 0.26878 at the
+    961 yaw-rotated grid points (SURVEY.md 8c invariant)."""
+    v = np.array([[-50, -50, 0], [50, -50, 0], [50, 50, 0], [-50, 50, 0]], dtype=np.float32)
+    v[:, 2] = 0.3 * v[:, 0] - 0.2 * v[:, 1] + 1.0
+    f = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32)
+    grid = ops.ScanGridHandle.from_mesh(v, f, cuda_device)
+    assert len(grid.grid.levels) == 1 and grid.grid.levels[0].cell > 50  # two giant triangles -> a coarse level
+    gen = torch.Generator().manual_seed(5)
+    n = 33
+    pos = torch.cat([torch.rand(n, 2, generator=gen) * 60 - 30, torch.rand(n, 1, generator=gen) * 3 + 20], 1)
+    yaw = (torch.rand(n, generator=gen) * 2 - 1) * np.pi
+    quat = synthetic.quat_from_euler(torch.randn(n, generator=gen) * 0.2, torch.randn(n, generator=gen) * 0.2, yaw)
+    rays = ops.grid_pattern()
+    h = ops.height_scan(pos.to(cuda_device), quat.to(cuda_device), rays.to(cuda_device), grid).cpu().double()
+    # float64 expectation with the true yaw of the full quaternion
+    w, x, y, z = quat.double().unbind(1)
+    yaw_true = torch.atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
+    c, s = torch.cos(yaw_true)[:, None], torch.sin(yaw_true)[:, None]
+    rx, ry = rays[:, 0].double()[None], rays[:, 1].double()[None]
+    X = pos[:, 0:1].double() + c * rx - s * ry
+    Y = pos[:, 1:2].double() + s * rx + c * ry
+    expect = pos[:, 2:3].double() - (0.3 * X - 0.2 * Y + 1.0) - 0.26878
+    torch.testing.assert_close(h, expect, rtol=0, atol=2e-4)
+
+
+def test_height_scan_mixed_mesh_levels_and_degenerates(cuda_device):
+    """Ground of two huge triangles + small rock pyramids + vertical / zero-area / flipped triangles."""
+    from oracle import raycast as oracle_raycast
+    from oracle import step as OS
+
+    rng = np.random.default_rng(2)
+    verts = [[-20, -20, 0.1], [20, -20, -0.1], [20, 20, 0.2], [-20, 20, 0.0]]
+    faces = [[0, 1, 2], [0, 3, 2]]  # second one is clockwise: double-sided must still hit
+    for _ in range(300):
+        cx, cy = rng.uniform(-15, 15, 2)
+        r, hgt = rng.uniform(0.1, 0.8), rng.uniform(0.2, 1.0)
+        b = len(verts)
+        verts += [[cx - r, cy - r, 0.05], [cx + r, cy - r, 0.05], [cx + r, cy + r, 0.05], [cx - r, cy + r, 0.05],
+                  [cx, cy, hgt]]
+        faces += [[b, b + 1, b + 4], [b + 1, b + 2, b + 4], [b + 2, b + 3, b + 4], [b + 3, b, b + 4]]
+    b = len(verts)
+    verts += [[1, 1, 0], [1, 1, 3], [2, 1, 0], [3, 3, 1], [3, 3, 1], [4, 4, 1]]  # vertical wall, zero-area
+    faces += [[b, b + 1, b + 2], [b + 3, b + 4, b + 5]]
+    v = np.array(verts, dtype=np.float32)
+    f = np.array(faces, dtype=np.int32)
+    grid = ops.ScanGridHandle.from_mesh(v, f, cuda_device)
+    assert len(grid.grid.levels) >= 2 and grid.grid.n_dropped == 2
+    gen = torch.Generator().manual_seed(9)
+    n = 128
+    pos = torch.cat([torch.rand(n, 2, generator=gen) * 44 - 22, torch.rand(n, 1, generator=gen) + 0.5], 1)
+    quat = synthetic.quat_from_euler(torch.zeros(n), torch.zeros(n), (torch.rand(n, generator=gen) * 2 - 1) * np.pi)
+    h = ops.height_scan(pos.to(cuda_device), quat.to(cuda_device), ops.grid_pattern().to(cuda_device), grid)
+    h_ref, _ = OS.height_scan(pos, quat, oracle_raycast.Mesh(v, f))
+    # rays within 1e-6 m of the outer border may legitimately differ (edge bias); none are generated here
+    _scan_compare(h, h_ref)
+
+
+def test_height_scan_max_distance_and_empty(cuda_device):
+    v = np.array([[-5, -5, -95.0], [5, -5, -95.0], [0, 5, -95.0]], dtype=np.float32)
+    f = np.array([[0, 1, 2]], dtype=np.int32)
+    grid = ops.ScanGridHandle.from_mesh(v, f, cuda_device)
+    rays = ops.grid_pattern().to(cuda_device)
+    pos = torch.tensor([[0.0, 0.0, -5.5], [0.0, 0.0, -4.5], [0.0, 0.0, -200.0]], device=cuda_device)
+    quat = torch.tensor([[1.0, 0, 0, 0]] * 3, device=cuda_device)
+    h = ops.height_scan(pos, quat, rays, grid).cpu()
+    assert torch.isfinite(h[0, 480])  # t = 99.5 < 100
+    assert torch.isinf(h[1]).all()  # t = 100.5: beyond max_distance
+    assert torch.isinf(h[2]).all()  # triangle above the ray start (t < 0)
+    # zero envs / empty mesh
+    assert ops.height_scan(pos[:0], quat[:0], rays, grid).shape == (0, 961)
+    empty = ops.ScanGridHandle.from_mesh(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32), cuda_device)
+    assert torch.isinf(ops.height_scan(pos, quat, rays, empty)).all()
+
+
+def _load_state(buf, ost):
+    for k in ("action", "prev_action", "pos_cmd_w", "heading_cmd_w", "pos_cmd_b", "heading_cmd_b", "time_left",
+              "command_counter", "episode_length_buf", "episode_sums", "env_origins", "err_pos", "err_heading"):
+        getattr(buf, k).copy_(getattr(ost, k))
+
+
+def _near(x, thr, tol):
+    return (x - thr).abs() <= tol
+
+
+def test_mdp_step_vs_oracle(world):
+    """Six consecutive steps; before each step the CUDA buffers are loaded with the oracle's state so that every
+    step is an independent single-step parity check over an evolving state distribution."""
+    from oracle import step as OS
+    from oracle import terms as OT
+
+    dev, n, tables = world["dev"], world["n"], world["tables"]
+    cfg = RoverEnvCfg(num_envs=n)
+    params = ops.mdp_params(cfg)
+    th = ops.TerrainTablesHandle(tables.heightmap, tables.safe_mask, tables.offset_xy, tables.spawn_table,
+                                 tables.resolution, dev)
+    otab = OS.TerrainTables(tables.heightmap, tables.safe_mask, tables.offset_xy, tables.spawn_table)
+    gen = torch.Generator().manual_seed(21)
+    vt = torch.from_numpy(world["v"])
+    st0 = synthetic.make_step(n, gen, vt, SIZE, RES, margin=4.0)
+    pos_cmd_w, heading_cmd_w, ep_len = synthetic.init_commands(n, gen, st0.root_pos_w)
+    ost = OS.MdpState.zeros(n)
+    ost.pos_cmd_w[:] = pos_cmd_w
+    ost.heading_cmd_w[:] = heading_cmd_w
+    ost.episode_length_buf[:] = ep_len
+    ost.env_origins[:] = st0.root_pos_w
+    ost.time_left[:] = 150.0
+    ost.time_left[5] = 0.1  # exercises the time-based resample branch (CommandTerm.compute)
+    ost.pos_cmd_b[:], ost.heading_cmd_b[:] = OT.update_command(pos_cmd_w, heading_cmd_w, st0.root_pos_w,
+                                                               st0.root_quat_w)
+    buf = ops.MdpBuffers.allocate(n, dev)
+    total_resets = 0
+    for step in range(6):
+        st = synthetic.make_step(n, gen, vt, SIZE, RES, margin=4.0)
+        if step == 2:
+            st.actions[:4] = torch.tensor([[0.0135, 0.0135], [0.0135, 0.7], [0.6, 0.0135], [-0.4, 0.2]])
+        _load_state(buf, ost)
+        buf.stats.zero_()
+        d = st.to(dev)
+        pre_pos_b = ost.pos_cmd_b.clone()
+        obs = torch.zeros(n, 965, device=dev)
+        ops.mdp_pre_step(buf, params, d.actions, d.force_matrix_w)
+        ops.mdp_post_step(buf, params, th, d.root_pos_w, d.root_quat_w, d.spawn_perm, d.yaw_u, d.heading_u,
+                          d.theta_u, obs)
+        torch.cuda.synchronize()
+        out = OS.oracle_step(ost, st.actions, st.root_pos_w, st.root_quat_w, st.force_matrix_w, otab, st.spawn_perm,
+                             st.yaw_u, st.theta_u, st.heading_u)
+        # ---- masks: bit-exact away from the thresholds
+        dist = pre_pos_b[:, :2].norm(dim=1)
+        amb = _near(dist, 0.18, 1e-6) | _near(dist, 11.0, 1e-5)
+        assert amb.sum() <= 2
+        ok = ~amb
+        flags = buf.term_flags.cpu().bool()
+        assert torch.equal(flags[ok], out.term_flags[ok])
+        assert torch.equal(buf.terminated.cpu().bool()[ok], out.terminated[ok])
+        assert torch.equal(buf.truncated.cpu().bool()[ok], out.truncated[ok])
+        if amb.any():  # keep the closed loop consistent for the statistics below
+            continue
+        # ---- actions / rewards: 1e-5 relative
+        torch.testing.assert_close(buf.processed_actions.cpu(), out.processed_actions, rtol=0, atol=0)
+        torch.testing.assert_close(buf.joint_pos.cpu(), out.joint_pos, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(buf.joint_vel.cpu(), out.joint_vel, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(buf.term_rewards.cpu(), out.term_rewards, rtol=1e-5, atol=1e-9)
+        torch.testing.assert_close(buf.reward.cpu(), out.reward, rtol=1e-5, atol=1e-8)
+        # ---- resets: indices bit-exact
+        ids = out.reset_ids
+        total_resets += len(ids)
+        sp = buf.spawn_index.cpu()
+        assert torch.equal((sp >= 0).nonzero().squeeze(-1), ids)
+        assert torch.equal(sp[ids], out.spawn_index)
+        torch.testing.assert_close(d.root_pos_w.cpu(), out.root_pos_w, rtol=0, atol=0)
+        torch.testing.assert_close(d.root_quat_w.cpu(), out.root_quat_w, rtol=1e-6, atol=1e-7)
+        # ---- state
+        assert torch.equal(buf.episode_length_buf.cpu(), ost.episode_length_buf)
+        assert torch.equal(buf.command_counter.cpu(), ost.command_counter)
+        assert torch.equal(buf.action.cpu(), ost.action) and torch.equal(buf.prev_action.cpu(), ost.prev_action)
+        assert torch.equal(buf.env_origins.cpu(), ost.env_origins)
+        torch.testing.assert_close(buf.episode_sums.cpu(), ost.episode_sums, rtol=1e-5, atol=1e-8)
+        torch.testing.assert_close(buf.time_left.cpu(), ost.time_left, rtol=1e-6, atol=1e-6)
+        # targets: sin/cos differ in the last ulp between libm and CUDA -> 9 m * 1e-6; the sampled cell (and so
+        # z from the heightmap) is compared exactly unless the candidate sits within 1e-4 cells of a cell border
+        torch.testing.assert_close(buf.pos_cmd_w.cpu()[:, :2], ost.pos_cmd_w[:, :2], rtol=1e-6, atol=2e-5)
+        cell = ost.pos_cmd_w[:, :2] / 0.05 + tables.offset_xy
+        border = ((cell - cell.round()).abs() < 1e-3).any(dim=1)
+        assert torch.equal(buf.pos_cmd_w.cpu()[~border, 2], ost.pos_cmd_w[~border, 2])
+        torch.testing.assert_close(buf.heading_cmd_w.cpu(), ost.heading_cmd_w, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(buf.pos_cmd_b.cpu(), ost.pos_cmd_b, rtol=1e-5, atol=2e-5)
+        head_err = (buf.heading_cmd_b.cpu() - ost.heading_cmd_b).abs()
+        assert (torch.minimum(head_err, (head_err - 2 * np.pi).abs()) < 1e-5).all()
+        torch.testing.assert_close(buf.err_pos.cpu(), ost.err_pos, rtol=1e-5, atol=2e-5)
+        torch.testing.assert_close(obs[:, :4].cpu(), out.obs_head, rtol=1e-5, atol=1e-5)
+        # ---- episode statistics (deterministic reduction)
+        s = buf.stats.cpu()
+        torch.testing.assert_close(s[:7], out.stats["reward_sums"], rtol=1e-5, atol=1e-7)
+        assert torch.equal(s[7:11].long(), out.stats["term_counts"].long())
+        assert int(s[13]) == out.stats["num_resets"] and int(s[14]) == out.stats["target_rounds_exhausted"]
+        assert int(s[15]) == out.stats["num_time_resamples"]
+        torch.testing.assert_close(s[11], out.stats["err_pos_sum"], rtol=1e-5, atol=1e-5)
+    assert total_resets > 10, "the fixture must exercise resets"
+
+
+def test_mdp_terms_against_reference_golden(cuda_device, golden_dir):
+    """The fused kernel against outputs of the UNMODIFIED reference functions (tests/golden/terms.npz)."""
+    z = np.load(os.path.join(golden_dir, "terms.npz"))
+    n = len(z["in_actions"])
+    cfg = RoverEnvCfg(num_envs=n)
+    params = ops.mdp_params(cfg)
+    buf = ops.MdpBuffers.allocate(n, cuda_device)
+    t = lambda k: torch.from_numpy(z[k]).to(cuda_device)  # noqa: E731
+    buf.action.copy_(t("in_prev_actions"))  # becomes prev_action inside the kernel
+    buf.pos_cmd_b.copy_(t("in_pos_b"))
+    buf.episode_length_buf.copy_(t("in_ep_len") - 1)  # the kernel increments before the terms read it
+    ops.mdp_pre_step(buf, params, t("in_actions").contiguous(), t("in_force").contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(buf.processed_actions.cpu(), torch.from_numpy(z["ref_processed"]))
+    torch.testing.assert_close(buf.joint_pos.cpu(), torch.from_numpy(z["ref_joint_pos"]), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(buf.joint_vel.cpu(), torch.from_numpy(z["ref_joint_vel"]), rtol=1e-5, atol=1e-6)
+    w = torch.tensor(cfg.rewards.weights) * cfg.step_dt
+    dist = torch.from_numpy(z["in_pos_b"])[:, :2].norm(dim=1)
+    ok = ~(_near(dist, 0.18, 1e-6) | _near(dist, 11.0, 1e-5))
+    ref_r = torch.from_numpy(z["ref_rewards"]) * w
+    torch.testing.assert_close(buf.term_rewards.cpu()[ok], ref_r[ok], rtol=1e-5, atol=1e-9)
+    flags = buf.term_flags.cpu().bool()
+    assert torch.equal(flags[ok][:, 1:], torch.from_numpy(z["ref_terms"])[ok])
+    assert torch.equal(flags[:, 0], torch.from_numpy(z["in_ep_len"]) >= 750)

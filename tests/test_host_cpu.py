@@ -1,0 +1,174 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports what ``include/rover_b200.h`` declares,
+ctypes structs match the C layout, operators refuse CPU tensors (no fallback), and the scan-grid builder is
+validated against the oracle raycast through a numpy emulation of the kernel's walk."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.dirname(__file__))
+
+import scan_emulation as SE  # noqa: E402
+
+from isaac_rover_orbit_b200 import _lib, ops  # noqa: E402
+from isaac_rover_orbit_b200 import terrain as TR  # noqa: E402
+from isaac_rover_orbit_b200.config import RoverEnvCfg  # noqa: E402
+from isaac_rover_orbit_b200.scan_grid import build_scan_grid  # noqa: E402
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__
+
+    __graft_entry__.build()
+
+
+def test_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rover_b200.h")).read()
+    declared = set(re.findall(r"\b(rover_[a-z_0-9]+)\s*\(", header))
+    assert declared >= {"rover_height_scan", "rover_mdp_pre_step", "rover_mdp_post_step"}
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(_lib.SYMBOLS) == declared
+    assert lib.rover_abi_version() == _lib.ABI_VERSION
+
+
+def test_ctypes_structs_match_c_layout(tmp_path):
+    names = {"RoverScanLevel": _lib.ScanLevel, "RoverScanGrid": _lib.ScanGrid, "RoverMdpParams": _lib.MdpParams,
+             "RoverMdpState": _lib.MdpState, "RoverMdpOut": _lib.MdpOut, "RoverTerrainTables": _lib.TerrainTables}
+    src = tmp_path / "sz.c"
+    body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
+    src.write_text(f'#include <stdio.h>\n#include "rover_b200.h"\nint main(void){{{body}return 0;}}')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    sizes = dict(zip(out[0::2], map(int, out[1::2])))
+    for n, cls in names.items():
+        assert ctypes.sizeof(cls) == sizes[n], n
+    header = open(os.path.join(ROOT, "include", "rover_b200.h")).read()
+    for macro, val in (("ROVER_MAX_LEVELS", _lib.MAX_LEVELS), ("ROVER_STATS_LEN", _lib.STATS_LEN),
+                       ("ROVER_MDP_BLOCK", _lib.MDP_BLOCK), ("ROVER_NUM_REWARD_TERMS", _lib.NUM_REWARD_TERMS)):
+        assert int(re.search(rf"#define {macro} (\d+)", header).group(1)) == val
+
+
+def test_no_cpu_fallback():
+    pos, quat = torch.zeros(2, 3), torch.zeros(2, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.ScanGridHandle.from_mesh(np.zeros((3, 3), np.float32), np.array([[0, 1, 2]]), "cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.MdpBuffers.allocate(4, "cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        _lib.require_cuda(pos, quat)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "isaac_rover_orbit_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py") and fn != "smoke.py":
+                text = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), fn
+
+
+def test_mdp_params_constants():
+    p = ops.mdp_params(RoverEnvCfg())
+    assert p.max_episode_length == 750 and abs(p.step_dt - 0.2) < 1e-7
+    assert abs(p.min_radius - np.float32(0.894 * 0.8)) < 1e-9 and p.num_bodies == 14
+    assert [round(w, 3) for w in p.weight] == [5.0, 5.0, -0.1, -1.5, -0.5, -2.0, -2.0]
+
+
+def _ray_world(n, gen, lo, hi):
+    from oracle import step as OS
+
+    pos = torch.cat([torch.rand(n, 2, generator=gen) * (hi - lo) + lo, torch.rand(n, 1, generator=gen) * 2], 1)
+    yaw = torch.rand(n, generator=gen) * 6.28 - 3.14
+    quat = torch.stack([torch.cos(yaw / 2), torch.zeros(n), torch.zeros(n), torch.sin(yaw / 2)], 1)
+    return pos, quat, OS.ray_starts_world(pos, quat).reshape(-1, 3)
+
+
+def test_scan_grid_builder_matches_oracle_on_terrain():
+    from oracle.raycast import Mesh
+
+    v, f = TR.make_synthetic_terrain(24.0, 0.2, seed=5)
+    g = build_scan_grid(v, f)
+    assert g.n_records == len(f) and len(g.levels) == 1
+    # records are sorted by home cell: cell_start is a non-decreasing partition of [0, n_records]
+    cs = g.cell_start.numpy()
+    assert cs[0] == 0 and cs[-1] == g.n_records and (np.diff(cs) >= 0).all()
+    gen = torch.Generator().manual_seed(0)
+    pos, quat, starts = _ray_world(24, gen, -2.0, 26.0)
+    # grid-aligned poses: rays exactly on mesh edges and vertices
+    d = torch.zeros_like(starts)
+    d[:, 2] = -1
+    hits, t, face = Mesh(v, f).raycast(starts, d, 100.0, return_t=True)
+    zb = SE.cast_down(g, starts[:, 0].numpy(), starts[:, 1].numpy(), starts[:, 2].numpy())
+    hit = (face >= 0).numpy()
+    assert hit.any() and (~hit).any()
+    assert np.array_equal(hit, np.isfinite(zb))
+    assert np.abs(hits[:, 2].numpy()[hit] - zb[hit]).max() < 1e-5
+
+
+def test_scan_grid_builder_levels_and_degenerates():
+    from oracle.raycast import Mesh
+
+    rng = np.random.default_rng(2)
+    verts = [[-20, -20, 0.1], [20, -20, -0.1], [20, 20, 0.2], [-20, 20, 0.0]]
+    faces = [[0, 1, 2], [0, 3, 2]]
+    for _ in range(120):
+        cx, cy = rng.uniform(-15, 15, 2)
+        r, hgt = rng.uniform(0.1, 0.8), rng.uniform(0.2, 1.0)
+        b = len(verts)
+        verts += [[cx - r, cy - r, 0.05], [cx + r, cy - r, 0.05], [cx + r, cy + r, 0.05], [cx - r, cy + r, 0.05],
+                  [cx, cy, hgt]]
+        faces += [[b, b + 1, b + 4], [b + 1, b + 2, b + 4], [b + 2, b + 3, b + 4], [b + 3, b, b + 4]]
+    b = len(verts)
+    verts += [[1, 1, 0], [1, 1, 3], [2, 1, 0], [3, 3, 1], [3, 3, 1], [4, 4, 1]]
+    faces += [[b, b + 1, b + 2], [b + 3, b + 4, b + 5]]
+    v, f = np.array(verts, np.float32), np.array(faces, np.int32)
+    g = build_scan_grid(v, f)
+    assert g.n_dropped == 2 and len(g.levels) >= 2 and g.n_records == len(f) - 2
+    gen = torch.Generator().manual_seed(3)
+    _, _, starts = _ray_world(16, gen, -22.0, 22.0)
+    d = torch.zeros_like(starts)
+    d[:, 2] = -1
+    hits, t, face = Mesh(v, f).raycast(starts, d, 100.0, return_t=True)
+    zb = SE.cast_down(g, starts[:, 0].numpy(), starts[:, 1].numpy(), starts[:, 2].numpy())
+    hit = (face >= 0).numpy()
+    assert np.array_equal(hit, np.isfinite(zb))
+    assert np.abs(hits[:, 2].numpy()[hit] - zb[hit]).max() < 1e-5
+
+
+def test_scan_grid_rejects_bad_faces():
+    with pytest.raises(ValueError):
+        build_scan_grid(np.zeros((3, 3), np.float32), np.array([[0, 1, 5]]))
+    g = build_scan_grid(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))
+    assert g.n_records == 0
+
+
+def test_oracle_bvh_equals_brute_force():
+    """Pins oracle/raycast.c: the BVH walk must agree bit for bit with the all-triangles scan, including rays that
+    run exactly along bounding-box faces (axis-parallel rays on grid lines)."""
+    from oracle.raycast import Mesh
+
+    v, f = TR.make_synthetic_terrain(12.0, 0.2, seed=1)
+    m = Mesh(v, f)
+    gen = torch.Generator().manual_seed(4)
+    xy = torch.rand(4000, 2, generator=gen) * 14 - 1
+    xy[:500] = (xy[:500] / 0.2).round() * 0.2  # on vertices / edges
+    s = torch.cat([xy, torch.full((4000, 1), 15.0)], 1)
+    d = torch.zeros(4000, 3)
+    d[:, 2] = -1
+    d[2000:] = torch.nn.functional.normalize(torch.randn(2000, 3, generator=gen) * torch.tensor([0.3, 0.3, 1.0]), dim=1)
+    d[2000:, 2] = -d[2000:, 2].abs()
+    a = m.raycast(s, d, 100.0, return_t=True)
+    b = m.raycast(s, d, 100.0, brute=True, return_t=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    assert (a[2][:500] >= 0).float().mean() > 0.7
