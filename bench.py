@@ -126,7 +126,7 @@ def dist_env():
     return rank, world, local
 
 
-def build_world(need_tables_for: int | None, device):
+def build_world(need_tables_for: int | None, build_device, device):
     """Synthetic terrain + scan grid (+ resample tables for `need_tables_for` envs)."""
     from isaac_rover_orbit_b200 import ops
     from isaac_rover_orbit_b200 import terrain as TR
@@ -139,7 +139,7 @@ def build_world(need_tables_for: int | None, device):
     tables = None
     if need_tables_for:
         t0 = time.time()
-        tables = TR.build_terrain_tables(v, f, need_tables_for, build_device=device)
+        tables = TR.build_terrain_tables(v, f, need_tables_for, build_device=build_device)
         log(f"terrain tables {tuple(tables.heightmap.shape)} ({time.time() - t0:.1f}s)")
     return v, f, grid, tables
 
@@ -177,10 +177,10 @@ def run_ours(args):
 
     n_scan = SCAN_ENVS_PER_GPU
     n_step = STEP_ENVS_1GPU if world == 1 else STEP_ENVS_PER_GPU_MULTI
-    v, f, grid, tables = build_world(n_step, dev)
+    v, f, grid, tables = build_world(n_step, "cpu" if args.init_on_cpu else dev, dev)
     vt = torch.from_numpy(v)
     cfg = RoverEnvCfg(num_envs=n_step)
-    rays = ops.grid_pattern().to(dev)
+    rays = ops.RayPattern.grid(dev)
     stream = torch.cuda.current_stream(dev)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -266,8 +266,15 @@ def run_ours(args):
         obs = torch.zeros(n_step, 4 + N_RAYS, device=dev)
         stats = EpisodeStats(buf, world)
 
+        # synthetic "physics": every step the rover sits at its env origin + a bounded offset, so that the
+        # far/success terminations stay rare and resets come from contacts (5 %) and time-outs
+        drift = [(torch.rand(n_step, 3, generator=gen2) * torch.tensor([4.0, 4.0, 0.0]) - torch.tensor([2.0, 2.0, 0.0])
+                  ).to(dev) for _ in range(4)]
+        buf.pos_cmd_w.copy_(sets[0].root_pos_w + torch.tensor([9.0, 0.0, 0.0], device=dev))
+
         def full_step(i):
-            s = sets[i % 4]  # the synthetic "physics" hands over root state + contact forces of this step
+            s = sets[i % 4]
+            torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)  # stand-in for PhysX, not one of our kernels
             ops.mdp_pre_step(buf, params, s.actions, s.force_matrix_w)
             ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
                               s.theta_u, obs)
@@ -277,6 +284,7 @@ def run_ours(args):
 
         def mdp_only(i):
             s = sets[i % 4]
+            torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)
             ops.mdp_pre_step(buf, params, s.actions, s.force_matrix_w)
             ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
                               s.theta_u, obs)
@@ -400,8 +408,9 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", type=int, default=int(os.environ.get("ROVER_SCAN_VARIANT", "0")))
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("ROVER_SCAN_VARIANT", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--init-on-cpu", action="store_true", help="build the init-time tables on the host (profiling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -59,10 +59,12 @@ typedef struct RoverScanGrid {
  * ray_starts_local [n_rays,3]: ORBIT RayCaster.ray_starts (grid_pattern + offset.pos), env frame.
  * out_heights [n_envs,n_rays]: pos_w.z - hit.z - base_offset; a miss (no hit with 0 <= t < max_dist) is -inf.
  * out_hits_w [n_envs,n_rays,3] (optional, may be NULL): sensor.data.ray_hits_w, +inf on a miss.
- * variant: 0 = direct (global-memory) kernel, 1 = shared-memory staged kernel. */
+ * pattern_box (HOST, 4 floats: xmin, xmax, ymin, ymax of ray_starts_local; required by variant 1).
+ * variant: 0 = direct (global-memory) kernel, 1 = shared-memory staged kernel (same results). */
 int rover_height_scan(const float* pos_w, const float* quat_w, int32_t n_envs, const float* ray_starts_local,
-                      int32_t n_rays, const RoverScanGrid* grid /* host */, float max_distance, float base_offset,
-                      float* out_heights, int32_t out_stride, float* out_hits_w, int32_t variant, void* stream);
+                      int32_t n_rays, const float* pattern_box /* host */, const RoverScanGrid* grid /* host */,
+                      float max_distance, float base_offset, float* out_heights, int32_t out_stride,
+                      float* out_hits_w, int32_t variant, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Fused MDP step.  Replaces, in one launch:
@@ -119,7 +121,7 @@ typedef struct RoverMdpOut {
     int32_t* block_reset_counts;   /* [ceil(N/ROVER_MDP_BLOCK)] resets per thread block (rank scan input) */
 } RoverMdpOut;
 
-#define ROVER_MDP_BLOCK 256
+#define ROVER_MDP_BLOCK 64
 
 /* new_actions [N,2]; force_matrix_w [N,B,1,3] (contact_sensor.data.force_matrix_w). */
 int rover_mdp_pre_step(const float* new_actions, const float* force_matrix_w, int32_t n_envs,

@@ -17,7 +17,7 @@ MAX_LEVELS = 12
 NUM_REWARD_TERMS = 7
 NUM_TERMINATION_TERMS = 4
 STATS_LEN = 16
-MDP_BLOCK = 256
+MDP_BLOCK = 64
 ABI_VERSION = 1
 
 SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_mdp_pre_step", "rover_mdp_post_step")
@@ -90,7 +90,8 @@ def load() -> C.CDLL:
         raise RuntimeError(f"librover_b200.so ABI {lib.rover_abi_version()} != expected {ABI_VERSION}")
     vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
     lib.rover_height_scan.restype = C.c_int
-    lib.rover_height_scan.argtypes = [vp, vp, i32, vp, i32, C.POINTER(ScanGrid), f32, f32, vp, i32, vp, i32, vp]
+    lib.rover_height_scan.argtypes = [vp, vp, i32, vp, i32, C.POINTER(C.c_float * 4), C.POINTER(ScanGrid), f32, f32, vp,
+                                      i32, vp, i32, vp]
     lib.rover_mdp_pre_step.restype = C.c_int
     lib.rover_mdp_pre_step.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut), vp]
     lib.rover_mdp_post_step.restype = C.c_int

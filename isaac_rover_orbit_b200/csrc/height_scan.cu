@@ -98,15 +98,16 @@ static int make_dev_grid(const RoverScanGrid* grid, ScanGridDev& g) {
 }
 
 int launch_height_scan_staged(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local, int n_rays,
-                              const ScanGridDev& g, float max_d, float base_offset, float* out, int out_stride,
-                              float* hits, cudaStream_t stream);  // height_scan_staged.cu
+                              const ScanGridDev& g, float4 pattern_box, float max_d, float base_offset, float* out,
+                              int out_stride, float* hits, cudaStream_t stream);  // height_scan_staged.cu
 
 }  // namespace rover
 
 extern "C" int rover_height_scan(const float* pos_w, const float* quat_w, int32_t n_envs,
-                                 const float* ray_starts_local, int32_t n_rays, const RoverScanGrid* grid,
-                                 float max_distance, float base_offset, float* out_heights, int32_t out_stride,
-                                 float* out_hits_w, int32_t variant, void* stream) {
+                                 const float* ray_starts_local, int32_t n_rays, const float* pattern_box,
+                                 const RoverScanGrid* grid, float max_distance, float base_offset,
+                                 float* out_heights, int32_t out_stride, float* out_hits_w, int32_t variant,
+                                 void* stream) {
     using namespace rover;
     ROVER_CHECK(n_envs >= 0 && n_rays >= 0, "rover_height_scan: negative sizes");
     if (n_envs == 0 || n_rays == 0) return 0;
@@ -122,7 +123,11 @@ extern "C" int rover_height_scan(const float* pos_w, const float* quat_w, int32_
         return check_launch("height_scan_direct_kernel");
     }
     if (variant == 1) {
-        return launch_height_scan_staged(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, max_distance,
+        ROVER_CHECK(pattern_box != nullptr, "rover_height_scan: variant 1 needs pattern_box (host, 4 floats)");
+        ROVER_CHECK(pattern_box[0] <= pattern_box[1] && pattern_box[2] <= pattern_box[3],
+                    "rover_height_scan: pattern_box must be (xmin, xmax, ymin, ymax)");
+        const float4 box = make_float4(pattern_box[0], pattern_box[1], pattern_box[2], pattern_box[3]);
+        return launch_height_scan_staged(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, box, max_distance,
                                          base_offset, out_heights, out_stride, out_hits_w, s);
     }
     return fail("rover_height_scan: unknown variant %d", variant);

@@ -59,11 +59,37 @@ def grid_pattern(resolution: float = 0.1, size=(3.0, 3.0), offset_pos=(0.0, 0.0,
     return starts + torch.tensor(offset_pos, dtype=torch.float32)
 
 
-def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, ray_starts_local: torch.Tensor, grid: ScanGridHandle,
+class RayPattern:
+    """ORBIT ``RayCaster.ray_starts`` on the device + its host-side bounding box (the staged kernel's window)."""
+
+    def __init__(self, ray_starts_local: torch.Tensor, device):
+        cpu = ray_starts_local.detach().to("cpu", torch.float32).contiguous()
+        self.n_rays = cpu.shape[0]
+        self.device = torch.device(device)
+        self.starts = cpu.to(self.device)
+        if self.n_rays:
+            self.box = (C.c_float * 4)(float(cpu[:, 0].min()), float(cpu[:, 0].max()), float(cpu[:, 1].min()),
+                                       float(cpu[:, 1].max()))
+        else:
+            self.box = (C.c_float * 4)(0.0, 0.0, 0.0, 0.0)
+
+    @classmethod
+    def grid(cls, device, resolution: float = 0.1, size=(3.0, 3.0), offset_pos=(0.0, 0.0, 10.0)) -> "RayPattern":
+        return cls(grid_pattern(resolution, size, offset_pos), device)
+
+
+DEFAULT_SCAN_VARIANT = 1
+
+
+def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle,
                 max_distance: float = 100.0, base_offset: float = 0.26878, out: torch.Tensor | None = None,
-                return_hits: bool = False, variant: int = 0):
+                return_hits: bool = False, variant: int | None = None):
     """``height_scan_rover`` over the CUDA raycaster.  ``out`` may be a ``[N, >=R]`` row-strided view (e.g. the
     scan columns of the observation buffer).  Returns heights ``[N,R]`` (and ``ray_hits_w [N,R,3]``)."""
+    if not isinstance(rays, RayPattern):
+        rays = RayPattern(rays, pos_w.device)
+    ray_starts_local = rays.starts
+    variant = DEFAULT_SCAN_VARIANT if variant is None else variant
     dev = _lib.require_cuda(pos_w, quat_w, ray_starts_local)
     n, r = pos_w.shape[0], ray_starts_local.shape[0]
     if pos_w.dtype != torch.float32 or quat_w.dtype != torch.float32 or ray_starts_local.dtype != torch.float32:
@@ -78,7 +104,7 @@ def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, ray_starts_local: tor
         raise RuntimeError("height_scan: out must be fp32 [N,R] with unit inner stride")
     hits = torch.empty(n, r, 3, dtype=torch.float32, device=dev) if return_hits else None
     _lib.check(_lib.load().rover_height_scan(
-        _lib.ptr(pos_w), _lib.ptr(quat_w), n, _lib.ptr(ray_starts_local), r, C.byref(grid.struct),
+        _lib.ptr(pos_w), _lib.ptr(quat_w), n, _lib.ptr(ray_starts_local), r, C.byref(rays.box), C.byref(grid.struct),
         float(max_distance), float(base_offset), C.c_void_p(out.data_ptr()), int(out.stride(0)) if n > 0 else r,
         _lib.ptr(hits), int(variant), _lib.current_stream(dev)))
     return (out, hits) if return_hits else out

@@ -28,10 +28,15 @@ def run(n: int = 64, size_m: float = 48.0, seed: int = 7) -> dict:
 
     # ---- height scan
     grid = ops.ScanGridHandle.from_mesh(v, f, dev)
-    rays = ops.grid_pattern(cfg.height_scanner.pattern_cfg.resolution, cfg.height_scanner.pattern_cfg.size,
-                            cfg.height_scanner.offset_pos)
-    h_gpu = ops.height_scan(st.root_pos_w.to(dev), st.root_quat_w.to(dev), rays.to(dev), grid,
-                            cfg.height_scanner.max_distance, cfg.height_scan_base_offset)
+    rays = ops.RayPattern.grid(dev, cfg.height_scanner.pattern_cfg.resolution, cfg.height_scanner.pattern_cfg.size,
+                               cfg.height_scanner.offset_pos)
+    h_direct = ops.height_scan(st.root_pos_w.to(dev), st.root_quat_w.to(dev), rays, grid,
+                               cfg.height_scanner.max_distance, cfg.height_scan_base_offset, variant=0)
+    h_gpu = ops.height_scan(st.root_pos_w.to(dev), st.root_quat_w.to(dev), rays, grid,
+                            cfg.height_scanner.max_distance, cfg.height_scan_base_offset, variant=1)
+    if not torch.equal(torch.isinf(h_direct), torch.isinf(h_gpu)) or \
+            (h_direct - h_gpu).nan_to_num(0.0, 0.0, 0.0).abs().max().item() > 1e-5:
+        raise AssertionError("smoke: staged and direct height-scan kernels disagree")
     torch.cuda.synchronize()
     h_ref, _ = OS.height_scan(st.root_pos_w, st.root_quat_w, oracle_raycast.Mesh(v, f))
     h_gpu = h_gpu.cpu()
@@ -67,7 +72,7 @@ def run(n: int = 64, size_m: float = 48.0, seed: int = 7) -> dict:
     obs = torch.zeros(n, 965, device=dev)
     ops.mdp_pre_step(buf, params, d.actions, d.force_matrix_w)
     ops.mdp_post_step(buf, params, th, d.root_pos_w, d.root_quat_w, d.spawn_perm, d.yaw_u, d.heading_u, d.theta_u, obs)
-    ops.height_scan(d.root_pos_w, d.root_quat_w, rays.to(dev), grid, out=obs[:, 4:])
+    ops.height_scan(d.root_pos_w, d.root_quat_w, rays, grid, out=obs[:, 4:])
     torch.cuda.synchronize()
     otab = OS.TerrainTables(tables.heightmap, tables.safe_mask, tables.offset_xy, tables.spawn_table)
     out = OS.oracle_step(ost, st.actions, st.root_pos_w, st.root_quat_w, st.force_matrix_w, otab, st.spawn_perm,

@@ -142,8 +142,9 @@ def test_scan_grid_builder_levels_and_degenerates():
     hits, t, face = Mesh(v, f).raycast(starts, d, 100.0, return_t=True)
     zb = SE.cast_down(g, starts[:, 0].numpy(), starts[:, 1].numpy(), starts[:, 2].numpy())
     hit = (face >= 0).numpy()
-    assert np.array_equal(hit, np.isfinite(zb))
-    assert np.abs(hits[:, 2].numpy()[hit] - zb[hit]).max() < 1e-5
+    inner = ((starts[:, :2].abs() - 20.0).abs() > 1e-3).all(dim=1).numpy()  # see the GPU twin of this test
+    assert np.array_equal(hit[inner], np.isfinite(zb)[inner])
+    assert np.abs(hits[:, 2].numpy()[hit & inner] - zb[hit & inner]).max() < 1e-5
 
 
 def test_scan_grid_rejects_bad_faces():
