@@ -55,16 +55,29 @@ typedef struct RoverScanGrid {
     int32_t reserved;
 } RoverScanGrid;
 
+/* Plane-cell table (plane_cells.py): rectilinear grid whose cells carry the closed-form surface
+ * z = a*lx + b*ly + c + k*min(A*lx + B*ly + C, 0); entry = {a,b,c,k | A,B,C,tag}; tag != 0 -> general cell,
+ * the ray falls back to the home-grid walk.  Used by variant 2. */
+typedef struct RoverPlaneCells {
+    const float* xs;       /* [nx+1] grid lines, strictly increasing */
+    const float* ys;       /* [ny+1] */
+    const float* entries;  /* [ny, nx, 8], 16-byte aligned */
+    int32_t nx, ny;
+    float inv_dx, inv_dy;  /* nx / (xs[nx]-xs[0]), ny / (ys[ny]-ys[0]): first guess of the cell */
+} RoverPlaneCells;
+
 /* pos_w [n_envs,3], quat_w [n_envs,4]: sensor (body) pose, sensor.data.pos_w / quat_w.
  * ray_starts_local [n_rays,3]: ORBIT RayCaster.ray_starts (grid_pattern + offset.pos), env frame.
  * out_heights [n_envs,n_rays]: pos_w.z - hit.z - base_offset; a miss (no hit with 0 <= t < max_dist) is -inf.
  * out_hits_w [n_envs,n_rays,3] (optional, may be NULL): sensor.data.ray_hits_w, +inf on a miss.
  * pattern_box (HOST, 4 floats: xmin, xmax, ymin, ymax of ray_starts_local; required by variant 1).
- * variant: 0 = direct (global-memory) kernel, 1 = shared-memory staged kernel (same results). */
+ * cells (HOST struct, device pointers inside; required by variant 2, may be NULL otherwise).
+ * variant: 0 = direct home-grid walk, 1 = shared-memory staged home-grid walk, 2 = plane-cell fast path with
+ * home-grid fallback for general cells.  All variants produce the same heights. */
 int rover_height_scan(const float* pos_w, const float* quat_w, int32_t n_envs, const float* ray_starts_local,
                       int32_t n_rays, const float* pattern_box /* host */, const RoverScanGrid* grid /* host */,
-                      float max_distance, float base_offset, float* out_heights, int32_t out_stride,
-                      float* out_hits_w, int32_t variant, void* stream);
+                      const RoverPlaneCells* cells /* host */, float max_distance, float base_offset,
+                      float* out_heights, int32_t out_stride, float* out_hits_w, int32_t variant, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Fused MDP step.  Replaces, in one launch:

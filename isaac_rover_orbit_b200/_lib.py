@@ -34,6 +34,11 @@ class ScanGrid(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class PlaneCells(C.Structure):
+    _fields_ = [("xs", C.c_void_p), ("ys", C.c_void_p), ("entries", C.c_void_p), ("nx", C.c_int32), ("ny", C.c_int32),
+                ("inv_dx", C.c_float), ("inv_dy", C.c_float)]
+
+
 class MdpParams(C.Structure):
     _fields_ = [("scale_lin", C.c_float), ("scale_ang", C.c_float), ("offset_lin", C.c_float),
                 ("offset_ang", C.c_float), ("wheelbase_length", C.c_float), ("middle_wheel_distance", C.c_float),
@@ -90,8 +95,8 @@ def load() -> C.CDLL:
         raise RuntimeError(f"librover_b200.so ABI {lib.rover_abi_version()} != expected {ABI_VERSION}")
     vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
     lib.rover_height_scan.restype = C.c_int
-    lib.rover_height_scan.argtypes = [vp, vp, i32, vp, i32, C.POINTER(C.c_float * 4), C.POINTER(ScanGrid), f32, f32, vp,
-                                      i32, vp, i32, vp]
+    lib.rover_height_scan.argtypes = [vp, vp, i32, vp, i32, C.POINTER(C.c_float * 4), C.POINTER(ScanGrid),
+                                      C.POINTER(PlaneCells), f32, f32, vp, i32, vp, i32, vp]
     lib.rover_mdp_pre_step.restype = C.c_int
     lib.rover_mdp_pre_step.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut), vp]
     lib.rover_mdp_post_step.restype = C.c_int

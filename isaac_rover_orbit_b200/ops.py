@@ -12,6 +12,7 @@ import torch
 
 from . import _lib
 from .config import RoverEnvCfg
+from .plane_cells import PlaneCells, build_plane_cells
 from .scan_grid import ScanGrid, build_scan_grid
 
 
@@ -21,11 +22,20 @@ from .scan_grid import ScanGrid, build_scan_grid
 class ScanGridHandle:
     """Device-resident home grid + the host struct the launcher reads (``RoverScanGrid``)."""
 
-    def __init__(self, grid: ScanGrid, device):
+    def __init__(self, grid: ScanGrid, device, cells: PlaneCells | None = None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("ScanGridHandle needs a CUDA device; there is no CPU fallback")
         self.grid = grid
+        self.cells = cells
+        self.cells_struct = None
+        if cells is not None:
+            self.cells_xs = cells.xs.to(self.device).contiguous()
+            self.cells_ys = cells.ys.to(self.device).contiguous()
+            self.cells_entries = cells.entries.to(self.device).contiguous()
+            self.cells_struct = _lib.PlaneCells(self.cells_xs.data_ptr(), self.cells_ys.data_ptr(),
+                                                self.cells_entries.data_ptr(), cells.nx, cells.ny, cells.inv_dx,
+                                                cells.inv_dy)
         self.cell_start = grid.cell_start.to(self.device).contiguous()
         self.records = grid.records.to(self.device).contiguous()
         if grid.n_records == 0:
@@ -41,10 +51,15 @@ class ScanGridHandle:
         self.struct = s
 
     @classmethod
-    def from_mesh(cls, vertices, faces, device, cell_size=None) -> "ScanGridHandle":
+    def from_mesh(cls, vertices, faces, device, cell_size=None, plane_cells: bool = True) -> "ScanGridHandle":
         v = vertices.detach().cpu().numpy() if isinstance(vertices, torch.Tensor) else np.asarray(vertices)
         f = faces.detach().cpu().numpy() if isinstance(faces, torch.Tensor) else np.asarray(faces)
-        return cls(build_scan_grid(v, f, cell_size=cell_size), device)
+        grid = build_scan_grid(v, f, cell_size=cell_size)
+        cells = build_plane_cells(v, f, fallback_cell=grid.levels[0].cell) if plane_cells else None
+        return cls(grid, device, cells)
+
+    def nbytes(self) -> int:
+        return self.grid.nbytes() + (self.cells.nbytes() if self.cells is not None else 0)
 
 
 def grid_pattern(resolution: float = 0.1, size=(3.0, 3.0), offset_pos=(0.0, 0.0, 10.0)) -> torch.Tensor:
@@ -78,7 +93,7 @@ class RayPattern:
         return cls(grid_pattern(resolution, size, offset_pos), device)
 
 
-DEFAULT_SCAN_VARIANT = 1
+DEFAULT_SCAN_VARIANT = 2
 
 
 def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle,
@@ -98,6 +113,8 @@ def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridH
         raise RuntimeError("height_scan: bad shapes")
     if grid.device != dev:
         raise RuntimeError("height_scan: grid lives on another device")
+    if variant == 2 and grid.cells_struct is None:
+        raise RuntimeError("height_scan: variant 2 needs a ScanGridHandle built with plane_cells=True")
     if out is None:
         out = torch.empty(n, r, dtype=torch.float32, device=dev)
     elif out.dtype != torch.float32 or out.shape != (n, r) or out.stride(1) != 1 or out.device != dev:
@@ -105,6 +122,7 @@ def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridH
     hits = torch.empty(n, r, 3, dtype=torch.float32, device=dev) if return_hits else None
     _lib.check(_lib.load().rover_height_scan(
         _lib.ptr(pos_w), _lib.ptr(quat_w), n, _lib.ptr(ray_starts_local), r, C.byref(rays.box), C.byref(grid.struct),
+        C.byref(grid.cells_struct) if grid.cells_struct is not None else None,
         float(max_distance), float(base_offset), C.c_void_p(out.data_ptr()), int(out.stride(0)) if n > 0 else r,
         _lib.ptr(hits), int(variant), _lib.current_stream(dev)))
     return (out, hits) if return_hits else out

@@ -33,10 +33,10 @@ def run(n: int = 64, size_m: float = 48.0, seed: int = 7) -> dict:
     h_direct = ops.height_scan(st.root_pos_w.to(dev), st.root_quat_w.to(dev), rays, grid,
                                cfg.height_scanner.max_distance, cfg.height_scan_base_offset, variant=0)
     h_gpu = ops.height_scan(st.root_pos_w.to(dev), st.root_quat_w.to(dev), rays, grid,
-                            cfg.height_scanner.max_distance, cfg.height_scan_base_offset, variant=1)
+                            cfg.height_scanner.max_distance, cfg.height_scan_base_offset)  # default: plane cells
     if not torch.equal(torch.isinf(h_direct), torch.isinf(h_gpu)) or \
             (h_direct - h_gpu).nan_to_num(0.0, 0.0, 0.0).abs().max().item() > 1e-5:
-        raise AssertionError("smoke: staged and direct height-scan kernels disagree")
+        raise AssertionError("smoke: plane-cell and direct height-scan kernels disagree")
     torch.cuda.synchronize()
     h_ref, _ = OS.height_scan(st.root_pos_w, st.root_quat_w, oracle_raycast.Mesh(v, f))
     h_gpu = h_gpu.cpu()

@@ -44,3 +44,29 @@ def cast_down(grid: ScanGrid, X, Y, Z, max_d=100.0):
                     hit = act & (np.minimum(e0, np.minimum(e1, e2)) >= 0) & (t >= 0) & (t < max_d)
                     best = np.where(hit, np.maximum(best, z), best)
     return best
+
+
+def cast_down_cells(cells, grid: ScanGrid, X, Y, Z, max_d=100.0):
+    """numpy emulation of ``csrc/height_scan.cu::height_scan_cells_kernel`` (variant 2)."""
+    X = np.asarray(X, np.float32)
+    Y = np.asarray(Y, np.float32)
+    Z = np.asarray(Z, np.float32)
+    xs, ys = cells.xs.numpy(), cells.ys.numpy()
+    ent = cells.entries.numpy().reshape(-1, 8)
+    nx, ny = cells.nx, cells.ny
+    i = np.clip(np.searchsorted(xs, X, side="right") - 1, 0, nx - 1)
+    j = np.clip(np.searchsorted(ys, Y, side="right") - 1, 0, ny - 1)
+    inside = (X >= xs[0]) & (X <= xs[-1]) & (Y >= ys[0]) & (Y <= ys[-1])
+    e = ent[j * nx + i]
+    lx, ly = (X - xs[i]).astype(np.float32), (Y - ys[j]).astype(np.float32)
+    fma = lambda a, x, c: (a.astype(np.float64) * x + c).astype(np.float32)  # noqa: E731
+    E = fma(e[:, 4], lx, fma(e[:, 5], ly, e[:, 6]))
+    with np.errstate(invalid="ignore"):
+        z = fma(e[:, 3], np.minimum(E, 0), fma(e[:, 0], lx, fma(e[:, 1], ly, e[:, 2])))
+    t = Z - z
+    closed = inside & (e[:, 7] == 0)
+    out = np.where(closed & (t >= 0) & (t < max_d), z, -np.inf).astype(np.float32)
+    gen = inside & (e[:, 7] != 0)
+    if gen.any():
+        out[gen] = cast_down(grid, X[gen], Y[gen], Z[gen], max_d)
+    return out, gen

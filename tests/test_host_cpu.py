@@ -19,6 +19,7 @@ import scan_emulation as SE  # noqa: E402
 from isaac_rover_orbit_b200 import _lib, ops  # noqa: E402
 from isaac_rover_orbit_b200 import terrain as TR  # noqa: E402
 from isaac_rover_orbit_b200.config import RoverEnvCfg  # noqa: E402
+from isaac_rover_orbit_b200.plane_cells import build_plane_cells  # noqa: E402
 from isaac_rover_orbit_b200.scan_grid import build_scan_grid  # noqa: E402
 
 
@@ -42,7 +43,8 @@ def test_abi_exports_every_declared_symbol():
 
 
 def test_ctypes_structs_match_c_layout(tmp_path):
-    names = {"RoverScanLevel": _lib.ScanLevel, "RoverScanGrid": _lib.ScanGrid, "RoverMdpParams": _lib.MdpParams,
+    names = {"RoverScanLevel": _lib.ScanLevel, "RoverScanGrid": _lib.ScanGrid, "RoverPlaneCells": _lib.PlaneCells,
+             "RoverMdpParams": _lib.MdpParams,
              "RoverMdpState": _lib.MdpState, "RoverMdpOut": _lib.MdpOut, "RoverTerrainTables": _lib.TerrainTables}
     src = tmp_path / "sz.c"
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
@@ -145,6 +147,79 @@ def test_scan_grid_builder_levels_and_degenerates():
     inner = ((starts[:, :2].abs() - 20.0).abs() > 1e-3).all(dim=1).numpy()  # see the GPU twin of this test
     assert np.array_equal(hit[inner], np.isfinite(zb)[inner])
     assert np.abs(hits[:, 2].numpy()[hit & inner] - zb[hit & inner]).max() < 1e-5
+
+
+def _mixed_mesh(n_rocks=120):
+    rng = np.random.default_rng(2)
+    verts = [[-20, -20, 0.1], [20, -20, -0.1], [20, 20, 0.2], [-20, 20, 0.0]]
+    faces = [[0, 1, 2], [0, 3, 2]]
+    for _ in range(n_rocks):
+        cx, cy = rng.uniform(-15, 15, 2)
+        r, hgt = rng.uniform(0.1, 0.8), rng.uniform(0.2, 1.0)
+        b = len(verts)
+        verts += [[cx - r, cy - r, 0.05], [cx + r, cy - r, 0.05], [cx + r, cy + r, 0.05], [cx - r, cy + r, 0.05],
+                  [cx, cy, hgt]]
+        faces += [[b, b + 1, b + 4], [b + 1, b + 2, b + 4], [b + 2, b + 3, b + 4], [b + 3, b, b + 4]]
+    return np.array(verts, np.float32), np.array(faces, np.int32)
+
+
+def test_plane_cells_lattice_terrain_all_closed_form():
+    """DEM-style mesh: the vertex lattice becomes the cell grid and every quad one two-plane cell."""
+    from oracle.raycast import Mesh
+
+    v, f = TR.make_synthetic_terrain(24.0, 0.2, seed=5)
+    pc = build_plane_cells(v, f)
+    assert pc.lattice and pc.nx == 120 and pc.ny == 120 and pc.n_general == 0 and pc.n_empty == 0
+    g = build_scan_grid(v, f)
+    gen = torch.Generator().manual_seed(0)
+    pos, quat, starts = _ray_world(24, gen, -2.0, 26.0)
+    starts[:961, :2] = (starts[:961, :2] / 0.1).round() * 0.1  # rays exactly on lattice lines and vertices
+    d = torch.zeros_like(starts)
+    d[:, 2] = -1
+    hits, t, face = Mesh(v, f).raycast(starts, d, 100.0, return_t=True)
+    zb, general = SE.cast_down_cells(pc, g, starts[:, 0].numpy(), starts[:, 1].numpy(), starts[:, 2].numpy())
+    hit = (face >= 0).numpy()
+    assert not general.any() and hit.any() and (~hit).any()
+    assert np.array_equal(hit, np.isfinite(zb))
+    assert np.abs(hits[:, 2].numpy()[hit] - zb[hit]).max() < 1e-5
+
+
+def test_plane_cells_general_mesh_falls_back():
+    """Non-lattice mesh: uniform lines; cells cut by several triangles are general and take the home-grid walk;
+    closed-form cells (inside one big ground triangle, or on the ground diagonal) must still be exact."""
+    from oracle.raycast import Mesh
+
+    v, f = _mixed_mesh()
+    g = build_scan_grid(v, f)
+    pc = build_plane_cells(v, f, fallback_cell=g.levels[0].cell)
+    assert not pc.lattice and 0 < pc.n_general < pc.nx * pc.ny
+    gen = torch.Generator().manual_seed(3)
+    _, _, starts = _ray_world(16, gen, -22.0, 22.0)
+    d = torch.zeros_like(starts)
+    d[:, 2] = -1
+    hits, t, face = Mesh(v, f).raycast(starts, d, 100.0, return_t=True)
+    zb, general = SE.cast_down_cells(pc, g, starts[:, 0].numpy(), starts[:, 1].numpy(), starts[:, 2].numpy())
+    assert general.any() and (~general).any()
+    hit = (face >= 0).numpy()
+    inner = ((starts[:, :2].abs() - 20.0).abs() > 1e-3).all(dim=1).numpy()
+    assert np.array_equal(hit[inner], np.isfinite(zb)[inner])
+    assert np.abs(hits[:, 2].numpy()[hit & inner] - zb[hit & inner]).max() < 1e-5
+
+
+def test_plane_cells_partial_cover_and_layers_are_general():
+    # one triangle covering half a lattice cell, and two stacked triangles over the same footprint
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0],          # quad split -> closed form
+                  [2, 0, 0], [3, 0, 0], [2, 1, 0], [3, 1, 5],          # single triangle in its cell -> general
+                  [0, 2, 0], [1, 2, 0], [0, 3, 0], [1, 3, 0]], np.float32)
+    f = np.array([[0, 1, 2], [1, 3, 2], [4, 5, 6], [8, 9, 10], [9, 11, 10], [8, 9, 10]], np.int32)
+    pc = build_plane_cells(v, f)
+    ent = pc.entries.numpy()
+    xs, ys = pc.xs.numpy().tolist(), pc.ys.numpy().tolist()
+    assert xs == [0, 1, 2, 3] and ys == [0, 1, 2, 3]
+    assert ent[0, 0, 7] == 0 and np.isfinite(ent[0, 0, 2])   # shared-edge quad
+    assert ent[0, 2, 7] == 1                                 # half-covered cell
+    assert ent[2, 0, 7] == 1                                 # three triangles (one duplicated layer)
+    assert ent[1, 1, 7] == 0 and ent[1, 1, 2] == -np.inf     # empty cell
 
 
 def test_scan_grid_rejects_bad_faces():
