@@ -81,14 +81,6 @@ height_scan_direct_kernel(const float* __restrict__ pos_w, const float* __restri
 // variant 2: plane-cell fast path.  One table entry (2 x float4) answers every ray of a closed-form cell:
 // 5 FMAs instead of ~8 candidate tests; rays of general cells take the home-grid walk above.
 // ---------------------------------------------------------------------------------------------------------
-struct PlaneCellsDev {
-    const float* __restrict__ xs;
-    const float* __restrict__ ys;
-    const float4* __restrict__ ent;
-    int nx, ny;
-    float inv_dx, inv_dy;
-};
-
 // column (row) of the half-open cell [lines[i], lines[i+1]) containing v; the far border is closed.
 __device__ __forceinline__ int locate(const float* __restrict__ lines, int n, float inv_d, float v, bool& inside) {
     const float lo = __ldg(lines), hi = __ldg(lines + n);
@@ -172,6 +164,11 @@ int launch_height_scan_staged(const float* pos_w, const float* quat_w, int n_env
                               const ScanGridDev& g, float4 pattern_box, float max_d, float base_offset, float* out,
                               int out_stride, float* hits, cudaStream_t stream);  // height_scan_staged.cu
 
+int launch_height_scan_cells_tma(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local,
+                                 int n_rays, const ScanGridDev& g, const RoverPlaneCells* cells, float4 pattern_box,
+                                 float max_d, float base_offset, float* out, int out_stride, float* hits,
+                                 cudaStream_t stream);  // height_scan_cells_tma.cu
+
 }  // namespace rover
 
 extern "C" int rover_height_scan(const float* pos_w, const float* quat_w, int32_t n_envs,
@@ -201,12 +198,18 @@ extern "C" int rover_height_scan(const float* pos_w, const float* quat_w, int32_
         return launch_height_scan_staged(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, box, max_distance,
                                          base_offset, out_heights, out_stride, out_hits_w, s);
     }
-    if (variant == 2) {
-        ROVER_CHECK(cells != nullptr, "rover_height_scan: variant 2 needs the plane-cell table");
+    if (variant == 2 || variant == 3) {
+        ROVER_CHECK(cells != nullptr, "rover_height_scan: variants 2/3 need the plane-cell table");
         ROVER_CHECK(cells->xs && cells->ys && cells->entries && cells->nx > 0 && cells->ny > 0,
                     "rover_height_scan: bad plane-cell table");
         ROVER_CHECK((reinterpret_cast<uintptr_t>(cells->entries) & 15) == 0,
                     "rover_height_scan: plane-cell entries not 16B aligned");
+        if (variant == 3) {
+            ROVER_CHECK(pattern_box != nullptr, "rover_height_scan: variant 3 needs pattern_box (host, 4 floats)");
+            const float4 box = make_float4(pattern_box[0], pattern_box[1], pattern_box[2], pattern_box[3]);
+            return launch_height_scan_cells_tma(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, cells, box,
+                                                max_distance, base_offset, out_heights, out_stride, out_hits_w, s);
+        }
         PlaneCellsDev pc{cells->xs, cells->ys, reinterpret_cast<const float4*>(cells->entries), cells->nx, cells->ny,
                          cells->inv_dx, cells->inv_dy};
         height_scan_cells_kernel<<<n_envs, kScanThreads, 0, s>>>(pos_w, quat_w, ray_starts_local, n_rays, g, pc,

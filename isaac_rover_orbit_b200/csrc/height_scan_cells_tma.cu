@@ -1,0 +1,248 @@
+// Plane-cell height scan with the per-environment window staged through the bulk-copy (TMA) engine -- variant 3.
+//
+// ncu on variant 2 (height_scan_cells_kernel): nothing saturated (L1TEX 32 %, issue 40 %, DRAM 4 %), 27 % of the
+// stall samples sit on the first use of the table entry -- every ray chases ~7 dependent global loads (grid-line
+// look-ups, then the entry, which comes from HBM when L2 is cold).  The window of table entries an environment can
+// touch is a dense 2-D tile of the row-major table (<= 32 rows of <= 32 cells x 32 B), so one CTA per environment
+//   1. computes its sensor frame and the window (bounding box of the yaw-rotated pattern rectangle);
+//   2. has warp 0 issue one cp.async.bulk (UBLKCP) per window row into shared memory, completion on an mbarrier,
+//      while the other warps load the window's grid lines and compute their ray origins;
+//   3. resolves every ray from shared memory only: locate in the window lines, 2 x LDS.128, 5 FMA.
+// Rays in general cells (tag != 0) and CTAs whose window exceeds the shared tile take the global-memory paths,
+// so results never depend on the staging.
+#include "scan_common.cuh"
+
+namespace rover {
+
+constexpr int kTmaThreads = 256;
+constexpr int kWinMax = 32;  // window cells per axis held in shared memory
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// index of the half-open interval [lines[i], lines[i+1]) containing v, i in [0, n-1]; lines may live in shared
+// or global memory.  `guess` is an arithmetic first guess; the loops make the answer exact for any monotone lines.
+__device__ __forceinline__ int locate_in(const float* lines, int n, int guess, float v) {
+    int i = min(max(guess, 0), n - 1);
+    while (i > 0 && v < lines[i]) --i;
+    while (i < n - 1 && v >= lines[i + 1]) ++i;
+    return i;
+}
+
+__device__ __forceinline__ int guess_cell(float v, float lo, float inv_d) {
+    return (int)fminf(fmaxf(floorf((v - lo) * inv_d), -1.0e6f), 1.0e6f);
+}
+
+__device__ __forceinline__ float eval_entry(const float4 p, const float4 q, float lx, float ly, float Z, float max_d) {
+    const float E = fmaf(q.x, lx, fmaf(q.y, ly, q.z));
+    const float z = fmaf(p.w, fminf(E, 0.f), fmaf(p.x, lx, fmaf(p.y, ly, p.z)));
+    const float t = Z - z;
+    return (t >= 0.f && t < max_d) ? z : -INFINITY;
+}
+
+// home-grid walk for rays of general cells (same code as the direct kernel)
+__device__ __noinline__ float cast_down_slow(const ScanGridDev& g, float X, float Y, float Z, float max_d) {
+    float best = -INFINITY;
+    for (int l = 0; l < g.n_levels; ++l) {
+        const ScanLevelDev& L = g.level[l];
+        const int i = cell_of(X, L.ox, L.inv_cell);
+        const int j = cell_of(Y, L.oy, L.inv_cell);
+        const int j0 = max(j - g.span, 0), j1 = min(j, L.ncy - 1);
+        const int i0 = max(i - g.span, 0), i1 = min(i, L.ncx - 1);
+        for (int jj = j0; jj <= j1; ++jj) {
+            const float ly = __fsub_rn(Y, __fadd_rn(L.oy, __fmul_rn((float)jj, L.cell)));
+            const int* __restrict__ row = g.cell_start + L.start_offset + jj * L.ncx;
+            for (int ii = i0; ii <= i1; ++ii) {
+                const float lx = __fsub_rn(X, __fadd_rn(L.ox, __fmul_rn((float)ii, L.cell)));
+                const int b = __ldg(row + ii), e = __ldg(row + ii + 1);
+                for (int r = b; r < e; ++r)
+                    test_record(__ldg(g.rec + 3 * r), __ldg(g.rec + 3 * r + 1), __ldg(g.rec + 3 * r + 2), lx, ly, Z,
+                                max_d, best);
+            }
+        }
+    }
+    return best;
+}
+
+// reference rounding chain: t -> hit.z = Z + t*(-1) -> (pos.z - hit.z) - offset ; a miss is -inf / +inf
+__device__ __forceinline__ void write_result(const SensorFrame& f, float X, float Y, float Z, float zhit,
+                                             float base_offset, float* __restrict__ out, float* __restrict__ hit3) {
+    float h = -INFINITY, hx = INFINITY, hy = INFINITY, hz = INFINITY;
+    if (zhit != -INFINITY) {
+        const float t = __fsub_rn(Z, zhit);
+        hz = __fsub_rn(Z, t);
+        hx = X;
+        hy = Y;
+        h = __fsub_rn(__fsub_rn(f.pz, hz), base_offset);
+    }
+    *out = h;
+    if (hit3) {
+        hit3[0] = hx;
+        hit3[1] = hy;
+        hit3[2] = hz;
+    }
+}
+
+struct CellWindow {
+    int ic0, jr0, ncols, nrows;
+    int staged;  // 1: window in shared memory; 0: this CTA reads the table from global memory
+};
+
+__global__ void __launch_bounds__(kTmaThreads, 3)
+height_scan_cells_tma_kernel(const float* __restrict__ pos_w, const float* __restrict__ quat_w,
+                             const float* __restrict__ ray_local, int n_rays, const __grid_constant__ ScanGridDev g,
+                             const __grid_constant__ PlaneCellsDev pc, float4 pattern_box, float max_d,
+                             float base_offset, float* __restrict__ out, int out_stride, float* __restrict__ hits) {
+    __shared__ __align__(128) float4 s_ent[kWinMax * kWinMax * 2];  // 32 KB: [row][col][2]
+    __shared__ float s_xs[kWinMax + 1], s_ys[kWinMax + 1];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ SensorFrame frame_s;
+    __shared__ CellWindow win_s;
+
+    const int env = blockIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        const SensorFrame f = make_frame(pos_w + 3 * (size_t)env, quat_w + 4 * (size_t)env);
+        frame_s = f;
+        float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float X, Y, Z;
+            ray_origin(f, (c & 1) ? pattern_box.y : pattern_box.x, (c & 2) ? pattern_box.w : pattern_box.z, 0.f, X, Y, Z);
+            xmin = fminf(xmin, X), xmax = fmaxf(xmax, X), ymin = fminf(ymin, Y), ymax = fmaxf(ymax, Y);
+        }
+        const float pad = 1.0e-3f;
+        const float x_lo = __ldg(pc.xs), y_lo = __ldg(pc.ys);
+        CellWindow w;
+        w.ic0 = locate_in(pc.xs, pc.nx, guess_cell(xmin - pad, x_lo, pc.inv_dx), xmin - pad);
+        w.jr0 = locate_in(pc.ys, pc.ny, guess_cell(ymin - pad, y_lo, pc.inv_dy), ymin - pad);
+        const int ic1 = locate_in(pc.xs, pc.nx, guess_cell(xmax + pad, x_lo, pc.inv_dx), xmax + pad);
+        const int jr1 = locate_in(pc.ys, pc.ny, guess_cell(ymax + pad, y_lo, pc.inv_dy), ymax + pad);
+        w.ncols = ic1 - w.ic0 + 1;
+        w.nrows = jr1 - w.jr0 + 1;
+        w.staged = (w.ncols <= kWinMax && w.nrows <= kWinMax) ? 1 : 0;
+        win_s = w;
+    }
+    __syncthreads();
+    const SensorFrame f = frame_s;
+    const CellWindow w = win_s;
+
+    if (w.staged) {
+        if (threadIdx.x < 32) {
+            // warp 0: arm the barrier with the byte count, then one bulk copy per window row
+            const uint32_t row_bytes = (uint32_t)w.ncols * 32u;
+            if (threadIdx.x == 0) mbar_expect_tx(&s_bar, row_bytes * (uint32_t)w.nrows);
+            __syncwarp();
+            for (int r = threadIdx.x; r < w.nrows; r += 32)
+                bulk_g2s(s_ent + (size_t)r * w.ncols * 2, pc.ent + 2 * ((size_t)(w.jr0 + r) * pc.nx + w.ic0), row_bytes,
+                         &s_bar);
+        } else if (threadIdx.x < 64) {
+            for (int c = threadIdx.x - 32; c <= w.ncols; c += 32) s_xs[c] = __ldg(pc.xs + w.ic0 + c);
+        } else if (threadIdx.x < 96) {
+            for (int r = threadIdx.x - 64; r <= w.nrows; r += 32) s_ys[r] = __ldg(pc.ys + w.jr0 + r);
+        }
+    }
+    __syncthreads();  // grid lines visible; the table tile is still in flight
+
+    const float gx_lo = __ldg(pc.xs), gx_hi = __ldg(pc.xs + pc.nx), gy_lo = __ldg(pc.ys), gy_hi = __ldg(pc.ys + pc.ny);
+    bool waited = false;
+    unsigned slow_mask = 0;  // bit k: the k-th ray of this thread sits in a general cell (second pass below)
+    int k = 0;
+    for (int r = threadIdx.x; r < n_rays; r += kTmaThreads, ++k) {
+        const float vx = __ldg(ray_local + 3 * r), vy = __ldg(ray_local + 3 * r + 1), vz = __ldg(ray_local + 3 * r + 2);
+        float X, Y, Z;
+        ray_origin(f, vx, vy, vz, X, Y, Z);
+        const bool inside = (X >= gx_lo) && (X <= gx_hi) && (Y >= gy_lo) && (Y <= gy_hi);
+        float zhit = -INFINITY;
+        bool slow = false;
+        if (w.staged) {
+            const int ci = locate_in(s_xs, w.ncols, guess_cell(X, s_xs[0], pc.inv_dx), X);
+            const int cj = locate_in(s_ys, w.nrows, guess_cell(Y, s_ys[0], pc.inv_dy), Y);
+            const float lx = __fsub_rn(X, s_xs[ci]), ly = __fsub_rn(Y, s_ys[cj]);
+            if (!waited) {
+                mbar_wait(&s_bar, 0);
+                waited = true;
+            }
+            if (inside) {
+                const float4 p = s_ent[2 * (cj * w.ncols + ci)], q = s_ent[2 * (cj * w.ncols + ci) + 1];
+                slow = q.w != 0.f;
+                zhit = eval_entry(p, q, lx, ly, Z, max_d);
+            }
+        } else if (inside) {
+            const int i = locate_in(pc.xs, pc.nx, guess_cell(X, gx_lo, pc.inv_dx), X);
+            const int j = locate_in(pc.ys, pc.ny, guess_cell(Y, gy_lo, pc.inv_dy), Y);
+            const float4* __restrict__ e = pc.ent + 2 * ((size_t)j * pc.nx + i);
+            const float4 p = __ldg(e), q = __ldg(e + 1);
+            const float lx = __fsub_rn(X, __ldg(pc.xs + i)), ly = __fsub_rn(Y, __ldg(pc.ys + j));
+            slow = q.w != 0.f;
+            zhit = eval_entry(p, q, lx, ly, Z, max_d);
+        }
+        if (slow) {
+            slow_mask |= 1u << (k & 31);
+            continue;
+        }
+        write_result(f, X, Y, Z, zhit, base_offset, out + (size_t)env * out_stride + r,
+                     hits ? hits + ((size_t)env * n_rays + r) * 3 : nullptr);
+    }
+    // second pass: rays of general cells walk the home grid (kept out of the hot loop: it needs many registers)
+    if (slow_mask | (unsigned)(k > 32)) {
+        k = 0;
+        for (int r = threadIdx.x; r < n_rays; r += kTmaThreads, ++k) {
+            if (k < 32 && !((slow_mask >> k) & 1u)) continue;
+            const float vx = __ldg(ray_local + 3 * r), vy = __ldg(ray_local + 3 * r + 1), vz = __ldg(ray_local + 3 * r + 2);
+            float X, Y, Z;
+            ray_origin(f, vx, vy, vz, X, Y, Z);
+            if (k >= 32) {  // more than 32 rays per thread: the mask wrapped, re-classify this ray from global memory
+                const bool inside = (X >= gx_lo) && (X <= gx_hi) && (Y >= gy_lo) && (Y <= gy_hi);
+                if (!inside) continue;
+                const int i = locate_in(pc.xs, pc.nx, guess_cell(X, gx_lo, pc.inv_dx), X);
+                const int j = locate_in(pc.ys, pc.ny, guess_cell(Y, gy_lo, pc.inv_dy), Y);
+                if (__ldg(pc.ent + 2 * ((size_t)j * pc.nx + i) + 1).w == 0.f) continue;
+            }
+            const float zhit = cast_down_slow(g, X, Y, Z, max_d);
+            write_result(f, X, Y, Z, zhit, base_offset, out + (size_t)env * out_stride + r,
+                         hits ? hits + ((size_t)env * n_rays + r) * 3 : nullptr);
+        }
+    }
+    // every thread must have observed the completed phase before the CTA (and its shared memory) retires
+    if (w.staged && !waited) mbar_wait(&s_bar, 0);
+}
+
+int launch_height_scan_cells_tma(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local,
+                                 int n_rays, const ScanGridDev& g, const RoverPlaneCells* cells, float4 pattern_box,
+                                 float max_d, float base_offset, float* out, int out_stride, float* hits,
+                                 cudaStream_t stream) {
+    PlaneCellsDev pc{cells->xs, cells->ys, reinterpret_cast<const float4*>(cells->entries), cells->nx, cells->ny,
+                     cells->inv_dx, cells->inv_dy};
+    height_scan_cells_tma_kernel<<<n_envs, kTmaThreads, 0, stream>>>(pos_w, quat_w, ray_local, n_rays, g, pc,
+                                                                      pattern_box, max_d, base_offset, out,
+                                                                      out_stride, hits);
+    return check_launch("height_scan_cells_tma_kernel");
+}
+
+}  // namespace rover

@@ -17,6 +17,14 @@ struct ScanGridDev {
     const float4* __restrict__ rec;
 };
 
+struct PlaneCellsDev {
+    const float* __restrict__ xs;
+    const float* __restrict__ ys;
+    const float4* __restrict__ ent;
+    int nx, ny;
+    float inv_dx, inv_dy;
+};
+
 struct SensorFrame {
     float cw, sz;      // yaw-only unit quaternion (cw, 0, 0, sz)
     float px, py, pz;  // sensor position
