@@ -14,8 +14,8 @@
 
 namespace rover {
 
-constexpr int kTmaThreads = 256;
-constexpr int kWinMax = 32;  // window cells per axis held in shared memory
+constexpr int kTmaThreads = 128;  // small CTAs: >= 8 resident per SM so that prologues overlap ray phases
+constexpr int kWinMax = 28;       // window cells per axis held in shared memory (28 x 28 x 32 B = 24.5 KB)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -46,11 +46,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // index of the half-open interval [lines[i], lines[i+1]) containing v, i in [0, n-1]; lines may live in shared
-// or global memory.  `guess` is an arithmetic first guess; the loops make the answer exact for any monotone lines.
-__device__ __forceinline__ int locate_in(const float* lines, int n, int guess, float v) {
+// or global memory.  `guess` is an arithmetic first guess (exact or off by one on a uniform lattice); both bounds
+// of the guessed interval are fetched together and the fix-up loops (exact for any monotone lines) rarely run.
+// `lo_out` receives lines[i], the cell's frame origin.
+__device__ __forceinline__ int locate_in(const float* lines, int n, int guess, float v, float& lo_out) {
     int i = min(max(guess, 0), n - 1);
-    while (i > 0 && v < lines[i]) --i;
-    while (i < n - 1 && v >= lines[i + 1]) ++i;
+    float a = lines[i];
+    const float b = lines[i + 1];
+    if (v < a || v >= b) {
+        while (i > 0 && v < lines[i]) --i;
+        while (i < n - 1 && v >= lines[i + 1]) ++i;
+        a = lines[i];
+    }
+    lo_out = a;
     return i;
 }
 
@@ -90,7 +98,7 @@ __device__ __noinline__ float cast_down_slow(const ScanGridDev& g, float X, floa
 }
 
 // reference rounding chain: t -> hit.z = Z + t*(-1) -> (pos.z - hit.z) - offset ; a miss is -inf / +inf
-__device__ __forceinline__ void write_result(const SensorFrame& f, float X, float Y, float Z, float zhit,
+__device__ __forceinline__ void write_result(const SensorFrame f, float X, float Y, float Z, float zhit,
                                              float base_offset, float* __restrict__ out, float* __restrict__ hit3) {
     float h = -INFINITY, hx = INFINITY, hy = INFINITY, hz = INFINITY;
     if (zhit != -INFINITY) {
@@ -110,51 +118,80 @@ __device__ __forceinline__ void write_result(const SensorFrame& f, float X, floa
 
 struct CellWindow {
     int ic0, jr0, ncols, nrows;
-    int staged;  // 1: window in shared memory; 0: this CTA reads the table from global memory
+    float xmin, xmax, ymin, ymax;  // padded bounding box of the ray origins
 };
 
-__global__ void __launch_bounds__(kTmaThreads, 3)
+// whole-environment fallback: the table is read from global memory (window larger than the shared tile, or the
+// arithmetic window guess did not cover the pattern on a non-uniform lattice).  Rare, so kept out of line.
+__device__ __noinline__ void scan_env_from_global(const SensorFrame f, const float* __restrict__ ray_local,
+                                                   int n_rays, const ScanGridDev& g, const PlaneCellsDev& pc,
+                                                   float max_d, float base_offset, float* __restrict__ out_row,
+                                                   float* __restrict__ hits_row) {
+    const float gx_lo = __ldg(pc.xs), gx_hi = __ldg(pc.xs + pc.nx), gy_lo = __ldg(pc.ys), gy_hi = __ldg(pc.ys + pc.ny);
+    for (int r = threadIdx.x; r < n_rays; r += kTmaThreads) {
+        float X, Y, Z;
+        ray_origin(f, __ldg(ray_local + 3 * r), __ldg(ray_local + 3 * r + 1), __ldg(ray_local + 3 * r + 2), X, Y, Z);
+        float zhit = -INFINITY;
+        if ((X >= gx_lo) && (X <= gx_hi) && (Y >= gy_lo) && (Y <= gy_hi)) {
+            float x0, y0;
+            const int i = locate_in(pc.xs, pc.nx, guess_cell(X, gx_lo, pc.inv_dx), X, x0);
+            const int j = locate_in(pc.ys, pc.ny, guess_cell(Y, gy_lo, pc.inv_dy), Y, y0);
+            const float4* __restrict__ e = pc.ent + 2 * ((size_t)j * pc.nx + i);
+            const float4 p = __ldg(e), q = __ldg(e + 1);
+            zhit = (q.w == 0.f) ? eval_entry(p, q, __fsub_rn(X, x0), __fsub_rn(Y, y0), Z, max_d)
+                                : cast_down_slow(g, X, Y, Z, max_d);
+        }
+        write_result(f, X, Y, Z, zhit, base_offset, out_row + r, hits_row ? hits_row + 3 * (size_t)r : nullptr);
+    }
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 6)
 height_scan_cells_tma_kernel(const float* __restrict__ pos_w, const float* __restrict__ quat_w,
                              const float* __restrict__ ray_local, int n_rays, const __grid_constant__ ScanGridDev g,
                              const __grid_constant__ PlaneCellsDev pc, float4 pattern_box, float max_d,
                              float base_offset, float* __restrict__ out, int out_stride, float* __restrict__ hits) {
-    __shared__ __align__(128) float4 s_ent[kWinMax * kWinMax * 2];  // 32 KB: [row][col][2]
+    __shared__ __align__(128) float4 s_ent[kWinMax * kWinMax * 2];  // [row][col][2]
     __shared__ float s_xs[kWinMax + 1], s_ys[kWinMax + 1];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ SensorFrame frame_s;
     __shared__ CellWindow win_s;
+    __shared__ int s_staged;
 
     const int env = blockIdx.x;
+    float* __restrict__ out_row = out + (size_t)env * out_stride;
+    float* __restrict__ hits_row = hits ? hits + (size_t)env * n_rays * 3 : nullptr;
+    const float gx_lo = __ldg(pc.xs), gx_hi = __ldg(pc.xs + pc.nx), gy_lo = __ldg(pc.ys), gy_hi = __ldg(pc.ys + pc.ny);
     if (threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
         const SensorFrame f = make_frame(pos_w + 3 * (size_t)env, quat_w + 4 * (size_t)env);
         frame_s = f;
-        float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+        CellWindow w;
+        w.xmin = INFINITY, w.xmax = -INFINITY, w.ymin = INFINITY, w.ymax = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 4; ++c) {  // ray origins are affine in the local pattern coordinates
             float X, Y, Z;
             ray_origin(f, (c & 1) ? pattern_box.y : pattern_box.x, (c & 2) ? pattern_box.w : pattern_box.z, 0.f, X, Y, Z);
-            xmin = fminf(xmin, X), xmax = fmaxf(xmax, X), ymin = fminf(ymin, Y), ymax = fmaxf(ymax, Y);
+            w.xmin = fminf(w.xmin, X), w.xmax = fmaxf(w.xmax, X), w.ymin = fminf(w.ymin, Y), w.ymax = fmaxf(w.ymax, Y);
         }
-        const float pad = 1.0e-3f;
-        const float x_lo = __ldg(pc.xs), y_lo = __ldg(pc.ys);
-        CellWindow w;
-        w.ic0 = locate_in(pc.xs, pc.nx, guess_cell(xmin - pad, x_lo, pc.inv_dx), xmin - pad);
-        w.jr0 = locate_in(pc.ys, pc.ny, guess_cell(ymin - pad, y_lo, pc.inv_dy), ymin - pad);
-        const int ic1 = locate_in(pc.xs, pc.nx, guess_cell(xmax + pad, x_lo, pc.inv_dx), xmax + pad);
-        const int jr1 = locate_in(pc.ys, pc.ny, guess_cell(ymax + pad, y_lo, pc.inv_dy), ymax + pad);
+        const float pad = 1.0e-3f;  // >> fp32 rounding of the affine map, << a cell
+        w.xmin -= pad, w.xmax += pad, w.ymin -= pad, w.ymax += pad;
+        // arithmetic guess +- one cell; verified against the real lines once they are in shared memory
+        w.ic0 = min(max(guess_cell(w.xmin, gx_lo, pc.inv_dx) - 1, 0), pc.nx - 1);
+        w.jr0 = min(max(guess_cell(w.ymin, gy_lo, pc.inv_dy) - 1, 0), pc.ny - 1);
+        const int ic1 = min(max(guess_cell(w.xmax, gx_lo, pc.inv_dx) + 1, 0), pc.nx - 1);
+        const int jr1 = min(max(guess_cell(w.ymax, gy_lo, pc.inv_dy) + 1, 0), pc.ny - 1);
         w.ncols = ic1 - w.ic0 + 1;
         w.nrows = jr1 - w.jr0 + 1;
-        w.staged = (w.ncols <= kWinMax && w.nrows <= kWinMax) ? 1 : 0;
+        s_staged = (w.ncols <= kWinMax && w.nrows <= kWinMax) ? 1 : 0;
         win_s = w;
     }
     __syncthreads();
-    const SensorFrame f = frame_s;
     const CellWindow w = win_s;
+    const bool fits = s_staged != 0;
 
-    if (w.staged) {
+    if (fits) {
         if (threadIdx.x < 32) {
-            // warp 0: arm the barrier with the byte count, then one bulk copy per window row
+            // warp 0: arm the barrier with the byte count, then one bulk copy (UBLKCP) per window row
             const uint32_t row_bytes = (uint32_t)w.ncols * 32u;
             if (threadIdx.x == 0) mbar_expect_tx(&s_bar, row_bytes * (uint32_t)w.nrows);
             __syncwarp();
@@ -167,70 +204,66 @@ height_scan_cells_tma_kernel(const float* __restrict__ pos_w, const float* __res
             for (int r = threadIdx.x - 64; r <= w.nrows; r += 32) s_ys[r] = __ldg(pc.ys + w.jr0 + r);
         }
     }
-    __syncthreads();  // grid lines visible; the table tile is still in flight
+    __syncthreads();  // grid lines visible; the table tile may still be in flight
 
-    const float gx_lo = __ldg(pc.xs), gx_hi = __ldg(pc.xs + pc.nx), gy_lo = __ldg(pc.ys), gy_hi = __ldg(pc.ys + pc.ny);
+    // does the window really cover every ray origin that lies inside the grid?
+    bool covered = fits;
+    if (fits) {
+        covered = (s_xs[0] <= fmaxf(w.xmin, gx_lo)) && (s_xs[w.ncols] >= fminf(w.xmax, gx_hi)) &&
+                  (s_ys[0] <= fmaxf(w.ymin, gy_lo)) && (s_ys[w.nrows] >= fminf(w.ymax, gy_hi));
+    }
+    const SensorFrame f = frame_s;
+    if (!covered) {
+        if (fits) mbar_wait(&s_bar, 0);  // the tile must land before this CTA's shared memory is released
+        scan_env_from_global(f, ray_local, n_rays, g, pc, max_d, base_offset, out_row, hits_row);
+        return;
+    }
+
     bool waited = false;
     unsigned slow_mask = 0;  // bit k: the k-th ray of this thread sits in a general cell (second pass below)
     int k = 0;
     for (int r = threadIdx.x; r < n_rays; r += kTmaThreads, ++k) {
-        const float vx = __ldg(ray_local + 3 * r), vy = __ldg(ray_local + 3 * r + 1), vz = __ldg(ray_local + 3 * r + 2);
         float X, Y, Z;
-        ray_origin(f, vx, vy, vz, X, Y, Z);
+        ray_origin(f, __ldg(ray_local + 3 * r), __ldg(ray_local + 3 * r + 1), __ldg(ray_local + 3 * r + 2), X, Y, Z);
         const bool inside = (X >= gx_lo) && (X <= gx_hi) && (Y >= gy_lo) && (Y <= gy_hi);
+        float x0, y0;
+        const int ci = locate_in(s_xs, w.ncols, guess_cell(X, s_xs[0], pc.inv_dx), X, x0);
+        const int cj = locate_in(s_ys, w.nrows, guess_cell(Y, s_ys[0], pc.inv_dy), Y, y0);
+        if (!waited) {
+            mbar_wait(&s_bar, 0);
+            waited = true;
+        }
         float zhit = -INFINITY;
-        bool slow = false;
-        if (w.staged) {
-            const int ci = locate_in(s_xs, w.ncols, guess_cell(X, s_xs[0], pc.inv_dx), X);
-            const int cj = locate_in(s_ys, w.nrows, guess_cell(Y, s_ys[0], pc.inv_dy), Y);
-            const float lx = __fsub_rn(X, s_xs[ci]), ly = __fsub_rn(Y, s_ys[cj]);
-            if (!waited) {
-                mbar_wait(&s_bar, 0);
-                waited = true;
+        if (inside) {
+            const float4 p = s_ent[2 * (cj * w.ncols + ci)], q = s_ent[2 * (cj * w.ncols + ci) + 1];
+            if (q.w != 0.f) {
+                slow_mask |= 1u << (k & 31);
+                continue;
             }
-            if (inside) {
-                const float4 p = s_ent[2 * (cj * w.ncols + ci)], q = s_ent[2 * (cj * w.ncols + ci) + 1];
-                slow = q.w != 0.f;
-                zhit = eval_entry(p, q, lx, ly, Z, max_d);
-            }
-        } else if (inside) {
-            const int i = locate_in(pc.xs, pc.nx, guess_cell(X, gx_lo, pc.inv_dx), X);
-            const int j = locate_in(pc.ys, pc.ny, guess_cell(Y, gy_lo, pc.inv_dy), Y);
-            const float4* __restrict__ e = pc.ent + 2 * ((size_t)j * pc.nx + i);
-            const float4 p = __ldg(e), q = __ldg(e + 1);
-            const float lx = __fsub_rn(X, __ldg(pc.xs + i)), ly = __fsub_rn(Y, __ldg(pc.ys + j));
-            slow = q.w != 0.f;
-            zhit = eval_entry(p, q, lx, ly, Z, max_d);
+            zhit = eval_entry(p, q, __fsub_rn(X, x0), __fsub_rn(Y, y0), Z, max_d);
         }
-        if (slow) {
-            slow_mask |= 1u << (k & 31);
-            continue;
-        }
-        write_result(f, X, Y, Z, zhit, base_offset, out + (size_t)env * out_stride + r,
-                     hits ? hits + ((size_t)env * n_rays + r) * 3 : nullptr);
+        write_result(f, X, Y, Z, zhit, base_offset, out_row + r, hits_row ? hits_row + 3 * (size_t)r : nullptr);
     }
+    if (!waited) mbar_wait(&s_bar, 0);  // threads without rays: still observe the phase before the CTA retires
+
     // second pass: rays of general cells walk the home grid (kept out of the hot loop: it needs many registers)
-    if (slow_mask | (unsigned)(k > 32)) {
+    if (slow_mask != 0u || k > 32) {
         k = 0;
         for (int r = threadIdx.x; r < n_rays; r += kTmaThreads, ++k) {
             if (k < 32 && !((slow_mask >> k) & 1u)) continue;
-            const float vx = __ldg(ray_local + 3 * r), vy = __ldg(ray_local + 3 * r + 1), vz = __ldg(ray_local + 3 * r + 2);
             float X, Y, Z;
-            ray_origin(f, vx, vy, vz, X, Y, Z);
-            if (k >= 32) {  // more than 32 rays per thread: the mask wrapped, re-classify this ray from global memory
-                const bool inside = (X >= gx_lo) && (X <= gx_hi) && (Y >= gy_lo) && (Y <= gy_hi);
-                if (!inside) continue;
-                const int i = locate_in(pc.xs, pc.nx, guess_cell(X, gx_lo, pc.inv_dx), X);
-                const int j = locate_in(pc.ys, pc.ny, guess_cell(Y, gy_lo, pc.inv_dy), Y);
-                if (__ldg(pc.ent + 2 * ((size_t)j * pc.nx + i) + 1).w == 0.f) continue;
+            ray_origin(f, __ldg(ray_local + 3 * r), __ldg(ray_local + 3 * r + 1), __ldg(ray_local + 3 * r + 2), X, Y, Z);
+            if (k >= 32) {  // more than 32 rays per thread: the mask wrapped, re-classify from the shared tile
+                if (!((X >= gx_lo) && (X <= gx_hi) && (Y >= gy_lo) && (Y <= gy_hi))) continue;
+                float x0, y0;
+                const int ci = locate_in(s_xs, w.ncols, guess_cell(X, s_xs[0], pc.inv_dx), X, x0);
+                const int cj = locate_in(s_ys, w.nrows, guess_cell(Y, s_ys[0], pc.inv_dy), Y, y0);
+                if (s_ent[2 * (cj * w.ncols + ci) + 1].w == 0.f) continue;
             }
             const float zhit = cast_down_slow(g, X, Y, Z, max_d);
-            write_result(f, X, Y, Z, zhit, base_offset, out + (size_t)env * out_stride + r,
-                         hits ? hits + ((size_t)env * n_rays + r) * 3 : nullptr);
+            write_result(f, X, Y, Z, zhit, base_offset, out_row + r, hits_row ? hits_row + 3 * (size_t)r : nullptr);
         }
     }
-    // every thread must have observed the completed phase before the CTA (and its shared memory) retires
-    if (w.staged && !waited) mbar_wait(&s_bar, 0);
 }
 
 int launch_height_scan_cells_tma(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local,
