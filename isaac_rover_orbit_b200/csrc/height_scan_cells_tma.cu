@@ -145,13 +145,19 @@ __device__ __noinline__ void scan_env_from_global(const SensorFrame f, const flo
     }
 }
 
-__global__ void __launch_bounds__(kTmaThreads, 6)
+// Hot-loop helpers index the __shared__ arrays directly (shared::cta addressing, no generic pointers).
+struct LinePair {
+    float lo, hi;  // lines[i], lines[i+1]: one LDS.64 answers "is v in cell i?"
+};
+
+template <bool kHits>
+__global__ void __launch_bounds__(kTmaThreads, 8)
 height_scan_cells_tma_kernel(const float* __restrict__ pos_w, const float* __restrict__ quat_w,
                              const float* __restrict__ ray_local, int n_rays, const __grid_constant__ ScanGridDev g,
                              const __grid_constant__ PlaneCellsDev pc, float4 pattern_box, float max_d,
                              float base_offset, float* __restrict__ out, int out_stride, float* __restrict__ hits) {
     __shared__ __align__(128) float4 s_ent[kWinMax * kWinMax * 2];  // [row][col][2]
-    __shared__ float s_xs[kWinMax + 1], s_ys[kWinMax + 1];
+    __shared__ __align__(8) LinePair s_xp[kWinMax], s_yp[kWinMax];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ SensorFrame frame_s;
     __shared__ CellWindow win_s;
@@ -159,10 +165,10 @@ height_scan_cells_tma_kernel(const float* __restrict__ pos_w, const float* __res
 
     const int env = blockIdx.x;
     float* __restrict__ out_row = out + (size_t)env * out_stride;
-    float* __restrict__ hits_row = hits ? hits + (size_t)env * n_rays * 3 : nullptr;
-    const float gx_lo = __ldg(pc.xs), gx_hi = __ldg(pc.xs + pc.nx), gy_lo = __ldg(pc.ys), gy_hi = __ldg(pc.ys + pc.ny);
+    float* __restrict__ hits_row = kHits ? hits + (size_t)env * n_rays * 3 : nullptr;
     if (threadIdx.x == 0) {
         mbar_init(&s_bar, 1);
+        const float gx_lo = __ldg(pc.xs), gy_lo = __ldg(pc.ys);
         const SensorFrame f = make_frame(pos_w + 3 * (size_t)env, quat_w + 4 * (size_t)env);
         frame_s = f;
         CellWindow w;
@@ -186,65 +192,84 @@ height_scan_cells_tma_kernel(const float* __restrict__ pos_w, const float* __res
         win_s = w;
     }
     __syncthreads();
-    const CellWindow w = win_s;
+    const int ncols = win_s.ncols, nrows = win_s.nrows;
     const bool fits = s_staged != 0;
 
     if (fits) {
         if (threadIdx.x < 32) {
             // warp 0: arm the barrier with the byte count, then one bulk copy (UBLKCP) per window row
-            const uint32_t row_bytes = (uint32_t)w.ncols * 32u;
-            if (threadIdx.x == 0) mbar_expect_tx(&s_bar, row_bytes * (uint32_t)w.nrows);
+            const uint32_t row_bytes = (uint32_t)ncols * 32u;
+            if (threadIdx.x == 0) mbar_expect_tx(&s_bar, row_bytes * (uint32_t)nrows);
             __syncwarp();
-            for (int r = threadIdx.x; r < w.nrows; r += 32)
-                bulk_g2s(s_ent + (size_t)r * w.ncols * 2, pc.ent + 2 * ((size_t)(w.jr0 + r) * pc.nx + w.ic0), row_bytes,
-                         &s_bar);
+            const int ic0 = win_s.ic0, jr0 = win_s.jr0;
+            for (int r = threadIdx.x; r < nrows; r += 32)
+                bulk_g2s(s_ent + (size_t)r * ncols * 2, pc.ent + 2 * ((size_t)(jr0 + r) * pc.nx + ic0), row_bytes, &s_bar);
         } else if (threadIdx.x < 64) {
-            for (int c = threadIdx.x - 32; c <= w.ncols; c += 32) s_xs[c] = __ldg(pc.xs + w.ic0 + c);
+            const int c = threadIdx.x - 32;
+            if (c < ncols) s_xp[c] = {__ldg(pc.xs + win_s.ic0 + c), __ldg(pc.xs + win_s.ic0 + c + 1)};
         } else if (threadIdx.x < 96) {
-            for (int r = threadIdx.x - 64; r <= w.nrows; r += 32) s_ys[r] = __ldg(pc.ys + w.jr0 + r);
+            const int r = threadIdx.x - 64;
+            if (r < nrows) s_yp[r] = {__ldg(pc.ys + win_s.jr0 + r), __ldg(pc.ys + win_s.jr0 + r + 1)};
         }
     }
     __syncthreads();  // grid lines visible; the table tile may still be in flight
 
-    // does the window really cover every ray origin that lies inside the grid?
+    const SensorFrame f = frame_s;
+    // does the window cover every ray origin that lies inside the grid?  (always, on a uniform lattice)
     bool covered = fits;
     if (fits) {
-        covered = (s_xs[0] <= fmaxf(w.xmin, gx_lo)) && (s_xs[w.ncols] >= fminf(w.xmax, gx_hi)) &&
-                  (s_ys[0] <= fmaxf(w.ymin, gy_lo)) && (s_ys[w.nrows] >= fminf(w.ymax, gy_hi));
+        const float gx_lo = __ldg(pc.xs), gx_hi = __ldg(pc.xs + pc.nx), gy_lo = __ldg(pc.ys), gy_hi = __ldg(pc.ys + pc.ny);
+        covered = (s_xp[0].lo <= fmaxf(win_s.xmin, gx_lo)) && (s_xp[ncols - 1].hi >= fminf(win_s.xmax, gx_hi)) &&
+                  (s_yp[0].lo <= fmaxf(win_s.ymin, gy_lo)) && (s_yp[nrows - 1].hi >= fminf(win_s.ymax, gy_hi));
     }
-    const SensorFrame f = frame_s;
     if (!covered) {
         if (fits) mbar_wait(&s_bar, 0);  // the tile must land before this CTA's shared memory is released
         scan_env_from_global(f, ray_local, n_rays, g, pc, max_d, base_offset, out_row, hits_row);
         return;
     }
 
-    bool waited = false;
+    const float wx0 = s_xp[0].lo, wy0 = s_yp[0].lo;
+    const float wx1 = s_xp[ncols - 1].hi, wy1 = s_yp[nrows - 1].hi;  // == grid border when the window is clamped
+    const float sz2 = __fmul_rn(f.sz, 2.f);  // fl(fl(sz*v)*2) == fl(fl(2*sz)*v): scaling by 2 is exact
+    const float inv_dx = pc.inv_dx, inv_dy = pc.inv_dy;
+    const int cmax = ncols - 1, rmax = nrows - 1;
+    mbar_wait(&s_bar, 0);
+
     unsigned slow_mask = 0;  // bit k: the k-th ray of this thread sits in a general cell (second pass below)
     int k = 0;
+#pragma unroll 2
     for (int r = threadIdx.x; r < n_rays; r += kTmaThreads, ++k) {
-        float X, Y, Z;
-        ray_origin(f, __ldg(ray_local + 3 * r), __ldg(ray_local + 3 * r + 1), __ldg(ray_local + 3 * r + 2), X, Y, Z);
-        const bool inside = (X >= gx_lo) && (X <= gx_hi) && (Y >= gy_lo) && (Y <= gy_hi);
-        float x0, y0;
-        const int ci = locate_in(s_xs, w.ncols, guess_cell(X, s_xs[0], pc.inv_dx), X, x0);
-        const int cj = locate_in(s_ys, w.nrows, guess_cell(Y, s_ys[0], pc.inv_dy), Y, y0);
-        if (!waited) {
-            mbar_wait(&s_bar, 0);
-            waited = true;
-        }
-        float zhit = -INFINITY;
-        if (inside) {
-            const float4 p = s_ent[2 * (cj * w.ncols + ci)], q = s_ent[2 * (cj * w.ncols + ci) + 1];
-            if (q.w != 0.f) {
-                slow_mask |= 1u << (k & 31);
+        const float vx = __ldg(ray_local + 3 * r), vy = __ldg(ray_local + 3 * r + 1), vz = __ldg(ray_local + 3 * r + 2);
+        // ORBIT quat_apply_yaw + pos (same roundings as ray_origin())
+        const float tx = -__fmul_rn(sz2, vy), ty = __fmul_rn(sz2, vx);
+        const float X = __fadd_rn(__fadd_rn(__fadd_rn(vx, __fmul_rn(f.cw, tx)), -__fmul_rn(f.sz, ty)), f.px);
+        const float Y = __fadd_rn(__fadd_rn(__fadd_rn(vy, __fmul_rn(f.cw, ty)), __fmul_rn(f.sz, tx)), f.py);
+        const float Z = __fadd_rn(vz, f.pz);
+        int ci = min(max((int)floorf((X - wx0) * inv_dx), 0), cmax);
+        int cj = min(max((int)floorf((Y - wy0) * inv_dy), 0), rmax);
+        LinePair xp = s_xp[ci], yp = s_yp[cj];
+        if (!(X >= xp.lo && X < xp.hi && Y >= yp.lo && Y < yp.hi)) {
+            // rare: guess off by one, ray on the closed far border of the grid, or ray outside the grid
+            if (!(X >= wx0 && X <= wx1 && Y >= wy0 && Y <= wy1)) {
+                write_result(f, X, Y, Z, -INFINITY, base_offset, out_row + r, kHits ? hits_row + 3 * (size_t)r : nullptr);
                 continue;
             }
-            zhit = eval_entry(p, q, __fsub_rn(X, x0), __fsub_rn(Y, y0), Z, max_d);
+            while (ci > 0 && X < s_xp[ci].lo) --ci;
+            while (ci < cmax && X >= s_xp[ci].hi) ++ci;
+            while (cj > 0 && Y < s_yp[cj].lo) --cj;
+            while (cj < rmax && Y >= s_yp[cj].hi) ++cj;
+            xp = s_xp[ci], yp = s_yp[cj];
         }
-        write_result(f, X, Y, Z, zhit, base_offset, out_row + r, hits_row ? hits_row + 3 * (size_t)r : nullptr);
+        const int e = 2 * (cj * ncols + ci);
+        const float4 q = s_ent[e + 1];
+        if (q.w != 0.f) {
+            slow_mask |= 1u << (k & 31);
+            continue;
+        }
+        const float4 p = s_ent[e];
+        const float zhit = eval_entry(p, q, __fsub_rn(X, xp.lo), __fsub_rn(Y, yp.lo), Z, max_d);
+        write_result(f, X, Y, Z, zhit, base_offset, out_row + r, kHits ? hits_row + 3 * (size_t)r : nullptr);
     }
-    if (!waited) mbar_wait(&s_bar, 0);  // threads without rays: still observe the phase before the CTA retires
 
     // second pass: rays of general cells walk the home grid (kept out of the hot loop: it needs many registers)
     if (slow_mask != 0u || k > 32) {
@@ -253,15 +278,15 @@ height_scan_cells_tma_kernel(const float* __restrict__ pos_w, const float* __res
             if (k < 32 && !((slow_mask >> k) & 1u)) continue;
             float X, Y, Z;
             ray_origin(f, __ldg(ray_local + 3 * r), __ldg(ray_local + 3 * r + 1), __ldg(ray_local + 3 * r + 2), X, Y, Z);
-            if (k >= 32) {  // more than 32 rays per thread: the mask wrapped, re-classify from the shared tile
-                if (!((X >= gx_lo) && (X <= gx_hi) && (Y >= gy_lo) && (Y <= gy_hi))) continue;
+            if (k >= 32) {  // more than 32 rays per thread: the mask wrapped, re-classify from the table
+                if (!(X >= wx0 && X <= wx1 && Y >= wy0 && Y <= wy1)) continue;
                 float x0, y0;
-                const int ci = locate_in(s_xs, w.ncols, guess_cell(X, s_xs[0], pc.inv_dx), X, x0);
-                const int cj = locate_in(s_ys, w.nrows, guess_cell(Y, s_ys[0], pc.inv_dy), Y, y0);
-                if (s_ent[2 * (cj * w.ncols + ci) + 1].w == 0.f) continue;
+                const int i = locate_in(pc.xs, pc.nx, guess_cell(X, __ldg(pc.xs), pc.inv_dx), X, x0);
+                const int j = locate_in(pc.ys, pc.ny, guess_cell(Y, __ldg(pc.ys), pc.inv_dy), Y, y0);
+                if (__ldg(pc.ent + 2 * ((size_t)j * pc.nx + i) + 1).w == 0.f) continue;
             }
             const float zhit = cast_down_slow(g, X, Y, Z, max_d);
-            write_result(f, X, Y, Z, zhit, base_offset, out_row + r, hits_row ? hits_row + 3 * (size_t)r : nullptr);
+            write_result(f, X, Y, Z, zhit, base_offset, out_row + r, kHits ? hits_row + 3 * (size_t)r : nullptr);
         }
     }
 }
@@ -272,9 +297,12 @@ int launch_height_scan_cells_tma(const float* pos_w, const float* quat_w, int n_
                                  cudaStream_t stream) {
     PlaneCellsDev pc{cells->xs, cells->ys, reinterpret_cast<const float4*>(cells->entries), cells->nx, cells->ny,
                      cells->inv_dx, cells->inv_dy};
-    height_scan_cells_tma_kernel<<<n_envs, kTmaThreads, 0, stream>>>(pos_w, quat_w, ray_local, n_rays, g, pc,
-                                                                      pattern_box, max_d, base_offset, out,
-                                                                      out_stride, hits);
+    if (hits)
+        height_scan_cells_tma_kernel<true><<<n_envs, kTmaThreads, 0, stream>>>(
+            pos_w, quat_w, ray_local, n_rays, g, pc, pattern_box, max_d, base_offset, out, out_stride, hits);
+    else
+        height_scan_cells_tma_kernel<false><<<n_envs, kTmaThreads, 0, stream>>>(
+            pos_w, quat_w, ray_local, n_rays, g, pc, pattern_box, max_d, base_offset, out, out_stride, hits);
     return check_launch("height_scan_cells_tma_kernel");
 }
 
