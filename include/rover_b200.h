@@ -73,7 +73,8 @@ typedef struct RoverPlaneCells {
  * pattern_box (HOST, 4 floats: xmin, xmax, ymin, ymax of ray_starts_local; required by variant 1).
  * cells (HOST struct, device pointers inside; required by variant 2, may be NULL otherwise).
  * variant: 0 = direct home-grid walk, 1 = shared-memory staged home-grid walk, 2 = plane-cell fast path with
- * home-grid fallback for general cells, 3 = variant 2 with the per-env table window staged through cp.async.bulk.
+ * home-grid fallback for general cells, 3 = variant 2 with the per-env table window staged through cp.async.bulk,
+ * 4 = persistent warp-specialised pipeline (producer warp + 2-stage cp.async.bulk/mbarrier ring + consumer warps).
  * All variants produce the same heights. */
 int rover_height_scan(const float* pos_w, const float* quat_w, int32_t n_envs, const float* ray_starts_local,
                       int32_t n_rays, const float* pattern_box /* host */, const RoverScanGrid* grid /* host */,

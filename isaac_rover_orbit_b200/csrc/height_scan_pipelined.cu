@@ -1,0 +1,345 @@
+// Persistent, warp-specialised plane-cell height scan -- variant 4.
+//
+// Why (ncu on variant 3, profiles/r01_scan_*): one CTA per environment pays a serial prologue (pose load -> atan2 /
+// sincos -> window -> bulk copies -> wait, ~3 us) that even 8 resident CTAs hide only partly (17 % barrier stalls),
+// and the per-ray loads of the ray-pattern table miss a 23 KB L1 (36 % long-scoreboard stalls).
+//
+// Structure (the TMA producer / consumer ring of the Blackwell playbook, with SIMT math instead of MMA):
+//   * grid = #SMs x kCtasPerSm persistent CTAs; CTA b owns environments b, b + grid, b + 2 grid, ...
+//   * warp 0 = producer.  Every 32 environments its lanes compute 32 sensor frames at once (ORBIT yaw_quat in the
+//     reference's fp32 order).  Per environment it derives the table window from the position alone
+//     (pattern radius, no yaw needed), loads the window's grid-line pairs, publishes frame + window in the stage
+//     header, arms the stage's `full` mbarrier with the byte count and issues one cp.async.bulk per window row.
+//   * warps 1..8 = consumers.  They wait on `full`, resolve 961 rays from shared memory only (pattern table, line
+//     pairs, table entries), store the heights, and release the stage through the `empty` mbarrier.
+//   * 2 stages: the copy + prologue of environment k+1 overlaps the ray phase of environment k.
+// Rays in general cells, windows that do not fit or do not cover (non-uniform lattices) use the global-memory
+// helpers, so the staging can never change a result.
+#include "scan_common.cuh"
+
+namespace rover {
+
+constexpr int kPipeConsumerWarps = 8;
+constexpr int kPipeThreads = 32 * (1 + kPipeConsumerWarps);
+constexpr int kPipeConsumers = 32 * kPipeConsumerWarps;
+constexpr int kPipeStages = 2;
+constexpr int kPipeWin = 28;            // window cells per axis
+constexpr int kPipeCtasPerSm = 3;
+constexpr int kPipeMaxRays = 1024;      // pattern table held in shared memory (float4 per ray)
+
+struct LinePair2 {
+    float lo, hi;
+};
+
+struct StageHeader {
+    float cw, sz, px, py, pz;
+    int ncols, nrows;
+    int mode;  // 1: window staged in shared memory, 0: consumers read the table from global memory
+};
+
+struct __align__(128) PipeStage {
+    float4 ent[kPipeWin * kPipeWin * 2];
+    LinePair2 xp[kPipeWin];
+    LinePair2 yp[kPipeWin];
+    StageHeader hdr;
+};
+
+struct PipeSmem {
+    PipeStage stage[kPipeStages];
+    float4 pattern[kPipeMaxRays];
+    unsigned long long full_bar[kPipeStages];
+    unsigned long long empty_bar[kPipeStages];
+};
+
+__device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(s_addr(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     s_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(s_addr(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ int guess_col(float v, float lo, float inv_d) {
+    return (int)fminf(fmaxf(floorf((v - lo) * inv_d), -1.0e6f), 1.0e6f);
+}
+
+__device__ __forceinline__ float eval_cell(const float4 p, const float4 q, float lx, float ly, float Z, float max_d) {
+    const float E = fmaf(q.x, lx, fmaf(q.y, ly, q.z));
+    const float z = fmaf(p.w, fminf(E, 0.f), fmaf(p.x, lx, fmaf(p.y, ly, p.z)));
+    const float t = Z - z;
+    return (t >= 0.f && t < max_d) ? z : -INFINITY;
+}
+
+__device__ __forceinline__ void store_result(float pz, float X, float Y, float Z, float zhit, float base_offset,
+                                             float* __restrict__ out, float* __restrict__ hit3) {
+    float h = -INFINITY, hx = INFINITY, hy = INFINITY, hz = INFINITY;
+    if (zhit != -INFINITY) {
+        const float t = __fsub_rn(Z, zhit);  // reference rounding chain: t, hit.z = Z - t, (pos.z - hit.z) - offset
+        hz = __fsub_rn(Z, t);
+        hx = X;
+        hy = Y;
+        h = __fsub_rn(__fsub_rn(pz, hz), base_offset);
+    }
+    *out = h;
+    if (hit3) {
+        hit3[0] = hx;
+        hit3[1] = hy;
+        hit3[2] = hz;
+    }
+}
+
+// home-grid walk (general cells)
+__device__ __noinline__ float walk_home_grid(const ScanGridDev& g, float X, float Y, float Z, float max_d) {
+    float best = -INFINITY;
+    for (int l = 0; l < g.n_levels; ++l) {
+        const ScanLevelDev& L = g.level[l];
+        const int i = cell_of(X, L.ox, L.inv_cell);
+        const int j = cell_of(Y, L.oy, L.inv_cell);
+        const int j0 = max(j - g.span, 0), j1 = min(j, L.ncy - 1);
+        const int i0 = max(i - g.span, 0), i1 = min(i, L.ncx - 1);
+        for (int jj = j0; jj <= j1; ++jj) {
+            const float ly = __fsub_rn(Y, __fadd_rn(L.oy, __fmul_rn((float)jj, L.cell)));
+            const int* __restrict__ row = g.cell_start + L.start_offset + jj * L.ncx;
+            for (int ii = i0; ii <= i1; ++ii) {
+                const float lx = __fsub_rn(X, __fadd_rn(L.ox, __fmul_rn((float)ii, L.cell)));
+                const int b = __ldg(row + ii), e = __ldg(row + ii + 1);
+                for (int r = b; r < e; ++r)
+                    test_record(__ldg(g.rec + 3 * r), __ldg(g.rec + 3 * r + 1), __ldg(g.rec + 3 * r + 2), lx, ly, Z,
+                                max_d, best);
+            }
+        }
+    }
+    return best;
+}
+
+// one ray resolved from the table in global memory (fallback environments and general cells)
+__device__ __noinline__ float resolve_from_global(const ScanGridDev& g, const PlaneCellsDev& pc, float X, float Y,
+                                                   float Z, float max_d) {
+    const float gx_lo = __ldg(pc.xs), gx_hi = __ldg(pc.xs + pc.nx), gy_lo = __ldg(pc.ys), gy_hi = __ldg(pc.ys + pc.ny);
+    if (!((X >= gx_lo) && (X <= gx_hi) && (Y >= gy_lo) && (Y <= gy_hi))) return -INFINITY;
+    int i = min(max(guess_col(X, gx_lo, pc.inv_dx), 0), pc.nx - 1);
+    int j = min(max(guess_col(Y, gy_lo, pc.inv_dy), 0), pc.ny - 1);
+    while (i > 0 && X < __ldg(pc.xs + i)) --i;
+    while (i < pc.nx - 1 && X >= __ldg(pc.xs + i + 1)) ++i;
+    while (j > 0 && Y < __ldg(pc.ys + j)) --j;
+    while (j < pc.ny - 1 && Y >= __ldg(pc.ys + j + 1)) ++j;
+    const float4* __restrict__ e = pc.ent + 2 * ((size_t)j * pc.nx + i);
+    const float4 p = __ldg(e), q = __ldg(e + 1);
+    if (q.w != 0.f) return walk_home_grid(g, X, Y, Z, max_d);
+    return eval_cell(p, q, __fsub_rn(X, __ldg(pc.xs + i)), __fsub_rn(Y, __ldg(pc.ys + j)), Z, max_d);
+}
+
+template <bool kHits>
+__global__ void __launch_bounds__(kPipeThreads, kPipeCtasPerSm)
+height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __restrict__ quat_w, int n_envs,
+                             const float* __restrict__ ray_local, int n_rays, const __grid_constant__ ScanGridDev g,
+                             const __grid_constant__ PlaneCellsDev pc, float pattern_radius, float max_d,
+                             float base_offset, float* __restrict__ out, int out_stride, float* __restrict__ hits) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PipeSmem& sm = *reinterpret_cast<PipeSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_iter = (n_envs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // envs of this CTA
+
+    // ---- one-time setup: barriers + pattern table
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPipeStages; ++s) {
+            bar_init(&sm.full_bar[s], 1);
+            bar_init(&sm.empty_bar[s], kPipeConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int r = threadIdx.x; r < n_rays; r += kPipeThreads)
+        sm.pattern[r] = make_float4(__ldg(ray_local + 3 * r), __ldg(ray_local + 3 * r + 1), __ldg(ray_local + 3 * r + 2), 0.f);
+    __syncthreads();
+
+    const float gx_lo = __ldg(pc.xs), gx_hi = __ldg(pc.xs + pc.nx), gy_lo = __ldg(pc.ys), gy_hi = __ldg(pc.ys + pc.ny);
+
+    if (warp == 0) {
+        // =============================== producer ===============================
+        float fcw = 0.f, fsz = 0.f, fpx = 0.f, fpy = 0.f, fpz = 0.f;
+        for (int it = 0; it < n_iter; ++it) {
+            if ((it & 31) == 0) {  // 32 sensor frames at once, one per lane
+                const int e = (int)blockIdx.x + (it + lane) * (int)gridDim.x;
+                if (e < n_envs) {
+                    const SensorFrame f = make_frame(pos_w + 3 * (size_t)e, quat_w + 4 * (size_t)e);
+                    fcw = f.cw, fsz = f.sz, fpx = f.px, fpy = f.py, fpz = f.pz;
+                }
+            }
+            const int src = it & 31;
+            const float cw = __shfl_sync(0xffffffffu, fcw, src), sz = __shfl_sync(0xffffffffu, fsz, src);
+            const float px = __shfl_sync(0xffffffffu, fpx, src), py = __shfl_sync(0xffffffffu, fpy, src);
+            const float pz = __shfl_sync(0xffffffffu, fpz, src);
+            const int s = it % kPipeStages;
+            const uint32_t ph = (uint32_t)(it / kPipeStages) & 1u;
+            PipeStage& st = sm.stage[s];
+            bar_wait(&sm.empty_bar[s], ph ^ 1u);  // consumers have drained this stage
+
+            // window from the position alone: every ray origin lies within pattern_radius of (px, py)
+            const float xmin = px - pattern_radius, xmax = px + pattern_radius;
+            const float ymin = py - pattern_radius, ymax = py + pattern_radius;
+            const int ic0 = min(max(guess_col(xmin, gx_lo, pc.inv_dx) - 1, 0), pc.nx - 1);
+            const int jr0 = min(max(guess_col(ymin, gy_lo, pc.inv_dy) - 1, 0), pc.ny - 1);
+            const int ic1 = min(max(guess_col(xmax, gx_lo, pc.inv_dx) + 1, 0), pc.nx - 1);
+            const int jr1 = min(max(guess_col(ymax, gy_lo, pc.inv_dy) + 1, 0), pc.ny - 1);
+            const int ncols = ic1 - ic0 + 1, nrows = jr1 - jr0 + 1;
+            bool ok = (ncols <= kPipeWin) && (nrows <= kPipeWin);
+            if (ok) {
+                if (lane < ncols) st.xp[lane] = {__ldg(pc.xs + ic0 + lane), __ldg(pc.xs + ic0 + lane + 1)};
+                if (lane < nrows) st.yp[lane] = {__ldg(pc.ys + jr0 + lane), __ldg(pc.ys + jr0 + lane + 1)};
+                __syncwarp();
+                // the arithmetic guess is exact +-1 on a uniform lattice; verify coverage for any other lattice
+                ok = (st.xp[0].lo <= fmaxf(xmin, gx_lo)) && (st.xp[ncols - 1].hi >= fminf(xmax, gx_hi)) &&
+                     (st.yp[0].lo <= fmaxf(ymin, gy_lo)) && (st.yp[nrows - 1].hi >= fminf(ymax, gy_hi));
+            }
+            if (lane == 0) st.hdr = {cw, sz, px, py, pz, ncols, nrows, ok ? 1 : 0};
+            __syncwarp();
+            if (ok) {
+                const uint32_t row_bytes = (uint32_t)ncols * 32u;
+                if (lane == 0) bar_arrive_expect_tx(&sm.full_bar[s], row_bytes * (uint32_t)nrows);
+                __syncwarp();
+                for (int r = lane; r < nrows; r += 32)
+                    bulk_copy_g2s(st.ent + (size_t)r * ncols * 2, pc.ent + 2 * ((size_t)(jr0 + r) * pc.nx + ic0),
+                                  row_bytes, &sm.full_bar[s]);
+            } else if (lane == 0) {
+                bar_arrive(&sm.full_bar[s]);
+            }
+        }
+    } else {
+        // =============================== consumers ===============================
+        const int t = threadIdx.x - 32;
+        for (int it = 0; it < n_iter; ++it) {
+            const int env = (int)blockIdx.x + it * (int)gridDim.x;
+            const int s = it % kPipeStages;
+            const uint32_t ph = (uint32_t)(it / kPipeStages) & 1u;
+            PipeStage& st = sm.stage[s];
+            bar_wait(&sm.full_bar[s], ph);
+            const StageHeader h = st.hdr;
+            float* __restrict__ out_row = out + (size_t)env * out_stride;
+            float* __restrict__ hits_row = kHits ? hits + (size_t)env * n_rays * 3 : nullptr;
+            const float sz2 = __fmul_rn(h.sz, 2.f);  // fl(fl(sz*v)*2) == fl(fl(2*sz)*v): scaling by 2 is exact
+            if (h.mode == 1) {
+                const int cmax = h.ncols - 1, rmax = h.nrows - 1;
+                const float wx0 = st.xp[0].lo, wy0 = st.yp[0].lo, wx1 = st.xp[cmax].hi, wy1 = st.yp[rmax].hi;
+                unsigned slow_mask = 0;
+                int k = 0;
+#pragma unroll 2
+                for (int r = t; r < n_rays; r += kPipeConsumers, ++k) {
+                    const float4 v = sm.pattern[r];
+                    // ORBIT quat_apply_yaw + pos, same roundings as ray_origin()
+                    const float tx = -__fmul_rn(sz2, v.y), ty = __fmul_rn(sz2, v.x);
+                    const float X = __fadd_rn(__fadd_rn(__fadd_rn(v.x, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
+                    const float Y = __fadd_rn(__fadd_rn(__fadd_rn(v.y, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
+                    const float Z = __fadd_rn(v.z, h.pz);
+                    int ci = min(max((int)floorf((X - wx0) * pc.inv_dx), 0), cmax);
+                    int cj = min(max((int)floorf((Y - wy0) * pc.inv_dy), 0), rmax);
+                    LinePair2 xp = st.xp[ci], yp = st.yp[cj];
+                    if (!(X >= xp.lo && X < xp.hi && Y >= yp.lo && Y < yp.hi)) {
+                        // rare: guess off by one, ray on the closed far border, or ray outside the grid
+                        if (!(X >= wx0 && X <= wx1 && Y >= wy0 && Y <= wy1)) {
+                            store_result(h.pz, X, Y, Z, -INFINITY, base_offset, out_row + r,
+                                         kHits ? hits_row + 3 * (size_t)r : nullptr);
+                            continue;
+                        }
+                        while (ci > 0 && X < st.xp[ci].lo) --ci;
+                        while (ci < cmax && X >= st.xp[ci].hi) ++ci;
+                        while (cj > 0 && Y < st.yp[cj].lo) --cj;
+                        while (cj < rmax && Y >= st.yp[cj].hi) ++cj;
+                        xp = st.xp[ci], yp = st.yp[cj];
+                    }
+                    const int e = 2 * (cj * h.ncols + ci);
+                    const float4 q = st.ent[e + 1];
+                    if (q.w != 0.f) {
+                        slow_mask |= 1u << (k & 31);
+                        continue;
+                    }
+                    const float zhit = eval_cell(st.ent[e], q, __fsub_rn(X, xp.lo), __fsub_rn(Y, yp.lo), Z, max_d);
+                    store_result(h.pz, X, Y, Z, zhit, base_offset, out_row + r, kHits ? hits_row + 3 * (size_t)r : nullptr);
+                }
+                if (slow_mask != 0u) {  // general cells: second pass through the home grid (k < 32 by construction)
+                    k = 0;
+                    for (int r = t; r < n_rays; r += kPipeConsumers, ++k) {
+                        if (!((slow_mask >> k) & 1u)) continue;
+                        const float4 v = sm.pattern[r];
+                        const float tx = -__fmul_rn(sz2, v.y), ty = __fmul_rn(sz2, v.x);
+                        const float X = __fadd_rn(__fadd_rn(__fadd_rn(v.x, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
+                        const float Y = __fadd_rn(__fadd_rn(__fadd_rn(v.y, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
+                        const float Z = __fadd_rn(v.z, h.pz);
+                        const float zhit = walk_home_grid(g, X, Y, Z, max_d);
+                        store_result(h.pz, X, Y, Z, zhit, base_offset, out_row + r,
+                                     kHits ? hits_row + 3 * (size_t)r : nullptr);
+                    }
+                }
+            } else {
+                for (int r = t; r < n_rays; r += kPipeConsumers) {
+                    const float4 v = sm.pattern[r];
+                    const float tx = -__fmul_rn(sz2, v.y), ty = __fmul_rn(sz2, v.x);
+                    const float X = __fadd_rn(__fadd_rn(__fadd_rn(v.x, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
+                    const float Y = __fadd_rn(__fadd_rn(__fadd_rn(v.y, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
+                    const float Z = __fadd_rn(v.z, h.pz);
+                    const float zhit = resolve_from_global(g, pc, X, Y, Z, max_d);
+                    store_result(h.pz, X, Y, Z, zhit, base_offset, out_row + r, kHits ? hits_row + 3 * (size_t)r : nullptr);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) bar_arrive(&sm.empty_bar[s]);  // this warp is done reading the stage
+        }
+    }
+}
+
+int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local,
+                                 int n_rays, const ScanGridDev& g, const RoverPlaneCells* cells, float4 pattern_box,
+                                 float max_d, float base_offset, float* out, int out_stride, float* hits,
+                                 cudaStream_t stream) {
+    ROVER_CHECK(n_rays <= kPipeMaxRays * 32, "height_scan_pipelined: more than 32768 rays per env is not supported");
+    ROVER_CHECK(n_rays <= kPipeMaxRays, "height_scan_pipelined: pattern larger than %d rays: use variant 2 or 3",
+                kPipeMaxRays);
+    static int n_sms = 0;
+    static bool configured = false;
+    if (!configured) {
+        int dev = 0;
+        ROVER_CUDA(cudaGetDevice(&dev));
+        ROVER_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+        ROVER_CUDA(cudaFuncSetAttribute(height_scan_pipelined_kernel<false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem)));
+        ROVER_CUDA(cudaFuncSetAttribute(height_scan_pipelined_kernel<true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem)));
+        configured = true;
+    }
+    PlaneCellsDev pc{cells->xs, cells->ys, reinterpret_cast<const float4*>(cells->entries), cells->nx, cells->ny,
+                     cells->inv_dx, cells->inv_dy};
+    // every ray origin lies within this distance of the sensor position (the yaw rotation preserves norms)
+    const float rx = fmaxf(fabsf(pattern_box.x), fabsf(pattern_box.y)), ry = fmaxf(fabsf(pattern_box.z), fabsf(pattern_box.w));
+    const float radius = sqrtf(rx * rx + ry * ry) * 1.0001f + 1.0e-3f;
+    const int grid = n_envs < n_sms * kPipeCtasPerSm ? n_envs : n_sms * kPipeCtasPerSm;
+    if (hits)
+        height_scan_pipelined_kernel<true><<<grid, kPipeThreads, sizeof(PipeSmem), stream>>>(
+            pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, radius, max_d, base_offset, out, out_stride, hits);
+    else
+        height_scan_pipelined_kernel<false><<<grid, kPipeThreads, sizeof(PipeSmem), stream>>>(
+            pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, radius, max_d, base_offset, out, out_stride, hits);
+    return check_launch("height_scan_pipelined_kernel");
+}
+
+}  // namespace rover
