@@ -26,6 +26,7 @@ constexpr int kPipeStages = 2;
 constexpr int kPipeWin = 28;            // window cells per axis
 constexpr int kPipeCtasPerSm = 3;
 constexpr int kPipeMaxRays = 1024;      // pattern table held in shared memory (float4 per ray)
+constexpr int kPipeMaxLines = 1024;     // grid lines per axis held in shared memory (else read from global)
 
 struct LinePair2 {
     float lo, hi;
@@ -47,6 +48,8 @@ struct __align__(128) PipeStage {
 struct PipeSmem {
     PipeStage stage[kPipeStages];
     float4 pattern[kPipeMaxRays];
+    float xs[kPipeMaxLines + 1];
+    float ys[kPipeMaxLines + 1];
     unsigned long long full_bar[kPipeStages];
     unsigned long long empty_bar[kPipeStages];
 };
@@ -172,6 +175,11 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
     }
     for (int r = threadIdx.x; r < n_rays; r += kPipeThreads)
         sm.pattern[r] = make_float4(__ldg(ray_local + 3 * r), __ldg(ray_local + 3 * r + 1), __ldg(ray_local + 3 * r + 2), 0.f);
+    const bool lines_in_smem = (pc.nx <= kPipeMaxLines) && (pc.ny <= kPipeMaxLines);
+    if (lines_in_smem) {
+        for (int i = threadIdx.x; i <= pc.nx; i += kPipeThreads) sm.xs[i] = __ldg(pc.xs + i);
+        for (int i = threadIdx.x; i <= pc.ny; i += kPipeThreads) sm.ys[i] = __ldg(pc.ys + i);
+    }
     __syncthreads();
 
     const float gx_lo = __ldg(pc.xs), gx_hi = __ldg(pc.xs + pc.nx), gy_lo = __ldg(pc.ys), gy_hi = __ldg(pc.ys + pc.ny);
@@ -206,8 +214,13 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
             const int ncols = ic1 - ic0 + 1, nrows = jr1 - jr0 + 1;
             bool ok = (ncols <= kPipeWin) && (nrows <= kPipeWin);
             if (ok) {
-                if (lane < ncols) st.xp[lane] = {__ldg(pc.xs + ic0 + lane), __ldg(pc.xs + ic0 + lane + 1)};
-                if (lane < nrows) st.yp[lane] = {__ldg(pc.ys + jr0 + lane), __ldg(pc.ys + jr0 + lane + 1)};
+                if (lines_in_smem) {
+                    if (lane < ncols) st.xp[lane] = {sm.xs[ic0 + lane], sm.xs[ic0 + lane + 1]};
+                    if (lane < nrows) st.yp[lane] = {sm.ys[jr0 + lane], sm.ys[jr0 + lane + 1]};
+                } else {
+                    if (lane < ncols) st.xp[lane] = {__ldg(pc.xs + ic0 + lane), __ldg(pc.xs + ic0 + lane + 1)};
+                    if (lane < nrows) st.yp[lane] = {__ldg(pc.ys + jr0 + lane), __ldg(pc.ys + jr0 + lane + 1)};
+                }
                 __syncwarp();
                 // the arithmetic guess is exact +-1 on a uniform lattice; verify coverage for any other lattice
                 ok = (st.xp[0].lo <= fmaxf(xmin, gx_lo)) && (st.xp[ncols - 1].hi >= fminf(xmax, gx_hi)) &&
@@ -242,53 +255,59 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
             if (h.mode == 1) {
                 const int cmax = h.ncols - 1, rmax = h.nrows - 1;
                 const float wx0 = st.xp[0].lo, wy0 = st.yp[0].lo, wx1 = st.xp[cmax].hi, wy1 = st.yp[rmax].hi;
-                unsigned slow_mask = 0;
-                int k = 0;
-#pragma unroll 2
-                for (int r = t; r < n_rays; r += kPipeConsumers, ++k) {
-                    const float4 v = sm.pattern[r];
-                    // ORBIT quat_apply_yaw + pos, same roundings as ray_origin()
-                    const float tx = -__fmul_rn(sz2, v.y), ty = __fmul_rn(sz2, v.x);
-                    const float X = __fadd_rn(__fadd_rn(__fadd_rn(v.x, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
-                    const float Y = __fadd_rn(__fadd_rn(__fadd_rn(v.y, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
-                    const float Z = __fadd_rn(v.z, h.pz);
-                    int ci = min(max((int)floorf((X - wx0) * pc.inv_dx), 0), cmax);
-                    int cj = min(max((int)floorf((Y - wy0) * pc.inv_dy), 0), rmax);
-                    LinePair2 xp = st.xp[ci], yp = st.yp[cj];
-                    if (!(X >= xp.lo && X < xp.hi && Y >= yp.lo && Y < yp.hi)) {
-                        // rare: guess off by one, ray on the closed far border, or ray outside the grid
-                        if (!(X >= wx0 && X <= wx1 && Y >= wy0 && Y <= wy1)) {
-                            store_result(h.pz, X, Y, Z, -INFINITY, base_offset, out_row + r,
-                                         kHits ? hits_row + 3 * (size_t)r : nullptr);
-                            continue;
-                        }
-                        while (ci > 0 && X < st.xp[ci].lo) --ci;
-                        while (ci < cmax && X >= st.xp[ci].hi) ++ci;
-                        while (cj > 0 && Y < st.yp[cj].lo) --cj;
-                        while (cj < rmax && Y >= st.yp[cj].hi) ++cj;
-                        xp = st.xp[ci], yp = st.yp[cj];
-                    }
-                    const int e = 2 * (cj * h.ncols + ci);
-                    const float4 q = st.ent[e + 1];
-                    if (q.w != 0.f) {
-                        slow_mask |= 1u << (k & 31);
-                        continue;
-                    }
-                    const float zhit = eval_cell(st.ent[e], q, __fsub_rn(X, xp.lo), __fsub_rn(Y, yp.lo), Z, max_d);
-                    store_result(h.pz, X, Y, Z, zhit, base_offset, out_row + r, kHits ? hits_row + 3 * (size_t)r : nullptr);
-                }
-                if (slow_mask != 0u) {  // general cells: second pass through the home grid (k < 32 by construction)
-                    k = 0;
-                    for (int r = t; r < n_rays; r += kPipeConsumers, ++k) {
-                        if (!((slow_mask >> k) & 1u)) continue;
-                        const float4 v = sm.pattern[r];
+                const float inv_dx = pc.inv_dx, inv_dy = pc.inv_dy;
+                for (int r0 = 0; r0 < n_rays; r0 += 4 * kPipeConsumers) {
+                    // branch-free body over 4 rays: every load uses a clamped (always valid) index, stores are
+                    // predicated, anything unusual is deferred -> the four dependency chains interleave (ILP)
+                    unsigned defer = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = r0 + u * kPipeConsumers + t;
+                        const bool valid = r < n_rays;
+                        const float4 v = sm.pattern[valid ? r : 0];
+                        // ORBIT quat_apply_yaw + pos, same roundings as ray_origin()
                         const float tx = -__fmul_rn(sz2, v.y), ty = __fmul_rn(sz2, v.x);
                         const float X = __fadd_rn(__fadd_rn(__fadd_rn(v.x, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
                         const float Y = __fadd_rn(__fadd_rn(__fadd_rn(v.y, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
                         const float Z = __fadd_rn(v.z, h.pz);
-                        const float zhit = walk_home_grid(g, X, Y, Z, max_d);
-                        store_result(h.pz, X, Y, Z, zhit, base_offset, out_row + r,
-                                     kHits ? hits_row + 3 * (size_t)r : nullptr);
+                        const int ci = min(max(__float2int_rd((X - wx0) * inv_dx), 0), cmax);
+                        const int cj = min(max(__float2int_rd((Y - wy0) * inv_dy), 0), rmax);
+                        const LinePair2 xp = st.xp[ci], yp = st.yp[cj];
+                        const int e = 2 * (cj * h.ncols + ci);
+                        const float4 q = st.ent[e + 1], p = st.ent[e];
+                        const bool fast = (X >= xp.lo) & (X < xp.hi) & (Y >= yp.lo) & (Y < yp.hi) & (q.w == 0.f);
+                        const float zhit = eval_cell(p, q, __fsub_rn(X, xp.lo), __fsub_rn(Y, yp.lo), Z, max_d);
+                        if (valid && fast)
+                            store_result(h.pz, X, Y, Z, zhit, base_offset, out_row + r, kHits ? hits_row + 3 * (size_t)r : nullptr);
+                        defer |= (valid && !fast) ? (1u << u) : 0u;
+                    }
+                    // rare: cell guess off by one, ray on the closed far border or outside the grid, general cell
+                    if (defer != 0u) {
+                        for (int u = 0; u < 4; ++u) {
+                            if (!((defer >> u) & 1u)) continue;
+                            const int r = r0 + u * kPipeConsumers + t;
+                            const float4 v = sm.pattern[r];
+                            const float tx = -__fmul_rn(sz2, v.y), ty = __fmul_rn(sz2, v.x);
+                            const float X = __fadd_rn(__fadd_rn(__fadd_rn(v.x, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
+                            const float Y = __fadd_rn(__fadd_rn(__fadd_rn(v.y, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
+                            const float Z = __fadd_rn(v.z, h.pz);
+                            float zhit = -INFINITY;
+                            if (X >= wx0 && X <= wx1 && Y >= wy0 && Y <= wy1) {
+                                int ci = min(max(__float2int_rd((X - wx0) * inv_dx), 0), cmax);
+                                int cj = min(max(__float2int_rd((Y - wy0) * inv_dy), 0), rmax);
+                                while (ci > 0 && X < st.xp[ci].lo) --ci;
+                                while (ci < cmax && X >= st.xp[ci].hi) ++ci;
+                                while (cj > 0 && Y < st.yp[cj].lo) --cj;
+                                while (cj < rmax && Y >= st.yp[cj].hi) ++cj;
+                                const int e = 2 * (cj * h.ncols + ci);
+                                const float4 q = st.ent[e + 1];
+                                zhit = (q.w == 0.f) ? eval_cell(st.ent[e], q, __fsub_rn(X, st.xp[ci].lo),
+                                                                __fsub_rn(Y, st.yp[cj].lo), Z, max_d)
+                                                    : walk_home_grid(g, X, Y, Z, max_d);
+                            }
+                            store_result(h.pz, X, Y, Z, zhit, base_offset, out_row + r,
+                                         kHits ? hits_row + 3 * (size_t)r : nullptr);
+                        }
                     }
                 }
             } else {
@@ -312,7 +331,6 @@ int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_
                                  int n_rays, const ScanGridDev& g, const RoverPlaneCells* cells, float4 pattern_box,
                                  float max_d, float base_offset, float* out, int out_stride, float* hits,
                                  cudaStream_t stream) {
-    ROVER_CHECK(n_rays <= kPipeMaxRays * 32, "height_scan_pipelined: more than 32768 rays per env is not supported");
     ROVER_CHECK(n_rays <= kPipeMaxRays, "height_scan_pipelined: pattern larger than %d rays: use variant 2 or 3",
                 kPipeMaxRays);
     static int n_sms = 0;
