@@ -5,26 +5,30 @@
 // and the per-ray loads of the ray-pattern table miss a 23 KB L1 (36 % long-scoreboard stalls).
 //
 // Structure (the TMA producer / consumer ring of the Blackwell playbook, with SIMT math instead of MMA):
-//   * grid = #SMs x kCtasPerSm persistent CTAs; CTA b owns environments b, b + grid, b + 2 grid, ...
+//   * grid = #SMs persistent CTAs (one per SM, 800 threads); CTA b owns environments b, b + grid, b + 2 grid, ...
 //   * warp 0 = producer.  Every 32 environments its lanes compute 32 sensor frames at once (ORBIT yaw_quat in the
 //     reference's fp32 order).  Per environment it derives the table window from the position alone
 //     (pattern radius, no yaw needed), loads the window's grid-line pairs, publishes frame + window in the stage
 //     header, arms the stage's `full` mbarrier with the byte count and issues one cp.async.bulk per window row.
-//   * warps 1..8 = consumers.  They wait on `full`, resolve 961 rays from shared memory only (pattern table, line
-//     pairs, table entries), store the heights, and release the stage through the `empty` mbarrier.
-//   * 2 stages: the copy + prologue of environment k+1 overlaps the ray phase of environment k.
+//   * warps 1..24 = three consumer groups of 8 warps; group q takes the CTA's environments q, q+3, ...  A group waits
+//     on `full`, resolves 961 rays from shared memory only (pattern table, line pairs, table entries), stores the
+//     heights, and releases the stage through the `empty` mbarrier.
+//   * 9 stages of 22 KB: up to nine table windows are in flight per SM, so the HBM/L2 latency of a window
+//     (~2 us cold) is hidden behind the ray phases of the environments ahead of it; pattern table and grid lines
+//     are loaded once per SM.
 // Rays in general cells, windows that do not fit or do not cover (non-uniform lattices) use the global-memory
 // helpers, so the staging can never change a result.
 #include "scan_common.cuh"
 
 namespace rover {
 
-constexpr int kPipeConsumerWarps = 8;
-constexpr int kPipeThreads = 32 * (1 + kPipeConsumerWarps);
+constexpr int kPipeGroups = 3;          // consumer groups; group q resolves environments it = q, q+3, ... of the CTA
+constexpr int kPipeConsumerWarps = 8;   // warps per consumer group
 constexpr int kPipeConsumers = 32 * kPipeConsumerWarps;
-constexpr int kPipeStages = 2;
-constexpr int kPipeWin = 28;            // window cells per axis
-constexpr int kPipeCtasPerSm = 3;
+constexpr int kPipeThreads = 32 * (1 + kPipeGroups * kPipeConsumerWarps);
+constexpr int kPipeStages = 9;          // ring depth (multiple of kPipeGroups: a stage always serves the same group)
+constexpr int kPipeWin = 26;            // window cells per axis
+constexpr int kPipeCtasPerSm = 1;
 constexpr int kPipeMaxRays = 1024;      // pattern table held in shared memory (float4 per ray)
 constexpr int kPipeMaxLines = 1024;     // grid lines per axis held in shared memory (else read from global)
 
@@ -53,6 +57,9 @@ struct PipeSmem {
     unsigned long long full_bar[kPipeStages];
     unsigned long long empty_bar[kPipeStages];
 };
+
+static_assert(kPipeStages % kPipeGroups == 0, "a stage must always be consumed by the same group");
+static_assert(sizeof(PipeSmem) <= 227 * 1024, "PipeSmem exceeds the shared memory of one SM");
 
 __device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -241,8 +248,9 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
         }
     } else {
         // =============================== consumers ===============================
-        const int t = threadIdx.x - 32;
-        for (int it = 0; it < n_iter; ++it) {
+        const int group = (warp - 1) / kPipeConsumerWarps;
+        const int t = threadIdx.x - 32 - group * kPipeConsumers;
+        for (int it = group; it < n_iter; it += kPipeGroups) {
             const int env = (int)blockIdx.x + it * (int)gridDim.x;
             const int s = it % kPipeStages;
             const uint32_t ph = (uint32_t)(it / kPipeStages) & 1u;
