@@ -18,6 +18,8 @@
 //     are loaded once per SM.
 // Rays in general cells, windows that do not fit or do not cover (non-uniform lattices) use the global-memory
 // helpers, so the staging can never change a result.
+#include <cuda.h>  // CUtensorMap types only; the encoder is resolved at run time (no link dependency on libcuda)
+
 #include "scan_common.cuh"
 
 namespace rover {
@@ -84,11 +86,14 @@ __device__ __forceinline__ void bar_wait(unsigned long long* bar, uint32_t parit
             : "memory");
     }
 }
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     s_addr(dst)),
-                 "l"(src), "r"(bytes), "r"(s_addr(bar))
-                 : "memory");
+// one 2-D TMA tile load (UTMALDG): box = kPipeWin rows x kPipeWin cells of the table, starting at cell (col, row)
+__device__ __forceinline__ void tma_load_window(void* dst, const CUtensorMap* tmap, int col, int row,
+                                                unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(s_addr(dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(col * 8), "r"(row), "r"(s_addr(bar))
+        : "memory");
 }
 
 __device__ __forceinline__ int guess_col(float v, float lo, float inv_d) {
@@ -165,7 +170,8 @@ template <bool kHits>
 __global__ void __launch_bounds__(kPipeThreads, kPipeCtasPerSm)
 height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __restrict__ quat_w, int n_envs,
                              const float* __restrict__ ray_local, int n_rays, const __grid_constant__ ScanGridDev g,
-                             const __grid_constant__ PlaneCellsDev pc, float pattern_radius, float max_d,
+                             const __grid_constant__ PlaneCellsDev pc, const __grid_constant__ CUtensorMap tmap,
+                             float pattern_radius, float max_d,
                              float base_offset, float* __restrict__ out, int out_stride, float* __restrict__ hits) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PipeSmem& sm = *reinterpret_cast<PipeSmem*>(smem_raw);
@@ -235,15 +241,14 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
             }
             if (lane == 0) st.hdr = {cw, sz, px, py, pz, ncols, nrows, ok ? 1 : 0};
             __syncwarp();
-            if (ok) {
-                const uint32_t row_bytes = (uint32_t)ncols * 32u;
-                if (lane == 0) bar_arrive_expect_tx(&sm.full_bar[s], row_bytes * (uint32_t)nrows);
-                __syncwarp();
-                for (int r = lane; r < nrows; r += 32)
-                    bulk_copy_g2s(st.ent + (size_t)r * ncols * 2, pc.ent + 2 * ((size_t)(jr0 + r) * pc.nx + ic0),
-                                  row_bytes, &sm.full_bar[s]);
-            } else if (lane == 0) {
-                bar_arrive(&sm.full_bar[s]);
+            if (lane == 0) {
+                if (ok) {
+                    // the box is always kPipeWin x kPipeWin cells; cells beyond the table are zero-filled and never read
+                    bar_arrive_expect_tx(&sm.full_bar[s], (uint32_t)(kPipeWin * kPipeWin * 32));
+                    tma_load_window(st.ent, &tmap, ic0, jr0, &sm.full_bar[s]);
+                } else {
+                    bar_arrive(&sm.full_bar[s]);
+                }
             }
         }
     } else {
@@ -281,7 +286,7 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
                         const int ci = min(max(__float2int_rd((X - wx0) * inv_dx), 0), cmax);
                         const int cj = min(max(__float2int_rd((Y - wy0) * inv_dy), 0), rmax);
                         const LinePair2 xp = st.xp[ci], yp = st.yp[cj];
-                        const int e = 2 * (cj * h.ncols + ci);
+                        const int e = 2 * (cj * kPipeWin + ci);
                         const float4 q = st.ent[e + 1], p = st.ent[e];
                         const bool fast = (X >= xp.lo) & (X < xp.hi) & (Y >= yp.lo) & (Y < yp.hi) & (q.w == 0.f);
                         const float zhit = eval_cell(p, q, __fsub_rn(X, xp.lo), __fsub_rn(Y, yp.lo), Z, max_d);
@@ -307,7 +312,7 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
                                 while (ci < cmax && X >= st.xp[ci].hi) ++ci;
                                 while (cj > 0 && Y < st.yp[cj].lo) --cj;
                                 while (cj < rmax && Y >= st.yp[cj].hi) ++cj;
-                                const int e = 2 * (cj * h.ncols + ci);
+                                const int e = 2 * (cj * kPipeWin + ci);
                                 const float4 q = st.ent[e + 1];
                                 zhit = (q.w == 0.f) ? eval_cell(st.ent[e], q, __fsub_rn(X, st.xp[ci].lo),
                                                                 __fsub_rn(Y, st.yp[cj].lo), Z, max_d)
@@ -341,6 +346,10 @@ int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_
                                  cudaStream_t stream) {
     ROVER_CHECK(n_rays <= kPipeMaxRays, "height_scan_pipelined: pattern larger than %d rays: use variant 2 or 3",
                 kPipeMaxRays);
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn encode = nullptr;
     static int n_sms = 0;
     static bool configured = false;
     if (!configured) {
@@ -351,7 +360,25 @@ int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem)));
         ROVER_CUDA(cudaFuncSetAttribute(height_scan_pipelined_kernel<true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem)));
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        ROVER_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        ROVER_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess,
+                    "height_scan_pipelined: cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
         configured = true;
+    }
+    // 2-D tensor map over the plane-cell table: rows of nx cells x 8 floats; box = kPipeWin x kPipeWin cells
+    alignas(64) CUtensorMap tmap;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)cells->nx * 8ull, (cuuint64_t)cells->ny};
+        const cuuint64_t gstride[1] = {(cuuint64_t)cells->nx * 32ull};
+        const cuuint32_t box[2] = {(cuuint32_t)kPipeWin * 8u, (cuuint32_t)kPipeWin};
+        const cuuint32_t estride[2] = {1u, 1u};
+        const CUresult rc = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(cells->entries), gdim,
+                                   gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        ROVER_CHECK(rc == CUDA_SUCCESS, "height_scan_pipelined: cuTensorMapEncodeTiled failed (%d)", (int)rc);
     }
     PlaneCellsDev pc{cells->xs, cells->ys, reinterpret_cast<const float4*>(cells->entries), cells->nx, cells->ny,
                      cells->inv_dx, cells->inv_dy};
@@ -361,10 +388,10 @@ int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_
     const int grid = n_envs < n_sms * kPipeCtasPerSm ? n_envs : n_sms * kPipeCtasPerSm;
     if (hits)
         height_scan_pipelined_kernel<true><<<grid, kPipeThreads, sizeof(PipeSmem), stream>>>(
-            pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, radius, max_d, base_offset, out, out_stride, hits);
+            pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, tmap, radius, max_d, base_offset, out, out_stride, hits);
     else
         height_scan_pipelined_kernel<false><<<grid, kPipeThreads, sizeof(PipeSmem), stream>>>(
-            pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, radius, max_d, base_offset, out, out_stride, hits);
+            pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, tmap, radius, max_d, base_offset, out, out_stride, hits);
     return check_launch("height_scan_pipelined_kernel");
 }
 
