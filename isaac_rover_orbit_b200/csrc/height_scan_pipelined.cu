@@ -186,6 +186,15 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // the producer warp computes its first 32 sensor frames while the other warps fill the shared tables
+    float fcw = 0.f, fsz = 0.f, fpx = 0.f, fpy = 0.f, fpz = 0.f;
+    if (warp == 0) {
+        const int e = (int)blockIdx.x + lane * (int)gridDim.x;
+        if (lane < n_iter && e < n_envs) {
+            const SensorFrame f = make_frame(pos_w + 3 * (size_t)e, quat_w + 4 * (size_t)e);
+            fcw = f.cw, fsz = f.sz, fpx = f.px, fpy = f.py, fpz = f.pz;
+        }
+    }
     for (int r = threadIdx.x; r < n_rays; r += kPipeThreads)
         sm.pattern[r] = make_float4(__ldg(ray_local + 3 * r), __ldg(ray_local + 3 * r + 1), __ldg(ray_local + 3 * r + 2), 0.f);
     const bool lines_in_smem = (pc.nx <= kPipeMaxLines) && (pc.ny <= kPipeMaxLines);
@@ -199,9 +208,8 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
 
     if (warp == 0) {
         // =============================== producer ===============================
-        float fcw = 0.f, fsz = 0.f, fpx = 0.f, fpy = 0.f, fpz = 0.f;
         for (int it = 0; it < n_iter; ++it) {
-            if ((it & 31) == 0) {  // 32 sensor frames at once, one per lane
+            if ((it & 31) == 0 && it > 0) {  // 32 sensor frames at once, one per lane (first batch: see above)
                 const int e = (int)blockIdx.x + (it + lane) * (int)gridDim.x;
                 if (e < n_envs) {
                     const SensorFrame f = make_frame(pos_w + 3 * (size_t)e, quat_w + 4 * (size_t)e);
