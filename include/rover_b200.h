@@ -129,6 +129,7 @@ typedef struct RoverMdpOut {
     float* joint_vel;              /* [N,6] drive targets     [ML,FL,RL,RR,MR,FR] */
     float* reward;                 /* [N]   */
     float* term_rewards;           /* [N,7] weight*value*dt per term */
+    float* term_values;            /* [N,7] unweighted term values (what the reference's reward functions return) */
     uint8_t* terminated;           /* [N]   */
     uint8_t* truncated;            /* [N]   */
     uint8_t* term_flags;           /* [N,4] time_limit,is_success,far_from_target,collision */
@@ -138,10 +139,15 @@ typedef struct RoverMdpOut {
 
 #define ROVER_MDP_BLOCK 64
 
-/* new_actions [N,2]; force_matrix_w [N,B,1,3] (contact_sensor.data.force_matrix_w). */
+/* new_actions [N,2]; force_matrix_w [N,B,1,3] (contact_sensor.data.force_matrix_w).
+ * phases: ROVER_PRE_ACTIONS = action-manager shift + Ackermann (what runs BEFORE the physics step),
+ *         ROVER_PRE_TERMS   = counters + terminations + rewards (what runs AFTER it); both = the fused launch. */
+#define ROVER_PRE_ACTIONS 1
+#define ROVER_PRE_TERMS 2
+#define ROVER_PRE_ALL 3
 int rover_mdp_pre_step(const float* new_actions, const float* force_matrix_w, int32_t n_envs,
                        const RoverMdpParams* params /* host */, const RoverMdpState* state /* host struct */,
-                       const RoverMdpOut* out /* host struct */, void* stream);
+                       const RoverMdpOut* out /* host struct */, int32_t phases, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Reset + command update + observation head.  Replaces, in one launch (rows a-4..a-6, a-22..a-28):
@@ -173,12 +179,30 @@ typedef struct RoverTerrainTables {
     int32_t reserved;
 } RoverTerrainTables;
 
+/* `phases` selects which parts of the post-step run (all of them in the fused step); the single-purpose
+ * combinations back the individual manager-term calls of the reference API:
+ *   ROVER_PHASE_SPAWN     reset_root_state_rover for envs with reset_flags != 0
+ *   ROVER_PHASE_MANAGERS  action / reward / command-metric / termination manager resets + statistics, ep_len = 0
+ *   ROVER_PHASE_RESAMPLE  CommandTerm._resample for envs with reset_flags != 0
+ *   ROVER_PHASE_METRICS   _update_metrics
+ *   ROVER_PHASE_TIME      time_left -= dt and the time-based resample
+ *   ROVER_PHASE_COMMAND   _update_command
+ *   ROVER_PHASE_OBS       observation head */
+#define ROVER_PHASE_SPAWN 1
+#define ROVER_PHASE_MANAGERS 2
+#define ROVER_PHASE_RESAMPLE 4
+#define ROVER_PHASE_METRICS 8
+#define ROVER_PHASE_TIME 16
+#define ROVER_PHASE_COMMAND 32
+#define ROVER_PHASE_OBS 64
+#define ROVER_PHASE_ALL 127
+
 int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_t n_envs, const RoverMdpParams* params,
                         const RoverMdpState* state, const RoverMdpOut* out, const RoverTerrainTables* tables,
                         const int64_t* spawn_perm, const float* yaw_u, const float* heading_u, const float* theta_u,
                         int32_t n_rounds, int64_t* out_spawn_index /* [N], -1 if not reset */, float* stats,
                         float* scratch /* [ceil(N/ROVER_MDP_BLOCK)*ROVER_STATS_LEN + 1] f32, zeroed once */,
-                        float* obs, int32_t obs_stride, void* stream);
+                        float* obs, int32_t obs_stride, int32_t phases, void* stream);
 
 #ifdef __cplusplus
 }

@@ -52,8 +52,12 @@ class MdpParams(C.Structure):
 
 _STATE_FIELDS = ("action", "prev_action", "pos_cmd_w", "heading_cmd_w", "pos_cmd_b", "heading_cmd_b", "time_left",
                  "command_counter", "episode_length_buf", "episode_sums", "env_origins", "err_pos", "err_heading")
-_OUT_FIELDS = ("processed_actions", "joint_pos", "joint_vel", "reward", "term_rewards", "terminated", "truncated",
-               "term_flags", "reset_flags", "block_reset_counts")
+_OUT_FIELDS = ("processed_actions", "joint_pos", "joint_vel", "reward", "term_rewards", "term_values", "terminated",
+               "truncated", "term_flags", "reset_flags", "block_reset_counts")
+
+PHASE_SPAWN, PHASE_MANAGERS, PHASE_RESAMPLE, PHASE_METRICS, PHASE_TIME, PHASE_COMMAND, PHASE_OBS = 1, 2, 4, 8, 16, 32, 64
+PHASE_ALL = 127
+PRE_ACTIONS, PRE_TERMS, PRE_ALL = 1, 2, 3
 
 
 class MdpState(C.Structure):
@@ -98,10 +102,11 @@ def load() -> C.CDLL:
     lib.rover_height_scan.argtypes = [vp, vp, i32, vp, i32, C.POINTER(C.c_float * 4), C.POINTER(ScanGrid),
                                       C.POINTER(PlaneCells), f32, f32, vp, i32, vp, i32, vp]
     lib.rover_mdp_pre_step.restype = C.c_int
-    lib.rover_mdp_pre_step.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut), vp]
+    lib.rover_mdp_pre_step.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut), i32,
+                                       vp]
     lib.rover_mdp_post_step.restype = C.c_int
     lib.rover_mdp_post_step.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
-                                        C.POINTER(TerrainTables), vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp]
+                                        C.POINTER(TerrainTables), vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp]
     _lib = lib
     return lib
 

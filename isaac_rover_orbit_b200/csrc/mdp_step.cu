@@ -72,13 +72,15 @@ __device__ __forceinline__ bool collision_active(const float* __restrict__ f, in
 __global__ void __launch_bounds__(ROVER_MDP_BLOCK)
 mdp_pre_step_kernel(const float* __restrict__ new_actions, const float* __restrict__ force, int n,
                     const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
-                    const __grid_constant__ RoverMdpOut O) {
+                    const __grid_constant__ RoverMdpOut O, int phases) {
     const int i = blockIdx.x * ROVER_MDP_BLOCK + threadIdx.x;
     bool reset = false;
     if (i < n) {
+        float2 a_old, a;
+        if (phases & ROVER_PRE_ACTIONS) {
         // ---- ActionManager.process_action: prev <- action <- new; term.process_actions (ackermann_actions.py:226-229)
-        const float2 a_old = reinterpret_cast<const float2*>(S.action)[i];
-        const float2 a = reinterpret_cast<const float2*>(new_actions)[i];
+        a_old = reinterpret_cast<const float2*>(S.action)[i];
+        a = reinterpret_cast<const float2*>(new_actions)[i];
         reinterpret_cast<float2*>(S.prev_action)[i] = a_old;
         reinterpret_cast<float2*>(S.action)[i] = a;
         const float lin_p = __fadd_rn(__fmul_rn(a.x, P.scale_lin), P.offset_lin);
@@ -116,7 +118,12 @@ mdp_pre_step_kernel(const float* __restrict__ new_actions, const float* __restri
             reinterpret_cast<float4*>(O.joint_pos)[i] =                                 // [FL,RL,RR,FR] :317
                 make_float4(point ? -q : ack, point ? q : ack, point ? -q : ack, point ? q : ack);
         }
+        } else {
+            a = reinterpret_cast<const float2*>(S.action)[i];
+            a_old = reinterpret_cast<const float2*>(S.prev_action)[i];
+        }
 
+        if (phases & ROVER_PRE_TERMS) {
         // ---- counters (rover_env.py:79)
         const long long ep = S.episode_length_buf[i] + 1;
         S.episode_length_buf[i] = ep;
@@ -159,17 +166,22 @@ mdp_pre_step_kernel(const float* __restrict__ new_actions, const float* __restri
         float total = 0.f;
         float* sums = S.episode_sums + ROVER_NUM_REWARD_TERMS * (size_t)i;
         float* tr = O.term_rewards + ROVER_NUM_REWARD_TERMS * (size_t)i;
+        float* tv = O.term_values + ROVER_NUM_REWARD_TERMS * (size_t)i;
 #pragma unroll
         for (int k = 0; k < ROVER_NUM_REWARD_TERMS; ++k) {
             const float c = __fmul_rn(__fmul_rn(val[k], P.weight[k]), P.step_dt);
             total = __fadd_rn(total, c);
             sums[k] = __fadd_rn(sums[k], c);
             tr[k] = c;
+            tv[k] = val[k];
         }
         O.reward[i] = total;
+        }
     }
-    const int cnt = __syncthreads_count(reset);
-    if (threadIdx.x == 0) O.block_reset_counts[blockIdx.x] = cnt;
+    if (phases & ROVER_PRE_TERMS) {
+        const int cnt = __syncthreads_count(reset);
+        if (threadIdx.x == 0) O.block_reset_counts[blockIdx.x] = cnt;
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -226,7 +238,7 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
                      const float* __restrict__ heading_u, const float* __restrict__ theta_u, int n_rounds,
                      long long* __restrict__ out_spawn_index, float* __restrict__ block_stats,
                      unsigned int* __restrict__ done_counter, float* __restrict__ stats, float* __restrict__ obs,
-                     int obs_stride) {
+                     int obs_stride, int phases) {
     __shared__ int warp_cnt[ROVER_MDP_BLOCK / 32];
     __shared__ int block_base;
     __shared__ float red[ROVER_MDP_BLOCK / 32][kStats];
@@ -263,7 +275,7 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
         long long spawn_idx = -1;
         bool cmd_dirty = false;
 
-        if (reset) {
+        if (reset && (phases & ROVER_PHASE_SPAWN)) {
             // -- reset_root_state_rover (randomizations.py:12-39)
             spawn_idx = __ldg(spawn_perm + rank);
             const float* sp = T.spawn + 3 * (size_t)spawn_idx;
@@ -280,6 +292,8 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
             root_pos_w[3 * (size_t)i + 1] = py;
             root_pos_w[3 * (size_t)i + 2] = pz;
             reinterpret_cast<float4*>(root_quat_w)[i] = q;
+        }
+        if (reset && (phases & ROVER_PHASE_MANAGERS)) {
             // -- ActionManager.reset
             act = make_float2(0.f, 0.f);
             reinterpret_cast<float2*>(S.action)[i] = act;
@@ -301,23 +315,32 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
             st[11] = S.err_pos[i];
             st[12] = S.err_heading[i];
             st[13] = 1.f;
-            const bool exhausted = resample_command(i, P, S, T, px, py, theta_u, n_rounds, __ldg(heading_u + i), cwx,
+            S.err_pos[i] = 0.f;
+            S.err_heading[i] = 0.f;
+            S.command_counter[i] = 0;
+            S.episode_length_buf[i] = 0;
+        }
+        if (reset && (phases & ROVER_PHASE_RESAMPLE)) {
+            // -- CommandTerm._resample: time_left, counter += 1, _resample_command around the (new) env origin
+            const float ox = S.env_origins[3 * (size_t)i], oy = S.env_origins[3 * (size_t)i + 1];
+            const bool exhausted = resample_command(i, P, S, T, ox, oy, theta_u, n_rounds, __ldg(heading_u + i), cwx,
                                                     cwy, cwz, chead);
             st[14] = exhausted ? 1.f : 0.f;
-            S.command_counter[i] = 1;
+            S.command_counter[i] += 1;
             time_left = P.resampling_time;
             cmd_dirty = true;
-            S.episode_length_buf[i] = 0;
         }
         if (out_spawn_index) out_spawn_index[i] = spawn_idx;
 
         // -- CommandManager.compute(dt): metrics, time_left, time-based resample, _update_command
-        const float ex = __fsub_rn(cwx, px), ey = __fsub_rn(cwy, py), ez = __fsub_rn(cwz, pz);
         const float hw = heading_w(q.x, q.y, q.z, q.w);
-        S.err_pos[i] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
-        S.err_heading[i] = fabsf(wrap_to_pi(__fsub_rn(chead, hw)));
-        time_left = __fsub_rn(time_left, P.step_dt);
-        if (time_left <= 0.f) {
+        if (phases & ROVER_PHASE_METRICS) {
+            const float ex = __fsub_rn(cwx, px), ey = __fsub_rn(cwy, py), ez = __fsub_rn(cwz, pz);
+            S.err_pos[i] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
+            S.err_heading[i] = fabsf(wrap_to_pi(__fsub_rn(chead, hw)));
+        }
+        if (phases & ROVER_PHASE_TIME) time_left = __fsub_rn(time_left, P.step_dt);
+        if ((phases & ROVER_PHASE_TIME) && time_left <= 0.f) {
             const float ox = S.env_origins[3 * (size_t)i], oy = S.env_origins[3 * (size_t)i + 1];
             const bool exhausted = resample_command(i, P, S, T, ox, oy, theta_u, n_rounds, __ldg(heading_u + i), cwx,
                                                     cwy, cwz, chead);
@@ -327,13 +350,15 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
             time_left = P.resampling_time;
             cmd_dirty = true;
         }
-        S.time_left[i] = time_left;
+        if (phases & (ROVER_PHASE_TIME | ROVER_PHASE_RESAMPLE)) S.time_left[i] = time_left;
         if (cmd_dirty) {
             S.pos_cmd_w[3 * (size_t)i] = cwx;
             S.pos_cmd_w[3 * (size_t)i + 1] = cwy;
             S.pos_cmd_w[3 * (size_t)i + 2] = cwz;
             S.heading_cmd_w[i] = chead;
         }
+        float pbx = S.pos_cmd_b[3 * (size_t)i], pby = S.pos_cmd_b[3 * (size_t)i + 1];
+        if (phases & ROVER_PHASE_COMMAND) {
         // _update_command (terrain_importer.py:97-101): quat_rotate_inverse(yaw_quat(q), target - root)
         const float vx = __fsub_rn(cwx, px), vy = __fsub_rn(cwy, py), vz = __fsub_rn(cwz, pz);
         const YawQuat yq = yaw_quat(q.x, q.y, q.z, q.w);
@@ -342,16 +367,17 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
         const float b_y = __fmul_rn(__fmul_rn(__fmul_rn(yq.sz, vx), yq.cw), 2.f);
         const float dot = __fmul_rn(yq.sz, vz);
         const float c_z = __fmul_rn(__fmul_rn(yq.sz, dot), 2.f);
-        const float pbx = __fsub_rn(__fmul_rn(vx, k), b_x);
-        const float pby = __fsub_rn(__fmul_rn(vy, k), b_y);
+        pbx = __fsub_rn(__fmul_rn(vx, k), b_x);
+        pby = __fsub_rn(__fmul_rn(vy, k), b_y);
         const float pbz = __fadd_rn(__fmul_rn(vz, k), c_z);
         S.pos_cmd_b[3 * (size_t)i] = pbx;
         S.pos_cmd_b[3 * (size_t)i + 1] = pby;
         S.pos_cmd_b[3 * (size_t)i + 2] = pbz;
         S.heading_cmd_b[i] = wrap_to_pi(__fsub_rn(chead, hw));
+        }
 
         // -- observation head (rover_env_cfg.py:103-112): last_action, distance * 0.11, angle / pi
-        if (obs) {
+        if (obs && (phases & ROVER_PHASE_OBS)) {
             float* o = obs + (size_t)i * obs_stride;
             o[0] = act.x;
             o[1] = act.y;
@@ -395,7 +421,7 @@ static int check_state(const RoverMdpState* s, const RoverMdpOut* o) {
                     s->err_pos && s->err_heading,
                 "rover_mdp: NULL pointer in RoverMdpState");
     ROVER_CHECK(o->processed_actions && o->joint_pos && o->joint_vel && o->reward && o->term_rewards && o->terminated &&
-                    o->truncated && o->term_flags && o->reset_flags && o->block_reset_counts,
+                        o->truncated && o->term_flags && o->reset_flags && o->block_reset_counts && o->term_values,
                 "rover_mdp: NULL pointer in RoverMdpOut");
     ROVER_CHECK((reinterpret_cast<uintptr_t>(o->joint_pos) & 15) == 0, "rover_mdp: joint_pos not 16B aligned");
     return 0;
@@ -403,16 +429,18 @@ static int check_state(const RoverMdpState* s, const RoverMdpOut* o) {
 
 extern "C" int rover_mdp_pre_step(const float* new_actions, const float* force_matrix_w, int32_t n_envs,
                                   const RoverMdpParams* params, const RoverMdpState* state, const RoverMdpOut* out,
-                                  void* stream) {
+                                  int32_t phases, void* stream) {
     using namespace rover;
     ROVER_CHECK(n_envs >= 0, "rover_mdp_pre_step: negative n_envs");
     if (n_envs == 0) return 0;
-    ROVER_CHECK(new_actions && force_matrix_w && params, "rover_mdp_pre_step: NULL argument");
+    ROVER_CHECK(params && (new_actions || !(phases & ROVER_PRE_ACTIONS)) &&
+                    (force_matrix_w || !(phases & ROVER_PRE_TERMS)),
+                "rover_mdp_pre_step: NULL argument");
     ROVER_CHECK(params->num_bodies >= 0 && params->max_episode_length > 0, "rover_mdp_pre_step: bad params");
     if (int rc = check_state(state, out)) return rc;
     const int blocks = (n_envs + ROVER_MDP_BLOCK - 1) / ROVER_MDP_BLOCK;
     mdp_pre_step_kernel<<<blocks, ROVER_MDP_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(
-        new_actions, force_matrix_w, n_envs, *params, *state, *out);
+        new_actions, force_matrix_w, n_envs, *params, *state, *out, phases);
     return check_launch("mdp_pre_step_kernel");
 }
 
@@ -421,7 +449,7 @@ extern "C" int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_
                                    const RoverTerrainTables* tables, const int64_t* spawn_perm, const float* yaw_u,
                                    const float* heading_u, const float* theta_u, int32_t n_rounds,
                                    int64_t* out_spawn_index, float* stats, float* scratch, float* obs,
-                                   int32_t obs_stride, void* stream) {
+                                   int32_t obs_stride, int32_t phases, void* stream) {
     using namespace rover;
     ROVER_CHECK(n_envs >= 0, "rover_mdp_post_step: negative n_envs");
     if (n_envs == 0) return 0;
@@ -444,6 +472,6 @@ extern "C" int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_
     mdp_post_step_kernel<<<blocks, ROVER_MDP_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(
         root_pos_w, root_quat_w, n_envs, *params, *state, *out, T, reinterpret_cast<const long long*>(spawn_perm),
         yaw_u, heading_u, theta_u, n_rounds, reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats,
-        obs, obs_stride);
+        obs, obs_stride, phases);
     return check_launch("mdp_post_step_kernel");
 }

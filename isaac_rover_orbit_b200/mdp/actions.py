@@ -1,0 +1,60 @@
+"""``AckermannAction2`` -- the action term selected by ``AckermannActionCfg.class_type``
+(rover_envs/mdp/actions/actions_cfg.py:17; class at rover_envs/mdp/actions/ackermann_actions.py:162-322).
+
+Same constructor, properties and methods; ``process_actions`` + ``apply_actions`` are served by the ACTIONS phase of
+the fused pre-step kernel (action-manager shift, scale/offset, Ackermann kinematics in one launch).  The reference
+recomputes the identical kinematics ``decimation`` = 6 times per env step (rover_env.py:64-66); here the first
+``apply_actions`` after a ``process_actions`` launches, the rest re-bind the same targets.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib, ops
+from ..config import AckermannActionCfg  # noqa: F401  (re-exported like actions_cfg.AckermannActionCfg)
+
+
+class AckermannAction2:
+    cfg: AckermannActionCfg
+
+    def __init__(self, cfg: AckermannActionCfg, env):
+        self.cfg = cfg
+        self._env = env
+        self._asset = env.scene[cfg.asset_name]
+        self._drive_joint_ids, self._drive_joint_names = self._asset.find_joints(cfg.drive_joint_names)
+        self._steering_joint_ids, self._steering_joint_names = self._asset.find_joints(cfg.steering_joint_names)
+        self._raw_actions = torch.zeros(self.num_envs, self.action_dim, device=self.device)
+        self._dirty = False
+
+    @property
+    def num_envs(self) -> int:
+        return self._env.num_envs
+
+    @property
+    def device(self):
+        return self._env.device
+
+    @property
+    def action_dim(self) -> int:
+        return 2  # (linear velocity, angular velocity)
+
+    @property
+    def raw_actions(self) -> torch.Tensor:
+        return self._raw_actions
+
+    @property
+    def processed_actions(self) -> torch.Tensor:
+        return self._env._buf.processed_actions
+
+    def process_actions(self, actions: torch.Tensor):
+        """ackermann_actions.py:226-229 (+ ORBIT ActionManager.process_action: prev_action <- action <- actions)."""
+        self._raw_actions[:] = actions
+        ops.mdp_pre_step(self._env._buf, self._env._params, self._raw_actions, None, phases=_lib.PRE_ACTIONS)
+        self._dirty = True
+
+    def apply_actions(self):
+        """ackermann_actions.py:231-236: joint targets [FL,RL,RR,FR] (rad) and [ML,FL,RL,RR,MR,FR] (rad/s)."""
+        b = self._env._buf
+        self._asset.set_joint_velocity_target(b.joint_vel, joint_ids=self._drive_joint_ids)
+        self._asset.set_joint_position_target(b.joint_pos, joint_ids=self._steering_joint_ids)
+        self._dirty = False

@@ -183,6 +183,7 @@ class MdpBuffers:
     joint_vel: torch.Tensor
     reward: torch.Tensor
     term_rewards: torch.Tensor
+    term_values: torch.Tensor
     terminated: torch.Tensor
     truncated: torch.Tensor
     term_flags: torch.Tensor
@@ -203,7 +204,7 @@ class MdpBuffers:
         blocks = (n + _lib.MDP_BLOCK - 1) // _lib.MDP_BLOCK
         return MdpBuffers(
             n, device, f(n, 2), f(n, 2), f(n, 3), f(n), f(n, 3), f(n), f(n), i64(n), i64(n), f(n, 7), f(n, 3), f(n),
-            f(n), f(n, 2), f(n, 4), f(n, 6), f(n), f(n, 7), u8(n), u8(n), u8(n, 4), u8(n),
+            f(n), f(n, 2), f(n, 4), f(n, 6), f(n), f(n, 7), f(n, 7), u8(n), u8(n), u8(n, 4), u8(n),
             torch.zeros(max(blocks, 1), dtype=torch.int32, device=device), torch.full((n,), -1, dtype=torch.int64,
                                                                                       device=device),
             f(_lib.STATS_LEN), f(max(blocks, 1) * _lib.STATS_LEN + 1))
@@ -234,23 +235,27 @@ class TerrainTablesHandle:
             raise RuntimeError("safe_mask and heightmap shapes differ")
 
 
-def mdp_pre_step(buf: MdpBuffers, params: _lib.MdpParams, actions: torch.Tensor, force_matrix_w: torch.Tensor):
-    """Action shift + Ackermann + counters + terminations + rewards (one launch, in place on ``buf``)."""
+def mdp_pre_step(buf: MdpBuffers, params: _lib.MdpParams, actions: torch.Tensor | None,
+                 force_matrix_w: torch.Tensor | None, phases: int = _lib.PRE_ALL):
+    """Action shift + Ackermann (``PRE_ACTIONS``) and counters + terminations + rewards (``PRE_TERMS``);
+    one launch, in place on ``buf``."""
     dev = _lib.require_cuda(actions, force_matrix_w)
-    if dev != buf.device:
+    if dev is not None and dev != buf.device:
         raise RuntimeError("mdp_pre_step: inputs on another device than the buffers")
-    if actions.shape != (buf.n, 2) or actions.dtype != torch.float32:
+    if phases & _lib.PRE_ACTIONS and (actions is None or actions.shape != (buf.n, 2) or actions.dtype != torch.float32):
         raise RuntimeError("mdp_pre_step: actions must be fp32 [N,2]")
-    if force_matrix_w.dtype != torch.float32 or force_matrix_w.numel() != buf.n * params.num_bodies * 3:
+    if phases & _lib.PRE_TERMS and (force_matrix_w is None or force_matrix_w.dtype != torch.float32 or
+                                    force_matrix_w.numel() != buf.n * params.num_bodies * 3):
         raise RuntimeError("mdp_pre_step: force_matrix_w must be fp32 [N,B,1,3]")
     st, out = buf.state_struct(), buf.out_struct()
     _lib.check(_lib.load().rover_mdp_pre_step(_lib.ptr(actions), _lib.ptr(force_matrix_w), buf.n, C.byref(params),
-                                               C.byref(st), C.byref(out), _lib.current_stream(dev)))
+                                               C.byref(st), C.byref(out), int(phases),
+                                               _lib.current_stream(buf.device)))
 
 
 def mdp_post_step(buf: MdpBuffers, params: _lib.MdpParams, tables: TerrainTablesHandle, root_pos_w: torch.Tensor,
                   root_quat_w: torch.Tensor, spawn_perm: torch.Tensor, yaw_u: torch.Tensor, heading_u: torch.Tensor,
-                  theta_u: torch.Tensor, obs: torch.Tensor | None = None):
+                  theta_u: torch.Tensor, obs: torch.Tensor | None = None, phases: int = _lib.PHASE_ALL):
     """Reset / resample / command update / observation head (one launch).  ``root_*`` are updated in place
     for the reset envs; ``buf.stats`` is accumulated; ``buf.spawn_index`` holds the spawn rows used (-1 else)."""
     dev = _lib.require_cuda(root_pos_w, root_quat_w, spawn_perm, yaw_u, heading_u, theta_u)
@@ -273,4 +278,4 @@ def mdp_post_step(buf: MdpBuffers, params: _lib.MdpParams, tables: TerrainTables
         _lib.ptr(root_pos_w), _lib.ptr(root_quat_w), n, C.byref(params), C.byref(st), C.byref(out),
         C.byref(tables.struct), _lib.ptr(spawn_perm), _lib.ptr(yaw_u), _lib.ptr(heading_u), _lib.ptr(theta_u),
         int(theta_u.shape[1]), _lib.ptr(buf.spawn_index), _lib.ptr(buf.stats), _lib.ptr(buf.scratch), obs_ptr,
-        obs_stride, _lib.current_stream(dev)))
+        obs_stride, int(phases), _lib.current_stream(dev)))
