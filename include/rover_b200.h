@@ -204,6 +204,28 @@ int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_t n_envs, c
                         float* scratch /* [ceil(N/ROVER_MDP_BLOCK)*ROVER_STATS_LEN + 1] f32, zeroed once */,
                         float* obs, int32_t obs_stride, int32_t phases, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Policy forward.  Replaces GaussianNeuralNetwork.compute + HeightmapEncoder
+ * (rover_envs/envs/navigation/learning/skrl/models.py:24-36, 89-102) and skrl GaussianMixin.act.
+ * Weights are packed once (host -> device) by rover_policy_pack; bf16 operands, fp32 accumulation
+ * on the tcgen05 tensor cores.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct RoverPolicyWeights {
+    const float* w[6];   /* nn.Linear weights [out,in] fp32, order: enc0, enc2, mlp0, mlp2, mlp4, mlp6 */
+    const float* b[6];   /* biases */
+    int32_t in_dim[6], out_dim[6];
+} RoverPolicyWeights;
+
+/* returns the number of bytes the packed blob needs (when packed == NULL) or packs into it */
+int64_t rover_policy_pack(const RoverPolicyWeights* weights /* host struct, device pointers */, void* packed,
+                          void* stream);
+/* obs [N, obs_stride] fp32 (965 columns used), rows 16-byte aligned (obs_stride % 4 == 0); mean [N,2] fp32 */
+int rover_policy_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed, float* mean,
+                         void* stream);
+/* actions = clamp(mean + exp(clamp(log_std,-20,2)) * eps, -1, 1); log_prob [N] = sum_j log N(a_j) */
+int rover_gaussian_act(const float* mean, const float* log_std, const float* eps, int32_t n_envs, float* actions,
+                       float* log_prob, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

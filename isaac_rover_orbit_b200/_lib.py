@@ -20,7 +20,8 @@ STATS_LEN = 16
 MDP_BLOCK = 64
 ABI_VERSION = 1
 
-SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_mdp_pre_step", "rover_mdp_post_step")
+SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_mdp_pre_step", "rover_mdp_post_step",
+           "rover_policy_pack", "rover_policy_forward", "rover_gaussian_act")
 
 
 class ScanLevel(C.Structure):
@@ -107,6 +108,12 @@ def load() -> C.CDLL:
     lib.rover_mdp_post_step.restype = C.c_int
     lib.rover_mdp_post_step.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
                                         C.POINTER(TerrainTables), vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp]
+    lib.rover_policy_pack.restype = C.c_int64
+    lib.rover_policy_pack.argtypes = [C.POINTER(PolicyWeights), vp, vp]
+    lib.rover_policy_forward.restype = C.c_int
+    lib.rover_policy_forward.argtypes = [vp, i32, i32, vp, vp, vp]
+    lib.rover_gaussian_act.restype = C.c_int
+    lib.rover_gaussian_act.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     _lib = lib
     return lib
 

@@ -1,0 +1,470 @@
+// Gaussian policy forward on the 5th-generation tensor cores (tcgen05 + TMEM), bf16 operands, fp32 accumulation.
+//
+// Replaces GaussianNeuralNetwork.compute + HeightmapEncoder of the reference
+// (rover_envs/envs/navigation/learning/skrl/models.py:24-36, 89-102; built by gaussian_model_skrl,
+// configure_models.py:37-53):
+//     x = s[:, 0:4];  e = LReLU(W1 LReLU(W0 s[:, 3:964] + b0) + b1)        (961 -> 80 -> 60; heading column included,
+//     y = tanh(W5 LReLU(W4 LReLU(W3 LReLU(W2 [x, e] + b2) + b3) + b4) + b5)  last ray dropped -- reference quirk kept)
+// and skrl's GaussianMixin.act sampling (rover_gaussian_act).  319,520 FLOP per environment.
+//
+// One persistent CTA per SM, 256 threads, tile = 128 environments (UMMA M = 128, cta_group::1):
+//   layer 0  K = 961 streamed in 16 chunks of 64 observation columns: a 2-D TMA tensor-map load (fp32, 128 x 64)
+//            + a bulk copy of the matching 80 x 64 bf16 weight chunk land on one mbarrier; all threads convert the
+//            chunk to bf16 in the UMMA K-major no-swizzle ("interleaved") layout; one thread issues the
+//            tcgen05.mma's (D0[128 x 80] in TMEM) and commits to the stage's mbarrier; two stages overlap
+//            TMA / convert / MMA.
+//   layers 1-5  the epilogue of layer l (tcgen05.ld -> +bias -> LeakyReLU -> bf16) writes the A operand of layer
+//            l+1 straight into shared memory; weights arrive by bulk copy from the pre-packed blob; accumulators
+//            alternate between two TMEM regions.  The last epilogue applies tanh and stores mean[128, 2].
+// Operand layout (SWIZZLE_NONE, K-major): 8 x 8 bf16 core matrices; element (row r, k) lives at
+//     (k / 8) * plane_stride + r * 16 + (k % 8) * 2,   descriptor LBO = plane_stride, SBO = 128 B.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace rover {
+
+constexpr int kPolThreads = 256;
+constexpr int kTileM = 128;
+constexpr int kObsCols = 965;
+constexpr int kEncIn = 961;       // obs[:, 3:964]
+constexpr int kEncInOffset = 3;
+constexpr int kChunkK = 64;
+constexpr int kNumChunks = 16;    // 15 full chunks + 1 chunk with a single real column
+constexpr int kAPlane = kTileM * 16 + 16;  // A plane stride (bytes), +16 B skew: conflict-free 16 B stores per plane
+constexpr int kNumLayers = 6;
+
+// padded layer shapes: K (multiple of 16), N (multiple of 16)
+__host__ __device__ constexpr int layer_k(int l) { return l == 0 ? 976 : l == 1 ? 80 : l == 2 ? 64 : l == 3 ? 256 : l == 4 ? 160 : 128; }
+__host__ __device__ constexpr int layer_n(int l) { return l == 0 ? 80 : l == 1 ? 64 : l == 2 ? 256 : l == 3 ? 160 : l == 4 ? 128 : 16; }
+__host__ __device__ constexpr int layer_k_real(int l) { return l == 0 ? 961 : l == 1 ? 80 : l == 2 ? 64 : l == 3 ? 256 : l == 4 ? 160 : 128; }
+__host__ __device__ constexpr int layer_n_real(int l) { return l == 0 ? 80 : l == 1 ? 60 : l == 2 ? 256 : l == 3 ? 160 : l == 4 ? 128 : 2; }
+
+// packed blob: [W0: 16 chunks x (8 planes x 80 rows x 16 B)] [W1..W5: (K/8 planes x N rows x 16 B)] [biases fp32]
+constexpr int kW0ChunkBytes = 8 * 80 * 16;  // 10,240
+__host__ __device__ constexpr int weight_bytes(int l) { return l == 0 ? kNumChunks * kW0ChunkBytes : (layer_k(l) / 8) * layer_n(l) * 16; }
+__host__ __device__ constexpr int weight_offset(int l) {
+    int off = 0;
+    for (int i = 0; i < l; ++i) off += weight_bytes(i);
+    return off;
+}
+constexpr int kBiasOffset = weight_offset(kNumLayers);
+__host__ __device__ constexpr int bias_offset(int l) {
+    int off = kBiasOffset;
+    for (int i = 0; i < l; ++i) off += layer_n(i) * 4;
+    return off;
+}
+constexpr int kPackedBytes = bias_offset(kNumLayers);
+
+// ---------------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t sptr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(unsigned long long* b, uint32_t n) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sptr(b)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(unsigned long long* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sptr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(unsigned long long* b, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(sptr(b)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sptr(dst)),
+                 "l"(src), "r"(bytes), "r"(sptr(b))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_2d(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* b) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(sptr(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(sptr(b))
+        : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE: LBO = byte stride between the two 8-element K chunks of one
+// MMA (= plane stride), SBO = byte stride between 8-row groups (= 128 B), version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((128u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor, kind::f16: D = F32, A = B = BF16, both K-major, M = 128
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* b) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sptr(b)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x; }
+
+// ---------------------------------------------------------------------------------------------------- shared memory
+struct __align__(128) PolSmem {
+    union {
+        struct {  // layer 0 streaming
+            float stage_f32[2][kTileM * kChunkK];              // 2 x 32 KB, TMA destination
+            unsigned char a_bf16[2][8 * kAPlane];              // 2 x 16.1 KB
+            unsigned char w0[2][kW0ChunkBytes];                // 2 x 10 KB
+        } l0;
+        struct {  // layers 1..5
+            unsigned char act[2][32 * kAPlane];                // up to K = 256 -> 32 planes, 2 x 64.5 KB
+            unsigned char w[(256 / 8) * 160 * 16];             // largest weight image (layer 3): 80 KB
+        } ln;
+    };
+    unsigned long long full[2];      // TMA / bulk copies of a layer-0 stage landed
+    unsigned long long mma_done[2];  // MMAs reading a layer-0 stage retired
+    unsigned long long w_full;       // weights of the current layer (l >= 1) landed
+    unsigned long long acc_done;     // accumulator of the current layer complete
+    uint32_t tmem_base;
+};
+
+// ---------------------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(kPolThreads, 1)
+policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* __restrict__ obs, int obs_stride,
+                      int n_envs, const unsigned char* __restrict__ packed, float* __restrict__ mean) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PolSmem& sm = *reinterpret_cast<PolSmem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = (n_envs + kTileM - 1) / kTileM;
+
+    if (tid == 0) {
+        mb_init(&sm.full[0], 1);
+        mb_init(&sm.full[1], 1);
+        mb_init(&sm.mma_done[0], 1);
+        mb_init(&sm.mma_done[1], 1);
+        mb_init(&sm.w_full, 1);
+        mb_init(&sm.acc_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // one warp allocates all 512 TMEM columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sptr(&sm.tmem_base)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    // barrier phase bookkeeping (each barrier completes once per use; parity flips per completion)
+    uint32_t ph_full[2] = {0, 0}, ph_mma[2] = {0, 0}, ph_w = 0, ph_acc = 0;
+    uint32_t mma_pending[2] = {0, 0};  // thread 0: a commit is outstanding on mma_done[s]
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = tile * kTileM;
+        // =========================================================== layer 0: stream K in 16 chunks of 64
+        const uint32_t idesc0 = make_idesc(layer_n(0));
+        if (tid == 0) {  // prologue: chunk 0 into stage 0
+            mb_expect_tx(&sm.full[0], kTileM * kChunkK * 4 + kW0ChunkBytes);
+            tma_2d(sm.l0.stage_f32[0], &obs_map, kEncInOffset, row0, &sm.full[0]);
+            bulk_g2s(sm.l0.w0[0], packed, kW0ChunkBytes, &sm.full[0]);
+        }
+        for (int c = 0; c < kNumChunks; ++c) {
+            const int s = c & 1;
+            if (tid == 0 && c + 1 < kNumChunks) {  // prefetch chunk c+1 into the other stage
+                const int s1 = s ^ 1;
+                if (mma_pending[s1]) {  // the MMAs that read a_bf16[s1] / w0[s1] must have retired
+                    mb_wait(&sm.mma_done[s1], ph_mma[s1]);
+                    ph_mma[s1] ^= 1;
+                    mma_pending[s1] = 0;
+                }
+                mb_expect_tx(&sm.full[s1], kTileM * kChunkK * 4 + kW0ChunkBytes);
+                tma_2d(sm.l0.stage_f32[s1], &obs_map, kEncInOffset + (c + 1) * kChunkK, row0, &sm.full[s1]);
+                bulk_g2s(sm.l0.w0[s1], packed + (size_t)(c + 1) * kW0ChunkBytes, kW0ChunkBytes, &sm.full[s1]);
+            }
+            mb_wait(&sm.full[s], ph_full[s]);
+            ph_full[s] ^= 1;
+            // a_bf16[s] may still be read by the MMAs of chunk c-2: thread 0 waited for them when it prefetched
+            // chunk c-1+1 = c into this stage (above, one iteration ago); the __syncthreads below that iteration
+            // ordered every thread after that wait.
+            // ---- convert fp32 [128][64] -> bf16 planes [8][128 rows][8]
+            const float* __restrict__ src = sm.l0.stage_f32[s];
+            unsigned char* dst = sm.l0.a_bf16[s];
+#pragma unroll
+            for (int i = 0; i < (kTileM * 8) / kPolThreads; ++i) {
+                const int p = tid + i * kPolThreads;
+                const int plane = p & 7, row = p >> 3;
+                const float4 lo = *reinterpret_cast<const float4*>(src + row * kChunkK + plane * 8);
+                const float4 hi = *reinterpret_cast<const float4*>(src + row * kChunkK + plane * 8 + 4);
+                float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                if (c == kNumChunks - 1) {  // only k = 960 (obs column 963) is real in the last chunk
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (plane * 8 + j >= kEncIn - (kNumChunks - 1) * kChunkK) v[j] = 0.f;
+                }
+                uint4 o;
+                o.x = pack_bf16(v[0], v[1]);
+                o.y = pack_bf16(v[2], v[3]);
+                o.z = pack_bf16(v[4], v[5]);
+                o.w = pack_bf16(v[6], v[7]);
+                *reinterpret_cast<uint4*>(dst + plane * kAPlane + row * 16) = o;
+            }
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const int n_mma = (c == kNumChunks - 1) ? 1 : kChunkK / 16;
+                const uint32_t a0 = sptr(sm.l0.a_bf16[s]), b0 = sptr(sm.l0.w0[s]);
+                for (int j = 0; j < n_mma; ++j)
+                    umma(tmem + 0, make_desc(a0 + j * 2 * kAPlane, kAPlane), make_desc(b0 + j * 2 * 80 * 16, 80 * 16),
+                         idesc0, (c | j) != 0);
+                umma_commit(&sm.mma_done[s]);
+                mma_pending[s] = 1;
+            }
+        }
+        if (tid == 0) {  // drain: every layer-0 MMA retired (both stages), then signal the accumulator
+            for (int s = 0; s < 2; ++s)
+                if (mma_pending[s]) {
+                    mb_wait(&sm.mma_done[s], ph_mma[s]);
+                    ph_mma[s] ^= 1;
+                    mma_pending[s] = 0;
+                }
+            // layer-0 buffers are free now: start the bulk copy of W1 into the layer region
+            mb_expect_tx(&sm.w_full, weight_bytes(1));
+            bulk_g2s(sm.ln.w, packed + weight_offset(1), weight_bytes(1), &sm.w_full);
+        }
+        __syncthreads();  // everyone may now read D0 from TMEM and overwrite the layer-0 shared buffers
+        tc_fence_after();
+
+        // =========================================================== layers: epilogue of l feeds layer l+1
+#pragma unroll 1
+        for (int l = 0; l < kNumLayers; ++l) {
+            const int n_pad = layer_n(l);
+            const uint32_t d_col = (l & 1) ? 256u : 0u;  // accumulator region of layer l
+            const float* __restrict__ bias = reinterpret_cast<const float*>(packed + bias_offset(l));
+            const int row = (warp & 3) * 32 + lane;       // TMEM lane == tile row
+            const int half = warp >> 2;                   // column half handled by this warp
+            const int cols_per_half = n_pad / 2;
+            const uint32_t t_lane = (uint32_t)((warp & 3) * 32) << 16;
+            unsigned char* act_out = sm.ln.act[l & 1];    // A operand of layer l+1
+            if (l < kNumLayers - 1) {
+                for (int n0 = half * cols_per_half; n0 < (half + 1) * cols_per_half; n0 += 8) {
+                    float v[8];
+                    tmem_ld8(tmem + t_lane + d_col + n0, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = leaky(v[j] + __ldg(bias + n0 + j));
+                    if (l == 1 && n0 == 56) {
+                        // layer 2 consumes [e(60), obs[:,0:4]] (W2's columns are permuted accordingly at pack time)
+                        const int grow = row0 + row;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[4 + j] = grow < n_envs ? __ldg(obs + (size_t)grow * obs_stride + j) : 0.f;
+                    }
+                    uint4 o;
+                    o.x = pack_bf16(v[0], v[1]);
+                    o.y = pack_bf16(v[2], v[3]);
+                    o.z = pack_bf16(v[4], v[5]);
+                    o.w = pack_bf16(v[6], v[7]);
+                    *reinterpret_cast<uint4*>(act_out + (n0 >> 3) * kAPlane + row * 16) = o;
+                }
+                tc_fence_before();
+                fence_async_smem();
+                __syncthreads();
+                // ---- layer l+1: D = act_out x W^T
+                if (tid == 0) {
+                    tc_fence_after();
+                    mb_wait(&sm.w_full, ph_w);
+                    const int ln = l + 1, k_pad = layer_k(ln), nn = layer_n(ln);
+                    const uint32_t idesc = make_idesc(nn), a0 = sptr(act_out), b0 = sptr(sm.ln.w);
+                    const uint32_t dn = (ln & 1) ? 256u : 0u;
+                    for (int j = 0; j < k_pad / 16; ++j)
+                        umma(tmem + dn, make_desc(a0 + j * 2 * kAPlane, kAPlane), make_desc(b0 + j * 2 * nn * 16, nn * 16),
+                             idesc, j != 0);
+                    umma_commit(&sm.acc_done);
+                    mb_wait(&sm.acc_done, ph_acc);  // accumulator complete, weight buffer free
+                    if (ln + 1 < kNumLayers) {      // prefetch the next layer's weights during this layer's epilogue
+                        mb_expect_tx(&sm.w_full, weight_bytes(ln + 1));
+                        bulk_g2s(sm.ln.w, packed + weight_offset(ln + 1), weight_bytes(ln + 1), &sm.w_full);
+                    }
+                }
+                ph_w ^= 1;
+                ph_acc ^= 1;
+                __syncthreads();
+                tc_fence_after();
+            } else {
+                // ---- last layer: mean = tanh(D5 + b5), two real columns
+                if (half == 0) {
+                    float v[8];
+                    tmem_ld8(tmem + t_lane + d_col, v);
+                    const int grow = row0 + row;
+                    if (grow < n_envs) {
+                        float2 m;
+                        m.x = tanhf(v[0] + __ldg(bias));
+                        m.y = tanhf(v[1] + __ldg(bias + 1));
+                        *reinterpret_cast<float2*>(mean + 2 * (size_t)grow) = m;
+                    }
+                }
+                tc_fence_before();
+                __syncthreads();  // TMEM reads finished before the next tile's MMAs overwrite the accumulators
+                tc_fence_after();
+            }
+        }
+    }
+
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- packing
+struct PackArgs {
+    const float* w[6];
+    const float* b[6];
+    int in_dim[6], out_dim[6];
+};
+
+__global__ void policy_pack_kernel(const __grid_constant__ PackArgs a, unsigned char* __restrict__ packed) {
+    const int l = blockIdx.y;
+    const int k_pad = layer_k(l), n_pad = layer_n(l), k_real = layer_k_real(l), n_real = layer_n_real(l);
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(packed + weight_offset(l));
+    const int total = (l == 0 ? kNumChunks * kChunkK : k_pad) * n_pad;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        // idx enumerates (plane-major) the packed image: [chunk][plane][n][8] for layer 0, [plane][n][8] otherwise
+        const int j = idx & 7;
+        const int n = (idx >> 3) % n_pad;
+        const int plane_g = (idx >> 3) / n_pad;  // global plane index = k / 8 (layer 0: chunk * 8 + plane)
+        const int k = plane_g * 8 + j;
+        float v = 0.f;
+        if (n < n_real && k < k_real) {
+            int src_k = k;
+            if (l == 2) src_k = (k < 60) ? k + 4 : k - 60;  // operand order [e(60), obs[:,0:4]] -> reference [x(4), e(60)]
+            v = a.w[l][(size_t)n * a.in_dim[l] + src_k];
+        }
+        dst[idx] = __float2bfloat16_rn(v);
+    }
+    float* bdst = reinterpret_cast<float*>(packed + bias_offset(l));
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_pad; n += gridDim.x * blockDim.x)
+        bdst[n] = n < n_real ? a.b[l][n] : 0.f;
+}
+
+__global__ void gaussian_act_kernel(const float* __restrict__ mean, const float* __restrict__ log_std,
+                                    const float* __restrict__ eps, int n, float* __restrict__ actions,
+                                    float* __restrict__ log_prob) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float lp = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float ls = fminf(fmaxf(__ldg(log_std + j), -20.f), 2.f);
+        const float sd = expf(ls);
+        const float m = mean[2 * i + j];
+        const float a = fminf(fmaxf(fmaf(sd, eps[2 * i + j], m), -1.f), 1.f);
+        actions[2 * i + j] = a;
+        const float d = a - m;
+        lp += -(d * d) / (2.f * sd * sd) - ls - 0.91893853320467274178f;
+    }
+    if (log_prob) log_prob[i] = lp;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace rover
+
+extern "C" int64_t rover_policy_pack(const RoverPolicyWeights* weights, void* packed, void* stream) {
+    using namespace rover;
+    if (packed == nullptr) return kPackedBytes;
+    if (weights == nullptr) {
+        fail("rover_policy_pack: weights is NULL");
+        return -1;
+    }
+    PackArgs a;
+    for (int l = 0; l < 6; ++l) {
+        if (!weights->w[l] || !weights->b[l] || weights->in_dim[l] < layer_k_real(l) ||
+            weights->out_dim[l] != layer_n_real(l)) {
+            fail("rover_policy_pack: layer %d has shape [%d,%d], expected [%d,%d]", l, weights->out_dim[l],
+                 weights->in_dim[l], layer_n_real(l), layer_k_real(l));
+            return -1;
+        }
+        a.w[l] = weights->w[l];
+        a.b[l] = weights->b[l];
+        a.in_dim[l] = weights->in_dim[l];
+        a.out_dim[l] = weights->out_dim[l];
+    }
+    policy_pack_kernel<<<dim3(64, 6), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, static_cast<unsigned char*>(packed));
+    return check_launch("policy_pack_kernel") ? -1 : kPackedBytes;
+}
+
+extern "C" int rover_policy_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed,
+                                    float* mean, void* stream) {
+    using namespace rover;
+    ROVER_CHECK(n_envs >= 0, "rover_policy_forward: negative n_envs");
+    if (n_envs == 0) return 0;
+    ROVER_CHECK(obs && packed && mean, "rover_policy_forward: NULL argument");
+    ROVER_CHECK(obs_stride >= kObsCols && obs_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0,
+                "rover_policy_forward: obs rows must be 16-byte aligned (obs_stride %% 4 == 0, got %d); allocate the "
+                "observation buffer with ops.alloc_obs()", obs_stride);
+    ROVER_CHECK((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "rover_policy_forward: packed blob not 128B aligned");
+    static EncodeTiledFn encode = nullptr;
+    static int n_sms = 0;
+    if (!encode) {
+        int dev = 0;
+        ROVER_CUDA(cudaGetDevice(&dev));
+        ROVER_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+        ROVER_CUDA(cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(PolSmem)));
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        ROVER_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        ROVER_CHECK(fn && q == cudaDriverEntryPointSuccess, "rover_policy_forward: cuTensorMapEncodeTiled unavailable");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    alignas(64) CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)kObsCols, (cuuint64_t)n_envs};
+    const cuuint64_t gstride[1] = {(cuuint64_t)obs_stride * 4ull};
+    const cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)kTileM};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult rc = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(obs), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ROVER_CHECK(rc == CUDA_SUCCESS, "rover_policy_forward: cuTensorMapEncodeTiled failed (%d)", (int)rc);
+    const int n_tiles = (n_envs + kTileM - 1) / kTileM;
+    const int grid = n_tiles < n_sms ? n_tiles : n_sms;
+    policy_forward_kernel<<<grid, kPolThreads, sizeof(PolSmem), static_cast<cudaStream_t>(stream)>>>(
+        map, obs, obs_stride, n_envs, static_cast<const unsigned char*>(packed), mean);
+    return check_launch("policy_forward_kernel");
+}
+
+extern "C" int rover_gaussian_act(const float* mean, const float* log_std, const float* eps, int32_t n_envs,
+                                  float* actions, float* log_prob, void* stream) {
+    using namespace rover;
+    ROVER_CHECK(n_envs >= 0, "rover_gaussian_act: negative n_envs");
+    if (n_envs == 0) return 0;
+    ROVER_CHECK(mean && log_std && eps && actions, "rover_gaussian_act: NULL argument");
+    gaussian_act_kernel<<<(n_envs + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(mean, log_std, eps, n_envs,
+                                                                                            actions, log_prob);
+    return check_launch("gaussian_act_kernel");
+}

@@ -1,0 +1,117 @@
+"""``GaussianNeuralNetwork`` -- the skrl Gaussian policy of the reference over the tcgen05 kernel.
+
+Mirrors rover_envs/envs/navigation/learning/skrl/models.py:39-102 (+ ``HeightmapEncoder`` :24-36): same constructor
+arguments, same ``state_dict`` keys as ``best_agent.pt`` (``dense_encoder.encoder_layers.{0,2}``, ``mlp.{0,2,4,6}``,
+``log_std_parameter``), ``compute(inputs, role) -> (mean [N,2], log_std [2], {})``, and ``act`` with skrl 1.1.0
+``GaussianMixin`` semantics (clamp log_std to [-20, 2], reparameterised sample, clip to the action box, summed
+log-prob).  The forward pass is inference-only (no autograd): bf16 operands, fp32 accumulation on the tensor cores.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+WEIGHT_KEYS = ("dense_encoder.encoder_layers.0", "dense_encoder.encoder_layers.2", "mlp.0", "mlp.2", "mlp.4", "mlp.6")
+OBS_COLS = 965
+
+
+def alloc_obs(num_envs: int, device, cols: int = OBS_COLS) -> torch.Tensor:
+    """Observation buffer ``[N, cols]`` whose rows start on 16-byte boundaries (row stride padded to a multiple of
+    4 floats), as the policy kernel's TMA tensor map requires.  Returns the ``[:, :cols]`` view."""
+    stride = (cols + 3) // 4 * 4
+    return torch.zeros(num_envs, stride, dtype=torch.float32, device=device)[:, :cols]
+
+
+class GaussianNeuralNetwork:
+    def __init__(self, observation_space=None, action_space=None, device="cuda:0", mlp_input_size=4,
+                 mlp_layers=(256, 160, 128), mlp_activation="leaky_relu", encoder_input_size=961,
+                 encoder_layers=(80, 60), encoder_activation="leaky_relu", **kwargs):
+        if mlp_activation != "leaky_relu" or encoder_activation != "leaky_relu":
+            raise ValueError(f"Activation function {mlp_activation}/{encoder_activation} not supported.")
+        if (mlp_input_size, tuple(mlp_layers), encoder_input_size, tuple(encoder_layers)) != (4, (256, 160, 128), 961, (80, 60)):
+            raise ValueError("the tcgen05 policy kernel is built for the AAURoverEnv-v0 policy shape "
+                             "(961->80->60 (+4) ->256->160->128->2, configure_models.py:41-53)")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("GaussianNeuralNetwork needs a CUDA device; there is no CPU fallback")
+        self.mlp_input_size, self.encoder_input_size = mlp_input_size, encoder_input_size
+        dims = [(80, 961), (60, 80), (256, 64), (160, 256), (128, 160), (2, 128)]
+        self._params = {}
+        for key, (o, i) in zip(WEIGHT_KEYS, dims):
+            self._params[key + ".weight"] = torch.zeros(o, i, device=self.device)
+            self._params[key + ".bias"] = torch.zeros(o, device=self.device)
+        self.log_std_parameter = torch.zeros(2, device=self.device)
+        self._clip_log_std, self._log_std_min, self._log_std_max = True, -20.0, 2.0  # models.py:65-67
+        n_bytes = int(_lib.load().rover_policy_pack(None, None, None))
+        self._packed = torch.zeros(n_bytes + 128, dtype=torch.uint8, device=self.device)
+        off = (-self._packed.data_ptr()) % 128
+        self._packed = self._packed[off: off + n_bytes]
+        self._dirty = True
+
+    # ---- state dict with the reference's keys
+    def state_dict(self) -> dict:
+        sd = {"log_std_parameter": self.log_std_parameter}
+        sd.update(self._params)
+        return sd
+
+    def load_state_dict(self, sd: dict, strict: bool = True):
+        want = set(self._params) | {"log_std_parameter"}
+        if strict and set(sd) != want:
+            raise KeyError(f"unexpected / missing keys: {sorted(set(sd) ^ want)}")
+        for k in want & set(sd):
+            dst = self.log_std_parameter if k == "log_std_parameter" else self._params[k]
+            src = torch.as_tensor(sd[k]).to(self.device, torch.float32)
+            if src.shape != dst.shape:
+                raise RuntimeError(f"size mismatch for {k}: {tuple(src.shape)} vs {tuple(dst.shape)}")
+            dst.copy_(src)
+        self._dirty = True
+
+    def _pack(self):
+        w = _lib.PolicyWeights()
+        for l, key in enumerate(WEIGHT_KEYS):
+            wt, bs = self._params[key + ".weight"], self._params[key + ".bias"]
+            w.w[l], w.b[l] = wt.data_ptr(), bs.data_ptr()
+            w.in_dim[l], w.out_dim[l] = wt.shape[1], wt.shape[0]
+        rc = _lib.load().rover_policy_pack(C.byref(w), C.c_void_p(self._packed.data_ptr()), _lib.current_stream(self.device))
+        if rc < 0:
+            _lib.check(1)
+        self._dirty = False
+
+    # ---- skrl Model API
+    def compute(self, inputs: dict, role: str = "actor"):
+        """models.py:89-102: ``(mean [N,2], log_std_parameter [2], {})`` for ``inputs["states"] [N,965]``."""
+        states = inputs["states"]
+        _lib.require_cuda(states) if states.is_contiguous() else None
+        if not states.is_cuda or states.dtype != torch.float32 or states.dim() != 2 or states.shape[1] != OBS_COLS:
+            raise RuntimeError("compute: states must be a CUDA fp32 [N,965] tensor")
+        if states.stride(1) != 1 or states.stride(0) % 4 != 0 or states.data_ptr() % 16 != 0:
+            # the reference accepts any tensor; re-home it once into an aligned buffer (one copy kernel)
+            buf = alloc_obs(states.shape[0], states.device)
+            buf.copy_(states)
+            states = buf
+        if self._dirty:
+            self._pack()
+        n = states.shape[0]
+        mean = torch.empty(n, 2, dtype=torch.float32, device=states.device)
+        _lib.check(_lib.load().rover_policy_forward(
+            C.c_void_p(states.data_ptr()), int(states.stride(0)), n, C.c_void_p(self._packed.data_ptr()),
+            C.c_void_p(mean.data_ptr()), _lib.current_stream(states.device)))
+        return mean, self.log_std_parameter, {}
+
+    def act(self, inputs: dict, role: str = "actor", eps: torch.Tensor | None = None):
+        """skrl 1.1.0 ``GaussianMixin.act``: returns ``(actions [N,2], log_prob [N,1], outputs)``.
+        ``eps`` (standard-normal draws) may be supplied for reproducible parity checks."""
+        mean, log_std, outputs = self.compute(inputs, role)
+        n = mean.shape[0]
+        if eps is None:
+            eps = torch.randn(n, 2, device=mean.device)
+        actions = torch.empty_like(mean)
+        log_prob = torch.empty(n, dtype=torch.float32, device=mean.device)
+        _lib.check(_lib.load().rover_gaussian_act(
+            C.c_void_p(mean.data_ptr()), C.c_void_p(log_std.data_ptr()), C.c_void_p(eps.contiguous().data_ptr()), n,
+            C.c_void_p(actions.data_ptr()), C.c_void_p(log_prob.data_ptr()), _lib.current_stream(mean.device)))
+        outputs["mean_actions"] = mean
+        return actions, log_prob.unsqueeze(-1), outputs

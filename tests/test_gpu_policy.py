@@ -1,0 +1,101 @@
+"""GPU: tcgen05 policy forward against (i) a torch emulation of the kernel's numerics (bf16 operands, fp32
+accumulation, bf16 activations between layers) and (ii) the fp32 oracle / the reference network's own outputs
+(tests/golden/policy.npz, generated from best_agent.pt by the unmodified reference model)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork, WEIGHT_KEYS, alloc_obs
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def emulate_bf16(obs, sd):
+    """The kernel's arithmetic: bf16(operands) x bf16(weights) accumulated in fp32, fp32 bias + activation."""
+    act = lambda x: torch.nn.functional.leaky_relu(x, 0.01)  # noqa: E731
+    lin = lambda k, x: _bf(x) @ _bf(sd[k + ".weight"]).T + sd[k + ".bias"]  # noqa: E731
+    e = act(lin(WEIGHT_KEYS[1], act(lin(WEIGHT_KEYS[0], obs[:, 3:964]))))
+    h = torch.cat([obs[:, 0:4], e], dim=1)
+    for k in WEIGHT_KEYS[2:5]:
+        h = act(lin(k, h))
+    return torch.tanh(lin(WEIGHT_KEYS[5], h))
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    from oracle import policy as OP
+
+    z = np.load(os.path.join(golden_dir, "policy.npz"))
+    return z, OP.load_golden_weights(z)
+
+
+def test_policy_forward_reference_checkpoint(cuda_device, golden):
+    from oracle import policy as OP
+
+    z, sd = golden
+    net = GaussianNeuralNetwork(device=cuda_device)
+    net.load_state_dict(sd, strict=True)
+    assert set(net.state_dict()) == set(sd)
+    obs = torch.from_numpy(z["in_obs"])
+    buf = alloc_obs(obs.shape[0], cuda_device)
+    buf.copy_(obs)
+    mean, log_std, _ = net.compute({"states": buf}, role="policy")
+    torch.cuda.synchronize()
+    mean = mean.cpu()
+    assert torch.equal(log_std.cpu(), sd["log_std_parameter"])
+    emu = emulate_bf16(obs, sd)
+    torch.testing.assert_close(mean, emu, rtol=0, atol=4e-3)          # same numerics: bf16 rounding noise only
+    ref = torch.from_numpy(z["ref_mean"])                             # the reference network in fp32
+    assert (mean - ref).abs().max() < 3e-2, (mean - ref).abs().max()  # bf16 operands cannot meet 1e-5
+    torch.testing.assert_close(OP.policy_mean(obs, sd), ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 1000, 4096 + 37])
+def test_policy_forward_tiles_and_tails(cuda_device, golden, n):
+    _, sd = golden
+    net = GaussianNeuralNetwork(device=cuda_device)
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(n)
+    obs = torch.cat([torch.rand(n, 2, generator=g) * 2 - 1, torch.rand(n, 1, generator=g) * 1.3,
+                     torch.rand(n, 1, generator=g) * 2 - 1, torch.randn(n, 961, generator=g) * 0.3], dim=1)
+    # an unaligned [N,965] tensor exercises the re-homing path of compute(); the last ray must not matter
+    states = obs.to(cuda_device)
+    mean, _, _ = net.compute({"states": states})
+    states2 = states.clone()
+    states2[:, 964] = 123.0
+    mean2, _, _ = net.compute({"states": states2})
+    torch.cuda.synchronize()
+    assert torch.equal(mean, mean2), "obs[:, -1] is not an input of the policy (models.py:95)"
+    torch.testing.assert_close(mean.cpu(), emulate_bf16(obs, sd), rtol=0, atol=4e-3)
+
+
+def test_gaussian_act(cuda_device, golden):
+    from oracle import policy as OP
+
+    z, sd = golden
+    net = GaussianNeuralNetwork(device=cuda_device)
+    net.load_state_dict(sd)
+    obs = torch.from_numpy(z["in_obs"]).to(cuda_device)
+    g = torch.Generator().manual_seed(3)
+    eps = torch.randn(obs.shape[0], 2, generator=g) * 3
+    actions, log_prob, out = net.act({"states": obs}, eps=eps.to(cuda_device))
+    a_ref, lp_ref = OP.gaussian_act(out["mean_actions"].cpu(), sd["log_std_parameter"], eps)
+    torch.testing.assert_close(actions.cpu(), a_ref, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(log_prob.cpu(), lp_ref, rtol=1e-4, atol=1e-4)
+    assert actions.abs().max() <= 1.0 and (actions.abs() == 1.0).any()
+
+
+def test_policy_rejects_other_shapes(cuda_device):
+    with pytest.raises(ValueError):
+        GaussianNeuralNetwork(device=cuda_device, mlp_layers=(64, 64))
+    with pytest.raises(ValueError):
+        GaussianNeuralNetwork(device=cuda_device, mlp_activation="relu")
+    net = GaussianNeuralNetwork(device=cuda_device)
+    with pytest.raises(KeyError):
+        net.load_state_dict({"mlp.0.weight": torch.zeros(256, 64)}, strict=True)
