@@ -8,7 +8,8 @@
 // and skrl's GaussianMixin.act sampling (rover_gaussian_act).  319,520 FLOP per environment.
 //
 // One persistent CTA per SM, 256 threads, tile = 128 environments (UMMA M = 128, cta_group::1):
-//   layer 0  K = 961 streamed in 16 chunks of 64 observation columns: a 2-D TMA tensor-map load (fp32, 128 x 64)
+//   layer 0  K = observation column (16-byte aligned TMA box origins; columns outside [3, 964) are zeroed and carry
+//            zero weights), streamed in 16 chunks of 64 columns: a 2-D TMA tensor-map load (fp32, 128 x 64)
 //            + a bulk copy of the matching 80 x 64 bf16 weight chunk land on one mbarrier; all threads convert the
 //            chunk to bf16 in the UMMA K-major no-swizzle ("interleaved") layout; one thread issues the
 //            tcgen05.mma's (D0[128 x 80] in TMEM) and commits to the stage's mbarrier; two stages overlap
@@ -21,6 +22,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rover {
@@ -31,12 +34,12 @@ constexpr int kObsCols = 965;
 constexpr int kEncIn = 961;       // obs[:, 3:964]
 constexpr int kEncInOffset = 3;
 constexpr int kChunkK = 64;
-constexpr int kNumChunks = 16;    // 15 full chunks + 1 chunk with a single real column
+constexpr int kNumChunks = 16;    // observation columns [0, 1024) in chunks of 64; columns outside [3, 964) are zeroed
 constexpr int kAPlane = kTileM * 16 + 16;  // A plane stride (bytes), +16 B skew: conflict-free 16 B stores per plane
 constexpr int kNumLayers = 6;
 
 // padded layer shapes: K (multiple of 16), N (multiple of 16)
-__host__ __device__ constexpr int layer_k(int l) { return l == 0 ? 976 : l == 1 ? 80 : l == 2 ? 64 : l == 3 ? 256 : l == 4 ? 160 : 128; }
+__host__ __device__ constexpr int layer_k(int l) { return l == 0 ? 1024 : l == 1 ? 80 : l == 2 ? 64 : l == 3 ? 256 : l == 4 ? 160 : 128; }
 __host__ __device__ constexpr int layer_n(int l) { return l == 0 ? 80 : l == 1 ? 64 : l == 2 ? 256 : l == 3 ? 160 : l == 4 ? 128 : 16; }
 __host__ __device__ constexpr int layer_k_real(int l) { return l == 0 ? 961 : l == 1 ? 80 : l == 2 ? 64 : l == 3 ? 256 : l == 4 ? 160 : 128; }
 __host__ __device__ constexpr int layer_n_real(int l) { return l == 0 ? 80 : l == 1 ? 60 : l == 2 ? 256 : l == 3 ? 160 : l == 4 ? 128 : 2; }
@@ -153,7 +156,7 @@ struct __align__(128) PolSmem {
 // ---------------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(kPolThreads, 1)
 policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* __restrict__ obs, int obs_stride,
-                      int n_envs, const unsigned char* __restrict__ packed, float* __restrict__ mean) {
+                      int n_envs, const unsigned char* __restrict__ packed, float* __restrict__ mean, int debug_stop) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PolSmem& sm = *reinterpret_cast<PolSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -177,6 +180,26 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    if (debug_stop == 1) {  // bring-up aid (ROVER_POLICY_DEBUG_STOP): TMEM alloc / dealloc only
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        return;
+    }
+
+    if (debug_stop >= 4 && debug_stop <= 6) {  // bring-up aid: isolate the async copies
+        if (tid == 0) {
+            const uint32_t bytes = (debug_stop == 4 ? kTileM * kChunkK * 4 : 0) + (debug_stop == 5 ? kW0ChunkBytes : 0) +
+                                   (debug_stop == 6 ? kTileM * kChunkK * 4 + kW0ChunkBytes : 0);
+            mb_expect_tx(&sm.full[0], bytes);
+            if (debug_stop != 5) tma_2d(sm.l0.stage_f32[0], &obs_map, 0, 0, &sm.full[0]);
+            if (debug_stop != 4) bulk_g2s(sm.l0.w0[0], packed, kW0ChunkBytes, &sm.full[0]);
+        }
+        mb_wait(&sm.full[0], 0);
+        if (tid < 2 && blockIdx.x == 0) mean[tid] = debug_stop == 5 ? (float)sm.l0.w0[0][tid] : sm.l0.stage_f32[0][tid];
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+        return;
+    }
 
     // barrier phase bookkeeping (each barrier completes once per use; parity flips per completion)
     uint32_t ph_full[2] = {0, 0}, ph_mma[2] = {0, 0}, ph_w = 0, ph_acc = 0;
@@ -188,7 +211,7 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
         const uint32_t idesc0 = make_idesc(layer_n(0));
         if (tid == 0) {  // prologue: chunk 0 into stage 0
             mb_expect_tx(&sm.full[0], kTileM * kChunkK * 4 + kW0ChunkBytes);
-            tma_2d(sm.l0.stage_f32[0], &obs_map, kEncInOffset, row0, &sm.full[0]);
+            tma_2d(sm.l0.stage_f32[0], &obs_map, 0, row0, &sm.full[0]);
             bulk_g2s(sm.l0.w0[0], packed, kW0ChunkBytes, &sm.full[0]);
         }
         for (int c = 0; c < kNumChunks; ++c) {
@@ -201,7 +224,7 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
                     mma_pending[s1] = 0;
                 }
                 mb_expect_tx(&sm.full[s1], kTileM * kChunkK * 4 + kW0ChunkBytes);
-                tma_2d(sm.l0.stage_f32[s1], &obs_map, kEncInOffset + (c + 1) * kChunkK, row0, &sm.full[s1]);
+                tma_2d(sm.l0.stage_f32[s1], &obs_map, (c + 1) * kChunkK, row0, &sm.full[s1]);
                 bulk_g2s(sm.l0.w0[s1], packed + (size_t)(c + 1) * kW0ChunkBytes, kW0ChunkBytes, &sm.full[s1]);
             }
             mb_wait(&sm.full[s], ph_full[s]);
@@ -219,10 +242,12 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
                 const float4 lo = *reinterpret_cast<const float4*>(src + row * kChunkK + plane * 8);
                 const float4 hi = *reinterpret_cast<const float4*>(src + row * kChunkK + plane * 8 + 4);
                 float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-                if (c == kNumChunks - 1) {  // only k = 960 (obs column 963) is real in the last chunk
+                if (c == 0 || c == kNumChunks - 1) {  // encoder input = observation columns [3, 964) (models.py:95)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (plane * 8 + j >= kEncIn - (kNumChunks - 1) * kChunkK) v[j] = 0.f;
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = c * kChunkK + plane * 8 + j;
+                        if (col < kEncInOffset || col >= kEncInOffset + kEncIn) v[j] = 0.f;
+                    }
                 }
                 uint4 o;
                 o.x = pack_bf16(v[0], v[1]);
@@ -233,9 +258,9 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
             }
             fence_async_smem();
             __syncthreads();
-            if (tid == 0) {
+            if (tid == 0 && debug_stop != 2) {
                 tc_fence_after();
-                const int n_mma = (c == kNumChunks - 1) ? 1 : kChunkK / 16;
+                const int n_mma = kChunkK / 16;
                 const uint32_t a0 = sptr(sm.l0.a_bf16[s]), b0 = sptr(sm.l0.w0[s]);
                 for (int j = 0; j < n_mma; ++j)
                     umma(tmem + 0, make_desc(a0 + j * 2 * kAPlane, kAPlane), make_desc(b0 + j * 2 * 80 * 16, 80 * 16),
@@ -257,6 +282,11 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
         }
         __syncthreads();  // everyone may now read D0 from TMEM and overwrite the layer-0 shared buffers
         tc_fence_after();
+        if (debug_stop == 2 || debug_stop == 3) {  // bring-up aid: stop after the layer-0 stream
+            if (tid == 0) mb_wait(&sm.w_full, ph_w);
+            __syncthreads();
+            break;
+        }
 
         // =========================================================== layers: epilogue of l feeds layer l+1
 #pragma unroll 1
@@ -357,11 +387,10 @@ __global__ void policy_pack_kernel(const __grid_constant__ PackArgs a, unsigned 
         const int plane_g = (idx >> 3) / n_pad;  // global plane index = k / 8 (layer 0: chunk * 8 + plane)
         const int k = plane_g * 8 + j;
         float v = 0.f;
-        if (n < n_real && k < k_real) {
-            int src_k = k;
-            if (l == 2) src_k = (k < 60) ? k + 4 : k - 60;  // operand order [e(60), obs[:,0:4]] -> reference [x(4), e(60)]
-            v = a.w[l][(size_t)n * a.in_dim[l] + src_k];
-        }
+        int src_k = k;
+        if (l == 0) src_k = k - kEncInOffset;               // layer-0 K index = observation column
+        if (l == 2) src_k = (k < 60) ? k + 4 : k - 60;      // operand order [e(60), obs[:,0:4]] -> reference [x(4), e(60)]
+        if (n < n_real && src_k >= 0 && src_k < k_real) v = a.w[l][(size_t)n * a.in_dim[l] + src_k];
         dst[idx] = __float2bfloat16_rn(v);
     }
     float* bdst = reinterpret_cast<float*>(packed + bias_offset(l));
@@ -453,8 +482,9 @@ extern "C" int rover_policy_forward(const float* obs, int32_t obs_stride, int32_
     ROVER_CHECK(rc == CUDA_SUCCESS, "rover_policy_forward: cuTensorMapEncodeTiled failed (%d)", (int)rc);
     const int n_tiles = (n_envs + kTileM - 1) / kTileM;
     const int grid = n_tiles < n_sms ? n_tiles : n_sms;
+    const char* dbg = getenv("ROVER_POLICY_DEBUG_STOP");
     policy_forward_kernel<<<grid, kPolThreads, sizeof(PolSmem), static_cast<cudaStream_t>(stream)>>>(
-        map, obs, obs_stride, n_envs, static_cast<const unsigned char*>(packed), mean);
+        map, obs, obs_stride, n_envs, static_cast<const unsigned char*>(packed), mean, dbg ? atoi(dbg) : 0);
     return check_launch("policy_forward_kernel");
 }
 
