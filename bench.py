@@ -321,6 +321,41 @@ def run_ours(args):
     except Exception as e:  # the headline number must survive a failure of the extra measurements
         extra = {"error": f"{type(e).__name__}: {e}"}
 
+    # ------------------------------------------------------------------ extra: policy forward (cfg-4)
+    try:
+        from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork, alloc_obs
+
+        n_pol = 65536
+        net = GaussianNeuralNetwork(device=dev)
+        gen3 = torch.Generator().manual_seed(7 + rank)
+        net.load_state_dict({k: (torch.randn(v.shape, generator=gen3) * (0.05 if v.dim() == 2 else 0.01))
+                             for k, v in net.state_dict().items()})
+        pol_obs = alloc_obs(n_pol, dev)
+        pol_obs.copy_(torch.randn(n_pol, 965, device=dev) * 0.3)
+        ksteps = max(min(args.steps, 100), 3)
+        ms_pol = time_steps(lambda i: net.compute({"states": pol_obs}), ksteps, 3, flush, stream)
+        tp = torch.tensor([ms_pol.sum()], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        t_pol = float(tp[0]) / ksteps * 1e-3
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+        extra["policy_forward"] = {
+            "workload": f"cfg-4: skrl Gaussian policy (961->80->60 (+4) ->256->160->128->2), {n_pol} envs/GPU, bf16 operands "
+                        "/ fp32 accumulate on tcgen05, random-init weights",
+            "env_forwards_per_s": n_pol * world / t_pol, "us_per_launch": t_pol * 1e6,
+            "tflops": n_pol * 319520 / t_pol / 1e12,
+            "roofline_frac_tensor": n_pol * 319520 / t_pol / 1e12 / tf_peak, "tensor_peak_tflops": tf_peak,
+            "roofline_frac_hbm": n_pol * (965 * 4 + 8) / t_pol / 1e9 / peak,
+            "note": "standalone forward reads 3860 B/env of fp32 observations: 83 FLOP/B < ridge, HBM-bound (SURVEY 8d)",
+        }
+    except Exception as e:
+        extra["policy_forward"] = {"error": f"{type(e).__name__}: {e}"}
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
