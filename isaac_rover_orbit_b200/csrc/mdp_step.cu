@@ -58,7 +58,24 @@ __device__ __forceinline__ float norm2(float x, float y) {
 }
 
 // contact_sensor force_matrix_w [B,1,3] of one env: L2 norm over bodies per axis, summed over axes, > 1
+template <int kBodies>
+__device__ __forceinline__ bool collision_active_fixed(const float* __restrict__ f) {
+    // all loads are issued before the first use (one memory round trip); accumulation order = body order
+    float v[3 * kBodies];
+#pragma unroll
+    for (int k = 0; k < 3 * kBodies; ++k) v[k] = __ldg(f + k);
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+    for (int b = 0; b < kBodies; ++b) {
+        sx = __fadd_rn(sx, __fmul_rn(v[3 * b], v[3 * b]));
+        sy = __fadd_rn(sy, __fmul_rn(v[3 * b + 1], v[3 * b + 1]));
+        sz = __fadd_rn(sz, __fmul_rn(v[3 * b + 2], v[3 * b + 2]));
+    }
+    return __fadd_rn(__fadd_rn(sqrtf(sx), sqrtf(sy)), sqrtf(sz)) > 1.f;
+}
+
 __device__ __forceinline__ bool collision_active(const float* __restrict__ f, int num_bodies) {
+    if (num_bodies == 14) return collision_active_fixed<14>(f);  // AAU rover: 6 Drive + 4 Steer + 3 Boogie + Body
     float sx = 0.f, sy = 0.f, sz = 0.f;
     for (int b = 0; b < num_bodies; ++b) {
         const float x = __ldg(f + 3 * b), y = __ldg(f + 3 * b + 1), z = __ldg(f + 3 * b + 2);
@@ -205,20 +222,39 @@ __device__ __forceinline__ void terrain_cell(const Tables& T, float x, float y, 
     row = (int)min(max(cy, 0LL), (long long)(T.H - 1));
 }
 
-// CommandTerm._resample + _resample_command + sample_new_targets (terrain_importer.py:74-95, 134-175)
+// CommandTerm._resample + _resample_command + sample_new_targets (terrain_importer.py:74-95, 134-175).
+// The reference's rejection loop is sequential (one host sync per round); here the candidates of a batch of 8 rounds
+// are generated together and their mask bytes fetched concurrently (one memory round trip per batch instead of per
+// round), then the first valid round wins -- the same candidate the sequential loop would have accepted.
 __device__ __forceinline__ bool resample_command(int i, const RoverMdpParams& P, const RoverMdpState& S, const Tables& T,
                                                  float ox, float oy, const float* __restrict__ theta_u, int n_rounds,
                                                  float heading_u, float& cx, float& cy, float& cz, float& chead) {
     const float pi_f = 3.1415927f;  // torch.pi as fp32; the reference computes rand * 2 * pi left to right
+    constexpr int kBatch = 8;
     float x = 0.f, y = 0.f;
     int col = 0, row = 0;
     bool bad = true;
-    for (int r = 0; r < n_rounds && bad; ++r) {
-        const float th = __fmul_rn(__fmul_rn(__ldg(theta_u + (size_t)i * n_rounds + r), 2.f), pi_f);  // :169
-        x = __fadd_rn(__fmul_rn(cosf(th), P.target_distance), ox);                                        // :172
-        y = __fadd_rn(__fmul_rn(sinf(th), P.target_distance), oy);                                        // :173
-        terrain_cell(T, x, y, col, row);
-        bad = __ldg(T.safe_mask + (size_t)row * T.W + col) == 1;                                          // :220
+    for (int r0 = 0; r0 < n_rounds && bad; r0 += kBatch) {
+        float u[kBatch], xs[kBatch], ys[kBatch];
+        int cols[kBatch], rows[kBatch];
+        uint8_t m[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) u[k] = (r0 + k < n_rounds) ? __ldg(theta_u + (size_t)i * n_rounds + r0 + k) : 0.f;
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const float th = __fmul_rn(__fmul_rn(u[k], 2.f), pi_f);                      // :169
+            xs[k] = __fadd_rn(__fmul_rn(cosf(th), P.target_distance), ox);               // :172
+            ys[k] = __fadd_rn(__fmul_rn(sinf(th), P.target_distance), oy);               // :173
+            terrain_cell(T, xs[k], ys[k], cols[k], rows[k]);
+            m[k] = __ldg(T.safe_mask + (size_t)rows[k] * T.W + cols[k]);                 // :220
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            if (bad && r0 + k < n_rounds) {  // sequential semantics: the first valid round, else the last tried
+                x = xs[k], y = ys[k], col = cols[k], row = rows[k];
+                bad = m[k] == 1;
+            }
+        }
     }
     cx = x;
     cy = y;
@@ -241,7 +277,8 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
                      int obs_stride, int phases) {
     __shared__ int warp_cnt[ROVER_MDP_BLOCK / 32];
     __shared__ int block_base;
-    __shared__ float red[ROVER_MDP_BLOCK / 32][kStats];
+    constexpr int kRedRows = (ROVER_MDP_BLOCK / 32 > ROVER_MDP_BLOCK / kStats) ? ROVER_MDP_BLOCK / 32 : ROVER_MDP_BLOCK / kStats;
+    __shared__ float red[kRedRows][kStats];
     __shared__ bool is_last;
     const int i = blockIdx.x * ROVER_MDP_BLOCK + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -403,11 +440,23 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (is_last && threadIdx.x < kStats) {
+    if (is_last) {
+        // fixed summation order (deterministic): thread (g, k) sums blocks g, g+G, ... of statistic k, then the G
+        // partials are combined in order of g
+        constexpr int G = ROVER_MDP_BLOCK / kStats;
+        const int k = threadIdx.x % kStats, g = threadIdx.x / kStats;
         float v = 0.f;
-        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(block_stats + (size_t)b * kStats + threadIdx.x);
-        stats[threadIdx.x] += v;
-        if (threadIdx.x == 0) *done_counter = 0u;  // re-arm for the next launch
+        if (g < G)
+            for (unsigned b = g; b < gridDim.x; b += G) v += __ldcg(block_stats + (size_t)b * kStats + k);
+        __syncthreads();  // red[] is free: every thread passed the block-level reduction above
+        if (g < G) red[g][k] = v;
+        __syncthreads();
+        if (threadIdx.x < kStats) {
+            float t = 0.f;
+            for (int q = 0; q < G; ++q) t += red[q][threadIdx.x];
+            stats[threadIdx.x] += t;
+            if (threadIdx.x == 0) *done_counter = 0u;  // re-arm for the next launch
+        }
     }
 }
 
