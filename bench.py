@@ -291,8 +291,41 @@ def run_ours(args):
                               s.theta_u, obs)
 
         ksteps = max(min(args.steps, 200), 3)
-        ms_full = time_steps(full_step, ksteps, 3, flush, stream)
-        ms_mdp = time_steps(mdp_only, ksteps, 3, flush, stream)
+        # the step is launch-bound on the host side (3 ctypes launches + 1 torch op ~ 40 us of Python per step):
+        # capture each input set's step once in a CUDA graph and replay it (one cudaGraphLaunch per step)
+        def graphed(fn):
+            if args.no_graph:
+                return fn
+            for i in range(4):
+                fn(i)  # warm-up outside capture (one-time attribute / driver-entry-point calls)
+            torch.cuda.synchronize()
+            graphs = []
+            for i in range(4):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn(i)
+                graphs.append(g)
+            return lambda i: graphs[i % 4].replay()
+
+        step_body = full_step
+        if world > 1:
+            def step_body(i):  # noqa: F811  (kernels only; the collective is issued after the replay)
+                s = sets[i % 4]
+                torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)
+                ops.mdp_pre_step(buf, params, s.actions, s.force_matrix_w)
+                ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
+                                  s.theta_u, obs)
+                ops.height_scan(s.root_pos_w, s.root_quat_w, rays, grid, out=obs[:, 4:], variant=args.variant)
+        g_full = graphed(step_body)
+        g_mdp = graphed(mdp_only)
+
+        def run_full(i):
+            g_full(i)
+            if world > 1:
+                stats.all_reduce_async()
+
+        ms_full = time_steps(run_full, ksteps, 3, flush, stream)
+        ms_mdp = time_steps(g_mdp, ksteps, 3, flush, stream)
         buf.stats.zero_()
         mdp_only(0)
         torch.cuda.synchronize()
@@ -307,7 +340,7 @@ def run_ours(args):
                             + (" + NCCL episode-stat all-reduce" if world > 1 else ""),
                 "env_steps_per_s": n_step * world * ksteps / (float(tf[0]) * 1e-3),
                 "ms_per_step": float(tf[0]) / ksteps,
-                "gpu_launches_per_step": 3,
+                "gpu_launches_per_step": 3, "cuda_graph": not args.no_graph,
                 "roofline_frac_hbm": full_bytes / (float(tf[0]) / ksteps * 1e-3) / 1e9 / peak,
                 "resets_in_one_step": resets_per_step,
             },
@@ -446,6 +479,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=int(os.environ.get("ROVER_SCAN_VARIANT", "4")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the fused step kernel by kernel instead of replaying CUDA graphs")
     ap.add_argument("--init-on-cpu", action="store_true", help="build the init-time tables on the host (profiling)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -210,10 +210,17 @@ class MdpBuffers:
             f(_lib.STATS_LEN), f(max(blocks, 1) * _lib.STATS_LEN + 1))
 
     def state_struct(self) -> _lib.MdpState:
-        return _lib.MdpState(*[getattr(self, k).data_ptr() for k in _lib._STATE_FIELDS])
+        """Host struct of device pointers; built once (the buffers are never re-allocated)."""
+        st = self.__dict__.get("_state_struct")
+        if st is None:
+            st = self.__dict__["_state_struct"] = _lib.MdpState(*[getattr(self, k).data_ptr() for k in _lib._STATE_FIELDS])
+        return st
 
     def out_struct(self) -> _lib.MdpOut:
-        return _lib.MdpOut(*[getattr(self, k).data_ptr() for k in _lib._OUT_FIELDS])
+        out = self.__dict__.get("_out_struct")
+        if out is None:
+            out = self.__dict__["_out_struct"] = _lib.MdpOut(*[getattr(self, k).data_ptr() for k in _lib._OUT_FIELDS])
+        return out
 
 
 class TerrainTablesHandle:
