@@ -24,11 +24,12 @@
 
 namespace rover {
 
-constexpr int kPipeGroups = 3;          // consumer groups; group q resolves environments it = q, q+3, ... of the CTA
-constexpr int kPipeConsumerWarps = 8;   // warps per consumer group
+constexpr int kPipeGroups = 2;          // consumer groups; group q resolves environments it = q, q+2, ... of the CTA
+constexpr int kPipeConsumerWarps = 11;  // warps per consumer group (1 + 2*11 = 23 warps -> 24-warp allocation, 80 regs)
+constexpr int kPipeRaysPerThread = 3;   // rays resolved together by one consumer thread (ILP)
 constexpr int kPipeConsumers = 32 * kPipeConsumerWarps;
 constexpr int kPipeThreads = 32 * (1 + kPipeGroups * kPipeConsumerWarps);
-constexpr int kPipeStages = 9;          // ring depth (multiple of kPipeGroups: a stage always serves the same group)
+constexpr int kPipeStages = 8;          // ring depth (multiple of kPipeGroups: a stage always serves the same group)
 constexpr int kPipeWin = 26;            // window cells per axis
 constexpr int kPipeCtasPerSm = 1;
 constexpr int kPipeMaxRays = 1024;      // pattern table held in shared memory (float4 per ray)
@@ -277,12 +278,12 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
                 const int cmax = h.ncols - 1, rmax = h.nrows - 1;
                 const float wx0 = st.xp[0].lo, wy0 = st.yp[0].lo, wx1 = st.xp[cmax].hi, wy1 = st.yp[rmax].hi;
                 const float inv_dx = pc.inv_dx, inv_dy = pc.inv_dy;
-                for (int r0 = 0; r0 < n_rays; r0 += 4 * kPipeConsumers) {
+                for (int r0 = 0; r0 < n_rays; r0 += kPipeRaysPerThread * kPipeConsumers) {
                     // branch-free body over 4 rays: every load uses a clamped (always valid) index, stores are
                     // predicated, anything unusual is deferred -> the four dependency chains interleave (ILP)
                     unsigned defer = 0;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < kPipeRaysPerThread; ++u) {
                         const int r = r0 + u * kPipeConsumers + t;
                         const bool valid = r < n_rays;
                         const float4 v = sm.pattern[valid ? r : 0];
@@ -304,7 +305,7 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
                     }
                     // rare: cell guess off by one, ray on the closed far border or outside the grid, general cell
                     if (defer != 0u) {
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < kPipeRaysPerThread; ++u) {
                             if (!((defer >> u) & 1u)) continue;
                             const int r = r0 + u * kPipeConsumers + t;
                             const float4 v = sm.pattern[r];
