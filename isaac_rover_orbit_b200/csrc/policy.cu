@@ -37,6 +37,8 @@ constexpr int kChunkK = 64;
 constexpr int kNumChunks = 16;    // observation columns [0, 1024) in chunks of 64; columns outside [3, 964) are zeroed
 constexpr int kAPlane = kTileM * 16 + 16;  // A plane stride (bytes), +16 B skew: conflict-free 16 B stores per plane
 constexpr int kNumLayers = 6;
+constexpr int kStagesF = 4;  // fp32 observation stages (prefetch distance 3 chunks)
+constexpr int kStagesW = 3;  // layer-0 weight-chunk stages (prefetch distance 2 chunks)
 
 // padded layer shapes: K (multiple of 16), N (multiple of 16)
 __host__ __device__ constexpr int layer_k(int l) { return l == 0 ? 1024 : l == 1 ? 80 : l == 2 ? 64 : l == 3 ? 256 : l == 4 ? 160 : 128; }
@@ -137,17 +139,18 @@ __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x
 struct __align__(128) PolSmem {
     union {
         struct {  // layer 0 streaming
-            float stage_f32[2][kTileM * kChunkK];              // 2 x 32 KB, TMA destination
+            float stage_f32[kStagesF][kTileM * kChunkK];       // 4 x 32 KB, TMA destinations (3 chunks in flight)
             unsigned char a_bf16[2][8 * kAPlane];              // 2 x 16.1 KB
-            unsigned char w0[2][kW0ChunkBytes];                // 2 x 10 KB
+            unsigned char w0[kStagesW][kW0ChunkBytes];         // 3 x 10 KB
         } l0;
         struct {  // layers 1..5
             unsigned char act[2][32 * kAPlane];                // up to K = 256 -> 32 planes, 2 x 64.5 KB
             unsigned char w[(256 / 8) * 160 * 16];             // largest weight image (layer 3): 80 KB
         } ln;
     };
-    unsigned long long full[2];      // TMA / bulk copies of a layer-0 stage landed
-    unsigned long long mma_done[2];  // MMAs reading a layer-0 stage retired
+    unsigned long long full[kStagesF];   // observation chunk landed in stage_f32[s]
+    unsigned long long w0_full[kStagesW];  // weight chunk landed in w0[s]
+    unsigned long long mma_done;     // the MMAs of the previous layer-0 chunk retired
     unsigned long long w_full;       // weights of the current layer (l >= 1) landed
     unsigned long long acc_done;     // accumulator of the current layer complete
     uint32_t tmem_base;
@@ -163,10 +166,9 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
     const int n_tiles = (n_envs + kTileM - 1) / kTileM;
 
     if (tid == 0) {
-        mb_init(&sm.full[0], 1);
-        mb_init(&sm.full[1], 1);
-        mb_init(&sm.mma_done[0], 1);
-        mb_init(&sm.mma_done[1], 1);
+        for (int i = 0; i < kStagesF; ++i) mb_init(&sm.full[i], 1);
+        for (int i = 0; i < kStagesW; ++i) mb_init(&sm.w0_full[i], 1);
+        mb_init(&sm.mma_done, 1);
         mb_init(&sm.w_full, 1);
         mb_init(&sm.acc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -202,39 +204,47 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
     }
 
     // barrier phase bookkeeping (each barrier completes once per use; parity flips per completion)
-    uint32_t ph_full[2] = {0, 0}, ph_mma[2] = {0, 0}, ph_w = 0, ph_acc = 0;
-    uint32_t mma_pending[2] = {0, 0};  // thread 0: a commit is outstanding on mma_done[s]
+    uint32_t ph_full = 0, ph_w0 = 0, ph_mma = 0, ph_w = 0, ph_acc = 0;  // bit s = parity of stage s
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int row0 = tile * kTileM;
-        // =========================================================== layer 0: stream K in 16 chunks of 64
+        // =========================================================== layer 0: stream K in 16 chunks of 64 columns
         const uint32_t idesc0 = make_idesc(layer_n(0));
-        if (tid == 0) {  // prologue: chunk 0 into stage 0
-            mb_expect_tx(&sm.full[0], kTileM * kChunkK * 4 + kW0ChunkBytes);
-            tma_2d(sm.l0.stage_f32[0], &obs_map, 0, row0, &sm.full[0]);
-            bulk_g2s(sm.l0.w0[0], packed, kW0ChunkBytes, &sm.full[0]);
+        if (tid == 0) {  // prologue: observation chunks 0..2 and weight chunks 0..1 in flight
+            for (int c = 0; c < kStagesF - 1; ++c) {
+                mb_expect_tx(&sm.full[c], kTileM * kChunkK * 4);
+                tma_2d(sm.l0.stage_f32[c], &obs_map, c * kChunkK, row0, &sm.full[c]);
+            }
+            for (int c = 0; c < kStagesW - 1; ++c) {
+                mb_expect_tx(&sm.w0_full[c], kW0ChunkBytes);
+                bulk_g2s(sm.l0.w0[c], packed + (size_t)c * kW0ChunkBytes, kW0ChunkBytes, &sm.w0_full[c]);
+            }
         }
         for (int c = 0; c < kNumChunks; ++c) {
-            const int s = c & 1;
-            if (tid == 0 && c + 1 < kNumChunks) {  // prefetch chunk c+1 into the other stage
-                const int s1 = s ^ 1;
-                if (mma_pending[s1]) {  // the MMAs that read a_bf16[s1] / w0[s1] must have retired
-                    mb_wait(&sm.mma_done[s1], ph_mma[s1]);
-                    ph_mma[s1] ^= 1;
-                    mma_pending[s1] = 0;
+            const int sf = c % kStagesF, sw = c % kStagesW, sa = c & 1;
+            if (tid == 0) {
+                if (c >= 1) {  // MMAs of chunk c-1 (and all earlier ones) retired: a_bf16[sa^1] and w0[(c-1)%3] are free
+                    mb_wait(&sm.mma_done, ph_mma & 1u);
+                    ph_mma ^= 1u;
                 }
-                mb_expect_tx(&sm.full[s1], kTileM * kChunkK * 4 + kW0ChunkBytes);
-                tma_2d(sm.l0.stage_f32[s1], &obs_map, (c + 1) * kChunkK, row0, &sm.full[s1]);
-                bulk_g2s(sm.l0.w0[s1], packed + (size_t)(c + 1) * kW0ChunkBytes, kW0ChunkBytes, &sm.full[s1]);
+                if (c + kStagesF - 1 < kNumChunks) {  // stage of chunk c-1: its conversion ended before the last sync
+                    const int cn = c + kStagesF - 1, sn = cn % kStagesF;
+                    mb_expect_tx(&sm.full[sn], kTileM * kChunkK * 4);
+                    tma_2d(sm.l0.stage_f32[sn], &obs_map, cn * kChunkK, row0, &sm.full[sn]);
+                }
+                if (c + kStagesW - 1 < kNumChunks) {
+                    const int cn = c + kStagesW - 1, sn = cn % kStagesW;
+                    mb_expect_tx(&sm.w0_full[sn], kW0ChunkBytes);
+                    bulk_g2s(sm.l0.w0[sn], packed + (size_t)cn * kW0ChunkBytes, kW0ChunkBytes, &sm.w0_full[sn]);
+                }
             }
-            mb_wait(&sm.full[s], ph_full[s]);
-            ph_full[s] ^= 1;
-            // a_bf16[s] may still be read by the MMAs of chunk c-2: thread 0 waited for them when it prefetched
-            // chunk c-1+1 = c into this stage (above, one iteration ago); the __syncthreads below that iteration
-            // ordered every thread after that wait.
+            mb_wait(&sm.full[sf], (ph_full >> sf) & 1u);
+            ph_full ^= 1u << sf;
+            // a_bf16[sa] was last read by the MMAs of chunk c-2: thread 0 waited for them one iteration ago, before
+            // that iteration's __syncthreads, which orders every thread's stores below after that wait.
             // ---- convert fp32 [128][64] -> bf16 planes [8][128 rows][8]
-            const float* __restrict__ src = sm.l0.stage_f32[s];
-            unsigned char* dst = sm.l0.a_bf16[s];
+            const float* __restrict__ src = sm.l0.stage_f32[sf];
+            unsigned char* dst = sm.l0.a_bf16[sa];
 #pragma unroll
             for (int i = 0; i < (kTileM * 8) / kPolThreads; ++i) {
                 const int p = tid + i * kPolThreads;
@@ -260,23 +270,23 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
             __syncthreads();
             if (tid == 0 && debug_stop != 2) {
                 tc_fence_after();
-                const int n_mma = kChunkK / 16;
-                const uint32_t a0 = sptr(sm.l0.a_bf16[s]), b0 = sptr(sm.l0.w0[s]);
-                for (int j = 0; j < n_mma; ++j)
+                mb_wait(&sm.w0_full[sw], (ph_w0 >> sw) & 1u);
+                ph_w0 ^= 1u << sw;
+                const uint32_t a0 = sptr(sm.l0.a_bf16[sa]), b0 = sptr(sm.l0.w0[sw]);
+#pragma unroll
+                for (int j = 0; j < kChunkK / 16; ++j)
                     umma(tmem + 0, make_desc(a0 + j * 2 * kAPlane, kAPlane), make_desc(b0 + j * 2 * 80 * 16, 80 * 16),
                          idesc0, (c | j) != 0);
-                umma_commit(&sm.mma_done[s]);
-                mma_pending[s] = 1;
+                umma_commit(&sm.mma_done);
+            } else if (tid == 0) {  // bring-up stop 2: no MMAs; keep the barrier protocol balanced
+                mb_wait(&sm.w0_full[sw], (ph_w0 >> sw) & 1u);
+                ph_w0 ^= 1u << sw;
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(&sm.mma_done)) : "memory");
             }
         }
-        if (tid == 0) {  // drain: every layer-0 MMA retired (both stages), then signal the accumulator
-            for (int s = 0; s < 2; ++s)
-                if (mma_pending[s]) {
-                    mb_wait(&sm.mma_done[s], ph_mma[s]);
-                    ph_mma[s] ^= 1;
-                    mma_pending[s] = 0;
-                }
-            // layer-0 buffers are free now: start the bulk copy of W1 into the layer region
+        if (tid == 0) {  // drain the last chunk's MMAs, then start the bulk copy of W1 into the layer region
+            mb_wait(&sm.mma_done, ph_mma & 1u);
+            ph_mma ^= 1u;
             mb_expect_tx(&sm.w_full, weight_bytes(1));
             bulk_g2s(sm.ln.w, packed + weight_offset(1), weight_bytes(1), &sm.w_full);
         }
