@@ -120,6 +120,12 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
 __device__ __forceinline__ void umma_commit(unsigned long long* b) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sptr(b)) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -151,6 +157,7 @@ struct __align__(128) PolSmem {
     unsigned long long full[kStagesF];   // observation chunk landed in stage_f32[s]
     unsigned long long w0_full[kStagesW];  // weight chunk landed in w0[s]
     unsigned long long mma_done;     // the MMAs of the previous layer-0 chunk retired
+    float bias[80 + 64 + 256 + 160 + 128 + 16];  // all layer biases (padded), loaded once per CTA
     unsigned long long w_full;       // weights of the current layer (l >= 1) landed
     unsigned long long acc_done;     // accumulator of the current layer complete
     uint32_t tmem_base;
@@ -173,6 +180,8 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
         mb_init(&sm.acc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = tid; i < (kPackedBytes - kBiasOffset) / 4; i += kPolThreads)
+        sm.bias[i] = __ldg(reinterpret_cast<const float*>(packed + kBiasOffset) + i);
     if (warp == 0) {  // one warp allocates all 512 TMEM columns (one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sptr(&sm.tmem_base)), "r"(512u)
                      : "memory");
@@ -303,30 +312,42 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
         for (int l = 0; l < kNumLayers; ++l) {
             const int n_pad = layer_n(l);
             const uint32_t d_col = (l & 1) ? 256u : 0u;  // accumulator region of layer l
-            const float* __restrict__ bias = reinterpret_cast<const float*>(packed + bias_offset(l));
+            const float* bias = sm.bias + (bias_offset(l) - kBiasOffset) / 4;
             const int row = (warp & 3) * 32 + lane;       // TMEM lane == tile row
             const int half = warp >> 2;                   // column half handled by this warp
             const int cols_per_half = n_pad / 2;
             const uint32_t t_lane = (uint32_t)((warp & 3) * 32) << 16;
             unsigned char* act_out = sm.ln.act[l & 1];    // A operand of layer l+1
             if (l < kNumLayers - 1) {
-                for (int n0 = half * cols_per_half; n0 < (half + 1) * cols_per_half; n0 += 8) {
-                    float v[8];
-                    tmem_ld8(tmem + t_lane + d_col + n0, v);
+                // all TMEM loads of this thread's columns are issued back to back (one wait per 40 columns at most)
+                for (int nb = half * cols_per_half; nb < (half + 1) * cols_per_half; nb += 40) {
+                    const int ngroups = min(5, ((half + 1) * cols_per_half - nb) / 8);
+                    uint32_t raw[5][8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = leaky(v[j] + __ldg(bias + n0 + j));
-                    if (l == 1 && n0 == 56) {
-                        // layer 2 consumes [e(60), obs[:,0:4]] (W2's columns are permuted accordingly at pack time)
-                        const int grow = row0 + row;
+                    for (int q = 0; q < 5; ++q)
+                        if (q < ngroups) tmem_ld8_nowait(tmem + t_lane + d_col + nb + q * 8, raw[q]);
+                    tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) v[4 + j] = grow < n_envs ? __ldg(obs + (size_t)grow * obs_stride + j) : 0.f;
+                    for (int q = 0; q < 5; ++q) {
+                        if (q >= ngroups) continue;
+                        const int n0 = nb + q * 8;
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = leaky(__uint_as_float(raw[q][j]) + bias[n0 + j]);
+                        if (l == 1 && n0 == 56) {
+                            // layer 2 consumes [e(60), obs[:,0:4]] (W2's columns are permuted accordingly at pack time)
+                            const int grow = row0 + row;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                v[4 + j] = grow < n_envs ? __ldg(obs + (size_t)grow * obs_stride + j) : 0.f;
+                        }
+                        uint4 o;
+                        o.x = pack_bf16(v[0], v[1]);
+                        o.y = pack_bf16(v[2], v[3]);
+                        o.z = pack_bf16(v[4], v[5]);
+                        o.w = pack_bf16(v[6], v[7]);
+                        *reinterpret_cast<uint4*>(act_out + (n0 >> 3) * kAPlane + row * 16) = o;
                     }
-                    uint4 o;
-                    o.x = pack_bf16(v[0], v[1]);
-                    o.y = pack_bf16(v[2], v[3]);
-                    o.z = pack_bf16(v[4], v[5]);
-                    o.w = pack_bf16(v[6], v[7]);
-                    *reinterpret_cast<uint4*>(act_out + (n0 >> 3) * kAPlane + row * 16) = o;
                 }
                 tc_fence_before();
                 fence_async_smem();
@@ -360,8 +381,8 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
                     const int grow = row0 + row;
                     if (grow < n_envs) {
                         float2 m;
-                        m.x = tanhf(v[0] + __ldg(bias));
-                        m.y = tanhf(v[1] + __ldg(bias + 1));
+                        m.x = tanhf(v[0] + bias[0]);
+                        m.y = tanhf(v[1] + bias[1]);
                         *reinterpret_cast<float2*>(mean + 2 * (size_t)grow) = m;
                     }
                 }
