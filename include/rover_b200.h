@@ -95,6 +95,7 @@ typedef struct RoverMdpParams {
     float scale_lin, scale_ang, offset_lin, offset_ang;
     float wheelbase_length, middle_wheel_distance, rear_and_front_wheel_distance, wheel_radius;
     float min_radius;            /* (float)(middle_wheel_distance * 0.8) evaluated in double, ackermann_actions.py:264 */
+    float wheel_diameter;        /* (float)(wheel_radius * 2) evaluated in double, ackermann_actions.py:503 (variant 3) */
     /* rover_env_cfg.py:128-163 */
     float weight[ROVER_NUM_REWARD_TERMS];
     float reached_threshold, far_threshold;
@@ -105,6 +106,8 @@ typedef struct RoverMdpParams {
     /* terrain_importer.py:132, rover_env_cfg.py:191-200, randomizations.py:12 */
     float target_distance, resampling_time, heading_lo, heading_hi, spawn_z_offset;
     int32_t num_bodies;          /* contact-sensor bodies B: force_matrix_w is [n_envs, B, 1, 3] */
+    int32_t action_variant;      /* 2 = AckermannAction2 (default, actions_cfg.py:17), 1 = AckermannAction
+                                    (ackermann_actions.py:19-158), 3 = ackermann() of AckermannAction3 (:423-505) */
 } RoverMdpParams;
 
 typedef struct RoverMdpState {     /* persistent manager state, mutated in place */
@@ -148,6 +151,14 @@ typedef struct RoverMdpOut {
 int rover_mdp_pre_step(const float* new_actions, const float* force_matrix_w, int32_t n_envs,
                        const RoverMdpParams* params /* host */, const RoverMdpState* state /* host struct */,
                        const RoverMdpOut* out /* host struct */, int32_t phases, void* stream);
+
+/* Stand-alone action kinematics (any of the three variants; joint orders as the reference returns them):
+ *   variant 2: joint_pos [FL,RL,RR,FR], joint_vel [ML,FL,RL,RR,MR,FR]       ackermann_actions.py:316-317
+ *   variant 1: joint_pos [FL,FR,RL,RR], joint_vel [FL,FR,ML,MR,RL,RR]       ackermann_actions.py:111, 158
+ *   variant 3: joint_pos [FL,FR,RL,RR], joint_vel [FL,FR,ML,MR,RL,RR]       ackermann_actions.py:499-501 */
+int rover_ackermann(const float* actions /* [N,2] raw */, int32_t n_envs, const RoverMdpParams* params /* host */,
+                    float* processed /* [N,2] */, float* joint_pos /* [N,4] */, float* joint_vel /* [N,6] */,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Reset + command update + observation head.  Replaces, in one launch (rows a-4..a-6, a-22..a-28):

@@ -21,6 +21,7 @@ MDP_BLOCK = 64
 ABI_VERSION = 1
 
 SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_mdp_pre_step", "rover_mdp_post_step",
+           "rover_ackermann",
            "rover_policy_pack", "rover_policy_forward", "rover_gaussian_act")
 
 
@@ -44,11 +45,12 @@ class MdpParams(C.Structure):
     _fields_ = [("scale_lin", C.c_float), ("scale_ang", C.c_float), ("offset_lin", C.c_float),
                 ("offset_ang", C.c_float), ("wheelbase_length", C.c_float), ("middle_wheel_distance", C.c_float),
                 ("rear_and_front_wheel_distance", C.c_float), ("wheel_radius", C.c_float), ("min_radius", C.c_float),
+                ("wheel_diameter", C.c_float),
                 ("weight", C.c_float * NUM_REWARD_TERMS), ("reached_threshold", C.c_float),
                 ("far_threshold", C.c_float), ("step_dt", C.c_float), ("max_episode_length", C.c_int32),
                 ("obs_distance_scale", C.c_float), ("obs_heading_scale", C.c_float), ("target_distance", C.c_float),
                 ("resampling_time", C.c_float), ("heading_lo", C.c_float), ("heading_hi", C.c_float),
-                ("spawn_z_offset", C.c_float), ("num_bodies", C.c_int32)]
+                ("spawn_z_offset", C.c_float), ("num_bodies", C.c_int32), ("action_variant", C.c_int32)]
 
 
 _STATE_FIELDS = ("action", "prev_action", "pos_cmd_w", "heading_cmd_w", "pos_cmd_b", "heading_cmd_b", "time_left",
@@ -108,6 +110,8 @@ def load() -> C.CDLL:
     lib.rover_mdp_post_step.restype = C.c_int
     lib.rover_mdp_post_step.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
                                         C.POINTER(TerrainTables), vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp]
+    lib.rover_ackermann.restype = C.c_int
+    lib.rover_ackermann.argtypes = [vp, i32, C.POINTER(MdpParams), vp, vp, vp, vp]
     lib.rover_policy_pack.restype = C.c_int64
     lib.rover_policy_pack.argtypes = [C.POINTER(PolicyWeights), vp, vp]
     lib.rover_policy_forward.restype = C.c_int

@@ -31,6 +31,7 @@ class AckermannActionCfg:
     drive_joint_names: list = field(default_factory=lambda: [".*Drive_Continuous"])
     steering_order: list = field(default_factory=lambda: ["FL", "FR", "RL", "RR"])
     drive_order: list = field(default_factory=lambda: ["FL", "FR", "CL", "CR", "RL", "RR"])
+    variant: int = 2  # which reference class backs ``class_type``: 1 AckermannAction, 2 AckermannAction2, 3 AckermannAction3
 
     def offsets(self) -> tuple:
         return tuple(self.offset) if isinstance(self.offset, (tuple, list)) else (self.offset, self.offset)

@@ -86,6 +86,120 @@ __device__ __forceinline__ bool collision_active(const float* __restrict__ f, in
     return __fadd_rn(__fadd_rn(sqrtf(sx), sqrtf(sy)), sqrtf(sz)) > 1.f;
 }
 
+// ---- AckermannAction2.ackermann (ackermann_actions.py:238-322): jp [FL,RL,RR,FR], jv [ML,FL,RL,RR,MR,FR]
+__device__ __forceinline__ void ackermann_v2(const RoverMdpParams& P, float lin_p, float ang_p, float* jp, float* jv) {
+    float dir = sgnf(lin_p);
+    const float turn = sgnf(ang_p);
+    if (dir == 0.f) dir = 1.f;                                                  // :255
+    const float v = fabsf(lin_p), w = fabsf(ang_p);
+    const bool moving = (w != 0.f) || (v != 0.f);                               // :262
+    float R = moving ? __fdiv_rn(v, w) : INFINITY;                              // :265-266 (x/0 = inf)
+    const float r_min = P.min_radius;                                           // :264
+    if (R < r_min) R = r_min;                                                   // :267
+    const float half_mw = P.middle_wheel_distance / 2.f, half_fr = P.rear_and_front_wheel_distance / 2.f;
+    const float r_ml = __fsub_rn(R, half_mw), r_mr = __fadd_rn(R, half_mw);     // :271-272
+    const float r_l = __fsub_rn(R, half_fr), r_r = __fadd_rn(R, half_fr);       // :273-276
+    const bool point = R < P.middle_wheel_distance;                             // :278
+    const float spin = __fmul_rn(__fadd_rn(v, 1.f), turn);
+    const float v_l = point ? -spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_l, w), dir);
+    const float v_r = point ? spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_r, w), dir);
+    const float v_ml = point ? -spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_ml, w), dir);
+    const float v_mr = point ? spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_mr, w), dir);
+    const float ack = __fmul_rn(atan2f(P.wheelbase_length, r_l), turn);         // :305 (FL radius for all four)
+    const float q = 0.78539816339744830962f;
+    jv[0] = __fdiv_rn(v_ml, P.wheel_radius);                                    // [ML,FL,RL,RR,MR,FR] :316
+    jv[1] = __fdiv_rn(v_l, P.wheel_radius);
+    jv[2] = __fdiv_rn(v_l, P.wheel_radius);
+    jv[3] = __fdiv_rn(v_r, P.wheel_radius);
+    jv[4] = __fdiv_rn(v_mr, P.wheel_radius);
+    jv[5] = __fdiv_rn(v_r, P.wheel_radius);
+    jp[0] = point ? -q : ack;                                                   // [FL,RL,RR,FR] :317
+    jp[1] = point ? q : ack;
+    jp[2] = point ? -q : ack;
+    jp[3] = point ? q : ack;
+}
+
+// ---- AckermannAction.ackermann (ackermann_actions.py:91-158): jp [FL,FR,RL,RR], jv [FL,FR,ML,MR,RL,RR]
+__device__ __forceinline__ void ackermann_v1(float lin, float ang, float* jp, float* jv) {
+    const float wx[6] = {-0.385f, 0.385f, -0.447f, 0.447f, -0.385f, 0.385f};    // :97-108 (x right, y forward)
+    const float wy[6] = {0.438f, 0.438f, 0.f, 0.f, -0.411f, -0.411f};
+    float p = copysignf(__fdiv_rn(lin, ang), -ang);                             // :117-118
+    p = (fabsf(p) > 0.45f) ? p : 0.f;                                           // :122
+    const float lin2 = (p != 0.f) ? lin : 0.f;                                  // :123
+    const float w_lin = copysignf(ang, lin2);                                   // :134
+    float steer[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const float dx = __fsub_rn(p, wx[k]), dy = __fsub_rn(0.f, wy[k]);
+        const float dist = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));   // :127
+        const float side = (k & 1) ? 1.f : -1.f;                                // :130-131
+        const float av = (lin2 != 0.f) ? w_lin : __fmul_rn(ang, side);          // :136-137
+        float vel = __fmul_rn(dist, av);                                        // :141
+        vel = (dist > 1000.f) ? lin2 : vel;                                     // :144
+        jv[k] = __fdiv_rn(vel, 0.2f);                                           // :147
+        float s = atan2f(wy[k], __fsub_rn(wx[k], p));                           // :149-154
+        if (s < -1.57f) s = __fadd_rn(s, 3.1415927f);                           // :155
+        if (s > 1.57f) s = __fsub_rn(s, 3.1415927f);                            // :156
+        steer[k] = s;
+    }
+    jp[0] = steer[0];                                                           // :158
+    jp[1] = steer[1];
+    jp[2] = steer[4];
+    jp[3] = steer[5];
+}
+
+// ---- ackermann() used by AckermannAction3 (ackermann_actions.py:423-505): jp [FL,FR,RL,RR], jv [FL,FR,ML,MR,RL,RR]
+__device__ __forceinline__ void ackermann_v3(const RoverMdpParams& P, float lin_p, float ang_p, float* jp, float* jv) {
+    float dir = sgnf(lin_p);
+    const float turn = sgnf(ang_p);
+    if (dir == 0.f) dir = 1.f;
+    const float v = fabsf(lin_p), w = fabsf(ang_p);
+    const bool moving = (w != 0.f) || (v != 0.f);
+    const float R = moving ? __fdiv_rn(v, w) : INFINITY;                        // :443-444 (no clamp, :445)
+    const float hm = __fmul_rn(P.middle_wheel_distance / 2.f, turn), hf = __fmul_rn(P.rear_and_front_wheel_distance / 2.f, turn);
+    const float r_ml = __fsub_rn(R, hm), r_mr = __fadd_rn(R, hm);               // :449-450
+    const float r_l = __fsub_rn(R, hf), r_r = __fadd_rn(R, hf);                 // :451-454
+    const bool point = R < P.min_radius;                                        // :461
+    const float spin = __fmul_rn(__fadd_rn(v, 1.f), turn);
+    const float v_l = point ? -spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_l, w), dir);
+    const float v_r = point ? spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_r, w), dir);
+    const float v_ml = point ? -spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_ml, w), dir);
+    const float v_mr = point ? spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_mr, w), dir);
+    const float half_wl = P.wheelbase_length / 2.f;
+    const float y_front = __fsub_rn(half_wl, P.offset_lin), y_rear = __fadd_rn(half_wl, P.offset_lin);  // :488-497
+    const float q = 0.78539816339744830962f;
+    jp[0] = point ? -q : __fmul_rn(atan2f(y_front, r_l), turn);                 // FL
+    jp[1] = point ? q : __fmul_rn(atan2f(y_front, r_r), turn);                  // FR
+    jp[2] = point ? q : __fmul_rn(atan2f(y_rear, r_l), -turn);                  // RL
+    jp[3] = point ? -q : __fmul_rn(atan2f(y_rear, r_r), -turn);                 // RR
+    const float diam = P.wheel_diameter;                                        // :503 (float)(wheel_radius * 2)
+    jv[0] = __fdiv_rn(v_l, diam);
+    jv[1] = __fdiv_rn(v_r, diam);
+    jv[2] = __fdiv_rn(v_ml, diam);
+    jv[3] = __fdiv_rn(v_mr, diam);
+    jv[4] = __fdiv_rn(v_l, diam);
+    jv[5] = __fdiv_rn(v_r, diam);
+}
+
+__device__ __forceinline__ void ackermann_dispatch(const RoverMdpParams& P, float lin_p, float ang_p, float* jp, float* jv) {
+    if (P.action_variant == 1) ackermann_v1(lin_p, ang_p, jp, jv);
+    else if (P.action_variant == 3) ackermann_v3(P, lin_p, ang_p, jp, jv);
+    else ackermann_v2(P, lin_p, ang_p, jp, jv);
+}
+
+__global__ void ackermann_kernel(const float* __restrict__ actions, int n, const __grid_constant__ RoverMdpParams P,
+                                 float* __restrict__ processed, float* __restrict__ jp, float* __restrict__ jv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float lin_p = __fadd_rn(__fmul_rn(actions[2 * i], P.scale_lin), P.offset_lin);
+    const float ang_p = __fadd_rn(__fmul_rn(actions[2 * i + 1], P.scale_ang), P.offset_ang);
+    if (processed) {
+        processed[2 * i] = lin_p;
+        processed[2 * i + 1] = ang_p;
+    }
+    ackermann_dispatch(P, lin_p, ang_p, jp + 4 * (size_t)i, jv + 6 * (size_t)i);
+}
+
 __global__ void __launch_bounds__(ROVER_MDP_BLOCK)
 mdp_pre_step_kernel(const float* __restrict__ new_actions, const float* __restrict__ force, int n,
                     const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
@@ -104,37 +218,7 @@ mdp_pre_step_kernel(const float* __restrict__ new_actions, const float* __restri
         const float ang_p = __fadd_rn(__fmul_rn(a.y, P.scale_ang), P.offset_ang);
         reinterpret_cast<float2*>(O.processed_actions)[i] = make_float2(lin_p, ang_p);
 
-        // ---- AckermannAction2.ackermann (ackermann_actions.py:238-322)
-        {
-            float dir = sgnf(lin_p);
-            const float turn = sgnf(ang_p);
-            if (dir == 0.f) dir = 1.f;                                                  // :255
-            const float v = fabsf(lin_p), w = fabsf(ang_p);
-            const bool moving = (w != 0.f) || (v != 0.f);                               // :262
-            float R = moving ? __fdiv_rn(v, w) : INFINITY;                              // :265-266 (x/0 = inf)
-            const float r_min = P.min_radius;                                           // :264
-            if (R < r_min) R = r_min;                                                   // :267
-            const float half_mw = P.middle_wheel_distance / 2.f, half_fr = P.rear_and_front_wheel_distance / 2.f;
-            const float r_ml = __fsub_rn(R, half_mw), r_mr = __fadd_rn(R, half_mw);     // :271-272
-            const float r_l = __fsub_rn(R, half_fr), r_r = __fadd_rn(R, half_fr);       // :273-276
-            const bool point = R < P.middle_wheel_distance;                             // :278
-            const float spin = __fmul_rn(__fadd_rn(v, 1.f), turn);
-            const float v_l = point ? -spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_l, w), dir);
-            const float v_r = point ? spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_r, w), dir);
-            const float v_ml = point ? -spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_ml, w), dir);
-            const float v_mr = point ? spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_mr, w), dir);
-            const float ack = __fmul_rn(atan2f(P.wheelbase_length, r_l), turn);         // :305 (FL radius for all)
-            const float q = 0.78539816339744830962f;
-            float* jv = O.joint_vel + 6 * (size_t)i;                                    // [ML,FL,RL,RR,MR,FR] :316
-            jv[0] = __fdiv_rn(v_ml, P.wheel_radius);
-            jv[1] = __fdiv_rn(v_l, P.wheel_radius);
-            jv[2] = __fdiv_rn(v_l, P.wheel_radius);
-            jv[3] = __fdiv_rn(v_r, P.wheel_radius);
-            jv[4] = __fdiv_rn(v_mr, P.wheel_radius);
-            jv[5] = __fdiv_rn(v_r, P.wheel_radius);
-            reinterpret_cast<float4*>(O.joint_pos)[i] =                                 // [FL,RL,RR,FR] :317
-                make_float4(point ? -q : ack, point ? q : ack, point ? -q : ack, point ? q : ack);
-        }
+        ackermann_dispatch(P, lin_p, ang_p, O.joint_pos + 4 * (size_t)i, O.joint_vel + 6 * (size_t)i);
         } else {
             a = reinterpret_cast<const float2*>(S.action)[i];
             a_old = reinterpret_cast<const float2*>(S.prev_action)[i];
@@ -474,6 +558,18 @@ static int check_state(const RoverMdpState* s, const RoverMdpOut* o) {
                 "rover_mdp: NULL pointer in RoverMdpOut");
     ROVER_CHECK((reinterpret_cast<uintptr_t>(o->joint_pos) & 15) == 0, "rover_mdp: joint_pos not 16B aligned");
     return 0;
+}
+
+extern "C" int rover_ackermann(const float* actions, int32_t n_envs, const RoverMdpParams* params, float* processed,
+                               float* joint_pos, float* joint_vel, void* stream) {
+    using namespace rover;
+    ROVER_CHECK(n_envs >= 0, "rover_ackermann: negative n_envs");
+    if (n_envs == 0) return 0;
+    ROVER_CHECK(actions && params && joint_pos && joint_vel, "rover_ackermann: NULL argument");
+    ROVER_CHECK(params->action_variant >= 1 && params->action_variant <= 3, "rover_ackermann: action_variant must be 1, 2 or 3");
+    ackermann_kernel<<<(n_envs + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(actions, n_envs, *params, processed,
+                                                                                        joint_pos, joint_vel);
+    return check_launch("ackermann_kernel");
 }
 
 extern "C" int rover_mdp_pre_step(const float* new_actions, const float* force_matrix_w, int32_t n_envs,

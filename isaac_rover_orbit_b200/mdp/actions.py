@@ -58,3 +58,57 @@ class AckermannAction2:
         self._asset.set_joint_velocity_target(b.joint_vel, joint_ids=self._drive_joint_ids)
         self._asset.set_joint_position_target(b.joint_pos, joint_ids=self._steering_joint_ids)
         self._dirty = False
+
+
+class AckermannAction(AckermannAction2):
+    """``AckermannAction`` (ackermann_actions.py:19-158): turning-point model with the AAU wheel locations hard-coded;
+    joint targets come back as [FL,FR,RL,RR] / [FL,FR,ML,MR,RL,RR].  Same ActionTerm API as ``AckermannAction2``."""
+
+    VARIANT = 1
+
+    def process_actions(self, actions: torch.Tensor):
+        self._env._params.action_variant = self.VARIANT
+        super().process_actions(actions)
+
+
+class AckermannAction3:
+    """``AckermannAction3`` (ackermann_actions.py:329-420) over ``ackermann()`` (:423-505): a stand-alone controller
+    (not an ActionTerm) constructed as ``(cfg, robot, num_envs, device)``; joint ids are re-ordered by
+    ``cfg.steering_order`` / ``cfg.drive_order`` like the reference does."""
+
+    def __init__(self, cfg: AckermannActionCfg, robot, num_envs: int, device):
+        from ..config import RoverEnvCfg
+
+        self.cfg, self.device, self.num_envs, self._asset = cfg, torch.device(device), num_envs, robot
+        self._drive_joint_ids, self._drive_joint_names = robot.find_joints(cfg.drive_joint_names)
+        self._steering_joint_ids, self._steering_joint_names = robot.find_joints(cfg.steering_joint_names)
+        so, do = list(cfg.steering_order), list(cfg.drive_order)
+        # the reference's drive_order spells the middle wheels "CL"/"CR" (actions_cfg.py:49); the AAU joints are "ML"/"MR"
+        key = lambda order: (lambda name: order.index({"ML": "CL", "MR": "CR"}.get(name[:2], name[:2])))  # noqa: E731
+        self._sorted_steering_ids = [i for _, i in sorted(zip(self._steering_joint_names, self._steering_joint_ids),
+                                                          key=lambda t: key(so)(t[0]))]
+        self._sorted_drive_ids = [i for _, i in sorted(zip(self._drive_joint_names, self._drive_joint_ids),
+                                                       key=lambda t: key(do)(t[0]))]
+        self._raw_actions = torch.zeros(num_envs, 2, device=self.device)
+        self._processed_actions = torch.zeros_like(self._raw_actions)
+        self._params = ops.mdp_params(RoverEnvCfg(num_envs=num_envs, actions=cfg))
+
+    @property
+    def action_dim(self) -> int:
+        return 2
+
+    @property
+    def raw_actions(self) -> torch.Tensor:
+        return self._raw_actions
+
+    @property
+    def processed_actions(self) -> torch.Tensor:
+        return self._processed_actions
+
+    def process_actions(self, actions):
+        self._raw_actions[:] = actions
+
+    def apply_actions(self):
+        self._processed_actions, self._joint_pos, self._joint_vel = ops.ackermann(self._raw_actions, self._params, 3)
+        self._asset.set_joint_velocity_target(self._joint_vel, joint_ids=self._sorted_drive_ids)
+        self._asset.set_joint_position_target(self._joint_pos, joint_ids=self._sorted_steering_ids)

@@ -141,6 +141,8 @@ def mdp_params(cfg: RoverEnvCfg) -> _lib.MdpParams:
     p.rear_and_front_wheel_distance = a.rear_and_front_wheel_distance
     p.wheel_radius = a.wheel_radius
     p.min_radius = a.middle_wheel_distance * 0.8  # evaluated in double, then fp32 (ackermann_actions.py:264)
+    p.wheel_diameter = a.wheel_radius * 2  # ackermann_actions.py:503
+    p.action_variant = getattr(a, "variant", 2)
     for i, w in enumerate(cfg.rewards.weights):
         p.weight[i] = w
     p.reached_threshold = cfg.rewards.reached_threshold
@@ -155,6 +157,22 @@ def mdp_params(cfg: RoverEnvCfg) -> _lib.MdpParams:
     p.spawn_z_offset = cfg.spawn_z_offset
     p.num_bodies = cfg.num_contact_bodies
     return p
+
+
+def ackermann(actions: torch.Tensor, params: _lib.MdpParams, variant: int = 2):
+    """Stand-alone Ackermann kinematics of any of the reference's three variants.
+    Returns ``(processed [N,2], joint_pos [N,4], joint_vel [N,6])`` in the joint orders of that variant."""
+    dev = _lib.require_cuda(actions)
+    if actions.dtype != torch.float32 or actions.dim() != 2 or actions.shape[1] != 2:
+        raise RuntimeError("ackermann: actions must be fp32 [N,2]")
+    n = actions.shape[0]
+    p = _lib.MdpParams.from_buffer_copy(params)
+    p.action_variant = int(variant)
+    processed = torch.empty(n, 2, device=dev)
+    jp, jv = torch.empty(n, 4, device=dev), torch.empty(n, 6, device=dev)
+    _lib.check(_lib.load().rover_ackermann(_lib.ptr(actions), n, C.byref(p), _lib.ptr(processed), _lib.ptr(jp),
+                                            _lib.ptr(jv), _lib.current_stream(dev)))
+    return processed, jp, jv
 
 
 @dataclass

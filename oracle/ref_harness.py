@@ -96,6 +96,27 @@ def ref_ackermann2(actions: torch.Tensor, c: RoverConstants = AAU_ROVER):
     return term.processed_actions.clone(), asset.joint_pos_target.clone(), asset.joint_vel_target.clone()
 
 
+def ref_ackermann_variants(actions: torch.Tensor, c: RoverConstants = AAU_ROVER):
+    """``AckermannAction`` (ackermann_actions.py:19-158) through its ActionTerm API and the free function
+    ``ackermann()`` of ``AckermannAction3`` (:423-505) on the processed actions."""
+    mod = ref_loader.load("ackermann_actions")
+    n = actions.shape[0]
+    env = make_env(n)
+    cfg = types.SimpleNamespace(
+        asset_name="robot", scale=c.action_scale, offset=c.action_offset, wheelbase_length=c.wheelbase_length,
+        middle_wheel_distance=c.middle_wheel_distance, rear_and_front_wheel_distance=c.rear_and_front_wheel_distance,
+        wheel_radius=c.wheel_radius, min_steering_radius=c.min_steering_radius,
+        steering_joint_names=[".*Steer_Revolute"], drive_joint_names=[".*Drive_Continuous"])
+    t1 = mod.AckermannAction(cfg, env)
+    t1.process_actions(actions)
+    t1.apply_actions()
+    asset = env.scene["robot"]
+    v1 = asset.joint_pos_target.clone(), asset.joint_vel_target.clone()
+    p = t1.processed_actions
+    sa, wv = mod.ackermann(p[:, 0], p[:, 1], cfg, "cpu")
+    return v1[0], v1[1], sa.clone(), wv.clone()
+
+
 def ref_rewards_terminations(pos_cmd_b, action, prev_action, episode_length_buf, force_matrix_w,
                              c: RoverConstants = AAU_ROVER):
     """All 7 reward terms (unweighted) and the 3 first-party terminations, reference code."""

@@ -277,3 +277,68 @@ def height_at(xy, heightmap, offset_xy, resolution: float):
     """terrain_utils.py:62-84."""
     col, row = terrain_cell(xy, offset_xy, heightmap.shape, resolution)
     return heightmap[row, col]
+
+
+# --------------------------------------------------------------------------------------
+# the other two action-term variants (SURVEY.md 8 f-1)
+# --------------------------------------------------------------------------------------
+_WHEELS_V1 = ((-0.385, 0.438), (0.385, 0.438), (-0.447, 0.0), (0.447, 0.0), (-0.385, -0.411), (0.385, -0.411))
+
+
+def ackermann1(lin_vel: torch.Tensor, ang_vel: torch.Tensor):
+    """ackermann_actions.py:91-158 (``AckermannAction.ackermann``, hard-coded AAU wheel locations FL,FR,ML,MR,RL,RR).
+
+    Returns ``(steering [N,4] = [FL,FR,RL,RR], motor_velocities [N,6] = [FL,FR,ML,MR,RL,RR])``."""
+    zeros = torch.zeros_like(lin_vel)
+    p = torch.copysign(lin_vel / ang_vel, -ang_vel)  # :117-118 turning point on the x axis
+    p = torch.where(torch.abs(p) > 0.45, p, zeros)  # :122 between the wheels -> turn on the spot
+    lin = torch.where(p != 0, lin_vel, zeros)  # :123
+    wx = torch.tensor([w[0] for w in _WHEELS_V1], dtype=lin_vel.dtype)
+    wy = torch.tensor([w[1] for w in _WHEELS_V1], dtype=lin_vel.dtype)
+    dist = ((p[:, None] - wx[None, :]).pow(2) + (zeros[:, None] - wy[None, :]).pow(2)).sqrt()  # :127
+    side = torch.tensor([-1.0, 1.0, -1.0, 1.0, -1.0, 1.0], dtype=lin_vel.dtype)  # :130-131
+    w_lin = torch.copysign(ang_vel, lin)[:, None].expand(-1, 6)  # :134
+    w_turn = ang_vel[:, None] * side[None, :]  # :136
+    w = torch.where(lin[:, None] != 0, w_lin, w_turn)  # :137
+    vel = dist * w  # :141
+    vel = torch.where(dist > 1000, lin[:, None].expand(-1, 6), vel)  # :144
+    vel = vel / 0.2  # :147 wheel diameter
+    ang = torch.atan2(wy[None, :].expand_as(dist), wx[None, :] - p[:, None])  # :149-154 (both where-branches equal)
+    ang = torch.where(ang < -3.14 / 2, ang + math.pi, ang)  # :155
+    ang = torch.where(ang > 3.14 / 2, ang - math.pi, ang)  # :156
+    return torch.cat([ang[:, 0:2], ang[:, 4:6]], dim=1), vel  # :158
+
+
+def ackermann3(lin_vel: torch.Tensor, ang_vel: torch.Tensor, c: RoverConstants = AAU_ROVER):
+    """ackermann_actions.py:423-505 (free function used by ``AckermannAction3``).
+
+    Returns ``(steering [N,4] = [FL,FR,RL,RR], wheel_velocities [N,6] = [FL,FR,ML,MR,RL,RR])``; velocities are divided
+    by the wheel DIAMETER here (:503), the turn direction enters the per-wheel radii (:449-454) and the steering
+    uses ``wl/2 -+ offset`` with each wheel's own radius (:486-497)."""
+    d_fr, d_mw, wl, off = c.rear_and_front_wheel_distance, c.middle_wheel_distance, c.wheelbase_length, c.action_offset
+    sgn_lin = torch.sign(lin_vel)
+    turn = torch.sign(ang_vel)
+    sgn_lin = torch.where(sgn_lin == 0, sgn_lin + 1, sgn_lin)
+    v, w = lin_vel.abs(), ang_vel.abs()
+    moving = (w != 0) | (v != 0)
+    radius = torch.where(moving, v / w, torch.tensor(float("inf"), dtype=v.dtype))
+    r_min = d_mw * 0.8
+    r_ml, r_mr = radius - (d_mw / 2) * turn, radius + (d_mw / 2) * turn
+    r_fl, r_fr = radius - (d_fr / 2) * turn, radius + (d_fr / 2) * turn
+    r_rl, r_rr = radius - (d_fr / 2) * turn, radius + (d_fr / 2) * turn
+    point = radius < r_min
+    spin = (v + 1) * turn
+
+    def wheel(r, left):
+        return torch.where(point, -spin if left else spin, torch.where(w == 0, v, r * w) * sgn_lin)
+
+    wl_t = torch.ones_like(r_fl) * wl
+    q = torch.tensor(math.pi / 4, dtype=v.dtype)
+    th_fl = torch.where(point, -q, torch.atan2((wl_t / 2) - off, r_fl) * turn)
+    th_rr = torch.where(point, -q, torch.atan2((wl_t / 2) + off, r_rr) * -turn)
+    th_fr = torch.where(point, q, torch.atan2((wl_t / 2) - off, r_fr) * turn)
+    th_rl = torch.where(point, q, torch.atan2((wl_t / 2) + off, r_rl) * -turn)
+    vel = torch.stack([wheel(r_fl, True), wheel(r_fr, False), wheel(r_ml, True), wheel(r_mr, False), wheel(r_rl, True),
+                       wheel(r_rr, False)], dim=1)
+    ang = torch.stack([th_fl, th_fr, th_rl, th_rr], dim=1)
+    return ang, vel / (c.wheel_radius * 2)

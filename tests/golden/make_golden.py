@@ -55,6 +55,11 @@ def gen_terms(path):
     force = torch.where(torch.rand(n, 1, 1, 1, generator=g) < 0.9, 0.0, 1.0) * torch.randn(n, 14, 1, 3, generator=g) * 2
     force[:32] *= 0.2  # sums close to the > 1 test
     processed, jpos, jvel = H.ref_ackermann2(act)
+    v1_pos, v1_vel, v3_pos, v3_vel = H.ref_ackermann_variants(act)
+    from oracle.terms import RoverConstants
+    exomy = RoverConstants(wheelbase_length=0.29778, middle_wheel_distance=0.1548, rear_and_front_wheel_distance=0.1548,
+                           wheel_radius=0.1, min_steering_radius=0.4, action_offset=0.0)
+    _, ex_pos, ex_vel = H.ref_ackermann2(act, exomy)
     rewards, terms = H.ref_rewards_terminations(pos_b, act, prev, ep, force)
     sensor_pos = torch.randn(n, 3, generator=g)
     hits = torch.randn(n, 7, 3, generator=g)
@@ -64,6 +69,8 @@ def gen_terms(path):
         path, in_actions=act.numpy(), in_prev_actions=prev.numpy(), in_pos_b=pos_b.numpy(), in_ep_len=ep.numpy(),
         in_force=force.numpy(), in_sensor_pos=sensor_pos.numpy(), in_hits=hits.numpy(),
         ref_processed=processed.numpy(), ref_joint_pos=jpos.numpy(), ref_joint_vel=jvel.numpy(),
+        ref_v1_joint_pos=v1_pos.numpy(), ref_v1_joint_vel=v1_vel.numpy(), ref_v3_joint_pos=v3_pos.numpy(),
+        ref_v3_joint_vel=v3_vel.numpy(), ref_exomy_joint_pos=ex_pos.numpy(), ref_exomy_joint_vel=ex_vel.numpy(),
         ref_rewards=rewards.numpy(), ref_terms=terms.numpy(), ref_obs_distance=d.numpy(), ref_obs_angle=a.numpy(),
         ref_obs_scan=h.numpy())
 

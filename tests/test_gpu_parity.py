@@ -281,3 +281,32 @@ def test_mdp_terms_against_reference_golden(cuda_device, golden_dir):
     flags = buf.term_flags.cpu().bool()
     assert torch.equal(flags[ok][:, 1:], torch.from_numpy(z["ref_terms"])[ok])
     assert torch.equal(flags[:, 0], torch.from_numpy(z["in_ep_len"]) >= 750)
+
+
+def test_ackermann_variants_against_reference_golden(cuda_device, golden_dir):
+    """the three action-term variants and the Exomy constants against outputs of the unmodified
+    reference classes (tests/golden/terms.npz)."""
+    from isaac_rover_orbit_b200 import mdp
+    from isaac_rover_orbit_b200.config import exomy_action_cfg
+    from isaac_rover_orbit_b200.env import RobotArticulation
+
+    z = np.load(os.path.join(golden_dir, "terms.npz"))
+    a = torch.from_numpy(z["in_actions"]).to(cuda_device)
+    params = ops.mdp_params(RoverEnvCfg(num_envs=len(a)))
+    for variant, kp, kv in ((2, "ref_joint_pos", "ref_joint_vel"), (1, "ref_v1_joint_pos", "ref_v1_joint_vel"),
+                            (3, "ref_v3_joint_pos", "ref_v3_joint_vel")):
+        processed, jp, jv = ops.ackermann(a, params, variant)
+        assert torch.equal(processed.cpu(), torch.from_numpy(z["ref_processed"]))
+        torch.testing.assert_close(jp.cpu(), torch.from_numpy(z[kp]), rtol=1e-5, atol=2e-6)
+        torch.testing.assert_close(jv.cpu(), torch.from_numpy(z[kv]), rtol=1e-5, atol=2e-6)
+    ex = ops.mdp_params(RoverEnvCfg(num_envs=len(a), actions=exomy_action_cfg()))
+    _, jp, jv = ops.ackermann(a, ex, 2)
+    torch.testing.assert_close(jp.cpu(), torch.from_numpy(z["ref_exomy_joint_pos"]), rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(jv.cpu(), torch.from_numpy(z["ref_exomy_joint_vel"]), rtol=1e-5, atol=2e-6)
+    # AckermannAction3 through its own (cfg, robot, num_envs, device) API
+    robot = RobotArticulation(len(a), cuda_device)
+    ctl = mdp.AckermannAction3(RoverEnvCfg().actions, robot, len(a), cuda_device)
+    ctl.process_actions(a)
+    ctl.apply_actions()
+    torch.testing.assert_close(robot.joint_pos_target.cpu(), torch.from_numpy(z["ref_v3_joint_pos"]), rtol=1e-5, atol=2e-6)
+    assert ctl.action_dim == 2 and torch.equal(ctl.processed_actions.cpu(), torch.from_numpy(z["ref_processed"]))

@@ -185,3 +185,21 @@ def test_live_reference_agrees_bitwise():
     assert torch.equal(r, r2.float())
     assert torch.equal(t, torch.stack([T.term_is_success(pos_b, 0.18), T.term_far_from_target(pos_b, 11.0),
                                        T.term_collision(force)], 1))
+
+
+def test_ackermann_variants_golden(terms_npz):
+    """AckermannAction (v1), ackermann() of AckermannAction3 and the Exomy constants."""
+    a = _t(terms_npz["in_actions"])
+    p = T.process_actions(a)
+    jp, jv = T.ackermann1(p[:, 0], p[:, 1])
+    torch.testing.assert_close(jp, _t(terms_npz["ref_v1_joint_pos"]), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(jv, _t(terms_npz["ref_v1_joint_vel"]), rtol=1e-6, atol=1e-6)
+    jp, jv = T.ackermann3(p[:, 0], p[:, 1])
+    torch.testing.assert_close(jp, _t(terms_npz["ref_v3_joint_pos"]), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(jv, _t(terms_npz["ref_v3_joint_vel"]), rtol=1e-6, atol=1e-6)
+    exomy = T.RoverConstants(wheelbase_length=0.29778, middle_wheel_distance=0.1548, rear_and_front_wheel_distance=0.1548,
+                             wheel_radius=0.1, min_steering_radius=0.4, action_offset=0.0)
+    pe = T.process_actions(a, exomy)
+    jp, jv = T.ackermann2(pe[:, 0], pe[:, 1], exomy)
+    torch.testing.assert_close(jp, _t(terms_npz["ref_exomy_joint_pos"]), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(jv, _t(terms_npz["ref_exomy_joint_vel"]), rtol=1e-6, atol=1e-6)
