@@ -25,8 +25,8 @@
 namespace rover {
 
 constexpr int kPipeGroups = 2;          // consumer groups; group q resolves environments it = q, q+2, ... of the CTA
-constexpr int kPipeConsumerWarps = 11;  // warps per consumer group (1 + 2*11 = 23 warps -> 24-warp allocation, 80 regs)
-constexpr int kPipeRaysPerThread = 3;   // rays resolved together by one consumer thread (ILP)
+constexpr int kPipeConsumerWarps = 7;   // warps per consumer group (1 + 2*7 = 15 warps -> 16-warp allocation, 128 regs)
+constexpr int kPipeRaysPerThread = 5;   // rays resolved together by one consumer thread (ILP)
 constexpr int kPipeConsumers = 32 * kPipeConsumerWarps;
 constexpr int kPipeThreads = 32 * (1 + kPipeGroups * kPipeConsumerWarps);
 constexpr int kPipeStages = 8;          // ring depth (multiple of kPipeGroups: a stage always serves the same group)
@@ -165,6 +165,46 @@ __device__ __noinline__ float resolve_from_global(const ScanGridDev& g, const Pl
     const float4 p = __ldg(e), q = __ldg(e + 1);
     if (q.w != 0.f) return walk_home_grid(g, X, Y, Z, max_d);
     return eval_cell(p, q, __fsub_rn(X, __ldg(pc.xs + i)), __fsub_rn(Y, __ldg(pc.ys + j)), Z, max_d);
+}
+
+// Rare paths, kept out of line so that they do not raise the register pressure of the consumer loop.
+// (a) a ray whose cell guess missed, that lies on the closed far border / outside the grid, or sits in a general cell
+__device__ __noinline__ void resolve_deferred_ray(const PipeStage* st, const ScanGridDev& g, float inv_dx, float inv_dy,
+                                                  float X, float Y, float Z, float pz, float max_d, float base_offset,
+                                                  float* __restrict__ out, float* __restrict__ hit3) {
+    const int cmax = st->hdr.ncols - 1, rmax = st->hdr.nrows - 1;
+    const float wx0 = st->xp[0].lo, wy0 = st->yp[0].lo, wx1 = st->xp[cmax].hi, wy1 = st->yp[rmax].hi;
+    float zhit = -INFINITY;
+    if (X >= wx0 && X <= wx1 && Y >= wy0 && Y <= wy1) {
+        int ci = min(max(__float2int_rd((X - wx0) * inv_dx), 0), cmax);
+        int cj = min(max(__float2int_rd((Y - wy0) * inv_dy), 0), rmax);
+        while (ci > 0 && X < st->xp[ci].lo) --ci;
+        while (ci < cmax && X >= st->xp[ci].hi) ++ci;
+        while (cj > 0 && Y < st->yp[cj].lo) --cj;
+        while (cj < rmax && Y >= st->yp[cj].hi) ++cj;
+        const int e = 2 * (cj * kPipeWin + ci);
+        const float4 q = st->ent[e + 1];
+        zhit = (q.w == 0.f) ? eval_cell(st->ent[e], q, __fsub_rn(X, st->xp[ci].lo), __fsub_rn(Y, st->yp[cj].lo), Z, max_d)
+                            : walk_home_grid(g, X, Y, Z, max_d);
+    }
+    store_result(pz, X, Y, Z, zhit, base_offset, out, hit3);
+}
+
+// (b) a whole environment whose window is not staged (too large, or not covered on a non-uniform lattice)
+__device__ __noinline__ void resolve_env_from_global(const float4* pattern, int t, int n_rays, const StageHeader h,
+                                                     const ScanGridDev& g, const PlaneCellsDev& pc, float max_d,
+                                                     float base_offset, float* __restrict__ out_row,
+                                                     float* __restrict__ hits_row) {
+    const float sz2 = __fmul_rn(h.sz, 2.f);
+    for (int r = t; r < n_rays; r += kPipeConsumers) {
+        const float4 v = pattern[r];
+        const float tx = -__fmul_rn(sz2, v.y), ty = __fmul_rn(sz2, v.x);
+        const float X = __fadd_rn(__fadd_rn(__fadd_rn(v.x, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
+        const float Y = __fadd_rn(__fadd_rn(__fadd_rn(v.y, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
+        const float Z = __fadd_rn(v.z, h.pz);
+        store_result(h.pz, X, Y, Z, resolve_from_global(g, pc, X, Y, Z, max_d), base_offset, out_row + r,
+                     hits_row ? hits_row + 3 * (size_t)r : nullptr);
+    }
 }
 
 template <bool kHits>
@@ -312,36 +352,13 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
                             const float tx = -__fmul_rn(sz2, v.y), ty = __fmul_rn(sz2, v.x);
                             const float X = __fadd_rn(__fadd_rn(__fadd_rn(v.x, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
                             const float Y = __fadd_rn(__fadd_rn(__fadd_rn(v.y, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
-                            const float Z = __fadd_rn(v.z, h.pz);
-                            float zhit = -INFINITY;
-                            if (X >= wx0 && X <= wx1 && Y >= wy0 && Y <= wy1) {
-                                int ci = min(max(__float2int_rd((X - wx0) * inv_dx), 0), cmax);
-                                int cj = min(max(__float2int_rd((Y - wy0) * inv_dy), 0), rmax);
-                                while (ci > 0 && X < st.xp[ci].lo) --ci;
-                                while (ci < cmax && X >= st.xp[ci].hi) ++ci;
-                                while (cj > 0 && Y < st.yp[cj].lo) --cj;
-                                while (cj < rmax && Y >= st.yp[cj].hi) ++cj;
-                                const int e = 2 * (cj * kPipeWin + ci);
-                                const float4 q = st.ent[e + 1];
-                                zhit = (q.w == 0.f) ? eval_cell(st.ent[e], q, __fsub_rn(X, st.xp[ci].lo),
-                                                                __fsub_rn(Y, st.yp[cj].lo), Z, max_d)
-                                                    : walk_home_grid(g, X, Y, Z, max_d);
-                            }
-                            store_result(h.pz, X, Y, Z, zhit, base_offset, out_row + r,
-                                         kHits ? hits_row + 3 * (size_t)r : nullptr);
+                            resolve_deferred_ray(&st, g, inv_dx, inv_dy, X, Y, __fadd_rn(v.z, h.pz), h.pz, max_d, base_offset,
+                                                 out_row + r, kHits ? hits_row + 3 * (size_t)r : nullptr);
                         }
                     }
                 }
             } else {
-                for (int r = t; r < n_rays; r += kPipeConsumers) {
-                    const float4 v = sm.pattern[r];
-                    const float tx = -__fmul_rn(sz2, v.y), ty = __fmul_rn(sz2, v.x);
-                    const float X = __fadd_rn(__fadd_rn(__fadd_rn(v.x, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
-                    const float Y = __fadd_rn(__fadd_rn(__fadd_rn(v.y, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
-                    const float Z = __fadd_rn(v.z, h.pz);
-                    const float zhit = resolve_from_global(g, pc, X, Y, Z, max_d);
-                    store_result(h.pz, X, Y, Z, zhit, base_offset, out_row + r, kHits ? hits_row + 3 * (size_t)r : nullptr);
-                }
+                resolve_env_from_global(sm.pattern, t, n_rays, h, g, pc, max_d, base_offset, out_row, hits_row);
             }
             __syncwarp();
             if (lane == 0) bar_arrive(&sm.empty_bar[s]);  // this warp is done reading the stage
