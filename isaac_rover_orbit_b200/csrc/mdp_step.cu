@@ -311,8 +311,9 @@ __device__ __forceinline__ void terrain_cell(const Tables& T, float x, float y, 
 // are generated together and their mask bytes fetched concurrently (one memory round trip per batch instead of per
 // round), then the first valid round wins -- the same candidate the sequential loop would have accepted.
 __device__ __forceinline__ bool resample_command(int i, const RoverMdpParams& P, const RoverMdpState& S, const Tables& T,
-                                                 float ox, float oy, const float* __restrict__ theta_u, int n_rounds,
-                                                 float heading_u, float& cx, float& cy, float& cz, float& chead) {
+                                                 float ox, float oy, const float* __restrict__ theta_u,
+                                                 const float (&theta0)[8], int n_rounds, float heading_u, float& cx,
+                                                 float& cy, float& cz, float& chead) {
     const float pi_f = 3.1415927f;  // torch.pi as fp32; the reference computes rand * 2 * pi left to right
     constexpr int kBatch = 8;
     float x = 0.f, y = 0.f;
@@ -323,7 +324,8 @@ __device__ __forceinline__ bool resample_command(int i, const RoverMdpParams& P,
         int cols[kBatch], rows[kBatch];
         uint8_t m[kBatch];
 #pragma unroll
-        for (int k = 0; k < kBatch; ++k) u[k] = (r0 + k < n_rounds) ? __ldg(theta_u + (size_t)i * n_rounds + r0 + k) : 0.f;
+        for (int k = 0; k < kBatch; ++k)  // the first batch was prefetched by the caller
+            u[k] = (r0 == 0) ? theta0[k] : ((r0 + k < n_rounds) ? __ldg(theta_u + (size_t)i * n_rounds + r0 + k) : 0.f);
 #pragma unroll
         for (int k = 0; k < kBatch; ++k) {
             const float th = __fmul_rn(__fmul_rn(u[k], 2.f), pi_f);                      // :169
@@ -369,6 +371,25 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
     const bool valid = i < n;
     const bool reset = valid && O.reset_flags[i] != 0;
 
+    // ---- every load that does not depend on the reset rank is issued up front, so that the kernel pays one memory
+    //      round trip for them instead of one per dependent stage (this launch is latency-bound, not bandwidth-bound)
+    float px = 0.f, py = 0.f, pz = 0.f, cwx = 0.f, cwy = 0.f, cwz = 0.f, chead = 0.f, time_left = 0.f;
+    float yaw_var = 0.f, heading_var = 0.f, theta0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    float2 act = make_float2(0.f, 0.f);
+    if (valid) {
+        px = root_pos_w[3 * (size_t)i], py = root_pos_w[3 * (size_t)i + 1], pz = root_pos_w[3 * (size_t)i + 2];
+        q = reinterpret_cast<float4*>(root_quat_w)[i];  // (w,x,y,z)
+        cwx = S.pos_cmd_w[3 * (size_t)i], cwy = S.pos_cmd_w[3 * (size_t)i + 1], cwz = S.pos_cmd_w[3 * (size_t)i + 2];
+        chead = S.heading_cmd_w[i];
+        act = reinterpret_cast<float2*>(S.action)[i];
+        time_left = S.time_left[i];
+        yaw_var = __ldg(yaw_u + i);
+        heading_var = __ldg(heading_u + i);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) theta0[k] = (k < n_rounds) ? __ldg(theta_u + (size_t)i * n_rounds + k) : 0.f;
+    }
+
     // ---- rank of this env among the reset envs in ascending env order (== reset_buf.nonzero() order)
     if (wid == 0) {
         int acc = 0;
@@ -387,12 +408,6 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
     for (int k = 0; k < kStats; ++k) st[k] = 0.f;
 
     if (valid) {
-        float px = root_pos_w[3 * (size_t)i], py = root_pos_w[3 * (size_t)i + 1], pz = root_pos_w[3 * (size_t)i + 2];
-        float4 q = reinterpret_cast<float4*>(root_quat_w)[i];  // (w,x,y,z)
-        float cwx = S.pos_cmd_w[3 * (size_t)i], cwy = S.pos_cmd_w[3 * (size_t)i + 1], cwz = S.pos_cmd_w[3 * (size_t)i + 2];
-        float chead = S.heading_cmd_w[i];
-        float2 act = reinterpret_cast<float2*>(S.action)[i];
-        float time_left = S.time_left[i];
         long long spawn_idx = -1;
         bool cmd_dirty = false;
 
@@ -403,7 +418,7 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
             px = __ldg(sp);
             py = __ldg(sp + 1);
             pz = __fadd_rn(__ldg(sp + 2), P.spawn_z_offset);
-            const float angle = __fmul_rn(__fmul_rn(__ldg(yaw_u + i), 2.f), 3.1415927f);
+            const float angle = __fmul_rn(__fmul_rn(yaw_var, 2.f), 3.1415927f);
             const float half = __fdiv_rn(angle, 2.f);
             q = make_float4(cosf(half), 0.f, 0.f, sinf(half));
             S.env_origins[3 * (size_t)i] = px;
@@ -444,7 +459,7 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
         if (reset && (phases & ROVER_PHASE_RESAMPLE)) {
             // -- CommandTerm._resample: time_left, counter += 1, _resample_command around the (new) env origin
             const float ox = S.env_origins[3 * (size_t)i], oy = S.env_origins[3 * (size_t)i + 1];
-            const bool exhausted = resample_command(i, P, S, T, ox, oy, theta_u, n_rounds, __ldg(heading_u + i), cwx,
+            const bool exhausted = resample_command(i, P, S, T, ox, oy, theta_u, theta0, n_rounds, heading_var, cwx,
                                                     cwy, cwz, chead);
             st[14] = exhausted ? 1.f : 0.f;
             S.command_counter[i] += 1;
@@ -463,7 +478,7 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
         if (phases & ROVER_PHASE_TIME) time_left = __fsub_rn(time_left, P.step_dt);
         if ((phases & ROVER_PHASE_TIME) && time_left <= 0.f) {
             const float ox = S.env_origins[3 * (size_t)i], oy = S.env_origins[3 * (size_t)i + 1];
-            const bool exhausted = resample_command(i, P, S, T, ox, oy, theta_u, n_rounds, __ldg(heading_u + i), cwx,
+            const bool exhausted = resample_command(i, P, S, T, ox, oy, theta_u, theta0, n_rounds, heading_var, cwx,
                                                     cwy, cwz, chead);
             st[14] += exhausted ? 1.f : 0.f;
             st[15] = 1.f;
