@@ -394,6 +394,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(v, f, steps=3, warmup=1, n_envs=256)
 
+    line = None
     if rank == 0:
         line = {
             "metric": "height_scan_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world,
@@ -415,10 +416,10 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "extra": extra,
         }
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 def cpu_reference(v, f, steps, warmup, n_envs):
@@ -471,6 +472,21 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class StdoutToStderr:
+    """Everything but the final JSON line goes to stderr (NCCL prints its version banner on fd 1)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -485,7 +501,10 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        with StdoutToStderr():
+            line = run_ours(args)
+        if line is not None:
+            print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
