@@ -219,7 +219,8 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     achieved = alg_bytes / t_launch / 1e9
     kname = {0: "height_scan_direct_kernel", 1: "height_scan_staged_kernel", 2: "height_scan_cells_kernel",
-             3: "height_scan_cells_tma_kernel", 4: "height_scan_pipelined_kernel"}[args.variant]
+             3: "height_scan_cells_tma_kernel", 4: "height_scan_pipelined_kernel",
+             5: "height_scan_paired_kernel"}[args.variant]
 
     # ------------------------------------------------------------------ e2e: host buffers through the public API
     pin = [(p.pin_memory(), q.pin_memory()) for p, q in poses]
@@ -493,7 +494,7 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", type=int, default=int(os.environ.get("ROVER_SCAN_VARIANT", "4")))
+    ap.add_argument("--variant", type=int, default=int(os.environ.get("ROVER_SCAN_VARIANT", "5")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the fused step kernel by kernel instead of replaying CUDA graphs")
     ap.add_argument("--init-on-cpu", action="store_true", help="build the init-time tables on the host (profiling)")

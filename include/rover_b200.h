@@ -74,7 +74,9 @@ typedef struct RoverPlaneCells {
  * cells (HOST struct, device pointers inside; required by variant 2, may be NULL otherwise).
  * variant: 0 = direct home-grid walk, 1 = shared-memory staged home-grid walk, 2 = plane-cell fast path with
  * home-grid fallback for general cells, 3 = variant 2 with the per-env table window staged through cp.async.bulk,
- * 4 = persistent warp-specialised pipeline (producer warp + 2-stage cp.async.bulk/mbarrier ring + consumer warps).
+ * 4 = persistent warp-specialised pipeline (producer warp + 8-stage ring of 2-D tensor-map TMA loads on mbarriers +
+ * consumer warps), 5 = variant 4's pipeline with 256-ray chunks dealt round-robin to the consumer warps and ray
+ * pairs resolved with packed fp32 (FADD2 / FMUL2) -- the default of the Python binding.
  * All variants produce the same heights. */
 int rover_height_scan(const float* pos_w, const float* quat_w, int32_t n_envs, const float* ray_starts_local,
                       int32_t n_rays, const float* pattern_box /* host */, const RoverScanGrid* grid /* host */,

@@ -174,6 +174,11 @@ int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_
                                  float max_d, float base_offset, float* out, int out_stride, float* hits,
                                  cudaStream_t stream);  // height_scan_pipelined.cu
 
+int launch_height_scan_paired(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local, int n_rays,
+                              const ScanGridDev& g, const RoverPlaneCells* cells, float4 pattern_box, float max_d,
+                              float base_offset, float* out, int out_stride, float* hits,
+                              cudaStream_t stream);  // height_scan_paired.cu
+
 }  // namespace rover
 
 extern "C" int rover_height_scan(const float* pos_w, const float* quat_w, int32_t n_envs,
@@ -203,19 +208,25 @@ extern "C" int rover_height_scan(const float* pos_w, const float* quat_w, int32_
         return launch_height_scan_staged(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, box, max_distance,
                                          base_offset, out_heights, out_stride, out_hits_w, s);
     }
-    if (variant == 2 || variant == 3 || variant == 4) {
-        ROVER_CHECK(cells != nullptr, "rover_height_scan: variants 2/3/4 need the plane-cell table");
+    if (variant >= 2 && variant <= 5) {
+        ROVER_CHECK(cells != nullptr, "rover_height_scan: variants 2..5 need the plane-cell table");
         ROVER_CHECK(cells->xs && cells->ys && cells->entries && cells->nx > 0 && cells->ny > 0,
                     "rover_height_scan: bad plane-cell table");
         ROVER_CHECK((reinterpret_cast<uintptr_t>(cells->entries) & 15) == 0,
                     "rover_height_scan: plane-cell entries not 16B aligned");
-        if (variant == 4 && n_rays <= 1024) {
+        if (variant == 5 && n_rays <= 1024) {
+            ROVER_CHECK(pattern_box != nullptr, "rover_height_scan: variant 5 needs pattern_box (host, 4 floats)");
+            const float4 box = make_float4(pattern_box[0], pattern_box[1], pattern_box[2], pattern_box[3]);
+            return launch_height_scan_paired(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, cells, box,
+                                             max_distance, base_offset, out_heights, out_stride, out_hits_w, s);
+        }
+        if (variant >= 4 && n_rays <= 1024) {
             ROVER_CHECK(pattern_box != nullptr, "rover_height_scan: variant 4 needs pattern_box (host, 4 floats)");
             const float4 box = make_float4(pattern_box[0], pattern_box[1], pattern_box[2], pattern_box[3]);
             return launch_height_scan_pipelined(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, cells, box,
                                                 max_distance, base_offset, out_heights, out_stride, out_hits_w, s);
         }
-        if (variant == 3 || variant == 4) {  // variant 4 with a pattern too large for its shared table -> variant 3
+        if (variant >= 3) {  // variants 4/5 with a pattern too large for their shared table -> variant 3
             ROVER_CHECK(pattern_box != nullptr, "rover_height_scan: variant 3 needs pattern_box (host, 4 floats)");
             const float4 box = make_float4(pattern_box[0], pattern_box[1], pattern_box[2], pattern_box[3]);
             return launch_height_scan_cells_tma(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, cells, box,

@@ -93,7 +93,7 @@ class RayPattern:
         return cls(grid_pattern(resolution, size, offset_pos), device)
 
 
-DEFAULT_SCAN_VARIANT = 4
+DEFAULT_SCAN_VARIANT = 5
 
 
 def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle,
@@ -113,8 +113,8 @@ def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridH
         raise RuntimeError("height_scan: bad shapes")
     if grid.device != dev:
         raise RuntimeError("height_scan: grid lives on another device")
-    if variant in (2, 3, 4) and grid.cells_struct is None:
-        raise RuntimeError("height_scan: variants 2/3/4 need a ScanGridHandle built with plane_cells=True")
+    if variant in (2, 3, 4, 5) and grid.cells_struct is None:
+        raise RuntimeError("height_scan: variants 2..5 need a ScanGridHandle built with plane_cells=True")
     if out is None:
         out = torch.empty(n, r, dtype=torch.float32, device=dev)
     elif out.dtype != torch.float32 or out.shape != (n, r) or out.stride(1) != 1 or out.device != dev:

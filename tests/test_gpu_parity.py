@@ -42,7 +42,7 @@ def _scan_compare(h_gpu, h_ref, t_ref=10.0):
         assert err <= 1e-5 * max(t_ref, 1.0), f"height error {err}"
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_height_scan_vs_oracle_small_terrain(world, variant):
     from oracle import step as OS
 
@@ -65,7 +65,7 @@ def test_height_scan_vs_oracle_small_terrain(world, variant):
     torch.testing.assert_close(hits[~miss], hits_ref[~miss], rtol=1e-6, atol=1e-4)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_height_scan_analytic_plane(cuda_device, variant):
     """Independent of the oracle: on the plane z = 0.3x - 0.2y + 1 the scan equals body_z - z(x,y) - 0.26878 at the
     961 yaw-rotated grid points (SURVEY.md 8c invariant)."""
@@ -93,7 +93,7 @@ def test_height_scan_analytic_plane(cuda_device, variant):
     torch.testing.assert_close(h, expect, rtol=0, atol=2e-4)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_height_scan_mixed_mesh_levels_and_degenerates(cuda_device, variant):
     """Ground of two huge triangles + small rock pyramids + vertical / zero-area / flipped triangles."""
     from oracle import raycast as oracle_raycast
@@ -133,7 +133,7 @@ def test_height_scan_mixed_mesh_levels_and_degenerates(cuda_device, variant):
     _scan_compare(h, h_ref)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_height_scan_max_distance_and_empty(cuda_device, variant):
     v = np.array([[-5, -5, -95.0], [5, -5, -95.0], [0, 5, -95.0]], dtype=np.float32)
     f = np.array([[0, 1, 2]], dtype=np.int32)
