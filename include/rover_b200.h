@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ROVER_B200_ABI_VERSION 1
+#define ROVER_B200_ABI_VERSION 2
 #define ROVER_MAX_LEVELS 12
 #define ROVER_NUM_REWARD_TERMS 7
 #define ROVER_NUM_TERMINATION_TERMS 4
@@ -64,6 +64,10 @@ typedef struct RoverPlaneCells {
     const float* entries;  /* [ny, nx, 8], 16-byte aligned */
     int32_t nx, ny;
     float inv_dx, inv_dy;  /* nx / (xs[nx]-xs[0]), ny / (ys[ny]-ys[0]): first guess of the cell */
+    const float* entries_planar; /* optional (may be NULL): the same table as two planes [2, ny, nx, 4] -- plane 0 the
+                                    first, plane 1 the second float4 of every entry; 16-byte aligned.  Variant 5 stages
+                                    windows from it (16-byte plane entries with an odd row pitch in shared memory make
+                                    the per-ray LDS.128 bank-conflict free); without it variant 5 runs as variant 4. */
 } RoverPlaneCells;
 
 /* pos_w [n_envs,3], quat_w [n_envs,4]: sensor (body) pose, sensor.data.pos_w / quat_w.

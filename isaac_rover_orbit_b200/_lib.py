@@ -18,7 +18,7 @@ NUM_REWARD_TERMS = 7
 NUM_TERMINATION_TERMS = 4
 STATS_LEN = 16
 MDP_BLOCK = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_mdp_pre_step", "rover_mdp_post_step",
            "rover_ackermann",
@@ -38,7 +38,7 @@ class ScanGrid(C.Structure):
 
 class PlaneCells(C.Structure):
     _fields_ = [("xs", C.c_void_p), ("ys", C.c_void_p), ("entries", C.c_void_p), ("nx", C.c_int32), ("ny", C.c_int32),
-                ("inv_dx", C.c_float), ("inv_dy", C.c_float)]
+                ("inv_dx", C.c_float), ("inv_dy", C.c_float), ("entries_planar", C.c_void_p)]
 
 
 class MdpParams(C.Structure):

@@ -54,6 +54,10 @@ constexpr int kPairThreads = 32 * (1 + kPairConsumerWarps);
 constexpr int kPairStages = 8;          // ring depth (data)
 constexpr int kPairFullBars = 16;       // `full` barriers: two per stage, see the note on phase aliasing below
 constexpr int kPairWin = 26;            // window cells per axis
+constexpr int kPairPitch = 27;          // cells per staged row: odd, so that consecutive rows shift by one 16-byte bank
+                                        // group and a quarter-warp's LDS.128 of 8 neighbouring cells is conflict free
+constexpr int kPairPlane = kPairWin * kPairPitch;             // float4 per plane
+constexpr uint32_t kPairStageBytes = 2u * kPairPlane * 16u;   // bytes one TMA load delivers
 constexpr int kPairChunk = 256;         // rays per work unit: 2 batches x 2 pair slots x 32 lanes x 2 rays
 constexpr int kPairMaxRays = 1024;      // pattern held in shared memory (3 float arrays)
 constexpr int kPairMaxLines = 1024;     // grid-line pairs per axis held in shared memory
@@ -67,10 +71,15 @@ struct PairHeader {
     int nrows, mode, pad0, pad1;  // mode 1: window staged in shared memory, 0: read the table from global memory
 };
 
+// Planes of the window: p[row][col] = (a, b, c, k), q[row][col] = (A, B, C, tag) of cell (jr0 + row, ic0 + col).
+// (With the interleaved 32-byte entries of the other variants every LDS.128 of a quarter-warp could reach only the
+// even 16-byte bank groups: 2.5x the minimum number of shared-memory wavefronts, measured with ncu.)
 struct __align__(128) PairStage {
-    float4 ent[kPairWin * kPairWin * 2];
+    float4 p[kPairPlane];
+    float4 q[kPairPlane];
     PairHeader hdr;
 };
+static_assert(offsetof(PairStage, q) == kPairPlane * 16, "planes must be contiguous: one 3-D TMA box fills both");
 
 struct PairSmem {
     PairStage stage[kPairStages];
@@ -88,6 +97,17 @@ struct PairSmem {
 static_assert(kPairFullBars == 2 * kPairStages, "full barriers: two per stage");
 
 static_assert(sizeof(PairSmem) <= 227 * 1024, "PairSmem exceeds the shared memory of one SM");
+
+// one 3-D TMA tile load (UTMALDG): box (set in the tensor map) = kPairPitch cells x kPairWin rows x 2 planes of the
+// planar table, starting at cell (col, row); lands as PairStage::p followed by PairStage::q
+__device__ __forceinline__ void tma_load_window_planar(void* dst, const CUtensorMap* tmap, int col, int row,
+                                                       unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+            "r"(s_addr(dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(col * 4), "r"(row), "r"(0), "r"(s_addr(bar))
+        : "memory");
+}
 
 // ---- packed fp32 pairs (one 64-bit register pair; lo = ray 2k, hi = ray 2k+1)
 typedef unsigned long long f32x2;
@@ -160,9 +180,9 @@ __device__ __noinline__ void pair_resolve_deferred_ray(const PairSmem* sm, const
         while (ci < cmax && X >= xp[ci].hi) ++ci;
         while (cj > 0 && Y < yp[cj].lo) --cj;
         while (cj < rmax && Y >= yp[cj].hi) ++cj;
-        const int e = 2 * (cj * kPairWin + ci);
-        const float4 q = st->ent[e + 1];
-        zhit = (q.w == 0.f) ? eval_cell(st->ent[e], q, __fsub_rn(X, xp[ci].lo), __fsub_rn(Y, yp[cj].lo), Z, max_d)
+        const int e = cj * kPairPitch + ci;
+        const float4 q = st->q[e];
+        zhit = (q.w == 0.f) ? eval_cell(st->p[e], q, __fsub_rn(X, xp[ci].lo), __fsub_rn(Y, yp[cj].lo), Z, max_d)
                             : walk_home_grid(g, X, Y, Z, max_d);
     }
     store_result(pz, X, Y, Z, zhit, base_offset, out, nullptr);
@@ -213,10 +233,18 @@ __device__ __forceinline__ unsigned resolve_pair(const unsigned char* __restrict
         const int bj = min(max(__float_as_int(k ? hi_of(BY) : lo_of(BY)), kFloorMagicBits), c.by_hi);
         const float2 xp = *reinterpret_cast<const float2*>(smem + (c.xoff + (uint32_t)bi * 8u));
         const float2 yp = *reinterpret_cast<const float2*>(smem + (c.yoff + (uint32_t)bj * 8u));
-        const uint32_t e = c.eoff + (uint32_t)bj * (uint32_t)(kPairWin * 32) + (uint32_t)bi * 32u;
-        const float4 q = *reinterpret_cast<const float4*>(smem + e + 16);
+#if ROVER_SCAN_DBG == 5  // timing experiment: conflict-free entry loads (results are wrong)
+        const uint32_t e = (c.eoff + (uint32_t)kFloorMagicBits * (uint32_t)(kPairPitch * 16 + 16)) + ((threadIdx.x & 31) * 16u) +
+                           (((uint32_t)bj + (uint32_t)bi) & 1u) * 1024u;
+        const float4 q = *reinterpret_cast<const float4*>(smem + e + 512);
+        const float4 p = *reinterpret_cast<const float4*>(smem + e);
+        const bool fast = (x >= xp.x) & (x < xp.y) & (y >= yp.x) & (y < yp.y);
+#else
+        const uint32_t e = c.eoff + (uint32_t)bj * (uint32_t)(kPairPitch * 16) + (uint32_t)bi * 16u;
+        const float4 q = *reinterpret_cast<const float4*>(smem + e + kPairPlane * 16);
         const float4 p = *reinterpret_cast<const float4*>(smem + e);
         const bool fast = (x >= xp.x) & (x < xp.y) & (y >= yp.x) & (y < yp.y) & (q.w == 0.f);
+#endif
         const float lx = __fsub_rn(x, xp.x), ly = __fsub_rn(y, yp.x);
         const float E = fmaf(q.x, lx, fmaf(q.y, ly, q.z));
         // -z, with z = fma(k, min(E, 0), fma(a, lx, fma(b, ly, c))) exactly as eval_cell (negation commutes with rn)
@@ -317,10 +345,10 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
         producer_load(cur, lane, n_iter, pos_w, quat_w);
         producer_window(cur, pc, pattern_radius);
         if (lane < n_iter && lane < kPairStages && ROVER_SCAN_DBG != 4) {
-            // the box is always kPairWin x kPairWin cells; cells beyond the table are zero-filled and never read;
+            // the box is always kPairPitch x kPairWin cells; cells beyond the table are zero-filled and never read;
             // a window that later turns out not to fit / not to cover is loaded all the same and simply not used
-            bar_arrive_expect_tx(&sm.full_bar[lane], (uint32_t)(kPairWin * kPairWin * 32));
-            tma_load_window(sm.stage[lane].ent, &tmap, cur.ic0, cur.jr0, &sm.full_bar[lane]);
+            bar_arrive_expect_tx(&sm.full_bar[lane], kPairStageBytes);
+            tma_load_window_planar(sm.stage[lane].p, &tmap, cur.ic0, cur.jr0, &sm.full_bar[lane]);
             DBG_STAMP_ANY(16 + lane);
         }
         producer_frame(cur);
@@ -389,8 +417,8 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
                     if (!first_pass) {
                         bar_wait(&sm.empty_bar[s], ((uint32_t)(it / kPairStages) & 1u) ^ 1u);  // stage drained
                         if (cur.ok && ROVER_SCAN_DBG != 2) {
-                            bar_arrive_expect_tx(full, (uint32_t)(kPairWin * kPairWin * 32));
-                            tma_load_window(st.ent, &tmap, cur.ic0, cur.jr0, full);
+                            bar_arrive_expect_tx(full, kPairStageBytes);
+                            tma_load_window_planar(st.p, &tmap, cur.ic0, cur.jr0, full);
                         } else {
                             bar_arrive(full);
                         }
@@ -443,8 +471,8 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
                 const uint32_t bias = (uint32_t)kFloorMagicBits;
                 cx.xoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.xpair + h.ic0) - smem_raw) - bias * 8u;
                 cx.yoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.ypair + h.jr0) - smem_raw) - bias * 8u;
-                cx.eoff = (uint32_t)(reinterpret_cast<const unsigned char*>(st.ent) - smem_raw) -
-                          bias * (uint32_t)(kPairWin * 32) - bias * 32u;
+                cx.eoff = (uint32_t)(reinterpret_cast<const unsigned char*>(st.p) - smem_raw) -
+                          bias * (uint32_t)(kPairPitch * 16) - bias * 16u;
                 for (int b0 = r_begin; b0 < r_end; b0 += kPairChunk / 2) {
                     const int r = b0 + 2 * lane;
                     float* __restrict__ o = out_row + r;
@@ -488,8 +516,9 @@ int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_
 int launch_height_scan_paired(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local, int n_rays,
                               const ScanGridDev& g, const RoverPlaneCells* cells, float4 pattern_box, float max_d,
                               float base_offset, float* out, int out_stride, float* hits, cudaStream_t stream) {
-    // hit positions are a debugging / test output: served by variant 4's kernel (same heights, same table)
-    if (hits != nullptr)
+    // hit positions are a debugging / test output: served by variant 4's kernel (same heights, same table); so is a
+    // table without the planar copy
+    if (hits != nullptr || cells->entries_planar == nullptr)
         return launch_height_scan_pipelined(pos_w, quat_w, n_envs, ray_local, n_rays, g, cells, pattern_box, max_d,
                                             base_offset, out, out_stride, hits, stream);
     ROVER_CHECK(n_rays >= 1 && n_rays <= kPairMaxRays, "height_scan_paired: pattern of %d rays (1..%d supported)", n_rays,
@@ -505,7 +534,7 @@ int launch_height_scan_paired(const float* pos_w, const float* quat_w, int n_env
         configured = true;
     }
     alignas(64) CUtensorMap tmap;
-    if (const int rc = encode_cells_tensor_map(&tmap, cells, kPairWin, "height_scan_paired")) return rc;
+    if (const int rc = encode_planar_tensor_map(&tmap, cells, kPairPitch, kPairWin, "height_scan_paired")) return rc;
     PlaneCellsDev pc{cells->xs, cells->ys, reinterpret_cast<const float4*>(cells->entries), cells->nx, cells->ny,
                      cells->inv_dx, cells->inv_dy};
     // every ray origin lies within this distance of the sensor position (the yaw rotation preserves norms)

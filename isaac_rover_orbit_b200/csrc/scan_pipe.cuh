@@ -147,4 +147,28 @@ inline int encode_cells_tensor_map(CUtensorMap* tmap, const RoverPlaneCells* cel
     return 0;
 }
 
+// 3-D tensor map over the planar copy of the table [2, ny, nx * 4 floats]; box = win_cols cells x win_rows rows x 2.
+inline int encode_planar_tensor_map(CUtensorMap* tmap, const RoverPlaneCells* cells, int win_cols, int win_rows,
+                                    const char* who) {
+    static TensorMapEncodeTiledFn encode = nullptr;
+    if (encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        ROVER_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        ROVER_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess,
+                    "%s: cuTensorMapEncodeTiled is not available in this driver", who);
+        encode = reinterpret_cast<TensorMapEncodeTiledFn>(fn);
+    }
+    ROVER_CHECK((reinterpret_cast<uintptr_t>(cells->entries_planar) & 15) == 0, "%s: entries_planar not 16B aligned", who);
+    const cuuint64_t gdim[3] = {(cuuint64_t)cells->nx * 4ull, (cuuint64_t)cells->ny, 2ull};
+    const cuuint64_t gstride[2] = {(cuuint64_t)cells->nx * 16ull, (cuuint64_t)cells->nx * 16ull * (cuuint64_t)cells->ny};
+    const cuuint32_t box[3] = {(cuuint32_t)win_cols * 4u, (cuuint32_t)win_rows, 2u};
+    const cuuint32_t estride[3] = {1u, 1u, 1u};
+    const CUresult rc = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(cells->entries_planar), gdim,
+                               gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ROVER_CHECK(rc == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled (planar) failed (%d)", who, (int)rc);
+    return 0;
+}
+
 }  // namespace rover

@@ -33,9 +33,11 @@ class ScanGridHandle:
             self.cells_xs = cells.xs.to(self.device).contiguous()
             self.cells_ys = cells.ys.to(self.device).contiguous()
             self.cells_entries = cells.entries.to(self.device).contiguous()
+            # the same table as two planes [2, ny, nx, 4] (variant 5 stages windows from it: conflict-free LDS.128)
+            self.cells_planar = self.cells_entries.view(cells.ny, cells.nx, 2, 4).permute(2, 0, 1, 3).contiguous()
             self.cells_struct = _lib.PlaneCells(self.cells_xs.data_ptr(), self.cells_ys.data_ptr(),
                                                 self.cells_entries.data_ptr(), cells.nx, cells.ny, cells.inv_dx,
-                                                cells.inv_dy)
+                                                cells.inv_dy, self.cells_planar.data_ptr())
         self.cell_start = grid.cell_start.to(self.device).contiguous()
         self.records = grid.records.to(self.device).contiguous()
         if grid.n_records == 0:
