@@ -30,6 +30,12 @@ namespace rover {
 
 #if ROVER_SCAN_DBG == 3  // timeline of CTA 0 and CTA 100 in SM cycles since the CTA started (bring-up builds only)
 __device__ unsigned long long g_scan_dbg[2][512];
+__device__ unsigned long long g_scan_cta[2][256];  // [0][b] = globaltimer at CTA start, [1][b] = at its last warp's end
+__device__ __forceinline__ unsigned long long dbg_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 #define DBG_STAMP(slot)                                                                             \
     do {                                                                                            \
         if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 100) && (slot) < 512)                    \
@@ -63,6 +69,20 @@ constexpr int kPairMaxRays = 1024;      // pattern held in shared memory (3 floa
 constexpr int kPairMaxLines = 1024;     // grid-line pairs per axis held in shared memory
 constexpr float kFloorMagic = 12582912.0f;  // 1.5 * 2^23: fl_rm(v + magic) has floor(v) in its mantissa for |v| < 2^22
 constexpr int kFloorMagicBits = 0x4B400000;
+
+// Lane <-> ray mapping inside a batch of 128 rays [b0, b0 + 128): lane l, slot u (0/1) resolves the pair
+//   A = b0 + 32u + l,  B = A + 64.
+// One instruction therefore serves 32 CONSECUTIVE rays (0.1 m apart: a quarter-warp touches ~4 cells, not 8, and
+// its stores fill whole sectors), while the two rays of a pair still come out of one LDS.64: the pattern arrays are
+// held in slot order, slot(A) = b0 + 64u + 2l, slot(B) = slot(A) + 1.
+__host__ __device__ __forceinline__ int ray_of_slot(int s) {
+    const int j = s & 127;
+    return (s & ~127) + 64 * (j & 1) + 32 * (j >> 6) + ((j & 63) >> 1);
+}
+__host__ __device__ __forceinline__ int slot_of_ray(int r) {
+    const int j = r & 127;
+    return (r & ~127) + 64 * ((j >> 5) & 1) + 2 * (j & 31) + (j >> 6);
+}
 
 struct PairHeader {
     float cw, sz, px, py;
@@ -156,10 +176,10 @@ __device__ __forceinline__ f32x2 add2_rm(f32x2 a, f32x2 b) {  // round toward -i
 
 // per-chunk constants of the consumer loop
 struct PairCtx {
-    f32x2 CW, SZ, NSZ, S2, NS2, PX, PY, PZ, NWX0, NWY0, IDX, IDY, MAGIC, BASE, NEG0;
+    f32x2 CW, SZ, NSZ, S2, NS2, PX, PY, PZ, NWX0, NWY0, IDX, IDY, MAGIC, BASE, NEG0, ZFLAT;
     float pz, max_d;
-    uint32_t xoff, yoff, eoff;  // byte offsets into shared memory with the magic bias folded in
-    int bx_hi, by_hi;           // clamp bounds on the raw bits
+    uint32_t xoff, yoff, eoff;  // byte offsets into shared memory of the window's line pairs / p plane
+    uint32_t cmax, rmax;        // last column / row of the window
 };
 
 // Rare path (a): a ray whose cell guess missed, that lies on the closed far border / outside the grid, or sits in a
@@ -196,30 +216,34 @@ __device__ __noinline__ void pair_resolve_chunk_from_global(const PairSmem* sm, 
                                                             float* __restrict__ out_row) {
     const float sz2 = __fmul_rn(h.sz, 2.f);
     for (int r = r_begin + lane; r < r_end; r += 32) {
-        const float vx = sm->vx[r], vy = sm->vy[r];
+        const int sl = slot_of_ray(r);
+        const float vx = sm->vx[sl], vy = sm->vy[sl];
         const float tx = -__fmul_rn(sz2, vy), ty = __fmul_rn(sz2, vx);
         const float X = __fadd_rn(__fadd_rn(__fadd_rn(vx, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
         const float Y = __fadd_rn(__fadd_rn(__fadd_rn(vy, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
-        const float Z = __fadd_rn(sm->vz[r], h.pz);
+        const float Z = __fadd_rn(sm->vz[sl], h.pz);
         store_result(h.pz, X, Y, Z, resolve_from_global(g, pc, X, Y, Z, max_d), base_offset, out_row + r, nullptr);
     }
 }
 
 // One pair slot: rays (r, r+1).  Everything that can go wrong is deferred, so the body is branch-free up to the stores.
 // Returns a 2-bit mask of the rays that need the rare path.
+// kFull: the whole batch lies inside the pattern (no per-ray validity predicates); kFlatZ: every ray starts at the
+// same local z (grid patterns), so Z is a per-environment constant.
+template <bool kFull, bool kFlatZ>
 __device__ __forceinline__ unsigned resolve_pair(const unsigned char* __restrict__ smem, const PairSmem& sm,
-                                                 const PairCtx& c, int r, int n_rays, float* __restrict__ o) {
-    const bool valid0 = r < n_rays, valid1 = r + 1 < n_rays;
-    const int idx = valid0 ? r : 0;
+                                                 const PairCtx& c, int slot, int ray_a, int n_rays,
+                                                 float* __restrict__ o) {
+    const bool valid0 = kFull || ray_a < n_rays, valid1 = kFull || ray_a + 64 < n_rays;
+    const int idx = slot;  // slots beyond the pattern hold zeros
     const f32x2 VX = *reinterpret_cast<const f32x2*>(sm.vx + idx);
     const f32x2 VY = *reinterpret_cast<const f32x2*>(sm.vy + idx);
-    const f32x2 VZ = *reinterpret_cast<const f32x2*>(sm.vz + idx);
     // ORBIT quat_apply_yaw + pos, same roundings as ray_origin(): tx = -(2sz * vy), ty = 2sz * vx,
     // X = ((vx + cw*tx) + (-(sz*ty))) + px, Y = ((vy + cw*ty) + sz*tx) + py, Z = vz + pz.  Negations are exact.
     const f32x2 TX = mul2(c.NS2, VY), TY = mul2(c.S2, VX);
     const f32x2 X = add2(add2(add2(VX, mul2_unfused(c.CW, TX, c.NEG0)), mul2_unfused(c.NSZ, TY, c.NEG0)), c.PX);
     const f32x2 Y = add2(add2(add2(VY, mul2_unfused(c.CW, TY, c.NEG0)), mul2_unfused(c.SZ, TX, c.NEG0)), c.PY);
-    const f32x2 Z = add2(VZ, c.PZ);
+    const f32x2 Z = kFlatZ ? c.ZFLAT : add2(*reinterpret_cast<const f32x2*>(sm.vz + idx), c.PZ);
     // window-relative cell guess: floor((X - wx0) * inv_dx) left in the mantissa, clamped on the raw bits
     const f32x2 BX = add2_rm(mul2(add2(X, c.NWX0), c.IDX), c.MAGIC);
     const f32x2 BY = add2_rm(mul2(add2(Y, c.NWY0), c.IDY), c.MAGIC);
@@ -229,18 +253,18 @@ __device__ __forceinline__ unsigned resolve_pair(const unsigned char* __restrict
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const float x = k ? hi_of(X) : lo_of(X), y = k ? hi_of(Y) : lo_of(Y);
-        const int bi = min(max(__float_as_int(k ? hi_of(BX) : lo_of(BX)), kFloorMagicBits), c.bx_hi);
-        const int bj = min(max(__float_as_int(k ? hi_of(BY) : lo_of(BY)), kFloorMagicBits), c.by_hi);
-        const float2 xp = *reinterpret_cast<const float2*>(smem + (c.xoff + (uint32_t)bi * 8u));
-        const float2 yp = *reinterpret_cast<const float2*>(smem + (c.yoff + (uint32_t)bj * 8u));
+        // one unsigned min clamps both ends: bits below the bias (negative index, NaN ...) wrap to a huge value
+        const uint32_t bi = min(__float_as_uint(k ? hi_of(BX) : lo_of(BX)) - (uint32_t)kFloorMagicBits, c.cmax);
+        const uint32_t bj = min(__float_as_uint(k ? hi_of(BY) : lo_of(BY)) - (uint32_t)kFloorMagicBits, c.rmax);
+        const float2 xp = *reinterpret_cast<const float2*>(smem + (c.xoff + bi * 8u));
+        const float2 yp = *reinterpret_cast<const float2*>(smem + (c.yoff + bj * 8u));
 #if ROVER_SCAN_DBG == 5  // timing experiment: conflict-free entry loads (results are wrong)
-        const uint32_t e = (c.eoff + (uint32_t)kFloorMagicBits * (uint32_t)(kPairPitch * 16 + 16)) + ((threadIdx.x & 31) * 16u) +
-                           (((uint32_t)bj + (uint32_t)bi) & 1u) * 1024u;
+        const uint32_t e = c.eoff + ((threadIdx.x & 31) * 16u) + ((bj + bi) & 1u) * 1024u;
         const float4 q = *reinterpret_cast<const float4*>(smem + e + 512);
         const float4 p = *reinterpret_cast<const float4*>(smem + e);
         const bool fast = (x >= xp.x) & (x < xp.y) & (y >= yp.x) & (y < yp.y);
 #else
-        const uint32_t e = c.eoff + (uint32_t)bj * (uint32_t)(kPairPitch * 16) + (uint32_t)bi * 16u;
+        const uint32_t e = c.eoff + bj * (uint32_t)(kPairPitch * 16) + bi * 16u;
         const float4 q = *reinterpret_cast<const float4*>(smem + e + kPairPlane * 16);
         const float4 p = *reinterpret_cast<const float4*>(smem + e);
         const bool fast = (x >= xp.x) & (x < xp.y) & (y >= yp.x) & (y < yp.y) & (q.w == 0.f);
@@ -260,7 +284,7 @@ __device__ __forceinline__ unsigned resolve_pair(const unsigned char* __restrict
     const float h0 = (t0 >= 0.f && t0 < c.max_d) ? lo_of(H) : -INFINITY;
     const float h1 = (t1 >= 0.f && t1 < c.max_d) ? hi_of(H) : -INFINITY;
     if (keep[0]) o[0] = h0;
-    if (keep[1]) o[1] = h1;
+    if (keep[1]) o[64] = h1;
     return defer;
 }
 
@@ -328,13 +352,19 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
     const bool lines_in_smem = (pc.nx <= kPairMaxLines) && (pc.ny <= kPairMaxLines);
 #if ROVER_SCAN_DBG == 3
     const long long dbg_t0 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x < 256) {
+        g_scan_cta[0][blockIdx.x] = dbg_globaltimer();
+        g_scan_cta[1][blockIdx.x] = 0;
+    }
 #endif
 
     // ---- prologue.  Producer warp: barriers, then -- lane-parallel, one environment per lane -- positions, table
     // windows and the first ring pass of TMA loads (a window needs the position only), then the sensor frames.
     // Consumer warps: pattern + line tables, every global load issued before the first shared store.
     ProducerEnv cur, nxt;
+    int my_flat_z = 1;
     if (warp == 0) {
+        producer_load(cur, lane, n_iter, pos_w, quat_w);  // cold misses: in flight while the barriers are set up
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
             for (int s = 0; s < kPairFullBars; ++s) bar_init(&sm.full_bar[s], 2);  // TMA bytes + header published
@@ -342,7 +372,6 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        producer_load(cur, lane, n_iter, pos_w, quat_w);
         producer_window(cur, pc, pattern_radius);
         if (lane < n_iter && lane < kPairStages && ROVER_SCAN_DBG != 4) {
             // the box is always kPairPitch x kPairWin cells; cells beyond the table are zero-filled and never read;
@@ -358,11 +387,18 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
         constexpr int kPatLoads = (3 * kPairMaxRays + kFill - 1) / kFill;
         constexpr int kLineLoads = (kPairMaxLines + kFill - 1) / kFill;
         const int ct = threadIdx.x - 32;
+        static_assert(offsetof(PairSmem, vy) == offsetof(PairSmem, vx) + 4 * kPairMaxRays &&
+                          offsetof(PairSmem, vz) == offsetof(PairSmem, vx) + 8 * kPairMaxRays,
+                      "vx, vy, vz are filled as one array");
+        float* pat_flat = sm.vx;
         float pat[kPatLoads], xl[kLineLoads], xh[kLineLoads], yl[kLineLoads], yh[kLineLoads];
 #pragma unroll
-        for (int k = 0; k < kPatLoads; ++k) {
+        const float vz0 = __ldg(ray_local + 2);
+        for (int k = 0; k < kPatLoads; ++k) {  // i = component * kPairMaxRays + slot (vx, vy, vz are contiguous)
             const int i = ct + k * kFill;
-            pat[k] = (i < 3 * n_rays) ? __ldg(ray_local + i) : 0.f;
+            const int comp = i / kPairMaxRays, r = ray_of_slot(i - comp * kPairMaxRays);
+            pat[k] = (i < 3 * kPairMaxRays && r < n_rays) ? __ldg(ray_local + 3 * r + comp) : 0.f;
+            if (comp == 2 && r < n_rays && pat[k] != vz0) my_flat_z = 0;
         }
 #pragma unroll
         for (int k = 0; k < kLineLoads; ++k) {
@@ -376,12 +412,8 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
 #pragma unroll
         for (int k = 0; k < kPatLoads; ++k) {
             const int i = ct + k * kFill;
-            if (i < 3 * n_rays) {
-                const int r = i / 3, comp = i - 3 * r;
-                (comp == 0 ? sm.vx : comp == 1 ? sm.vy : sm.vz)[r] = pat[k];
-            }
+            if (i < 3 * kPairMaxRays) pat_flat[i] = pat[k];
         }
-        if (ct == 0 && (n_rays & 1) && n_rays < kPairMaxRays) sm.vx[n_rays] = sm.vy[n_rays] = sm.vz[n_rays] = 0.f;
 #pragma unroll
         for (int k = 0; k < kLineLoads; ++k) {
             const int i = ct + k * kFill;
@@ -390,7 +422,7 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
         }
     }
     if (warp == 1) DBG_STAMP(3);
-    __syncthreads();
+    const bool flat_z = __syncthreads_and(my_flat_z) != 0;  // also publishes the tables / barriers to every warp
     if (warp == 0) DBG_STAMP(0);
 
     if (warp == 0) {
@@ -467,27 +499,33 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
                 cx.MAGIC = dup(kFloorMagic), cx.BASE = dup(base_offset);
                 cx.NEG0 = dup(__uint_as_float(0x80000000u | (unsigned)(n_envs >> 31)));  // -0.0, opaque to the compiler
                 cx.pz = h.pz, cx.max_d = max_d;
-                cx.bx_hi = kFloorMagicBits + h.ncols - 1, cx.by_hi = kFloorMagicBits + h.nrows - 1;
-                const uint32_t bias = (uint32_t)kFloorMagicBits;
-                cx.xoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.xpair + h.ic0) - smem_raw) - bias * 8u;
-                cx.yoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.ypair + h.jr0) - smem_raw) - bias * 8u;
-                cx.eoff = (uint32_t)(reinterpret_cast<const unsigned char*>(st.p) - smem_raw) -
-                          bias * (uint32_t)(kPairPitch * 16) - bias * 16u;
+                cx.ZFLAT = dup(__fadd_rn(sm.vz[0], h.pz));
+                cx.cmax = (uint32_t)(h.ncols - 1), cx.rmax = (uint32_t)(h.nrows - 1);
+                cx.xoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.xpair + h.ic0) - smem_raw);
+                cx.yoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.ypair + h.jr0) - smem_raw);
+                cx.eoff = (uint32_t)(reinterpret_cast<const unsigned char*>(st.p) - smem_raw);
                 for (int b0 = r_begin; b0 < r_end; b0 += kPairChunk / 2) {
-                    const int r = b0 + 2 * lane;
+                    const int r = b0 + lane;  // rays r, r + 64 (slot 0) and r + 32, r + 96 (slot 1)
                     float* __restrict__ o = out_row + r;
-                    unsigned defer = resolve_pair(smem_raw, sm, cx, r, n_rays, o);
-                    defer |= resolve_pair(smem_raw, sm, cx, r + 64, n_rays, o + 64) << 2;
+                    unsigned defer;
+                    if (flat_z && b0 + kPairChunk / 2 <= n_rays) {
+                        defer = resolve_pair<true, true>(smem_raw, sm, cx, b0 + 2 * lane, r, n_rays, o);
+                        defer |= resolve_pair<true, true>(smem_raw, sm, cx, b0 + 64 + 2 * lane, r + 32, n_rays, o + 32) << 2;
+                    } else {
+                        defer = resolve_pair<false, false>(smem_raw, sm, cx, b0 + 2 * lane, r, n_rays, o);
+                        defer |= resolve_pair<false, false>(smem_raw, sm, cx, b0 + 64 + 2 * lane, r + 32, n_rays, o + 32) << 2;
+                    }
                     // rare: cell guess off by one, ray on the closed far border or outside the grid, general cell
                     if (defer != 0u) {
                         for (int u = 0; u < 4; ++u) {
                             if (!((defer >> u) & 1u)) continue;
-                            const int rr = r + (u >> 1) * 64 + (u & 1);
-                            const float vx = sm.vx[rr], vy = sm.vy[rr];
+                            const int rr = r + (u >> 1) * 32 + (u & 1) * 64;
+                            const int sl = b0 + (u >> 1) * 64 + 2 * lane + (u & 1);
+                            const float vx = sm.vx[sl], vy = sm.vy[sl];
                             const float tx = -__fmul_rn(sz2, vy), ty = __fmul_rn(sz2, vx);
                             const float X = __fadd_rn(__fadd_rn(__fadd_rn(vx, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
                             const float Y = __fadd_rn(__fadd_rn(__fadd_rn(vy, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
-                            pair_resolve_deferred_ray(&sm, &st, g, pc.inv_dx, pc.inv_dy, X, Y, __fadd_rn(sm.vz[rr], h.pz),
+                            pair_resolve_deferred_ray(&sm, &st, g, pc.inv_dx, pc.inv_dy, X, Y, __fadd_rn(sm.vz[sl], h.pz),
                                                       h.pz, max_d, base_offset, out_row + rr);
                         }
                     }
@@ -506,6 +544,9 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
             }
         }
     }
+#if ROVER_SCAN_DBG == 3
+    if (lane == 0 && blockIdx.x < 256) atomicMax(&g_scan_cta[1][blockIdx.x], dbg_globaltimer());
+#endif
 }
 
 int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local,
@@ -551,5 +592,8 @@ int launch_height_scan_paired(const float* pos_w, const float* quat_w, int n_env
 #if ROVER_SCAN_DBG == 3
 extern "C" int rover_debug_scan_timeline(unsigned long long* host_dst) {
     return (int)cudaMemcpyFromSymbol(host_dst, rover::g_scan_dbg, sizeof(rover::g_scan_dbg));
+}
+extern "C" int rover_debug_scan_ctas(unsigned long long* host_dst) {
+    return (int)cudaMemcpyFromSymbol(host_dst, rover::g_scan_cta, sizeof(rover::g_scan_cta));
 }
 #endif

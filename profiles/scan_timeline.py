@@ -38,3 +38,11 @@ for b in range(2):
         waits = sum(r[1] - r[0] for r in rows)
         work = sum(r[2] - r[1] for r in rows)
         print(f"   total wait {waits} cycles, total work {work} cycles, chunks {len(rows)}")
+cta = np.zeros((2, 256), dtype=np.uint64)
+assert lib.rover_debug_scan_ctas(cta.ctypes.data_as(C.c_void_p)) == 0
+st, en = cta[0, :148].astype(np.int64), cta[1, :148].astype(np.int64)
+t0 = st.min()
+print(f"CTA starts (ns after first): max {int((st - t0).max())}; CTA ends: min {int((en - t0).min())} median {int(np.median(en - t0))} max {int((en - t0).max())}")
+dur = en - st
+order = np.argsort(dur)
+print("CTA durations ns: min", int(dur.min()), "median", int(np.median(dur)), "max", int(dur.max()), "slowest CTAs", order[-6:].tolist(), "fastest", order[:4].tolist())
