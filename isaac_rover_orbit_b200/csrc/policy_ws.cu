@@ -1,0 +1,375 @@
+// Gaussian policy forward, warp-specialised (v2): the observation stream of tile i+1 overlaps layers 1-5 of tile i.
+//
+// Why (ncu on v1, profiles/r01_policy_v1_tcgen05.md): v1 runs one 128-env tile at a time per SM with every phase
+// behind a CTA-wide barrier -- issue slots 15 % busy, tensor pipe 8 %, HBM idle during layers 1-5; 130 us at cfg-4
+// where the 254 MB of fp32 observations alone take 39 us at the measured HBM rate.
+//
+// Roles (one persistent CTA per SM, 10 warps, all 512 TMEM columns):
+//   warp 8      TMA producer: obs chunks (128 envs x 32 columns fp32, SWIZZLE_128B) into a 5-stage ring + the matching
+//               5 KB slice of W0 into a 3-stage ring, running ahead across tiles.
+//   warps 4-7   converters: fp32 stage -> bf16 A operand (K-major core-matrix layout), 2-stage ring.
+//   warp 9      layer-0 MMA issuer: 2 tcgen05.mma per chunk into D0[tile parity] (two 80-column accumulators);
+//               tcgen05.commit frees the A / W0 stages and, after the last chunk, publishes D0.
+//   warps 0-3   layer group: epilogue of layer l (tcgen05.ld -> +bias -> LeakyReLU -> bf16) writes the A operand of
+//               layer l+1; its thread 0 streams W1..W5 (bulk copies into one 40 KB buffer; W3 in two K halves) and
+//               issues the MMAs of layers 1-5 into one 256-column accumulator.
+// Same arithmetic as v1 (bf16 operands, fp32 accumulation, same K order inside a layer), so the means are identical.
+#include "policy_common.cuh"
+
+namespace rover {
+
+constexpr int kWsThreads = 320;
+constexpr int kWsChunkK = 32;
+constexpr int kWsChunks = 31;  // observation columns [0, 992) cover the encoder input [3, 964)
+constexpr int kWsStagesF = 5;
+constexpr int kWsStagesA = 2;
+constexpr int kWsStagesW = 3;
+constexpr int kWsPlane = kTileM * 16;              // bytes between K-adjacent core matrices (A operands)
+constexpr int kWsW0Chunk = (kWsChunkK / 8) * 80 * 16;  // 5,120 B of the packed W0 image per chunk
+constexpr int kWsWBuf = 40 * 1024;                 // largest single weight load: W4, or one K half of W3
+constexpr uint32_t kWsColD0 = 0, kWsColD0Stride = 128, kWsColAcc = 256;
+
+static_assert(weight_bytes(1) <= kWsWBuf && weight_bytes(2) <= kWsWBuf && weight_bytes(3) == 2 * kWsWBuf &&
+                  weight_bytes(4) <= kWsWBuf && weight_bytes(5) <= kWsWBuf,
+              "weight buffer plan");
+static_assert(kW0ChunkBytes == 2 * kWsW0Chunk, "a 32-column chunk is half of a packed 64-column chunk");
+
+struct WsSmem {
+    float stage_f[kWsStagesF][kTileM * kWsChunkK];        // 5 x 16 KB, TMA destinations (1024-byte aligned)
+    unsigned char a_bf16[kWsStagesA][4 * kWsPlane];       // 2 x 8 KB
+    unsigned char w0[kWsStagesW][kWsW0Chunk];             // 3 x 5 KB
+    unsigned char act[32 * kWsPlane];                     // A operand of layers 1..5 (K <= 256): 64 KB
+    unsigned char w[kWsWBuf];                             // weights of the current layer
+    float bias[80 + 64 + 256 + 160 + 128 + 16];
+    unsigned long long f_full[kWsStagesF], f_empty[kWsStagesF];
+    unsigned long long a_full[kWsStagesA], a_empty[kWsStagesA];
+    unsigned long long w0_full[kWsStagesW], w0_empty[kWsStagesW];
+    unsigned long long d0_full[2], d0_empty[2];
+    unsigned long long w_full, acc_done;
+    uint32_t tmem_base;
+};
+static_assert(sizeof(WsSmem) + 1024 <= 227 * 1024, "WsSmem exceeds the shared memory of one SM");
+
+__device__ __forceinline__ void mb_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(b)) : "memory");
+}
+__device__ __forceinline__ void layer_group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// Epilogue of one layer for one tile row: D[row, 0:n_cols] -> +bias -> LeakyReLU -> bf16 -> A planes of the next layer.
+// inject != nullptr: columns 60..63 are replaced by inject[0..3] (layer 2 consumes [e(60), obs[:, 0:4]]).
+__device__ __forceinline__ void epilogue_to_act(uint32_t taddr, int n_cols, const float* __restrict__ bias,
+                                                unsigned char* __restrict__ act, int row, const float* inject) {
+    for (int n0 = 0; n0 < n_cols; n0 += 32) {
+        uint32_t raw[2][16];
+        const bool two = n0 + 16 < n_cols;
+        tmem_ld16_nowait(taddr + n0, raw[0]);
+        if (two) tmem_ld16_nowait(taddr + n0 + 16, raw[1]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (q == 1 && !two) break;
+            const int nq = n0 + 16 * q;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = leaky(__uint_as_float(raw[q][j]) + bias[nq + j]);
+            if (inject != nullptr && nq == 48) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[12 + j] = inject[j];
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint4 o;
+                o.x = pack_bf16(v[8 * h + 0], v[8 * h + 1]);
+                o.y = pack_bf16(v[8 * h + 2], v[8 * h + 3]);
+                o.z = pack_bf16(v[8 * h + 4], v[8 * h + 5]);
+                o.w = pack_bf16(v[8 * h + 6], v[8 * h + 7]);
+                *reinterpret_cast<uint4*>(act + ((nq >> 3) + h) * kWsPlane + row * 16) = o;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kWsThreads, 1)
+policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const float* __restrict__ obs, int obs_stride,
+                         int n_envs, const unsigned char* __restrict__ packed, float* __restrict__ mean) {
+    extern __shared__ unsigned char smem_dyn[];
+    WsSmem& sm = *reinterpret_cast<WsSmem*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = (n_envs + kTileM - 1) / kTileM;
+
+    if (tid == 0) {
+        for (int i = 0; i < kWsStagesF; ++i) {
+            mb_init(&sm.f_full[i], 1);
+            mb_init(&sm.f_empty[i], 4);  // one arrival per converter warp
+        }
+        for (int i = 0; i < kWsStagesA; ++i) {
+            mb_init(&sm.a_full[i], 4);
+            mb_init(&sm.a_empty[i], 1);  // tcgen05.commit
+        }
+        for (int i = 0; i < kWsStagesW; ++i) {
+            mb_init(&sm.w0_full[i], 1);
+            mb_init(&sm.w0_empty[i], 1);  // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mb_init(&sm.d0_full[i], 1);   // tcgen05.commit
+            mb_init(&sm.d0_empty[i], 1);  // thread 0 of the layer group
+        }
+        mb_init(&sm.w_full, 1);
+        mb_init(&sm.acc_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < (kPackedBytes - kBiasOffset) / 4; i += kWsThreads)
+        sm.bias[i] = __ldg(reinterpret_cast<const float*>(packed + kBiasOffset) + i);
+    if (warp == 0) {  // one warp allocates all 512 TMEM columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sptr(&sm.tmem_base)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 8) {
+        // =============================================================== TMA producer
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&obs_map)) : "memory");
+            int sf = 0, sw = 0;
+            uint32_t pf = 0, pw = 0;  // completed passes over the rings (parity)
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int row0 = tile * kTileM;
+                for (int c = 0; c < kWsChunks; ++c) {
+                    mb_wait(&sm.f_empty[sf], (pf & 1u) ^ 1u);
+                    mb_expect_tx(&sm.f_full[sf], kTileM * kWsChunkK * 4);
+                    tma_2d(sm.stage_f[sf], &obs_map, c * kWsChunkK, row0, &sm.f_full[sf]);
+                    mb_wait(&sm.w0_empty[sw], (pw & 1u) ^ 1u);
+                    mb_expect_tx(&sm.w0_full[sw], kWsW0Chunk);
+                    bulk_g2s(sm.w0[sw], packed + (size_t)c * kWsW0Chunk, kWsW0Chunk, &sm.w0_full[sw]);
+                    if (++sf == kWsStagesF) sf = 0, ++pf;
+                    if (++sw == kWsStagesW) sw = 0, ++pw;
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // =============================================================== layer-0 MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc0 = make_idesc(layer_n(0));
+            int sa = 0, sw = 0, i = 0;
+            uint32_t pa = 0, pw = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+                const int buf = i & 1;
+                mb_wait(&sm.d0_empty[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);  // the layer group has drained D0[buf]
+                tc_fence_after();
+                const uint32_t d0 = tmem + kWsColD0 + buf * kWsColD0Stride;
+                for (int c = 0; c < kWsChunks; ++c) {
+                    mb_wait(&sm.a_full[sa], pa & 1u);
+                    mb_wait(&sm.w0_full[sw], pw & 1u);
+                    tc_fence_after();
+                    const uint32_t a0 = sptr(sm.a_bf16[sa]), b0 = sptr(sm.w0[sw]);
+#pragma unroll
+                    for (int j = 0; j < kWsChunkK / 16; ++j)
+                        umma(d0, make_desc(a0 + j * 2 * kWsPlane, kWsPlane), make_desc(b0 + j * 2 * 80 * 16, 80 * 16), idesc0,
+                             (c | j) != 0);
+                    umma_commit(&sm.a_empty[sa]);   // A stage and W0 stage are free once these MMAs retire
+                    umma_commit(&sm.w0_empty[sw]);
+                    if (++sa == kWsStagesA) sa = 0, ++pa;
+                    if (++sw == kWsStagesW) sw = 0, ++pw;
+                }
+                umma_commit(&sm.d0_full[buf]);
+            }
+        }
+    } else if (warp >= 4) {
+        // =============================================================== converters: fp32 stage -> bf16 A operand
+        const int row = tid - 128;  // tile row
+        const int sx = row & 7;     // SWIZZLE_128B: 16-byte unit u of row r sits at unit u ^ (r & 7)
+        int sf = 0, sa = 0;
+        uint32_t pf = 0, pa = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int c = 0; c < kWsChunks; ++c) {
+                mb_wait(&sm.f_full[sf], pf & 1u);
+                mb_wait(&sm.a_empty[sa], (pa & 1u) ^ 1u);
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(sm.stage_f[sf]) + row * (kWsChunkK * 4);
+                unsigned char* dst = sm.a_bf16[sa] + row * 16;
+#pragma unroll
+                for (int plane = 0; plane < kWsChunkK / 8; ++plane) {
+                    const float4 lo = *reinterpret_cast<const float4*>(src + (((2 * plane) ^ sx) << 4));
+                    const float4 hi = *reinterpret_cast<const float4*>(src + (((2 * plane + 1) ^ sx) << 4));
+                    float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                    if (c == 0 || c == kWsChunks - 1) {  // encoder input = observation columns [3, 964) (models.py:95)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int col = c * kWsChunkK + plane * 8 + j;
+                            if (col < kEncInOffset || col >= kEncInOffset + kEncIn) v[j] = 0.f;
+                        }
+                    }
+                    uint4 o;
+                    o.x = pack_bf16(v[0], v[1]);
+                    o.y = pack_bf16(v[2], v[3]);
+                    o.z = pack_bf16(v[4], v[5]);
+                    o.w = pack_bf16(v[6], v[7]);
+                    *reinterpret_cast<uint4*>(dst + plane * kWsPlane) = o;
+                }
+                fence_async_smem();  // the bf16 stage is read by the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    mb_arrive(&sm.a_full[sa]);
+                    mb_arrive(&sm.f_empty[sf]);
+                }
+                if (++sf == kWsStagesF) sf = 0, ++pf;
+                if (++sa == kWsStagesA) sa = 0, ++pa;
+            }
+        }
+    } else {
+        // =============================================================== layer group (warps 0-3): layers 1..5
+        const int row = tid;  // TMEM lane == tile row; warp w may touch lanes 32w .. 32w+31
+        const uint32_t t_lane = (uint32_t)(warp * 32) << 16;
+        const uint32_t acc = tmem + kWsColAcc;
+        const uint32_t a0 = sptr(sm.act), b0 = sptr(sm.w);
+        uint32_t ph_w = 0, ph_acc = 0;
+        // weights of layer l (or one K half of layer 3) into the single weight buffer; only thread 0 calls these
+        auto load_w = [&](int byte_offset, int bytes) {
+            mb_expect_tx(&sm.w_full, (uint32_t)bytes);
+            bulk_g2s(sm.w, packed + byte_offset, (uint32_t)bytes, &sm.w_full);
+        };
+        // D[128 x nn] (+)= A[planes plane0 ..] x W^T, k_steps MMAs of K = 16; then commit to acc_done
+        auto issue_mma = [&](int plane0, int k_steps, int nn, bool accumulate) {
+            tc_fence_after();
+            mb_wait(&sm.w_full, ph_w);
+            const uint32_t idesc = make_idesc(nn);
+            for (int j = 0; j < k_steps; ++j)
+                umma(acc, make_desc(a0 + (plane0 + 2 * j) * kWsPlane, kWsPlane), make_desc(b0 + j * 2 * nn * 16, nn * 16), idesc,
+                     accumulate || j != 0);
+            umma_commit(&sm.acc_done);
+        };
+        auto wait_acc = [&]() {
+            mb_wait(&sm.acc_done, ph_acc);
+            ph_acc ^= 1u;
+            tc_fence_after();
+        };
+        auto publish_act = [&]() {  // this thread's A-operand stores are visible to the tensor core; TMEM reads done
+            tc_fence_before();
+            fence_async_smem();
+            layer_group_sync();
+        };
+        if (tid == 0) load_w(weight_offset(1), weight_bytes(1));
+        int i = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+            const int buf = i & 1;
+            const int grow = tile * kTileM + row;
+            float inject[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) inject[j] = grow < n_envs ? __ldg(obs + (size_t)grow * obs_stride + j) : 0.f;
+            // ---- layer 0 epilogue: D0[buf] -> A1 (80 columns)
+            mb_wait(&sm.d0_full[buf], ((uint32_t)i >> 1) & 1u);
+            tc_fence_after();
+            epilogue_to_act(tmem + t_lane + kWsColD0 + buf * kWsColD0Stride, layer_n(0), sm.bias, sm.act, row, nullptr);
+            publish_act();
+            if (tid == 0) {
+                mb_arrive(&sm.d0_empty[buf]);  // the layer-0 issuer may start tile i+2 into D0[buf]
+                issue_mma(0, layer_k(1) / 16, layer_n(1), false);
+            }
+            ph_w ^= 1u;
+            wait_acc();
+            if (tid == 0) load_w(weight_offset(2), weight_bytes(2));
+            // ---- layer 1 epilogue -> A2 = [e(60), obs[:, 0:4]]
+            epilogue_to_act(acc + t_lane, layer_n(1), sm.bias + (bias_offset(1) - kBiasOffset) / 4, sm.act, row, inject);
+            publish_act();
+            if (tid == 0) issue_mma(0, layer_k(2) / 16, layer_n(2), false);
+            ph_w ^= 1u;
+            wait_acc();
+            if (tid == 0) load_w(weight_offset(3), kWsWBuf);  // W3, K planes 0..15
+            // ---- layer 2 epilogue -> A3 (256 columns); layer 3 in two K halves through the 40 KB weight buffer
+            epilogue_to_act(acc + t_lane, layer_n(2), sm.bias + (bias_offset(2) - kBiasOffset) / 4, sm.act, row, nullptr);
+            publish_act();
+            if (tid == 0) issue_mma(0, 8, layer_n(3), false);
+            ph_w ^= 1u;
+            wait_acc();
+            if (tid == 0) {
+                load_w(weight_offset(3) + kWsWBuf, kWsWBuf);  // W3, K planes 16..31
+                issue_mma(16, 8, layer_n(3), true);
+            }
+            ph_w ^= 1u;
+            wait_acc();
+            if (tid == 0) load_w(weight_offset(4), weight_bytes(4));
+            // ---- layer 3 epilogue -> A4
+            epilogue_to_act(acc + t_lane, layer_n(3), sm.bias + (bias_offset(3) - kBiasOffset) / 4, sm.act, row, nullptr);
+            publish_act();
+            if (tid == 0) issue_mma(0, layer_k(4) / 16, layer_n(4), false);
+            ph_w ^= 1u;
+            wait_acc();
+            if (tid == 0) load_w(weight_offset(5), weight_bytes(5));
+            // ---- layer 4 epilogue -> A5
+            epilogue_to_act(acc + t_lane, layer_n(4), sm.bias + (bias_offset(4) - kBiasOffset) / 4, sm.act, row, nullptr);
+            publish_act();
+            if (tid == 0) issue_mma(0, layer_k(5) / 16, layer_n(5), false);
+            ph_w ^= 1u;
+            wait_acc();
+            if (tid == 0 && tile + (int)gridDim.x < n_tiles) load_w(weight_offset(1), weight_bytes(1));  // next tile's W1
+            // ---- last layer: mean = tanh(D5 + b5), two real columns
+            {
+                float v[8];
+                tmem_ld8(acc + t_lane, v);
+                const float* b5 = sm.bias + (bias_offset(5) - kBiasOffset) / 4;
+                if (grow < n_envs) {
+                    float2 m;
+                    m.x = tanhf(v[0] + b5[0]);
+                    m.y = tanhf(v[1] + b5[1]);
+                    *reinterpret_cast<float2*>(mean + 2 * (size_t)grow) = m;
+                }
+            }
+            tc_fence_before();
+            layer_group_sync();  // every TMEM read of this tile is done before the next tile's layer-1 MMA overwrites acc
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+typedef CUresult (*WsEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int launch_policy_forward_ws(const float* obs, int obs_stride, int n_envs, const void* packed, float* mean,
+                             cudaStream_t stream) {
+    static WsEncodeTiledFn encode = nullptr;
+    static int n_sms = 0;
+    constexpr int kSmemBytes = (int)sizeof(WsSmem) + 1024;
+    if (!encode) {
+        int dev = 0;
+        ROVER_CUDA(cudaGetDevice(&dev));
+        ROVER_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+        ROVER_CUDA(cudaFuncSetAttribute(policy_forward_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        ROVER_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        ROVER_CHECK(fn && q == cudaDriverEntryPointSuccess, "rover_policy_forward: cuTensorMapEncodeTiled unavailable");
+        encode = reinterpret_cast<WsEncodeTiledFn>(fn);
+    }
+    alignas(64) CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)kObsCols, (cuuint64_t)n_envs};
+    const cuuint64_t gstride[1] = {(cuuint64_t)obs_stride * 4ull};
+    const cuuint32_t box[2] = {(cuuint32_t)kWsChunkK, (cuuint32_t)kTileM};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult rc = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(obs), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ROVER_CHECK(rc == CUDA_SUCCESS, "rover_policy_forward: cuTensorMapEncodeTiled failed (%d)", (int)rc);
+    const int n_tiles = (n_envs + kTileM - 1) / kTileM;
+    const int grid = n_tiles < n_sms ? n_tiles : n_sms;
+    policy_forward_ws_kernel<<<grid, kWsThreads, kSmemBytes, stream>>>(map, obs, obs_stride, n_envs,
+                                                                        static_cast<const unsigned char*>(packed), mean);
+    return check_launch("policy_forward_ws_kernel");
+}
+
+}  // namespace rover
