@@ -5,8 +5,10 @@
 // where the 254 MB of fp32 observations alone take 39 us at the measured HBM rate.
 //
 // Roles (one persistent CTA per SM, 10 warps, all 512 TMEM columns):
-//   warp 8      TMA producer: obs chunks (128 envs x 32 columns fp32, SWIZZLE_128B) into a 5-stage ring + the matching
-//               5 KB slice of W0 into a 3-stage ring, running ahead across tiles.
+//   warp 8      TMA producer: obs chunks (128 envs x 32 columns fp32, SWIZZLE_128B) into a 5-stage ring, running ahead
+//               across tiles (up to 80 KB of HBM reads in flight per SM).
+//   warp 10     W0 producer: the matching 5 KB slice of the packed W0 image into a 3-stage ring.  (A single producer
+//               thread serving both rings stalled the observation stream on the shallower W0 ring: 84 us.)
 //   warps 4-7   converters: fp32 stage -> bf16 A operand (K-major core-matrix layout), 2-stage ring.
 //   warp 9      layer-0 MMA issuer: 2 tcgen05.mma per chunk into D0[tile parity] (two 80-column accumulators);
 //               tcgen05.commit frees the A / W0 stages and, after the last chunk, publishes D0.
@@ -16,9 +18,25 @@
 // Same arithmetic as v1 (bf16 operands, fp32 accumulation, same K order inside a layer), so the means are identical.
 #include "policy_common.cuh"
 
+#ifndef ROVER_POLICY_DBG
+#define ROVER_POLICY_DBG 0  // 1: timeline of CTA 0 in SM cycles (bring-up builds only, profiles/policy_timeline.py)
+#endif
+
 namespace rover {
 
-constexpr int kWsThreads = 320;
+#if ROVER_POLICY_DBG
+__device__ long long g_pol_dbg[2048];
+#define PDBG(slot)                                                                     \
+    do {                                                                               \
+        if (blockIdx.x == 0 && (slot) < 2048) g_pol_dbg[slot] = clock64() - dbg_t0;    \
+    } while (0)
+#else
+#define PDBG(slot) \
+    do {           \
+    } while (0)
+#endif
+
+constexpr int kWsThreads = 352;
 constexpr int kWsChunkK = 32;
 constexpr int kWsChunks = 31;  // observation columns [0, 992) cover the encoder input [3, 964)
 constexpr int kWsStagesF = 5;
@@ -78,7 +96,15 @@ __device__ __forceinline__ void epilogue_to_act(uint32_t taddr, int n_cols, cons
             const int nq = n0 + 16 * q;
             float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = leaky(__uint_as_float(raw[q][j]) + bias[nq + j]);
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b = *reinterpret_cast<const float4*>(bias + nq + 4 * j4);  // broadcast LDS.128
+                const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float x = __uint_as_float(raw[q][4 * j4 + j]) + bb[j];
+                    v[4 * j4 + j] = fmaxf(x, 0.01f * x);  // == x > 0 ? x : 0.01 x (LeakyReLU, slope 0.01), one op less
+                }
+            }
             if (inject != nullptr && nq == 48) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[12 + j] = inject[j];
@@ -98,17 +124,36 @@ __device__ __forceinline__ void epilogue_to_act(uint32_t taddr, int n_cols, cons
 
 __global__ void __launch_bounds__(kWsThreads, 1)
 policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const float* __restrict__ obs, int obs_stride,
-                         int n_envs, const unsigned char* __restrict__ packed, float* __restrict__ mean) {
+                         int n_envs, int tile_rows, const unsigned char* __restrict__ packed, float* __restrict__ mean) {
     extern __shared__ unsigned char smem_dyn[];
-    WsSmem& sm = *reinterpret_cast<WsSmem*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array, so that the compiler keeps
+    // the address space (an integer round-trip turns every access into a generic LD/ST)
+    WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_dyn + ((1024u - (sptr(smem_dyn) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_tiles = (n_envs + kTileM - 1) / kTileM;
+    // A tile holds tile_rows <= 128 environments (multiple of 8, chosen by the launcher so that the tiles fill whole
+    // rounds of the grid: 65536 envs on 148 SMs -> 586 tiles of 112 instead of 512 of 128 = 3.96 instead of 3.46 -> 4
+    // rounds).  The MMAs stay M = 128; accumulator rows >= tile_rows hold garbage and are never stored.
+    const int n_tiles = (n_envs + tile_rows - 1) / tile_rows;
+    const uint32_t chunk_bytes = (uint32_t)tile_rows * kWsChunkK * 4;
+#if ROVER_POLICY_DBG
+    const long long dbg_t0 = clock64();
+#endif
 
-    if (tid == 0) {
+    if (tid == 8 * 32) {
+        // the producer sets up its own ring and starts the first loads before the CTA-wide barrier below
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&obs_map)) : "memory");
         for (int i = 0; i < kWsStagesF; ++i) {
             mb_init(&sm.f_full[i], 1);
             mb_init(&sm.f_empty[i], 4);  // one arrival per converter warp
         }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((int)blockIdx.x < n_tiles)
+            for (int c = 0; c < kWsStagesF; ++c) {
+                mb_expect_tx(&sm.f_full[c], chunk_bytes);
+                tma_2d(sm.stage_f[c], &obs_map, c * kWsChunkK, blockIdx.x * tile_rows, &sm.f_full[c]);
+            }
+    }
+    if (tid == 0) {
         for (int i = 0; i < kWsStagesA; ++i) {
             mb_init(&sm.a_full[i], 4);
             mb_init(&sm.a_empty[i], 1);  // tcgen05.commit
@@ -125,8 +170,6 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
         mb_init(&sm.acc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < (kPackedBytes - kBiasOffset) / 4; i += kWsThreads)
-        sm.bias[i] = __ldg(reinterpret_cast<const float*>(packed + kBiasOffset) + i);
     if (warp == 0) {  // one warp allocates all 512 TMEM columns (one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sptr(&sm.tmem_base)), "r"(512u)
                      : "memory");
@@ -140,19 +183,35 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
     if (warp == 8) {
         // =============================================================== TMA producer
         if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&obs_map)) : "memory");
-            int sf = 0, sw = 0;
-            uint32_t pf = 0, pw = 0;  // completed passes over the rings (parity)
+            int sf = 0;
+            uint32_t pf = 0;  // completed passes over the ring (parity)
+            int dbg_g = 0;
+            bool first = true;  // chunks 0 .. kWsStagesF-1 of the first tile were issued in the prologue
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int row0 = tile * kTileM;
+                const int row0 = tile * tile_rows;
                 for (int c = 0; c < kWsChunks; ++c) {
-                    mb_wait(&sm.f_empty[sf], (pf & 1u) ^ 1u);
-                    mb_expect_tx(&sm.f_full[sf], kTileM * kWsChunkK * 4);
-                    tma_2d(sm.stage_f[sf], &obs_map, c * kWsChunkK, row0, &sm.f_full[sf]);
+                    if (!(first && c < kWsStagesF)) {
+                        mb_wait(&sm.f_empty[sf], (pf & 1u) ^ 1u);
+                        mb_expect_tx(&sm.f_full[sf], chunk_bytes);
+                        tma_2d(sm.stage_f[sf], &obs_map, c * kWsChunkK, row0, &sm.f_full[sf]);
+                    }
+                    if (dbg_g < 128) PDBG(dbg_g);
+                    ++dbg_g;
+                    if (++sf == kWsStagesF) sf = 0, ++pf;
+                }
+                first = false;
+            }
+        }
+    } else if (warp == 10) {
+        // =============================================================== W0 producer
+        if (lane == 0) {
+            int sw = 0;
+            uint32_t pw = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int c = 0; c < kWsChunks; ++c) {
                     mb_wait(&sm.w0_empty[sw], (pw & 1u) ^ 1u);
                     mb_expect_tx(&sm.w0_full[sw], kWsW0Chunk);
                     bulk_g2s(sm.w0[sw], packed + (size_t)c * kWsW0Chunk, kWsW0Chunk, &sm.w0_full[sw]);
-                    if (++sf == kWsStagesF) sf = 0, ++pf;
                     if (++sw == kWsStagesW) sw = 0, ++pw;
                 }
             }
@@ -163,6 +222,7 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
             const uint32_t idesc0 = make_idesc(layer_n(0));
             int sa = 0, sw = 0, i = 0;
             uint32_t pa = 0, pw = 0;
+            int dbg_g = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
                 const int buf = i & 1;
                 mb_wait(&sm.d0_empty[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);  // the layer group has drained D0[buf]
@@ -177,6 +237,8 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
                     for (int j = 0; j < kWsChunkK / 16; ++j)
                         umma(d0, make_desc(a0 + j * 2 * kWsPlane, kWsPlane), make_desc(b0 + j * 2 * 80 * 16, 80 * 16), idesc0,
                              (c | j) != 0);
+                    if (dbg_g < 128) PDBG(512 + dbg_g);
+                    ++dbg_g;
                     umma_commit(&sm.a_empty[sa]);   // A stage and W0 stage are free once these MMAs retire
                     umma_commit(&sm.w0_empty[sw]);
                     if (++sa == kWsStagesA) sa = 0, ++pa;
@@ -191,14 +253,18 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
         const int sx = row & 7;     // SWIZZLE_128B: 16-byte unit u of row r sits at unit u ^ (r & 7)
         int sf = 0, sa = 0;
         uint32_t pf = 0, pa = 0;
+        int dbg_g = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int c = 0; c < kWsChunks; ++c) {
                 mb_wait(&sm.f_full[sf], pf & 1u);
+                if (tid == 128 && dbg_g < 128) PDBG(128 + dbg_g);
                 mb_wait(&sm.a_empty[sa], (pa & 1u) ^ 1u);
+                if (tid == 128 && dbg_g < 128) PDBG(256 + dbg_g);
                 const unsigned char* src = reinterpret_cast<const unsigned char*>(sm.stage_f[sf]) + row * (kWsChunkK * 4);
                 unsigned char* dst = sm.a_bf16[sa] + row * 16;
 #pragma unroll
                 for (int plane = 0; plane < kWsChunkK / 8; ++plane) {
+                    if (row >= tile_rows) break;  // rows beyond the tile: never loaded, never stored
                     const float4 lo = *reinterpret_cast<const float4*>(src + (((2 * plane) ^ sx) << 4));
                     const float4 hi = *reinterpret_cast<const float4*>(src + (((2 * plane + 1) ^ sx) << 4));
                     float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
@@ -222,6 +288,8 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
                     mb_arrive(&sm.a_full[sa]);
                     mb_arrive(&sm.f_empty[sf]);
                 }
+                if (tid == 128 && dbg_g < 128) PDBG(384 + dbg_g);
+                ++dbg_g;
                 if (++sf == kWsStagesF) sf = 0, ++pf;
                 if (++sa == kWsStagesA) sa = 0, ++pa;
             }
@@ -259,16 +327,35 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
             layer_group_sync();
         };
         if (tid == 0) load_w(weight_offset(1), weight_bytes(1));
+        {   // biases: cold global loads that only this group needs (and only ~one tile-time from now), so they stay out
+            // of the CTA-wide prologue that the observation stream waits for
+            constexpr int kBiasFloats = (kPackedBytes - kBiasOffset) / 4;
+            float b[(kBiasFloats + 127) / 128];
+#pragma unroll
+            for (int k = 0; k < (kBiasFloats + 127) / 128; ++k)
+                b[k] = tid + 128 * k < kBiasFloats ? __ldg(reinterpret_cast<const float*>(packed + kBiasOffset) + tid + 128 * k) : 0.f;
+#pragma unroll
+            for (int k = 0; k < (kBiasFloats + 127) / 128; ++k)
+                if (tid + 128 * k < kBiasFloats) sm.bias[tid + 128 * k] = b[k];
+            layer_group_sync();
+        }
         int i = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
             const int buf = i & 1;
-            const int grow = tile * kTileM + row;
+            const int grow = tile * tile_rows + row;
+            const bool live = row < tile_rows && grow < n_envs;
             float inject[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) inject[j] = grow < n_envs ? __ldg(obs + (size_t)grow * obs_stride + j) : 0.f;
+            for (int j = 0; j < 4; ++j) inject[j] = live ? __ldg(obs + (size_t)grow * obs_stride + j) : 0.f;
             // ---- layer 0 epilogue: D0[buf] -> A1 (80 columns)
+#define LDBG(k)                                        \
+    do {                                               \
+        if (tid == 0 && i < 8) PDBG(1024 + 16 * i + (k)); \
+    } while (0)
+            LDBG(0);
             mb_wait(&sm.d0_full[buf], ((uint32_t)i >> 1) & 1u);
             tc_fence_after();
+            LDBG(1);
             epilogue_to_act(tmem + t_lane + kWsColD0 + buf * kWsColD0Stride, layer_n(0), sm.bias, sm.act, row, nullptr);
             publish_act();
             if (tid == 0) {
@@ -276,54 +363,66 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
                 issue_mma(0, layer_k(1) / 16, layer_n(1), false);
             }
             ph_w ^= 1u;
+            LDBG(2);
             wait_acc();
+            LDBG(3);
             if (tid == 0) load_w(weight_offset(2), weight_bytes(2));
             // ---- layer 1 epilogue -> A2 = [e(60), obs[:, 0:4]]
             epilogue_to_act(acc + t_lane, layer_n(1), sm.bias + (bias_offset(1) - kBiasOffset) / 4, sm.act, row, inject);
             publish_act();
             if (tid == 0) issue_mma(0, layer_k(2) / 16, layer_n(2), false);
             ph_w ^= 1u;
+            LDBG(4);
             wait_acc();
+            LDBG(5);
             if (tid == 0) load_w(weight_offset(3), kWsWBuf);  // W3, K planes 0..15
             // ---- layer 2 epilogue -> A3 (256 columns); layer 3 in two K halves through the 40 KB weight buffer
             epilogue_to_act(acc + t_lane, layer_n(2), sm.bias + (bias_offset(2) - kBiasOffset) / 4, sm.act, row, nullptr);
             publish_act();
             if (tid == 0) issue_mma(0, 8, layer_n(3), false);
             ph_w ^= 1u;
+            LDBG(6);
             wait_acc();
+            LDBG(7);
             if (tid == 0) {
                 load_w(weight_offset(3) + kWsWBuf, kWsWBuf);  // W3, K planes 16..31
                 issue_mma(16, 8, layer_n(3), true);
             }
             ph_w ^= 1u;
             wait_acc();
+            LDBG(8);
             if (tid == 0) load_w(weight_offset(4), weight_bytes(4));
             // ---- layer 3 epilogue -> A4
             epilogue_to_act(acc + t_lane, layer_n(3), sm.bias + (bias_offset(3) - kBiasOffset) / 4, sm.act, row, nullptr);
             publish_act();
             if (tid == 0) issue_mma(0, layer_k(4) / 16, layer_n(4), false);
             ph_w ^= 1u;
+            LDBG(9);
             wait_acc();
+            LDBG(10);
             if (tid == 0) load_w(weight_offset(5), weight_bytes(5));
             // ---- layer 4 epilogue -> A5
             epilogue_to_act(acc + t_lane, layer_n(4), sm.bias + (bias_offset(4) - kBiasOffset) / 4, sm.act, row, nullptr);
             publish_act();
             if (tid == 0) issue_mma(0, layer_k(5) / 16, layer_n(5), false);
             ph_w ^= 1u;
+            LDBG(11);
             wait_acc();
+            LDBG(12);
             if (tid == 0 && tile + (int)gridDim.x < n_tiles) load_w(weight_offset(1), weight_bytes(1));  // next tile's W1
             // ---- last layer: mean = tanh(D5 + b5), two real columns
             {
                 float v[8];
                 tmem_ld8(acc + t_lane, v);
                 const float* b5 = sm.bias + (bias_offset(5) - kBiasOffset) / 4;
-                if (grow < n_envs) {
+                if (live) {
                     float2 m;
                     m.x = tanhf(v[0] + b5[0]);
                     m.y = tanhf(v[1] + b5[1]);
                     *reinterpret_cast<float2*>(mean + 2 * (size_t)grow) = m;
                 }
             }
+            LDBG(13);
             tc_fence_before();
             layer_group_sync();  // every TMEM read of this tile is done before the next tile's layer-1 MMA overwrites acc
         }
@@ -359,17 +458,28 @@ int launch_policy_forward_ws(const float* obs, int obs_stride, int n_envs, const
     alignas(64) CUtensorMap map;
     const cuuint64_t gdim[2] = {(cuuint64_t)kObsCols, (cuuint64_t)n_envs};
     const cuuint64_t gstride[1] = {(cuuint64_t)obs_stride * 4ull};
-    const cuuint32_t box[2] = {(cuuint32_t)kWsChunkK, (cuuint32_t)kTileM};
+    // rows per tile: fill whole rounds of the grid (see the kernel); multiple of 8 (core-matrix rows), at most 128
+    const int rounds = (n_envs + kTileM * n_sms - 1) / (kTileM * n_sms);
+    int tile_rows = (n_envs + rounds * n_sms - 1) / (rounds * n_sms);
+    tile_rows = ((tile_rows + 7) / 8) * 8;
+    if (tile_rows > kTileM) tile_rows = kTileM;
+    const cuuint32_t box[2] = {(cuuint32_t)kWsChunkK, (cuuint32_t)tile_rows};
     const cuuint32_t estr[2] = {1u, 1u};
     const CUresult rc = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(obs), gdim, gstride, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ROVER_CHECK(rc == CUDA_SUCCESS, "rover_policy_forward: cuTensorMapEncodeTiled failed (%d)", (int)rc);
-    const int n_tiles = (n_envs + kTileM - 1) / kTileM;
+    const int n_tiles = (n_envs + tile_rows - 1) / tile_rows;
     const int grid = n_tiles < n_sms ? n_tiles : n_sms;
-    policy_forward_ws_kernel<<<grid, kWsThreads, kSmemBytes, stream>>>(map, obs, obs_stride, n_envs,
+    policy_forward_ws_kernel<<<grid, kWsThreads, kSmemBytes, stream>>>(map, obs, obs_stride, n_envs, tile_rows,
                                                                         static_cast<const unsigned char*>(packed), mean);
     return check_launch("policy_forward_ws_kernel");
 }
 
 }  // namespace rover
+
+#if ROVER_POLICY_DBG
+extern "C" int rover_debug_policy_timeline(long long* host_dst) {
+    return (int)cudaMemcpyFromSymbol(host_dst, rover::g_pol_dbg, sizeof(rover::g_pol_dbg));
+}
+#endif
