@@ -84,41 +84,43 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
 // inject != nullptr: columns 60..63 are replaced by inject[0..3] (layer 2 consumes [e(60), obs[:, 0:4]]).
 __device__ __forceinline__ void epilogue_to_act(uint32_t taddr, int n_cols, const float* __restrict__ bias,
                                                 unsigned char* __restrict__ act, int row, const float* inject) {
-    for (int n0 = 0; n0 < n_cols; n0 += 32) {
-        uint32_t raw[2][16];
-        const bool two = n0 + 16 < n_cols;
-        tmem_ld16_nowait(taddr + n0, raw[0]);
-        if (two) tmem_ld16_nowait(taddr + n0 + 16, raw[1]);
-        tmem_wait_ld();
+    // Software pipeline over batches of 16 columns: the tcgen05.ld of batch k+1 is in flight while batch k is converted.
+    // (The epilogues are bound by the TMEM read port, ~64 B/clk per SM: 128 rows x 256 columns take >= 2048 cycles, and
+    // a second group of four warps on the upper half of the columns did not shorten them -- measured.)
+    uint32_t raw[2][16];
+    tmem_ld16_nowait(taddr, raw[0]);
+    tmem_wait_ld();
+    const int n_batches = n_cols >> 4;
+#pragma unroll 2
+    for (int k = 0; k < n_batches; ++k) {
+        const int cur = k & 1;  // compile-time after the unroll by 2: raw[][] stays in registers
+        const int nq = 16 * k;
+        if (k + 1 < n_batches) tmem_ld16_nowait(taddr + nq + 16, raw[cur ^ 1]);
+        float v[16];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            if (q == 1 && !two) break;
-            const int nq = n0 + 16 * q;
-            float v[16];
+        for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + nq + 4 * j4);  // broadcast LDS.128
+            const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 b = *reinterpret_cast<const float4*>(bias + nq + 4 * j4);  // broadcast LDS.128
-                const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float x = __uint_as_float(raw[q][4 * j4 + j]) + bb[j];
-                    v[4 * j4 + j] = fmaxf(x, 0.01f * x);  // == x > 0 ? x : 0.01 x (LeakyReLU, slope 0.01), one op less
-                }
-            }
-            if (inject != nullptr && nq == 48) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[12 + j] = inject[j];
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint4 o;
-                o.x = pack_bf16(v[8 * h + 0], v[8 * h + 1]);
-                o.y = pack_bf16(v[8 * h + 2], v[8 * h + 3]);
-                o.z = pack_bf16(v[8 * h + 4], v[8 * h + 5]);
-                o.w = pack_bf16(v[8 * h + 6], v[8 * h + 7]);
-                *reinterpret_cast<uint4*>(act + ((nq >> 3) + h) * kWsPlane + row * 16) = o;
+            for (int j = 0; j < 4; ++j) {
+                const float x = __uint_as_float(raw[cur][4 * j4 + j]) + bb[j];
+                v[4 * j4 + j] = fmaxf(x, 0.01f * x);  // == x > 0 ? x : 0.01 x (LeakyReLU, slope 0.01), one op less
             }
         }
+        if (inject != nullptr && nq == 48) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[12 + j] = inject[j];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint4 o;
+            o.x = pack_bf16(v[8 * h + 0], v[8 * h + 1]);
+            o.y = pack_bf16(v[8 * h + 2], v[8 * h + 3]);
+            o.z = pack_bf16(v[8 * h + 4], v[8 * h + 5]);
+            o.w = pack_bf16(v[8 * h + 6], v[8 * h + 7]);
+            *reinterpret_cast<uint4*>(act + ((nq >> 3) + h) * kWsPlane + row * 16) = o;
+        }
+        tmem_wait_ld();  // batch k+1 has landed
     }
 }
 

@@ -75,6 +75,25 @@ def test_policy_forward_tiles_and_tails(cuda_device, golden, n):
     torch.testing.assert_close(mean.cpu(), emulate_bf16(obs, sd), rtol=0, atol=4e-3)
 
 
+@pytest.mark.parametrize("n", [1, 129, 3000, 18944 + 5, 40000])
+def test_policy_kernels_agree_bitwise(cuda_device, golden, n, monkeypatch):
+    """The warp-specialised kernel (default) and the tile-serial v1 (ROVER_POLICY_KERNEL=v1) run the same arithmetic in
+    the same order: identical means for every tiling (tile height varies with N: whole rounds of the grid)."""
+    _, sd = golden
+    net = GaussianNeuralNetwork(device=cuda_device)
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(100 + n)
+    obs = alloc_obs(n, cuda_device)
+    obs.copy_((torch.randn(n, 965, generator=g) * 0.4).to(cuda_device))
+    monkeypatch.setenv("ROVER_POLICY_KERNEL", "v1")
+    m1 = net.compute({"states": obs})[0].clone()
+    monkeypatch.setenv("ROVER_POLICY_KERNEL", "ws")
+    m2 = net.compute({"states": obs})[0].clone()
+    torch.cuda.synchronize()
+    assert torch.equal(m1, m2)
+    assert torch.isfinite(m2).all()
+
+
 def test_gaussian_act(cuda_device, golden):
     from oracle import policy as OP
 
