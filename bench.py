@@ -385,6 +385,8 @@ def run_ours(args):
             "tflops": n_pol * 319520 / t_pol / 1e12,
             "roofline_frac_tensor": n_pol * 319520 / t_pol / 1e12 / tf_peak, "tensor_peak_tflops": tf_peak,
             "roofline_frac_hbm": n_pol * (965 * 4 + 8) / t_pol / 1e9 / peak,
+            "kernel": "policy_forward_ws_kernel" if os.environ.get("ROVER_POLICY_KERNEL", "ws")[:2] != "v1"
+                      else "policy_forward_kernel",
             "note": "standalone forward reads 3860 B/env of fp32 observations: 83 FLOP/B < ridge, HBM-bound (SURVEY 8d)",
         }
     except Exception as e:
