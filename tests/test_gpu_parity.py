@@ -133,6 +133,68 @@ def test_height_scan_mixed_mesh_levels_and_degenerates(cuda_device, variant):
     _scan_compare(h, h_ref)
 
 
+def _heightfield_mesh(nx, ny, dx, dy, seed):
+    """Regular heightfield, two triangles per quad (same diagonal), vertices x-fastest."""
+    rng = np.random.default_rng(seed)
+    xs, ys = np.arange(nx + 1) * dx, np.arange(ny + 1) * dy
+    X, Y = np.meshgrid(xs, ys)
+    Z = 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y) + 0.05 * rng.standard_normal(X.shape)
+    v = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1).astype(np.float32)
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny))
+    a = (j * (nx + 1) + i).ravel()
+    f = np.concatenate([np.stack([a, a + 1, a + nx + 2], 1), np.stack([a, a + nx + 2, a + nx + 1], 1)]).astype(np.int32)
+    return v, f
+
+
+@pytest.mark.parametrize("shape", ["more lines than the shared tables hold", "cells so small that windows do not fit",
+                                   "narrow strip"])
+def test_height_scan_pipelined_variants_fallback_paths(cuda_device, shape):
+    """Variants 4 / 5 stage table windows in shared memory; tables whose grid lines do not fit the shared line tables,
+    whose windows exceed the staged 26 x 26 cells, or that are narrower than a window take the global-memory paths and
+    must return exactly what variant 2 returns."""
+    if shape.startswith("more lines"):
+        v, f = _heightfield_mesh(1100, 30, 0.2, 0.2, 1)     # 1100 > 1024 lines in x
+        lo, hi = (2.0, 2.0), (218.0, 4.0)
+    elif shape.startswith("cells so small"):
+        v, f = _heightfield_mesh(400, 400, 0.05, 0.05, 2)   # a 3 m pattern spans ~85 cells > 26
+        lo, hi = (1.0, 1.0), (19.0, 19.0)
+    else:
+        v, f = _heightfield_mesh(300, 9, 0.2, 0.2, 3)        # 9 rows: every window hangs over both borders in y
+        lo, hi = (-1.0, -1.0), (61.0, 3.0)
+    grid = ops.ScanGridHandle.from_mesh(v, f, cuda_device)
+    gen = torch.Generator().manual_seed(11)
+    n = 700
+    u = torch.rand(n, 2, generator=gen)
+    pos = torch.cat([u * (torch.tensor(hi) - torch.tensor(lo)) + torch.tensor(lo), torch.rand(n, 1, generator=gen) + 0.5], 1)
+    quat = synthetic.quat_from_euler(torch.zeros(n), torch.zeros(n), (torch.rand(n, generator=gen) * 2 - 1) * np.pi)
+    rays = ops.RayPattern.grid(cuda_device)
+    pos, quat = pos.to(cuda_device), quat.to(cuda_device)
+    ref = ops.height_scan(pos, quat, rays, grid, variant=2)
+    assert torch.isfinite(ref).any() and torch.isinf(ref).any()  # hits and misses (rays beyond the border) both occur
+    for variant in (3, 4, 5):
+        h = ops.height_scan(pos, quat, rays, grid, variant=variant)
+        assert torch.equal(h, ref), f"variant {variant} differs from variant 2 ({shape})"
+
+
+def test_height_scan_variant5_without_planar_table_runs_as_variant4(cuda_device):
+    """RoverPlaneCells.entries_planar is optional (ABI v2): a NULL pointer must not break variant 5."""
+    v, f = _heightfield_mesh(120, 120, 0.2, 0.2, 4)
+    grid = ops.ScanGridHandle.from_mesh(v, f, cuda_device)
+    gen = torch.Generator().manual_seed(12)
+    n = 200
+    pos = torch.cat([torch.rand(n, 2, generator=gen) * 20 + 2, torch.rand(n, 1, generator=gen) + 0.5], 1).to(cuda_device)
+    quat = synthetic.quat_from_euler(torch.zeros(n), torch.zeros(n), (torch.rand(n, generator=gen) * 2 - 1) * np.pi).to(cuda_device)
+    rays = ops.RayPattern.grid(cuda_device)
+    ref = ops.height_scan(pos, quat, rays, grid, variant=5)
+    saved = grid.cells_struct.entries_planar
+    grid.cells_struct.entries_planar = None
+    try:
+        h = ops.height_scan(pos, quat, rays, grid, variant=5)
+    finally:
+        grid.cells_struct.entries_planar = saved
+    assert torch.equal(h, ref)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_height_scan_max_distance_and_empty(cuda_device, variant):
     v = np.array([[-5, -5, -95.0], [5, -5, -95.0], [0, 5, -95.0]], dtype=np.float32)
