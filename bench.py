@@ -392,6 +392,39 @@ def run_ours(args):
     except Exception as e:
         extra["policy_forward"] = {"error": f"{type(e).__name__}: {e}"}
 
+    # ------------------------------------------------------------------ extra: closed non-physics loop with the policy
+    # obs -> policy -> action -> (stand-in physics) -> pre_step -> post_step -> height scan -> obs, one CUDA graph per step
+    try:
+        loop_obs = alloc_obs(n_step, dev)
+        act_buf = torch.zeros(n_step, 2, device=dev)
+        eps_sets = [torch.randn(n_step, 2, generator=gen3).to(dev) for _ in range(4)]
+
+        def closed_step(i):
+            s = sets[i % 4]
+            torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)  # stand-in for PhysX
+            ops.mdp_pre_step(buf, params, act_buf, s.force_matrix_w)
+            ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
+                              s.theta_u, loop_obs)
+            ops.height_scan(s.root_pos_w, s.root_quat_w, rays, grid, out=loop_obs[:, 4:], variant=args.variant)
+            actions, _, _ = net.act({"states": loop_obs}, eps=eps_sets[i % 4])
+            act_buf.copy_(actions)
+
+        g_loop = graphed(closed_step)
+        ksteps = max(min(args.steps, 200), 3)
+        ms_loop = time_steps(g_loop, ksteps, 3, flush, stream)
+        tl = torch.tensor([ms_loop.sum()], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        extra["closed_loop_step"] = {
+            "workload": f"{n_step} envs/GPU: pre_step + post_step + height scan + policy forward (tcgen05) + Gaussian act, "
+                        "actions fed back to the next step; physics replaced by a synthetic pose update",
+            "env_steps_per_s": n_step * world * ksteps / (float(tl[0]) * 1e-3),
+            "ms_per_step": float(tl[0]) / ksteps, "gpu_launches_per_step": 5, "cuda_graph": not args.no_graph,
+            "finite_actions": bool(torch.isfinite(act_buf).all().item()),
+        }
+    except Exception as e:
+        extra["closed_loop_step"] = {"error": f"{type(e).__name__}: {e}"}
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
