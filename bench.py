@@ -295,18 +295,9 @@ def run_ours(args):
         # the step is launch-bound on the host side (3 ctypes launches + 1 torch op ~ 40 us of Python per step):
         # capture each input set's step once in a CUDA graph and replay it (one cudaGraphLaunch per step)
         def graphed(fn):
-            if args.no_graph:
-                return fn
-            for i in range(4):
-                fn(i)  # warm-up outside capture (one-time attribute / driver-entry-point calls)
-            torch.cuda.synchronize()
-            graphs = []
-            for i in range(4):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    fn(i)
-                graphs.append(g)
-            return lambda i: graphs[i % 4].replay()
+            from isaac_rover_orbit_b200.trainer import capture_steps
+
+            return fn if args.no_graph else capture_steps(fn, n_variants=4, warmup=1)
 
         step_body = full_step
         if world > 1:

@@ -58,6 +58,10 @@ __device__ __forceinline__ unsigned long long dbg_globaltimer() {
 constexpr int kPairConsumerWarps = 14;  // 1 + 14 warps -> 16-warp register allocation -> 128 registers / thread
 constexpr int kPairThreads = 32 * (1 + kPairConsumerWarps);
 constexpr int kPairStages = 8;          // ring depth (data)
+#ifndef ROVER_PAIR_EARLY
+#define ROVER_PAIR_EARLY 8
+#endif
+constexpr int kPairEarly = ROVER_PAIR_EARLY;  // windows whose TMA load is issued in the prologue (<= kPairStages)
 constexpr int kPairFullBars = 16;       // `full` barriers: two per stage, see the note on phase aliasing below
 constexpr int kPairWin = 26;            // window cells per axis
 constexpr int kPairPitch = 27;          // cells per staged row: odd, so that consecutive rows shift by one 16-byte bank
@@ -373,7 +377,7 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
         }
         __syncwarp();
         producer_window(cur, pc, pattern_radius);
-        if (lane < n_iter && lane < kPairStages && ROVER_SCAN_DBG != 4) {
+        if (lane < n_iter && lane < kPairEarly && ROVER_SCAN_DBG != 4) {
             // the box is always kPairPitch x kPairWin cells; cells beyond the table are zero-filled and never read;
             // a window that later turns out not to fit / not to cover is loaded all the same and simply not used
             bar_arrive_expect_tx(&sm.full_bar[lane], kPairStageBytes);
@@ -445,7 +449,7 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
                     const int s = it % kPairStages;
                     unsigned long long* full = &sm.full_bar[it % kPairFullBars];
                     PairStage& st = sm.stage[s];
-                    const bool first_pass = it < kPairStages && ROVER_SCAN_DBG != 4;  // loaded in the prologue
+                    const bool first_pass = it < kPairEarly && ROVER_SCAN_DBG != 4;  // loaded in the prologue
                     if (!first_pass) {
                         bar_wait(&sm.empty_bar[s], ((uint32_t)(it / kPairStages) & 1u) ^ 1u);  // stage drained
                         if (cur.ok && ROVER_SCAN_DBG != 2) {

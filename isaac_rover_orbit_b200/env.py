@@ -251,7 +251,9 @@ class RoverEnv:
         self._reset_idx(ids)
         self._run_post(ids[:0], _lib.PHASE_METRICS | _lib.PHASE_COMMAND | _lib.PHASE_OBS, obs=self.obs_buf)
         self._scan()
-        return self.obs_buf, self.extras
+        # a private copy: ``step`` refreshes ``obs_buf`` in place, and the reference's trainer keeps the tensor it got
+        # from ``reset`` as its ``states`` buffer (``states.copy_(next_states)``, skrl_utils.py:148)
+        return self.obs_buf.clone(), self.extras
 
     def _reset_idx(self, idx):
         """rover_env.py:27-39 / ORBIT ``RLTaskEnv._reset_idx`` (A.2) for explicit ids."""

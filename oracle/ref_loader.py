@@ -168,6 +168,60 @@ def install_stubs() -> None:
     _mod("skrl.models.torch.gaussian", GaussianMixin=GaussianMixin)
     _mod("skrl.models.torch.deterministic", DeterministicMixin=DeterministicMixin)
 
+    # ---- skrl 1.1.0 trainer base (third-party, absent here): restated from the published 1.1.0 sources --
+    # skrl/trainers/torch/base.py (Trainer.__init__, single_agent_eval) and sequential.py (default config)
+    class Agent:
+        pass
+
+    class Wrapper:
+        pass
+
+    class Trainer:
+        def __init__(self, env, agents, agents_scope=None, cfg=None):
+            self.cfg = cfg if cfg is not None else {}
+            self.env = env
+            self.agents = agents
+            self.agents_scope = agents_scope if agents_scope is not None else []
+            self.timesteps = self.cfg.get("timesteps", 0)
+            self.headless = self.cfg.get("headless", False)
+            self.disable_progressbar = self.cfg.get("disable_progressbar", False)
+            self.close_environment_at_exit = self.cfg.get("close_environment_at_exit", True)
+            self.initial_timestep = 0
+            self.num_simultaneous_agents = len(agents) if isinstance(agents, (list, tuple)) else 1
+
+        def single_agent_eval(self):
+            states, infos = self.env.reset()
+            for timestep in range(self.initial_timestep, self.timesteps):
+                with torch.no_grad():
+                    actions = self.agents.act(states, timestep=timestep, timesteps=self.timesteps)[0]
+                next_states, rewards, terminated, truncated, infos = self.env.step(actions)
+                if not self.headless:
+                    self.env.render()
+                with torch.no_grad():
+                    super(type(self.agents), self.agents).record_transition(
+                        states=states, actions=actions, rewards=rewards, next_states=next_states,
+                        terminated=terminated, truncated=truncated, infos=infos, timestep=timestep,
+                        timesteps=self.timesteps)
+                if self.env.num_envs > 1:
+                    states = next_states
+                else:
+                    if terminated.any() or truncated.any():
+                        with torch.no_grad():
+                            states, infos = self.env.reset()
+                    else:
+                        states = next_states
+
+    _mod("skrl.agents")
+    _mod("skrl.agents.torch", Agent=Agent)
+    _mod("skrl.envs")
+    _mod("skrl.envs.wrappers")
+    _mod("skrl.envs.wrappers.torch", Wrapper=Wrapper, wrap_env=lambda env, wrapper=None: env)
+    _mod("skrl.trainers")
+    _mod("skrl.trainers.torch", Trainer=Trainer)
+    _mod("skrl.trainers.torch.sequential",
+         SEQUENTIAL_TRAINER_DEFAULT_CONFIG={"timesteps": 100000, "headless": False, "disable_progressbar": False,
+                                            "close_environment_at_exit": True})
+
     if "pymeshlab" not in sys.modules:
         _mod("pymeshlab")
     try:
@@ -198,6 +252,7 @@ _FILES = {
     "randomizations": ("rover_envs/envs/navigation/mdp/randomizations.py",
                        "rover_envs.envs.navigation.mdp.randomizations"),
     "models": ("rover_envs/envs/navigation/learning/skrl/models.py", "rover_envs.envs.navigation.learning.skrl.models"),
+    "skrl_utils": ("rover_envs/utils/skrl_utils.py", "rover_envs.utils.skrl_utils"),
 }
 
 

@@ -1,0 +1,67 @@
+"""GPU, SURVEY.md 8 (f-2): act -> step -> record through the trainer mirror on the real env and the tcgen05 policy."""
+import pytest
+import torch
+
+from isaac_rover_orbit_b200 import terrain as TR
+from isaac_rover_orbit_b200.config import RoverEnvCfg
+from isaac_rover_orbit_b200.env import RoverEnv
+from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork
+from isaac_rover_orbit_b200.trainer import RolloutAgent, RolloutMemory, SkrlSequentialLogTrainer, capture_steps
+
+pytestmark = pytest.mark.gpu
+
+
+def test_train_loop_records_the_rollout(cuda_device):
+    n, steps = 160, 6
+    v, f = TR.make_synthetic_terrain(48.0, 0.2, seed=5)
+    tables = TR.build_terrain_tables(v, f, n)
+    gen = torch.Generator().manual_seed(3)
+    drift = [(torch.rand(n, 3, generator=gen) * torch.tensor([3.0, 3.0, 0.0])).to(cuda_device) for _ in range(steps)]
+    seen = {"obs": [], "act": [], "rew": []}
+
+    def physics(env):  # stand-in for PhysX: the rover sits near its spawn point
+        k = env.common_step_counter % steps
+        pos = env.scene["robot"].data.root_pos_w
+        pos.copy_(env._buf.env_origins + drift[k])
+        pos[:, 2] = 0.3
+
+    env = RoverEnv(RoverEnvCfg(num_envs=n), tables, cuda_device, physics=physics, seed=2)
+    step0 = env.step
+
+    def spy_step(actions):
+        out = step0(actions)
+        seen["act"].append(actions.clone())
+        seen["obs"].append(out[0].clone())
+        seen["rew"].append(out[1].clone())
+        return out
+
+    env.step = spy_step
+    net = GaussianNeuralNetwork(device=cuda_device)
+    g2 = torch.Generator().manual_seed(4)
+    net.load_state_dict({k: torch.randn(t.shape, generator=g2) * (0.05 if t.dim() == 2 else 0.01)
+                         for k, t in net.state_dict().items()})
+    mem = RolloutMemory(memory_size=steps, num_envs=n, device=cuda_device)
+    agent = RolloutAgent(net, mem)
+    SkrlSequentialLogTrainer(env=env, agents=agent, cfg={"timesteps": steps, "disable_progressbar": True}).train()
+    torch.cuda.synchronize()
+    assert mem.filled and mem.memory_index == 0
+    st, ac = mem.get_tensor_by_name("states"), mem.get_tensor_by_name("actions")
+    for t in range(steps):
+        assert torch.equal(ac[t], seen["act"][t]), "the recorded action is the one the env stepped with"
+        assert torch.equal(mem.get_tensor_by_name("rewards")[t, :, 0], seen["rew"][t])
+        if t + 1 < steps:
+            assert torch.equal(st[t + 1], seen["obs"][t]), "states of step t+1 = observation returned by step t"
+    assert torch.isfinite(st[:, :, :4]).all() and (ac.abs() <= 1.0).all()
+    assert torch.isfinite(mem.get_tensor_by_name("log_prob")).all()
+    assert any(k.startswith("EpisodeInfo / ") for k in agent.tracking_data)
+
+
+def test_capture_steps_replays_the_enqueued_work(cuda_device):
+    acc = torch.zeros(4, device=cuda_device)
+    inc = [torch.full((4,), float(i + 1), device=cuda_device) for i in range(3)]
+    replay = capture_steps(lambda i: acc.add_(inc[i]), n_variants=3, warmup=1)
+    base = acc.clone()  # warm-up already added 1 + 2 + 3
+    for i in range(6):
+        replay(i)
+    torch.cuda.synchronize()
+    assert torch.equal(acc, base + 12.0)
