@@ -230,7 +230,7 @@ int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_t n_envs, c
 typedef struct RoverPolicyWeights {
     const float* w[6];   /* nn.Linear weights [out,in] fp32, order: enc0, enc2, mlp0, mlp2, mlp4, mlp6 */
     const float* b[6];   /* biases */
-    int32_t in_dim[6], out_dim[6];
+    int32_t in_dim[6], out_dim[6];  /* out_dim[5] = 2 (policy mean) or 1 (value) */
 } RoverPolicyWeights;
 
 /* returns the number of bytes the packed blob needs (when packed == NULL) or packs into it */
@@ -239,6 +239,11 @@ int64_t rover_policy_pack(const RoverPolicyWeights* weights /* host struct, devi
 /* obs [N, obs_stride] fp32 (965 columns used), rows 16-byte aligned (obs_stride % 4 == 0); mean [N,2] fp32 */
 int rover_policy_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed, float* mean,
                          void* stream);
+/* Value network forward.  Replaces DeterministicNeuralNetwork.compute (models.py:105-162; built by
+ * gaussian_model_skrl, configure_models.py:54-64): the same encoder + MLP as the policy with its own weights, one
+ * linear output, no tanh.  `packed` comes from rover_policy_pack with out_dim[5] == 1; value [N] fp32. */
+int rover_value_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed, float* value,
+                        void* stream);
 /* actions = clamp(mean + exp(clamp(log_std,-20,2)) * eps, -1, 1); log_prob [N] = sum_j log N(a_j) */
 int rover_gaussian_act(const float* mean, const float* log_std, const float* eps, int32_t n_envs, float* actions,
                        float* log_prob, void* stream);

@@ -48,7 +48,8 @@ struct __align__(128) PolSmem {
 // ---------------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(kPolThreads, 1)
 policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* __restrict__ obs, int obs_stride,
-                      int n_envs, const unsigned char* __restrict__ packed, float* __restrict__ mean, int debug_stop) {
+                      int n_envs, const unsigned char* __restrict__ packed, float* __restrict__ mean, int debug_stop,
+                      int value_head) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PolSmem& sm = *reinterpret_cast<PolSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -261,7 +262,9 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap obs_map, const float* 
                     float v[8];
                     tmem_ld8(tmem + t_lane + d_col, v);
                     const int grow = row0 + row;
-                    if (grow < n_envs) {
+                    if (grow < n_envs && value_head) {
+                        mean[grow] = v[0] + bias[0];  // DeterministicNeuralNetwork: one linear output, no tanh
+                    } else if (grow < n_envs) {
                         float2 m;
                         m.x = tanhf(v[0] + bias[0]);
                         m.y = tanhf(v[1] + bias[1]);
@@ -290,7 +293,7 @@ struct PackArgs {
 
 __global__ void policy_pack_kernel(const __grid_constant__ PackArgs a, unsigned char* __restrict__ packed) {
     const int l = blockIdx.y;
-    const int k_pad = layer_k(l), n_pad = layer_n(l), k_real = layer_k_real(l), n_real = layer_n_real(l);
+    const int k_pad = layer_k(l), n_pad = layer_n(l), k_real = layer_k_real(l), n_real = a.out_dim[l];
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(packed + weight_offset(l));
     const int total = (l == 0 ? kNumChunks * kChunkK : k_pad) * n_pad;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -334,8 +337,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int launch_policy_forward_ws(const float* obs, int obs_stride, int n_envs, const void* packed, float* mean,
-                             cudaStream_t stream);  // policy_ws.cu
+int launch_policy_forward_ws(const float* obs, int obs_stride, int n_envs, const void* packed, float* out,
+                             bool value_head, cudaStream_t stream);  // policy_ws.cu
 
 }  // namespace rover
 
@@ -348,8 +351,8 @@ extern "C" int64_t rover_policy_pack(const RoverPolicyWeights* weights, void* pa
     }
     PackArgs a;
     for (int l = 0; l < 6; ++l) {
-        if (!weights->w[l] || !weights->b[l] || weights->in_dim[l] < layer_k_real(l) ||
-            weights->out_dim[l] != layer_n_real(l)) {
+        const bool out_ok = weights->out_dim[l] == layer_n_real(l) || (l == 5 && weights->out_dim[l] == 1);  // value head
+        if (!weights->w[l] || !weights->b[l] || weights->in_dim[l] < layer_k_real(l) || !out_ok) {
             fail("rover_policy_pack: layer %d has shape [%d,%d], expected [%d,%d]", l, weights->out_dim[l],
                  weights->in_dim[l], layer_n_real(l), layer_k_real(l));
             return -1;
@@ -363,8 +366,8 @@ extern "C" int64_t rover_policy_pack(const RoverPolicyWeights* weights, void* pa
     return check_launch("policy_pack_kernel") ? -1 : kPackedBytes;
 }
 
-extern "C" int rover_policy_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed,
-                                    float* mean, void* stream) {
+static int policy_or_value_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed, float* mean,
+                                   void* stream, bool value_head) {
     using namespace rover;
     ROVER_CHECK(n_envs >= 0, "rover_policy_forward: negative n_envs");
     if (n_envs == 0) return 0;
@@ -376,7 +379,8 @@ extern "C" int rover_policy_forward(const float* obs, int32_t obs_stride, int32_
     {   // default: the warp-specialised kernel (policy_ws.cu); ROVER_POLICY_KERNEL=v1 selects the tile-serial one
         const char* which = getenv("ROVER_POLICY_KERNEL");
         if (which == nullptr || which[0] != 'v' || which[1] != '1')
-            return launch_policy_forward_ws(obs, obs_stride, n_envs, packed, mean, static_cast<cudaStream_t>(stream));
+            return launch_policy_forward_ws(obs, obs_stride, n_envs, packed, mean, value_head,
+                                            static_cast<cudaStream_t>(stream));
     }
     static EncodeTiledFn encode = nullptr;
     static int n_sms = 0;
@@ -405,8 +409,19 @@ extern "C" int rover_policy_forward(const float* obs, int32_t obs_stride, int32_
     const int grid = n_tiles < n_sms ? n_tiles : n_sms;
     const char* dbg = getenv("ROVER_POLICY_DEBUG_STOP");
     policy_forward_kernel<<<grid, kPolThreads, sizeof(PolSmem), static_cast<cudaStream_t>(stream)>>>(
-        map, obs, obs_stride, n_envs, static_cast<const unsigned char*>(packed), mean, dbg ? atoi(dbg) : 0);
+        map, obs, obs_stride, n_envs, static_cast<const unsigned char*>(packed), mean, dbg ? atoi(dbg) : 0,
+        value_head ? 1 : 0);
     return check_launch("policy_forward_kernel");
+}
+
+extern "C" int rover_policy_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed,
+                                    float* mean, void* stream) {
+    return policy_or_value_forward(obs, obs_stride, n_envs, packed, mean, stream, false);
+}
+
+extern "C" int rover_value_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed,
+                                   float* value, void* stream) {
+    return policy_or_value_forward(obs, obs_stride, n_envs, packed, value, stream, true);
 }
 
 extern "C" int rover_gaussian_act(const float* mean, const float* log_std, const float* eps, int32_t n_envs,

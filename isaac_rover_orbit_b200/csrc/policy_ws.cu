@@ -126,7 +126,8 @@ __device__ __forceinline__ void epilogue_to_act(uint32_t taddr, int n_cols, cons
 
 __global__ void __launch_bounds__(kWsThreads, 1)
 policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const float* __restrict__ obs, int obs_stride,
-                         int n_envs, int tile_rows, const unsigned char* __restrict__ packed, float* __restrict__ mean) {
+                         int n_envs, int tile_rows, const unsigned char* __restrict__ packed, float* __restrict__ mean,
+                         int value_head) {
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array, so that the compiler keeps
     // the address space (an integer round-trip turns every access into a generic LD/ST)
@@ -417,7 +418,9 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
                 float v[8];
                 tmem_ld8(acc + t_lane, v);
                 const float* b5 = sm.bias + (bias_offset(5) - kBiasOffset) / 4;
-                if (live) {
+                if (live && value_head) {
+                    mean[grow] = v[0] + b5[0];  // DeterministicNeuralNetwork (models.py:151-162): linear output, no tanh
+                } else if (live) {
                     float2 m;
                     m.x = tanhf(v[0] + b5[0]);
                     m.y = tanhf(v[1] + b5[1]);
@@ -442,7 +445,7 @@ typedef CUresult (*WsEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int launch_policy_forward_ws(const float* obs, int obs_stride, int n_envs, const void* packed, float* mean,
-                             cudaStream_t stream) {
+                             bool value_head, cudaStream_t stream) {
     static WsEncodeTiledFn encode = nullptr;
     static int n_sms = 0;
     constexpr int kSmemBytes = (int)sizeof(WsSmem) + 1024;
@@ -474,7 +477,8 @@ int launch_policy_forward_ws(const float* obs, int obs_stride, int n_envs, const
     const int n_tiles = (n_envs + tile_rows - 1) / tile_rows;
     const int grid = n_tiles < n_sms ? n_tiles : n_sms;
     policy_forward_ws_kernel<<<grid, kWsThreads, kSmemBytes, stream>>>(map, obs, obs_stride, n_envs, tile_rows,
-                                                                        static_cast<const unsigned char*>(packed), mean);
+                                                                        static_cast<const unsigned char*>(packed), mean,
+                                                                        value_head ? 1 : 0);
     return check_launch("policy_forward_ws_kernel");
 }
 

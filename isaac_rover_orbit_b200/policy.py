@@ -25,7 +25,12 @@ def alloc_obs(num_envs: int, device, cols: int = OBS_COLS) -> torch.Tensor:
     return torch.zeros(num_envs, stride, dtype=torch.float32, device=device)[:, :cols]
 
 
-class GaussianNeuralNetwork:
+class _RoverNetwork:
+    """Encoder + MLP of both reference networks (models.py:24-36, 39-162) over the packed tcgen05 weights."""
+
+    _OUT_DIM = 2
+    _HAS_LOG_STD = True
+
     def __init__(self, observation_space=None, action_space=None, device="cuda:0", mlp_input_size=4,
                  mlp_layers=(256, 160, 128), mlp_activation="leaky_relu", encoder_input_size=961,
                  encoder_layers=(80, 60), encoder_activation="leaky_relu", **kwargs):
@@ -38,7 +43,7 @@ class GaussianNeuralNetwork:
         if self.device.type != "cuda":
             raise RuntimeError("GaussianNeuralNetwork needs a CUDA device; there is no CPU fallback")
         self.mlp_input_size, self.encoder_input_size = mlp_input_size, encoder_input_size
-        dims = [(80, 961), (60, 80), (256, 64), (160, 256), (128, 160), (2, 128)]
+        dims = [(80, 961), (60, 80), (256, 64), (160, 256), (128, 160), (self._OUT_DIM, 128)]
         self._params = {}
         for key, (o, i) in zip(WEIGHT_KEYS, dims):
             self._params[key + ".weight"] = torch.zeros(o, i, device=self.device)
@@ -53,12 +58,12 @@ class GaussianNeuralNetwork:
 
     # ---- state dict with the reference's keys
     def state_dict(self) -> dict:
-        sd = {"log_std_parameter": self.log_std_parameter}
+        sd = {"log_std_parameter": self.log_std_parameter} if self._HAS_LOG_STD else {}
         sd.update(self._params)
         return sd
 
     def load_state_dict(self, sd: dict, strict: bool = True):
-        want = set(self._params) | {"log_std_parameter"}
+        want = set(self._params) | ({"log_std_parameter"} if self._HAS_LOG_STD else set())
         if strict and set(sd) != want:
             raise KeyError(f"unexpected / missing keys: {sorted(set(sd) ^ want)}")
         for k in want & set(sd):
@@ -80,11 +85,7 @@ class GaussianNeuralNetwork:
             _lib.check(1)
         self._dirty = False
 
-    # ---- skrl Model API
-    def compute(self, inputs: dict, role: str = "actor"):
-        """models.py:89-102: ``(mean [N,2], log_std_parameter [2], {})`` for ``inputs["states"] [N,965]``."""
-        states = inputs["states"]
-        _lib.require_cuda(states) if states.is_contiguous() else None
+    def _forward(self, states: torch.Tensor, entry: str) -> torch.Tensor:
         if not states.is_cuda or states.dtype != torch.float32 or states.dim() != 2 or states.shape[1] != OBS_COLS:
             raise RuntimeError("compute: states must be a CUDA fp32 [N,965] tensor")
         if states.stride(1) != 1 or states.stride(0) % 4 != 0 or states.data_ptr() % 16 != 0:
@@ -95,11 +96,20 @@ class GaussianNeuralNetwork:
         if self._dirty:
             self._pack()
         n = states.shape[0]
-        mean = torch.empty(n, 2, dtype=torch.float32, device=states.device)
-        _lib.check(_lib.load().rover_policy_forward(
+        out = torch.empty(n, self._OUT_DIM, dtype=torch.float32, device=states.device)
+        _lib.check(getattr(_lib.load(), entry)(
             C.c_void_p(states.data_ptr()), int(states.stride(0)), n, C.c_void_p(self._packed.data_ptr()),
-            C.c_void_p(mean.data_ptr()), _lib.current_stream(states.device)))
-        return mean, self.log_std_parameter, {}
+            C.c_void_p(out.data_ptr()), _lib.current_stream(states.device)))
+        return out
+
+
+class GaussianNeuralNetwork(_RoverNetwork):
+    """models.py:39-102."""
+
+    # ---- skrl Model API
+    def compute(self, inputs: dict, role: str = "actor"):
+        """models.py:89-102: ``(mean [N,2], log_std_parameter [2], {})`` for ``inputs["states"] [N,965]``."""
+        return self._forward(inputs["states"], "rover_policy_forward"), self.log_std_parameter, {}
 
     def act(self, inputs: dict, role: str = "actor", eps: torch.Tensor | None = None):
         """skrl 1.1.0 ``GaussianMixin.act``: returns ``(actions [N,2], log_prob [N,1], outputs)``.
@@ -115,3 +125,19 @@ class GaussianNeuralNetwork:
             C.c_void_p(actions.data_ptr()), C.c_void_p(log_prob.data_ptr()), _lib.current_stream(mean.device)))
         outputs["mean_actions"] = mean
         return actions, log_prob.unsqueeze(-1), outputs
+
+
+class DeterministicNeuralNetwork(_RoverNetwork):
+    """The value network: rover_envs/envs/navigation/learning/skrl/models.py:105-162 (same encoder + MLP with its own
+    weights -- the ``value`` entry of ``best_agent.pt`` -- one linear output, no tanh), ``compute -> (value [N,1], {})``
+    and skrl 1.1.0 ``DeterministicMixin.act`` (``clip_actions=False``): ``(value, None, outputs)``."""
+
+    _OUT_DIM = 1
+    _HAS_LOG_STD = False
+
+    def compute(self, inputs: dict, role: str = "actor"):
+        return self._forward(inputs["states"], "rover_value_forward"), {}
+
+    def act(self, inputs: dict, role: str = "actor"):
+        value, outputs = self.compute(inputs, role)
+        return value, None, outputs

@@ -33,6 +33,18 @@ def policy_mean(obs: torch.Tensor, sd: dict) -> torch.Tensor:
     return torch.tanh(lin(WEIGHT_KEYS[5], h))
 
 
+def value_forward(obs: torch.Tensor, sd: dict) -> torch.Tensor:
+    """``DeterministicNeuralNetwork.compute`` (models.py:151-162): the policy's encoder + MLP structure with the
+    value weights, final ``nn.Linear(128, 1)`` without activation.  Pinned by ``tests/golden/value.npz``."""
+    lin = lambda k, x: F.linear(x, sd[k + ".weight"], sd[k + ".bias"])  # noqa: E731
+    act = lambda x: F.leaky_relu(x, 0.01)  # noqa: E731
+    e = act(lin(WEIGHT_KEYS[1], act(lin(WEIGHT_KEYS[0], obs[:, 3:-1]))))
+    h = torch.cat([obs[:, 0:4], e], dim=1)
+    for k in WEIGHT_KEYS[2:5]:
+        h = act(lin(k, h))
+    return lin(WEIGHT_KEYS[5], h)
+
+
 def gaussian_act(mean: torch.Tensor, log_std_parameter: torch.Tensor, eps: torch.Tensor):
     log_std = torch.clamp(log_std_parameter, -20.0, 2.0)
     std = log_std.exp()

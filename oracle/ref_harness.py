@@ -242,6 +242,20 @@ def ref_reset_root_state(env, ids, spawn_perm, yaw_u):
     return env.scene["robot"].written_pose
 
 
+def ref_value():
+    """The reference ``DeterministicNeuralNetwork`` (models.py:105-162) with the ``value`` weights of ``best_agent.pt``."""
+    md = ref_loader.load("models")
+    space = types.SimpleNamespace(shape=(2,))
+    net = md.DeterministicNeuralNetwork(observation_space=None, action_space=space, device="cpu", mlp_input_size=4,
+                                        mlp_layers=[256, 160, 128], mlp_activation="leaky_relu",
+                                        encoder_input_size=961, encoder_layers=[80, 60],
+                                        encoder_activation="leaky_relu")
+    sd = torch.load(ref_loader.POLICY_CHECKPOINT, map_location="cpu", weights_only=False)["value"]
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    return net
+
+
 def ref_policy():
     """The reference ``GaussianNeuralNetwork`` (models.py:39-102) with ``best_agent.pt`` loaded strictly."""
     md = ref_loader.load("models")

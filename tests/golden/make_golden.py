@@ -147,11 +147,27 @@ def gen_policy(path):
     np.savez_compressed(path, in_obs=obs.numpy(), ref_mean=mean.numpy(), ref_log_std=log_std.detach().numpy(), **sd)
 
 
+def gen_value(path):
+    net = H.ref_value()
+    g = torch.Generator().manual_seed(101)
+    n = 64
+    obs = torch.cat([torch.rand(n, 2, generator=g) * 2 - 1, torch.rand(n, 1, generator=g) * 1.3,
+                     torch.rand(n, 1, generator=g) * 2 - 1, torch.randn(n, 961, generator=g) * 0.15], dim=1)
+    with torch.no_grad():
+        value, _ = net.compute({"states": obs}, role="value")
+    sd = {k.replace(".", "__"): v.numpy() for k, v in net.state_dict().items()}
+    np.savez_compressed(path, in_obs=obs.numpy(), ref_value=value.numpy(), **sd)
+
+
 def main():
     assert ref_loader.available(), "run this where /root/reference exists"
+    if "--value-only" in sys.argv:  # added after the other fixtures were committed: leaves them untouched
+        gen_value(os.path.join(HERE, "value.npz"))
+        return
     gen_terms(os.path.join(HERE, "terms.npz"))
     gen_terrain_and_command(os.path.join(HERE, "terrain_command.npz"))
     gen_policy(os.path.join(HERE, "policy.npz"))
+    gen_value(os.path.join(HERE, "value.npz"))
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith(".npz"):
             print(fn, os.path.getsize(os.path.join(HERE, fn)) // 1024, "KiB")

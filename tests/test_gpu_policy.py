@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork, WEIGHT_KEYS, alloc_obs
+from isaac_rover_orbit_b200.policy import DeterministicNeuralNetwork, GaussianNeuralNetwork, WEIGHT_KEYS, alloc_obs
 
 pytestmark = pytest.mark.gpu
 
@@ -118,3 +118,44 @@ def test_policy_rejects_other_shapes(cuda_device):
     net = GaussianNeuralNetwork(device=cuda_device)
     with pytest.raises(KeyError):
         net.load_state_dict({"mlp.0.weight": torch.zeros(256, 64)}, strict=True)
+
+
+def emulate_value_bf16(obs, sd):
+    act = lambda x: torch.nn.functional.leaky_relu(x, 0.01)  # noqa: E731
+    lin = lambda k, x: _bf(x) @ _bf(sd[k + ".weight"]).T + sd[k + ".bias"]  # noqa: E731
+    e = act(lin(WEIGHT_KEYS[1], act(lin(WEIGHT_KEYS[0], obs[:, 3:964]))))
+    h = torch.cat([obs[:, 0:4], e], dim=1)
+    for k in WEIGHT_KEYS[2:5]:
+        h = act(lin(k, h))
+    return lin(WEIGHT_KEYS[5], h)
+
+
+@pytest.mark.parametrize("kernel", ["ws", "v1"])
+def test_value_forward_reference_checkpoint(cuda_device, golden_dir, kernel, monkeypatch):
+    """DeterministicNeuralNetwork (models.py:105-162) with the ``value`` weights of best_agent.pt:
+    bf16-emulation tolerance 2e-2 abs on values of magnitude ~10 (unbounded linear output), 1e-1 vs the fp32 reference."""
+    from oracle import policy as OP
+
+    monkeypatch.setenv("ROVER_POLICY_KERNEL", kernel)
+    z = np.load(os.path.join(golden_dir, "value.npz"))
+    sd = OP.load_golden_weights(z)
+    net = DeterministicNeuralNetwork(device=cuda_device)
+    assert set(net.state_dict()) == set(sd)
+    net.load_state_dict(sd)
+    obs = torch.from_numpy(z["in_obs"])
+    value, outputs = net.compute({"states": obs.to(cuda_device)}, role="value")
+    assert value.shape == (obs.shape[0], 1) and outputs == {}
+    ref = torch.from_numpy(z["ref_value"])
+    scale = float(ref.abs().max())
+    torch.testing.assert_close(value.cpu(), emulate_value_bf16(obs, sd), rtol=0, atol=2e-3 * max(scale, 1.0))
+    torch.testing.assert_close(value.cpu(), ref, rtol=0, atol=2e-2 * max(scale, 1.0))
+    v2, none, _ = net.act({"states": obs.to(cuda_device)})
+    assert none is None and torch.equal(v2, value)
+    n = 5000  # several tiles, ragged tail
+    g = torch.Generator().manual_seed(5)
+    big = torch.cat([torch.rand(n, 4, generator=g) * 2 - 1, torch.randn(n, 961, generator=g) * 0.3], dim=1)
+    vb = net.compute({"states": big.to(cuda_device)})[0]
+    emu = emulate_value_bf16(big, sd)
+    # same arithmetic, different fp32 summation order inside the MMAs; bf16 re-rounding of the activations amplifies
+    # it: 4e-3 of the output range (the policy test uses 4e-3 on tanh outputs in [-1, 1])
+    torch.testing.assert_close(vb.cpu(), emu, rtol=0, atol=4e-3 * max(float(emu.abs().max()), 1.0))

@@ -203,3 +203,15 @@ def test_ackermann_variants_golden(terms_npz):
     jp, jv = T.ackermann2(pe[:, 0], pe[:, 1], exomy)
     torch.testing.assert_close(jp, _t(terms_npz["ref_exomy_joint_pos"]), rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(jv, _t(terms_npz["ref_exomy_joint_vel"]), rtol=1e-6, atol=1e-6)
+
+
+def test_value_oracle_matches_reference_network(golden_dir):
+    """oracle.policy.value_forward vs the outputs of the unmodified DeterministicNeuralNetwork (value weights of
+    best_agent.pt), tests/golden/value.npz."""
+    from oracle import policy as OP
+
+    z = np.load(os.path.join(golden_dir, "value.npz"))
+    sd = OP.load_golden_weights(z)
+    assert sd["mlp.6.weight"].shape == (1, 128) and "log_std_parameter" not in sd
+    out = OP.value_forward(torch.from_numpy(z["in_obs"]), sd)
+    torch.testing.assert_close(out, torch.from_numpy(z["ref_value"]), rtol=1e-5, atol=1e-6)
