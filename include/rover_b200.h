@@ -244,6 +244,14 @@ int rover_policy_forward(const float* obs, int32_t obs_stride, int32_t n_envs, c
  * linear output, no tanh.  `packed` comes from rover_policy_pack with out_dim[5] == 1; value [N] fp32. */
 int rover_value_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed, float* value,
                         void* stream);
+/* The same two networks on a bf16 copy of the observation, obs_bf16 [N, stride] (stride % 8 == 0, rows 16-byte
+ * aligned; columns 0..963 are read), as rover_height_scan_obs writes it.  A TMA tile of that buffer is the MMA operand
+ * as it lands (no conversion stage, half the bytes); results are bit-identical to the fp32 entry points fed with
+ * observations that round to the same bf16 values. */
+int rover_policy_forward_bf16(const uint16_t* obs_bf16, int32_t stride, int32_t n_envs, const void* packed, float* mean,
+                              void* stream);
+int rover_value_forward_bf16(const uint16_t* obs_bf16, int32_t stride, int32_t n_envs, const void* packed, float* value,
+                             void* stream);
 /* actions = clamp(mean + exp(clamp(log_std,-20,2)) * eps, -1, 1); log_prob [N] = sum_j log N(a_j) */
 int rover_gaussian_act(const float* mean, const float* log_std, const float* eps, int32_t n_envs, float* actions,
                        float* log_prob, void* stream);

@@ -22,7 +22,8 @@ ABI_VERSION = 2
 
 SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_mdp_pre_step", "rover_mdp_post_step",
            "rover_ackermann",
-           "rover_policy_pack", "rover_policy_forward", "rover_value_forward", "rover_gaussian_act")
+           "rover_policy_pack", "rover_policy_forward", "rover_value_forward", "rover_policy_forward_bf16",
+           "rover_value_forward_bf16", "rover_gaussian_act")
 
 
 class ScanLevel(C.Structure):
@@ -118,6 +119,9 @@ def load() -> C.CDLL:
     lib.rover_policy_forward.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.rover_value_forward.restype = C.c_int
     lib.rover_value_forward.argtypes = [vp, i32, i32, vp, vp, vp]
+    for fn in (lib.rover_policy_forward_bf16, lib.rover_value_forward_bf16):
+        fn.restype = C.c_int
+        fn.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.rover_gaussian_act.restype = C.c_int
     lib.rover_gaussian_act.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     _lib = lib

@@ -337,8 +337,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int launch_policy_forward_ws(const float* obs, int obs_stride, int n_envs, const void* packed, float* out,
-                             bool value_head, cudaStream_t stream);  // policy_ws.cu
+int launch_policy_forward_ws(const void* obs, int obs_stride, int n_envs, const void* packed, float* out,
+                             bool value_head, bool bf16_in, cudaStream_t stream);  // policy_ws.cu
 
 }  // namespace rover
 
@@ -379,7 +379,7 @@ static int policy_or_value_forward(const float* obs, int32_t obs_stride, int32_t
     {   // default: the warp-specialised kernel (policy_ws.cu); ROVER_POLICY_KERNEL=v1 selects the tile-serial one
         const char* which = getenv("ROVER_POLICY_KERNEL");
         if (which == nullptr || which[0] != 'v' || which[1] != '1')
-            return launch_policy_forward_ws(obs, obs_stride, n_envs, packed, mean, value_head,
+            return launch_policy_forward_ws(obs, obs_stride, n_envs, packed, mean, value_head, false,
                                             static_cast<cudaStream_t>(stream));
     }
     static EncodeTiledFn encode = nullptr;
@@ -417,6 +417,28 @@ static int policy_or_value_forward(const float* obs, int32_t obs_stride, int32_t
 extern "C" int rover_policy_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed,
                                     float* mean, void* stream) {
     return policy_or_value_forward(obs, obs_stride, n_envs, packed, mean, stream, false);
+}
+
+static int forward_bf16(const uint16_t* obs_bf16, int32_t stride, int32_t n_envs, const void* packed, float* out,
+                        void* stream, bool value_head) {
+    using namespace rover;
+    ROVER_CHECK(n_envs >= 0, "rover_*_forward_bf16: negative n_envs");
+    if (n_envs == 0) return 0;
+    ROVER_CHECK(obs_bf16 && packed && out, "rover_*_forward_bf16: NULL argument");
+    ROVER_CHECK(stride >= kObsCols && stride % 8 == 0 && (reinterpret_cast<uintptr_t>(obs_bf16) & 15) == 0,
+                "rover_*_forward_bf16: bf16 observation rows must be 16-byte aligned (stride %% 8 == 0, got %d)", stride);
+    ROVER_CHECK((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "rover_*_forward_bf16: packed blob not 128B aligned");
+    return launch_policy_forward_ws(obs_bf16, stride, n_envs, packed, out, value_head, true, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rover_policy_forward_bf16(const uint16_t* obs_bf16, int32_t stride, int32_t n_envs, const void* packed,
+                                         float* mean, void* stream) {
+    return forward_bf16(obs_bf16, stride, n_envs, packed, mean, stream, false);
+}
+
+extern "C" int rover_value_forward_bf16(const uint16_t* obs_bf16, int32_t stride, int32_t n_envs, const void* packed,
+                                        float* value, void* stream) {
+    return forward_bf16(obs_bf16, stride, n_envs, packed, value, stream, true);
 }
 
 extern "C" int rover_value_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed,

@@ -51,11 +51,17 @@ static_assert(weight_bytes(1) <= kWsWBuf && weight_bytes(2) <= kWsWBuf && weight
                   weight_bytes(4) <= kWsWBuf && weight_bytes(5) <= kWsWBuf,
               "weight buffer plan");
 static_assert(kW0ChunkBytes == 2 * kWsW0Chunk, "a 32-column chunk is half of a packed 64-column chunk");
+// bf16-observation mode (kBf16In): the observation arrives as bf16 [N, stride] (written by the height scan, see
+// rover_height_scan_obs), so a TMA tile of 64 columns x tile rows (128 B per row, SWIZZLE_128B) IS the A operand of
+// the MMA (canonical K-major SWIZZLE_128B layout) -- no conversion stage, half the HBM bytes.
+constexpr int kBfChunkK = 64;
+constexpr int kBfChunks = 16;                 // columns [0, 1024); beyond column 963 the tensor map zero-fills
+constexpr int kBfStagesW = 3;                 // 10 KB W0 chunks in the space of a_bf16[] + w0[]
 
 struct WsSmem {
     float stage_f[kWsStagesF][kTileM * kWsChunkK];        // 5 x 16 KB, TMA destinations (1024-byte aligned)
-    unsigned char a_bf16[kWsStagesA][4 * kWsPlane];       // 2 x 8 KB
-    unsigned char w0[kWsStagesW][kWsW0Chunk];             // 3 x 5 KB
+    unsigned char a_bf16[kWsStagesA][4 * kWsPlane];       // 2 x 8 KB   } bf16-observation mode: three 10 KB W0
+    unsigned char w0[kWsStagesW][kWsW0Chunk];             // 3 x 5 KB   } chunks live in these two arrays
     unsigned char act[32 * kWsPlane];                     // A operand of layers 1..5 (K <= 256): 64 KB
     unsigned char w[kWsWBuf];                             // weights of the current layer
     float bias[80 + 64 + 256 + 160 + 128 + 16];
@@ -67,6 +73,22 @@ struct WsSmem {
     uint32_t tmem_base;
 };
 static_assert(sizeof(WsSmem) + 1024 <= 227 * 1024, "WsSmem exceeds the shared memory of one SM");
+static_assert(offsetof(WsSmem, w0) == offsetof(WsSmem, a_bf16) + kWsStagesA * 4 * kWsPlane &&
+                  kBfStagesW * kW0ChunkBytes <= kWsStagesA * 4 * kWsPlane + kWsStagesW * kWsW0Chunk,
+              "bf16-observation mode: W0 ring overlays a_bf16[] + w0[]");
+static_assert(kTileM * kBfChunkK * 2 == kTileM * kWsChunkK * 4, "both modes use the same 16 KB stages");
+
+// shared-memory matrix descriptor, K-major SWIZZLE_128B (the layout a 128-byte-wide SWIZZLE_128B TMA box lands in):
+// 8-row groups are 1024 B apart (SBO), LBO is not used by swizzled K-major layouts, layout type 2, version 1
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 
 __device__ __forceinline__ void mb_arrive(unsigned long long* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(b)) : "memory");
@@ -124,6 +146,7 @@ __device__ __forceinline__ void epilogue_to_act(uint32_t taddr, int n_cols, cons
     }
 }
 
+template <bool kBf16In>
 __global__ void __launch_bounds__(kWsThreads, 1)
 policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const float* __restrict__ obs, int obs_stride,
                          int n_envs, int tile_rows, const unsigned char* __restrict__ packed, float* __restrict__ mean,
@@ -137,7 +160,12 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
     // rounds of the grid: 65536 envs on 148 SMs -> 586 tiles of 112 instead of 512 of 128 = 3.96 instead of 3.46 -> 4
     // rounds).  The MMAs stay M = 128; accumulator rows >= tile_rows hold garbage and are never stored.
     const int n_tiles = (n_envs + tile_rows - 1) / tile_rows;
-    const uint32_t chunk_bytes = (uint32_t)tile_rows * kWsChunkK * 4;
+    constexpr int kChunks = kBf16In ? kBfChunks : kWsChunks;
+    constexpr int kChunkK = kBf16In ? kBfChunkK : kWsChunkK;        // observation columns per chunk
+    constexpr int kStagesW = kBf16In ? kBfStagesW : kWsStagesW;
+    constexpr int kW0Chunk = kBf16In ? kW0ChunkBytes : kWsW0Chunk;  // bytes of the packed W0 image per chunk
+    const uint32_t chunk_bytes = (uint32_t)tile_rows * 128u;        // 32 fp32 or 64 bf16 columns per row
+    unsigned char* const w0_ring = kBf16In ? &sm.a_bf16[0][0] : &sm.w0[0][0];
 #if ROVER_POLICY_DBG
     const long long dbg_t0 = clock64();
 #endif
@@ -147,13 +175,13 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&obs_map)) : "memory");
         for (int i = 0; i < kWsStagesF; ++i) {
             mb_init(&sm.f_full[i], 1);
-            mb_init(&sm.f_empty[i], 4);  // one arrival per converter warp
+            mb_init(&sm.f_empty[i], kBf16In ? 1 : 4);  // converter warps, or the commit of the MMAs that read the stage
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if ((int)blockIdx.x < n_tiles)
             for (int c = 0; c < kWsStagesF; ++c) {
                 mb_expect_tx(&sm.f_full[c], chunk_bytes);
-                tma_2d(sm.stage_f[c], &obs_map, c * kWsChunkK, blockIdx.x * tile_rows, &sm.f_full[c]);
+                tma_2d(sm.stage_f[c], &obs_map, c * kChunkK, blockIdx.x * tile_rows, &sm.f_full[c]);
             }
     }
     if (tid == 0) {
@@ -192,11 +220,11 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
             bool first = true;  // chunks 0 .. kWsStagesF-1 of the first tile were issued in the prologue
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int row0 = tile * tile_rows;
-                for (int c = 0; c < kWsChunks; ++c) {
+                for (int c = 0; c < kChunks; ++c) {
                     if (!(first && c < kWsStagesF)) {
                         mb_wait(&sm.f_empty[sf], (pf & 1u) ^ 1u);
                         mb_expect_tx(&sm.f_full[sf], chunk_bytes);
-                        tma_2d(sm.stage_f[sf], &obs_map, c * kWsChunkK, row0, &sm.f_full[sf]);
+                        tma_2d(sm.stage_f[sf], &obs_map, c * kChunkK, row0, &sm.f_full[sf]);
                     }
                     if (dbg_g < 128) PDBG(dbg_g);
                     ++dbg_g;
@@ -211,11 +239,11 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
             int sw = 0;
             uint32_t pw = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int c = 0; c < kWsChunks; ++c) {
+                for (int c = 0; c < kChunks; ++c) {
                     mb_wait(&sm.w0_empty[sw], (pw & 1u) ^ 1u);
-                    mb_expect_tx(&sm.w0_full[sw], kWsW0Chunk);
-                    bulk_g2s(sm.w0[sw], packed + (size_t)c * kWsW0Chunk, kWsW0Chunk, &sm.w0_full[sw]);
-                    if (++sw == kWsStagesW) sw = 0, ++pw;
+                    mb_expect_tx(&sm.w0_full[sw], kW0Chunk);
+                    bulk_g2s(w0_ring + sw * kW0Chunk, packed + (size_t)c * kW0Chunk, kW0Chunk, &sm.w0_full[sw]);
+                    if (++sw == kStagesW) sw = 0, ++pw;
                 }
             }
         }
@@ -231,25 +259,37 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
                 mb_wait(&sm.d0_empty[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);  // the layer group has drained D0[buf]
                 tc_fence_after();
                 const uint32_t d0 = tmem + kWsColD0 + buf * kWsColD0Stride;
-                for (int c = 0; c < kWsChunks; ++c) {
-                    mb_wait(&sm.a_full[sa], pa & 1u);
+                for (int c = 0; c < kChunks; ++c) {
+                    if (kBf16In) mb_wait(&sm.f_full[sa], pa & 1u);  // sa / pa walk the 5-stage TMA ring in this mode
+                    else mb_wait(&sm.a_full[sa], pa & 1u);
                     mb_wait(&sm.w0_full[sw], pw & 1u);
                     tc_fence_after();
-                    const uint32_t a0 = sptr(sm.a_bf16[sa]), b0 = sptr(sm.w0[sw]);
+                    const uint32_t b0 = sptr(w0_ring + sw * kW0Chunk);
+                    if (kBf16In) {
+                        const uint32_t a0 = sptr(sm.stage_f[sa]);
 #pragma unroll
-                    for (int j = 0; j < kWsChunkK / 16; ++j)
-                        umma(d0, make_desc(a0 + j * 2 * kWsPlane, kWsPlane), make_desc(b0 + j * 2 * 80 * 16, 80 * 16), idesc0,
-                             (c | j) != 0);
+                        for (int j = 0; j < kBfChunkK / 16; ++j)  // 16 bf16 = 32 B further along K inside the 128 B rows
+                            umma(d0, make_desc_sw128(a0 + j * 32), make_desc(b0 + j * 2 * 80 * 16, 80 * 16), idesc0, (c | j) != 0);
+                        umma_commit(&sm.f_empty[sa]);  // the TMA stage is free once these MMAs retire
+                    } else {
+                        const uint32_t a0 = sptr(sm.a_bf16[sa]);
+#pragma unroll
+                        for (int j = 0; j < kWsChunkK / 16; ++j)
+                            umma(d0, make_desc(a0 + j * 2 * kWsPlane, kWsPlane), make_desc(b0 + j * 2 * 80 * 16, 80 * 16), idesc0,
+                                 (c | j) != 0);
+                        umma_commit(&sm.a_empty[sa]);  // A stage and W0 stage are free once these MMAs retire
+                    }
                     if (dbg_g < 128) PDBG(512 + dbg_g);
                     ++dbg_g;
-                    umma_commit(&sm.a_empty[sa]);   // A stage and W0 stage are free once these MMAs retire
                     umma_commit(&sm.w0_empty[sw]);
-                    if (++sa == kWsStagesA) sa = 0, ++pa;
-                    if (++sw == kWsStagesW) sw = 0, ++pw;
+                    if (++sa == (kBf16In ? kWsStagesF : kWsStagesA)) sa = 0, ++pa;
+                    if (++sw == kStagesW) sw = 0, ++pw;
                 }
                 umma_commit(&sm.d0_full[buf]);
             }
         }
+    } else if (warp >= 4 && kBf16In) {
+        // bf16-observation mode: no conversion stage, these warps idle
     } else if (warp >= 4) {
         // =============================================================== converters: fp32 stage -> bf16 A operand
         const int row = tid - 128;  // tile row
@@ -349,7 +389,13 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
             const bool live = row < tile_rows && grow < n_envs;
             float inject[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) inject[j] = live ? __ldg(obs + (size_t)grow * obs_stride + j) : 0.f;
+            for (int j = 0; j < 4; ++j) {
+                if (kBf16In)  // obs points at bf16 rows; the values are re-rounded to bf16 below either way
+                    inject[j] = live ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(obs)[(size_t)grow * obs_stride + j])
+                                     : 0.f;
+                else
+                    inject[j] = live ? __ldg(obs + (size_t)grow * obs_stride + j) : 0.f;
+            }
             // ---- layer 0 epilogue: D0[buf] -> A1 (80 columns)
 #define LDBG(k)                                        \
     do {                                               \
@@ -444,8 +490,9 @@ typedef CUresult (*WsEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int launch_policy_forward_ws(const float* obs, int obs_stride, int n_envs, const void* packed, float* mean,
-                             bool value_head, cudaStream_t stream) {
+// obs: fp32 [N, obs_stride] (bf16_in == false) or bf16 [N, obs_stride] (bf16_in == true; strides in elements)
+int launch_policy_forward_ws(const void* obs, int obs_stride, int n_envs, const void* packed, float* mean,
+                             bool value_head, bool bf16_in, cudaStream_t stream) {
     static WsEncodeTiledFn encode = nullptr;
     static int n_sms = 0;
     constexpr int kSmemBytes = (int)sizeof(WsSmem) + 1024;
@@ -453,32 +500,42 @@ int launch_policy_forward_ws(const float* obs, int obs_stride, int n_envs, const
         int dev = 0;
         ROVER_CUDA(cudaGetDevice(&dev));
         ROVER_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-        ROVER_CUDA(cudaFuncSetAttribute(policy_forward_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        ROVER_CUDA(cudaFuncSetAttribute(policy_forward_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        ROVER_CUDA(cudaFuncSetAttribute(policy_forward_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
         ROVER_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
         ROVER_CHECK(fn && q == cudaDriverEntryPointSuccess, "rover_policy_forward: cuTensorMapEncodeTiled unavailable");
         encode = reinterpret_cast<WsEncodeTiledFn>(fn);
     }
-    alignas(64) CUtensorMap map;
-    const cuuint64_t gdim[2] = {(cuuint64_t)kObsCols, (cuuint64_t)n_envs};
-    const cuuint64_t gstride[1] = {(cuuint64_t)obs_stride * 4ull};
     // rows per tile: fill whole rounds of the grid (see the kernel); multiple of 8 (core-matrix rows), at most 128
     const int rounds = (n_envs + kTileM * n_sms - 1) / (kTileM * n_sms);
     int tile_rows = (n_envs + rounds * n_sms - 1) / (rounds * n_sms);
     tile_rows = ((tile_rows + 7) / 8) * 8;
     if (tile_rows > kTileM) tile_rows = kTileM;
-    const cuuint32_t box[2] = {(cuuint32_t)kWsChunkK, (cuuint32_t)tile_rows};
+    alignas(64) CUtensorMap map;
+    // fp32: columns [0, 965), the converter zeroes what lies outside [3, 964).  bf16: the tile is the MMA operand as
+    // it lands, so the map ends at column 964 (the ray the reference's slicing drops is zero-filled; columns 0..2 are
+    // finite and meet zero weights)
+    const cuuint64_t gdim[2] = {(cuuint64_t)(bf16_in ? kEncInOffset + kEncIn : kObsCols), (cuuint64_t)n_envs};
+    const cuuint64_t gstride[1] = {(cuuint64_t)obs_stride * (bf16_in ? 2ull : 4ull)};
+    const cuuint32_t box[2] = {(cuuint32_t)(bf16_in ? kBfChunkK : kWsChunkK), (cuuint32_t)tile_rows};
     const cuuint32_t estr[2] = {1u, 1u};
-    const CUresult rc = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(obs), gdim, gstride, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    const CUresult rc = encode(&map, bf16_in ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                               const_cast<void*>(obs), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ROVER_CHECK(rc == CUDA_SUCCESS, "rover_policy_forward: cuTensorMapEncodeTiled failed (%d)", (int)rc);
     const int n_tiles = (n_envs + tile_rows - 1) / tile_rows;
     const int grid = n_tiles < n_sms ? n_tiles : n_sms;
-    policy_forward_ws_kernel<<<grid, kWsThreads, kSmemBytes, stream>>>(map, obs, obs_stride, n_envs, tile_rows,
-                                                                        static_cast<const unsigned char*>(packed), mean,
-                                                                        value_head ? 1 : 0);
+    if (bf16_in)
+        policy_forward_ws_kernel<true><<<grid, kWsThreads, kSmemBytes, stream>>>(
+            map, static_cast<const float*>(obs), obs_stride, n_envs, tile_rows, static_cast<const unsigned char*>(packed), mean,
+            value_head ? 1 : 0);
+    else
+        policy_forward_ws_kernel<false><<<grid, kWsThreads, kSmemBytes, stream>>>(
+            map, static_cast<const float*>(obs), obs_stride, n_envs, tile_rows, static_cast<const unsigned char*>(packed), mean,
+            value_head ? 1 : 0);
     return check_launch("policy_forward_ws_kernel");
 }
 

@@ -25,6 +25,13 @@ def alloc_obs(num_envs: int, device, cols: int = OBS_COLS) -> torch.Tensor:
     return torch.zeros(num_envs, stride, dtype=torch.float32, device=device)[:, :cols]
 
 
+def alloc_obs_bf16(num_envs: int, device, cols: int = OBS_COLS) -> torch.Tensor:
+    """bf16 mirror of the observation buffer (``ops.height_scan(..., obs_bf16=...)`` fills it): rows padded to a
+    multiple of 8 elements so that they start on 16-byte boundaries.  Returns the ``[:, :cols]`` view."""
+    stride = (cols + 7) // 8 * 8
+    return torch.zeros(num_envs, stride, dtype=torch.bfloat16, device=device)[:, :cols]
+
+
 class _RoverNetwork:
     """Encoder + MLP of both reference networks (models.py:24-36, 39-162) over the packed tcgen05 weights."""
 
@@ -102,6 +109,20 @@ class _RoverNetwork:
             C.c_void_p(out.data_ptr()), _lib.current_stream(states.device)))
         return out
 
+    def _forward_bf16(self, states: torch.Tensor, entry: str) -> torch.Tensor:
+        """bf16 observations ``[N, 965]`` (``alloc_obs_bf16`` layout): the TMA tile is the MMA operand, no conversion."""
+        if (not states.is_cuda or states.dtype != torch.bfloat16 or states.dim() != 2 or states.shape[1] != OBS_COLS
+                or states.stride(1) != 1 or states.stride(0) % 8 != 0 or states.data_ptr() % 16 != 0):
+            raise RuntimeError("compute_bf16: states must be a CUDA bf16 [N,965] view from alloc_obs_bf16()")
+        if self._dirty:
+            self._pack()
+        n = states.shape[0]
+        out = torch.empty(n, self._OUT_DIM, dtype=torch.float32, device=states.device)
+        _lib.check(getattr(_lib.load(), entry)(
+            C.c_void_p(states.data_ptr()), int(states.stride(0)), n, C.c_void_p(self._packed.data_ptr()),
+            C.c_void_p(out.data_ptr()), _lib.current_stream(states.device)))
+        return out
+
 
 class GaussianNeuralNetwork(_RoverNetwork):
     """models.py:39-102."""
@@ -110,6 +131,10 @@ class GaussianNeuralNetwork(_RoverNetwork):
     def compute(self, inputs: dict, role: str = "actor"):
         """models.py:89-102: ``(mean [N,2], log_std_parameter [2], {})`` for ``inputs["states"] [N,965]``."""
         return self._forward(inputs["states"], "rover_policy_forward"), self.log_std_parameter, {}
+
+    def compute_bf16(self, inputs: dict, role: str = "actor"):
+        """``compute`` on the bf16 observation mirror; identical means (the fp32 path rounds to the same bf16)."""
+        return self._forward_bf16(inputs["states"], "rover_policy_forward_bf16"), self.log_std_parameter, {}
 
     def act(self, inputs: dict, role: str = "actor", eps: torch.Tensor | None = None):
         """skrl 1.1.0 ``GaussianMixin.act``: returns ``(actions [N,2], log_prob [N,1], outputs)``.
@@ -137,6 +162,9 @@ class DeterministicNeuralNetwork(_RoverNetwork):
 
     def compute(self, inputs: dict, role: str = "actor"):
         return self._forward(inputs["states"], "rover_value_forward"), {}
+
+    def compute_bf16(self, inputs: dict, role: str = "actor"):
+        return self._forward_bf16(inputs["states"], "rover_value_forward_bf16"), {}
 
     def act(self, inputs: dict, role: str = "actor"):
         value, outputs = self.compute(inputs, role)
