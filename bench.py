@@ -348,7 +348,7 @@ def run_ours(args):
 
     # ------------------------------------------------------------------ extra: policy forward (cfg-4)
     try:
-        from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork, alloc_obs
+        from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork, alloc_obs, alloc_obs_bf16
 
         n_pol = 65536
         net = GaussianNeuralNetwork(device=dev)
@@ -363,6 +363,18 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tp, op=dist.ReduceOp.MAX)
         t_pol = float(tp[0]) / ksteps * 1e-3
+        # the same forward on the bf16 observation mirror (what the closed loop uses: written by the height scan)
+        pol_obs_bf = alloc_obs_bf16(n_pol, dev)
+        pol_obs_bf.copy_(pol_obs)
+        ms_bf = time_steps(lambda i: net.compute({"states": pol_obs_bf}), ksteps, 3, flush, stream)
+        tb = torch.tensor([ms_bf.sum()], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        t_bf = float(tb[0]) / ksteps * 1e-3
+        same = bool(torch.equal(net.compute({"states": pol_obs})[0], net.compute({"states": pol_obs_bf})[0]))
+        bf16_pol = {"env_forwards_per_s": n_pol * world / t_bf, "us_per_launch": t_bf * 1e6,
+                    "bit_identical_to_fp32_path": same,
+                    "roofline_frac_hbm": n_pol * (964 * 2 + 8) / t_bf / 1e9 / measured_peak()[0]}
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -378,6 +390,7 @@ def run_ours(args):
             "roofline_frac_hbm": n_pol * (965 * 4 + 8) / t_pol / 1e9 / peak,
             "kernel": "policy_forward_ws_kernel" if os.environ.get("ROVER_POLICY_KERNEL", "ws")[:2] != "v1"
                       else "policy_forward_kernel",
+            "bf16_observation": bf16_pol,
             "note": "standalone forward reads 3860 B/env of fp32 observations: 83 FLOP/B < ridge, HBM-bound (SURVEY 8d)",
         }
     except Exception as e:
@@ -400,10 +413,23 @@ def run_ours(args):
             actions, _, _ = net.act({"states": loop_obs}, eps=eps_sets[i % 4])
             act_buf.copy_(actions)
 
-        g_loop = graphed(closed_step)
+        loop_obs_bf = alloc_obs_bf16(n_step, dev)
+
+        def closed_step_bf16(i):  # the scan also writes the bf16 observation; the policy reads only that
+            s = sets[i % 4]
+            torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)
+            ops.mdp_pre_step(buf, params, act_buf, s.force_matrix_w)
+            ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
+                              s.theta_u, loop_obs)
+            ops.height_scan_obs(s.root_pos_w, s.root_quat_w, rays, grid, loop_obs, loop_obs_bf)
+            actions, _, _ = net.act({"states": loop_obs_bf}, eps=eps_sets[i % 4])
+            act_buf.copy_(actions)
+
         ksteps = max(min(args.steps, 200), 3)
-        ms_loop = time_steps(g_loop, ksteps, 3, flush, stream)
-        tl = torch.tensor([ms_loop.sum()], dtype=torch.float64, device=dev)
+        ms_loop = time_steps(graphed(closed_step), ksteps, 3, flush, stream)
+        act_buf.zero_()
+        ms_loop_bf = time_steps(graphed(closed_step_bf16), ksteps, 3, flush, stream)
+        tl = torch.tensor([ms_loop.sum(), ms_loop_bf.sum()], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tl, op=dist.ReduceOp.MAX)
         extra["closed_loop_step"] = {
@@ -412,6 +438,9 @@ def run_ours(args):
             "env_steps_per_s": n_step * world * ksteps / (float(tl[0]) * 1e-3),
             "ms_per_step": float(tl[0]) / ksteps, "gpu_launches_per_step": 5, "cuda_graph": not args.no_graph,
             "finite_actions": bool(torch.isfinite(act_buf).all().item()),
+            "bf16_observation": {"env_steps_per_s": n_step * world * ksteps / (float(tl[1]) * 1e-3),
+                                 "ms_per_step": float(tl[1]) / ksteps,
+                                 "how": "rover_height_scan_obs writes the bf16 mirror, rover_policy_forward_bf16 reads it"},
         }
     except Exception as e:
         extra["closed_loop_step"] = {"error": f"{type(e).__name__}: {e}"}

@@ -87,6 +87,17 @@ int rover_height_scan(const float* pos_w, const float* quat_w, int32_t n_envs, c
                       const RoverPlaneCells* cells /* host */, float max_distance, float base_offset,
                       float* out_heights, int32_t out_stride, float* out_hits_w, int32_t variant, void* stream);
 
+/* The observation variant of the height scan (B200-native addition, no counterpart in the reference): obs is the fp32
+ * observation buffer [n_envs, obs_stride] whose columns [0, head_cols) were written by rover_mdp_post_step; the heights
+ * go to columns [head_cols, head_cols + n_rays), and obs_bf16 [n_envs, bf16_stride] receives the bf16 (round to nearest
+ * even) mirror of columns [0, head_cols + n_rays) -- the operand of rover_policy_forward_bf16 / rover_value_forward_bf16.
+ * Runs as variant 5 with the extra stores when the table has a planar copy and n_rays <= 1024, else as the best
+ * applicable variant followed by one conversion pass.  Heights are exactly those of rover_height_scan. */
+int rover_height_scan_obs(const float* pos_w, const float* quat_w, int32_t n_envs, const float* ray_starts_local,
+                          int32_t n_rays, const float* pattern_box /* host */, const RoverScanGrid* grid /* host */,
+                          const RoverPlaneCells* cells /* host */, float max_distance, float base_offset, float* obs,
+                          int32_t obs_stride, int32_t head_cols, uint16_t* obs_bf16, int32_t bf16_stride, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Fused MDP step.  Replaces, in one launch:
  *   AckermannAction2.process_actions/apply_actions/ackermann  rover_envs/mdp/actions/ackermann_actions.py:226-322

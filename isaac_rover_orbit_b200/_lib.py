@@ -20,7 +20,8 @@ STATS_LEN = 16
 MDP_BLOCK = 64
 ABI_VERSION = 2
 
-SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_mdp_pre_step", "rover_mdp_post_step",
+SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_height_scan_obs", "rover_mdp_pre_step",
+           "rover_mdp_post_step",
            "rover_ackermann",
            "rover_policy_pack", "rover_policy_forward", "rover_value_forward", "rover_policy_forward_bf16",
            "rover_value_forward_bf16", "rover_gaussian_act")
@@ -115,6 +116,9 @@ def load() -> C.CDLL:
     lib.rover_ackermann.argtypes = [vp, i32, C.POINTER(MdpParams), vp, vp, vp, vp]
     lib.rover_policy_pack.restype = C.c_int64
     lib.rover_policy_pack.argtypes = [C.POINTER(PolicyWeights), vp, vp]
+    lib.rover_height_scan_obs.restype = C.c_int
+    lib.rover_height_scan_obs.argtypes = [vp, vp, i32, vp, i32, C.POINTER(C.c_float * 4), C.POINTER(ScanGrid),
+                                          C.POINTER(PlaneCells), f32, f32, vp, i32, i32, vp, i32, vp]
     lib.rover_policy_forward.restype = C.c_int
     lib.rover_policy_forward.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.rover_value_forward.restype = C.c_int

@@ -10,6 +10,8 @@
 //     triangles can cover the ray's cell; a record test is 8 FMAs (3 edge functions + plane);
 //   * closest hit along (0,0,-1) == highest z with 0 <= Z - z < max_distance;
 //   * heights are written coalesced (consecutive threads = consecutive rays of one env).
+#include <cuda_bf16.h>
+
 #include "scan_common.cuh"
 
 namespace rover {
@@ -176,8 +178,19 @@ int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_
 
 int launch_height_scan_paired(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local, int n_rays,
                               const ScanGridDev& g, const RoverPlaneCells* cells, float4 pattern_box, float max_d,
-                              float base_offset, float* out, int out_stride, float* hits,
-                              cudaStream_t stream);  // height_scan_paired.cu
+                              float base_offset, float* out, int out_stride, float* hits, uint16_t* obs_bf16,
+                              int bf16_stride, int head_cols, cudaStream_t stream);  // height_scan_paired.cu
+
+// fallback of rover_height_scan_obs when variant 5 cannot run: mirror obs[:, 0:cols] into bf16
+__global__ void obs_to_bf16_kernel(const float* __restrict__ obs, int obs_stride, int n_envs, int cols,
+                                   __nv_bfloat16* __restrict__ dst, int dst_stride) {
+    const size_t total = (size_t)n_envs * cols;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = k / cols;
+        const int c = (int)(k - e * cols);
+        dst[e * dst_stride + c] = __float2bfloat16_rn(obs[e * obs_stride + c]);
+    }
+}
 
 }  // namespace rover
 
@@ -218,7 +231,7 @@ extern "C" int rover_height_scan(const float* pos_w, const float* quat_w, int32_
             ROVER_CHECK(pattern_box != nullptr, "rover_height_scan: variant 5 needs pattern_box (host, 4 floats)");
             const float4 box = make_float4(pattern_box[0], pattern_box[1], pattern_box[2], pattern_box[3]);
             return launch_height_scan_paired(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, cells, box,
-                                             max_distance, base_offset, out_heights, out_stride, out_hits_w, s);
+                                             max_distance, base_offset, out_heights, out_stride, out_hits_w, nullptr, 0, 0, s);
         }
         if (variant >= 4 && n_rays <= 1024) {
             ROVER_CHECK(pattern_box != nullptr, "rover_height_scan: variant 4 needs pattern_box (host, 4 floats)");
@@ -240,4 +253,40 @@ extern "C" int rover_height_scan(const float* pos_w, const float* quat_w, int32_
         return check_launch("height_scan_cells_kernel");
     }
     return fail("rover_height_scan: unknown variant %d", variant);
+}
+
+extern "C" int rover_height_scan_obs(const float* pos_w, const float* quat_w, int32_t n_envs,
+                                     const float* ray_starts_local, int32_t n_rays, const float* pattern_box,
+                                     const RoverScanGrid* grid, const RoverPlaneCells* cells, float max_distance,
+                                     float base_offset, float* obs, int32_t obs_stride, int32_t head_cols,
+                                     uint16_t* obs_bf16, int32_t bf16_stride, void* stream) {
+    using namespace rover;
+    ROVER_CHECK(n_envs >= 0 && n_rays >= 0 && head_cols >= 0, "rover_height_scan_obs: negative sizes");
+    if (n_envs == 0) return 0;
+    ROVER_CHECK(obs && obs_bf16, "rover_height_scan_obs: NULL observation buffer");
+    ROVER_CHECK(obs_stride >= head_cols + n_rays && bf16_stride >= head_cols + n_rays,
+                "rover_height_scan_obs: row strides %d / %d < head_cols + n_rays = %d", obs_stride, bf16_stride,
+                head_cols + n_rays);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool fused = cells != nullptr && cells->entries_planar != nullptr && n_rays >= 1 && n_rays <= 1024 &&
+                       head_cols <= 32 && pattern_box != nullptr;
+    if (fused) {
+        ROVER_CHECK(pos_w && quat_w && ray_starts_local, "rover_height_scan_obs: NULL tensor");
+        ROVER_CHECK(cells->xs && cells->ys && cells->entries && cells->nx > 0 && cells->ny > 0,
+                    "rover_height_scan_obs: bad plane-cell table");
+        ScanGridDev g;
+        if (int rc = make_dev_grid(grid, g)) return rc;
+        const float4 box = make_float4(pattern_box[0], pattern_box[1], pattern_box[2], pattern_box[3]);
+        return launch_height_scan_paired(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, cells, box, max_distance,
+                                         base_offset, obs + head_cols, obs_stride, nullptr, obs_bf16, bf16_stride, head_cols,
+                                         s);
+    }
+    // any other table / pattern: the best variant that applies, then one conversion pass
+    const int variant = cells != nullptr ? (pattern_box != nullptr ? 3 : 2) : 0;
+    if (int rc = rover_height_scan(pos_w, quat_w, n_envs, ray_starts_local, n_rays, pattern_box, grid, cells, max_distance,
+                                   base_offset, obs + head_cols, obs_stride, nullptr, variant, stream))
+        return rc;
+    obs_to_bf16_kernel<<<1184, 256, 0, s>>>(obs, obs_stride, n_envs, head_cols + n_rays,
+                                            reinterpret_cast<__nv_bfloat16*>(obs_bf16), bf16_stride);
+    return check_launch("obs_to_bf16_kernel");
 }

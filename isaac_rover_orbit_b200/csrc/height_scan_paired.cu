@@ -20,6 +20,8 @@
 //     the prologue issues all of its global loads before the first store (one cold-miss latency instead of three).
 // Rays in general cells, cell guesses that miss, windows that do not fit or do not cover (non-uniform lattices) take
 // the same out-of-line global-memory helpers as variant 4, so the staging can never change a result.
+#include <cuda_bf16.h>
+
 #include "scan_pipe.cuh"
 
 #ifndef ROVER_SCAN_DBG
@@ -190,7 +192,8 @@ struct PairCtx {
 // general cell.  Out of line so that it does not raise the register pressure of the consumer loop.
 __device__ __noinline__ void pair_resolve_deferred_ray(const PairSmem* sm, const PairStage* st, const ScanGridDev& g,
                                                        float inv_dx, float inv_dy, float X, float Y, float Z, float pz,
-                                                       float max_d, float base_offset, float* __restrict__ out) {
+                                                       float max_d, float base_offset, float* __restrict__ out,
+                                                       __nv_bfloat16* __restrict__ out_bf) {
     const PairHeader& h = st->hdr;
     const int cmax = h.ncols - 1, rmax = h.nrows - 1;
     const LinePair2* xp = sm->xpair + h.ic0;
@@ -210,6 +213,7 @@ __device__ __noinline__ void pair_resolve_deferred_ray(const PairSmem* sm, const
                             : walk_home_grid(g, X, Y, Z, max_d);
     }
     store_result(pz, X, Y, Z, zhit, base_offset, out, nullptr);
+    if (out_bf != nullptr) *out_bf = __float2bfloat16_rn(*out);
 }
 
 // Rare path (b): a chunk of an environment whose window is not staged (too large, not covered on a non-uniform
@@ -217,7 +221,8 @@ __device__ __noinline__ void pair_resolve_deferred_ray(const PairSmem* sm, const
 __device__ __noinline__ void pair_resolve_chunk_from_global(const PairSmem* sm, int lane, int r_begin, int r_end,
                                                             const PairHeader h, const ScanGridDev& g,
                                                             const PlaneCellsDev& pc, float max_d, float base_offset,
-                                                            float* __restrict__ out_row) {
+                                                            float* __restrict__ out_row,
+                                                            __nv_bfloat16* __restrict__ bf_row) {
     const float sz2 = __fmul_rn(h.sz, 2.f);
     for (int r = r_begin + lane; r < r_end; r += 32) {
         const int sl = slot_of_ray(r);
@@ -227,6 +232,7 @@ __device__ __noinline__ void pair_resolve_chunk_from_global(const PairSmem* sm, 
         const float Y = __fadd_rn(__fadd_rn(__fadd_rn(vy, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
         const float Z = __fadd_rn(sm->vz[sl], h.pz);
         store_result(h.pz, X, Y, Z, resolve_from_global(g, pc, X, Y, Z, max_d), base_offset, out_row + r, nullptr);
+        if (bf_row != nullptr) bf_row[r] = __float2bfloat16_rn(out_row[r]);
     }
 }
 
@@ -234,10 +240,12 @@ __device__ __noinline__ void pair_resolve_chunk_from_global(const PairSmem* sm, 
 // Returns a 2-bit mask of the rays that need the rare path.
 // kFull: the whole batch lies inside the pattern (no per-ray validity predicates); kFlatZ: every ray starts at the
 // same local z (grid patterns), so Z is a per-environment constant.
-template <bool kFull, bool kFlatZ>
+// kBf: the heights are also stored as bf16 (round to nearest even) at ob[0] / ob[64] -- the observation mirror that
+// feeds rover_policy_forward_bf16.
+template <bool kFull, bool kFlatZ, bool kBf>
 __device__ __forceinline__ unsigned resolve_pair(const unsigned char* __restrict__ smem, const PairSmem& sm,
                                                  const PairCtx& c, int slot, int ray_a, int n_rays,
-                                                 float* __restrict__ o) {
+                                                 float* __restrict__ o, __nv_bfloat16* __restrict__ ob) {
     const bool valid0 = kFull || ray_a < n_rays, valid1 = kFull || ray_a + 64 < n_rays;
     const int idx = slot;  // slots beyond the pattern hold zeros
     const f32x2 VX = *reinterpret_cast<const f32x2*>(sm.vx + idx);
@@ -289,6 +297,10 @@ __device__ __forceinline__ unsigned resolve_pair(const unsigned char* __restrict
     const float h1 = (t1 >= 0.f && t1 < c.max_d) ? hi_of(H) : -INFINITY;
     if (keep[0]) o[0] = h0;
     if (keep[1]) o[64] = h1;
+    if (kBf) {
+        if (keep[0]) ob[0] = __float2bfloat16_rn(h0);
+        if (keep[1]) ob[64] = __float2bfloat16_rn(h1);
+    }
     return defer;
 }
 
@@ -342,12 +354,16 @@ __device__ __forceinline__ void producer_verdict(ProducerEnv& e, const PairSmem&
     e.ok = ok;
 }
 
+// kBf16: rover_height_scan_obs -- `out` points at column head_cols of the fp32 observation rows; the kernel also
+// writes the bf16 mirror obs_bf16[env, 0 : head_cols + n_rays] (head columns converted from the fp32 row, heights
+// rounded from the values it stores).
+template <bool kBf16>
 __global__ void __launch_bounds__(kPairThreads, 1)
 height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restrict__ quat_w, int n_envs,
                           const float* __restrict__ ray_local, int n_rays, const __grid_constant__ ScanGridDev g,
                           const __grid_constant__ PlaneCellsDev pc, const __grid_constant__ CUtensorMap tmap,
                           float pattern_radius, float max_d, float base_offset, float* __restrict__ out,
-                          int out_stride) {
+                          int out_stride, __nv_bfloat16* __restrict__ obs_bf16, int bf16_stride, int head_cols) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairSmem& sm = *reinterpret_cast<PairSmem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -491,7 +507,10 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
             DBG_STAMP(dbg_slot + 1);
             const PairHeader h = st.hdr;
             float* __restrict__ out_row = out + (size_t)env * out_stride;
+            __nv_bfloat16* __restrict__ bf_row = kBf16 ? obs_bf16 + (size_t)env * bf16_stride + head_cols : nullptr;
             const int r_begin = c * kPairChunk, r_end = min(r_begin + kPairChunk, n_rays);
+            if (kBf16 && c == 0 && lane < head_cols)  // the head of the observation (written by the post-step kernel)
+                bf_row[lane - head_cols] = __float2bfloat16_rn(out_row[lane - head_cols]);
             if (ROVER_SCAN_DBG == 1) {
             } else if (h.mode == 1) {
                 PairCtx cx;
@@ -511,13 +530,16 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
                 for (int b0 = r_begin; b0 < r_end; b0 += kPairChunk / 2) {
                     const int r = b0 + lane;  // rays r, r + 64 (slot 0) and r + 32, r + 96 (slot 1)
                     float* __restrict__ o = out_row + r;
+                    __nv_bfloat16* __restrict__ ob = kBf16 ? bf_row + r : nullptr;
                     unsigned defer;
                     if (flat_z && b0 + kPairChunk / 2 <= n_rays) {
-                        defer = resolve_pair<true, true>(smem_raw, sm, cx, b0 + 2 * lane, r, n_rays, o);
-                        defer |= resolve_pair<true, true>(smem_raw, sm, cx, b0 + 64 + 2 * lane, r + 32, n_rays, o + 32) << 2;
+                        defer = resolve_pair<true, true, kBf16>(smem_raw, sm, cx, b0 + 2 * lane, r, n_rays, o, ob);
+                        defer |= resolve_pair<true, true, kBf16>(smem_raw, sm, cx, b0 + 64 + 2 * lane, r + 32, n_rays, o + 32,
+                                                                 ob + 32) << 2;
                     } else {
-                        defer = resolve_pair<false, false>(smem_raw, sm, cx, b0 + 2 * lane, r, n_rays, o);
-                        defer |= resolve_pair<false, false>(smem_raw, sm, cx, b0 + 64 + 2 * lane, r + 32, n_rays, o + 32) << 2;
+                        defer = resolve_pair<false, false, kBf16>(smem_raw, sm, cx, b0 + 2 * lane, r, n_rays, o, ob);
+                        defer |= resolve_pair<false, false, kBf16>(smem_raw, sm, cx, b0 + 64 + 2 * lane, r + 32, n_rays, o + 32,
+                                                                   ob + 32) << 2;
                     }
                     // rare: cell guess off by one, ray on the closed far border or outside the grid, general cell
                     if (defer != 0u) {
@@ -530,12 +552,13 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
                             const float X = __fadd_rn(__fadd_rn(__fadd_rn(vx, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
                             const float Y = __fadd_rn(__fadd_rn(__fadd_rn(vy, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
                             pair_resolve_deferred_ray(&sm, &st, g, pc.inv_dx, pc.inv_dy, X, Y, __fadd_rn(sm.vz[sl], h.pz),
-                                                      h.pz, max_d, base_offset, out_row + rr);
+                                                      h.pz, max_d, base_offset, out_row + rr,
+                                                      kBf16 ? bf_row + rr : nullptr);
                         }
                     }
                 }
             } else {
-                pair_resolve_chunk_from_global(&sm, lane, r_begin, r_end, h, g, pc, max_d, base_offset, out_row);
+                pair_resolve_chunk_from_global(&sm, lane, r_begin, r_end, h, g, pc, max_d, base_offset, out_row, bf_row);
             }
             __syncwarp();
             DBG_STAMP(dbg_slot + 2);
@@ -558,23 +581,30 @@ int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_
                                  float max_d, float base_offset, float* out, int out_stride, float* hits,
                                  cudaStream_t stream);
 
+// obs_bf16 != nullptr: `out` is column head_cols of the fp32 observation rows and the bf16 mirror is written as well
+// (rover_height_scan_obs); the caller has checked that variant 5 can run (planar table, pattern size, no hit output).
 int launch_height_scan_paired(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local, int n_rays,
                               const ScanGridDev& g, const RoverPlaneCells* cells, float4 pattern_box, float max_d,
-                              float base_offset, float* out, int out_stride, float* hits, cudaStream_t stream) {
+                              float base_offset, float* out, int out_stride, float* hits, uint16_t* obs_bf16,
+                              int bf16_stride, int head_cols, cudaStream_t stream) {
     // hit positions are a debugging / test output: served by variant 4's kernel (same heights, same table); so is a
     // table without the planar copy
-    if (hits != nullptr || cells->entries_planar == nullptr)
+    if (obs_bf16 == nullptr && (hits != nullptr || cells->entries_planar == nullptr))
         return launch_height_scan_pipelined(pos_w, quat_w, n_envs, ray_local, n_rays, g, cells, pattern_box, max_d,
                                             base_offset, out, out_stride, hits, stream);
     ROVER_CHECK(n_rays >= 1 && n_rays <= kPairMaxRays, "height_scan_paired: pattern of %d rays (1..%d supported)", n_rays,
                 kPairMaxRays);
+    ROVER_CHECK(cells->entries_planar != nullptr && hits == nullptr, "height_scan_paired: bf16 mirror needs the planar table");
+    ROVER_CHECK(head_cols >= 0 && head_cols <= 32, "height_scan_paired: head_cols %d out of range", head_cols);
     static int n_sms = 0;
     static bool configured = false;
     if (!configured) {
         int dev = 0;
         ROVER_CUDA(cudaGetDevice(&dev));
         ROVER_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-        ROVER_CUDA(cudaFuncSetAttribute(height_scan_paired_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ROVER_CUDA(cudaFuncSetAttribute(height_scan_paired_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(PairSmem)));
+        ROVER_CUDA(cudaFuncSetAttribute(height_scan_paired_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(PairSmem)));
         configured = true;
     }
@@ -586,8 +616,13 @@ int launch_height_scan_paired(const float* pos_w, const float* quat_w, int n_env
     const float rx = fmaxf(fabsf(pattern_box.x), fabsf(pattern_box.y)), ry = fmaxf(fabsf(pattern_box.z), fabsf(pattern_box.w));
     const float radius = sqrtf(rx * rx + ry * ry) * 1.0001f + 1.0e-3f;
     const int grid = n_envs < n_sms ? n_envs : n_sms;
-    height_scan_paired_kernel<<<grid, kPairThreads, sizeof(PairSmem), stream>>>(
-        pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, tmap, radius, max_d, base_offset, out, out_stride);
+    if (obs_bf16 != nullptr)
+        height_scan_paired_kernel<true><<<grid, kPairThreads, sizeof(PairSmem), stream>>>(
+            pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, tmap, radius, max_d, base_offset, out, out_stride,
+            reinterpret_cast<__nv_bfloat16*>(obs_bf16), bf16_stride, head_cols);
+    else
+        height_scan_paired_kernel<false><<<grid, kPairThreads, sizeof(PairSmem), stream>>>(
+            pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, tmap, radius, max_d, base_offset, out, out_stride, nullptr, 0, 0);
     return check_launch("height_scan_paired_kernel");
 }
 

@@ -133,6 +133,28 @@ def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridH
 # ------------------------------------------------------------------------------------------------------
 # fused MDP step
 # ------------------------------------------------------------------------------------------------------
+def height_scan_obs(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle, obs: torch.Tensor,
+                    obs_bf16: torch.Tensor, head_cols: int = 4, max_distance: float = 100.0,
+                    base_offset: float = 0.26878) -> None:
+    """Height scan into the observation buffers of the closed loop: heights -> ``obs[:, head_cols:head_cols + R]``
+    (fp32) and the bf16 mirror of ``obs[:, :head_cols + R]`` -> ``obs_bf16`` (``policy.alloc_obs_bf16``), the operand
+    of ``GaussianNeuralNetwork.compute_bf16``.  One launch (variant 5 with the extra stores)."""
+    if not isinstance(rays, RayPattern):
+        rays = RayPattern(rays, pos_w.device)
+    _lib.require_cuda(pos_w, quat_w)  # obs / obs_bf16 are row-strided views: checked below
+    n = pos_w.shape[0]
+    if (not obs.is_cuda or obs.dtype != torch.float32 or obs.shape[0] != n or obs.stride(1) != 1 or obs.shape[1] < head_cols + rays.n_rays
+            or obs_bf16.dtype != torch.bfloat16 or obs_bf16.shape[0] != n or obs_bf16.stride(1) != 1
+            or obs_bf16.shape[1] < head_cols + rays.n_rays or not obs_bf16.is_cuda):
+        raise RuntimeError("height_scan_obs: obs must be fp32 and obs_bf16 bf16, both [N, >= head_cols + R] with unit inner stride")
+    dev = pos_w.device
+    _lib.check(_lib.load().rover_height_scan_obs(
+        _lib.ptr(pos_w), _lib.ptr(quat_w), n, _lib.ptr(rays.starts), rays.n_rays, C.byref(rays.box),
+        C.byref(grid.struct), C.byref(grid.cells_struct) if grid.cells_struct is not None else None,
+        float(max_distance), float(base_offset), C.c_void_p(obs.data_ptr()), int(obs.stride(0)), int(head_cols),
+        C.c_void_p(obs_bf16.data_ptr()), int(obs_bf16.stride(0)), _lib.current_stream(dev)))
+
+
 def mdp_params(cfg: RoverEnvCfg) -> _lib.MdpParams:
     a = cfg.actions
     p = _lib.MdpParams()

@@ -129,7 +129,10 @@ class GaussianNeuralNetwork(_RoverNetwork):
 
     # ---- skrl Model API
     def compute(self, inputs: dict, role: str = "actor"):
-        """models.py:89-102: ``(mean [N,2], log_std_parameter [2], {})`` for ``inputs["states"] [N,965]``."""
+        """models.py:89-102: ``(mean [N,2], log_std_parameter [2], {})`` for ``inputs["states"] [N,965]``.
+        A bf16 observation (``alloc_obs_bf16`` layout) is routed to ``compute_bf16``."""
+        if inputs["states"].dtype == torch.bfloat16:
+            return self.compute_bf16(inputs, role)
         return self._forward(inputs["states"], "rover_policy_forward"), self.log_std_parameter, {}
 
     def compute_bf16(self, inputs: dict, role: str = "actor"):
@@ -161,6 +164,8 @@ class DeterministicNeuralNetwork(_RoverNetwork):
     _HAS_LOG_STD = False
 
     def compute(self, inputs: dict, role: str = "actor"):
+        if inputs["states"].dtype == torch.bfloat16:
+            return self.compute_bf16(inputs, role)
         return self._forward(inputs["states"], "rover_value_forward"), {}
 
     def compute_bf16(self, inputs: dict, role: str = "actor"):

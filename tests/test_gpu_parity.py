@@ -195,6 +195,43 @@ def test_height_scan_variant5_without_planar_table_runs_as_variant4(cuda_device)
     assert torch.equal(h, ref)
 
 
+@pytest.mark.parametrize("case", ["fused (variant 5 with the extra stores)", "fallback (no planar table)",
+                                  "fallback (cells too small for a window)"])
+def test_height_scan_obs_writes_fp32_heights_and_bf16_mirror(cuda_device, case):
+    """rover_height_scan_obs: the fp32 heights are exactly rover_height_scan's, the bf16 buffer is the round-to-nearest
+    mirror of obs[:, :4 + R] (head columns included), nothing else is touched -- on the fused path, on the generic
+    fallback, and with border envs whose rays miss (-inf) or take the deferred path."""
+    if case.endswith("window)"):
+        v, f = _heightfield_mesh(300, 300, 0.05, 0.05, 6)
+        span = 15.0
+    else:
+        v, f = _heightfield_mesh(150, 150, 0.2, 0.2, 5)
+        span = 30.0
+    grid = ops.ScanGridHandle.from_mesh(v, f, cuda_device)
+    gen = torch.Generator().manual_seed(13)
+    n = 333
+    pos = torch.cat([torch.rand(n, 2, generator=gen) * (span + 2.0) - 1.0, torch.rand(n, 1, generator=gen) + 0.5], 1).to(cuda_device)
+    quat = synthetic.quat_from_euler(torch.zeros(n), torch.zeros(n), (torch.rand(n, generator=gen) * 2 - 1) * np.pi).to(cuda_device)
+    rays = ops.RayPattern.grid(cuda_device)
+    ref = ops.height_scan(pos, quat, rays, grid, variant=2)
+    assert torch.isinf(ref).any() and torch.isfinite(ref).any()
+    obs = torch.full((n, 968), 7.0, device=cuda_device)
+    obs[:, :4] = torch.randn(n, 4, generator=gen).to(cuda_device)
+    head = obs[:, :4].clone()
+    obs_bf = torch.full((n, 968), 9.0, dtype=torch.bfloat16, device=cuda_device)
+    saved = grid.cells_struct.entries_planar
+    if case.startswith("fallback (no planar"):
+        grid.cells_struct.entries_planar = None
+    try:
+        ops.height_scan_obs(pos, quat, rays, grid, obs[:, :965], obs_bf[:, :965])
+    finally:
+        grid.cells_struct.entries_planar = saved
+    torch.cuda.synchronize()
+    assert torch.equal(obs[:, 4:965], ref) and torch.equal(obs[:, :4], head) and bool((obs[:, 965:] == 7.0).all())
+    assert torch.equal(obs_bf[:, :965], obs[:, :965].to(torch.bfloat16))
+    assert bool((obs_bf[:, 965:] == 9.0).all())
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_height_scan_max_distance_and_empty(cuda_device, variant):
     v = np.array([[-5, -5, -95.0], [5, -5, -95.0], [0, 5, -95.0]], dtype=np.float32)

@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 import torch
 
-from isaac_rover_orbit_b200.policy import DeterministicNeuralNetwork, GaussianNeuralNetwork, WEIGHT_KEYS, alloc_obs
+from isaac_rover_orbit_b200.policy import (DeterministicNeuralNetwork, GaussianNeuralNetwork, WEIGHT_KEYS, alloc_obs,
+                                            alloc_obs_bf16)
 
 pytestmark = pytest.mark.gpu
 
@@ -159,3 +160,30 @@ def test_value_forward_reference_checkpoint(cuda_device, golden_dir, kernel, mon
     # same arithmetic, different fp32 summation order inside the MMAs; bf16 re-rounding of the activations amplifies
     # it: 4e-3 of the output range (the policy test uses 4e-3 on tanh outputs in [-1, 1])
     torch.testing.assert_close(vb.cpu(), emu, rtol=0, atol=4e-3 * max(float(emu.abs().max()), 1.0))
+
+
+@pytest.mark.parametrize("n", [1, 129, 3000, 18944 + 5])
+def test_bf16_observation_path_is_bit_identical(cuda_device, golden, golden_dir, n):
+    """rover_policy_forward_bf16 / rover_value_forward_bf16: the SWIZZLE_128B TMA tile of the bf16 observation is the
+    MMA operand; the fp32 entry points round the same observation to the same bf16 values, so the outputs are equal
+    bit for bit -- also when the column the reference drops (964) holds -inf (a missed ray)."""
+    from oracle import policy as OP
+
+    _, sd = golden
+    pol = GaussianNeuralNetwork(device=cuda_device)
+    pol.load_state_dict(sd)
+    val = DeterministicNeuralNetwork(device=cuda_device)
+    val.load_state_dict(OP.load_golden_weights(np.load(os.path.join(golden_dir, "value.npz"))))
+    g = torch.Generator().manual_seed(200 + n)
+    obs = alloc_obs(n, cuda_device)
+    obs.copy_((torch.randn(n, 965, generator=g) * 0.4).to(cuda_device))
+    ob = alloc_obs_bf16(n, cuda_device)
+    ob.copy_(obs)
+    ob[:, 964] = float("-inf")
+    for net in (pol, val):
+        a = net.compute({"states": obs})[0]
+        b = net.compute_bf16({"states": ob})[0]
+        torch.cuda.synchronize()
+        assert torch.equal(a, b) and torch.isfinite(b).all(), type(net).__name__
+    with pytest.raises(RuntimeError):
+        pol.compute_bf16({"states": obs})  # fp32 tensor on the bf16 entry point
