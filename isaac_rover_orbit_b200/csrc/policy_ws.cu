@@ -26,6 +26,7 @@ namespace rover {
 
 #if ROVER_POLICY_DBG
 __device__ long long g_pol_dbg[2048];
+__device__ unsigned long long g_pol_cta[2][256];  // globaltimer (ns) at CTA start / end
 #define PDBG(slot)                                                                     \
     do {                                                                               \
         if (blockIdx.x == 0 && (slot) < 2048) g_pol_dbg[slot] = clock64() - dbg_t0;    \
@@ -168,6 +169,11 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
     unsigned char* const w0_ring = kBf16In ? &sm.a_bf16[0][0] : &sm.w0[0][0];
 #if ROVER_POLICY_DBG
     const long long dbg_t0 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x < 256) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_pol_cta[0][blockIdx.x] = t;
+    }
 #endif
 
     if (tid == 8 * 32) {
@@ -289,9 +295,15 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
             }
         }
     } else if (warp >= 4 && kBf16In) {
-        // bf16-observation mode: no conversion stage, these warps idle
+        // bf16-observation mode: no conversion stage; these warps only pull the packed weights into L2
+        for (int off = (tid - 128) * 128; off < kPackedBytes; off += 128 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(packed + off));
     } else if (warp >= 4) {
         // =============================================================== converters: fp32 stage -> bf16 A operand
+        // first the packed weights into L2 (326 KB; after an L2 flush every layer's first load was a cold miss that the
+        // layer group waited for: 21 k instead of 13 k cycles for the first tile)
+        for (int off = (tid - 128) * 128; off < kPackedBytes; off += 128 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(packed + off));
         const int row = tid - 128;  // tile row
         const int sx = row & 7;     // SWIZZLE_128B: 16-byte unit u of row r sits at unit u ^ (r & 7)
         int sf = 0, sa = 0;
@@ -484,6 +496,13 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
+#if ROVER_POLICY_DBG
+    if (threadIdx.x == 0 && blockIdx.x < 256) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_pol_cta[1][blockIdx.x] = t;
+    }
+#endif
 }
 
 typedef CUresult (*WsEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -544,5 +563,8 @@ int launch_policy_forward_ws(const void* obs, int obs_stride, int n_envs, const 
 #if ROVER_POLICY_DBG
 extern "C" int rover_debug_policy_timeline(long long* host_dst) {
     return (int)cudaMemcpyFromSymbol(host_dst, rover::g_pol_dbg, sizeof(rover::g_pol_dbg));
+}
+extern "C" int rover_debug_policy_ctas(unsigned long long* host_dst) {
+    return (int)cudaMemcpyFromSymbol(host_dst, rover::g_pol_cta, sizeof(rover::g_pol_cta));
 }
 #endif

@@ -9,13 +9,17 @@ sys.path.insert(0, ".")
 from isaac_rover_orbit_b200 import _lib  # noqa: E402
 
 _lib.LIB_PATH = sys.argv[1]
-from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork, alloc_obs  # noqa: E402
+from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork, alloc_obs, alloc_obs_bf16  # noqa: E402
 
 dev = torch.device("cuda:0")
 net = GaussianNeuralNetwork(device=dev)
 obs = alloc_obs(65536, dev)
 obs.copy_(torch.randn(65536, 965, device=dev) * 0.3)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+if len(sys.argv) > 2 and sys.argv[2] == "bf16":  # the bf16-observation mode (16 chunks of 64 columns per tile)
+    ob = alloc_obs_bf16(65536, dev)
+    ob.copy_(obs)
+    obs = ob
 for _ in range(3):
     flush.fill_(1)
     net.compute({"states": obs})
@@ -23,7 +27,7 @@ torch.cuda.synchronize()
 lib = C.CDLL(_lib.LIB_PATH)
 t = np.zeros(2048, dtype=np.int64)
 assert lib.rover_debug_policy_timeline(t.ctypes.data_as(C.c_void_p)) == 0
-n = 124
+n = 64 if obs.dtype == torch.bfloat16 else 124
 print("producer issue      :", t[0:n:4].tolist())
 print("converter got data  :", t[128:128 + n:4].tolist())
 print("converter got A slot:", t[256:256 + n:4].tolist())
@@ -37,3 +41,10 @@ names = ["begin", "D0 ready", "epi0+MMA1 issued", "MMA1 done", "epi1+MMA2 issued
 for i in range(4):
     row = t[1024 + 16 * i:1024 + 16 * i + 14]
     print(f"layer group tile {i}:", {nm: int(v) for nm, v in zip(names, row)})
+cta = np.zeros((2, 256), dtype=np.uint64)
+assert lib.rover_debug_policy_ctas(cta.ctypes.data_as(C.c_void_p)) == 0
+st, en = cta[0, :148].astype(np.int64), cta[1, :148].astype(np.int64)
+t0 = st.min()
+dur = en - st
+print(f"CTA starts spread {int((st - t0).max())} ns; kernel span (first start -> last end) {int(en.max() - t0)} ns; CTA durations min/median/max "
+      f"{int(dur.min())}/{int(np.median(dur))}/{int(dur.max())} ns; CTA 0: {int(dur[0])} ns for {int(t[1024 + 16 * 3 + 13])} cycles")
