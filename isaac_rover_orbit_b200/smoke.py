@@ -82,8 +82,31 @@ def run(n: int = 64, size_m: float = 48.0, seed: int = 7) -> dict:
     torch.testing.assert_close(buf.reward.cpu(), out.reward, rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(buf.joint_vel.cpu(), out.joint_vel, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(obs[:, :4].cpu(), out.obs_head, rtol=1e-5, atol=1e-5)
+    # ---- policy forward on the tensor cores (tcgen05), on the observation just produced, vs the fp32 oracle network
+    from oracle import policy as OP
+
+    from .policy import GaussianNeuralNetwork, alloc_obs, alloc_obs_bf16
+
+    net = GaussianNeuralNetwork(device=dev)
+    g2 = torch.Generator().manual_seed(seed + 1)
+    sd = {k: torch.randn(t.shape, generator=g2) * (0.05 if t.dim() == 2 else 0.01) for k, t in net.state_dict().items()}
+    net.load_state_dict(sd)
+    pobs = alloc_obs(n, dev)
+    pobs.copy_(obs.nan_to_num(0.0, 0.0, 0.0))  # rays that miss are -inf: keep the comparison finite
+    mean = net.compute({"states": pobs})[0]
+    pobs_bf = alloc_obs_bf16(n, dev)
+    ops.height_scan_obs(d.root_pos_w, d.root_quat_w, rays, grid, pobs.clone(), pobs_bf)  # exercises the bf16 mirror
+    pobs_bf.copy_(pobs)
+    mean_bf = net.compute({"states": pobs_bf})[0]
+    torch.cuda.synchronize()
+    ref_mean = OP.policy_mean(pobs.cpu(), sd)
+    pol_err = (mean.cpu() - ref_mean).abs().max().item()
+    if pol_err > 3e-2:  # bf16 operands vs the fp32 reference network (tests/test_gpu_policy.py uses the same bound)
+        raise AssertionError(f"smoke: policy forward differs from the fp32 oracle by {pol_err}")
+    if not torch.equal(mean, mean_bf):
+        raise AssertionError("smoke: bf16-observation policy path differs from the fp32-observation path")
     return {"n_envs": n, "rays": int(h_ref.numel()), "scan_max_abs_err": err,
-            "resets": int(out.stats["num_resets"])}
+            "resets": int(out.stats["num_resets"]), "policy_max_abs_err": pol_err}
 
 
 if __name__ == "__main__":
