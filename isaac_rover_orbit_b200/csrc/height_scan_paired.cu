@@ -412,8 +412,8 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
                       "vx, vy, vz are filled as one array");
         float* pat_flat = sm.vx;
         float pat[kPatLoads], xl[kLineLoads], xh[kLineLoads], yl[kLineLoads], yh[kLineLoads];
-#pragma unroll
         const float vz0 = __ldg(ray_local + 2);
+#pragma unroll
         for (int k = 0; k < kPatLoads; ++k) {  // i = component * kPairMaxRays + slot (vx, vy, vz are contiguous)
             const int i = ct + k * kFill;
             const int comp = i / kPairMaxRays, r = ray_of_slot(i - comp * kPairMaxRays);
