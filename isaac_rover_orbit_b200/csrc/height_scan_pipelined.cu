@@ -203,7 +203,7 @@ height_scan_pipelined_kernel(const float* __restrict__ pos_w, const float* __res
             const float sz2 = __fmul_rn(h.sz, 2.f);  // fl(fl(sz*v)*2) == fl(fl(2*sz)*v): scaling by 2 is exact
             if (h.mode == 1) {
                 const int cmax = h.ncols - 1, rmax = h.nrows - 1;
-                const float wx0 = st.xp[0].lo, wy0 = st.yp[0].lo, wx1 = st.xp[cmax].hi, wy1 = st.yp[rmax].hi;
+                const float wx0 = st.xp[0].lo, wy0 = st.yp[0].lo;
                 const float inv_dx = pc.inv_dx, inv_dy = pc.inv_dy;
                 for (int r0 = 0; r0 < n_rays; r0 += kPipeRaysPerThread * kPipeConsumers) {
                     // branch-free body over 4 rays: every load uses a clamped (always valid) index, stores are
