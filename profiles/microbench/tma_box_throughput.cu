@@ -100,7 +100,11 @@ int main() {
         int w, h, stages;
         CUtensorMapSwizzle sw;
         const char* name;
+        CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     } cfgs[] = {
+        {32, 128, 5, CU_TENSOR_MAP_SWIZZLE_128B, "32 x 128 rows, swizzle128, 5 stages, L2 promotion 256B", CU_TENSOR_MAP_L2_PROMOTION_L2_256B},
+        {32, 128, 5, CU_TENSOR_MAP_SWIZZLE_128B, "32 x 128 rows, swizzle128, 5 stages, L2 promotion none", CU_TENSOR_MAP_L2_PROMOTION_NONE},
+        {32, 112, 5, CU_TENSOR_MAP_SWIZZLE_128B, "32 x 112 rows (tile 112), 5 stages, L2 promotion 256B", CU_TENSOR_MAP_L2_PROMOTION_L2_256B},
         {32, 128, 5, CU_TENSOR_MAP_SWIZZLE_128B, "32 x 128 rows, swizzle128, 5 stages (policy v2)"},
         {32, 128, 10, CU_TENSOR_MAP_SWIZZLE_128B, "32 x 128 rows, swizzle128, 10 stages"},
         {64, 128, 3, CU_TENSOR_MAP_SWIZZLE_NONE, "64 x 128 rows, 3 stages (policy v1)"},
@@ -121,7 +125,7 @@ int main() {
         const cuuint32_t box[2] = {(cuuint32_t)c.w, (cuuint32_t)c.h};
         const cuuint32_t estr[2] = {1u, 1u};
         CUresult rc = cuTensorMapEncodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d, gdim, gstride, box, estr,
-                                             CU_TENSOR_MAP_INTERLEAVE_NONE, c.sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, c.sw, c.promo,
                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS) {
             printf("%s: encode failed %d\n", c.name, (int)rc);
@@ -136,7 +140,7 @@ int main() {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
             cudaEventRecord(a);
-            stream_kernel<<<148, 64, c.stages * stage_bytes>>>(map, n_rows_run, n_cols, c.w, c.h, 128, c.stages, stage_bytes, sink);
+            stream_kernel<<<148, 64, c.stages * stage_bytes>>>(map, n_rows_run, n_cols, c.w, c.h, c.h == 112 ? 112 : 128, c.stages, stage_bytes, sink);
             cudaEventRecord(b);
             CK(cudaDeviceSynchronize());
             float ms;
