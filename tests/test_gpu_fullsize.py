@@ -1,0 +1,150 @@
+"""GPU, BASELINE.json full sizes: properties that do not need the (slow) oracle at that size.
+
+cfg-2: 4096 envs x 961 rays on the 2,000,000-triangle terrain; cfg-3: 16384 envs through the fused MDP step; cfg-4:
+65536 envs through the policy.  Checked: every kernel variant returns the same bits, repeated launches are
+deterministic, results are equivariant under a permutation of the environments and invariant under q -> -q, the
+episode statistics equal plain torch reductions of the per-env outputs, the reset ranks reproduce
+``reset_buf.nonzero()`` order (index-exact), and a 48-env sample of the full-size scan agrees with the CPU oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+import bench
+from isaac_rover_orbit_b200 import ops, synthetic
+from isaac_rover_orbit_b200.config import RoverEnvCfg
+from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork, alloc_obs, alloc_obs_bf16
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full(cuda_device):
+    v, f, grid, tables = bench.build_world(bench.STEP_ENVS_1GPU, cuda_device, cuda_device)
+    gen = torch.Generator().manual_seed(2024)
+    vt = torch.from_numpy(v)
+    pos, quat = synthetic.make_poses(bench.SCAN_ENVS_PER_GPU, gen, vt, bench.TERRAIN["size_m"], bench.TERRAIN["grid_res"])
+    return dict(v=v, f=f, vt=vt, grid=grid, tables=tables, pos=pos.to(cuda_device), quat=quat.to(cuda_device),
+                rays=ops.RayPattern.grid(cuda_device), dev=cuda_device, gen=gen)
+
+
+def test_scan_cfg2_variants_determinism_and_symmetries(full):
+    pos, quat, rays, grid = full["pos"], full["quat"], full["rays"], full["grid"]
+    assert pos.shape[0] == 4096 and rays.n_rays == 961
+    ref = ops.height_scan(pos, quat, rays, grid, variant=2)
+    assert float(torch.isfinite(ref).float().mean()) > 0.99  # the bench poses keep (nearly) every ray over the terrain
+    for variant in (3, 4, 5):
+        assert torch.equal(ops.height_scan(pos, quat, rays, grid, variant=variant), ref), f"variant {variant}"
+    h1 = ops.height_scan(pos, quat, rays, grid)
+    h2 = ops.height_scan(pos, quat, rays, grid)
+    assert torch.equal(h1, h2) and torch.equal(h1, ref)  # deterministic, default variant included
+    perm = torch.randperm(pos.shape[0], generator=torch.Generator().manual_seed(1)).to(pos.device)
+    assert torch.equal(ops.height_scan(pos[perm].contiguous(), quat[perm].contiguous(), rays, grid), ref[perm])
+    assert torch.equal(ops.height_scan(pos, (-quat).contiguous(), rays, grid), ref)  # q and -q are the same rotation
+    # lifting the sensor by dz lifts every height by dz up to fp32 rounding of (z + dz) - hit - offset
+    up = pos.clone()
+    up[:, 2] += 0.5
+    lifted = ops.height_scan(up, quat, rays, grid)
+    fin = torch.isfinite(ref)
+    assert torch.equal(torch.isfinite(lifted), fin)
+    torch.testing.assert_close(lifted[fin], ref[fin] + 0.5, rtol=0, atol=2e-6)
+    # checksum of checksums: per-env sums (fp64) of two variants agree exactly because the heights do
+    assert torch.equal(h1.double().sum(1), ref.double().sum(1))
+
+
+def test_scan_cfg2_sample_against_oracle(full):
+    from oracle import raycast as oracle_raycast
+    from oracle import step as OS
+
+    idx = torch.arange(0, 4096, 86)[:48]
+    pos, quat = full["pos"][idx.to(full["dev"])].cpu(), full["quat"][idx.to(full["dev"])].cpu()
+    h = ops.height_scan(pos.to(full["dev"]), quat.to(full["dev"]), full["rays"], full["grid"]).cpu()
+    h_ref, _ = OS.height_scan(pos, quat, oracle_raycast.Mesh(full["v"], full["f"]))
+    assert torch.equal(torch.isinf(h), torch.isinf(h_ref))
+    fin = ~torch.isinf(h_ref)
+    assert (h[fin] - h_ref[fin]).abs().max().item() <= 1e-4  # 1e-5 relative on the ray distance t ~ 10 m
+
+
+def test_mdp_cfg3_statistics_ranks_and_determinism(full):
+    dev, tables, n = full["dev"], full["tables"], bench.STEP_ENVS_1GPU
+    cfg = RoverEnvCfg(num_envs=n)
+    params = ops.mdp_params(cfg)
+    th = ops.TerrainTablesHandle(tables.heightmap, tables.safe_mask, tables.offset_xy, tables.spawn_table,
+                                 tables.resolution, dev)
+    gen = torch.Generator().manual_seed(5)
+    st = synthetic.make_step(n, gen, full["vt"], bench.TERRAIN["size_m"], bench.TERRAIN["grid_res"],
+                             cfg.num_contact_bodies, cfg.target_rounds).to(dev)
+    pc, hc, ep = synthetic.init_commands(n, gen, st.root_pos_w.cpu())
+
+    def run():
+        buf = ops.MdpBuffers.allocate(n, dev)
+        buf.pos_cmd_w.copy_(pc)
+        buf.heading_cmd_w.copy_(hc)
+        buf.episode_length_buf.copy_(ep)
+        buf.env_origins.copy_(st.root_pos_w)
+        buf.time_left.fill_(150.0)
+        gb = torch.Generator().manual_seed(8)  # previous body-frame command: 1..7 m away, so few envs terminate
+        ang = torch.rand(n, generator=gb) * 6.2831853
+        rad = torch.rand(n, generator=gb) * 6.0 + 1.0
+        buf.pos_cmd_b.copy_(torch.stack([rad * torch.cos(ang), rad * torch.sin(ang), torch.zeros(n)], 1))
+        buf.heading_cmd_b.copy_(torch.rand(n, generator=gb) * 2 - 1)
+        buf.episode_sums.copy_(torch.rand(n, 7, generator=torch.Generator().manual_seed(6)))
+        sums_before = buf.episode_sums.clone()
+        pos, quat = st.root_pos_w.clone(), st.root_quat_w.clone()
+        obs = torch.zeros(n, 965, device=dev)
+        ops.mdp_pre_step(buf, params, st.actions, st.force_matrix_w)
+        sums_mid = buf.episode_sums.clone()
+        ops.mdp_post_step(buf, params, th, pos, quat, st.spawn_perm, st.yaw_u, st.heading_u, st.theta_u, obs)
+        torch.cuda.synchronize()
+        return buf, pos, quat, obs, sums_before, sums_mid
+
+    buf, pos, quat, obs, sums_before, sums_mid = run()
+    reset = buf.reset_flags.bool()
+    k = int(reset.sum())
+    assert 0 < k < n
+    # index-exact: the j-th reset env (ascending env id, = reset_buf.nonzero()) takes spawn row spawn_perm[j]
+    ids = reset.nonzero().squeeze(1)
+    assert torch.equal(buf.spawn_index[ids], st.spawn_perm[:k])
+    assert bool((buf.spawn_index[~reset] == -1).all())
+    assert torch.equal(pos[ids, :2], th.spawn_table[st.spawn_perm[:k], :2])
+    assert torch.equal(pos[~reset], st.root_pos_w[~reset])
+    # reward bookkeeping: episodic sums advance by the weighted term rewards, the step reward is their sum in order
+    torch.testing.assert_close(sums_mid, sums_before + buf.term_rewards, rtol=0, atol=1e-6)
+    total = torch.zeros(n, device=dev)
+    for j in range(7):
+        total = total + buf.term_rewards[:, j]
+    assert torch.equal(total, buf.reward)
+    # statistics vector = torch reductions over the reset envs (sums in another order: fp32 tolerance)
+    stats = buf.stats.cpu().double()
+    torch.testing.assert_close(stats[:7], sums_mid[reset].double().sum(0).cpu(), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(stats[7:11], buf.term_flags[reset].double().sum(0).cpu(), rtol=0, atol=0)
+    assert stats[13] == k
+    assert bool((buf.episode_sums[reset] == 0).all()) and bool((buf.episode_length_buf[reset] == 0).all())
+    # the observation head is finite and repeated runs are bit-identical (deterministic statistics included)
+    assert torch.isfinite(obs[:, :4]).all()
+    buf2, pos2, quat2, obs2, _, _ = run()
+    assert torch.equal(buf.stats, buf2.stats) and torch.equal(obs, obs2) and torch.equal(pos, pos2)
+    assert torch.equal(buf.pos_cmd_w, buf2.pos_cmd_w) and torch.equal(buf.reward, buf2.reward)
+
+
+def test_policy_cfg4_kernels_agree_and_rows_are_independent(full, monkeypatch):
+    dev, n = full["dev"], 65536
+    net = GaussianNeuralNetwork(device=dev)
+    g = torch.Generator().manual_seed(9)
+    net.load_state_dict({k: torch.randn(t.shape, generator=g) * (0.05 if t.dim() == 2 else 0.01)
+                         for k, t in net.state_dict().items()})
+    obs = alloc_obs(n, dev)
+    obs.copy_(torch.randn(n, 965, device=dev, generator=torch.Generator(device=dev).manual_seed(3)) * 0.3)
+    mean = net.compute({"states": obs})[0]
+    assert torch.isfinite(mean).all() and float(mean.abs().max()) <= 1.0
+    monkeypatch.setenv("ROVER_POLICY_KERNEL", "v1")
+    assert torch.equal(net.compute({"states": obs})[0], mean)
+    monkeypatch.setenv("ROVER_POLICY_KERNEL", "ws")
+    ob = alloc_obs_bf16(n, dev)
+    ob.copy_(obs)
+    assert torch.equal(net.compute({"states": ob})[0], mean)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(2)).to(dev)
+    obs_p = alloc_obs(n, dev)
+    obs_p.copy_(obs[perm])
+    assert torch.equal(net.compute({"states": obs_p})[0], mean[perm])  # tiles / rounds do not leak between rows
+    assert torch.equal(net.compute({"states": obs[:1000]})[0], mean[:1000])  # another tile height, same rows
