@@ -267,6 +267,13 @@ def run_ours(args):
         buf.time_left.fill_(150.0)
         obs = torch.zeros(n_step, 4 + N_RAYS, device=dev)
         stats = EpisodeStats(buf, world)
+        # several GPUs: the episode statistics travel as peer stores issued by the post-step kernel itself
+        # (dist.P2PStats); ROVER_STATS=nccl keeps the all-reduce per step (EpisodeStats)
+        p2p = None
+        if world > 1 and os.environ.get("ROVER_STATS", "p2p") != "nccl":
+            from isaac_rover_orbit_b200.dist import P2PStats
+
+            p2p = P2PStats(dev, rank, world)
 
         # synthetic "physics": every step the rover sits at its env origin + a bounded offset, so that the
         # far/success terminations stay rare and resets come from contacts (5 %) and time-outs
@@ -301,19 +308,19 @@ def run_ours(args):
 
         step_body = full_step
         if world > 1:
-            def step_body(i):  # noqa: F811  (kernels only; the collective is issued after the replay)
+            def step_body(i):  # noqa: F811  (kernels only; an NCCL all-reduce, if used, is issued after the replay)
                 s = sets[i % 4]
                 torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)
                 ops.mdp_pre_step(buf, params, s.actions, s.force_matrix_w)
                 ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
-                                  s.theta_u, obs)
+                                  s.theta_u, obs, xchg=p2p)
                 ops.height_scan(s.root_pos_w, s.root_quat_w, rays, grid, out=obs[:, 4:], variant=args.variant)
         g_full = graphed(step_body)
         g_mdp = graphed(mdp_only)
 
         def run_full(i):
             g_full(i)
-            if world > 1:
+            if world > 1 and p2p is None:
                 stats.all_reduce_async()
 
         ms_full = time_steps(run_full, ksteps, 3, flush, stream)
@@ -323,8 +330,22 @@ def run_ours(args):
         torch.cuda.synchronize()
         resets_per_step = float(buf.stats[13].item())
         tf = torch.tensor([ms_full.sum(), ms_mdp.sum()], dtype=torch.float64, device=dev)
+        stats_check = None
         if world > 1:
             dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            if p2p is not None:
+                # one-off check outside the timed region: the mailbox totals equal an NCCL all-reduce of the ranks' totals
+                dist.barrier()
+                torch.cuda.synchronize()
+                mine = p2p._cumulative.clone()
+                dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+                got = p2p.read().clone()
+                torch.cuda.synchronize()
+                stats_check = {"exchange": "p2p mailbox stores from mdp_post_step (no collective launch on the step path)",
+                               "equals_nccl_all_reduce": bool(torch.equal(got, mine)),
+                               "global_resets": float(got[13].item())}
+            else:
+                stats_check = {"exchange": "nccl all_reduce per step"}
         full_bytes = n_step * (414.0 + 4.0 * N_RAYS) + TERRAIN_BYTES
         extra = {
             "fused_step": {
@@ -335,6 +356,7 @@ def run_ours(args):
                 "gpu_launches_per_step": 3, "cuda_graph": not args.no_graph,
                 "roofline_frac_hbm": full_bytes / (float(tf[0]) / ksteps * 1e-3) / 1e9 / peak,
                 "resets_in_one_step": resets_per_step,
+                "episode_stats": stats_check,
             },
             "mdp_only": {
                 "env_steps_per_s": n_step * world * ksteps / (float(tf[1]) * 1e-3),

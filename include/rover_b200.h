@@ -233,6 +233,40 @@ int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_t n_envs, c
                         float* obs, int32_t obs_stride, int32_t phases, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Multi-GPU episode statistics without a collective launch (the only cross-rank quantity on the path).
+ * Each rank owns a MAILBOX with one slot per rank; the last block of rover_mdp_post_step_x adds the launch's 16
+ * statistics to the rank's running totals (fp64) and stores them into its slot of EVERY rank's mailbox -- plain
+ * stores over NVLink peer mappings under a sequence lock -- so the exchange rides on the kernel that produces the
+ * numbers.  rover_stats_read sums the slots in rank order (deterministic) whenever a log line is wanted.
+ * Replaces the logging reductions of the ORBIT managers' reset() (consumed at rover_envs/utils/skrl_utils.py:139-142)
+ * for env shards on several GPUs; torch.distributed (NCCL) only carries the 64-byte IPC handles once at start-up.
+ * ------------------------------------------------------------------------------------------------- */
+#define ROVER_MAILBOX_SLOT_BYTES 256 /* uint64 sequence + 16 doubles, padded */
+
+typedef struct RoverStatsExchange {
+    void* const* peer_mailbox; /* DEVICE array [world]: mailbox base of every rank as mapped into this process */
+    double* cumulative;        /* DEVICE [16]: this rank's running totals */
+    uint64_t* sequence;        /* DEVICE [1]: this rank's sequence counter (even = published) */
+    int32_t rank, world;
+} RoverStatsExchange;
+
+/* cudaMalloc'ed, zeroed device memory that can be exported to other processes of the node (not from a pooled allocator) */
+int rover_p2p_alloc(void** out_ptr, int64_t bytes);
+int rover_p2p_free(void* ptr);
+int rover_p2p_export(void* ptr, uint8_t handle_out[64]);          /* cudaIpcGetMemHandle */
+int rover_p2p_open(const uint8_t handle[64], void** out_ptr);     /* cudaIpcOpenMemHandle (peer access enabled lazily) */
+int rover_p2p_close(void* ptr);
+/* rover_mdp_post_step plus the publication of the statistics (xchg may be NULL: identical to rover_mdp_post_step) */
+int rover_mdp_post_step_x(float* root_pos_w, float* root_quat_w, int32_t n_envs, const RoverMdpParams* params,
+                          const RoverMdpState* state, const RoverMdpOut* out, const RoverTerrainTables* tables,
+                          const int64_t* spawn_perm, const float* yaw_u, const float* heading_u, const float* theta_u,
+                          int32_t n_rounds, int64_t* out_spawn_index, float* stats, float* scratch, float* obs,
+                          int32_t obs_stride, int32_t phases, const RoverStatsExchange* xchg /* host */, void* stream);
+/* out [16] f64 (device): sum over the world's slots of the local mailbox, in rank order; a slot that is being written is
+ * re-read (sequence lock), so every addend is one rank's totals after some whole number of its steps */
+int rover_stats_read(const void* mailbox_local, int32_t world, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Policy forward.  Replaces GaussianNeuralNetwork.compute + HeightmapEncoder
  * (rover_envs/envs/navigation/learning/skrl/models.py:24-36, 89-102) and skrl GaussianMixin.act.
  * Weights are packed once (host -> device) by rover_policy_pack; bf16 operands, fp32 accumulation

@@ -21,7 +21,8 @@ MDP_BLOCK = 64
 ABI_VERSION = 2
 
 SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_height_scan_obs", "rover_mdp_pre_step",
-           "rover_mdp_post_step",
+           "rover_mdp_post_step", "rover_mdp_post_step_x", "rover_stats_read", "rover_p2p_alloc", "rover_p2p_free",
+           "rover_p2p_export", "rover_p2p_open", "rover_p2p_close",
            "rover_ackermann",
            "rover_policy_pack", "rover_policy_forward", "rover_value_forward", "rover_policy_forward_bf16",
            "rover_value_forward_bf16", "rover_gaussian_act")
@@ -41,6 +42,14 @@ class ScanGrid(C.Structure):
 class PlaneCells(C.Structure):
     _fields_ = [("xs", C.c_void_p), ("ys", C.c_void_p), ("entries", C.c_void_p), ("nx", C.c_int32), ("ny", C.c_int32),
                 ("inv_dx", C.c_float), ("inv_dy", C.c_float), ("entries_planar", C.c_void_p)]
+
+
+class StatsExchange(C.Structure):
+    _fields_ = [("peer_mailbox", C.c_void_p), ("cumulative", C.c_void_p), ("sequence", C.c_void_p),
+                ("rank", C.c_int32), ("world", C.c_int32)]
+
+
+MAILBOX_SLOT_BYTES = 256
 
 
 class MdpParams(C.Structure):
@@ -112,6 +121,21 @@ def load() -> C.CDLL:
     lib.rover_mdp_post_step.restype = C.c_int
     lib.rover_mdp_post_step.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
                                         C.POINTER(TerrainTables), vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp]
+    lib.rover_mdp_post_step_x.restype = C.c_int
+    lib.rover_mdp_post_step_x.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
+                                          C.POINTER(TerrainTables), vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32,
+                                          C.POINTER(StatsExchange), vp]
+    lib.rover_stats_read.restype = C.c_int
+    lib.rover_stats_read.argtypes = [vp, i32, vp, vp]
+    lib.rover_p2p_alloc.restype = C.c_int
+    lib.rover_p2p_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
+    lib.rover_p2p_export.restype = C.c_int
+    lib.rover_p2p_export.argtypes = [vp, C.POINTER(C.c_uint8 * 64)]
+    lib.rover_p2p_open.restype = C.c_int
+    lib.rover_p2p_open.argtypes = [C.POINTER(C.c_uint8 * 64), C.POINTER(C.c_void_p)]
+    for fn in (lib.rover_p2p_free, lib.rover_p2p_close):
+        fn.restype = C.c_int
+        fn.argtypes = [vp]
     lib.rover_ackermann.restype = C.c_int
     lib.rover_ackermann.argtypes = [vp, i32, C.POINTER(MdpParams), vp, vp, vp, vp]
     lib.rover_policy_pack.restype = C.c_int64

@@ -14,6 +14,8 @@
 // plus the ORBIT manager combine rules and math helpers of SURVEY.md Appendix A.1/A.2.
 // fp32 arithmetic follows the reference's operation order; contraction is disabled (__f*_rn) wherever a
 // value is compared against a threshold or truncated to an index.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace rover {
@@ -352,6 +354,13 @@ __device__ __forceinline__ bool resample_command(int i, const RoverMdpParams& P,
 
 constexpr int kStats = ROVER_STATS_LEN;
 
+struct StatsExchangeDev {
+    void* const* peer_mailbox;
+    double* cumulative;
+    unsigned long long* sequence;
+    int rank, world;  // world == 0: no exchange
+};
+
 __global__ void __launch_bounds__(ROVER_MDP_BLOCK)
 mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_quat_w, int n,
                      const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
@@ -360,7 +369,7 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
                      const float* __restrict__ heading_u, const float* __restrict__ theta_u, int n_rounds,
                      long long* __restrict__ out_spawn_index, float* __restrict__ block_stats,
                      unsigned int* __restrict__ done_counter, float* __restrict__ stats, float* __restrict__ obs,
-                     int obs_stride, int phases) {
+                     int obs_stride, int phases, const __grid_constant__ StatsExchangeDev X) {
     __shared__ int warp_cnt[ROVER_MDP_BLOCK / 32];
     __shared__ int block_base;
     constexpr int kRedRows = (ROVER_MDP_BLOCK / 32 > ROVER_MDP_BLOCK / kStats) ? ROVER_MDP_BLOCK / 32 : ROVER_MDP_BLOCK / kStats;
@@ -562,12 +571,67 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
         __syncthreads();  // red[] is free: every thread passed the block-level reduction above
         if (g < G) red[g][k] = v;
         __syncthreads();
+        double total = 0.0;
         if (threadIdx.x < kStats) {
             float t = 0.f;
             for (int q = 0; q < G; ++q) t += red[q][threadIdx.x];
             stats[threadIdx.x] += t;
             if (threadIdx.x == 0) *done_counter = 0u;  // re-arm for the next launch
+            if (X.world > 0) {
+                total = X.cumulative[threadIdx.x] + (double)t;
+                X.cumulative[threadIdx.x] = total;
+            }
         }
+        // ---- multi-GPU: publish the running totals into this rank's slot of every rank's mailbox (peer stores over
+        //      NVLink) under a sequence lock: odd = being written.  No collective, no extra launch.
+        if (X.world > 0) {
+            const unsigned long long seq = *X.sequence;  // even
+            for (int p = 0; p < X.world; ++p) {
+                unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
+                volatile unsigned long long* sq = reinterpret_cast<volatile unsigned long long*>(slot);
+                volatile double* val = reinterpret_cast<volatile double*>(slot + 8);
+                if (threadIdx.x == 0) *sq = seq + 1ull;
+                __threadfence_system();
+                __syncthreads();
+                if (threadIdx.x < kStats) val[threadIdx.x] = total;
+                __threadfence_system();
+                __syncthreads();
+                if (threadIdx.x == 0) *sq = seq + 2ull;
+            }
+            __threadfence_system();
+            if (threadIdx.x == 0) *X.sequence = seq + 2ull;
+        }
+    }
+}
+
+// one block: thread (p, k) = (threadIdx.x / 16, threadIdx.x % 16) reads statistic k of rank p's slot consistently
+__global__ void stats_read_kernel(const unsigned char* __restrict__ mailbox, int world, double* __restrict__ out) {
+    __shared__ double v[64][kStats];
+    const int p = threadIdx.x / kStats, k = threadIdx.x % kStats;
+    for (int p0 = 0; p0 < world; p0 += 64) {
+        const int pp = p0 + p;
+        if (pp < world && p < 64) {
+            const unsigned char* slot = mailbox + (size_t)pp * ROVER_MAILBOX_SLOT_BYTES;
+            const volatile unsigned long long* sq = reinterpret_cast<const volatile unsigned long long*>(slot);
+            const volatile double* val = reinterpret_cast<const volatile double*>(slot + 8);
+            double x;
+            unsigned long long s1, s2;
+            do {
+                s1 = *sq;
+                __threadfence_system();
+                x = val[k];
+                __threadfence_system();
+                s2 = *sq;
+            } while ((s1 & 1ull) || s1 != s2);
+            v[p][k] = x;
+        }
+        __syncthreads();
+        if (threadIdx.x < kStats) {
+            double t = p0 == 0 ? 0.0 : out[threadIdx.x];
+            for (int q = 0; q < min(64, world - p0); ++q) t += v[q][threadIdx.x];
+            out[threadIdx.x] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -622,7 +686,26 @@ extern "C" int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_
                                    const float* heading_u, const float* theta_u, int32_t n_rounds,
                                    int64_t* out_spawn_index, float* stats, float* scratch, float* obs,
                                    int32_t obs_stride, int32_t phases, void* stream) {
+    return rover_mdp_post_step_x(root_pos_w, root_quat_w, n_envs, params, state, out, tables, spawn_perm, yaw_u, heading_u,
+                                 theta_u, n_rounds, out_spawn_index, stats, scratch, obs, obs_stride, phases, nullptr,
+                                 stream);
+}
+
+extern "C" int rover_mdp_post_step_x(float* root_pos_w, float* root_quat_w, int32_t n_envs, const RoverMdpParams* params,
+                                     const RoverMdpState* state, const RoverMdpOut* out,
+                                     const RoverTerrainTables* tables, const int64_t* spawn_perm, const float* yaw_u,
+                                     const float* heading_u, const float* theta_u, int32_t n_rounds,
+                                     int64_t* out_spawn_index, float* stats, float* scratch, float* obs,
+                                     int32_t obs_stride, int32_t phases, const RoverStatsExchange* xchg, void* stream) {
     using namespace rover;
+    StatsExchangeDev X{nullptr, nullptr, nullptr, 0, 0};
+    if (xchg != nullptr) {
+        ROVER_CHECK(xchg->peer_mailbox && xchg->cumulative && xchg->sequence && xchg->world >= 1 && xchg->rank >= 0 &&
+                        xchg->rank < xchg->world,
+                    "rover_mdp_post_step_x: bad RoverStatsExchange");
+        X = StatsExchangeDev{xchg->peer_mailbox, xchg->cumulative,
+                             reinterpret_cast<unsigned long long*>(xchg->sequence), xchg->rank, xchg->world};
+    }
     ROVER_CHECK(n_envs >= 0, "rover_mdp_post_step: negative n_envs");
     if (n_envs == 0) return 0;
     ROVER_CHECK(root_pos_w && root_quat_w && params && tables && spawn_perm && yaw_u && heading_u && theta_u && stats &&
@@ -644,6 +727,48 @@ extern "C" int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_
     mdp_post_step_kernel<<<blocks, ROVER_MDP_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(
         root_pos_w, root_quat_w, n_envs, *params, *state, *out, T, reinterpret_cast<const long long*>(spawn_perm),
         yaw_u, heading_u, theta_u, n_rounds, reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats,
-        obs, obs_stride, phases);
+        obs, obs_stride, phases, X);
     return check_launch("mdp_post_step_kernel");
+}
+
+extern "C" int rover_stats_read(const void* mailbox_local, int32_t world, double* out, void* stream) {
+    using namespace rover;
+    ROVER_CHECK(mailbox_local && out && world >= 1, "rover_stats_read: bad arguments");
+    stats_read_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned char*>(mailbox_local), world,
+                                                                        out);
+    return check_launch("stats_read_kernel");
+}
+
+extern "C" int rover_p2p_alloc(void** out_ptr, int64_t bytes) {
+    using namespace rover;
+    ROVER_CHECK(out_ptr && bytes > 0, "rover_p2p_alloc: bad arguments");
+    ROVER_CUDA(cudaMalloc(out_ptr, (size_t)bytes));
+    ROVER_CUDA(cudaMemset(*out_ptr, 0, (size_t)bytes));
+    ROVER_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int rover_p2p_free(void* ptr) {
+    using namespace rover;
+    ROVER_CUDA(cudaFree(ptr));
+    return 0;
+}
+extern "C" int rover_p2p_export(void* ptr, uint8_t handle_out[64]) {
+    using namespace rover;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    ROVER_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+extern "C" int rover_p2p_open(const uint8_t handle[64], void** out_ptr) {
+    using namespace rover;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    ROVER_CUDA(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int rover_p2p_close(void* ptr) {
+    using namespace rover;
+    ROVER_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
 }

@@ -10,6 +10,8 @@ them with a single ``all_reduce(SUM)`` (NCCL over NVLink on GPUs, gloo in the CP
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -75,3 +77,85 @@ class EpisodeStats:
 
     def log(self, episode_length_s: float = 150.0) -> dict:
         return episode_log(self.result(), episode_length_s)
+
+
+class P2PStats:
+    """Episode statistics across the GPUs of one node without a collective on the step path.
+
+    Every rank owns a mailbox (one 256-byte slot per rank, ``cudaMalloc``'ed and exported through CUDA IPC); the handles
+    are exchanged once with ``all_gather`` and every rank maps every mailbox.  Passing the object to
+    ``ops.mdp_post_step(..., xchg=...)`` makes the last block of that launch add the step's statistics to the rank's
+    running totals (fp64) and store them into its slot of every mailbox (peer stores over NVLink, sequence-locked).
+    ``read()`` sums the slots of the local mailbox in rank order -- the global running totals as of each rank's latest
+    published step -- and ``interval()`` returns the difference to the previous call (the numbers ``episode_log``
+    divides: sum / count over all ranks, not a mean of means).  ``EpisodeStats`` (one all-reduce) remains the portable
+    path (several nodes, CPU tests)."""
+
+    def __init__(self, device, rank: int | None = None, world: int | None = None, group=None):
+        from . import _lib
+
+        self._lib = _lib
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("P2PStats needs a CUDA device; there is no CPU fallback (use EpisodeStats)")
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            mb = C.c_void_p()
+            _lib.check(lib.rover_p2p_alloc(C.byref(mb), _lib.MAILBOX_SLOT_BYTES * self.world))
+            self._mailbox = mb.value
+            handle = (C.c_uint8 * 64)()
+            _lib.check(lib.rover_p2p_export(C.c_void_p(self._mailbox), C.byref(handle)))
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+            if self.world > 1:
+                gathered = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(gathered, mine, group=group)
+            else:
+                gathered = [mine]
+            ptrs = []
+            self._opened = []
+            for r, h in enumerate(gathered):
+                if r == self.rank:
+                    ptrs.append(self._mailbox)
+                    continue
+                raw = (C.c_uint8 * 64)(*h.cpu().tolist())
+                p = C.c_void_p()
+                _lib.check(lib.rover_p2p_open(C.byref(raw), C.byref(p)))
+                ptrs.append(p.value)
+                self._opened.append(p.value)
+            self._peer_table = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+            self._cumulative = torch.zeros(STATS_LEN, dtype=torch.float64, device=self.device)
+            self._sequence = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._out = torch.zeros(STATS_LEN, dtype=torch.float64, device=self.device)
+            self._last = torch.zeros(STATS_LEN, dtype=torch.float64, device=self.device)
+        self.struct = _lib.StatsExchange(self._peer_table.data_ptr(), self._cumulative.data_ptr(),
+                                         self._sequence.data_ptr(), self.rank, self.world)
+        if self.world > 1:
+            dist.barrier(group=group)  # every mailbox is mapped everywhere before anyone publishes
+
+    def read(self) -> torch.Tensor:
+        """Global running totals ``[16]`` f64 (device tensor, enqueued on the current stream)."""
+        self._lib.check(self._lib.load().rover_stats_read(C.c_void_p(self._mailbox), self.world,
+                                                          C.c_void_p(self._out.data_ptr()),
+                                                          self._lib.current_stream(self.device)))
+        return self._out
+
+    def interval(self) -> torch.Tensor:
+        """Totals accumulated since the previous ``interval()`` call (what ``episode_log`` expects)."""
+        now = self.read().clone()
+        delta = now - self._last
+        self._last = now
+        return delta
+
+    def log(self, episode_length_s: float = 150.0) -> dict:
+        return episode_log(self.interval(), episode_length_s)
+
+    def close(self) -> None:
+        lib = self._lib.load()
+        for p in self._opened:
+            lib.rover_p2p_close(C.c_void_p(p))
+        self._opened = []
+        if self._mailbox:
+            lib.rover_p2p_free(C.c_void_p(self._mailbox))
+            self._mailbox = None

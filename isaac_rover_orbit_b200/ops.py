@@ -304,7 +304,8 @@ def mdp_pre_step(buf: MdpBuffers, params: _lib.MdpParams, actions: torch.Tensor 
 
 def mdp_post_step(buf: MdpBuffers, params: _lib.MdpParams, tables: TerrainTablesHandle, root_pos_w: torch.Tensor,
                   root_quat_w: torch.Tensor, spawn_perm: torch.Tensor, yaw_u: torch.Tensor, heading_u: torch.Tensor,
-                  theta_u: torch.Tensor, obs: torch.Tensor | None = None, phases: int = _lib.PHASE_ALL):
+                  theta_u: torch.Tensor, obs: torch.Tensor | None = None, phases: int = _lib.PHASE_ALL,
+                  xchg=None):
     """Reset / resample / command update / observation head (one launch).  ``root_*`` are updated in place
     for the reset envs; ``buf.stats`` is accumulated; ``buf.spawn_index`` holds the spawn rows used (-1 else)."""
     dev = _lib.require_cuda(root_pos_w, root_quat_w, spawn_perm, yaw_u, heading_u, theta_u)
@@ -323,8 +324,9 @@ def mdp_post_step(buf: MdpBuffers, params: _lib.MdpParams, tables: TerrainTables
             raise RuntimeError("mdp_post_step: obs must be fp32 [N,>=4] with unit inner stride")
         obs_ptr, obs_stride = C.c_void_p(obs.data_ptr()), int(obs.stride(0))
     st, out = buf.state_struct(), buf.out_struct()
-    _lib.check(_lib.load().rover_mdp_post_step(
+    # xchg: a dist.P2PStats -- the launch also publishes the rank's running statistics to every rank's mailbox
+    _lib.check(_lib.load().rover_mdp_post_step_x(
         _lib.ptr(root_pos_w), _lib.ptr(root_quat_w), n, C.byref(params), C.byref(st), C.byref(out),
         C.byref(tables.struct), _lib.ptr(spawn_perm), _lib.ptr(yaw_u), _lib.ptr(heading_u), _lib.ptr(theta_u),
         int(theta_u.shape[1]), _lib.ptr(buf.spawn_index), _lib.ptr(buf.stats), _lib.ptr(buf.scratch), obs_ptr,
-        obs_stride, int(phases), _lib.current_stream(dev)))
+        obs_stride, int(phases), C.byref(xchg.struct) if xchg is not None else None, _lib.current_stream(dev)))

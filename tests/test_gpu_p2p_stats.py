@@ -1,0 +1,57 @@
+"""GPU: episode statistics through the P2P mailbox (dist.P2PStats).  World size 1 here (the mailbox of the rank itself);
+``tests/p2p_stats_worker.py`` is the world-size-2 check, launched by this test when two GPUs are visible and by
+``gpurun --gpus 2`` during development."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from isaac_rover_orbit_b200 import ops, synthetic
+from isaac_rover_orbit_b200 import terrain as TR
+from isaac_rover_orbit_b200.config import RoverEnvCfg
+from isaac_rover_orbit_b200.dist import P2PStats, episode_log
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_p2p_stats_world1_equals_accumulator(cuda_device):
+    n = 512
+    v, f = TR.make_synthetic_terrain(48.0, 0.2, seed=3)
+    tables = TR.build_terrain_tables(v, f, n)
+    cfg = RoverEnvCfg(num_envs=n)
+    params = ops.mdp_params(cfg)
+    th = ops.TerrainTablesHandle(tables.heightmap, tables.safe_mask, tables.offset_xy, tables.spawn_table,
+                                 tables.resolution, cuda_device)
+    buf = ops.MdpBuffers.allocate(n, cuda_device)
+    buf.time_left.fill_(150.0)
+    p2p = P2PStats(cuda_device, rank=0, world=1)
+    gen = torch.Generator().manual_seed(3)
+    vt = torch.from_numpy(v)
+    total = torch.zeros(16, dtype=torch.float64)
+    for step in range(5):
+        st = synthetic.make_step(n, gen, vt, 48.0, 0.2, margin=4.0).to(cuda_device)
+        buf.stats.zero_()
+        ops.mdp_pre_step(buf, params, st.actions, st.force_matrix_w)
+        ops.mdp_post_step(buf, params, th, st.root_pos_w, st.root_quat_w, st.spawn_perm, st.yaw_u, st.heading_u,
+                          st.theta_u, None, xchg=p2p)
+        total += buf.stats.double().cpu()
+        if step == 2:
+            first = p2p.interval().cpu()
+            assert torch.equal(first, total)  # fp64 running totals of fp32 per-launch statistics: exact
+    torch.cuda.synchronize()
+    assert torch.equal(p2p.read().cpu(), total) and total[13] > 0
+    log = episode_log(p2p.interval())
+    assert log["num_resets"] == int(total[13] - first[13])
+    p2p.close()
+
+
+def test_p2p_stats_world2(cuda_device):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one node")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(ROOT, "tests", "p2p_stats_worker.py")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "P2P_STATS_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
