@@ -236,12 +236,13 @@ int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_t n_envs, c
  * Multi-GPU episode statistics without a collective launch (the only cross-rank quantity on the path).
  * Each rank owns a MAILBOX with one slot per rank; the last block of rover_mdp_post_step_x adds the launch's 16
  * statistics to the rank's running totals (fp64) and stores them into its slot of EVERY rank's mailbox -- plain
- * stores over NVLink peer mappings under a sequence lock -- so the exchange rides on the kernel that produces the
- * numbers.  rover_stats_read sums the slots in rank order (deterministic) whenever a log line is wanted.
+ * stores over NVLink peer mappings, sequence-numbered -- so the exchange rides on the kernel that produces the
+ * numbers (one system-scope fence per step: values into the idle one of two buffers, then the sequence number).
+ * rover_stats_read sums the slots in rank order (deterministic) whenever a log line is wanted.
  * Replaces the logging reductions of the ORBIT managers' reset() (consumed at rover_envs/utils/skrl_utils.py:139-142)
  * for env shards on several GPUs; torch.distributed (NCCL) only carries the 64-byte IPC handles once at start-up.
  * ------------------------------------------------------------------------------------------------- */
-#define ROVER_MAILBOX_SLOT_BYTES 256 /* uint64 sequence + 16 doubles, padded */
+#define ROVER_MAILBOX_SLOT_BYTES 512 /* uint64 sequence + 2 x 16 doubles (double-buffered), padded */
 
 typedef struct RoverStatsExchange {
     void* const* peer_mailbox; /* DEVICE array [world]: mailbox base of every rank as mapped into this process */

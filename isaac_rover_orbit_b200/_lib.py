@@ -49,7 +49,7 @@ class StatsExchange(C.Structure):
                 ("rank", C.c_int32), ("world", C.c_int32)]
 
 
-MAILBOX_SLOT_BYTES = 256
+MAILBOX_SLOT_BYTES = 512
 
 
 class MdpParams(C.Structure):

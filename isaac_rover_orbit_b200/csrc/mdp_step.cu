@@ -583,23 +583,26 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
             }
         }
         // ---- multi-GPU: publish the running totals into this rank's slot of every rank's mailbox (peer stores over
-        //      NVLink) under a sequence lock: odd = being written.  No collective, no extra launch.
+        //      NVLink).  A slot holds a sequence number and two value buffers; the writer fills buffer (seq + 1) & 1 in
+        //      every mailbox, fences once, then stores seq + 1 everywhere -- one system-scope fence per step, all peers
+        //      in flight together.  No collective, no extra launch.
         if (X.world > 0) {
-            const unsigned long long seq = *X.sequence;  // even
-            for (int p = 0; p < X.world; ++p) {
+            __shared__ double pub[kStats];
+            if (threadIdx.x < kStats) pub[threadIdx.x] = total;
+            __syncthreads();
+            const unsigned long long seq = *X.sequence + 1ull;
+            for (int e = threadIdx.x; e < X.world * kStats; e += ROVER_MDP_BLOCK) {
+                const int p = e / kStats, k = e % kStats;
                 unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
-                volatile unsigned long long* sq = reinterpret_cast<volatile unsigned long long*>(slot);
-                volatile double* val = reinterpret_cast<volatile double*>(slot + 8);
-                if (threadIdx.x == 0) *sq = seq + 1ull;
-                __threadfence_system();
-                __syncthreads();
-                if (threadIdx.x < kStats) val[threadIdx.x] = total;
-                __threadfence_system();
-                __syncthreads();
-                if (threadIdx.x == 0) *sq = seq + 2ull;
+                reinterpret_cast<volatile double*>(slot + 8)[(seq & 1ull) * kStats + k] = pub[k];
             }
             __threadfence_system();
-            if (threadIdx.x == 0) *X.sequence = seq + 2ull;
+            __syncthreads();
+            for (int p = threadIdx.x; p < X.world; p += ROVER_MDP_BLOCK) {
+                unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
+                *reinterpret_cast<volatile unsigned long long*>(slot) = seq;
+            }
+            if (threadIdx.x == 0) *X.sequence = seq;
         }
     }
 }
@@ -616,13 +619,13 @@ __global__ void stats_read_kernel(const unsigned char* __restrict__ mailbox, int
             const volatile double* val = reinterpret_cast<const volatile double*>(slot + 8);
             double x;
             unsigned long long s1, s2;
-            do {
+            do {  // buffer s1 & 1 holds the totals of sequence s1; it is rewritten only on the way to s1 + 2
                 s1 = *sq;
                 __threadfence_system();
-                x = val[k];
+                x = val[(s1 & 1ull) * kStats + k];
                 __threadfence_system();
                 s2 = *sq;
-            } while ((s1 & 1ull) || s1 != s2);
+            } while (s1 != s2);
             v[p][k] = x;
         }
         __syncthreads();
