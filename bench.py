@@ -470,7 +470,7 @@ def run_ours(args):
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference(v, f, steps=3, warmup=1, n_envs=256)
+        cpu = cpu_reference(v, f, steps=None, warmup=1, n_envs=SCAN_ENVS_PER_GPU, budget_s=12.0)
 
     line = None
     if rank == 0:
@@ -500,9 +500,11 @@ def run_ours(args):
     return line
 
 
-def cpu_reference(v, f, steps, warmup, n_envs):
+def cpu_reference(v, f, steps, warmup, n_envs, budget_s=None):
     """The reference's CPU path for the height scan, restated (oracle port): torch pose->ray transform
-    (ORBIT RayCaster) + BVH/watertight closest hit (warp mesh_query_ray) + height_scan_rover, all host threads."""
+    (ORBIT RayCaster) + BVH/watertight closest hit (warp mesh_query_ray) + height_scan_rover, all host threads.
+    ``budget_s``: size the sample from a probe so that the timed part takes about that long -- ``steps`` is then
+    chosen here (cpu_baseline leg) or, with ``steps`` fixed by the caller, the envs per step are (reference arm)."""
     from isaac_rover_orbit_b200 import synthetic
     from oracle import raycast as oracle_raycast
     from oracle import step as OS
@@ -514,6 +516,16 @@ def cpu_reference(v, f, steps, warmup, n_envs):
     log(f"oracle BVH over {len(f)} triangles ({time.time() - t0:.1f}s)")
     gen = torch.Generator().manual_seed(4321)
     vt = torch.from_numpy(v)
+    if budget_s is not None:
+        probe = synthetic.make_poses(256, gen, vt, TERRAIN["size_m"], TERRAIN["grid_res"])
+        OS.height_scan(*probe, mesh)
+        t0 = time.perf_counter()
+        OS.height_scan(*probe, mesh)
+        t_env = (time.perf_counter() - t0) / 256  # seconds per env (961 rays)
+        if steps is None:   # cpu_baseline leg: whole cfg-2 batches, as many as fit the budget
+            steps = int(min(max(round(budget_s / (t_env * n_envs)), 3), 200))
+        else:               # reference arm: K steps are given, bound the envs per step
+            n_envs = int(min(n_envs, max(64, budget_s / (t_env * (steps + warmup)))))
     sets = [synthetic.make_poses(n_envs, gen, vt, TERRAIN["size_m"], TERRAIN["grid_res"]) for _ in range(4)]
     for i in range(warmup):
         OS.height_scan(*sets[i % 4], mesh)
@@ -522,9 +534,9 @@ def cpu_reference(v, f, steps, warmup, n_envs):
         OS.height_scan(*sets[i % 4], mesh)
     dt = time.perf_counter() - t0
     return {"value": n_envs * N_RAYS * steps / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} steps x {n_envs} envs x {N_RAYS} rays on the same 2,000,000-triangle terrain "
-                      f"(oracle/: torch ray transform + C BVH raycast with OpenMP)",
-            "ms_per_step": dt / steps * 1e3}
+            "sample": f"{steps} steps x {n_envs} envs x {N_RAYS} rays on the same 2,000,000-triangle terrain, "
+                      f"{dt:.1f} s of CPU work (oracle/: torch ray transform + C BVH raycast with OpenMP)",
+            "ms_per_step": dt / steps * 1e3, "envs_per_step": n_envs}
 
 
 def run_reference(args):
@@ -534,8 +546,10 @@ def run_reference(args):
     from isaac_rover_orbit_b200 import terrain as TR
 
     v, f = TR.make_synthetic_terrain(**TERRAIN)
-    n_envs = 256
-    cpu = cpu_reference(v, f, steps=max(args.steps, 1), warmup=max(args.warmup, 1), n_envs=n_envs)
+    # every step = one cfg-2 batch (4096 envs) when K + W such steps fit ~2 minutes of host time, else a bounded sample
+    cpu = cpu_reference(v, f, steps=max(args.steps, 1), warmup=max(args.warmup, 1), n_envs=SCAN_ENVS_PER_GPU,
+                        budget_s=120.0)
+    n_envs = cpu["envs_per_step"]
     line = {
         "impl": "reference", "metric": "height_scan_rays_per_s", "value": cpu["value"], "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
