@@ -108,8 +108,9 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
 __device__ __forceinline__ void epilogue_to_act(uint32_t taddr, int n_cols, const float* __restrict__ bias,
                                                 unsigned char* __restrict__ act, int row, const float* inject) {
     // Software pipeline over batches of 16 columns: the tcgen05.ld of batch k+1 is in flight while batch k is converted.
-    // (The epilogues are bound by the TMEM read port, ~64 B/clk per SM: 128 rows x 256 columns take >= 2048 cycles, and
-    // a second group of four warps on the upper half of the columns did not shorten them -- measured.)
+    // (Measured on the 256-column epilogue, ~3200 cycles: a build without the TMEM loads is only 14 % faster, one with
+    // the loads alone 2x faster, and a second group of four warps on the upper half of the columns changes nothing --
+    // the bound is the SM-wide rate of the conversion arithmetic (bias add, LeakyReLU, F2FP bf16 pack, STS), not TMEM.)
     uint32_t raw[2][16];
     tmem_ld16_nowait(taddr, raw[0]);
     tmem_wait_ld();
