@@ -126,9 +126,18 @@ __device__ __forceinline__ void epilogue_to_act(uint32_t taddr, int n_cols, cons
             const float4 b = *reinterpret_cast<const float4*>(bias + nq + 4 * j4);  // broadcast LDS.128
             const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float x = __uint_as_float(raw[cur][4 * j4 + j]) + bb[j];
-                v[4 * j4 + j] = fmaxf(x, 0.01f * x);  // == x > 0 ? x : 0.01 x (LeakyReLU, slope 0.01), one op less
+            for (int j = 0; j < 4; j += 2) {
+                // two columns per FADD2 / FMUL2 (per-lane IEEE fp32: same values as the scalar ops, half the issue slots)
+                unsigned long long acc2, b2, x2, t2;
+                const unsigned long long slope2 = 0x3c23d70a3c23d70aull;  // (0.01f, 0.01f)
+                asm("mov.b64 %0, {%1, %2};" : "=l"(acc2) : "r"(raw[cur][4 * j4 + j]), "r"(raw[cur][4 * j4 + j + 1]));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(b2) : "f"(bb[j]), "f"(bb[j + 1]));
+                asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x2) : "l"(acc2), "l"(b2));
+                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t2) : "l"(x2), "l"(slope2));
+                const float x0 = __uint_as_float((unsigned)(x2 & 0xffffffffull)), x1 = __uint_as_float((unsigned)(x2 >> 32));
+                const float t0 = __uint_as_float((unsigned)(t2 & 0xffffffffull)), t1 = __uint_as_float((unsigned)(t2 >> 32));
+                v[4 * j4 + j] = fmaxf(x0, t0);  // == x > 0 ? x : 0.01 x (LeakyReLU, slope 0.01)
+                v[4 * j4 + j + 1] = fmaxf(x1, t1);
             }
         }
         if (inject != nullptr && nq == 48) {
