@@ -372,7 +372,7 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
                      int obs_stride, int phases, const __grid_constant__ StatsExchangeDev X) {
     __shared__ int warp_cnt[ROVER_MDP_BLOCK / 32];
     __shared__ int block_base;
-    constexpr int kRedRows = (ROVER_MDP_BLOCK / 32 > ROVER_MDP_BLOCK / kStats) ? ROVER_MDP_BLOCK / 32 : ROVER_MDP_BLOCK / kStats;
+    constexpr int kRedRows = ROVER_MDP_BLOCK / 4;  // 16 row groups of the last-block reduction (>= warps per block)
     __shared__ float red[kRedRows][kStats];
     __shared__ bool is_last;
     const int i = blockIdx.x * ROVER_MDP_BLOCK + threadIdx.x;
@@ -550,27 +550,28 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
     __syncthreads();
     if (is_last) {
         // Fixed summation tree (deterministic, same result for the same inputs whatever the block schedule): thread t
-        // owns statistic k = t % 16 of the block rows g, g + 4, ... (g = t / 16) and sums them in ascending order with
-        // kUnroll independent loads in flight (the partials sit in L2: one sequential chain of 64 dependent L2 round
-        // trips cost ~5 us of a 25 us launch); the 4 row groups are then combined in order of g.
-        constexpr int G = ROVER_MDP_BLOCK / kStats;
-        constexpr int kUnroll = 8;
-        const int k = threadIdx.x % kStats, g = threadIdx.x / kStats;
-        float v = 0.f;
-        if (g < G) {
-            unsigned b = g;
-            for (; b + (kUnroll - 1) * G < gridDim.x; b += kUnroll * G) {
-                float x[kUnroll];
+        // owns the statistics quad c = t % 4 of the block rows g, g + 16, ... (g = t / 4): float4 loads, kUnroll of them
+        // in flight per thread, so the 16 KB of partials (L2) cost one or two round trips instead of a chain of them;
+        // the 16 row groups are then combined in order of g.
+        static_assert(ROVER_MDP_BLOCK == 64 && kStats == 16, "last-block reduction layout");
+        constexpr int kGroups = ROVER_MDP_BLOCK / 4, kUnroll = 16;
+        const int c4 = threadIdx.x & 3, g = threadIdx.x >> 2;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (unsigned b0 = g; b0 < gridDim.x; b0 += kGroups * kUnroll) {
+            float4 x[kUnroll];
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) x[u] = __ldcg(block_stats + (size_t)(b + u * G) * kStats + k);
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) v += x[u];
+            for (int u = 0; u < kUnroll; ++u) {
+                const unsigned bb = b0 + u * kGroups;
+                x[u] = bb < gridDim.x ? __ldcg(reinterpret_cast<const float4*>(block_stats + (size_t)bb * kStats) + c4)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            for (; b < gridDim.x; b += G) v += __ldcg(block_stats + (size_t)b * kStats + k);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) acc.x += x[u].x, acc.y += x[u].y, acc.z += x[u].z, acc.w += x[u].w;
         }
         __syncthreads();  // red[] is free: every thread passed the block-level reduction above
-        if (g < G) red[g][k] = v;
+        red[g][4 * c4 + 0] = acc.x, red[g][4 * c4 + 1] = acc.y, red[g][4 * c4 + 2] = acc.z, red[g][4 * c4 + 3] = acc.w;
         __syncthreads();
+        constexpr int G = kGroups;
         double total = 0.0;
         if (threadIdx.x < kStats) {
             float t = 0.f;
