@@ -45,7 +45,8 @@ def test_abi_exports_every_declared_symbol():
 def test_ctypes_structs_match_c_layout(tmp_path):
     names = {"RoverScanLevel": _lib.ScanLevel, "RoverScanGrid": _lib.ScanGrid, "RoverPlaneCells": _lib.PlaneCells,
              "RoverMdpParams": _lib.MdpParams,
-             "RoverMdpState": _lib.MdpState, "RoverMdpOut": _lib.MdpOut, "RoverTerrainTables": _lib.TerrainTables}
+             "RoverMdpState": _lib.MdpState, "RoverMdpOut": _lib.MdpOut, "RoverTerrainTables": _lib.TerrainTables,
+             "RoverStatsExchange": _lib.StatsExchange, "RoverPolicyWeights": _lib.PolicyWeights}
     src = tmp_path / "sz.c"
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in names)
     src.write_text(f'#include <stdio.h>\n#include "rover_b200.h"\nint main(void){{{body}return 0;}}')
@@ -57,7 +58,8 @@ def test_ctypes_structs_match_c_layout(tmp_path):
         assert ctypes.sizeof(cls) == sizes[n], n
     header = open(os.path.join(ROOT, "include", "rover_b200.h")).read()
     for macro, val in (("ROVER_MAX_LEVELS", _lib.MAX_LEVELS), ("ROVER_STATS_LEN", _lib.STATS_LEN),
-                       ("ROVER_MDP_BLOCK", _lib.MDP_BLOCK), ("ROVER_NUM_REWARD_TERMS", _lib.NUM_REWARD_TERMS)):
+                       ("ROVER_MDP_BLOCK", _lib.MDP_BLOCK), ("ROVER_NUM_REWARD_TERMS", _lib.NUM_REWARD_TERMS),
+                       ("ROVER_MAILBOX_SLOT_BYTES", _lib.MAILBOX_SLOT_BYTES), ("ROVER_B200_ABI_VERSION", _lib.ABI_VERSION)):
         assert int(re.search(rf"#define {macro} (\d+)", header).group(1)) == val
 
 
