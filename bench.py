@@ -323,12 +323,21 @@ def run_ours(args):
                   ).to(dev) for _ in range(4)]
         buf.pos_cmd_w.copy_(sets[0].root_pos_w + torch.tensor([9.0, 0.0, 0.0], device=dev))
 
+        def mdp(buf, params, th, actions, s, obs_, xchg=None):
+            """pre-step + post-step: two launches (the faster arrangement, profiles/r01_mdp_v1.md); --single-launch-mdp
+            runs both in one launch (rover_mdp_step, reset rank by decoupled look-back)"""
+            if not args.single_launch_mdp:
+                ops.mdp_pre_step(buf, params, actions, s.force_matrix_w)
+                ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
+                                  s.theta_u, obs_, xchg=xchg)
+            else:
+                ops.mdp_step(buf, params, th, actions, s.force_matrix_w, s.root_pos_w, s.root_quat_w, s.spawn_perm,
+                             s.yaw_u, s.heading_u, s.theta_u, obs_, xchg=xchg)
+
         def full_step(i):
             s = sets[i % 4]
             torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)  # stand-in for PhysX, not one of our kernels
-            ops.mdp_pre_step(buf, params, s.actions, s.force_matrix_w)
-            ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
-                              s.theta_u, obs)
+            mdp(buf, params, th, s.actions, s, obs)
             ops.height_scan(s.root_pos_w, s.root_quat_w, rays, grid, out=obs[:, 4:], variant=args.variant)
             if world > 1:
                 stats.all_reduce_async()
@@ -336,9 +345,7 @@ def run_ours(args):
         def mdp_only(i):
             s = sets[i % 4]
             torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)
-            ops.mdp_pre_step(buf, params, s.actions, s.force_matrix_w)
-            ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
-                              s.theta_u, obs)
+            mdp(buf, params, th, s.actions, s, obs)
 
         ksteps = max(min(args.steps, 200), 3)
         # the step is launch-bound on the host side (3 ctypes launches + 1 torch op ~ 40 us of Python per step):
@@ -353,9 +360,7 @@ def run_ours(args):
             def step_body(i):  # noqa: F811  (kernels only; an NCCL all-reduce, if used, is issued after the replay)
                 s = sets[i % 4]
                 torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)
-                ops.mdp_pre_step(buf, params, s.actions, s.force_matrix_w)
-                ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
-                                  s.theta_u, obs, xchg=p2p)
+                mdp(buf, params, th, s.actions, s, obs, xchg=p2p)
                 ops.height_scan(s.root_pos_w, s.root_quat_w, rays, grid, out=obs[:, 4:], variant=args.variant)
         g_full = graphed(step_body)
         g_mdp = graphed(mdp_only)
@@ -395,7 +400,7 @@ def run_ours(args):
                             + (" + NCCL episode-stat all-reduce" if world > 1 else ""),
                 "env_steps_per_s": n_step * world * ksteps / (float(tf[0]) * 1e-3),
                 "ms_per_step": float(tf[0]) / ksteps,
-                "gpu_launches_per_step": 3, "cuda_graph": not args.no_graph,
+                "gpu_launches_per_step": 2 if args.single_launch_mdp else 3, "cuda_graph": not args.no_graph,
                 "roofline_frac_hbm": full_bytes / (float(tf[0]) / ksteps * 1e-3) / 1e9 / peak,
                 "resets_in_one_step": resets_per_step,
                 "episode_stats": stats_check,
@@ -404,7 +409,7 @@ def run_ours(args):
                 "env_steps_per_s": n_step * world * ksteps / (float(tf[1]) * 1e-3),
                 "ms_per_step": float(tf[1]) / ksteps,
                 "roofline_frac_hbm": n_step * 414.0 / (float(tf[1]) / ksteps * 1e-3) / 1e9 / peak,
-                "note": "two launches over 414 B/env: launch-latency bound at this N (SURVEY.md 8d)",
+                "note": "414 B/env: launch-latency bound at this N (SURVEY.md 8d); pre + post launch (one launch with --single-launch-mdp, measured 1.4 us slower)",
             },
         }
     except Exception as e:  # the headline number must survive a failure of the extra measurements
@@ -470,9 +475,7 @@ def run_ours(args):
         def closed_step(i):
             s = sets[i % 4]
             torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)  # stand-in for PhysX
-            ops.mdp_pre_step(buf, params, act_buf, s.force_matrix_w)
-            ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
-                              s.theta_u, loop_obs)
+            mdp(buf, params, th, act_buf, s, loop_obs)
             ops.height_scan(s.root_pos_w, s.root_quat_w, rays, grid, out=loop_obs[:, 4:], variant=args.variant)
             actions, _, _ = net.act({"states": loop_obs}, eps=eps_sets[i % 4])
             act_buf.copy_(actions)
@@ -482,9 +485,7 @@ def run_ours(args):
         def closed_step_bf16(i):  # the scan also writes the bf16 observation; the policy reads only that
             s = sets[i % 4]
             torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)
-            ops.mdp_pre_step(buf, params, act_buf, s.force_matrix_w)
-            ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
-                              s.theta_u, loop_obs)
+            mdp(buf, params, th, act_buf, s, loop_obs)
             ops.height_scan_obs(s.root_pos_w, s.root_quat_w, rays, grid, loop_obs, loop_obs_bf)
             actions, _, _ = net.act({"states": loop_obs_bf}, eps=eps_sets[i % 4])
             act_buf.copy_(actions)
@@ -500,7 +501,8 @@ def run_ours(args):
             "workload": f"{n_step} envs/GPU: pre_step + post_step + height scan + policy forward (tcgen05) + Gaussian act, "
                         "actions fed back to the next step; physics replaced by a synthetic pose update",
             "env_steps_per_s": n_step * world * ksteps / (float(tl[0]) * 1e-3),
-            "ms_per_step": float(tl[0]) / ksteps, "gpu_launches_per_step": 5, "cuda_graph": not args.no_graph,
+            "ms_per_step": float(tl[0]) / ksteps, "gpu_launches_per_step": 4 if args.single_launch_mdp else 5,
+            "cuda_graph": not args.no_graph,
             "finite_actions": bool(torch.isfinite(act_buf).all().item()),
             "bf16_observation": {"env_steps_per_s": n_step * world * ksteps / (float(tl[1]) * 1e-3),
                                  "ms_per_step": float(tl[1]) / ksteps,
@@ -628,6 +630,8 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--single-launch-mdp", action="store_true",
+                    help="fused step through the single rover_mdp_step launch instead of rover_mdp_pre_step + rover_mdp_post_step")
     ap.add_argument("--variant", type=int, default=int(os.environ.get("ROVER_SCAN_VARIANT", "5")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the fused step kernel by kernel instead of replaying CUDA graphs")

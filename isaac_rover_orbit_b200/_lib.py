@@ -21,7 +21,7 @@ MDP_BLOCK = 64
 ABI_VERSION = 2
 
 SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_height_scan_obs", "rover_mdp_pre_step",
-           "rover_mdp_post_step", "rover_mdp_post_step_x", "rover_stats_read", "rover_p2p_alloc", "rover_p2p_free",
+           "rover_mdp_post_step", "rover_mdp_post_step_x", "rover_mdp_step", "rover_stats_read", "rover_p2p_alloc", "rover_p2p_free",
            "rover_p2p_export", "rover_p2p_open", "rover_p2p_close",
            "rover_ackermann",
            "rover_policy_pack", "rover_policy_forward", "rover_value_forward", "rover_policy_forward_bf16",
@@ -125,6 +125,10 @@ def load() -> C.CDLL:
     lib.rover_mdp_post_step_x.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
                                           C.POINTER(TerrainTables), vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32,
                                           C.POINTER(StatsExchange), vp]
+    lib.rover_mdp_step.restype = C.c_int
+    lib.rover_mdp_step.argtypes = [vp, vp, vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
+                                   C.POINTER(TerrainTables), vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32,
+                                   C.POINTER(StatsExchange), vp]
     lib.rover_stats_read.restype = C.c_int
     lib.rover_stats_read.argtypes = [vp, i32, vp, vp]
     lib.rover_p2p_alloc.restype = C.c_int

@@ -202,11 +202,10 @@ __global__ void ackermann_kernel(const float* __restrict__ actions, int n, const
     ackermann_dispatch(P, lin_p, ang_p, jp + 4 * (size_t)i, jv + 6 * (size_t)i);
 }
 
-__global__ void __launch_bounds__(ROVER_MDP_BLOCK)
-mdp_pre_step_kernel(const float* __restrict__ new_actions, const float* __restrict__ force, int n,
-                    const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
-                    const __grid_constant__ RoverMdpOut O, int phases) {
-    const int i = blockIdx.x * ROVER_MDP_BLOCK + threadIdx.x;
+// The per-env work of the pre-step (one thread per env); returns the env's reset flag.
+__device__ __forceinline__ bool pre_step_env(int i, const float* __restrict__ new_actions, const float* __restrict__ force,
+                                             int n, const RoverMdpParams& P, const RoverMdpState& S, const RoverMdpOut& O,
+                                             int phases) {
     bool reset = false;
     if (i < n) {
         float2 a_old, a;
@@ -281,6 +280,15 @@ mdp_pre_step_kernel(const float* __restrict__ new_actions, const float* __restri
         O.reward[i] = total;
         }
     }
+    return reset;
+}
+
+__global__ void __launch_bounds__(ROVER_MDP_BLOCK)
+mdp_pre_step_kernel(const float* __restrict__ new_actions, const float* __restrict__ force, int n,
+                    const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
+                    const __grid_constant__ RoverMdpOut O, int phases) {
+    const int i = blockIdx.x * ROVER_MDP_BLOCK + threadIdx.x;
+    const bool reset = pre_step_env(i, new_actions, force, n, P, S, O, phases);
     if (phases & ROVER_PRE_TERMS) {
         const int cnt = __syncthreads_count(reset);
         if (threadIdx.x == 0) O.block_reset_counts[blockIdx.x] = cnt;
@@ -361,24 +369,35 @@ struct StatsExchangeDev {
     int rank, world;  // world == 0: no exchange
 };
 
-__global__ void __launch_bounds__(ROVER_MDP_BLOCK)
-mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_quat_w, int n,
-                     const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
-                     const __grid_constant__ RoverMdpOut O, const __grid_constant__ Tables T,
-                     const long long* __restrict__ spawn_perm, const float* __restrict__ yaw_u,
-                     const float* __restrict__ heading_u, const float* __restrict__ theta_u, int n_rounds,
-                     long long* __restrict__ out_spawn_index, float* __restrict__ block_stats,
-                     unsigned int* __restrict__ done_counter, float* __restrict__ stats, float* __restrict__ obs,
-                     int obs_stride, int phases, const __grid_constant__ StatsExchangeDev X) {
+// look-back descriptor of the fused step: [epoch : 30 | status : 2 | value : 32]
+constexpr unsigned long long kDescAggregate = 1ull, kDescPrefix = 2ull;
+__device__ __forceinline__ unsigned long long make_lookback(unsigned epoch, unsigned long long status, unsigned value) {
+    return ((unsigned long long)(epoch & 0x3fffffffu) << 34) | (status << 32) | value;
+}
+
+// The block-level work of the post-step.  kFused = false: the reset flags and the per-block reset counts come from the
+// pre-step launch.  kFused = true (rover_mdp_step): `reset_in` comes from pre_step_env of the same thread and the rank of
+// the block's first reset env from a decoupled look-back over the blocks' reset counts (no second launch).
+template <bool kFused>
+__device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool reset_in, float* __restrict__ root_pos_w,
+                                                float* __restrict__ root_quat_w, int n, const RoverMdpParams& P,
+                                                const RoverMdpState& S, const RoverMdpOut& O, const Tables& T,
+                                                const long long* __restrict__ spawn_perm, const float* __restrict__ yaw_u,
+                                                const float* __restrict__ heading_u, const float* __restrict__ theta_u,
+                                                int n_rounds, long long* __restrict__ out_spawn_index,
+                                                float* __restrict__ block_stats, unsigned int* __restrict__ done_counter,
+                                                float* __restrict__ stats, float* __restrict__ obs, int obs_stride, int phases,
+                                                const StatsExchangeDev& X, unsigned long long* __restrict__ lookback,
+                                                unsigned epoch) {
     __shared__ int warp_cnt[ROVER_MDP_BLOCK / 32];
     __shared__ int block_base;
     constexpr int kRedRows = ROVER_MDP_BLOCK / 4;  // 16 row groups of the last-block reduction (>= warps per block)
     __shared__ float red[kRedRows][kStats];
     __shared__ bool is_last;
-    const int i = blockIdx.x * ROVER_MDP_BLOCK + threadIdx.x;
+    const int i = bid * ROVER_MDP_BLOCK + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool valid = i < n;
-    const bool reset = valid && O.reset_flags[i] != 0;
+    const bool reset = kFused ? (valid && reset_in) : (valid && O.reset_flags[i] != 0);
 
     // ---- every load that does not depend on the reset rank is issued up front, so that the kernel pays one memory
     //      round trip for them instead of one per dependent stage (this launch is latency-bound, not bandwidth-bound)
@@ -400,15 +419,55 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
     }
 
     // ---- rank of this env among the reset envs in ascending env order (== reset_buf.nonzero() order)
-    if (wid == 0) {
-        int acc = 0;
-        for (int b = lane; b < (int)blockIdx.x; b += 32) acc += O.block_reset_counts[b];
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) block_base = acc;
-    }
     const unsigned ballot = __ballot_sync(0xffffffffu, reset);
     if (lane == 0) warp_cnt[wid] = __popc(ballot);
-    __syncthreads();
+    if (!kFused) {
+        if (wid == 0) {
+            int acc = 0;
+            for (int b = lane; b < bid; b += 32) acc += O.block_reset_counts[b];
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) block_base = acc;
+        }
+        __syncthreads();
+    } else {
+        __syncthreads();
+        if (wid == 0) {
+            // decoupled look-back (single pass): publish this block's count, walk back over the predecessors' descriptors
+            // until one carries an inclusive prefix, publish our own.  Logical block ids are tickets, so every
+            // predecessor has started; descriptors are tagged with the launch epoch, so nothing is re-zeroed.
+            int cnt = 0;
+            for (int w = 0; w < ROVER_MDP_BLOCK / 32; ++w) cnt += warp_cnt[w];
+            volatile unsigned long long* desc = lookback;
+            int base = 0;
+            if (bid > 0) {
+                if (lane == 0) desc[bid] = make_lookback(epoch, kDescAggregate, (unsigned)cnt);
+                int look = bid - 1;
+                while (true) {
+                    const int idx = look - lane;
+                    unsigned long long d = make_lookback(epoch, kDescPrefix, 0u);  // before block 0: prefix 0
+                    if (idx >= 0) {
+                        do {
+                            d = desc[idx];
+                        } while ((unsigned)(d >> 34) != (epoch & 0x3fffffffu) || ((d >> 32) & 3ull) == 0ull);
+                    }
+                    const bool is_prefix = ((d >> 32) & 3ull) == kDescPrefix;
+                    const unsigned pmask = __ballot_sync(0xffffffffu, is_prefix);
+                    const int first = pmask ? __ffs(pmask) - 1 : 32;  // closest predecessor with an inclusive prefix
+                    int v = (lane <= first) ? (int)(unsigned)(d & 0xffffffffull) : 0;
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    base += v;
+                    if (pmask) break;
+                    look -= 32;
+                }
+            }
+            if (lane == 0) {
+                __threadfence();
+                desc[bid] = make_lookback(epoch, kDescPrefix, (unsigned)(base + cnt));
+                block_base = base;
+            }
+        }
+        __syncthreads();
+    }
     int rank = block_base + __popc(ballot & ((1u << lane) - 1u));
     for (int w = 0; w < wid; ++w) rank += warp_cnt[w];
 
@@ -542,11 +601,11 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
     if (threadIdx.x < kStats) {
         float v = 0.f;
         for (int w = 0; w < ROVER_MDP_BLOCK / 32; ++w) v += red[w][threadIdx.x];
-        block_stats[(size_t)blockIdx.x * kStats + threadIdx.x] = v;
+        block_stats[(size_t)bid * kStats + threadIdx.x] = v;
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) is_last = (atomicAdd(done_counter, 1u) == (unsigned)n_blocks - 1u);
     __syncthreads();
     if (is_last) {
         // Fixed summation tree (deterministic, same result for the same inputs whatever the block schedule): thread t
@@ -557,12 +616,12 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
         constexpr int kGroups = ROVER_MDP_BLOCK / 4, kUnroll = 16;
         const int c4 = threadIdx.x & 3, g = threadIdx.x >> 2;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (unsigned b0 = g; b0 < gridDim.x; b0 += kGroups * kUnroll) {
+        for (unsigned b0 = g; b0 < (unsigned)n_blocks; b0 += kGroups * kUnroll) {
             float4 x[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 const unsigned bb = b0 + u * kGroups;
-                x[u] = bb < gridDim.x ? __ldcg(reinterpret_cast<const float4*>(block_stats + (size_t)bb * kStats) + c4)
+                x[u] = bb < (unsigned)n_blocks ? __ldcg(reinterpret_cast<const float4*>(block_stats + (size_t)bb * kStats) + c4)
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
@@ -577,7 +636,13 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
             float t = 0.f;
             for (int q = 0; q < G; ++q) t += red[q][threadIdx.x];
             stats[threadIdx.x] += t;
-            if (threadIdx.x == 0) *done_counter = 0u;  // re-arm for the next launch
+            if (threadIdx.x == 0) {
+                *done_counter = 0u;  // re-arm for the next launch
+                if (kFused) {        // fused step: next launch = next epoch, tickets from 0 again
+                    lookback[n_blocks] = 0ull;
+                    lookback[n_blocks + 1] = (unsigned long long)(epoch + 1u);
+                }
+            }
             if (X.world > 0) {
                 total = X.cumulative[threadIdx.x] + (double)t;
                 X.cumulative[threadIdx.x] = total;
@@ -606,6 +671,70 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
             if (threadIdx.x == 0) *X.sequence = seq;
         }
     }
+}
+
+__global__ void __launch_bounds__(ROVER_MDP_BLOCK)
+mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_quat_w, int n,
+                     const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
+                     const __grid_constant__ RoverMdpOut O, const __grid_constant__ Tables T,
+                     const long long* __restrict__ spawn_perm, const float* __restrict__ yaw_u,
+                     const float* __restrict__ heading_u, const float* __restrict__ theta_u, int n_rounds,
+                     long long* __restrict__ out_spawn_index, float* __restrict__ block_stats,
+                     unsigned int* __restrict__ done_counter, float* __restrict__ stats, float* __restrict__ obs,
+                     int obs_stride, int phases, const __grid_constant__ StatsExchangeDev X) {
+    post_step_block<false>((int)blockIdx.x, (int)gridDim.x, false, root_pos_w, root_quat_w, n, P, S, O, T, spawn_perm, yaw_u,
+                           heading_u, theta_u, n_rounds, out_spawn_index, block_stats, done_counter, stats, obs, obs_stride,
+                           phases, X, nullptr, 0u);
+}
+
+// rover_mdp_step: pre-step + post-step of one env block in ONE launch (the reset rank comes from a look-back instead of a
+// second launch; the pre-step's outputs of an env are consumed by the same thread).  lookback: [n_blocks] descriptors,
+// then the ticket counter and the epoch (both maintained by the kernel itself, so the launch can sit in a CUDA graph).
+__global__ void __launch_bounds__(ROVER_MDP_BLOCK)
+mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __restrict__ force,
+                      float* __restrict__ root_pos_w, float* __restrict__ root_quat_w, int n,
+                      const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
+                      const __grid_constant__ RoverMdpOut O, const __grid_constant__ Tables T,
+                      const long long* __restrict__ spawn_perm, const float* __restrict__ yaw_u,
+                      const float* __restrict__ heading_u, const float* __restrict__ theta_u, int n_rounds,
+                      long long* __restrict__ out_spawn_index, float* __restrict__ block_stats,
+                      unsigned int* __restrict__ done_counter, float* __restrict__ stats, float* __restrict__ obs,
+                      int obs_stride, int pre_phases, int phases, const __grid_constant__ StatsExchangeDev X,
+                      unsigned long long* __restrict__ lookback, int use_tickets) {
+    __shared__ int s_bid;
+    __shared__ unsigned s_epoch;
+    const int n_blocks = (int)gridDim.x;
+    int bid = (int)blockIdx.x;
+    unsigned long long epoch_raw = 0ull;
+    if (threadIdx.x == 0) epoch_raw = *reinterpret_cast<volatile unsigned long long*>(lookback + n_blocks + 1);
+    if (use_tickets) {  // more blocks than the device holds at once: logical ids by ticket, so predecessors have started
+        if (threadIdx.x == 0) s_bid = (int)atomicAdd(lookback + n_blocks, 1ull);
+        __syncthreads();
+        bid = s_bid;
+    }
+    const int i = bid * ROVER_MDP_BLOCK + threadIdx.x;
+    if (i < n) {  // the post-step's rank-independent inputs: in flight while the pre-step part runs
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(root_pos_w + 3 * (size_t)i));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(root_quat_w + 4 * (size_t)i));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.pos_cmd_w + 3 * (size_t)i));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(theta_u + (size_t)i * n_rounds));
+        if ((threadIdx.x & 31) == 0) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(S.heading_cmd_w + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(S.time_left + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(yaw_u + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(heading_u + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(S.err_pos + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(S.err_heading + i));
+        }
+    }
+    const bool reset = pre_step_env(i, new_actions, force, n, P, S, O, pre_phases);
+    if (threadIdx.x == 0) s_epoch = (unsigned)epoch_raw;
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    if ((pre_phases & ROVER_PRE_TERMS) && threadIdx.x == 0) O.block_reset_counts[bid] = 0;  // unused by this path
+    post_step_block<true>(bid, n_blocks, reset, root_pos_w, root_quat_w, n, P, S, O, T, spawn_perm, yaw_u, heading_u,
+                          theta_u, n_rounds, out_spawn_index, block_stats, done_counter, stats, obs, obs_stride, phases, X,
+                          lookback, epoch);
 }
 
 // one block: thread (p, k) = (threadIdx.x / 16, threadIdx.x % 16) reads statistic k of rank p's slot consistently
@@ -733,6 +862,57 @@ extern "C" int rover_mdp_post_step_x(float* root_pos_w, float* root_quat_w, int3
         yaw_u, heading_u, theta_u, n_rounds, reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats,
         obs, obs_stride, phases, X);
     return check_launch("mdp_post_step_kernel");
+}
+
+extern "C" int rover_mdp_step(const float* new_actions, const float* force_matrix_w, float* root_pos_w, float* root_quat_w,
+                              int32_t n_envs, const RoverMdpParams* params, const RoverMdpState* state,
+                              const RoverMdpOut* out, const RoverTerrainTables* tables, const int64_t* spawn_perm,
+                              const float* yaw_u, const float* heading_u, const float* theta_u, int32_t n_rounds,
+                              int64_t* out_spawn_index, float* stats, float* scratch, uint64_t* lookback, float* obs,
+                              int32_t obs_stride, int32_t pre_phases, int32_t phases, const RoverStatsExchange* xchg,
+                              void* stream) {
+    using namespace rover;
+    ROVER_CHECK(n_envs >= 0, "rover_mdp_step: negative n_envs");
+    if (n_envs == 0) return 0;
+    ROVER_CHECK(params && (new_actions || !(pre_phases & ROVER_PRE_ACTIONS)) &&
+                    (force_matrix_w || !(pre_phases & ROVER_PRE_TERMS)) && root_pos_w && root_quat_w && tables &&
+                    spawn_perm && yaw_u && heading_u && theta_u && stats && scratch && lookback,
+                "rover_mdp_step: NULL argument");
+    ROVER_CHECK(params->num_bodies >= 0 && params->max_episode_length > 0 && n_rounds >= 1, "rover_mdp_step: bad params");
+    ROVER_CHECK(tables->heightmap && tables->safe_mask && tables->spawn_table && tables->height > 0 &&
+                    tables->width > 0 && tables->n_spawns > 0 && tables->resolution > 0.f,
+                "rover_mdp_step: bad terrain tables");
+    ROVER_CHECK((reinterpret_cast<uintptr_t>(root_quat_w) & 15) == 0, "rover_mdp_step: root_quat_w not 16B aligned");
+    ROVER_CHECK(obs == nullptr || obs_stride >= 4, "rover_mdp_step: obs_stride < 4");
+    if (int rc = check_state(state, out)) return rc;
+    StatsExchangeDev X{nullptr, nullptr, nullptr, 0, 0};
+    if (xchg != nullptr) {
+        ROVER_CHECK(xchg->peer_mailbox && xchg->cumulative && xchg->sequence && xchg->world >= 1 && xchg->rank >= 0 &&
+                        xchg->rank < xchg->world,
+                    "rover_mdp_step: bad RoverStatsExchange");
+        X = StatsExchangeDev{xchg->peer_mailbox, xchg->cumulative,
+                             reinterpret_cast<unsigned long long*>(xchg->sequence), xchg->rank, xchg->world};
+    }
+    Tables T{tables->heightmap, tables->safe_mask, tables->height,   tables->width,   tables->offset_x,
+             tables->offset_y,  tables->resolution, tables->spawn_table, tables->n_spawns};
+    const int blocks = (n_envs + ROVER_MDP_BLOCK - 1) / ROVER_MDP_BLOCK;
+    float* block_stats = scratch;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + (size_t)blocks * ROVER_STATS_LEN);
+    // how many blocks the device holds at once: below that every block is resident and blockIdx is a safe logical id
+    static int resident_blocks = 0;
+    if (resident_blocks == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        ROVER_CUDA(cudaGetDevice(&dev));
+        ROVER_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        ROVER_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mdp_fused_step_kernel, ROVER_MDP_BLOCK, 0));
+        resident_blocks = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    mdp_fused_step_kernel<<<blocks, ROVER_MDP_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(
+        new_actions, force_matrix_w, root_pos_w, root_quat_w, n_envs, *params, *state, *out, T,
+        reinterpret_cast<const long long*>(spawn_perm), yaw_u, heading_u, theta_u, n_rounds,
+        reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats, obs, obs_stride, pre_phases, phases, X,
+        reinterpret_cast<unsigned long long*>(lookback), blocks > resident_blocks ? 1 : 0);
+    return check_launch("mdp_fused_step_kernel");
 }
 
 extern "C" int rover_stats_read(const void* mailbox_local, int32_t world, double* out, void* stream) {

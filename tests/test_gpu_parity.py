@@ -356,6 +356,70 @@ def test_mdp_step_vs_oracle(world):
     assert total_resets > 10, "the fixture must exercise resets"
 
 
+@pytest.mark.parametrize("n", [64, 5000, 16384 + 17])
+def test_mdp_fused_single_launch_equals_two_launches(cuda_device, n):
+    """rover_mdp_step (pre + post in one launch, reset rank by decoupled look-back) against the two-launch sequence over
+    consecutive steps with carried state: every buffer bit-identical (ranks, spawn rows, resampled commands, rewards,
+    statistics); then the fused launch replayed from a CUDA graph (the kernel maintains its own epoch / tickets)."""
+    v, f = TR.make_synthetic_terrain(SIZE, RES, seed=3)
+    tables = TR.build_terrain_tables(v, f, n)
+    cfg = RoverEnvCfg(num_envs=n)
+    params = ops.mdp_params(cfg)
+    th = ops.TerrainTablesHandle(tables.heightmap, tables.safe_mask, tables.offset_xy, tables.spawn_table,
+                                 tables.resolution, cuda_device)
+    gen = torch.Generator().manual_seed(31)
+    vt = torch.from_numpy(v)
+    bufs = [ops.MdpBuffers.allocate(n, cuda_device) for _ in range(2)]
+    for b in bufs:
+        b.time_left.fill_(150.0)
+        b.time_left[: n // 50] = 0.05  # time-based resamples as well
+    obs = [torch.zeros(n, 965, device=cuda_device) for _ in range(2)]
+    names = ("action", "prev_action", "pos_cmd_w", "heading_cmd_w", "pos_cmd_b", "heading_cmd_b", "time_left",
+             "command_counter", "episode_length_buf", "episode_sums", "env_origins", "err_pos", "err_heading",
+             "processed_actions", "joint_pos", "joint_vel", "reward", "term_rewards", "term_values", "terminated",
+             "truncated", "term_flags", "reset_flags", "spawn_index", "stats")
+    steps = [synthetic.make_step(n, gen, vt, SIZE, RES, margin=4.0).to(cuda_device) for _ in range(4)]
+    total_resets = 0
+    for k, st in enumerate(steps):
+        pos = [st.root_pos_w.clone(), st.root_pos_w.clone()]
+        quat = [st.root_quat_w.clone(), st.root_quat_w.clone()]
+        ops.mdp_pre_step(bufs[0], params, st.actions, st.force_matrix_w)
+        ops.mdp_post_step(bufs[0], params, th, pos[0], quat[0], st.spawn_perm, st.yaw_u, st.heading_u, st.theta_u, obs[0])
+        ops.mdp_step(bufs[1], params, th, st.actions, st.force_matrix_w, pos[1], quat[1], st.spawn_perm, st.yaw_u,
+                     st.heading_u, st.theta_u, obs[1])
+        torch.cuda.synchronize()
+        for name in names:
+            assert torch.equal(getattr(bufs[0], name), getattr(bufs[1], name)), f"step {k}: {name}"
+        assert torch.equal(pos[0], pos[1]) and torch.equal(quat[0], quat[1]) and torch.equal(obs[0], obs[1])
+        total_resets += int(bufs[0].reset_flags.sum())
+    assert total_resets > 0 and float(bufs[1].stats[13]) == total_resets
+    # CUDA-graph replay of the fused launch: epoch and tickets live on the device
+    st = steps[0]
+    pos_g, quat_g = st.root_pos_w.clone(), st.root_quat_w.clone()
+    g = torch.cuda.CUDAGraph()
+    ops.mdp_step(bufs[1], params, th, st.actions, st.force_matrix_w, pos_g, quat_g, st.spawn_perm, st.yaw_u, st.heading_u,
+                 st.theta_u, obs[1])  # warm-up outside capture (state advances on both sides below)
+    ops.mdp_pre_step(bufs[0], params, st.actions, st.force_matrix_w)
+    pos_e, quat_e = st.root_pos_w.clone(), st.root_quat_w.clone()
+    ops.mdp_post_step(bufs[0], params, th, pos_e, quat_e, st.spawn_perm, st.yaw_u, st.heading_u, st.theta_u, obs[0])
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        ops.mdp_step(bufs[1], params, th, st.actions, st.force_matrix_w, pos_g, quat_g, st.spawn_perm, st.yaw_u,
+                     st.heading_u, st.theta_u, obs[1])
+    for _ in range(3):
+        pos_g.copy_(st.root_pos_w)
+        quat_g.copy_(st.root_quat_w)
+        g.replay()
+        pos_e.copy_(st.root_pos_w)
+        quat_e.copy_(st.root_quat_w)
+        ops.mdp_pre_step(bufs[0], params, st.actions, st.force_matrix_w)
+        ops.mdp_post_step(bufs[0], params, th, pos_e, quat_e, st.spawn_perm, st.yaw_u, st.heading_u, st.theta_u, obs[0])
+        torch.cuda.synchronize()
+        for name in names:
+            assert torch.equal(getattr(bufs[0], name), getattr(bufs[1], name)), f"graph replay: {name}"
+        assert torch.equal(pos_e, pos_g) and torch.equal(obs[0], obs[1])
+
+
 def test_mdp_terms_against_reference_golden(cuda_device, golden_dir):
     """The fused kernel against outputs of the UNMODIFIED reference functions (tests/golden/terms.npz)."""
     z = np.load(os.path.join(golden_dir, "terms.npz"))
