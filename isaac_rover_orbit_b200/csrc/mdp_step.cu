@@ -319,20 +319,22 @@ __device__ __forceinline__ void terrain_cell(const Tables& T, float x, float y, 
 // CommandTerm._resample + _resample_command + sample_new_targets (terrain_importer.py:74-95, 134-175).
 // The reference's rejection loop is sequential (one host sync per round); here the candidates of a batch of 8 rounds
 // are generated together and their mask bytes fetched concurrently (one memory round trip per batch instead of per
-// round), then the first valid round wins -- the same candidate the sequential loop would have accepted.
+// round), then the first valid round wins -- the same candidate the sequential loop would have accepted.  The height
+// under every candidate is fetched in the same round trip (speculatively: 8 loads for the ~5 % of envs that resample),
+// which takes the heightmap lookup off the dependent chain rank -> spawn row -> mask -> height.
 __device__ __forceinline__ bool resample_command(int i, const RoverMdpParams& P, const RoverMdpState& S, const Tables& T,
                                                  float ox, float oy, const float* __restrict__ theta_u,
                                                  const float (&theta0)[8], int n_rounds, float heading_u, float& cx,
                                                  float& cy, float& cz, float& chead) {
     const float pi_f = 3.1415927f;  // torch.pi as fp32; the reference computes rand * 2 * pi left to right
     constexpr int kBatch = 8;
-    float x = 0.f, y = 0.f;
-    int col = 0, row = 0;
+    float x = 0.f, y = 0.f, z = 0.f;
     bool bad = true;
     for (int r0 = 0; r0 < n_rounds && bad; r0 += kBatch) {
         float u[kBatch], xs[kBatch], ys[kBatch];
         int cols[kBatch], rows[kBatch];
         uint8_t m[kBatch];
+        float hz[kBatch];
 #pragma unroll
         for (int k = 0; k < kBatch; ++k)  // the first batch was prefetched by the caller
             u[k] = (r0 == 0) ? theta0[k] : ((r0 + k < n_rounds) ? __ldg(theta_u + (size_t)i * n_rounds + r0 + k) : 0.f);
@@ -343,18 +345,19 @@ __device__ __forceinline__ bool resample_command(int i, const RoverMdpParams& P,
             ys[k] = __fadd_rn(__fmul_rn(sinf(th), P.target_distance), oy);               // :173
             terrain_cell(T, xs[k], ys[k], cols[k], rows[k]);
             m[k] = __ldg(T.safe_mask + (size_t)rows[k] * T.W + cols[k]);                 // :220
+            hz[k] = __ldg(T.heightmap + (size_t)rows[k] * T.W + cols[k]);                // :154, used if round k wins
         }
 #pragma unroll
         for (int k = 0; k < kBatch; ++k) {
             if (bad && r0 + k < n_rounds) {  // sequential semantics: the first valid round, else the last tried
-                x = xs[k], y = ys[k], col = cols[k], row = rows[k];
+                x = xs[k], y = ys[k], z = hz[k];
                 bad = m[k] == 1;
             }
         }
     }
     cx = x;
     cy = y;
-    cz = __ldg(T.heightmap + (size_t)row * T.W + col);                       // :154 (+ default_root_state z = 0)
+    cz = z;                                                                  // :154 (+ default_root_state z = 0)
     chead = __fadd_rn(__fmul_rn(heading_u, __fsub_rn(P.heading_hi, P.heading_lo)), P.heading_lo);  // uniform_(lo, hi)
     S.time_left[i] = P.resampling_time;
     return bad;
@@ -478,6 +481,8 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
     if (valid) {
         long long spawn_idx = -1;
         bool cmd_dirty = false;
+        bool origin_known = false;  // env origin of a freshly spawned env stays in registers (no store -> load round trip)
+        float org_x = 0.f, org_y = 0.f;
 
         if (reset && (phases & ROVER_PHASE_SPAWN)) {
             // -- reset_root_state_rover (randomizations.py:12-39)
@@ -489,6 +494,7 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
             const float angle = __fmul_rn(__fmul_rn(yaw_var, 2.f), 3.1415927f);
             const float half = __fdiv_rn(angle, 2.f);
             q = make_float4(cosf(half), 0.f, 0.f, sinf(half));
+            org_x = px, org_y = py, origin_known = true;
             S.env_origins[3 * (size_t)i] = px;
             S.env_origins[3 * (size_t)i + 1] = py;
             S.env_origins[3 * (size_t)i + 2] = pz;
@@ -526,7 +532,8 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
         }
         if (reset && (phases & ROVER_PHASE_RESAMPLE)) {
             // -- CommandTerm._resample: time_left, counter += 1, _resample_command around the (new) env origin
-            const float ox = S.env_origins[3 * (size_t)i], oy = S.env_origins[3 * (size_t)i + 1];
+            const float ox = origin_known ? org_x : S.env_origins[3 * (size_t)i];
+            const float oy = origin_known ? org_y : S.env_origins[3 * (size_t)i + 1];
             const bool exhausted = resample_command(i, P, S, T, ox, oy, theta_u, theta0, n_rounds, heading_var, cwx,
                                                     cwy, cwz, chead);
             st[14] = exhausted ? 1.f : 0.f;
@@ -545,7 +552,8 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
         }
         if (phases & ROVER_PHASE_TIME) time_left = __fsub_rn(time_left, P.step_dt);
         if ((phases & ROVER_PHASE_TIME) && time_left <= 0.f) {
-            const float ox = S.env_origins[3 * (size_t)i], oy = S.env_origins[3 * (size_t)i + 1];
+            const float ox = origin_known ? org_x : S.env_origins[3 * (size_t)i];
+            const float oy = origin_known ? org_y : S.env_origins[3 * (size_t)i + 1];
             const bool exhausted = resample_command(i, P, S, T, ox, oy, theta_u, theta0, n_rounds, heading_var, cwx,
                                                     cwy, cwz, chead);
             st[14] += exhausted ? 1.f : 0.f;
