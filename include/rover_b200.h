@@ -317,6 +317,26 @@ int rover_value_forward_bf16(const uint16_t* obs_bf16, int32_t stride, int32_t n
 int rover_gaussian_act(const float* mean, const float* log_std, const float* eps, int32_t n_envs, float* actions,
                        float* log_prob, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Init-time terrain tables.  Not on the step path; built once per terrain.
+ * rover_mesh_to_heightmap replaces mesh_to_heightmap (rover_envs/utils/terrains/terrain_utils.py:23-57): per face, the
+ * cells covered by its XY bounding box take max(cell, max z of the face).  heightmap [rows, cols] fp32 must be
+ * pre-filled with -99 (the reference's "no data" value); (min_x, min_y) = mesh bounds shrunk by the 1 m border,
+ * (cell_x, cell_y) = (max - min) / grid_size as the reference computes them in fp32.  Indices truncate toward zero,
+ * only the upper index is clamped and negative indices wrap once (Python indexing) -- the reference's quirks, kept
+ * because the per-step lookups read the table they define.  *out_of_range (device, zeroed by the caller) counts faces
+ * whose indices fall beyond the wrap range (the reference raises IndexError there).  Bit-identical: max() does not
+ * depend on the visiting order.
+ * rover_steep_mask replaces the first stage of find_rocks_in_heightmap (terrain_utils.py:265-279): Sobel gradients
+ * with wrap-around borders in float64, steep = |grad| > threshold (uint8 0/1).  The morphological clean-up that follows
+ * (:281-311, OpenCV / scipy) stays on the host.
+ * ------------------------------------------------------------------------------------------------- */
+int rover_mesh_to_heightmap(const float* vertices /* [V,3] */, const int32_t* faces /* [F,3] */, int32_t n_faces,
+                            float min_x, float min_y, float cell_x, float cell_y, int32_t rows, int32_t cols,
+                            float* heightmap, int32_t* out_of_range, void* stream);
+int rover_steep_mask(const float* heightmap, int32_t rows, int32_t cols, double threshold, uint8_t* steep /* [rows, cols] */,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_
            "rover_p2p_export", "rover_p2p_open", "rover_p2p_close",
            "rover_ackermann",
            "rover_policy_pack", "rover_policy_forward", "rover_value_forward", "rover_policy_forward_bf16",
-           "rover_value_forward_bf16", "rover_gaussian_act")
+           "rover_value_forward_bf16", "rover_gaussian_act", "rover_mesh_to_heightmap", "rover_steep_mask")
 
 
 class ScanLevel(C.Structure):
@@ -129,6 +129,10 @@ def load() -> C.CDLL:
     lib.rover_mdp_step.argtypes = [vp, vp, vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
                                    C.POINTER(TerrainTables), vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32,
                                    C.POINTER(StatsExchange), vp]
+    lib.rover_mesh_to_heightmap.restype = C.c_int
+    lib.rover_mesh_to_heightmap.argtypes = [vp, vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, i32, vp, vp, vp]
+    lib.rover_steep_mask.restype = C.c_int
+    lib.rover_steep_mask.argtypes = [vp, i32, i32, C.c_double, vp, vp]
     lib.rover_stats_read.restype = C.c_int
     lib.rover_stats_read.argtypes = [vp, i32, vp, vp]
     lib.rover_p2p_alloc.restype = C.c_int

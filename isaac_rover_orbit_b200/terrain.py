@@ -105,6 +105,10 @@ def mesh_to_heightmap(vertices: np.ndarray, faces: np.ndarray, resolution: float
     (toward zero) and only the upper index is clamped, so faces in the lower border wrap to the far side
     through Python's negative indexing.
 
+    ``device`` = a CUDA device: the rasterisation runs in ``rover_mesh_to_heightmap`` (one thread per face, atomic max;
+    csrc/terrain_build.cu) -- bit-identical, no fallback if the library is missing.  ``device="cpu"``: the host
+    builder (vectorised torch scatter), which the CPU tests pin against the reference's golden tables.
+
     Returns ``(heightmap f32 [nx, ny], min_x, min_y, max_x, max_y)``.
     """
     v = np.asarray(vertices, dtype=np.float32)
@@ -119,6 +123,10 @@ def mesh_to_heightmap(vertices: np.ndarray, faces: np.ndarray, resolution: float
     shape = (int(gsx + 1), int(gsy + 1))
     csx = (max_x - min_x) / gsx
     csy = (max_y - min_y) / gsy
+    dev = torch.device(device)
+    if dev.type == "cuda":
+        hm = _mesh_to_heightmap_cuda(v, f, min_x, min_y, csx, csy, shape, dev)
+        return hm.cpu().numpy(), float(min_x), float(min_y), float(max_x), float(max_y)
     tri = v[f]  # [F, 3, 3]
     lo = tri.min(axis=1)
     hi = tri.max(axis=1)
@@ -130,7 +138,6 @@ def mesh_to_heightmap(vertices: np.ndarray, faces: np.ndarray, resolution: float
     di = max_i - min_i + 1
     dj = max_j - min_j + 1
     keep = (di > 0) & (dj > 0)
-    dev = torch.device(device)
     hm = torch.full((shape[0] * shape[1],), -99.0, dtype=torch.float32, device=dev)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     tmin_i, tmin_j, tdi, tdj, tz, tkeep = t(min_i), t(min_j), t(di), t(dj), t(zmax), t(keep)
@@ -149,17 +156,59 @@ def mesh_to_heightmap(vertices: np.ndarray, faces: np.ndarray, resolution: float
     return hm.view(shape).cpu().numpy(), float(min_x), float(min_y), float(max_x), float(max_y)
 
 
-def find_rocks_in_heightmap(heightmap: np.ndarray, threshold: float = GRADIENT_THRESHOLD):
-    """terrain_utils.py:265-311: Sobel gradient magnitude (wrap boundary) > threshold, then
-    close 3x3 -> fill holes -> open 7x7 -> dilate 11x11 (= rock mask) -> dilate 42x42 (= safe mask)."""
-    import cv2
-    from scipy import ndimage
+def _mesh_to_heightmap_cuda(v: np.ndarray, f: np.ndarray, min_x, min_y, csx, csy, shape, dev) -> torch.Tensor:
+    """The rasterisation of ``mesh_to_heightmap`` on the GPU (``rover_mesh_to_heightmap``); returns the device tensor."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        tv = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(dev)
+        tf = torch.from_numpy(np.ascontiguousarray(f, dtype=np.int32)).to(dev)
+        hm = torch.full(shape, -99.0, dtype=torch.float32, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.rover_mesh_to_heightmap(C.c_void_p(tv.data_ptr()), C.c_void_p(tf.data_ptr()), tf.shape[0],
+                                               float(min_x), float(min_y), float(csx), float(csy), shape[0], shape[1],
+                                               C.c_void_p(hm.data_ptr()), C.c_void_p(bad.data_ptr()),
+                                               _lib.current_stream(dev)))
+        if int(bad.item()):
+            raise IndexError("face outside the heightmap beyond the wrap range (the reference raises here too)")
+    return hm
+
+
+def steep_mask(heightmap: np.ndarray, threshold: float = GRADIENT_THRESHOLD, device="cpu") -> np.ndarray:
+    """terrain_utils.py:265-279: Sobel gradient magnitude (wrap boundary, float64) > threshold -> bool ``[H, W]``.
+    On a CUDA device the stencil runs in ``rover_steep_mask`` (csrc/terrain_build.cu)."""
+    dev = torch.device(device)
+    if dev.type == "cuda":
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            hm = torch.from_numpy(np.ascontiguousarray(heightmap, dtype=np.float32)).to(dev)
+            out = torch.empty(hm.shape, dtype=torch.uint8, device=dev)
+            _lib.check(lib.rover_steep_mask(C.c_void_p(hm.data_ptr()), hm.shape[0], hm.shape[1], float(threshold),
+                                            C.c_void_p(out.data_ptr()), _lib.current_stream(dev)))
+            return out.cpu().numpy().astype(bool)
     from scipy.signal import convolve2d
 
     kx = np.array([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]])
     gx = convolve2d(heightmap, kx, mode="same", boundary="wrap")
     gy = convolve2d(heightmap, kx.T, mode="same", boundary="wrap")
-    steep = np.sqrt(gx**2 + gy**2) > threshold
+    return np.sqrt(gx**2 + gy**2) > threshold
+
+
+def find_rocks_in_heightmap(heightmap: np.ndarray, threshold: float = GRADIENT_THRESHOLD, device="cpu"):
+    """terrain_utils.py:265-311: Sobel gradient magnitude (wrap boundary) > threshold, then
+    close 3x3 -> fill holes -> open 7x7 -> dilate 11x11 (= rock mask) -> dilate 42x42 (= safe mask).
+    ``device``: where the gradient stencil runs (``steep_mask``); the morphology is OpenCV / scipy on the host."""
+    import cv2
+    from scipy import ndimage
+
+    steep = steep_mask(heightmap, threshold, device)
     ones = lambda k: np.ones((k, k), np.uint8)  # noqa: E731
     mask = cv2.morphologyEx(steep.astype(np.uint8), cv2.MORPH_CLOSE, ones(3))
     mask = ndimage.binary_fill_holes(mask).astype(np.uint8)
@@ -221,7 +270,7 @@ def build_terrain_tables(vertices: np.ndarray, faces: np.ndarray, num_envs: int,
                          border_offset: float = SPAWN_BORDER_OFFSET, build_device=None) -> TerrainTables:
     """What ``TerrainManager.__init__`` (terrain_utils.py:92-127) computes, for ``num_envs`` envs."""
     hm, min_x, min_y, _, _ = mesh_to_heightmap(vertices, faces, device=build_device or "cpu")
-    rock, safe = find_rocks_in_heightmap(hm)
+    rock, safe = find_rocks_in_heightmap(hm, device=build_device or "cpu")
     spawns = random_rover_spawns(safe, hm, min_x, min_y, n_spawns=2 * num_envs, border_offset=border_offset)
     t = torch.from_numpy
     return TerrainTables(
