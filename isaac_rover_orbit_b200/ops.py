@@ -130,47 +130,6 @@ def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridH
     return (out, hits) if return_hits else out
 
 
-# ------------------------------------------------------------------------------------------------------
-# fused MDP step
-# ------------------------------------------------------------------------------------------------------
-def mdp_step(buf: MdpBuffers, params: _lib.MdpParams, tables: "TerrainTablesHandle", new_actions: torch.Tensor | None,
-             force_matrix_w: torch.Tensor | None, root_pos_w: torch.Tensor, root_quat_w: torch.Tensor,
-             spawn_perm: torch.Tensor, yaw_u: torch.Tensor, heading_u: torch.Tensor, theta_u: torch.Tensor,
-             obs: torch.Tensor | None = None, pre_phases: int = _lib.PRE_ACTIONS | _lib.PRE_TERMS,
-             phases: int = _lib.PHASE_ALL, xchg=None):
-    """``mdp_pre_step`` + ``mdp_post_step`` in ONE launch (``rover_mdp_step``): for loops whose physics does not sit
-    between the two.  Bit-identical to the two-launch sequence (``tests/test_gpu_parity.py``)."""
-    dev = _lib.require_cuda(root_pos_w, root_quat_w, spawn_perm, yaw_u, heading_u, theta_u)
-    if dev != buf.device or tables.device != dev:
-        raise RuntimeError("mdp_step: tensors on different devices")
-    n = buf.n
-    if root_pos_w.shape != (n, 3) or root_quat_w.shape != (n, 4):
-        raise RuntimeError("mdp_step: bad root state shapes")
-    if (pre_phases & _lib.PRE_ACTIONS) and (new_actions is None or new_actions.shape != (n, 2)):
-        raise RuntimeError("mdp_step: new_actions must be [N,2]")
-    if (pre_phases & _lib.PRE_TERMS) and (force_matrix_w is None or force_matrix_w.numel() != n * params.num_bodies * 3):
-        raise RuntimeError("mdp_step: force_matrix_w must be [N, num_bodies, 1, 3]")
-    for t in (new_actions, force_matrix_w):
-        if t is not None:
-            _lib.require_cuda(t)
-    if spawn_perm.dtype != torch.int64 or spawn_perm.numel() < n:
-        raise RuntimeError("mdp_step: spawn_perm must be int64 with at least N entries")
-    if theta_u.dim() != 2 or theta_u.shape[0] != n or yaw_u.shape != (n,) or heading_u.shape != (n,):
-        raise RuntimeError("mdp_step: variates must be yaw_u[N], heading_u[N], theta_u[N,R]")
-    obs_ptr, obs_stride = None, 0
-    if obs is not None:
-        if obs.dtype != torch.float32 or obs.shape[0] != n or obs.stride(1) != 1 or obs.shape[1] < 4:
-            raise RuntimeError("mdp_step: obs must be fp32 [N,>=4] with unit inner stride")
-        obs_ptr, obs_stride = C.c_void_p(obs.data_ptr()), int(obs.stride(0))
-    st, out = buf.state_struct(), buf.out_struct()
-    _lib.check(_lib.load().rover_mdp_step(
-        _lib.ptr(new_actions), _lib.ptr(force_matrix_w), _lib.ptr(root_pos_w), _lib.ptr(root_quat_w), n, C.byref(params),
-        C.byref(st), C.byref(out), C.byref(tables.struct), _lib.ptr(spawn_perm), _lib.ptr(yaw_u), _lib.ptr(heading_u),
-        _lib.ptr(theta_u), int(theta_u.shape[1]), _lib.ptr(buf.spawn_index), _lib.ptr(buf.stats), _lib.ptr(buf.scratch),
-        _lib.ptr(buf.lookback), obs_ptr, obs_stride, int(pre_phases), int(phases),
-        C.byref(xchg.struct) if xchg is not None else None, _lib.current_stream(dev)))
-
-
 def height_scan_obs(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle, obs: torch.Tensor,
                     obs_bf16: torch.Tensor, head_cols: int = 4, max_distance: float = 100.0,
                     base_offset: float = 0.26878) -> None:
@@ -191,6 +150,16 @@ def height_scan_obs(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanG
         C.byref(grid.struct), C.byref(grid.cells_struct) if grid.cells_struct is not None else None,
         float(max_distance), float(base_offset), C.c_void_p(obs.data_ptr()), int(obs.stride(0)), int(head_cols),
         C.c_void_p(obs_bf16.data_ptr()), int(obs_bf16.stride(0)), _lib.current_stream(dev)))
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused MDP step
+# ------------------------------------------------------------------------------------------------------
+def _require_f32(what: str, **tensors) -> None:
+    """The kernels read raw fp32: a tensor of another dtype would be reinterpreted silently."""
+    for name, t in tensors.items():
+        if t is not None and t.dtype != torch.float32:
+            raise RuntimeError(f"{what}: {name} must be fp32, got {t.dtype}")
 
 
 def mdp_params(cfg: RoverEnvCfg) -> _lib.MdpParams:
@@ -358,6 +327,8 @@ def mdp_post_step(buf: MdpBuffers, params: _lib.MdpParams, tables: TerrainTables
     dev = _lib.require_cuda(root_pos_w, root_quat_w, spawn_perm, yaw_u, heading_u, theta_u)
     if dev != buf.device or tables.device != dev:
         raise RuntimeError("mdp_post_step: tensors on different devices")
+    _require_f32("mdp_post_step", root_pos_w=root_pos_w, root_quat_w=root_quat_w, yaw_u=yaw_u, heading_u=heading_u,
+                 theta_u=theta_u)
     n = buf.n
     if root_pos_w.shape != (n, 3) or root_quat_w.shape != (n, 4):
         raise RuntimeError("mdp_post_step: bad root state shapes")
@@ -377,3 +348,43 @@ def mdp_post_step(buf: MdpBuffers, params: _lib.MdpParams, tables: TerrainTables
         C.byref(tables.struct), _lib.ptr(spawn_perm), _lib.ptr(yaw_u), _lib.ptr(heading_u), _lib.ptr(theta_u),
         int(theta_u.shape[1]), _lib.ptr(buf.spawn_index), _lib.ptr(buf.stats), _lib.ptr(buf.scratch), obs_ptr,
         obs_stride, int(phases), C.byref(xchg.struct) if xchg is not None else None, _lib.current_stream(dev)))
+
+
+def mdp_step(buf: MdpBuffers, params: _lib.MdpParams, tables: "TerrainTablesHandle", new_actions: torch.Tensor | None,
+             force_matrix_w: torch.Tensor | None, root_pos_w: torch.Tensor, root_quat_w: torch.Tensor,
+             spawn_perm: torch.Tensor, yaw_u: torch.Tensor, heading_u: torch.Tensor, theta_u: torch.Tensor,
+             obs: torch.Tensor | None = None, pre_phases: int = _lib.PRE_ACTIONS | _lib.PRE_TERMS,
+             phases: int = _lib.PHASE_ALL, xchg=None):
+    """``mdp_pre_step`` + ``mdp_post_step`` in ONE launch (``rover_mdp_step``): for loops whose physics does not sit
+    between the two.  Bit-identical to the two-launch sequence (``tests/test_gpu_parity.py``)."""
+    dev = _lib.require_cuda(root_pos_w, root_quat_w, spawn_perm, yaw_u, heading_u, theta_u)
+    if dev != buf.device or tables.device != dev:
+        raise RuntimeError("mdp_step: tensors on different devices")
+    _require_f32("mdp_step", root_pos_w=root_pos_w, root_quat_w=root_quat_w, yaw_u=yaw_u, heading_u=heading_u,
+                 theta_u=theta_u, new_actions=new_actions, force_matrix_w=force_matrix_w)
+    n = buf.n
+    if root_pos_w.shape != (n, 3) or root_quat_w.shape != (n, 4):
+        raise RuntimeError("mdp_step: bad root state shapes")
+    if (pre_phases & _lib.PRE_ACTIONS) and (new_actions is None or new_actions.shape != (n, 2)):
+        raise RuntimeError("mdp_step: new_actions must be [N,2]")
+    if (pre_phases & _lib.PRE_TERMS) and (force_matrix_w is None or force_matrix_w.numel() != n * params.num_bodies * 3):
+        raise RuntimeError("mdp_step: force_matrix_w must be [N, num_bodies, 1, 3]")
+    for t in (new_actions, force_matrix_w):
+        if t is not None:
+            _lib.require_cuda(t)
+    if spawn_perm.dtype != torch.int64 or spawn_perm.numel() < n:
+        raise RuntimeError("mdp_step: spawn_perm must be int64 with at least N entries")
+    if theta_u.dim() != 2 or theta_u.shape[0] != n or yaw_u.shape != (n,) or heading_u.shape != (n,):
+        raise RuntimeError("mdp_step: variates must be yaw_u[N], heading_u[N], theta_u[N,R]")
+    obs_ptr, obs_stride = None, 0
+    if obs is not None:
+        if obs.dtype != torch.float32 or obs.shape[0] != n or obs.stride(1) != 1 or obs.shape[1] < 4:
+            raise RuntimeError("mdp_step: obs must be fp32 [N,>=4] with unit inner stride")
+        obs_ptr, obs_stride = C.c_void_p(obs.data_ptr()), int(obs.stride(0))
+    st, out = buf.state_struct(), buf.out_struct()
+    _lib.check(_lib.load().rover_mdp_step(
+        _lib.ptr(new_actions), _lib.ptr(force_matrix_w), _lib.ptr(root_pos_w), _lib.ptr(root_quat_w), n, C.byref(params),
+        C.byref(st), C.byref(out), C.byref(tables.struct), _lib.ptr(spawn_perm), _lib.ptr(yaw_u), _lib.ptr(heading_u),
+        _lib.ptr(theta_u), int(theta_u.shape[1]), _lib.ptr(buf.spawn_index), _lib.ptr(buf.stats), _lib.ptr(buf.scratch),
+        _lib.ptr(buf.lookback), obs_ptr, obs_stride, int(pre_phases), int(phases),
+        C.byref(xchg.struct) if xchg is not None else None, _lib.current_stream(dev)))

@@ -420,6 +420,35 @@ def test_mdp_fused_single_launch_equals_two_launches(cuda_device, n):
         assert torch.equal(pos_e, pos_g) and torch.equal(obs[0], obs[1])
 
 
+def test_mdp_operators_reject_wrong_dtype_device_and_shape(cuda_device):
+    """The kernels read raw fp32 / int64: anything else must raise instead of being reinterpreted (no CPU path either)."""
+    n = 64
+    v, f = TR.make_synthetic_terrain(SIZE, RES, seed=3)
+    tables = TR.build_terrain_tables(v, f, n)
+    params = ops.mdp_params(RoverEnvCfg(num_envs=n))
+    th = ops.TerrainTablesHandle(tables.heightmap, tables.safe_mask, tables.offset_xy, tables.spawn_table,
+                                 tables.resolution, cuda_device)
+    buf = ops.MdpBuffers.allocate(n, cuda_device)
+    st = synthetic.make_step(n, torch.Generator().manual_seed(1), torch.from_numpy(v), SIZE, RES, margin=4.0).to(cuda_device)
+    good = dict(root_pos_w=st.root_pos_w, root_quat_w=st.root_quat_w, spawn_perm=st.spawn_perm, yaw_u=st.yaw_u,
+                heading_u=st.heading_u, theta_u=st.theta_u)
+    ops.mdp_pre_step(buf, params, st.actions, st.force_matrix_w)
+    ops.mdp_post_step(buf, params, th, **good)  # the unmodified arguments are accepted
+    for key, bad in (("theta_u", st.theta_u.double()), ("yaw_u", st.yaw_u.half()), ("root_pos_w", st.root_pos_w.double()),
+                     ("spawn_perm", st.spawn_perm.int()), ("root_quat_w", st.root_quat_w[:, :3].contiguous()),
+                     ("heading_u", st.heading_u.cpu()), ("theta_u", st.theta_u[: n // 2])):
+        with pytest.raises(RuntimeError):
+            ops.mdp_post_step(buf, params, th, **{**good, key: bad})
+        with pytest.raises(RuntimeError):
+            ops.mdp_step(buf, params, th, st.actions, st.force_matrix_w, **{**good, key: bad})
+    with pytest.raises(RuntimeError):
+        ops.mdp_step(buf, params, th, st.actions.double(), st.force_matrix_w, **good)
+    with pytest.raises(RuntimeError):
+        ops.mdp_pre_step(buf, params, st.actions.double(), st.force_matrix_w)
+    with pytest.raises(RuntimeError):
+        ops.mdp_pre_step(buf, params, st.actions.cpu(), st.force_matrix_w)
+
+
 def test_mdp_terms_against_reference_golden(cuda_device, golden_dir):
     """The fused kernel against outputs of the UNMODIFIED reference functions (tests/golden/terms.npz)."""
     z = np.load(os.path.join(golden_dir, "terms.npz"))
