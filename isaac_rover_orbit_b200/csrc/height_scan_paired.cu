@@ -57,7 +57,10 @@ __device__ __forceinline__ unsigned long long dbg_globaltimer() {
     } while (0)
 #endif
 
-constexpr int kPairConsumerWarps = 14;  // 1 + 14 warps -> 16-warp register allocation -> 128 registers / thread
+#ifndef ROVER_PAIR_WARPS
+#define ROVER_PAIR_WARPS 14
+#endif
+constexpr int kPairConsumerWarps = ROVER_PAIR_WARPS;  // 1 + 14 warps -> 16-warp register allocation -> 128 registers / thread
 constexpr int kPairThreads = 32 * (1 + kPairConsumerWarps);
 constexpr int kPairStages = 8;          // ring depth (data)
 #ifndef ROVER_PAIR_EARLY
