@@ -73,7 +73,12 @@ constexpr int kPairPitch = 27;          // cells per staged row: odd, so that co
                                         // group and a quarter-warp's LDS.128 of 8 neighbouring cells is conflict free
 constexpr int kPairPlane = kPairWin * kPairPitch;             // float4 per plane
 constexpr uint32_t kPairStageBytes = 2u * kPairPlane * 16u;   // bytes one TMA load delivers
-constexpr int kPairChunk = 256;         // rays per work unit: 2 batches x 2 pair slots x 32 lanes x 2 rays
+#ifndef ROVER_PAIR_CHUNK
+#define ROVER_PAIR_CHUNK 256
+#endif
+constexpr int kPairBatch = 128;         // rays per pass of a warp: 2 pair slots x 32 lanes x 2 rays
+constexpr int kPairChunk = ROVER_PAIR_CHUNK;  // rays per work unit (a whole number of batches)
+static_assert(kPairChunk % kPairBatch == 0, "a chunk is a whole number of batches");
 constexpr int kPairMaxRays = 1024;      // pattern held in shared memory (3 float arrays)
 constexpr int kPairMaxLines = 1024;     // grid-line pairs per axis held in shared memory
 constexpr float kFloorMagic = 12582912.0f;  // 1.5 * 2^23: fl_rm(v + magic) has floor(v) in its mantissa for |v| < 2^22
@@ -530,12 +535,12 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
                 cx.xoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.xpair + h.ic0) - smem_raw);
                 cx.yoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.ypair + h.jr0) - smem_raw);
                 cx.eoff = (uint32_t)(reinterpret_cast<const unsigned char*>(st.p) - smem_raw);
-                for (int b0 = r_begin; b0 < r_end; b0 += kPairChunk / 2) {
+                for (int b0 = r_begin; b0 < r_end; b0 += kPairBatch) {
                     const int r = b0 + lane;  // rays r, r + 64 (slot 0) and r + 32, r + 96 (slot 1)
                     float* __restrict__ o = out_row + r;
                     __nv_bfloat16* __restrict__ ob = kBf16 ? bf_row + r : nullptr;
                     unsigned defer;
-                    if (flat_z && b0 + kPairChunk / 2 <= n_rays) {
+                    if (flat_z && b0 + kPairBatch <= n_rays) {
                         defer = resolve_pair<true, true, kBf16>(smem_raw, sm, cx, b0 + 2 * lane, r, n_rays, o, ob);
                         defer |= resolve_pair<true, true, kBf16>(smem_raw, sm, cx, b0 + 64 + 2 * lane, r + 32, n_rays, o + 32,
                                                                  ob + 32) << 2;

@@ -1,13 +1,17 @@
 """GPU check: every plane-cell scan variant returns bit-identical heights on the bench workload and on ragged
 pattern sizes / strided outputs; prints a quick timing per variant (CUDA events, L2 flushed between launches).
 
-    python profiles/cmp_scan_variants.py
+    python profiles/cmp_scan_variants.py [path/to/librover_b200.so]
 """
 import sys
 
 import torch
 
 sys.path.insert(0, ".")
+from isaac_rover_orbit_b200 import _lib  # noqa: E402
+
+if len(sys.argv) > 1:  # an alternative build of the library (bring-up experiments)
+    _lib.LIB_PATH = sys.argv[1]
 import bench  # noqa: E402
 from isaac_rover_orbit_b200 import ops, synthetic  # noqa: E402
 
