@@ -250,3 +250,36 @@ def test_oracle_bvh_equals_brute_force():
     b = m.raycast(s, d, 100.0, brute=True, return_t=True)
     assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
     assert (a[2][:500] >= 0).float().mean() > 0.7
+
+
+def test_steep_mask_host_path_equals_roll_based_sobel():
+    """terrain.steep_mask (host path, scipy convolve2d with wrap borders) against an independent np.roll restatement of
+    terrain_utils.py:265-279; the GPU stencil is checked against the same host path in tests/test_gpu_terrain_build.py."""
+    from isaac_rover_orbit_b200 import terrain as TR
+
+    rng = np.random.default_rng(11)
+    hm = rng.normal(0.0, 0.01, size=(37, 53)).astype(np.float32)
+    hm[10:14, 20:25] += 0.8  # a rock
+    hm[0, :] = -99.0         # "no data" border rows as the rasteriser leaves them
+    h = hm.astype(np.float64)
+    r = lambda a, dy, dx: np.roll(np.roll(a, dy, axis=0), dx, axis=1)  # noqa: E731  r(a, 1, 0)[y, x] = a[y-1, x]
+    gx = (r(h, 1, 1) - r(h, 1, -1)) + 2.0 * (r(h, 0, 1) - r(h, 0, -1)) + (r(h, -1, 1) - r(h, -1, -1))
+    gy = (r(h, 1, 1) - r(h, -1, 1)) + 2.0 * (r(h, 1, 0) - r(h, -1, 0)) + (r(h, 1, -1) - r(h, -1, -1))
+    want = np.sqrt(gx**2 + gy**2) > 0.3
+    got = TR.steep_mask(hm, 0.3, device="cpu")
+    assert got.dtype == bool and np.array_equal(got, want)
+    assert want[10:14, 19:26].any() and not want[25:30, 5:15].any()
+
+
+def test_heightmap_builder_rejects_cuda_device_without_gpu():
+    """No silent CPU fallback in the init-time builders either: asking for the CUDA rasteriser on a box without a GPU
+    raises instead of quietly running the host path."""
+    import torch
+    from isaac_rover_orbit_b200 import terrain as TR
+
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    v = np.array([[0, 0, 0], [10, 0, 0], [0, 10, 0], [10, 10, 0]], np.float32)
+    f = np.array([[0, 1, 2], [1, 3, 2]], np.int32)
+    with pytest.raises((RuntimeError, AssertionError)):
+        TR.mesh_to_heightmap(v, f, device="cuda")
