@@ -45,3 +45,30 @@ for flush in (True, False):
     for ph, name in ((_lib.PHASE_METRICS | _lib.PHASE_COMMAND | _lib.PHASE_OBS, "metrics+command+obs"), (_lib.PHASE_OBS, "obs only"), (_lib.PHASE_ALL, "all, with resets")):
         pre(); torch.cuda.synchronize()
         print("flush", flush, "post phases", name, timeit(lambda: ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u, s.theta_u, obs, phases=ph), flush=flush))
+
+# ---- how much of the cold launch is instruction fetch?  (ncu: 44 % of the post-step's stall samples are `no_inst`.)
+# After the L2 flush, a 64-env launch of the same kernels on separate buffers brings their code back into L2 / the SM
+# instruction caches; the timed 16384-env launch then still sees cold DATA.
+small = 64
+tb2 = TR.build_terrain_tables(v, f, small, build_device=dev)
+buf2 = ops.MdpBuffers.allocate(small, dev)
+th2 = ops.TerrainTablesHandle(tb2.heightmap, tb2.safe_mask, tb2.offset_xy, tb2.spawn_table, tb2.resolution, dev)
+s2 = synthetic.make_step(small, gen, vt, size, 0.2).to(dev)
+buf2.time_left.fill_(150.0)
+
+
+def timeit_warm_code(fn, reps=50):
+    ts = []
+    for i in range(reps + 5):
+        flush_buf.fill_(1)
+        ops.mdp_pre_step(buf2, params, s2.actions, s2.force_matrix_w)
+        ops.mdp_post_step(buf2, params, th2, s2.root_pos_w, s2.root_quat_w, s2.spawn_perm, s2.yaw_u, s2.heading_u, s2.theta_u)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); fn(); b.record(stream); torch.cuda.synchronize()
+        if i >= 5: ts.append(a.elapsed_time(b) * 1e3)
+    return float(np.median(ts))
+
+
+print("code warm, data cold: pre_step us", timeit_warm_code(pre))
+pre(); torch.cuda.synchronize()
+print("code warm, data cold: post_step (all phases, with resets) us", timeit_warm_code(post))
