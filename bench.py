@@ -61,6 +61,14 @@ def recorded_traffic(kernel: str):
     return None
 
 
+def recorded_metric(kernel: str, key: str):
+    """One number of the committed ncu capture of `kernel` (profiles/ncu_summary.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(kernel, {}).get(key)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons of one GPU while the timed region runs (pynvml, ~20 ms period)."""
 
@@ -443,6 +451,8 @@ def run_ours(args):
         same = bool(torch.equal(net.compute({"states": pol_obs})[0], net.compute({"states": pol_obs_bf})[0]))
         bf16_pol = {"env_forwards_per_s": n_pol * world / t_bf, "us_per_launch": t_bf * 1e6,
                     "bit_identical_to_fp32_path": same,
+                    "tensor_pipe_active_pct_ncu": recorded_metric("policy_forward_ws_kernel<bf16 observation>",
+                                                                  "tensor_pipe_active_pct"),
                     "roofline_frac_hbm": n_pol * (964 * 2 + 8) / t_bf / 1e9 / measured_peak()[0]}
         peaks = {}
         try:
@@ -457,6 +467,7 @@ def run_ours(args):
             "tflops": n_pol * 319520 / t_pol / 1e12,
             "roofline_frac_tensor": n_pol * 319520 / t_pol / 1e12 / tf_peak, "tensor_peak_tflops": tf_peak,
             "roofline_frac_hbm": n_pol * (965 * 4 + 8) / t_pol / 1e9 / peak,
+            "tensor_pipe_active_pct_ncu": recorded_metric("policy_forward_ws_kernel", "tensor_pipe_active_pct"),
             "kernel": "policy_forward_ws_kernel" if os.environ.get("ROVER_POLICY_KERNEL", "ws")[:2] != "v1"
                       else "policy_forward_kernel",
             "bf16_observation": bf16_pol,
