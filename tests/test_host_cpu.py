@@ -283,3 +283,62 @@ def test_heightmap_builder_rejects_cuda_device_without_gpu():
     f = np.array([[0, 1, 2], [1, 3, 2]], np.int32)
     with pytest.raises((RuntimeError, AssertionError)):
         TR.mesh_to_heightmap(v, f, device="cuda")
+
+
+def test_oracle_raycast_against_independent_float64_geometry():
+    """The raycast oracle has no reference fixture to pin it (warp / ORBIT are absent: 'parity unpinned'), so it is held
+    against geometry derived independently of its code, in float64: (i) vertical rays over a triangulated heightfield
+    must return the barycentric interpolation of the quad's triangle under the ray; (ii) tilted rays against a tilted
+    plane must return the closed-form intersection; (iii) max_dist and rays pointing away give misses (inf hits)."""
+    from oracle.raycast import Mesh
+
+    rng = np.random.default_rng(3)
+    n, dx = 33, 0.25
+    z = rng.uniform(-0.5, 0.5, size=(n, n))
+    xs, ys = np.meshgrid(np.arange(n) * dx, np.arange(n) * dx)  # [row = y index, col = x index]
+    v = np.stack([xs.ravel(), ys.ravel(), z.ravel()], 1).astype(np.float32)
+    idx = np.arange(n * n).reshape(n, n)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel()
+    f = np.concatenate([np.stack([a, b, d], 1), np.stack([a, d, c], 1)]).astype(np.int32)  # diagonal (0,0)-(1,1)
+    m = Mesh(v, f)
+    # (i) strictly inside cells, away from edges (edge ownership is a tie-break, not geometry)
+    k = 3000
+    ci, cj = rng.integers(0, n - 1, k), rng.integers(0, n - 1, k)
+    u, w = rng.uniform(0.05, 0.95, k), rng.uniform(0.05, 0.95, k)
+    keep = np.abs(u - w) > 0.02
+    ci, cj, u, w = ci[keep], cj[keep], u[keep], w[keep]
+    px, py = (ci + u) * dx, (cj + w) * dx
+    z64 = v[:, 2].astype(np.float64).reshape(n, n)
+    z00, z10, z01, z11 = z64[cj, ci], z64[cj, ci + 1], z64[cj + 1, ci], z64[cj + 1, ci + 1]
+    below = u > w  # triangle (a, b, d): under the diagonal
+    want = np.where(below, z00 + u * (z10 - z00) + w * (z11 - z10), z00 + u * (z11 - z01) + w * (z01 - z00))
+    starts = torch.tensor(np.stack([px, py, np.full_like(px, 12.0)], 1), dtype=torch.float32)
+    dirs = torch.zeros(len(px), 3)
+    dirs[:, 2] = -1.0
+    hits, t, face = m.raycast(starts, dirs, 100.0, return_t=True)
+    assert (face >= 0).all()
+    # fp32 ray parameter: |err| <= 1e-5 * t (north_star tolerance for ray distances), t ~ 12 m
+    s64 = starts.numpy().astype(np.float64)
+    u32, w32 = s64[:, 0] / dx - ci, s64[:, 1] / dx - cj  # the fp32-rounded start positions the oracle actually saw
+    want32 = np.where(below, z00 + u32 * (z10 - z00) + w32 * (z11 - z10), z00 + u32 * (z11 - z01) + w32 * (z01 - z00))
+    assert np.abs(hits[:, 2].numpy() - want32).max() <= 1e-5 * 12.5
+    assert np.abs(t.numpy() - (12.0 - want32)).max() <= 1e-5 * 12.5
+    assert np.abs(want - want32).max() < 1e-5  # the float64 ideal and its fp32-input version agree to rounding
+    # (ii) tilted rays against the plane z = 0.3 x - 0.2 y + 1 (two big triangles)
+    P = np.array([[-50, -50], [50, -50], [-50, 50], [50, 50]], np.float64)
+    pv = np.concatenate([P, (0.3 * P[:, :1] - 0.2 * P[:, 1:] + 1.0)], 1).astype(np.float32)
+    pm = Mesh(pv, np.array([[0, 1, 3], [0, 3, 2]], np.int32))
+    o = np.concatenate([rng.uniform(-20, 20, (500, 2)), rng.uniform(15, 25, (500, 1))], 1)
+    dd = np.concatenate([rng.normal(0, 0.3, (500, 2)), -np.ones((500, 1))], 1)
+    dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+    o32, d32 = o.astype(np.float32).astype(np.float64), dd.astype(np.float32).astype(np.float64)
+    nrm = np.array([0.3, -0.2, -1.0])
+    t_want = -(o32 @ nrm + 1.0) / (d32 @ nrm)
+    _, t2, face2 = pm.raycast(torch.tensor(o32, dtype=torch.float32), torch.tensor(d32, dtype=torch.float32), 100.0,
+                              return_t=True)
+    assert (face2 >= 0).all() and np.abs(t2.numpy() - t_want).max() <= 1e-5 * t_want.max()
+    # (iii) misses: beyond max_dist, and pointing away
+    h3 = pm.raycast(torch.tensor(o32, dtype=torch.float32), torch.tensor(d32, dtype=torch.float32), 5.0)
+    assert torch.isinf(h3).all()
+    h4 = pm.raycast(torch.tensor(o32, dtype=torch.float32), torch.tensor(-d32, dtype=torch.float32), 100.0)
+    assert torch.isinf(h4).all()
