@@ -4,7 +4,8 @@ cfg-2: 4096 envs x 961 rays on the 2,000,000-triangle terrain; cfg-3: 16384 envs
 65536 envs through the policy.  Checked: every kernel variant returns the same bits, repeated launches are
 deterministic, results are equivariant under a permutation of the environments and invariant under q -> -q, the
 episode statistics equal plain torch reductions of the per-env outputs, the reset ranks reproduce
-``reset_buf.nonzero()`` order (index-exact), and a 48-env sample of the full-size scan agrees with the CPU oracle.
+``reset_buf.nonzero()`` order (index-exact), a 48-env sample of the full-size scan agrees with the CPU oracle, and
+EVERY ray of the cfg-2 launch agrees with a float64 interpolation of the heightfield derived independently of both.
 """
 import numpy as np
 import pytest
@@ -63,6 +64,41 @@ def test_scan_cfg2_sample_against_oracle(full):
     assert torch.equal(torch.isinf(h), torch.isinf(h_ref))
     fin = ~torch.isinf(h_ref)
     assert (h[fin] - h_ref[fin]).abs().max().item() <= 1e-4  # 1e-5 relative on the ray distance t ~ 10 m
+
+
+def test_scan_cfg2_every_ray_against_float64_heightfield_interpolation(full):
+    """All 3,936,256 rays of the cfg-2 launch against geometry derived independently of the kernels AND of the oracle, in
+    float64 on the same fp32 inputs: ORBIT's yaw-only ray transform, then the barycentric interpolation of the lattice
+    triangle under the ray (terrain.make_synthetic_terrain splits every quad along (1,0)-(0,1)).
+    Tolerance: the north-star 1e-5 relative on the ray distance (t ~ 10 m -> 1e-4 m); a ray within rounding of a cell or
+    diagonal border may be evaluated on the neighbouring triangle by either side, which changes z by slope * 1e-6 m."""
+    dev = full["dev"]
+    pos, quat, rays = full["pos"].double(), full["quat"].double(), full["rays"]
+    res = bench.TERRAIN["grid_res"]
+    n = int(round(bench.TERRAIN["size_m"] / res)) + 1
+    z = torch.from_numpy(full["v"][:, 2].astype(np.float64)).reshape(n, n).to(dev)  # [y index, x index]
+    xs = torch.from_numpy(full["v"][:n, 0].astype(np.float64)).to(dev)             # the fp32 lattice lines, exactly
+    w_, x_, y_, z_ = quat.unbind(1)
+    yaw = torch.atan2(2.0 * (w_ * z_ + x_ * y_), 1.0 - 2.0 * (y_ * y_ + z_ * z_))
+    c, s = torch.cos(yaw)[:, None], torch.sin(yaw)[:, None]
+    loc = rays.starts.double()
+    X = pos[:, 0:1] + c * loc[None, :, 0] - s * loc[None, :, 1]
+    Y = pos[:, 1:2] + s * loc[None, :, 0] + c * loc[None, :, 1]
+    ci = (torch.searchsorted(xs, X.contiguous(), right=True) - 1).clamp_(0, n - 2)
+    cj = (torch.searchsorted(xs, Y.contiguous(), right=True) - 1).clamp_(0, n - 2)
+    u = (X - xs[ci]) / (xs[ci + 1] - xs[ci])
+    w = (Y - xs[cj]) / (xs[cj + 1] - xs[cj])
+    z00, z10, z01, z11 = z[cj, ci], z[cj, ci + 1], z[cj + 1, ci], z[cj + 1, ci + 1]
+    lower = (u + w) <= 1.0
+    zhit = torch.where(lower, z00 + u * (z10 - z00) + w * (z01 - z00),
+                       z11 + (1.0 - u) * (z01 - z11) + (1.0 - w) * (z10 - z11))
+    want = pos[:, 2:3] - zhit - 0.26878
+    got = ops.height_scan(full["pos"], full["quat"], rays, full["grid"])
+    inside = (X > xs[0]) & (X < xs[-1]) & (Y > xs[0]) & (Y < xs[-1])
+    assert float(inside.double().mean()) > 0.99 and bool(torch.isfinite(got[inside]).all())
+    err = (got.double() - want)[inside].abs()
+    assert float(err.max()) <= 1e-4, float(err.max())
+    assert float(err.mean()) < 3e-6  # typical error is fp32 rounding of a ~10 m ray parameter
 
 
 def test_mdp_cfg3_statistics_ranks_and_determinism(full):
