@@ -101,6 +101,18 @@ def test_scan_cfg2_every_ray_against_float64_heightfield_interpolation(full):
     assert float(err.mean()) < 3e-6  # typical error is fp32 rounding of a ~10 m ray parameter
 
 
+def test_mdp_cfg3_steps_against_oracle(full):
+    """cfg-3 size (16384 envs, 200 m terrain tables): three consecutive fused MDP steps against the vectorised CPU oracle
+    with the same checks as the small-terrain parity test -- masks and reset indices bit-exact, floats 1e-5 relative."""
+    from mdp_parity import check_mdp_steps_vs_oracle
+
+    n = bench.STEP_ENVS_1GPU
+    assert n == 16384
+    resets = check_mdp_steps_vs_oracle(full["dev"], n, full["v"], full["tables"].to("cpu"), bench.TERRAIN["size_m"],
+                                       bench.TERRAIN["grid_res"], n_steps=3, margin=20.0, max_ambiguous=4)
+    assert resets > 500
+
+
 def test_mdp_cfg3_statistics_ranks_and_determinism(full):
     dev, tables, n = full["dev"], full["tables"], bench.STEP_ENVS_1GPU
     cfg = RoverEnvCfg(num_envs=n)
