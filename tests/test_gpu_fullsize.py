@@ -14,7 +14,7 @@ import torch
 import bench
 from isaac_rover_orbit_b200 import ops, synthetic
 from isaac_rover_orbit_b200.config import RoverEnvCfg
-from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork, alloc_obs, alloc_obs_bf16
+from isaac_rover_orbit_b200.policy import WEIGHT_KEYS, GaussianNeuralNetwork, alloc_obs, alloc_obs_bf16
 
 pytestmark = pytest.mark.gpu
 
@@ -196,3 +196,23 @@ def test_policy_cfg4_kernels_agree_and_rows_are_independent(full, monkeypatch):
     obs_p.copy_(obs[perm])
     assert torch.equal(net.compute({"states": obs_p})[0], mean[perm])  # tiles / rounds do not leak between rows
     assert torch.equal(net.compute({"states": obs[:1000]})[0], mean[:1000])  # another tile height, same rows
+    # every one of the 65536 rows against a torch emulation of the same numerics on the GPU (bf16 operands, fp32
+    # accumulation; true fp32 matmuls, TF32 off) and against the plain fp32 network
+    from test_gpu_policy import emulate_bf16
+
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd = {k: t.to(dev) for k, t in net.state_dict().items()}
+        emu = emulate_bf16(obs[:, :965], sd)
+        assert float((mean - emu).abs().max()) <= 4e-3
+        lin = lambda k, x: x @ sd[k + ".weight"].T + sd[k + ".bias"]  # noqa: E731
+        lr = lambda x: torch.nn.functional.leaky_relu(x, 0.01)  # noqa: E731
+        keys = WEIGHT_KEYS
+        h = torch.cat([obs[:, 0:4], lr(lin(keys[1], lr(lin(keys[0], obs[:, 3:964]))))], dim=1)
+        for k in keys[2:5]:
+            h = lr(lin(k, h))
+        ref = torch.tanh(lin(keys[5], h))
+        assert float((mean - ref).abs().max()) < 3e-2  # bf16 operands cannot meet 1e-5
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
