@@ -2,7 +2,7 @@
 
 Every function takes plain tensors (no ``env`` object) and cites the reference lines it follows.
 Paths are relative to ``/root/reference``.  The restatement is pinned in two ways
-(``tests/test_oracle_vs_reference.py`` / ``tests/golden/make_golden.py``):
+(``tests/test_oracle_golden.py::test_live_reference_agrees_bitwise`` / ``tests/golden/make_golden.py``):
 
 * in the build container the UNMODIFIED reference functions are imported through
   :mod:`oracle.ref_loader` and must agree bit-for-bit with these on seeded inputs;
