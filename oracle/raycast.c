@@ -16,7 +16,9 @@
  *
  * PARITY UNPINNED: the reference ships no test or golden vector for the raycast;
  * this file is pinned instead by (i) a brute-force all-triangles mode that must agree with the BVH
- * mode bit for bit, and (ii) analytic surfaces (planes, heightfields) in tests/test_oracle_raycast.py.
+ * mode bit for bit (tests/test_host_cpu.py::test_oracle_bvh_equals_brute_force), and (ii) analytic surfaces derived
+ * independently in float64 -- heightfield interpolation, tilted planes, misses --
+ * (tests/test_host_cpu.py::test_oracle_raycast_against_independent_float64_geometry).
  *
  * Build: oracle/Makefile (gcc -O2 -fopenmp -ffp-contract=off).  Only tests/, smoke() and bench.py's
  * cpu_baseline / --impl reference legs may load the resulting library.
