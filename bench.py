@@ -405,7 +405,8 @@ def run_ours(args):
         extra = {
             "fused_step": {
                 "workload": f"cfg-{'3' if world == 1 else '5'}: {n_step} envs/GPU, pre_step + post_step + height scan"
-                            + (" + NCCL episode-stat all-reduce" if world > 1 else ""),
+                            + ("" if world == 1 else " + episode statistics through P2P mailboxes (peer stores from the "
+                               "post-step kernel)" if p2p is not None else " + NCCL episode-stat all-reduce"),
                 "env_steps_per_s": n_step * world * ksteps / (float(tf[0]) * 1e-3),
                 "ms_per_step": float(tf[0]) / ksteps,
                 "gpu_launches_per_step": 2 if args.single_launch_mdp else 3, "cuda_graph": not args.no_graph,
