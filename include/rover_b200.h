@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ROVER_B200_ABI_VERSION 2
+#define ROVER_B200_ABI_VERSION 3
 #define ROVER_MAX_LEVELS 12
 #define ROVER_NUM_REWARD_TERMS 7
 #define ROVER_NUM_TERMINATION_TERMS 4
@@ -125,6 +125,7 @@ typedef struct RoverMdpParams {
     int32_t num_bodies;          /* contact-sensor bodies B: force_matrix_w is [n_envs, B, 1, 3] */
     int32_t action_variant;      /* 2 = AckermannAction2 (default, actions_cfg.py:17), 1 = AckermannAction
                                     (ackermann_actions.py:19-158), 3 = ackermann() of AckermannAction3 (:423-505) */
+    float episode_length_s;      /* max_episode_length_s (rover_env_cfg.py:269): divisor of the "Episode Reward/..." log */
 } RoverMdpParams;
 
 typedef struct RoverMdpState {     /* persistent manager state, mutated in place */
@@ -232,6 +233,43 @@ int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_t n_envs, c
                         float* scratch /* [ceil(N/ROVER_MDP_BLOCK)*ROVER_STATS_LEN + 1] f32, zeroed once */,
                         float* obs, int32_t obs_stride, int32_t phases, void* stream);
 
+/* Where the random variates of the reset path come from (randomizations.py:22, 30; terrain_importer.py:94-95, 169).
+ *   rng_state == NULL: explicit arrays, as documented above (parity tests feed the oracle the same numbers);
+ *   rng_state != NULL: DEVICE uint64[2] = {seed, step}.  The kernel evaluates the counter-based generator of
+ *     csrc/rng.cuh in registers -- Philox4x32-10, key = seed, counter = (env, step, stream); the spawn row of reset rank j
+ *     is a keyed bijection of [0, n_spawns) at j (without replacement, like randperm(len)[:K]) -- and its last block
+ *     advances `step`, so the launch is CUDA-graph safe and needs no torch generator call on the step path.
+ *     rover_rng_variates() evaluates the same functions on the host: spawn_perm[j], yaw_u[i], heading_u[i],
+ *     theta_u[i, r] for one (seed, step) -- what a kernel launched with that state consumes, bit for bit. */
+typedef struct RoverResetVariates {
+    const int64_t* spawn_perm;
+    const float* yaw_u;
+    const float* heading_u;
+    const float* theta_u;
+    int32_t n_rounds;          /* bound of the rejection loop (both modes) */
+    int32_t reserved;
+    uint64_t* rng_state;
+} RoverResetVariates;
+
+/* The post-step with every option (the entries above forward to it):
+ *   variates: explicit arrays or the in-kernel generator (see RoverResetVariates);
+ *   log_out (DEVICE f32[16], may be NULL): extras["log"] as the ORBIT managers' reset() build it --
+ *     [0..6] Episode Reward/<term> = mean(episode_sums[ids]) / episode_length_s, [7..10] Episode Termination/<term>
+ *     counts, [11], [12] Metrics/target_pose/error_pos|error_heading means, [13] number of resets, [14] rounds
+ *     exhausted, [15] time-based resamples -- written ONLY by a launch (with ROVER_PHASE_MANAGERS) in which at least one
+ *     env reset: the reference calls _reset_idx only then (rover_env.py:89-91), so the last values persist otherwise. */
+int rover_mdp_post_step_v3(float* root_pos_w, float* root_quat_w, int32_t n_envs, const RoverMdpParams* params,
+                           const RoverMdpState* state, const RoverMdpOut* out, const RoverTerrainTables* tables,
+                           const RoverResetVariates* variates /* host */, int64_t* out_spawn_index, float* stats,
+                           float* scratch, float* log_out, float* obs, int32_t obs_stride, int32_t phases,
+                           const struct RoverStatsExchange* xchg /* host, may be NULL */, void* stream);
+/* HOST function (no GPU work): the variates of one (seed, step) into host arrays; any output may be NULL.
+ * spawn_perm [min(n_envs, n_spawns)], yaw_u [n_envs], heading_u [n_envs], theta_u [n_envs, n_rounds]. */
+int rover_rng_variates(uint64_t seed, uint64_t step, int32_t n_envs, int32_t n_rounds, int32_t n_spawns,
+                       int64_t* spawn_perm, float* yaw_u, float* heading_u, float* theta_u);
+/* HOST: one Philox4x32-10 block (Random123 known-answer vectors pin it: tests/test_rng_cpu.py) */
+int rover_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+
 /* rover_mdp_pre_step + rover_mdp_post_step_x in ONE launch, for callers whose physics does not sit between the two (the
  * synthetic-physics loop of bench.py; a simulator that hands over root state and contacts before the step): the reset
  * rank that the post-step needs comes from a decoupled look-back over the blocks' reset counts instead of a second
@@ -246,6 +284,13 @@ int rover_mdp_step(const float* new_actions, const float* force_matrix_w, float*
                    const float* theta_u, int32_t n_rounds, int64_t* out_spawn_index, float* stats, float* scratch,
                    uint64_t* lookback, float* obs, int32_t obs_stride, int32_t pre_phases, int32_t phases,
                    const struct RoverStatsExchange* xchg /* host, may be NULL; defined below */, void* stream);
+/* the same with RoverResetVariates and log_out (see rover_mdp_post_step_v3) */
+int rover_mdp_step_v3(const float* new_actions, const float* force_matrix_w, float* root_pos_w, float* root_quat_w,
+                      int32_t n_envs, const RoverMdpParams* params, const RoverMdpState* state, const RoverMdpOut* out,
+                      const RoverTerrainTables* tables, const RoverResetVariates* variates /* host */,
+                      int64_t* out_spawn_index, float* stats, float* scratch, uint64_t* lookback, float* log_out, float* obs,
+                      int32_t obs_stride, int32_t pre_phases, int32_t phases, const struct RoverStatsExchange* xchg,
+                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Multi-GPU episode statistics without a collective launch (the only cross-rank quantity on the path).

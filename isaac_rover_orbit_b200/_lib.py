@@ -18,10 +18,11 @@ NUM_REWARD_TERMS = 7
 NUM_TERMINATION_TERMS = 4
 STATS_LEN = 16
 MDP_BLOCK = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_height_scan_obs", "rover_mdp_pre_step",
-           "rover_mdp_post_step", "rover_mdp_post_step_x", "rover_mdp_step", "rover_stats_read", "rover_p2p_alloc", "rover_p2p_free",
+           "rover_mdp_post_step", "rover_mdp_post_step_x", "rover_mdp_post_step_v3", "rover_mdp_step", "rover_mdp_step_v3",
+           "rover_rng_variates", "rover_philox4x32_10", "rover_stats_read", "rover_p2p_alloc", "rover_p2p_free",
            "rover_p2p_export", "rover_p2p_open", "rover_p2p_close",
            "rover_ackermann",
            "rover_policy_pack", "rover_policy_forward", "rover_value_forward", "rover_policy_forward_bf16",
@@ -61,7 +62,16 @@ class MdpParams(C.Structure):
                 ("far_threshold", C.c_float), ("step_dt", C.c_float), ("max_episode_length", C.c_int32),
                 ("obs_distance_scale", C.c_float), ("obs_heading_scale", C.c_float), ("target_distance", C.c_float),
                 ("resampling_time", C.c_float), ("heading_lo", C.c_float), ("heading_hi", C.c_float),
-                ("spawn_z_offset", C.c_float), ("num_bodies", C.c_int32), ("action_variant", C.c_int32)]
+                ("spawn_z_offset", C.c_float), ("num_bodies", C.c_int32), ("action_variant", C.c_int32),
+                ("episode_length_s", C.c_float)]
+
+
+class ResetVariates(C.Structure):
+    """``RoverResetVariates``: explicit arrays, or ``rng_state`` (device uint64[2] = {seed, step}) for the in-kernel
+    counter-based generator."""
+
+    _fields_ = [("spawn_perm", C.c_void_p), ("yaw_u", C.c_void_p), ("heading_u", C.c_void_p), ("theta_u", C.c_void_p),
+                ("n_rounds", C.c_int32), ("reserved", C.c_int32), ("rng_state", C.c_void_p)]
 
 
 _STATE_FIELDS = ("action", "prev_action", "pos_cmd_w", "heading_cmd_w", "pos_cmd_b", "heading_cmd_b", "time_left",
@@ -125,6 +135,18 @@ def load() -> C.CDLL:
     lib.rover_mdp_post_step_x.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
                                           C.POINTER(TerrainTables), vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32,
                                           C.POINTER(StatsExchange), vp]
+    lib.rover_mdp_post_step_v3.restype = C.c_int
+    lib.rover_mdp_post_step_v3.argtypes = [vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
+                                           C.POINTER(TerrainTables), C.POINTER(ResetVariates), vp, vp, vp, vp, vp, i32, i32,
+                                           C.POINTER(StatsExchange), vp]
+    lib.rover_mdp_step_v3.restype = C.c_int
+    lib.rover_mdp_step_v3.argtypes = [vp, vp, vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
+                                      C.POINTER(TerrainTables), C.POINTER(ResetVariates), vp, vp, vp, vp, vp, vp, i32, i32,
+                                      i32, C.POINTER(StatsExchange), vp]
+    lib.rover_rng_variates.restype = C.c_int
+    lib.rover_rng_variates.argtypes = [C.c_uint64, C.c_uint64, i32, i32, i32, vp, vp, vp, vp]
+    lib.rover_philox4x32_10.restype = C.c_int
+    lib.rover_philox4x32_10.argtypes = [C.POINTER(C.c_uint32 * 4), C.POINTER(C.c_uint32 * 2), C.POINTER(C.c_uint32 * 4)]
     lib.rover_mdp_step.restype = C.c_int
     lib.rover_mdp_step.argtypes = [vp, vp, vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
                                    C.POINTER(TerrainTables), vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32,
@@ -192,3 +214,18 @@ def ptr(t: torch.Tensor | None):
 
 def current_stream(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def rng_variates(seed: int, step: int, n_envs: int, n_rounds: int, n_spawns: int):
+    """Host evaluation of the kernels' counter-based variates (``rover_rng_variates``; no GPU work): numpy arrays
+    ``(spawn_perm [min(N, n_spawns)] int64, yaw_u [N], heading_u [N], theta_u [N, n_rounds])`` -- exactly what a
+    launch whose ``rng_state`` holds ``{seed, step}`` consumes."""
+    import numpy as np
+
+    k = min(n_envs, n_spawns)
+    sp = np.empty(k, dtype=np.int64)
+    yaw, head = np.empty(n_envs, dtype=np.float32), np.empty(n_envs, dtype=np.float32)
+    theta = np.empty((n_envs, n_rounds), dtype=np.float32)
+    check(load().rover_rng_variates(C.c_uint64(seed), C.c_uint64(step), n_envs, n_rounds, n_spawns, sp.ctypes.data,
+                                    yaw.ctypes.data, head.ctypes.data, theta.ctypes.data))
+    return sp, yaw, head, theta

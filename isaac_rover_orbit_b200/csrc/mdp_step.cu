@@ -17,6 +17,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace rover {
 
@@ -322,10 +323,23 @@ __device__ __forceinline__ void terrain_cell(const Tables& T, float x, float y, 
 // round), then the first valid round wins -- the same candidate the sequential loop would have accepted.  The height
 // under every candidate is fetched in the same round trip (speculatively: 8 loads for the ~5 % of envs that resample),
 // which takes the heightmap lookup off the dependent chain rank -> spawn row -> mask -> height.
+// The random variates of the reset path: explicit arrays (parity tests: oracle and kernel read the same numbers) or the
+// counter-based generator of rng.cuh evaluated in registers (rng != nullptr: {seed, step} in device memory, the step
+// counter advanced by the launch itself, so the launch can sit in a CUDA graph).
+struct VariatesDev {
+    const long long* __restrict__ spawn_perm;
+    const float* __restrict__ yaw_u;
+    const float* __restrict__ heading_u;
+    const float* __restrict__ theta_u;
+    unsigned long long* rng;
+    int n_rounds;
+};
+
+template <bool kRng>
 __device__ __forceinline__ bool resample_command(int i, const RoverMdpParams& P, const RoverMdpState& S, const Tables& T,
                                                  float ox, float oy, const float* __restrict__ theta_u,
-                                                 const float (&theta0)[8], int n_rounds, float heading_u, float& cx,
-                                                 float& cy, float& cz, float& chead) {
+                                                 const float (&theta0)[8], const RngKey& key, int n_rounds,
+                                                 float heading_u, float& cx, float& cy, float& cz, float& chead) {
     const float pi_f = 3.1415927f;  // torch.pi as fp32; the reference computes rand * 2 * pi left to right
     constexpr int kBatch = 8;
     float x = 0.f, y = 0.f, z = 0.f;
@@ -335,9 +349,19 @@ __device__ __forceinline__ bool resample_command(int i, const RoverMdpParams& P,
         int cols[kBatch], rows[kBatch];
         uint8_t m[kBatch];
         float hz[kBatch];
+        if (kRng) {  // rounds 4q .. 4q+3 = Philox stream 1 + q of this env
 #pragma unroll
-        for (int k = 0; k < kBatch; ++k)  // the first batch was prefetched by the caller
-            u[k] = (r0 == 0) ? theta0[k] : ((r0 + k < n_rounds) ? __ldg(theta_u + (size_t)i * n_rounds + r0 + k) : 0.f);
+            for (int q = 0; q < kBatch / 4; ++q) {
+                uint32_t w[4];
+                rng_env_stream(key, (uint32_t)i, 1u + (uint32_t)(r0 / 4 + q), w);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) u[4 * q + k] = u01(w[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k)  // the first batch was prefetched by the caller
+                u[k] = (r0 == 0) ? theta0[k] : ((r0 + k < n_rounds) ? __ldg(theta_u + (size_t)i * n_rounds + r0 + k) : 0.f);
+        }
 #pragma unroll
         for (int k = 0; k < kBatch; ++k) {
             const float th = __fmul_rn(__fmul_rn(u[k], 2.f), pi_f);                      // :169
@@ -381,17 +405,25 @@ __device__ __forceinline__ unsigned long long make_lookback(unsigned epoch, unsi
 // The block-level work of the post-step.  kFused = false: the reset flags and the per-block reset counts come from the
 // pre-step launch.  kFused = true (rover_mdp_step): `reset_in` comes from pre_step_env of the same thread and the rank of
 // the block's first reset env from a decoupled look-back over the blocks' reset counts (no second launch).
-template <bool kFused>
+template <bool kFused, bool kRng>
 __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool reset_in, float* __restrict__ root_pos_w,
                                                 float* __restrict__ root_quat_w, int n, const RoverMdpParams& P,
                                                 const RoverMdpState& S, const RoverMdpOut& O, const Tables& T,
-                                                const long long* __restrict__ spawn_perm, const float* __restrict__ yaw_u,
-                                                const float* __restrict__ heading_u, const float* __restrict__ theta_u,
-                                                int n_rounds, long long* __restrict__ out_spawn_index,
+                                                const VariatesDev& V, long long* __restrict__ out_spawn_index,
                                                 float* __restrict__ block_stats, unsigned int* __restrict__ done_counter,
-                                                float* __restrict__ stats, float* __restrict__ obs, int obs_stride, int phases,
+                                                float* __restrict__ stats, float* __restrict__ log_out,
+                                                float* __restrict__ obs, int obs_stride, int phases,
                                                 const StatsExchangeDev& X, unsigned long long* __restrict__ lookback,
                                                 unsigned epoch) {
+    const long long* __restrict__ spawn_perm = V.spawn_perm;
+    const float* __restrict__ yaw_u = V.yaw_u;
+    const float* __restrict__ heading_u = V.heading_u;
+    const float* __restrict__ theta_u = V.theta_u;
+    const int n_rounds = V.n_rounds;
+    // {seed, step}: one uniform load per thread (L2 / L1 hit after the first); the step word is advanced by the last
+    // block of the launch, after every block has read it
+    RngKey key = make_rng_key(0ull, 0ull);
+    if (kRng) key = make_rng_key(V.rng[0], *reinterpret_cast<volatile unsigned long long*>(V.rng + 1));
     __shared__ int warp_cnt[ROVER_MDP_BLOCK / 32];
     __shared__ int block_base;
     constexpr int kRedRows = ROVER_MDP_BLOCK / 4;  // 16 row groups of the last-block reduction (>= warps per block)
@@ -415,10 +447,12 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
         chead = S.heading_cmd_w[i];
         act = reinterpret_cast<float2*>(S.action)[i];
         time_left = S.time_left[i];
-        yaw_var = __ldg(yaw_u + i);
-        heading_var = __ldg(heading_u + i);
+        if (!kRng) {
+            yaw_var = __ldg(yaw_u + i);
+            heading_var = __ldg(heading_u + i);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) theta0[k] = (k < n_rounds) ? __ldg(theta_u + (size_t)i * n_rounds + k) : 0.f;
+            for (int k = 0; k < 8; ++k) theta0[k] = (k < n_rounds) ? __ldg(theta_u + (size_t)i * n_rounds + k) : 0.f;
+        }
     }
 
     // ---- rank of this env among the reset envs in ascending env order (== reset_buf.nonzero() order)
@@ -484,9 +518,16 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
         bool origin_known = false;  // env origin of a freshly spawned env stays in registers (no store -> load round trip)
         float org_x = 0.f, org_y = 0.f;
 
+        if (kRng && (reset || time_left <= P.step_dt)) {  // the only envs that consume variates this step
+            uint32_t w[4];
+            rng_env_stream(key, (uint32_t)i, 0u, w);
+            yaw_var = u01(w[0]);
+            heading_var = u01(w[1]);
+        }
         if (reset && (phases & ROVER_PHASE_SPAWN)) {
             // -- reset_root_state_rover (randomizations.py:12-39)
-            spawn_idx = __ldg(spawn_perm + rank);
+            if (kRng) spawn_idx = (long long)spawn_perm_at(make_spawn_perm_key(key, (uint32_t)T.n_spawns), (uint32_t)rank);
+            else spawn_idx = __ldg(spawn_perm + rank);
             const float* sp = T.spawn + 3 * (size_t)spawn_idx;
             px = __ldg(sp);
             py = __ldg(sp + 1);
@@ -534,8 +575,8 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
             // -- CommandTerm._resample: time_left, counter += 1, _resample_command around the (new) env origin
             const float ox = origin_known ? org_x : S.env_origins[3 * (size_t)i];
             const float oy = origin_known ? org_y : S.env_origins[3 * (size_t)i + 1];
-            const bool exhausted = resample_command(i, P, S, T, ox, oy, theta_u, theta0, n_rounds, heading_var, cwx,
-                                                    cwy, cwz, chead);
+            const bool exhausted = resample_command<kRng>(i, P, S, T, ox, oy, theta_u, theta0, key, n_rounds, heading_var,
+                                                          cwx, cwy, cwz, chead);
             st[14] = exhausted ? 1.f : 0.f;
             S.command_counter[i] += 1;
             time_left = P.resampling_time;
@@ -554,8 +595,10 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
         if ((phases & ROVER_PHASE_TIME) && time_left <= 0.f) {
             const float ox = origin_known ? org_x : S.env_origins[3 * (size_t)i];
             const float oy = origin_known ? org_y : S.env_origins[3 * (size_t)i + 1];
-            const bool exhausted = resample_command(i, P, S, T, ox, oy, theta_u, theta0, n_rounds, heading_var, cwx,
-                                                    cwy, cwz, chead);
+            // (a reset resample above and this one never meet in one step: the reset sets time_left = resampling_time,
+            // which the launcher requires to exceed step_dt -- so sharing the env's variates between them is safe)
+            const bool exhausted = resample_command<kRng>(i, P, S, T, ox, oy, theta_u, theta0, key, n_rounds, heading_var,
+                                                          cwx, cwy, cwz, chead);
             st[14] += exhausted ? 1.f : 0.f;
             st[15] = 1.f;
             S.command_counter[i] += 1;
@@ -644,8 +687,21 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
             float t = 0.f;
             for (int q = 0; q < G; ++q) t += red[q][threadIdx.x];
             stats[threadIdx.x] += t;
+            // extras["log"] of the ORBIT managers' reset() (A.2), refreshed only by a launch that reset something -- the
+            // reference calls _reset_idx only then (rover_env.py:89-91), so the previous values stay visible otherwise:
+            //   Episode Reward/<term> = mean(episode_sums[ids]) / max_episode_length_s, Episode Termination/<term> =
+            //   count, Metrics/target_pose/<m> = mean over ids; [13] = number of resets, [14], [15] as in stats
+            const float cnt = __shfl_sync(0xffffu, t, 13);  // the 16 statistics live in lanes 0..15 of warp 0
+            if (log_out != nullptr && (phases & ROVER_PHASE_MANAGERS) && cnt > 0.f) {
+                const int k = (int)threadIdx.x;
+                float v = t;
+                if (k < ROVER_NUM_REWARD_TERMS) v = __fdiv_rn(__fdiv_rn(t, cnt), P.episode_length_s);
+                else if (k == 11 || k == 12) v = __fdiv_rn(t, cnt);
+                log_out[k] = v;
+            }
             if (threadIdx.x == 0) {
                 *done_counter = 0u;  // re-arm for the next launch
+                if (kRng) V.rng[1] = V.rng[1] + 1ull;  // next launch = next step of the variate streams
                 if (kFused) {        // fused step: next launch = next epoch, tickets from 0 again
                     lookback[n_blocks] = 0ull;
                     lookback[n_blocks + 1] = (unsigned long long)(epoch + 1u);
@@ -681,68 +737,67 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
     }
 }
 
+template <bool kRng>
 __global__ void __launch_bounds__(ROVER_MDP_BLOCK)
 mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_quat_w, int n,
                      const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
                      const __grid_constant__ RoverMdpOut O, const __grid_constant__ Tables T,
-                     const long long* __restrict__ spawn_perm, const float* __restrict__ yaw_u,
-                     const float* __restrict__ heading_u, const float* __restrict__ theta_u, int n_rounds,
-                     long long* __restrict__ out_spawn_index, float* __restrict__ block_stats,
-                     unsigned int* __restrict__ done_counter, float* __restrict__ stats, float* __restrict__ obs,
-                     int obs_stride, int phases, const __grid_constant__ StatsExchangeDev X) {
-    post_step_block<false>((int)blockIdx.x, (int)gridDim.x, false, root_pos_w, root_quat_w, n, P, S, O, T, spawn_perm, yaw_u,
-                           heading_u, theta_u, n_rounds, out_spawn_index, block_stats, done_counter, stats, obs, obs_stride,
-                           phases, X, nullptr, 0u);
+                     const __grid_constant__ VariatesDev V, long long* __restrict__ out_spawn_index,
+                     float* __restrict__ block_stats, unsigned int* __restrict__ done_counter, float* __restrict__ stats,
+                     float* __restrict__ log_out, float* __restrict__ obs, int obs_stride, int phases,
+                     const __grid_constant__ StatsExchangeDev X) {
+    post_step_block<false, kRng>((int)blockIdx.x, (int)gridDim.x, false, root_pos_w, root_quat_w, n, P, S, O, T, V,
+                                 out_spawn_index, block_stats, done_counter, stats, log_out, obs, obs_stride, phases, X,
+                                 nullptr, 0u);
 }
 
 // rover_mdp_step: pre-step + post-step of one env block in ONE launch (the reset rank comes from a look-back instead of a
 // second launch; the pre-step's outputs of an env are consumed by the same thread).  lookback: [n_blocks] descriptors,
 // then the ticket counter and the epoch (both maintained by the kernel itself, so the launch can sit in a CUDA graph).
+// Logical block ids are ALWAYS tickets: the look-back spins on predecessors, which is only safe if every predecessor
+// has started -- blockIdx order guarantees that on an idle GPU only, a ticket taken at block start guarantees it under
+// MPS, concurrent kernels or a partitioned device as well (one atomic per block).
+template <bool kRng>
 __global__ void __launch_bounds__(ROVER_MDP_BLOCK)
 mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __restrict__ force,
                       float* __restrict__ root_pos_w, float* __restrict__ root_quat_w, int n,
                       const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
                       const __grid_constant__ RoverMdpOut O, const __grid_constant__ Tables T,
-                      const long long* __restrict__ spawn_perm, const float* __restrict__ yaw_u,
-                      const float* __restrict__ heading_u, const float* __restrict__ theta_u, int n_rounds,
-                      long long* __restrict__ out_spawn_index, float* __restrict__ block_stats,
-                      unsigned int* __restrict__ done_counter, float* __restrict__ stats, float* __restrict__ obs,
-                      int obs_stride, int pre_phases, int phases, const __grid_constant__ StatsExchangeDev X,
-                      unsigned long long* __restrict__ lookback, int use_tickets) {
+                      const __grid_constant__ VariatesDev V, long long* __restrict__ out_spawn_index,
+                      float* __restrict__ block_stats, unsigned int* __restrict__ done_counter, float* __restrict__ stats,
+                      float* __restrict__ log_out, float* __restrict__ obs, int obs_stride, int pre_phases, int phases,
+                      const __grid_constant__ StatsExchangeDev X, unsigned long long* __restrict__ lookback) {
     __shared__ int s_bid;
     __shared__ unsigned s_epoch;
     const int n_blocks = (int)gridDim.x;
-    int bid = (int)blockIdx.x;
-    unsigned long long epoch_raw = 0ull;
-    if (threadIdx.x == 0) epoch_raw = *reinterpret_cast<volatile unsigned long long*>(lookback + n_blocks + 1);
-    if (use_tickets) {  // more blocks than the device holds at once: logical ids by ticket, so predecessors have started
-        if (threadIdx.x == 0) s_bid = (int)atomicAdd(lookback + n_blocks, 1ull);
-        __syncthreads();
-        bid = s_bid;
+    if (threadIdx.x == 0) {
+        s_epoch = (unsigned)*reinterpret_cast<volatile unsigned long long*>(lookback + n_blocks + 1);
+        s_bid = (int)atomicAdd(lookback + n_blocks, 1ull);
     }
+    __syncthreads();
+    const int bid = s_bid;
+    const unsigned epoch = s_epoch;
     const int i = bid * ROVER_MDP_BLOCK + threadIdx.x;
     if (i < n) {  // the post-step's rank-independent inputs: in flight while the pre-step part runs
         asm volatile("prefetch.global.L2 [%0];" ::"l"(root_pos_w + 3 * (size_t)i));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(root_quat_w + 4 * (size_t)i));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(S.pos_cmd_w + 3 * (size_t)i));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(theta_u + (size_t)i * n_rounds));
+        if (!kRng) asm volatile("prefetch.global.L2 [%0];" ::"l"(V.theta_u + (size_t)i * V.n_rounds));
         if ((threadIdx.x & 31) == 0) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(S.heading_cmd_w + i));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(S.time_left + i));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(yaw_u + i));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(heading_u + i));
+            if (!kRng) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(V.yaw_u + i));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(V.heading_u + i));
+            }
             asm volatile("prefetch.global.L2 [%0];" ::"l"(S.err_pos + i));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(S.err_heading + i));
         }
     }
     const bool reset = pre_step_env(i, new_actions, force, n, P, S, O, pre_phases);
-    if (threadIdx.x == 0) s_epoch = (unsigned)epoch_raw;
-    __syncthreads();
-    const unsigned epoch = s_epoch;
     if ((pre_phases & ROVER_PRE_TERMS) && threadIdx.x == 0) O.block_reset_counts[bid] = 0;  // unused by this path
-    post_step_block<true>(bid, n_blocks, reset, root_pos_w, root_quat_w, n, P, S, O, T, spawn_perm, yaw_u, heading_u,
-                          theta_u, n_rounds, out_spawn_index, block_stats, done_counter, stats, obs, obs_stride, phases, X,
-                          lookback, epoch);
+    post_step_block<true, kRng>(bid, n_blocks, reset, root_pos_w, root_quat_w, n, P, S, O, T, V, out_spawn_index, block_stats,
+                                done_counter, stats, log_out, obs, obs_stride, phases, X, lookback, epoch);
 }
 
 // one block: thread (p, k) = (threadIdx.x / 16, threadIdx.x % 16) reads statistic k of rank p's slot consistently
@@ -821,6 +876,56 @@ extern "C" int rover_mdp_pre_step(const float* new_actions, const float* force_m
     return check_launch("mdp_pre_step_kernel");
 }
 
+namespace rover {
+
+static int make_variates(const RoverResetVariates* var, int n_envs, VariatesDev& V, const char* who) {
+    ROVER_CHECK(var != nullptr, "%s: NULL RoverResetVariates", who);
+    ROVER_CHECK(var->n_rounds >= 1 && var->n_rounds <= 4096, "%s: n_rounds must be in [1, 4096]", who);
+    if (var->rng_state != nullptr) {
+        V = VariatesDev{nullptr, nullptr, nullptr, nullptr, reinterpret_cast<unsigned long long*>(var->rng_state), var->n_rounds};
+    } else {
+        ROVER_CHECK(var->spawn_perm && var->yaw_u && var->heading_u && var->theta_u,
+                    "%s: explicit variates need spawn_perm, yaw_u, heading_u and theta_u (or set rng_state)", who);
+        V = VariatesDev{reinterpret_cast<const long long*>(var->spawn_perm), var->yaw_u, var->heading_u, var->theta_u, nullptr,
+                        var->n_rounds};
+    }
+    (void)n_envs;
+    return 0;
+}
+
+static int make_exchange(const RoverStatsExchange* xchg, StatsExchangeDev& X, const char* who) {
+    X = StatsExchangeDev{nullptr, nullptr, nullptr, 0, 0};
+    if (xchg != nullptr) {
+        ROVER_CHECK(xchg->peer_mailbox && xchg->cumulative && xchg->sequence && xchg->world >= 1 && xchg->rank >= 0 &&
+                        xchg->rank < xchg->world,
+                    "%s: bad RoverStatsExchange", who);
+        X = StatsExchangeDev{xchg->peer_mailbox, xchg->cumulative, reinterpret_cast<unsigned long long*>(xchg->sequence),
+                             xchg->rank, xchg->world};
+    }
+    return 0;
+}
+
+static int check_post_args(const float* root_pos_w, const float* root_quat_w, int n_envs, const RoverMdpParams* params,
+                           const RoverTerrainTables* tables, const float* stats, const float* scratch, const float* obs,
+                           int obs_stride, int phases, const char* who) {
+    ROVER_CHECK(root_pos_w && root_quat_w && params && tables && stats && scratch, "%s: NULL argument", who);
+    ROVER_CHECK(tables->heightmap && tables->safe_mask && tables->spawn_table && tables->height > 0 &&
+                    tables->width > 0 && tables->n_spawns > 0 && tables->resolution > 0.f,
+                "%s: bad terrain tables", who);
+    // without-replacement spawn draw: reset rank j < n_envs indexes a permutation of the table's rows
+    ROVER_CHECK(!(phases & ROVER_PHASE_SPAWN) || tables->n_spawns >= n_envs,
+                "%s: spawn table has %d rows for %d envs (randperm(len(spawn))[:K] needs K <= len)", who, tables->n_spawns,
+                n_envs);
+    // a reset resample and a time-based resample of one env share the env's variates; they never meet in one step as
+    // long as a fresh command outlives the step (reference: 150 s against 0.2 s)
+    ROVER_CHECK(params->resampling_time > params->step_dt, "%s: resampling_time must exceed step_dt", who);
+    ROVER_CHECK((reinterpret_cast<uintptr_t>(root_quat_w) & 15) == 0, "%s: root_quat_w not 16B aligned", who);
+    ROVER_CHECK(obs == nullptr || obs_stride >= 4, "%s: obs_stride < 4", who);
+    return 0;
+}
+
+}  // namespace rover
+
 extern "C" int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_t n_envs, const RoverMdpParams* params,
                                    const RoverMdpState* state, const RoverMdpOut* out,
                                    const RoverTerrainTables* tables, const int64_t* spawn_perm, const float* yaw_u,
@@ -838,26 +943,26 @@ extern "C" int rover_mdp_post_step_x(float* root_pos_w, float* root_quat_w, int3
                                      const float* heading_u, const float* theta_u, int32_t n_rounds,
                                      int64_t* out_spawn_index, float* stats, float* scratch, float* obs,
                                      int32_t obs_stride, int32_t phases, const RoverStatsExchange* xchg, void* stream) {
+    const RoverResetVariates var{spawn_perm, yaw_u, heading_u, theta_u, n_rounds, 0, nullptr};
+    return rover_mdp_post_step_v3(root_pos_w, root_quat_w, n_envs, params, state, out, tables, &var, out_spawn_index, stats,
+                                  scratch, nullptr, obs, obs_stride, phases, xchg, stream);
+}
+
+extern "C" int rover_mdp_post_step_v3(float* root_pos_w, float* root_quat_w, int32_t n_envs, const RoverMdpParams* params,
+                                      const RoverMdpState* state, const RoverMdpOut* out,
+                                      const RoverTerrainTables* tables, const RoverResetVariates* variates,
+                                      int64_t* out_spawn_index, float* stats, float* scratch, float* log_out, float* obs,
+                                      int32_t obs_stride, int32_t phases, const RoverStatsExchange* xchg, void* stream) {
     using namespace rover;
-    StatsExchangeDev X{nullptr, nullptr, nullptr, 0, 0};
-    if (xchg != nullptr) {
-        ROVER_CHECK(xchg->peer_mailbox && xchg->cumulative && xchg->sequence && xchg->world >= 1 && xchg->rank >= 0 &&
-                        xchg->rank < xchg->world,
-                    "rover_mdp_post_step_x: bad RoverStatsExchange");
-        X = StatsExchangeDev{xchg->peer_mailbox, xchg->cumulative,
-                             reinterpret_cast<unsigned long long*>(xchg->sequence), xchg->rank, xchg->world};
-    }
+    StatsExchangeDev X;
+    if (int rc = make_exchange(xchg, X, "rover_mdp_post_step")) return rc;
     ROVER_CHECK(n_envs >= 0, "rover_mdp_post_step: negative n_envs");
     if (n_envs == 0) return 0;
-    ROVER_CHECK(root_pos_w && root_quat_w && params && tables && spawn_perm && yaw_u && heading_u && theta_u && stats &&
-                    scratch,
-                "rover_mdp_post_step: NULL argument");
-    ROVER_CHECK(n_rounds >= 1, "rover_mdp_post_step: n_rounds must be >= 1");
-    ROVER_CHECK(tables->heightmap && tables->safe_mask && tables->spawn_table && tables->height > 0 &&
-                    tables->width > 0 && tables->n_spawns > 0 && tables->resolution > 0.f,
-                "rover_mdp_post_step: bad terrain tables");
-    ROVER_CHECK((reinterpret_cast<uintptr_t>(root_quat_w) & 15) == 0, "rover_mdp_post_step: root_quat_w not 16B aligned");
-    ROVER_CHECK(obs == nullptr || obs_stride >= 4, "rover_mdp_post_step: obs_stride < 4");
+    if (int rc = check_post_args(root_pos_w, root_quat_w, n_envs, params, tables, stats, scratch, obs, obs_stride, phases,
+                                 "rover_mdp_post_step"))
+        return rc;
+    VariatesDev V;
+    if (int rc = make_variates(variates, n_envs, V, "rover_mdp_post_step")) return rc;
     if (int rc = check_state(state, out)) return rc;
     Tables T{tables->heightmap, tables->safe_mask, tables->height,   tables->width,   tables->offset_x,
              tables->offset_y,  tables->resolution, tables->spawn_table, tables->n_spawns};
@@ -865,10 +970,15 @@ extern "C" int rover_mdp_post_step_x(float* root_pos_w, float* root_quat_w, int3
     // scratch layout: [blocks * 16] block partials, then one uint32 completion counter (zero-initialised by caller)
     float* block_stats = scratch;
     unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + (size_t)blocks * ROVER_STATS_LEN);
-    mdp_post_step_kernel<<<blocks, ROVER_MDP_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(
-        root_pos_w, root_quat_w, n_envs, *params, *state, *out, T, reinterpret_cast<const long long*>(spawn_perm),
-        yaw_u, heading_u, theta_u, n_rounds, reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats,
-        obs, obs_stride, phases, X);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (V.rng != nullptr)
+        mdp_post_step_kernel<true><<<blocks, ROVER_MDP_BLOCK, 0, st>>>(
+            root_pos_w, root_quat_w, n_envs, *params, *state, *out, T, V, reinterpret_cast<long long*>(out_spawn_index),
+            block_stats, counter, stats, log_out, obs, obs_stride, phases, X);
+    else
+        mdp_post_step_kernel<false><<<blocks, ROVER_MDP_BLOCK, 0, st>>>(
+            root_pos_w, root_quat_w, n_envs, *params, *state, *out, T, V, reinterpret_cast<long long*>(out_spawn_index),
+            block_stats, counter, stats, log_out, obs, obs_stride, phases, X);
     return check_launch("mdp_post_step_kernel");
 }
 
@@ -879,48 +989,84 @@ extern "C" int rover_mdp_step(const float* new_actions, const float* force_matri
                               int64_t* out_spawn_index, float* stats, float* scratch, uint64_t* lookback, float* obs,
                               int32_t obs_stride, int32_t pre_phases, int32_t phases, const RoverStatsExchange* xchg,
                               void* stream) {
+    const RoverResetVariates var{spawn_perm, yaw_u, heading_u, theta_u, n_rounds, 0, nullptr};
+    return rover_mdp_step_v3(new_actions, force_matrix_w, root_pos_w, root_quat_w, n_envs, params, state, out, tables, &var,
+                             out_spawn_index, stats, scratch, lookback, nullptr, obs, obs_stride, pre_phases, phases, xchg,
+                             stream);
+}
+
+extern "C" int rover_mdp_step_v3(const float* new_actions, const float* force_matrix_w, float* root_pos_w,
+                                 float* root_quat_w, int32_t n_envs, const RoverMdpParams* params,
+                                 const RoverMdpState* state, const RoverMdpOut* out, const RoverTerrainTables* tables,
+                                 const RoverResetVariates* variates, int64_t* out_spawn_index, float* stats, float* scratch,
+                                 uint64_t* lookback, float* log_out, float* obs, int32_t obs_stride, int32_t pre_phases,
+                                 int32_t phases, const RoverStatsExchange* xchg, void* stream) {
     using namespace rover;
     ROVER_CHECK(n_envs >= 0, "rover_mdp_step: negative n_envs");
     if (n_envs == 0) return 0;
     ROVER_CHECK(params && (new_actions || !(pre_phases & ROVER_PRE_ACTIONS)) &&
-                    (force_matrix_w || !(pre_phases & ROVER_PRE_TERMS)) && root_pos_w && root_quat_w && tables &&
-                    spawn_perm && yaw_u && heading_u && theta_u && stats && scratch && lookback,
+                    (force_matrix_w || !(pre_phases & ROVER_PRE_TERMS)) && lookback,
                 "rover_mdp_step: NULL argument");
-    ROVER_CHECK(params->num_bodies >= 0 && params->max_episode_length > 0 && n_rounds >= 1, "rover_mdp_step: bad params");
-    ROVER_CHECK(tables->heightmap && tables->safe_mask && tables->spawn_table && tables->height > 0 &&
-                    tables->width > 0 && tables->n_spawns > 0 && tables->resolution > 0.f,
-                "rover_mdp_step: bad terrain tables");
-    ROVER_CHECK((reinterpret_cast<uintptr_t>(root_quat_w) & 15) == 0, "rover_mdp_step: root_quat_w not 16B aligned");
-    ROVER_CHECK(obs == nullptr || obs_stride >= 4, "rover_mdp_step: obs_stride < 4");
+    ROVER_CHECK(params->num_bodies >= 0 && params->max_episode_length > 0, "rover_mdp_step: bad params");
+    if (int rc = check_post_args(root_pos_w, root_quat_w, n_envs, params, tables, stats, scratch, obs, obs_stride, phases,
+                                 "rover_mdp_step"))
+        return rc;
+    VariatesDev V;
+    if (int rc = make_variates(variates, n_envs, V, "rover_mdp_step")) return rc;
     if (int rc = check_state(state, out)) return rc;
-    StatsExchangeDev X{nullptr, nullptr, nullptr, 0, 0};
-    if (xchg != nullptr) {
-        ROVER_CHECK(xchg->peer_mailbox && xchg->cumulative && xchg->sequence && xchg->world >= 1 && xchg->rank >= 0 &&
-                        xchg->rank < xchg->world,
-                    "rover_mdp_step: bad RoverStatsExchange");
-        X = StatsExchangeDev{xchg->peer_mailbox, xchg->cumulative,
-                             reinterpret_cast<unsigned long long*>(xchg->sequence), xchg->rank, xchg->world};
-    }
+    StatsExchangeDev X;
+    if (int rc = make_exchange(xchg, X, "rover_mdp_step")) return rc;
     Tables T{tables->heightmap, tables->safe_mask, tables->height,   tables->width,   tables->offset_x,
              tables->offset_y,  tables->resolution, tables->spawn_table, tables->n_spawns};
     const int blocks = (n_envs + ROVER_MDP_BLOCK - 1) / ROVER_MDP_BLOCK;
     float* block_stats = scratch;
     unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + (size_t)blocks * ROVER_STATS_LEN);
-    // how many blocks the device holds at once: below that every block is resident and blockIdx is a safe logical id
-    static int resident_blocks = 0;
-    if (resident_blocks == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        ROVER_CUDA(cudaGetDevice(&dev));
-        ROVER_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        ROVER_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mdp_fused_step_kernel, ROVER_MDP_BLOCK, 0));
-        resident_blocks = sms * (per_sm > 0 ? per_sm : 1);
-    }
-    mdp_fused_step_kernel<<<blocks, ROVER_MDP_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(
-        new_actions, force_matrix_w, root_pos_w, root_quat_w, n_envs, *params, *state, *out, T,
-        reinterpret_cast<const long long*>(spawn_perm), yaw_u, heading_u, theta_u, n_rounds,
-        reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats, obs, obs_stride, pre_phases, phases, X,
-        reinterpret_cast<unsigned long long*>(lookback), blocks > resident_blocks ? 1 : 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (V.rng != nullptr)
+        mdp_fused_step_kernel<true><<<blocks, ROVER_MDP_BLOCK, 0, st>>>(
+            new_actions, force_matrix_w, root_pos_w, root_quat_w, n_envs, *params, *state, *out, T, V,
+            reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats, log_out, obs, obs_stride, pre_phases,
+            phases, X, reinterpret_cast<unsigned long long*>(lookback));
+    else
+        mdp_fused_step_kernel<false><<<blocks, ROVER_MDP_BLOCK, 0, st>>>(
+            new_actions, force_matrix_w, root_pos_w, root_quat_w, n_envs, *params, *state, *out, T, V,
+            reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats, log_out, obs, obs_stride, pre_phases,
+            phases, X, reinterpret_cast<unsigned long long*>(lookback));
     return check_launch("mdp_fused_step_kernel");
+}
+
+// The variates the kernels generate in registers, evaluated on the HOST by the same functions (rng.cuh): the oracle is
+// fed these, the kernel generates its own, and the two must agree bit for bit (tests/test_gpu_rng.py).
+extern "C" int rover_rng_variates(uint64_t seed, uint64_t step, int32_t n_envs, int32_t n_rounds, int32_t n_spawns,
+                                  int64_t* spawn_perm, float* yaw_u, float* heading_u, float* theta_u) {
+    using namespace rover;
+    ROVER_CHECK(n_envs >= 0 && n_rounds >= 1 && n_spawns >= 1, "rover_rng_variates: bad sizes");
+    const RngKey key = make_rng_key(seed, step);
+    if (spawn_perm != nullptr) {
+        const SpawnPermKey pk = make_spawn_perm_key(key, (uint32_t)n_spawns);
+        const int k = n_envs < n_spawns ? n_envs : n_spawns;
+        for (int j = 0; j < k; ++j) spawn_perm[j] = (int64_t)spawn_perm_at(pk, (uint32_t)j);
+    }
+    for (int i = 0; i < n_envs; ++i) {
+        uint32_t w[4];
+        rng_env_stream(key, (uint32_t)i, 0u, w);
+        if (yaw_u) yaw_u[i] = u01(w[0]);
+        if (heading_u) heading_u[i] = u01(w[1]);
+        if (theta_u) {
+            for (int r0 = 0; r0 < n_rounds; r0 += 4) {
+                rng_env_stream(key, (uint32_t)i, 1u + (uint32_t)(r0 / 4), w);
+                for (int k = 0; k < 4 && r0 + k < n_rounds; ++k) theta_u[(size_t)i * n_rounds + r0 + k] = u01(w[k]);
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" int rover_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t o[4];
+    rover::philox4x32_10(counter[0], counter[1], counter[2], counter[3], key[0], key[1], o);
+    for (int k = 0; k < 4; ++k) out[k] = o[k];
+    return 0;
 }
 
 extern "C" int rover_stats_read(const void* mailbox_local, int32_t world, double* out, void* stream) {

@@ -107,7 +107,10 @@ class P2PStats:
             self._mailbox = mb.value
             handle = (C.c_uint8 * 64)()
             _lib.check(lib.rover_p2p_export(C.c_void_p(self._mailbox), C.byref(handle)))
-            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+            # the 64-byte IPC handles are the only thing the process group ever carries (once, here); under gloo -- the
+            # one-GPU test of the protocol: two processes sharing a device -- they travel as host tensors
+            on_host = self.world > 1 and dist.get_backend(group) == "gloo"
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device="cpu" if on_host else self.device)
             if self.world > 1:
                 gathered = [torch.empty_like(mine) for _ in range(self.world)]
                 dist.all_gather(gathered, mine, group=group)

@@ -187,6 +187,7 @@ def mdp_params(cfg: RoverEnvCfg) -> _lib.MdpParams:
     p.heading_lo, p.heading_hi = cfg.commands.heading_range
     p.spawn_z_offset = cfg.spawn_z_offset
     p.num_bodies = cfg.num_contact_bodies
+    p.episode_length_s = cfg.episode_length_s
     return p
 
 

@@ -50,6 +50,14 @@ def check_mdp_steps_vs_oracle(dev, n, v, tables, size, res, n_steps=6, margin=4.
         st = synthetic.make_step(n, gen, vt, size, res, margin=margin)
         if step == 2:
             st.actions[:4] = torch.tensor([[0.0135, 0.0135], [0.0135, 0.7], [0.6, 0.0135], [-0.4, 0.2]])
+        # Envs whose distance to the target sits within an ulp or two of a termination threshold would let libm and
+        # CUDA disagree on the mask, and one flipped reset shifts the reset RANK (hence the spawn row) of every later
+        # env.  Their command is moved off the threshold (same edit on both sides: the CUDA buffers are loaded from
+        # the oracle state below), so that every check of the step runs on every env.
+        dist0 = ost.pos_cmd_b[:, :2].norm(dim=1)
+        amb0 = _near(dist0, 0.18, 1e-6) | _near(dist0, 11.0, 1e-5)
+        assert amb0.sum() <= max_ambiguous
+        ost.pos_cmd_b[amb0] *= 1.001
         _load_state(buf, ost)
         buf.stats.zero_()
         d = st.to(dev)
@@ -63,15 +71,11 @@ def check_mdp_steps_vs_oracle(dev, n, v, tables, size, res, n_steps=6, margin=4.
                              st.yaw_u, st.theta_u, st.heading_u)
         # ---- masks: bit-exact away from the thresholds
         dist = pre_pos_b[:, :2].norm(dim=1)
-        amb = _near(dist, 0.18, 1e-6) | _near(dist, 11.0, 1e-5)
-        assert amb.sum() <= max_ambiguous
-        ok = ~amb
+        assert not (_near(dist, 0.18, 1e-6) | _near(dist, 11.0, 1e-5)).any()
         flags = buf.term_flags.cpu().bool()
-        assert torch.equal(flags[ok], out.term_flags[ok])
-        assert torch.equal(buf.terminated.cpu().bool()[ok], out.terminated[ok])
-        assert torch.equal(buf.truncated.cpu().bool()[ok], out.truncated[ok])
-        if amb.any():  # keep the closed loop consistent for the statistics below
-            continue
+        assert torch.equal(flags, out.term_flags)
+        assert torch.equal(buf.terminated.cpu().bool(), out.terminated)
+        assert torch.equal(buf.truncated.cpu().bool(), out.truncated)
         # ---- actions / rewards: 1e-5 relative
         torch.testing.assert_close(buf.processed_actions.cpu(), out.processed_actions, rtol=0, atol=0)
         torch.testing.assert_close(buf.joint_pos.cpu(), out.joint_pos, rtol=1e-5, atol=1e-6)

@@ -15,9 +15,17 @@ from isaac_rover_orbit_b200.dist import P2PStats  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    # ROVER_P2P_SAME_DEVICE=1: every rank is a separate process on cuda:0 -- the mailboxes are still mapped through CUDA
+    # IPC and written by "peer" stores, so the sequence-lock protocol runs on a one-GPU box (NCCL refuses two ranks on
+    # one device: the handles and the reference sum travel over gloo there)
+    same_device = os.environ.get("ROVER_P2P_SAME_DEVICE", "0") == "1"
+    local = 0 if same_device else local
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if same_device:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
     n = 1024
     v, f = TR.make_synthetic_terrain(48.0, 0.2, seed=3)
     tables = TR.build_terrain_tables(v, f, n)
@@ -31,7 +39,7 @@ def main():
     gen = torch.Generator().manual_seed(100 + rank)
     vt = torch.from_numpy(v)
     mine = torch.zeros(16, dtype=torch.float64, device=dev)
-    steps = 20 + 3 * rank  # ranks publish different numbers of steps
+    steps = 20 + (3 + int(os.environ.get("ROVER_P2P_EXTRA_STEPS", "0"))) * rank  # ranks publish different numbers of steps
     for _ in range(steps):
         st = synthetic.make_step(n, gen, vt, 48.0, 0.2, margin=4.0).to(dev)
         buf.stats.zero_()
@@ -43,12 +51,12 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    want = mine.clone()
+    want = mine.cpu() if same_device else mine.clone()
     dist.all_reduce(want, op=dist.ReduceOp.SUM)
     got = p2p.read().clone()
     torch.cuda.synchronize()
-    ok = bool(torch.equal(got, want)) and float(got[13]) > 0
-    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    ok = bool(torch.equal(got.cpu(), want.cpu())) and float(got[13]) > 0
+    flag = torch.tensor([1.0 if ok else 0.0], device="cpu" if same_device else dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("P2P_STATS_OK" if flag.item() == 1.0 else f"P2P_STATS_MISMATCH got {got.tolist()} want {want.tolist()}", flush=True)

@@ -213,6 +213,9 @@ def test_policy_cfg4_kernels_agree_and_rows_are_independent(full, monkeypatch):
         for k in keys[2:5]:
             h = lr(lin(k, h))
         ref = torch.tanh(lin(keys[5], h))
-        assert float((mean - ref).abs().max()) < 3e-2  # bf16 operands cannot meet 1e-5
+        # bf16 operands cannot meet 1e-5: the kernel may be no further from the fp32 network than
+        # the emulation's own operand-rounding distance plus the accumulation-order allowance above
+        assert float((mean - ref).abs().max()) <= float((emu - ref).abs().max()) + 4e-3
+        assert float((mean - ref).abs().max()) < 3e-2
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev

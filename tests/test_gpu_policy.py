@@ -53,7 +53,13 @@ def test_policy_forward_reference_checkpoint(cuda_device, golden):
     emu = emulate_bf16(obs, sd)
     torch.testing.assert_close(mean, emu, rtol=0, atol=4e-3)          # same numerics: bf16 rounding noise only
     ref = torch.from_numpy(z["ref_mean"])                             # the reference network in fp32
-    assert (mean - ref).abs().max() < 3e-2, (mean - ref).abs().max()  # bf16 operands cannot meet 1e-5
+    # bf16 operands cannot meet 1e-5.  On these inputs the bf16 emulation itself sits 7.1e-3 from the
+    # fp32 network (max; mean 1.4e-3) -- pure operand rounding, measured on the CPU -- so the kernel is held to 1e-2
+    # and to the emulation's own distance (+ the 4e-3 accumulation-order allowance above), not to a looser bound.
+    emu_err = float((emu - ref).abs().max())
+    assert emu_err < 8e-3, emu_err
+    assert (mean - ref).abs().max() < 1e-2, (mean - ref).abs().max()
+    assert (mean - ref).abs().max() <= emu_err + 4e-3
     torch.testing.assert_close(OP.policy_mean(obs, sd), ref, rtol=1e-5, atol=1e-6)
 
 
