@@ -134,6 +134,11 @@ class P2PStats:
             self._last = torch.zeros(STATS_LEN, dtype=torch.float64, device=self.device)
         self.struct = _lib.StatsExchange(self._peer_table.data_ptr(), self._cumulative.data_ptr(),
                                          self._sequence.data_ptr(), self.rank, self.world)
+        from . import torch_ops
+
+        self.desc = torch_ops.descriptor(self.struct)  # argument of torch.ops.rover_b200.mdp_post_step(..., xchg=)
+        # the local mailbox as a tensor (not torch-allocated memory: cudaMalloc'ed so that it can be exported over IPC)
+        self._mailbox_words = _lib.MAILBOX_SLOT_BYTES * self.world // 8
         if self.world > 1:
             dist.barrier(group=group)  # every mailbox is mapped everywhere before anyone publishes
 
@@ -142,7 +147,7 @@ class P2PStats:
         self._lib.check(self._lib.load().rover_stats_read(C.c_void_p(self._mailbox), self.world,
                                                           C.c_void_p(self._out.data_ptr()),
                                                           self._lib.current_stream(self.device)))
-        return self._out
+        return self._out  # (the mailbox is raw cudaMalloc memory, so this one call stays on the plain C ABI)
 
     def interval(self) -> torch.Tensor:
         """Totals accumulated since the previous ``interval()`` call (what ``episode_log`` expects)."""

@@ -10,8 +10,10 @@ read (SURVEY.md 8b "What env must expose to terms"):
     env.scene[asset].data.{root_pos_w, root_quat_w, heading_w, default_root_state}, env.scene.terrain
 
 The step keeps the reference's order (process actions -> physics x decimation -> counters -> terminations ->
-rewards -> reset -> command update -> observations) but runs it as three launches:
-``rover_mdp_pre_step`` (ACTIONS | TERMS), ``rover_mdp_post_step`` and ``rover_height_scan``.
+rewards -> reset -> command update -> observations) but runs it as three launches -- ``rover_mdp_pre_step``
+(ACTIONS | TERMS), ``rover_mdp_post_step_v3`` (variates drawn in the kernel, episode log written by the kernel) and
+``rover_height_scan`` -- or four when the physics callable must see this step's joint targets (ACTIONS and TERMS then
+sit on either side of it).  Nothing else is launched per step.
 PhysX is out of scope: ``physics`` is any callable ``(env) -> None`` that updates ``robot.data.root_pos_w /
 root_quat_w`` and ``contact_sensor.data.force_matrix_w`` in place (default: synthetic state, see synthetic.py).
 """
@@ -23,7 +25,6 @@ import torch
 
 from . import _lib, ops
 from .config import REWARD_TERMS, TERMINATION_TERMS, RoverEnvCfg
-from .dist import EpisodeStats, episode_log
 from .terrain import TerrainTables
 
 
@@ -177,11 +178,23 @@ class CommandManager:
 
 
 class RoverEnv:
-    """Drop-in for ``RoverEnv.step`` on synthetic physics (see the module docstring)."""
+    """Drop-in for ``RoverEnv.step`` on synthetic physics (see the module docstring).
 
-    def __init__(self, cfg: RoverEnvCfg, terrain: TerrainTables, device="cuda:0", physics=None, seed: int = 0):
+    ``physics``: callable ``(env) -> None``, the stand-in for the PhysX stepping of rover_env.py:64-75.
+    ``physics_needs_targets`` (default True): the callable reads the joint targets of this step, so the action term must
+    have run before it -- ``step`` is then pre_step(ACTIONS), physics, pre_step(TERMS), post_step, scan (4 launches).
+    With ``False`` (a replayed / synthetic state source) or without physics the two pre-step phases run as ONE launch
+    after the state update: 3 launches per step.
+    Random variates of the reset path come from the in-kernel counter-based generator keyed on ``seed`` (no torch
+    generator call per step); ``set_variates`` feeds explicit arrays instead (parity tests).
+    ``enable_cuda_graph()`` captures the whole step once; ``step`` then costs one action copy + one graph launch.
+    """
+
+    def __init__(self, cfg: RoverEnvCfg, terrain: TerrainTables, device="cuda:0", physics=None, seed: int = 0,
+                 physics_needs_targets: bool = True):
         from .mdp.actions import AckermannAction2
         from .mdp.commands import TerrainBasedPositionCommand
+        from .policy import alloc_obs
 
         self.cfg = cfg
         self.device = torch.device(device)
@@ -199,35 +212,62 @@ class RoverEnv:
         robot = RobotArticulation(n, self.device)
         self.scene = Scene({"robot": robot}, {}, None)
         self.scene.terrain = RoverTerrainImporter(self, terrain)
+        if self.scene.terrain.handle.n_spawns < n:
+            # randomizations.py:22 draws randperm(len(spawn_locations))[:K] with K up to num_envs
+            raise ValueError(f"spawn table has {self.scene.terrain.handle.n_spawns} rows for {n} envs: build the terrain "
+                             f"tables for at least num_envs environments")
         self.scene.sensors["height_scanner"] = RayCaster(self, cfg.height_scanner)
         self.scene.sensors["contact_sensor"] = ContactSensor(n, cfg.num_contact_bodies, self.device)
         self.action_manager = ActionManager(self, AckermannAction2(cfg.actions, self))
         self.command_manager = CommandManager(self, {"target_pose": TerrainBasedPositionCommand(cfg.commands, self)})
-        self.obs_buf = torch.zeros(n, 4 + self.scene.sensors["height_scanner"].ray_pattern.n_rays, device=self.device)
+        # rows padded to 16 bytes: the policy kernel's TMA tensor map reads the buffer in place (no re-homing copy)
+        self.obs_buf = alloc_obs(n, self.device, 4 + self.scene.sensors["height_scanner"].ray_pattern.n_rays)
         self.reward_buf = self._buf.reward
         self.reset_buf = self._buf.reset_flags
-        self.reset_terminated = self._buf.terminated
-        self.reset_time_outs = self._buf.truncated
-        self.extras = {}
-        self._stats = EpisodeStats(self._buf)
-        self._gen = torch.Generator(device=self.device).manual_seed(seed)
+        # the kernels write 0 / 1 bytes: the bool tensors the reference returns are views, not per-step conversions
+        self.reset_terminated = self._buf.terminated.view(torch.bool)
+        self.reset_time_outs = self._buf.truncated.view(torch.bool)
+        # extras["log"]: 0-dim views of the vector the post-step kernel refreshes whenever an env reset (ORBIT
+        # manager.reset() semantics, A.2; the values of the last reset persist in between, as in the reference)
+        lg = self._buf.log
+        self._log = {f"Episode Reward/{name}": lg[i] for i, name in enumerate(REWARD_TERMS)}
+        self._log.update({f"Episode Termination/{name}": lg[7 + i] for i, name in enumerate(TERMINATION_TERMS)})
+        self._log["Metrics/target_pose/error_pos"] = lg[11]
+        self._log["Metrics/target_pose/error_heading"] = lg[12]
+        self.extras = {"log": self._log, "episode": self._log}
+        self._rng = ops.ResetRng(seed, self.device)
         self._physics = physics
+        self._physics_needs_targets = bool(physics_needs_targets) and physics is not None
         self._variates = None
+        self._terms_current = False   # term columns (rewards / terminations) belong to the current state
+        self._graph = None
+        self._action_in = torch.zeros(n, 2, device=self.device)
         # rover_env.py:18-25: env origins are shifted by +100 m in x and y
         self._buf.env_origins[:, 0] += 100.0
         self._buf.env_origins[:, 1] += 100.0
         self._buf.time_left.fill_(cfg.commands.resampling_time_range[0])
 
     # ---------------------------------------------------------------------------------------------- helpers
-    def _draw_variates(self):
-        n, g = self.num_envs, self._gen
-        return (torch.randperm(2 * n, device=self.device, generator=g),
-                torch.rand(n, device=self.device, generator=g), torch.rand(n, device=self.device, generator=g),
-                torch.rand(n, self.cfg.target_rounds, device=self.device, generator=g))
+    def seed(self, seed: int = -1) -> int:
+        """``RLTaskEnv.seed``: re-key the variate generator (step counter back to 0)."""
+        self._rng.state.copy_(torch.tensor([int(seed), 0], dtype=torch.int64))
+        return seed
 
     def set_variates(self, spawn_perm, yaw_u, heading_u, theta_u):
         """Parity hook: feed the random variates of the next post-step explicitly (oracle and kernel share them)."""
+        if self._graph is not None:
+            raise RuntimeError("set_variates: the captured step draws its variates in the kernel")
         self._variates = (spawn_perm, yaw_u, heading_u, theta_u)
+
+    def _post(self, phases, obs):
+        robot = self.scene["robot"].data
+        v, self._variates = self._variates, None
+        if v is not None:
+            ops.mdp_post_step(self._buf, self._params, self.scene.terrain.handle, robot.root_pos_w, robot.root_quat_w, *v,
+                              obs=obs, phases=phases)
+        else:
+            ops.mdp_post_step(self._buf, self._params, self.scene.terrain.handle, robot.root_pos_w, robot.root_quat_w,
+                              obs=obs, phases=phases, rng=self._rng, n_rounds=self.cfg.target_rounds)
 
     def _run_post(self, env_ids, phases, obs=None):
         """Single-purpose use of the post-step kernel for the envs in ``env_ids`` (the reference's per-term calls)."""
@@ -238,11 +278,7 @@ class RoverEnv:
         padded = torch.zeros(blocks * _lib.MDP_BLOCK, dtype=torch.int32, device=self.device)
         padded[: self.num_envs] = b.reset_flags
         b.block_reset_counts.copy_(padded.view(blocks, _lib.MDP_BLOCK).sum(dim=1))
-        v = self._variates or self._draw_variates()
-        self._variates = None
-        robot = self.scene["robot"].data
-        ops.mdp_post_step(b, self._params, self.scene.terrain.handle, robot.root_pos_w, robot.root_quat_w, *v, obs=obs,
-                          phases=phases)
+        self._post(phases, obs)
 
     # ---------------------------------------------------------------------------------------------- API
     def reset(self):
@@ -257,10 +293,7 @@ class RoverEnv:
 
     def _reset_idx(self, idx):
         """rover_env.py:27-39 / ORBIT ``RLTaskEnv._reset_idx`` (A.2) for explicit ids."""
-        self._buf.stats.zero_()
         self._run_post(idx, _lib.PHASE_SPAWN | _lib.PHASE_MANAGERS | _lib.PHASE_RESAMPLE)
-        self.extras["log"] = self._log_tensors()
-        self.extras["episode"] = self.extras["log"]
 
     def _scan(self):
         robot = self.scene["robot"].data
@@ -268,40 +301,72 @@ class RoverEnv:
         ops.height_scan(robot.root_pos_w, robot.root_quat_w, sensor.ray_pattern, self.scan_grid,
                         sensor.cfg.max_distance, self.cfg.height_scan_base_offset, out=self.obs_buf[:, 4:])
 
-    def _log_tensors(self):
-        """``extras["log"]`` as 0-dim device tensors (no host sync), ORBIT manager ``reset`` semantics (A.2)."""
-        s = self._buf.stats
-        k = torch.clamp(s[13], min=1.0)
-        log = {f"Episode Reward/{name}": s[i] / k / self.max_episode_length_s for i, name in enumerate(REWARD_TERMS)}
-        log.update({f"Episode Termination/{name}": s[7 + i] for i, name in enumerate(TERMINATION_TERMS)})
-        log["Metrics/target_pose/error_pos"] = s[11] / k
-        log["Metrics/target_pose/error_heading"] = s[12] / k
+    def episode_log(self) -> dict:
+        """Host-side copy of the last episode log (synchronises): the values of ``extras["log"]`` + ``num_resets``."""
+        s = self._buf.log.detach().double().cpu()
+        log = {k: float(v) for k, v in zip(self._log, s[:13])}
+        for name in TERMINATION_TERMS:
+            log[f"Episode Termination/{name}"] = int(round(log[f"Episode Termination/{name}"]))
+        log["num_resets"] = int(round(float(s[13])))
         return log
 
-    def episode_log(self) -> dict:
-        """Host-side copy of the last episode statistics (synchronises)."""
-        return episode_log(self._buf.stats, self.max_episode_length_s)
+    def render(self, *args, **kwargs):
+        """No viewport without Isaac Sim; the reference's eval loop calls it unless ``headless`` (skrl_utils.py:150-206)."""
+        return None
+
+    def close(self):
+        self._graph = None
+
+    def _step_body(self, action):
+        b, robot = self._buf, self.scene["robot"].data
+        contact = self.scene.sensors["contact_sensor"].data
+        if self._physics_needs_targets:
+            # -- process actions; physics stepping (decimation x: identical joint targets, ackermann_actions.py:231-236)
+            self.action_manager.process_action(action)
+            self.action_manager.apply_action()
+            self._physics(self)
+            # -- counters, terminations, rewards (one launch; reads the PREVIOUS command like the reference)
+            ops.mdp_pre_step(b, self._params, None, contact.force_matrix_w, phases=_lib.PRE_TERMS)
+        else:
+            # the state source does not read the joint targets: action term + counters + terminations + rewards in ONE launch
+            if self._physics is not None:
+                self._physics(self)
+            term = self.action_manager.get_term()
+            term.process_actions(action, fused_terms_force=contact.force_matrix_w)
+            self.action_manager.apply_action()
+        # -- reset, command update, observation head, episode log (one launch; variates drawn in the kernel)
+        self._post(_lib.PHASE_ALL, self.obs_buf)
+        # -- height scan straight into the observation buffer (one launch)
+        self._scan()
+
+    def enable_cuda_graph(self, warmup: int = 2):
+        """Capture the step (all launches + a graph-safe ``physics``) into one CUDA graph.  The warm-up steps are real
+        steps (they advance the env); afterwards ``step(action)`` = copy of the action into the captured input + one
+        ``cudaGraphLaunch``."""
+        if self._variates is not None:
+            raise RuntimeError("enable_cuda_graph: explicit variates are pending (set_variates)")
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                self._step_body(self._action_in)
+                self.common_step_counter += 1
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_body(self._action_in)
+        self._graph = g  # (capturing does not execute: the first replay is the next step)
+        return self
 
     def step(self, action: torch.Tensor):
         """rover_env.py:42-102."""
-        b, robot = self._buf, self.scene["robot"].data
-        contact = self.scene.sensors["contact_sensor"].data
-        # -- process actions; physics stepping (decimation x: identical joint targets, ackermann_actions.py:231-236)
-        self.action_manager.process_action(action)
-        self.action_manager.apply_action()
-        if self._physics is not None:
-            self._physics(self)
-        # -- counters, terminations, rewards (one launch; reads the PREVIOUS command like the reference)
-        ops.mdp_pre_step(b, self._params, None, contact.force_matrix_w, phases=_lib.PRE_TERMS)
+        if self._graph is not None:
+            if action.data_ptr() != self._action_in.data_ptr():
+                self._action_in.copy_(action)
+            self._graph.replay()
+        else:
+            self._step_body(action)
         self.common_step_counter += 1
-        # -- reset, command update, observation head (one launch)
-        b.stats.zero_()
-        v = self._variates or self._draw_variates()
-        self._variates = None
-        ops.mdp_post_step(b, self._params, self.scene.terrain.handle, robot.root_pos_w, robot.root_quat_w, *v,
-                          obs=self.obs_buf)
-        # -- height scan straight into the observation buffer (one launch)
-        self._scan()
-        self.extras["log"] = self._log_tensors()
-        self.extras["episode"] = self.extras["log"]
-        return self.obs_buf, self.reward_buf, self.reset_terminated.bool(), self.reset_time_outs.bool(), self.extras
+        self._terms_current = True
+        return self.obs_buf, self.reward_buf, self.reset_terminated, self.reset_time_outs, self.extras

@@ -16,6 +16,7 @@ from ..config import AckermannActionCfg  # noqa: F401  (re-exported like actions
 
 class AckermannAction2:
     cfg: AckermannActionCfg
+    VARIANT = 2
 
     def __init__(self, cfg: AckermannActionCfg, env):
         self.cfg = cfg
@@ -24,7 +25,9 @@ class AckermannAction2:
         self._drive_joint_ids, self._drive_joint_names = self._asset.find_joints(cfg.drive_joint_names)
         self._steering_joint_ids, self._steering_joint_names = self._asset.find_joints(cfg.steering_joint_names)
         self._raw_actions = torch.zeros(self.num_envs, self.action_dim, device=self.device)
-        self._dirty = False
+        # the term's own copy of the kernel parameters: its class selects the kinematics, the env's struct is not touched
+        self._params = _lib.MdpParams.from_buffer_copy(env._params)
+        self._params.action_variant = self.VARIANT
 
     @property
     def num_envs(self) -> int:
@@ -46,18 +49,23 @@ class AckermannAction2:
     def processed_actions(self) -> torch.Tensor:
         return self._env._buf.processed_actions
 
-    def process_actions(self, actions: torch.Tensor):
-        """ackermann_actions.py:226-229 (+ ORBIT ActionManager.process_action: prev_action <- action <- actions)."""
+    def process_actions(self, actions: torch.Tensor, fused_terms_force: torch.Tensor | None = None):
+        """ackermann_actions.py:226-229 (+ ORBIT ActionManager.process_action: prev_action <- action <- actions).
+        ``fused_terms_force`` (``RoverEnv.step`` when nothing has to run between the action term and the reward /
+        termination terms): the contact forces -- the same launch then also advances the counters and computes the
+        terminations and rewards."""
         self._raw_actions[:] = actions
-        ops.mdp_pre_step(self._env._buf, self._env._params, self._raw_actions, None, phases=_lib.PRE_ACTIONS)
-        self._dirty = True
+        phases = _lib.PRE_ACTIONS | (_lib.PRE_TERMS if fused_terms_force is not None else 0)
+        ops.mdp_pre_step(self._env._buf, self._params, self._raw_actions, fused_terms_force, phases=phases)
+        self._env._terms_current = False  # the reward / termination columns describe the previous action until TERMS runs
 
     def apply_actions(self):
-        """ackermann_actions.py:231-236: joint targets [FL,RL,RR,FR] (rad) and [ML,FL,RL,RR,MR,FR] (rad/s)."""
+        """ackermann_actions.py:231-236: joint targets [FL,RL,RR,FR] (rad) and [ML,FL,RL,RR,MR,FR] (rad/s).  The
+        reference recomputes them on each of the ``decimation`` calls; here they were computed once by
+        ``process_actions`` and are re-bound."""
         b = self._env._buf
         self._asset.set_joint_velocity_target(b.joint_vel, joint_ids=self._drive_joint_ids)
         self._asset.set_joint_position_target(b.joint_pos, joint_ids=self._steering_joint_ids)
-        self._dirty = False
 
 
 class AckermannAction(AckermannAction2):
@@ -65,10 +73,6 @@ class AckermannAction(AckermannAction2):
     joint targets come back as [FL,FR,RL,RR] / [FL,FR,ML,MR,RL,RR].  Same ActionTerm API as ``AckermannAction2``."""
 
     VARIANT = 1
-
-    def process_actions(self, actions: torch.Tensor):
-        self._env._params.action_variant = self.VARIANT
-        super().process_actions(actions)
 
 
 class AckermannAction3:

@@ -1,5 +1,8 @@
-"""Thin Python operators over the C ABI (``include/rover_b200.h``): tensors in, tensors out, current stream.
+"""Python operators of the hot path: tensors in, tensors out, current stream.
 
+Every call goes through a torch custom operator (``torch.ops.rover_b200.*``, ``torch_ops.py``: schema + CUDA
+implementation + fake implementation) that forwards to the C ABI of ``include/rover_b200.h``.  The handle classes here
+own the device memory the ABI's host structs point into and hand those structs over as descriptor tensors.
 No operator has a CPU or eager-PyTorch fallback: CUDA tensors are required and a missing library raises.
 """
 from __future__ import annotations
@@ -10,7 +13,7 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, torch_ops
 from .config import RoverEnvCfg
 from .plane_cells import PlaneCells, build_plane_cells
 from .scan_grid import ScanGrid, build_scan_grid
@@ -51,6 +54,9 @@ class ScanGridHandle:
         s.records = self.records.data_ptr()
         s.n_records = grid.n_records
         self.struct = s
+        # descriptor tensors of the torch custom ops: CPU uint8 views of the host structs (no copy)
+        self.desc = torch_ops.descriptor(self.struct)
+        self.cells_desc = torch_ops.descriptor(self.cells_struct) if self.cells_struct is not None else None
 
     @classmethod
     def from_mesh(cls, vertices, faces, device, cell_size=None, plane_cells: bool = True) -> "ScanGridHandle":
@@ -89,6 +95,7 @@ class RayPattern:
                                        float(cpu[:, 1].max()))
         else:
             self.box = (C.c_float * 4)(0.0, 0.0, 0.0, 0.0)
+        self.box_t = torch.frombuffer(self.box, dtype=torch.float32)  # host tensor aliasing the box
 
     @classmethod
     def grid(cls, device, resolution: float = 0.1, size=(3.0, 3.0), offset_pos=(0.0, 0.0, 10.0)) -> "RayPattern":
@@ -117,17 +124,18 @@ def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridH
         raise RuntimeError("height_scan: grid lives on another device")
     if variant in (2, 3, 4, 5) and grid.cells_struct is None:
         raise RuntimeError("height_scan: variants 2..5 need a ScanGridHandle built with plane_cells=True")
+    args = (pos_w, quat_w, ray_starts_local, rays.box_t, grid.desc, grid.cells_desc, float(max_distance),
+            float(base_offset), int(variant))
+    if return_hits:
+        if out is not None:
+            raise RuntimeError("height_scan: return_hits allocates its outputs (out= is not supported with it)")
+        return torch.ops.rover_b200.height_scan_hits(*args)
     if out is None:
-        out = torch.empty(n, r, dtype=torch.float32, device=dev)
-    elif out.dtype != torch.float32 or out.shape != (n, r) or out.stride(1) != 1 or out.device != dev:
+        return torch.ops.rover_b200.height_scan(*args)
+    if out.dtype != torch.float32 or out.shape != (n, r) or out.stride(1) != 1 or out.device != dev:
         raise RuntimeError("height_scan: out must be fp32 [N,R] with unit inner stride")
-    hits = torch.empty(n, r, 3, dtype=torch.float32, device=dev) if return_hits else None
-    _lib.check(_lib.load().rover_height_scan(
-        _lib.ptr(pos_w), _lib.ptr(quat_w), n, _lib.ptr(ray_starts_local), r, C.byref(rays.box), C.byref(grid.struct),
-        C.byref(grid.cells_struct) if grid.cells_struct is not None else None,
-        float(max_distance), float(base_offset), C.c_void_p(out.data_ptr()), int(out.stride(0)) if n > 0 else r,
-        _lib.ptr(hits), int(variant), _lib.current_stream(dev)))
-    return (out, hits) if return_hits else out
+    torch.ops.rover_b200.height_scan_out(*args, out)
+    return out
 
 
 def height_scan_obs(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle, obs: torch.Tensor,
@@ -144,12 +152,8 @@ def height_scan_obs(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanG
             or obs_bf16.dtype != torch.bfloat16 or obs_bf16.shape[0] != n or obs_bf16.stride(1) != 1
             or obs_bf16.shape[1] < head_cols + rays.n_rays or not obs_bf16.is_cuda):
         raise RuntimeError("height_scan_obs: obs must be fp32 and obs_bf16 bf16, both [N, >= head_cols + R] with unit inner stride")
-    dev = pos_w.device
-    _lib.check(_lib.load().rover_height_scan_obs(
-        _lib.ptr(pos_w), _lib.ptr(quat_w), n, _lib.ptr(rays.starts), rays.n_rays, C.byref(rays.box),
-        C.byref(grid.struct), C.byref(grid.cells_struct) if grid.cells_struct is not None else None,
-        float(max_distance), float(base_offset), C.c_void_p(obs.data_ptr()), int(obs.stride(0)), int(head_cols),
-        C.c_void_p(obs_bf16.data_ptr()), int(obs_bf16.stride(0)), _lib.current_stream(dev)))
+    torch.ops.rover_b200.height_scan_obs(pos_w, quat_w, rays.starts, rays.box_t, grid.desc, grid.cells_desc,
+                                         float(max_distance), float(base_offset), obs, int(head_cols), obs_bf16)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -188,7 +192,20 @@ def mdp_params(cfg: RoverEnvCfg) -> _lib.MdpParams:
     p.spawn_z_offset = cfg.spawn_z_offset
     p.num_bodies = cfg.num_contact_bodies
     p.episode_length_s = cfg.episode_length_s
+    if cfg.commands.resampling_time_range[0] != cfg.commands.resampling_time_range[1]:
+        raise ValueError("resampling_time_range must be (t, t): the kernels resample on a fixed period "
+                         "(the reference uses (150, 150), rover_env_cfg.py:191-200)")
+    if p.resampling_time <= p.step_dt:
+        raise ValueError("resampling_time must exceed step_dt")
     return p
+
+
+def params_desc(params: _lib.MdpParams) -> torch.Tensor:
+    """Descriptor tensor of a ``RoverMdpParams`` (cached on the struct; aliases its bytes)."""
+    d = getattr(params, "_desc", None)
+    if d is None:
+        d = params._desc = torch_ops.descriptor(params)
+    return d
 
 
 def ackermann(actions: torch.Tensor, params: _lib.MdpParams, variant: int = 2):
@@ -197,14 +214,9 @@ def ackermann(actions: torch.Tensor, params: _lib.MdpParams, variant: int = 2):
     dev = _lib.require_cuda(actions)
     if actions.dtype != torch.float32 or actions.dim() != 2 or actions.shape[1] != 2:
         raise RuntimeError("ackermann: actions must be fp32 [N,2]")
-    n = actions.shape[0]
     p = _lib.MdpParams.from_buffer_copy(params)
     p.action_variant = int(variant)
-    processed = torch.empty(n, 2, device=dev)
-    jp, jv = torch.empty(n, 4, device=dev), torch.empty(n, 6, device=dev)
-    _lib.check(_lib.load().rover_ackermann(_lib.ptr(actions), n, C.byref(p), _lib.ptr(processed), _lib.ptr(jp),
-                                            _lib.ptr(jv), _lib.current_stream(dev)))
-    return processed, jp, jv
+    return torch.ops.rover_b200.ackermann(actions, torch_ops.descriptor(p))
 
 
 @dataclass
@@ -242,6 +254,7 @@ class MdpBuffers:
     spawn_index: torch.Tensor
     stats: torch.Tensor
     scratch: torch.Tensor
+    log: torch.Tensor  # [16] extras["log"] values, refreshed by a post-step launch that reset at least one env
 
     @staticmethod
     def allocate(n: int, device) -> "MdpBuffers":
@@ -257,7 +270,20 @@ class MdpBuffers:
             f(n), f(n, 2), f(n, 4), f(n, 6), f(n), f(n, 7), f(n, 7), u8(n), u8(n), u8(n, 4), u8(n),
             torch.zeros(max(blocks, 1), dtype=torch.int32, device=device), torch.full((n,), -1, dtype=torch.int64,
                                                                                       device=device),
-            f(_lib.STATS_LEN), f(max(blocks, 1) * _lib.STATS_LEN + 1))
+            f(_lib.STATS_LEN), f(max(blocks, 1) * _lib.STATS_LEN + 1), f(_lib.STATS_LEN))
+
+    def state_list(self) -> list:
+        """The manager state as ``Tensor[]`` in ``RoverMdpState`` field order (argument of the custom ops)."""
+        ls = self.__dict__.get("_state_list")
+        if ls is None:
+            ls = self.__dict__["_state_list"] = [getattr(self, k) for k in _lib._STATE_FIELDS]
+        return ls
+
+    def out_list(self) -> list:
+        ls = self.__dict__.get("_out_list")
+        if ls is None:
+            ls = self.__dict__["_out_list"] = [getattr(self, k) for k in _lib._OUT_FIELDS]
+        return ls
 
     @property
     def lookback(self) -> torch.Tensor:
@@ -267,19 +293,6 @@ class MdpBuffers:
             blocks = (self.n + _lib.MDP_BLOCK - 1) // _lib.MDP_BLOCK
             lb = self.__dict__["_lookback"] = torch.zeros(max(blocks, 1) + 2, dtype=torch.int64, device=self.device)
         return lb
-
-    def state_struct(self) -> _lib.MdpState:
-        """Host struct of device pointers; built once (the buffers are never re-allocated)."""
-        st = self.__dict__.get("_state_struct")
-        if st is None:
-            st = self.__dict__["_state_struct"] = _lib.MdpState(*[getattr(self, k).data_ptr() for k in _lib._STATE_FIELDS])
-        return st
-
-    def out_struct(self) -> _lib.MdpOut:
-        out = self.__dict__.get("_out_struct")
-        if out is None:
-            out = self.__dict__["_out_struct"] = _lib.MdpOut(*[getattr(self, k).data_ptr() for k in _lib._OUT_FIELDS])
-        return out
 
 
 class TerrainTablesHandle:
@@ -299,6 +312,32 @@ class TerrainTablesHandle:
                                          float(resolution), self.spawn_table.data_ptr(), self.spawn_table.shape[0], 0)
         if self.safe_mask.shape != self.heightmap.shape:
             raise RuntimeError("safe_mask and heightmap shapes differ")
+        self.desc = torch_ops.descriptor(self.struct)
+
+    @property
+    def n_spawns(self) -> int:
+        return int(self.spawn_table.shape[0])
+
+
+class ResetRng:
+    """``{seed, step}`` of the in-kernel variate generator (``RoverResetVariates.rng_state``): a CUDA int64[2] tensor the
+    post-step launch reads and advances.  ``variates(n, rounds, n_spawns)`` evaluates, on the host, what the NEXT launch
+    will draw (``rover_rng_variates``; synchronises to read the step word) -- the parity tests feed that to the oracle."""
+
+    def __init__(self, seed: int, device, step: int = 0):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ResetRng needs a CUDA device; there is no CPU fallback")
+        self.state = torch.tensor([int(seed), int(step)], dtype=torch.int64, device=self.device)
+
+    def peek(self) -> tuple:
+        seed, step = (int(v) for v in self.state.cpu())
+        return seed & 0xFFFFFFFFFFFFFFFF, step & 0xFFFFFFFFFFFFFFFF
+
+    def variates(self, n_envs: int, n_rounds: int, n_spawns: int):
+        seed, step = self.peek()
+        sp, yaw, head, theta = _lib.rng_variates(seed, step, n_envs, n_rounds, n_spawns)
+        return torch.from_numpy(sp), torch.from_numpy(yaw), torch.from_numpy(head), torch.from_numpy(theta)
 
 
 def mdp_pre_step(buf: MdpBuffers, params: _lib.MdpParams, actions: torch.Tensor | None,
@@ -313,79 +352,71 @@ def mdp_pre_step(buf: MdpBuffers, params: _lib.MdpParams, actions: torch.Tensor 
     if phases & _lib.PRE_TERMS and (force_matrix_w is None or force_matrix_w.dtype != torch.float32 or
                                     force_matrix_w.numel() != buf.n * params.num_bodies * 3):
         raise RuntimeError("mdp_pre_step: force_matrix_w must be fp32 [N,B,1,3]")
-    st, out = buf.state_struct(), buf.out_struct()
-    _lib.check(_lib.load().rover_mdp_pre_step(_lib.ptr(actions), _lib.ptr(force_matrix_w), buf.n, C.byref(params),
-                                               C.byref(st), C.byref(out), int(phases),
-                                               _lib.current_stream(buf.device)))
+    torch.ops.rover_b200.mdp_pre_step(actions, force_matrix_w, params_desc(params), buf.state_list(), buf.out_list(),
+                                      int(phases))
+
+
+def _check_variates(what, n, spawn_perm, yaw_u, heading_u, theta_u):
+    _lib.require_cuda(spawn_perm, yaw_u, heading_u, theta_u)
+    _require_f32(what, yaw_u=yaw_u, heading_u=heading_u, theta_u=theta_u)
+    if spawn_perm.dtype != torch.int64 or spawn_perm.numel() < n:
+        raise RuntimeError(f"{what}: spawn_perm must be int64 with at least N entries")
+    if theta_u.dim() != 2 or theta_u.shape[0] != n or yaw_u.shape != (n,) or heading_u.shape != (n,):
+        raise RuntimeError(f"{what}: variates must be yaw_u[N], heading_u[N], theta_u[N,R]")
 
 
 def mdp_post_step(buf: MdpBuffers, params: _lib.MdpParams, tables: TerrainTablesHandle, root_pos_w: torch.Tensor,
-                  root_quat_w: torch.Tensor, spawn_perm: torch.Tensor, yaw_u: torch.Tensor, heading_u: torch.Tensor,
-                  theta_u: torch.Tensor, obs: torch.Tensor | None = None, phases: int = _lib.PHASE_ALL,
-                  xchg=None):
+                  root_quat_w: torch.Tensor, spawn_perm: torch.Tensor | None = None, yaw_u: torch.Tensor | None = None,
+                  heading_u: torch.Tensor | None = None, theta_u: torch.Tensor | None = None,
+                  obs: torch.Tensor | None = None, phases: int = _lib.PHASE_ALL, xchg=None, rng: ResetRng | None = None,
+                  n_rounds: int | None = None, log: bool = True):
     """Reset / resample / command update / observation head (one launch).  ``root_*`` are updated in place
-    for the reset envs; ``buf.stats`` is accumulated; ``buf.spawn_index`` holds the spawn rows used (-1 else)."""
-    dev = _lib.require_cuda(root_pos_w, root_quat_w, spawn_perm, yaw_u, heading_u, theta_u)
+    for the reset envs; ``buf.stats`` is accumulated; ``buf.spawn_index`` holds the spawn rows used (-1 else);
+    ``buf.log`` takes the episode log of the launch if it reset an env.  The random variates are either the explicit
+    arrays (``spawn_perm[j]`` by reset rank, ``yaw_u / heading_u / theta_u`` by env id) or, with ``rng=``, drawn inside
+    the kernel from the counter-based generator (no torch generator call, CUDA-graph safe)."""
+    dev = _lib.require_cuda(root_pos_w, root_quat_w)
     if dev != buf.device or tables.device != dev:
         raise RuntimeError("mdp_post_step: tensors on different devices")
-    _require_f32("mdp_post_step", root_pos_w=root_pos_w, root_quat_w=root_quat_w, yaw_u=yaw_u, heading_u=heading_u,
-                 theta_u=theta_u)
+    _require_f32("mdp_post_step", root_pos_w=root_pos_w, root_quat_w=root_quat_w)
     n = buf.n
     if root_pos_w.shape != (n, 3) or root_quat_w.shape != (n, 4):
         raise RuntimeError("mdp_post_step: bad root state shapes")
-    if spawn_perm.dtype != torch.int64 or spawn_perm.numel() < n:
-        raise RuntimeError("mdp_post_step: spawn_perm must be int64 with at least N entries")
-    if theta_u.dim() != 2 or theta_u.shape[0] != n or yaw_u.shape != (n,) or heading_u.shape != (n,):
-        raise RuntimeError("mdp_post_step: variates must be yaw_u[N], heading_u[N], theta_u[N,R]")
-    obs_ptr, obs_stride = None, 0
-    if obs is not None:
-        if obs.dtype != torch.float32 or obs.shape[0] != n or obs.stride(1) != 1 or obs.shape[1] < 4:
-            raise RuntimeError("mdp_post_step: obs must be fp32 [N,>=4] with unit inner stride")
-        obs_ptr, obs_stride = C.c_void_p(obs.data_ptr()), int(obs.stride(0))
-    st, out = buf.state_struct(), buf.out_struct()
+    if rng is not None:
+        variates, rounds = [], int(n_rounds if n_rounds is not None else 16)
+    else:
+        _check_variates("mdp_post_step", n, spawn_perm, yaw_u, heading_u, theta_u)
+        variates, rounds = [spawn_perm, yaw_u, heading_u, theta_u], int(theta_u.shape[1])
+    if (phases & _lib.PHASE_SPAWN) and tables.n_spawns < n:
+        raise RuntimeError(f"mdp_post_step: spawn table has {tables.n_spawns} rows for {n} envs")
     # xchg: a dist.P2PStats -- the launch also publishes the rank's running statistics to every rank's mailbox
-    _lib.check(_lib.load().rover_mdp_post_step_x(
-        _lib.ptr(root_pos_w), _lib.ptr(root_quat_w), n, C.byref(params), C.byref(st), C.byref(out),
-        C.byref(tables.struct), _lib.ptr(spawn_perm), _lib.ptr(yaw_u), _lib.ptr(heading_u), _lib.ptr(theta_u),
-        int(theta_u.shape[1]), _lib.ptr(buf.spawn_index), _lib.ptr(buf.stats), _lib.ptr(buf.scratch), obs_ptr,
-        obs_stride, int(phases), C.byref(xchg.struct) if xchg is not None else None, _lib.current_stream(dev)))
+    torch.ops.rover_b200.mdp_post_step(
+        root_pos_w, root_quat_w, params_desc(params), buf.state_list(), buf.out_list(), tables.desc, variates,
+        rng.state if rng is not None else None, rounds, buf.spawn_index, buf.stats, buf.scratch, buf.log if log else None,
+        obs, int(phases), xchg.desc if xchg is not None else None)
 
 
 def mdp_step(buf: MdpBuffers, params: _lib.MdpParams, tables: "TerrainTablesHandle", new_actions: torch.Tensor | None,
              force_matrix_w: torch.Tensor | None, root_pos_w: torch.Tensor, root_quat_w: torch.Tensor,
-             spawn_perm: torch.Tensor, yaw_u: torch.Tensor, heading_u: torch.Tensor, theta_u: torch.Tensor,
-             obs: torch.Tensor | None = None, pre_phases: int = _lib.PRE_ACTIONS | _lib.PRE_TERMS,
-             phases: int = _lib.PHASE_ALL, xchg=None):
+             spawn_perm: torch.Tensor | None = None, yaw_u: torch.Tensor | None = None,
+             heading_u: torch.Tensor | None = None, theta_u: torch.Tensor | None = None, obs: torch.Tensor | None = None,
+             pre_phases: int = _lib.PRE_ACTIONS | _lib.PRE_TERMS, phases: int = _lib.PHASE_ALL, xchg=None,
+             rng: ResetRng | None = None, n_rounds: int | None = None, log: bool = True):
     """``mdp_pre_step`` + ``mdp_post_step`` in ONE launch (``rover_mdp_step``): for loops whose physics does not sit
     between the two.  Bit-identical to the two-launch sequence (``tests/test_gpu_parity.py``)."""
-    dev = _lib.require_cuda(root_pos_w, root_quat_w, spawn_perm, yaw_u, heading_u, theta_u)
+    dev = _lib.require_cuda(root_pos_w, root_quat_w, new_actions, force_matrix_w)
     if dev != buf.device or tables.device != dev:
         raise RuntimeError("mdp_step: tensors on different devices")
-    _require_f32("mdp_step", root_pos_w=root_pos_w, root_quat_w=root_quat_w, yaw_u=yaw_u, heading_u=heading_u,
-                 theta_u=theta_u, new_actions=new_actions, force_matrix_w=force_matrix_w)
+    _require_f32("mdp_step", root_pos_w=root_pos_w, root_quat_w=root_quat_w, new_actions=new_actions,
+                 force_matrix_w=force_matrix_w)
     n = buf.n
-    if root_pos_w.shape != (n, 3) or root_quat_w.shape != (n, 4):
-        raise RuntimeError("mdp_step: bad root state shapes")
-    if (pre_phases & _lib.PRE_ACTIONS) and (new_actions is None or new_actions.shape != (n, 2)):
-        raise RuntimeError("mdp_step: new_actions must be [N,2]")
-    if (pre_phases & _lib.PRE_TERMS) and (force_matrix_w is None or force_matrix_w.numel() != n * params.num_bodies * 3):
-        raise RuntimeError("mdp_step: force_matrix_w must be [N, num_bodies, 1, 3]")
-    for t in (new_actions, force_matrix_w):
-        if t is not None:
-            _lib.require_cuda(t)
-    if spawn_perm.dtype != torch.int64 or spawn_perm.numel() < n:
-        raise RuntimeError("mdp_step: spawn_perm must be int64 with at least N entries")
-    if theta_u.dim() != 2 or theta_u.shape[0] != n or yaw_u.shape != (n,) or heading_u.shape != (n,):
-        raise RuntimeError("mdp_step: variates must be yaw_u[N], heading_u[N], theta_u[N,R]")
-    obs_ptr, obs_stride = None, 0
-    if obs is not None:
-        if obs.dtype != torch.float32 or obs.shape[0] != n or obs.stride(1) != 1 or obs.shape[1] < 4:
-            raise RuntimeError("mdp_step: obs must be fp32 [N,>=4] with unit inner stride")
-        obs_ptr, obs_stride = C.c_void_p(obs.data_ptr()), int(obs.stride(0))
-    st, out = buf.state_struct(), buf.out_struct()
-    _lib.check(_lib.load().rover_mdp_step(
-        _lib.ptr(new_actions), _lib.ptr(force_matrix_w), _lib.ptr(root_pos_w), _lib.ptr(root_quat_w), n, C.byref(params),
-        C.byref(st), C.byref(out), C.byref(tables.struct), _lib.ptr(spawn_perm), _lib.ptr(yaw_u), _lib.ptr(heading_u),
-        _lib.ptr(theta_u), int(theta_u.shape[1]), _lib.ptr(buf.spawn_index), _lib.ptr(buf.stats), _lib.ptr(buf.scratch),
-        _lib.ptr(buf.lookback), obs_ptr, obs_stride, int(pre_phases), int(phases),
-        C.byref(xchg.struct) if xchg is not None else None, _lib.current_stream(dev)))
+    if rng is not None:
+        variates, rounds = [], int(n_rounds if n_rounds is not None else 16)
+    else:
+        _check_variates("mdp_step", n, spawn_perm, yaw_u, heading_u, theta_u)
+        variates, rounds = [spawn_perm, yaw_u, heading_u, theta_u], int(theta_u.shape[1])
+    torch.ops.rover_b200.mdp_step(
+        new_actions, force_matrix_w, root_pos_w, root_quat_w, params_desc(params), buf.state_list(), buf.out_list(),
+        tables.desc, variates, rng.state if rng is not None else None, rounds, buf.spawn_index, buf.stats, buf.scratch,
+        buf.lookback, buf.log if log else None, obs, int(pre_phases), int(phases),
+        xchg.desc if xchg is not None else None)

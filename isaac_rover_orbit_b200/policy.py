@@ -8,11 +8,9 @@ log-prob).  The forward pass is inference-only (no autograd): bf16 operands, fp3
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 
-from . import _lib
+from . import _lib, torch_ops
 
 WEIGHT_KEYS = ("dense_encoder.encoder_layers.0", "dense_encoder.encoder_layers.2", "mlp.0", "mlp.2", "mlp.4", "mlp.6")
 OBS_COLS = 965
@@ -57,7 +55,7 @@ class _RoverNetwork:
             self._params[key + ".bias"] = torch.zeros(o, device=self.device)
         self.log_std_parameter = torch.zeros(2, device=self.device)
         self._clip_log_std, self._log_std_min, self._log_std_max = True, -20.0, 2.0  # models.py:65-67
-        n_bytes = int(_lib.load().rover_policy_pack(None, None, None))
+        n_bytes = torch_ops.policy_packed_bytes()
         self._packed = torch.zeros(n_bytes + 128, dtype=torch.uint8, device=self.device)
         off = (-self._packed.data_ptr()) % 128
         self._packed = self._packed[off: off + n_bytes]
@@ -82,17 +80,11 @@ class _RoverNetwork:
         self._dirty = True
 
     def _pack(self):
-        w = _lib.PolicyWeights()
-        for l, key in enumerate(WEIGHT_KEYS):
-            wt, bs = self._params[key + ".weight"], self._params[key + ".bias"]
-            w.w[l], w.b[l] = wt.data_ptr(), bs.data_ptr()
-            w.in_dim[l], w.out_dim[l] = wt.shape[1], wt.shape[0]
-        rc = _lib.load().rover_policy_pack(C.byref(w), C.c_void_p(self._packed.data_ptr()), _lib.current_stream(self.device))
-        if rc < 0:
-            _lib.check(1)
+        torch.ops.rover_b200.policy_pack([self._params[k + ".weight"] for k in WEIGHT_KEYS],
+                                         [self._params[k + ".bias"] for k in WEIGHT_KEYS], self._packed)
         self._dirty = False
 
-    def _forward(self, states: torch.Tensor, entry: str) -> torch.Tensor:
+    def _forward(self, states: torch.Tensor, value_head: bool) -> torch.Tensor:
         if not states.is_cuda or states.dtype != torch.float32 or states.dim() != 2 or states.shape[1] != OBS_COLS:
             raise RuntimeError("compute: states must be a CUDA fp32 [N,965] tensor")
         if states.stride(1) != 1 or states.stride(0) % 4 != 0 or states.data_ptr() % 16 != 0:
@@ -102,26 +94,16 @@ class _RoverNetwork:
             states = buf
         if self._dirty:
             self._pack()
-        n = states.shape[0]
-        out = torch.empty(n, self._OUT_DIM, dtype=torch.float32, device=states.device)
-        _lib.check(getattr(_lib.load(), entry)(
-            C.c_void_p(states.data_ptr()), int(states.stride(0)), n, C.c_void_p(self._packed.data_ptr()),
-            C.c_void_p(out.data_ptr()), _lib.current_stream(states.device)))
-        return out
+        return torch.ops.rover_b200.policy_forward(states, self._packed, value_head)
 
-    def _forward_bf16(self, states: torch.Tensor, entry: str) -> torch.Tensor:
+    def _forward_bf16(self, states: torch.Tensor, value_head: bool) -> torch.Tensor:
         """bf16 observations ``[N, 965]`` (``alloc_obs_bf16`` layout): the TMA tile is the MMA operand, no conversion."""
         if (not states.is_cuda or states.dtype != torch.bfloat16 or states.dim() != 2 or states.shape[1] != OBS_COLS
                 or states.stride(1) != 1 or states.stride(0) % 8 != 0 or states.data_ptr() % 16 != 0):
             raise RuntimeError("compute_bf16: states must be a CUDA bf16 [N,965] view from alloc_obs_bf16()")
         if self._dirty:
             self._pack()
-        n = states.shape[0]
-        out = torch.empty(n, self._OUT_DIM, dtype=torch.float32, device=states.device)
-        _lib.check(getattr(_lib.load(), entry)(
-            C.c_void_p(states.data_ptr()), int(states.stride(0)), n, C.c_void_p(self._packed.data_ptr()),
-            C.c_void_p(out.data_ptr()), _lib.current_stream(states.device)))
-        return out
+        return torch.ops.rover_b200.policy_forward(states, self._packed, value_head)
 
 
 class GaussianNeuralNetwork(_RoverNetwork):
@@ -133,11 +115,11 @@ class GaussianNeuralNetwork(_RoverNetwork):
         A bf16 observation (``alloc_obs_bf16`` layout) is routed to ``compute_bf16``."""
         if inputs["states"].dtype == torch.bfloat16:
             return self.compute_bf16(inputs, role)
-        return self._forward(inputs["states"], "rover_policy_forward"), self.log_std_parameter, {}
+        return self._forward(inputs["states"], False), self.log_std_parameter, {}
 
     def compute_bf16(self, inputs: dict, role: str = "actor"):
         """``compute`` on the bf16 observation mirror; identical means (the fp32 path rounds to the same bf16)."""
-        return self._forward_bf16(inputs["states"], "rover_policy_forward_bf16"), self.log_std_parameter, {}
+        return self._forward_bf16(inputs["states"], False), self.log_std_parameter, {}
 
     def act(self, inputs: dict, role: str = "actor", eps: torch.Tensor | None = None):
         """skrl 1.1.0 ``GaussianMixin.act``: returns ``(actions [N,2], log_prob [N,1], outputs)``.
@@ -146,11 +128,7 @@ class GaussianNeuralNetwork(_RoverNetwork):
         n = mean.shape[0]
         if eps is None:
             eps = torch.randn(n, 2, device=mean.device)
-        actions = torch.empty_like(mean)
-        log_prob = torch.empty(n, dtype=torch.float32, device=mean.device)
-        _lib.check(_lib.load().rover_gaussian_act(
-            C.c_void_p(mean.data_ptr()), C.c_void_p(log_std.data_ptr()), C.c_void_p(eps.contiguous().data_ptr()), n,
-            C.c_void_p(actions.data_ptr()), C.c_void_p(log_prob.data_ptr()), _lib.current_stream(mean.device)))
+        actions, log_prob = torch.ops.rover_b200.gaussian_act(mean, log_std, eps.contiguous())
         outputs["mean_actions"] = mean
         return actions, log_prob.unsqueeze(-1), outputs
 
@@ -166,10 +144,10 @@ class DeterministicNeuralNetwork(_RoverNetwork):
     def compute(self, inputs: dict, role: str = "actor"):
         if inputs["states"].dtype == torch.bfloat16:
             return self.compute_bf16(inputs, role)
-        return self._forward(inputs["states"], "rover_value_forward"), {}
+        return self._forward(inputs["states"], True), {}
 
     def compute_bf16(self, inputs: dict, role: str = "actor"):
-        return self._forward_bf16(inputs["states"], "rover_value_forward_bf16"), {}
+        return self._forward_bf16(inputs["states"], True), {}
 
     def act(self, inputs: dict, role: str = "actor"):
         value, outputs = self.compute(inputs, role)

@@ -158,20 +158,14 @@ def mesh_to_heightmap(vertices: np.ndarray, faces: np.ndarray, resolution: float
 
 def _mesh_to_heightmap_cuda(v: np.ndarray, f: np.ndarray, min_x, min_y, csx, csy, shape, dev) -> torch.Tensor:
     """The rasterisation of ``mesh_to_heightmap`` on the GPU (``rover_mesh_to_heightmap``); returns the device tensor."""
-    import ctypes as C
+    from . import torch_ops  # noqa: F401  (registers torch.ops.rover_b200)
 
-    from . import _lib
-
-    lib = _lib.load()
     with torch.cuda.device(dev):
         tv = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(dev)
         tf = torch.from_numpy(np.ascontiguousarray(f, dtype=np.int32)).to(dev)
         hm = torch.full(shape, -99.0, dtype=torch.float32, device=dev)
         bad = torch.zeros(1, dtype=torch.int32, device=dev)
-        _lib.check(lib.rover_mesh_to_heightmap(C.c_void_p(tv.data_ptr()), C.c_void_p(tf.data_ptr()), tf.shape[0],
-                                               float(min_x), float(min_y), float(csx), float(csy), shape[0], shape[1],
-                                               C.c_void_p(hm.data_ptr()), C.c_void_p(bad.data_ptr()),
-                                               _lib.current_stream(dev)))
+        torch.ops.rover_b200.mesh_to_heightmap(tv, tf, float(min_x), float(min_y), float(csx), float(csy), hm, bad)
         if int(bad.item()):
             raise IndexError("face outside the heightmap beyond the wrap range (the reference raises here too)")
     return hm
@@ -182,17 +176,11 @@ def steep_mask(heightmap: np.ndarray, threshold: float = GRADIENT_THRESHOLD, dev
     On a CUDA device the stencil runs in ``rover_steep_mask`` (csrc/terrain_build.cu)."""
     dev = torch.device(device)
     if dev.type == "cuda":
-        import ctypes as C
+        from . import torch_ops  # noqa: F401
 
-        from . import _lib
-
-        lib = _lib.load()
         with torch.cuda.device(dev):
             hm = torch.from_numpy(np.ascontiguousarray(heightmap, dtype=np.float32)).to(dev)
-            out = torch.empty(hm.shape, dtype=torch.uint8, device=dev)
-            _lib.check(lib.rover_steep_mask(C.c_void_p(hm.data_ptr()), hm.shape[0], hm.shape[1], float(threshold),
-                                            C.c_void_p(out.data_ptr()), _lib.current_stream(dev)))
-            return out.cpu().numpy().astype(bool)
+            return torch.ops.rover_b200.steep_mask(hm, float(threshold)).cpu().numpy().astype(bool)
     from scipy.signal import convolve2d
 
     kx = np.array([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]])

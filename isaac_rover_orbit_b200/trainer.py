@@ -77,24 +77,20 @@ class RolloutMemory:
             self.filled = True
 
 
-class RolloutAgent:
-    """The part of the reference's skrl agent that sits on the hot path: ``act`` = ``GaussianMixin.act`` of the policy
-    (sampling + log-prob, SURVEY.md A.4) and ``record_transition`` = the ``RandomMemory`` rollout write.  The
-    hooks the trainer calls around them exist and do what skrl's base ``Agent`` does (tracking), nothing more."""
+class BaseAgent:
+    """What skrl 1.1.0's base ``Agent`` (agents/torch/base.py) does in the hooks the trainer calls: tracking only.
+    ``record_transition`` keeps per-env running returns / lengths and folds finished episodes into device-side totals
+    (skrl reads them back with ``.item()`` at its write interval; ``finished_episode_stats`` does that on demand --
+    nothing here synchronises per step).  The evaluation loop records through THIS method, bypassing the subclass
+    (``super(type(agent), agent).record_transition``, skrl ``Trainer.single_agent_eval``)."""
 
-    def __init__(self, policy, memory: RolloutMemory | None = None, observation_size: int = 965, action_size: int = 2):
-        self.policy = policy
-        self.memory = memory
+    def __init__(self):
         self.training = False
         self.tracking_data: dict[str, list] = {}
-        self._log_prob = None
         self._initialised = 0
-        if memory is not None:
-            memory.create_tensor("states", observation_size)
-            memory.create_tensor("actions", action_size)
-            memory.create_tensor("rewards", 1)
-            memory.create_tensor("terminated", 1, dtype=torch.bool)
-            memory.create_tensor("log_prob", 1)
+        self._cum_rewards = None
+        self._cum_steps = None
+        self._finished = None  # [episodes, return sum, length sum]
 
     def init(self, trainer_cfg=None) -> None:
         self._initialised += 1
@@ -111,6 +107,45 @@ class RolloutAgent:
     def track_data(self, tag: str, value: float) -> None:
         self.tracking_data.setdefault(tag, []).append(value)
 
+    def record_transition(self, states, actions, rewards, next_states, terminated, truncated, infos, timestep,
+                          timesteps) -> None:
+        r = rewards.reshape(-1).float()
+        if self._cum_rewards is None:
+            self._cum_rewards = torch.zeros_like(r)
+            self._cum_steps = torch.zeros_like(r)
+            self._finished = torch.zeros(3, device=r.device)
+        self._cum_rewards += r
+        self._cum_steps += 1
+        done = (terminated.reshape(-1) | truncated.reshape(-1)).float()
+        self._finished += torch.stack([done.sum(), (self._cum_rewards * done).sum(), (self._cum_steps * done).sum()])
+        self._cum_rewards *= 1.0 - done
+        self._cum_steps *= 1.0 - done
+
+    def finished_episode_stats(self) -> dict:
+        """Mean return / length of the episodes that finished so far (synchronises)."""
+        if self._finished is None:
+            return {"episodes": 0, "mean_return": 0.0, "mean_length": 0.0}
+        k, ret, length = (float(v) for v in self._finished.cpu())
+        return {"episodes": int(k), "mean_return": ret / max(k, 1.0), "mean_length": length / max(k, 1.0)}
+
+
+class RolloutAgent(BaseAgent):
+    """The part of the reference's skrl agent that sits on the hot path: ``act`` = ``GaussianMixin.act`` of the policy
+    (sampling + log-prob, SURVEY.md A.4) and ``record_transition`` = the ``RandomMemory`` rollout write.  The
+    hooks the trainer calls around them exist and do what skrl's base ``Agent`` does (tracking), nothing more."""
+
+    def __init__(self, policy, memory: RolloutMemory | None = None, observation_size: int = 965, action_size: int = 2):
+        super().__init__()
+        self.policy = policy
+        self.memory = memory
+        self._log_prob = None
+        if memory is not None:
+            memory.create_tensor("states", observation_size)
+            memory.create_tensor("actions", action_size)
+            memory.create_tensor("rewards", 1)
+            memory.create_tensor("terminated", 1, dtype=torch.bool)
+            memory.create_tensor("log_prob", 1)
+
     def act(self, states: torch.Tensor, timestep: int, timesteps: int):
         actions, log_prob, outputs = self.policy.act({"states": states}, role="policy")
         self._log_prob = log_prob
@@ -118,6 +153,7 @@ class RolloutAgent:
 
     def record_transition(self, states, actions, rewards, next_states, terminated, truncated, infos, timestep,
                           timesteps) -> None:
+        super().record_transition(states, actions, rewards, next_states, terminated, truncated, infos, timestep, timesteps)
         if self.memory is not None:
             self.memory.add_samples(states=states, actions=actions, rewards=rewards, terminated=terminated,
                                     log_prob=self._log_prob)
@@ -205,7 +241,7 @@ class SkrlSequentialLogTrainer:
                 actions = self.agents.act(states, timestep=timestep, timesteps=self.timesteps)[0]
             next_states, rewards, terminated, truncated, infos = self.env.step(actions)
             if not self.headless:
-                self.env.render()
+                self.env.render()  # skrl renders unless headless; RoverEnv.render is a no-op (no viewport without the simulator)
             with torch.no_grad():
                 # evaluation records through the base class of the agent (tracking only), as skrl does
                 super(type(self.agents), self.agents).record_transition(

@@ -56,6 +56,29 @@ def test_train_loop_records_the_rollout(cuda_device):
     assert any(k.startswith("EpisodeInfo / ") for k in agent.tracking_data)
 
 
+def test_eval_loop_runs_on_the_real_env_and_agent(cuda_device):
+    """``SkrlSequentialLogTrainer.eval()`` (the reference's eval.py path, skrl_utils.py:150-206) with the
+    shipped ``RoverEnv`` + ``RolloutAgent``: records through the base agent (tracking only, no rollout write) and calls
+    ``env.render()`` unless headless."""
+    n, steps = 96, 5
+    v, f = TR.make_synthetic_terrain(48.0, 0.2, seed=5)
+    tables = TR.build_terrain_tables(v, f, n)
+    env = RoverEnv(RoverEnvCfg(num_envs=n), tables, cuda_device, seed=2)
+    net = GaussianNeuralNetwork(device=cuda_device)
+    g2 = torch.Generator().manual_seed(4)
+    net.load_state_dict({k: torch.randn(t.shape, generator=g2) * (0.05 if t.dim() == 2 else 0.01)
+                         for k, t in net.state_dict().items()})
+    mem = RolloutMemory(memory_size=steps, num_envs=n, device=cuda_device)
+    agent = RolloutAgent(net, mem)
+    for headless in (False, True):
+        SkrlSequentialLogTrainer(env=env, agents=agent, cfg={"timesteps": steps, "headless": headless}).eval()
+    torch.cuda.synchronize()
+    assert mem.memory_index == 0 and not mem.filled, "evaluation must not write the rollout memory"
+    assert not agent.training
+    stats = agent.finished_episode_stats()
+    assert stats["episodes"] >= 0 and env.common_step_counter == 2 * steps
+
+
 def test_capture_steps_replays_the_enqueued_work(cuda_device):
     acc = torch.zeros(4, device=cuda_device)
     inc = [torch.full((4,), float(i + 1), device=cuda_device) for i in range(3)]
