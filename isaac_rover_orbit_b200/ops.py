@@ -357,6 +357,8 @@ def mdp_pre_step(buf: MdpBuffers, params: _lib.MdpParams, actions: torch.Tensor 
 
 
 def _check_variates(what, n, spawn_perm, yaw_u, heading_u, theta_u):
+    if spawn_perm is None or yaw_u is None or heading_u is None or theta_u is None:
+        raise RuntimeError(f"{what}: pass the variates (spawn_perm, yaw_u, heading_u, theta_u) or rng=ResetRng(...)")
     _lib.require_cuda(spawn_perm, yaw_u, heading_u, theta_u)
     _require_f32(what, yaw_u=yaw_u, heading_u=heading_u, theta_u=theta_u)
     if spawn_perm.dtype != torch.int64 or spawn_perm.numel() < n:

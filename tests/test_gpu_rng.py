@@ -42,7 +42,7 @@ def _fresh(n, dev, init, root):
     buf.episode_length_buf.copy_(init[2])
     buf.env_origins.copy_(root)
     buf.time_left.fill_(150.0)
-    buf.time_left[3] = 0.1  # the time-based resample draws from the env's variates as well
+    buf.time_left[min(3, n - 1)] = 0.1  # the time-based resample draws from the env's variates as well
     return buf
 
 
