@@ -6,8 +6,15 @@
 
 Headline metric (BASELINE.json): height-scan rays/s on cfg-2 -- 4096 envs x 961 rays per GPU on the synthetic
 200 m x 200 m / 2,000,000-triangle terrain.  A "step" is one height-scan pass over one batch of synthetic poses.
-The same run also measures the fused non-physics step (cfg-3 at N=1, cfg-5 = 8192 envs/GPU + the NCCL
-episode-statistics all-reduce under torchrun) and reports it under "extra".
+
+The driver keeps only the contract's keys of the JSON line, so everything else this run measures lives INSIDE them:
+  roofline.by_size          the scan at 16384 / 65536 envs (the 36 MB terrain term cannot carry the fraction there)
+  roofline.fused_step       cfg-3 (16384 envs, N=1) and cfg-5 (8192 envs/GPU at EVERY N, so 1 -> 8 is a ratio):
+                            pre_step + post_step (reset variates drawn in the kernel) + height scan, one CUDA graph
+  roofline.mdp_only / policy_forward / fused_scan_policy / closed_loop    cfg-4 and the loop with the policy in it
+  e2e.env_step              the reference-facing call, RoverEnv.step(), eager and graph-captured, beside the ops.* figure
+  e2e.episode_stats         (N > 1) the P2P-mailbox totals against an NCCL all-reduce
+  cpu_baseline.cfg1         cfg-1: the whole non-physics step at 256 envs on the host cores, and the same 256 envs here
 
 Timing: CUDA events on the launching stream around every timed step, L2 flushed (256 MiB write) between steps and
 excluded from the timed region, max over ranks.  One JSON line on stdout (rank 0).
@@ -15,6 +22,7 @@ excluded from the timed region, max over ranks.  One JSON line on stdout (rank 0
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import json
 import os
 import sys
@@ -29,44 +37,50 @@ sys.path.insert(0, ROOT)
 
 TERRAIN = dict(size_m=200.0, grid_res=0.2, seed=0)
 SCAN_ENVS_PER_GPU = 4096  # cfg-2
-STEP_ENVS_1GPU = 16384  # cfg-3
-STEP_ENVS_PER_GPU_MULTI = 8192  # cfg-5
+STEP_ENVS_CFG3 = 16384  # cfg-3
+STEP_ENVS_CFG5 = 8192  # cfg-5 (per GPU)
+CFG1_ENVS = 256  # cfg-1
+POLICY_ENVS = 65536  # cfg-4
 N_RAYS = 961
 TERRAIN_BYTES = 36.0e6  # compulsory mesh footprint (12.0 MB vertices + 24.0 MB indices)
 POSE_SETS = 8
+POLICY_FLOP = 319520  # SURVEY.md 8(d), per env
+
+
+def bench_config(warmup: int) -> dict:
+    """`config` of the JSON line -- the SAME dict in both arms (the driver compares them)."""
+    return {"workload": "cfg-2 height-scan raycast only: 4096 envs x 961 rays per GPU, synthetic 200 m x 200 m Mars-like "
+                        "terrain, 2,000,000 triangles",
+            "envs_per_gpu": SCAN_ENVS_PER_GPU, "rays_per_env": N_RAYS,
+            "l2": "flushed between timed steps (256 MiB write, outside the timed region)",
+            "pose_sets": POSE_SETS, "untimed_warmup_steps": max(warmup, 3)}
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
 def measured_peak():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-        except Exception:
-            pass
+    p = peaks()
+    if "hbm_gbs" in p:
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(kernel: str):
-    """DRAM bytes per launch from the committed ncu capture (profiles/ncu_summary.json), or None."""
-    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
-
-
-def recorded_metric(kernel: str, key: str):
-    """One number of the committed ncu capture of `kernel` (profiles/ncu_summary.json), or None."""
+def ncu_record(kernel: str) -> dict:
+    """The committed ncu capture of `kernel` for this round (profiles/ncu_summary.json; the command that produced it and
+    the raw csv are named inside), or {}."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(kernel, {}).get(key)
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(kernel, {})
     except Exception:
-        return None
+        return {}
 
 
 class ClockSampler:
@@ -128,10 +142,7 @@ class ClockSampler:
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
 def build_world(need_tables_for: int | None, build_device, device):
@@ -168,6 +179,17 @@ def time_steps(fn, steps, warmup, flush, stream):
     return np.array([a.elapsed_time(b) for a, b in ev])
 
 
+def guarded(name, out: dict, fn):
+    """The headline number must survive a failure of the additional measurements."""
+    try:
+        out[name] = fn()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+
+        log(f"[{name}] failed:\n{traceback.format_exc()}")
+        out[name] = {"error": f"{type(e).__name__}: {e}"}
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
@@ -175,25 +197,33 @@ def run_ours(args):
                            "use --impl reference for the CPU baseline")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
+    import torch.distributed as dist
 
+    if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from isaac_rover_orbit_b200 import ops, synthetic
     from isaac_rover_orbit_b200.config import RoverEnvCfg
-    from isaac_rover_orbit_b200.dist import EpisodeStats
+    from isaac_rover_orbit_b200.trainer import capture_steps
+
+    def max_over_ranks(x):
+        t = torch.tensor(list(x), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
 
     n_scan = SCAN_ENVS_PER_GPU
-    n_step = STEP_ENVS_1GPU if world == 1 else STEP_ENVS_PER_GPU_MULTI
-    v, f, grid, tables = build_world(n_step, "cpu" if args.init_on_cpu else dev, dev)
+    v, f, grid, tables = build_world(STEP_ENVS_CFG3, "cpu" if args.init_on_cpu else dev, dev)
     vt = torch.from_numpy(v)
-    cfg = RoverEnvCfg(num_envs=n_step)
     rays = ops.RayPattern.grid(dev)
     stream = torch.cuda.current_stream(dev)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    peak, peak_src = measured_peak()
 
     def flush():
         flush_buf.fill_(1)
+
+    def graphed(fn, variants=4):
+        return fn if args.no_graph else capture_steps(fn, n_variants=variants, warmup=1)
 
     # ------------------------------------------------------------------ headline: height scan (cfg-2 per GPU)
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -210,25 +240,55 @@ def run_ours(args):
     torch.cuda.synchronize()
     with ClockSampler(local) as clocks:
         ms = time_steps(scan_step, args.steps, max(args.warmup, 3), flush, stream)  # never fewer than 3 untimed steps
-        # keep the GPU busy long enough for >= a few clock samples
-        t_end = time.time() + 0.3
+        t_end = time.time() + 0.3  # keep the GPU busy long enough for a few clock samples
         while time.time() < t_end:
             scan_step(0)
         torch.cuda.synchronize()
-    total_ms = torch.tensor([ms.sum()], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    rays_total = n_scan * N_RAYS * args.steps * world
-    value = rays_total / (total_ms * 1e-3)
+    total_ms = max_over_ranks([ms.sum()])[0]
+    value = n_scan * N_RAYS * args.steps * world / (total_ms * 1e-3)
     t_launch = float(ms.mean()) * 1e-3
     alg_bytes = 4.0 * n_scan * N_RAYS + 28.0 * n_scan + TERRAIN_BYTES
-    peak, peak_src = measured_peak()
     achieved = alg_bytes / t_launch / 1e9
-    kname = {0: "height_scan_direct_kernel", 1: "height_scan_staged_kernel", 2: "height_scan_cells_kernel",
-             3: "height_scan_cells_tma_kernel", 4: "height_scan_pipelined_kernel",
-             5: "height_scan_paired_kernel"}[args.variant]
+    kname = {0: "height_scan_direct_kernel", 2: "height_scan_cells_kernel", 4: "height_scan_pipelined_kernel",
+             5: "height_scan_paired_kernel"}.get(args.variant, f"variant {args.variant}")
+    rec = ncu_record(kname)
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "traffic": rec.get("dram_bytes_per_launch"),
+                "traffic_source": rec.get("source"), "algorithmic_bytes_per_launch": alg_bytes, "launch_us": t_launch * 1e6,
+                "ncu_kernel_us": rec.get("duration_us")}
+
+    # the same launch over 300 more steps (the driver passes --steps 20: quote nothing from fewer than 100 launches)
+    def steady():
+        ms3 = time_steps(scan_step, 300, 3, flush, stream)
+        t = max_over_ranks([ms3.mean()])[0] * 1e-3
+        return {"launches": 300, "launch_us": t * 1e6, "frac": alg_bytes / t / 1e9 / peak,
+                "rays_per_s": n_scan * N_RAYS * world / t, "p10_us": float(np.percentile(ms3, 10)) * 1e3,
+                "p90_us": float(np.percentile(ms3, 90)) * 1e3}
+
+    guarded("steady_300", roofline, steady)
+
+    # the scan at larger batches: the terrain term (36 MB) is amortised, the per-ray work is not
+    def by_size():
+        rows = []
+        for n_big in (16384, 65536):
+            g2 = torch.Generator().manual_seed(77 + rank)
+            sets = [tuple(t.to(dev) for t in synthetic.make_poses(n_big, g2, vt, TERRAIN["size_m"], TERRAIN["grid_res"]))
+                    for _ in range(2)]
+            ob = torch.empty(n_big, N_RAYS, device=dev)
+            msb = time_steps(lambda i: ops.height_scan(*sets[i % 2], rays, grid, out=ob, variant=args.variant), 100, 3, flush,
+                             stream)
+            t = max_over_ranks([msb.mean()])[0] * 1e-3
+            b = 4.0 * n_big * N_RAYS + 28.0 * n_big + TERRAIN_BYTES
+            r = ncu_record(f"{kname}@{n_big}")
+            rows.append({"envs": n_big, "launch_us": t * 1e6, "rays_per_s": n_big * N_RAYS * world / t,
+                         "algorithmic_bytes": b, "frac": b / t / 1e9 / peak, "traffic": r.get("dram_bytes_per_launch")})
+            del ob, sets
+        return rows
+
+    if world == 1:
+        guarded("by_size", roofline, by_size)
 
     # ------------------------------------------------------------------ e2e: host buffers through the public API
     pin = [(p.pin_memory(), q.pin_memory()) for p, q in poses]
@@ -252,15 +312,13 @@ def run_ours(args):
     for i in range(e2e_steps):
         e2e_step(i)
         torch.cuda.synchronize()  # the caller reads the heights of step i before issuing step i+1
-    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = n_scan * N_RAYS * e2e_steps * world / float(e2e_t.item())
+    e2e_value = n_scan * N_RAYS * e2e_steps * world / max_over_ranks([time.perf_counter() - t0])[0]
+    e2e = {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_scan * 28, "d2h_bytes_per_step": n_scan * N_RAYS * 4,
+           "steps": e2e_steps, "how": "pinned host poses -> H2D -> rover_height_scan -> D2H heights, synchronised per step"}
 
-    # the same calls double-buffered on two streams: step i+1's H2D and kernel overlap step i's D2H; the host waits for
-    # step i-2 before it reuses that step's buffers (reported next to the synchronous figure, which stays the headline)
-    e2e_pipe = None
-    try:
+    def pipelined():
+        # the same calls double-buffered on two streams: step i+1's H2D and kernel overlap step i's D2H; the host waits
+        # for step i-2 before it reuses that step's buffers
         streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
         dbuf = [(torch.empty(n_scan, 3, device=dev), torch.empty(n_scan, 4, device=dev),
                  torch.empty(n_scan, N_RAYS, device=dev), torch.empty(n_scan, N_RAYS).pin_memory()) for _ in range(2)]
@@ -289,244 +347,292 @@ def run_ours(args):
         for i in range(e2e_steps):
             piped(i)
         torch.cuda.synchronize()
-        tp_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tp_, op=dist.ReduceOp.MAX)
+        dt = max_over_ranks([time.perf_counter() - t0])[0]
         ok = bool(torch.equal(dbuf[(e2e_steps - 1) & 1][3], dbuf[(e2e_steps - 1) & 1][2].cpu()))
-        e2e_pipe = {"value": n_scan * N_RAYS * e2e_steps * world / float(tp_.item()), "unit": "rays/s",
-                    "how": "two streams, double-buffered pinned host buffers; every step still moves its poses in and "
-                           "its heights out", "host_copy_equals_device": ok}
-    except Exception as e:  # the synchronous figure above is the contract; this one is informative
-        e2e_pipe = {"error": f"{type(e).__name__}: {e}"}
+        return {"value": n_scan * N_RAYS * e2e_steps * world / dt, "unit": "rays/s",
+                "how": "two streams, double-buffered pinned host buffers; every step still moves its poses in and its "
+                       "heights out", "host_copy_equals_device": ok}
 
-    # ------------------------------------------------------------------ extra: fused non-physics step
-    extra = {}
-    try:
-        buf = ops.MdpBuffers.allocate(n_step, dev)
-        params = ops.mdp_params(cfg)
-        th = ops.TerrainTablesHandle(tables.heightmap, tables.safe_mask, tables.offset_xy, tables.spawn_table,
-                                     tables.resolution, dev)
-        gen2 = torch.Generator().manual_seed(99 + rank)
-        sets = [synthetic.make_step(n_step, gen2, vt, TERRAIN["size_m"], TERRAIN["grid_res"],
-                                    cfg.num_contact_bodies, cfg.target_rounds).to(dev) for _ in range(4)]
-        pc, hc, ep = synthetic.init_commands(n_step, gen2, sets[0].root_pos_w.cpu())
-        buf.pos_cmd_w.copy_(pc)
-        buf.heading_cmd_w.copy_(hc)
-        buf.episode_length_buf.copy_(ep)
-        buf.env_origins.copy_(sets[0].root_pos_w)
-        buf.time_left.fill_(150.0)
-        obs = torch.zeros(n_step, 4 + N_RAYS, device=dev)
-        stats = EpisodeStats(buf, world)
-        # several GPUs: the episode statistics travel as peer stores issued by the post-step kernel itself
-        # (dist.P2PStats); ROVER_STATS=nccl keeps the all-reduce per step (EpisodeStats)
-        p2p = None
-        if world > 1 and os.environ.get("ROVER_STATS", "p2p") != "nccl":
-            from isaac_rover_orbit_b200.dist import P2PStats
+    guarded("pipelined", e2e, pipelined)
 
-            p2p = P2PStats(dev, rank, world)
+    # ------------------------------------------------------------------ fused non-physics step (cfg-3 / cfg-5 / cfg-1)
+    from isaac_rover_orbit_b200.dist import P2PStats
 
-        # synthetic "physics": every step the rover sits at its env origin + a bounded offset, so that the
-        # far/success terminations stay rare and resets come from contacts (5 %) and time-outs
-        drift = [(torch.rand(n_step, 3, generator=gen2) * torch.tensor([4.0, 4.0, 0.0]) - torch.tensor([2.0, 2.0, 0.0])
-                  ).to(dev) for _ in range(4)]
-        buf.pos_cmd_w.copy_(sets[0].root_pos_w + torch.tensor([9.0, 0.0, 0.0], device=dev))
+    cfg3 = RoverEnvCfg(num_envs=STEP_ENVS_CFG3)
+    params = ops.mdp_params(cfg3)
+    p2p = None
+    if world > 1 and os.environ.get("ROVER_STATS", "p2p") != "nccl":
+        p2p = P2PStats(dev, rank, world)
+    ksteps = max(min(args.steps, 200), 100)
 
-        def mdp(buf, params, th, actions, s, obs_, xchg=None):
-            """pre-step + post-step: two launches (the faster arrangement, profiles/r01_mdp_v1.md); --single-launch-mdp
-            runs both in one launch (rover_mdp_step, reset rank by decoupled look-back)"""
-            if not args.single_launch_mdp:
-                ops.mdp_pre_step(buf, params, actions, s.force_matrix_w)
-                ops.mdp_post_step(buf, params, th, s.root_pos_w, s.root_quat_w, s.spawn_perm, s.yaw_u, s.heading_u,
-                                  s.theta_u, obs_, xchg=xchg)
+    class StepWorld:
+        """Synthetic state of `n` envs + the kernels' buffers; `step(i)` = one fused non-physics step."""
+
+        def __init__(self, n, seed, xchg=None):
+            self.n, self.xchg = n, xchg
+            g = torch.Generator().manual_seed(seed)
+            self.sets = [synthetic.make_step(n, g, vt, TERRAIN["size_m"], TERRAIN["grid_res"], cfg3.num_contact_bodies,
+                                             cfg3.target_rounds).to(dev) for _ in range(4)]
+            self.buf = ops.MdpBuffers.allocate(n, dev)
+            # spawn rows of this rank: a disjoint slice of the table (the without-replacement draw stays shard-local)
+            self.th = ops.TerrainTablesHandle(tables.heightmap, tables.safe_mask, tables.offset_xy,
+                                              tables.spawn_table[: 2 * n], tables.resolution, dev)
+            pc, hc, ep = synthetic.init_commands(n, g, self.sets[0].root_pos_w.cpu())
+            self.buf.heading_cmd_w.copy_(hc)
+            self.buf.episode_length_buf.copy_(ep)
+            self.buf.env_origins.copy_(self.sets[0].root_pos_w)
+            self.buf.time_left.fill_(150.0)
+            self.buf.pos_cmd_w.copy_(self.sets[0].root_pos_w + torch.tensor([9.0, 0.0, 0.0], device=dev))
+            self.obs = torch.zeros(n, 968, device=dev)[:, :965]
+            self.rng = ops.ResetRng(1000 + seed, dev)
+            # synthetic "physics": every step the rover sits at its env origin + a bounded offset, so that the far/success
+            # terminations stay rare and resets come from contacts (5 %) and time-outs (SURVEY.md 8d)
+            self.drift = [(torch.rand(n, 3, generator=g) * torch.tensor([4.0, 4.0, 0.0]) - torch.tensor([2.0, 2.0, 0.0])
+                           ).to(dev) for _ in range(4)]
+
+        def physics(self, i):
+            torch.add(self.buf.env_origins, self.drift[i % 4], out=self.sets[i % 4].root_pos_w)  # stand-in for PhysX
+
+        def mdp(self, i, actions=None):
+            s = self.sets[i % 4]
+            a = s.actions if actions is None else actions
+            if args.single_launch_mdp:
+                ops.mdp_step(self.buf, params, self.th, a, s.force_matrix_w, s.root_pos_w, s.root_quat_w, obs=self.obs,
+                             rng=self.rng, xchg=self.xchg)
             else:
-                ops.mdp_step(buf, params, th, actions, s.force_matrix_w, s.root_pos_w, s.root_quat_w, s.spawn_perm,
-                             s.yaw_u, s.heading_u, s.theta_u, obs_, xchg=xchg)
+                ops.mdp_pre_step(self.buf, params, a, s.force_matrix_w)
+                ops.mdp_post_step(self.buf, params, self.th, s.root_pos_w, s.root_quat_w, obs=self.obs, rng=self.rng,
+                                  xchg=self.xchg)
 
-        def full_step(i):
-            s = sets[i % 4]
-            torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)  # stand-in for PhysX, not one of our kernels
-            mdp(buf, params, th, s.actions, s, obs)
-            ops.height_scan(s.root_pos_w, s.root_quat_w, rays, grid, out=obs[:, 4:], variant=args.variant)
-            if world > 1:
-                stats.all_reduce_async()
+        def scan(self, i):
+            s = self.sets[i % 4]
+            ops.height_scan(s.root_pos_w, s.root_quat_w, rays, grid, out=self.obs[:, 4:], variant=args.variant)
 
-        def mdp_only(i):
-            s = sets[i % 4]
-            torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)
-            mdp(buf, params, th, s.actions, s, obs)
+        def full(self, i):
+            self.physics(i)
+            self.mdp(i)
+            self.scan(i)
 
-        ksteps = max(min(args.steps, 200), 3)
-        # the step is launch-bound on the host side (3 ctypes launches + 1 torch op ~ 40 us of Python per step):
-        # capture each input set's step once in a CUDA graph and replay it (one cudaGraphLaunch per step)
-        def graphed(fn):
-            from isaac_rover_orbit_b200.trainer import capture_steps
+        def mdp_only(self, i):
+            self.physics(i)
+            self.mdp(i)
 
-            return fn if args.no_graph else capture_steps(fn, n_variants=4, warmup=1)
+    def fused_numbers(n, t_ms, launches):
+        t = t_ms * 1e-3
+        b = n * (414.0 + 4.0 * N_RAYS) + TERRAIN_BYTES
+        return {"envs_per_gpu": n, "env_steps_per_s": n * world / t, "us_per_step": t * 1e6, "algorithmic_bytes": b,
+                "frac": b / t / 1e9 / peak, "gpu_launches_per_step": launches, "cuda_graph": not args.no_graph,
+                "timed_steps": ksteps}
 
-        step_body = full_step
-        if world > 1:
-            def step_body(i):  # noqa: F811  (kernels only; an NCCL all-reduce, if used, is issued after the replay)
-                s = sets[i % 4]
-                torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)
-                mdp(buf, params, th, s.actions, s, obs, xchg=p2p)
-                ops.height_scan(s.root_pos_w, s.root_quat_w, rays, grid, out=obs[:, 4:], variant=args.variant)
-        g_full = graphed(step_body)
-        g_mdp = graphed(mdp_only)
+    fused = {}
+    worlds = {}
 
-        def run_full(i):
+    def run_fused(n, tag, use_xchg):
+        w = worlds[tag] = StepWorld(n, 99 + rank + 17 * n % 1000, p2p if use_xchg else None)
+        g_full = graphed(w.full)
+        nccl_stats = None
+        if world > 1 and use_xchg is False and tag == "cfg5":
+            from isaac_rover_orbit_b200.dist import EpisodeStats
+
+            nccl_stats = EpisodeStats(w.buf, world)
+
+        def run(i):
             g_full(i)
-            if world > 1 and p2p is None:
-                stats.all_reduce_async()
+            if nccl_stats is not None:
+                nccl_stats.all_reduce_async()
 
-        ms_full = time_steps(run_full, ksteps, 3, flush, stream)
-        ms_mdp = time_steps(g_mdp, ksteps, 3, flush, stream)
-        buf.stats.zero_()
-        mdp_only(0)
+        ms_f = time_steps(run, ksteps, 3, flush, stream)
+        t_full = max_over_ranks([ms_f.mean()])[0]
+        w.buf.stats.zero_()
+        run(0)
         torch.cuda.synchronize()
-        resets_per_step = float(buf.stats[13].item())
-        tf = torch.tensor([ms_full.sum(), ms_mdp.sum()], dtype=torch.float64, device=dev)
-        stats_check = None
+        d = fused_numbers(n, t_full, 2 if args.single_launch_mdp else 3)
+        d["resets_in_one_step"] = float(w.buf.stats[13].item())
+        d["variates"] = "drawn in the post-step kernel (Philox4x32-10 keyed on seed, step, env)"
         if world > 1:
-            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-            if p2p is not None:
-                # one-off check outside the timed region: the mailbox totals equal an NCCL all-reduce of the ranks' totals
-                dist.barrier()
-                torch.cuda.synchronize()
-                mine = p2p._cumulative.clone()
-                dist.all_reduce(mine, op=dist.ReduceOp.SUM)
-                got = p2p.read().clone()
-                torch.cuda.synchronize()
-                stats_check = {"exchange": "p2p mailbox stores from mdp_post_step (no collective launch on the step path)",
-                               "equals_nccl_all_reduce": bool(torch.equal(got, mine)),
-                               "global_resets": float(got[13].item())}
-            else:
-                stats_check = {"exchange": "nccl all_reduce per step"}
-        full_bytes = n_step * (414.0 + 4.0 * N_RAYS) + TERRAIN_BYTES
-        extra = {
-            "fused_step": {
-                "workload": f"cfg-{'3' if world == 1 else '5'}: {n_step} envs/GPU, pre_step + post_step + height scan"
-                            + ("" if world == 1 else " + episode statistics through P2P mailboxes (peer stores from the "
-                               "post-step kernel)" if p2p is not None else " + NCCL episode-stat all-reduce"),
-                "env_steps_per_s": n_step * world * ksteps / (float(tf[0]) * 1e-3),
-                "ms_per_step": float(tf[0]) / ksteps,
-                "gpu_launches_per_step": 2 if args.single_launch_mdp else 3, "cuda_graph": not args.no_graph,
-                "roofline_frac_hbm": full_bytes / (float(tf[0]) / ksteps * 1e-3) / 1e9 / peak,
-                "resets_in_one_step": resets_per_step,
-                "episode_stats": stats_check,
-            },
-            "mdp_only": {
-                "env_steps_per_s": n_step * world * ksteps / (float(tf[1]) * 1e-3),
-                "ms_per_step": float(tf[1]) / ksteps,
-                "roofline_frac_hbm": n_step * 414.0 / (float(tf[1]) / ksteps * 1e-3) / 1e9 / peak,
-                "note": "414 B/env: launch-latency bound at this N (SURVEY.md 8d); pre + post launch (one launch with --single-launch-mdp, measured 1.4 us slower)",
-            },
-        }
-    except Exception as e:  # the headline number must survive a failure of the extra measurements
-        extra = {"error": f"{type(e).__name__}: {e}"}
+            d["episode_statistics"] = ("P2P mailboxes: peer stores from the post-step kernel, no collective launch" if use_xchg
+                                       else "NCCL all_reduce per step")
+        return d
 
-    # ------------------------------------------------------------------ extra: policy forward (cfg-4)
-    try:
-        from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork, alloc_obs, alloc_obs_bf16
+    if world == 1:
+        guarded("cfg3", fused, lambda: run_fused(STEP_ENVS_CFG3, "cfg3", False))
+    guarded("cfg5", fused, lambda: run_fused(STEP_ENVS_CFG5, "cfg5", p2p is not None))
+    fused["note"] = ("cfg5 = 8192 envs/GPU at every N (weak scaling: the ratio of its env_steps_per_s across N is the "
+                     "scaling of the fused step); cfg3 = 16384 envs on one GPU")
+    roofline["fused_step"] = fused
 
-        n_pol = 65536
-        net = GaussianNeuralNetwork(device=dev)
-        gen3 = torch.Generator().manual_seed(7 + rank)
-        net.load_state_dict({k: (torch.randn(v.shape, generator=gen3) * (0.05 if v.dim() == 2 else 0.01))
-                             for k, v in net.state_dict().items()})
+    def mdp_only():
+        tag = "cfg3" if "cfg3" in worlds else "cfg5"
+        w = worlds[tag]
+        t = max_over_ranks([time_steps(graphed(w.mdp_only), ksteps, 3, flush, stream).mean()])[0] * 1e-3
+        return {"envs_per_gpu": w.n, "env_steps_per_s": w.n * world / t, "us_per_step": t * 1e6,
+                "frac": w.n * 414.0 / t / 1e9 / peak,
+                "note": "414 B/env: launch-latency bound at this N (SURVEY.md 8d); pre + post launch"}
+
+    guarded("mdp_only", roofline, mdp_only)
+
+    stats_check = None
+    if world > 1 and p2p is not None:
+        # outside the timed regions: the mailbox totals equal an NCCL all-reduce of the ranks' running totals
+        dist.barrier()
+        torch.cuda.synchronize()
+        mine = p2p._cumulative.clone()
+        dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+        got = p2p.read().clone()
+        torch.cuda.synchronize()
+        stats_check = {"exchange": "p2p mailbox stores from mdp_post_step (no collective launch on the step path)",
+                       "equals_nccl_all_reduce": bool(torch.equal(got, mine)), "global_resets": float(got[13].item())}
+    elif world > 1:
+        stats_check = {"exchange": "nccl all_reduce per step"}
+    e2e["episode_stats"] = stats_check
+
+    # ------------------------------------------------------------------ policy forward (cfg-4) and the closed loop
+    from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork, alloc_obs, alloc_obs_bf16
+
+    net = GaussianNeuralNetwork(device=dev)
+    gen3 = torch.Generator().manual_seed(7 + rank)
+    net.load_state_dict({k: (torch.randn(t.shape, generator=gen3) * (0.05 if t.dim() == 2 else 0.01))
+                         for k, t in net.state_dict().items()})
+    tf_peak = float(peaks().get("bf16_tflops", 1590.0))
+
+    def policy_forward():
+        n_pol = POLICY_ENVS
         pol_obs = alloc_obs(n_pol, dev)
         pol_obs.copy_(torch.randn(n_pol, 965, device=dev) * 0.3)
-        ksteps = max(min(args.steps, 100), 3)
-        ms_pol = time_steps(lambda i: net.compute({"states": pol_obs}), ksteps, 3, flush, stream)
-        tp = torch.tensor([ms_pol.sum()], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-        t_pol = float(tp[0]) / ksteps * 1e-3
-        # the same forward on the bf16 observation mirror (what the closed loop uses: written by the height scan)
+        k = 100
+        t_pol = max_over_ranks([time_steps(lambda i: net.compute({"states": pol_obs}), k, 3, flush, stream).mean()])[0] * 1e-3
         pol_obs_bf = alloc_obs_bf16(n_pol, dev)
         pol_obs_bf.copy_(pol_obs)
-        ms_bf = time_steps(lambda i: net.compute({"states": pol_obs_bf}), ksteps, 3, flush, stream)
-        tb = torch.tensor([ms_bf.sum()], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
-        t_bf = float(tb[0]) / ksteps * 1e-3
+        t_bf = max_over_ranks([time_steps(lambda i: net.compute({"states": pol_obs_bf}), k, 3, flush, stream).mean()])[0] * 1e-3
         same = bool(torch.equal(net.compute({"states": pol_obs})[0], net.compute({"states": pol_obs_bf})[0]))
-        bf16_pol = {"env_forwards_per_s": n_pol * world / t_bf, "us_per_launch": t_bf * 1e6,
-                    "bit_identical_to_fp32_path": same,
-                    "tensor_pipe_active_pct_ncu": recorded_metric("policy_forward_ws_kernel<bf16 observation>",
-                                                                  "tensor_pipe_active_pct"),
-                    "roofline_frac_hbm": n_pol * (964 * 2 + 8) / t_bf / 1e9 / measured_peak()[0]}
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        tf_peak = float(peaks.get("bf16_tflops", 1590.0))
-        extra["policy_forward"] = {
-            "workload": f"cfg-4: skrl Gaussian policy (961->80->60 (+4) ->256->160->128->2), {n_pol} envs/GPU, bf16 operands "
-                        "/ fp32 accumulate on tcgen05, random-init weights",
-            "env_forwards_per_s": n_pol * world / t_pol, "us_per_launch": t_pol * 1e6,
-            "tflops": n_pol * 319520 / t_pol / 1e12,
-            "roofline_frac_tensor": n_pol * 319520 / t_pol / 1e12 / tf_peak, "tensor_peak_tflops": tf_peak,
-            "roofline_frac_hbm": n_pol * (965 * 4 + 8) / t_pol / 1e9 / peak,
-            "tensor_pipe_active_pct_ncu": recorded_metric("policy_forward_ws_kernel", "tensor_pipe_active_pct"),
-            "kernel": "policy_forward_ws_kernel" if os.environ.get("ROVER_POLICY_KERNEL", "ws")[:2] != "v1"
-                      else "policy_forward_kernel",
-            "bf16_observation": bf16_pol,
-            "note": "standalone forward reads 3860 B/env of fp32 observations: 83 FLOP/B < ridge, HBM-bound (SURVEY 8d)",
-        }
-    except Exception as e:
-        extra["policy_forward"] = {"error": f"{type(e).__name__}: {e}"}
+        rec32, rec16 = ncu_record("policy_forward_ws_kernel"), ncu_record("policy_forward_ws_kernel<bf16 observation>")
+        return {"workload": f"cfg-4 (standalone): skrl Gaussian policy 961->80->60 (+4) ->256->160->128->2, {n_pol} envs/GPU, "
+                            "bf16 operands / fp32 accumulate on tcgen05, random-init weights",
+                "env_forwards_per_s": n_pol * world / t_pol, "us_per_launch": t_pol * 1e6,
+                "tflops": n_pol * POLICY_FLOP / t_pol / 1e12, "frac_tensor": n_pol * POLICY_FLOP / t_pol / 1e12 / tf_peak,
+                "tensor_peak_tflops": tf_peak, "frac_hbm": n_pol * (965 * 4 + 8) / t_pol / 1e9 / peak,
+                "tensor_pipe_active_pct_ncu": rec32.get("tensor_pipe_active_pct"),
+                "bf16_observation": {"env_forwards_per_s": n_pol * world / t_bf, "us_per_launch": t_bf * 1e6,
+                                     "bit_identical_to_fp32_path": same, "frac_hbm": n_pol * (964 * 2 + 8) / t_bf / 1e9 / peak,
+                                     "tflops": n_pol * POLICY_FLOP / t_bf / 1e12,
+                                     "tensor_pipe_active_pct_ncu": rec16.get("tensor_pipe_active_pct")},
+                "note": "standalone forward reads 3860 B/env of fp32 observations: 83 FLOP/B < ridge, HBM-bound (SURVEY 8d)"}
 
-    # ------------------------------------------------------------------ extra: closed non-physics loop with the policy
-    # obs -> policy -> action -> (stand-in physics) -> pre_step -> post_step -> height scan -> obs, one CUDA graph per step
-    try:
-        loop_obs = alloc_obs(n_step, dev)
-        act_buf = torch.zeros(n_step, 2, device=dev)
-        eps_sets = [torch.randn(n_step, 2, generator=gen3).to(dev) for _ in range(4)]
+    guarded("policy_forward", roofline, policy_forward)
 
-        def closed_step(i):
-            s = sets[i % 4]
-            torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)  # stand-in for PhysX
-            mdp(buf, params, th, act_buf, s, loop_obs)
-            ops.height_scan(s.root_pos_w, s.root_quat_w, rays, grid, out=loop_obs[:, 4:], variant=args.variant)
-            actions, _, _ = net.act({"states": loop_obs}, eps=eps_sets[i % 4])
+    def closed_loop():
+        # obs -> policy -> action -> (stand-in physics) -> pre_step -> post_step -> height scan -> obs, one graph per step
+        tag = "cfg3" if "cfg3" in worlds else "cfg5"
+        w = worlds[tag]
+        n = w.n
+        act_buf = torch.zeros(n, 2, device=dev)
+        eps_sets = [torch.randn(n, 2, generator=gen3).to(dev) for _ in range(4)]
+        loop_bf = alloc_obs_bf16(n, dev)
+
+        def step_fp32(i):
+            w.physics(i)
+            w.mdp(i, act_buf)
+            w.scan(i)
+            actions, _, _ = net.act({"states": w.obs}, eps=eps_sets[i % 4])
             act_buf.copy_(actions)
 
-        loop_obs_bf = alloc_obs_bf16(n_step, dev)
-
-        def closed_step_bf16(i):  # the scan also writes the bf16 observation; the policy reads only that
-            s = sets[i % 4]
-            torch.add(buf.env_origins, drift[i % 4], out=s.root_pos_w)
-            mdp(buf, params, th, act_buf, s, loop_obs)
-            ops.height_scan_obs(s.root_pos_w, s.root_quat_w, rays, grid, loop_obs, loop_obs_bf)
-            actions, _, _ = net.act({"states": loop_obs_bf}, eps=eps_sets[i % 4])
+        def step_bf16(i):  # the scan also writes the bf16 observation; the policy reads only that
+            s = w.sets[i % 4]
+            w.physics(i)
+            w.mdp(i, act_buf)
+            ops.height_scan_obs(s.root_pos_w, s.root_quat_w, rays, grid, w.obs, loop_bf)
+            actions, _, _ = net.act({"states": loop_bf}, eps=eps_sets[i % 4])
             act_buf.copy_(actions)
 
-        ksteps = max(min(args.steps, 200), 3)
-        ms_loop = time_steps(graphed(closed_step), ksteps, 3, flush, stream)
+        t32 = max_over_ranks([time_steps(graphed(step_fp32), ksteps, 3, flush, stream).mean()])[0] * 1e-3
         act_buf.zero_()
-        ms_loop_bf = time_steps(graphed(closed_step_bf16), ksteps, 3, flush, stream)
-        tl = torch.tensor([ms_loop.sum(), ms_loop_bf.sum()], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
-        extra["closed_loop_step"] = {
-            "workload": f"{n_step} envs/GPU: pre_step + post_step + height scan + policy forward (tcgen05) + Gaussian act, "
-                        "actions fed back to the next step; physics replaced by a synthetic pose update",
-            "env_steps_per_s": n_step * world * ksteps / (float(tl[0]) * 1e-3),
-            "ms_per_step": float(tl[0]) / ksteps, "gpu_launches_per_step": 4 if args.single_launch_mdp else 5,
-            "cuda_graph": not args.no_graph,
-            "finite_actions": bool(torch.isfinite(act_buf).all().item()),
-            "bf16_observation": {"env_steps_per_s": n_step * world * ksteps / (float(tl[1]) * 1e-3),
-                                 "ms_per_step": float(tl[1]) / ksteps,
-                                 "how": "rover_height_scan_obs writes the bf16 mirror, rover_policy_forward_bf16 reads it"},
-        }
-    except Exception as e:
-        extra["closed_loop_step"] = {"error": f"{type(e).__name__}: {e}"}
+        t16 = max_over_ranks([time_steps(graphed(step_bf16), ksteps, 3, flush, stream).mean()])[0] * 1e-3
+        return {"workload": f"{n} envs/GPU: pre_step + post_step + height scan + policy forward (tcgen05) + Gaussian act, "
+                            "actions fed back to the next step; physics replaced by a synthetic pose update",
+                "env_steps_per_s": n * world / t32, "us_per_step": t32 * 1e6, "cuda_graph": not args.no_graph,
+                "finite_actions": bool(torch.isfinite(act_buf).all().item()),
+                "bf16_observation": {"env_steps_per_s": n * world / t16, "us_per_step": t16 * 1e6,
+                                     "how": "rover_height_scan_obs writes the bf16 mirror, rover_policy_forward_bf16 reads it"}}
 
-    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    guarded("closed_loop", roofline, closed_loop)
+
+    # ------------------------------------------------------------------ the reference-facing call: RoverEnv.step()
+    def env_step():
+        from isaac_rover_orbit_b200.env import RoverEnv
+
+        n = STEP_ENVS_CFG3 if world == 1 else STEP_ENVS_CFG5
+        gen4 = torch.Generator().manual_seed(5 + rank)
+        drift = torch.stack([(torch.rand(n, 3, generator=gen4) * torch.tensor([4.0, 4.0, 0.0]) - torch.tensor([2.0, 2.0, 0.0]))
+                             for _ in range(4)]).to(dev)
+        forces = torch.stack([synthetic.make_step(n, gen4, vt, TERRAIN["size_m"], TERRAIN["grid_res"],
+                                                  cfg3.num_contact_bodies, 1).force_matrix_w for _ in range(4)]).to(dev)
+        quats = torch.stack([synthetic.make_poses(n, gen4, vt, TERRAIN["size_m"], TERRAIN["grid_res"])[1] for _ in range(4)]).to(dev)
+        tick = torch.zeros((), dtype=torch.int64, device=dev)
+        out = {}
+        for mode in ("eager", "cuda_graph"):
+            tick.zero_()
+
+            def physics(env):  # graph-safe stand-in for PhysX (a device-side counter picks the state set)
+                k = tick % 4
+                robot = env.scene["robot"].data
+                torch.add(env._buf.env_origins, drift.index_select(0, k.reshape(1))[0], out=robot.root_pos_w)
+                robot.root_quat_w.copy_(quats.index_select(0, k.reshape(1))[0])
+                env.scene.sensors["contact_sensor"].data.force_matrix_w.copy_(forces.index_select(0, k.reshape(1))[0])
+                tick.add_(1)
+
+            sub = dataclasses.replace(tables, spawn_table=tables.spawn_table[: 2 * n])
+            env = RoverEnv(RoverEnvCfg(num_envs=n), sub, dev, physics=physics, seed=3 + rank, physics_needs_targets=False,
+                           scan_grid=grid)
+            env.reset()
+            if mode == "cuda_graph":
+                env.enable_cuda_graph(warmup=2)
+            acts = [(torch.rand(n, 2, generator=gen4) * 2 - 1).to(dev) for _ in range(4)]
+            ms_e = time_steps(lambda i: env.step(acts[i % 4]), ksteps, 5, flush, stream)
+            t = max_over_ranks([ms_e.mean()])[0] * 1e-3
+            # wall clock of the same loop without flushes: what a host-driven loop sees per call
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(ksteps):
+                env.step(acts[i % 4])
+            torch.cuda.synchronize()
+            wall = max_over_ranks([(time.perf_counter() - t0) / ksteps])[0]
+            out[mode] = {"env_steps_per_s": n * world / t, "us_per_step": t * 1e6, "wall_us_per_step_warm_l2": wall * 1e6,
+                         "resets_last_step": float(env._buf.log[13].item())}
+            env.close()
+            del env
+        ref_tag = "cfg3" if world == 1 else "cfg5"
+        ops_us = fused.get(ref_tag, {}).get("us_per_step")
+        out["envs_per_gpu"] = n
+        out["ops_graph_us_per_step"] = ops_us
+        if ops_us:
+            out["api_over_ops"] = out["cuda_graph"]["us_per_step"] / ops_us
+        out["how"] = ("RoverEnv.step(action): action copy + pre_step(ACTIONS|TERMS) + post_step (variates and episode log in "
+                      "the kernel) + height scan; physics = synthetic pose/contact update (3 small torch kernels inside the "
+                      "timed region, as in the ops.* figure's 1)")
+        return out
+
+    guarded("env_step", e2e, env_step)
+
+    # ------------------------------------------------------------------ cfg-1: 256 envs here and on the host cores
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference(v, f, steps=None, warmup=1, n_envs=SCAN_ENVS_PER_GPU, budget_s=12.0)
+    cfg1 = {}
+
+    def cfg1_gpu():
+        w = StepWorld(CFG1_ENVS, 4242)
+        ms1 = time_steps(graphed(w.full), max(ksteps, 100), 20, flush, stream)
+        t = float(ms1.mean()) * 1e-3
+        return {"envs": CFG1_ENVS, "env_steps_per_s": CFG1_ENVS / t, "us_per_step": t * 1e6, "cuda_graph": not args.no_graph,
+                "what": "pre_step + post_step + height scan of the same 256-env workload on one B200"}
+
+    if rank == 0 and world == 1:
+        guarded("gpu", cfg1, cfg1_gpu)
+        if not args.no_cpu_baseline:
+            cpu = cpu_reference(v, f, steps=None, warmup=1, n_envs=SCAN_ENVS_PER_GPU, budget_s=10.0)
+            mesh = cpu.pop("_mesh")
+            guarded("cpu", cfg1, lambda: cpu_full_step(v, f, tables, mesh))
+            if "env_steps_per_s" in cfg1.get("cpu", {}) and "env_steps_per_s" in cfg1.get("gpu", {}):
+                cfg1["gpu_over_cpu"] = cfg1["gpu"]["env_steps_per_s"] / cfg1["cpu"]["env_steps_per_s"]
+            cpu["cfg1"] = cfg1
 
     line = None
     if rank == 0:
@@ -534,22 +640,8 @@ def run_ours(args):
             "metric": "height_scan_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg-2 height-scan raycast only: 4096 envs x 961 rays per GPU, synthetic 200 m x "
-                                   "200 m Mars-like terrain, 2,000,000 triangles",
-                       "envs_per_gpu": n_scan, "rays_per_env": N_RAYS, "kernel_variant": args.variant,
-                       "l2": "flushed between timed steps (256 MiB write, outside the timed region)",
-                       "pose_sets": POSE_SETS, "untimed_warmup_steps": max(args.warmup, 3)},
-            "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_scan * 28,
-                    "d2h_bytes_per_step": n_scan * N_RAYS * 4, "steps": e2e_steps,
-                    "how": "pinned host poses -> H2D -> rover_height_scan -> D2H heights, synchronised per step",
-                    "pipelined": e2e_pipe},
-            "gpu_launches": args.steps,
-            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": recorded_traffic(kname),
-                         "algorithmic_bytes_per_launch": alg_bytes, "launch_us": t_launch * 1e6},
-            "cpu_baseline": cpu,
-            "extra": extra,
+            "config": bench_config(args.warmup), "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": args.steps,
+            "roofline": roofline, "cpu_baseline": cpu,
         }
     if world > 1:
         dist.barrier()
@@ -583,17 +675,68 @@ def cpu_reference(v, f, steps, warmup, n_envs, budget_s=None):
             steps = int(min(max(round(budget_s / (t_env * n_envs)), 3), 200))
         else:               # reference arm: K steps are given, bound the envs per step
             n_envs = int(min(n_envs, max(64, budget_s / (t_env * (steps + warmup)))))
-    sets = [synthetic.make_poses(n_envs, gen, vt, TERRAIN["size_m"], TERRAIN["grid_res"]) for _ in range(4)]
+    sets = [synthetic.make_poses(n_envs, gen, vt, TERRAIN["size_m"], TERRAIN["grid_res"]) for _ in range(POSE_SETS)]
     for i in range(warmup):
-        OS.height_scan(*sets[i % 4], mesh)
+        OS.height_scan(*sets[i % POSE_SETS], mesh)
     t0 = time.perf_counter()
     for i in range(steps):
-        OS.height_scan(*sets[i % 4], mesh)
+        OS.height_scan(*sets[i % POSE_SETS], mesh)
     dt = time.perf_counter() - t0
     return {"value": n_envs * N_RAYS * steps / dt, "unit": "rays/s", "cores": cores, "kind": "port",
             "sample": f"{steps} steps x {n_envs} envs x {N_RAYS} rays on the same 2,000,000-triangle terrain, "
                       f"{dt:.1f} s of CPU work (oracle/: torch ray transform + C BVH raycast with OpenMP)",
-            "ms_per_step": dt / steps * 1e3, "envs_per_step": n_envs}
+            "ms_per_step": dt / steps * 1e3, "envs_per_step": n_envs, "_mesh": mesh}
+
+
+def cpu_full_step(v, f, tables, mesh=None, warmup=20, steps=30):
+    """cfg-1 (BASELINE.json configs[0]): one whole non-physics step of AAURoverEnv-v0 at 256 envs on
+    the host cores -- the reference's term functions as restated by the oracle (bit-identical to the imported reference:
+    tests/test_oracle_golden.py::test_live_reference_agrees_bitwise) + the raycast port; >= 20 warm-up + >= 30 timed steps
+    (SURVEY.md 8d "CPU baseline timing")."""
+    from isaac_rover_orbit_b200 import synthetic
+    from oracle import raycast as oracle_raycast
+    from oracle import step as OS
+
+    n = CFG1_ENVS
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    mesh = mesh if mesh is not None else oracle_raycast.Mesh(v, f)
+    vt = torch.from_numpy(v)
+    gen = torch.Generator().manual_seed(4242)
+    sets = [synthetic.make_step(n, gen, vt, TERRAIN["size_m"], TERRAIN["grid_res"]) for _ in range(4)]
+    otab = OS.TerrainTables(tables.heightmap, tables.safe_mask, tables.offset_xy, tables.spawn_table[: 2 * n])
+    ost = OS.MdpState.zeros(n)
+    pc, hc, ep = synthetic.init_commands(n, gen, sets[0].root_pos_w)
+    ost.heading_cmd_w[:], ost.episode_length_buf[:] = hc, ep
+    ost.env_origins[:] = sets[0].root_pos_w
+    ost.time_left[:] = 150.0
+    ost.pos_cmd_w[:] = sets[0].root_pos_w + torch.tensor([9.0, 0.0, 0.0])
+    drift = [torch.rand(n, 3, generator=gen) * torch.tensor([4.0, 4.0, 0.0]) - torch.tensor([2.0, 2.0, 0.0]) for _ in range(4)]
+
+    def step(i):
+        s = sets[i % 4]
+        pos = ost.env_origins + drift[i % 4]
+        out = OS.oracle_step(ost, s.actions, pos, s.root_quat_w, s.force_matrix_w, otab, s.spawn_perm, s.yaw_u, s.theta_u,
+                             s.heading_u)
+        h, _ = OS.height_scan(out.root_pos_w, out.root_quat_w, mesh)
+        return torch.cat([out.obs_head, h], dim=1)
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(warmup + i)
+    dt = (time.perf_counter() - t0) / steps
+    t1 = time.perf_counter()
+    for i in range(steps):  # the share of the terms alone (no raycast)
+        s = sets[i % 4]
+        OS.oracle_step(ost, s.actions, ost.env_origins + drift[i % 4], s.root_quat_w, s.force_matrix_w, otab, s.spawn_perm,
+                       s.yaw_u, s.theta_u, s.heading_u)
+    dt_terms = (time.perf_counter() - t1) / steps
+    return {"envs": n, "env_steps_per_s": n / dt, "ms_per_step": dt * 1e3, "ms_terms_only": dt_terms * 1e3, "cores": cores,
+            "kind": "port", "warmup_steps": warmup, "timed_steps": steps,
+            "what": "oracle/step.py (reference term functions + ORBIT manager rules, torch CPU) + oracle/raycast.c "
+                    "(BVH closest hit, OpenMP) on the 2,000,000-triangle terrain"}
 
 
 def run_reference(args):
@@ -606,15 +749,20 @@ def run_reference(args):
     # every step = one cfg-2 batch (4096 envs) when K + W such steps fit ~2 minutes of host time, else a bounded sample
     cpu = cpu_reference(v, f, steps=max(args.steps, 1), warmup=max(args.warmup, 1), n_envs=SCAN_ENVS_PER_GPU,
                         budget_s=120.0)
+    mesh = cpu.pop("_mesh")
     n_envs = cpu["envs_per_step"]
+    cpu["sample"] = f"each step = {n_envs} envs x {N_RAYS} rays of the cfg-2 workload (bounded CPU sample); " + cpu["sample"]
+    if not args.no_cfg1:
+        try:
+            tables = TR.build_terrain_tables(v, f, CFG1_ENVS)
+            cpu["cfg1"] = {"cpu": cpu_full_step(v, f, tables, mesh)}
+        except Exception as e:  # noqa: BLE001
+            cpu["cfg1"] = {"error": f"{type(e).__name__}: {e}"}
     line = {
         "impl": "reference", "metric": "height_scan_rays_per_s", "value": cpu["value"], "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg-2 height-scan raycast only: 4096 envs x 961 rays per GPU, synthetic 200 m x "
-                               "200 m Mars-like terrain, 2,000,000 triangles",
-                   "sample": f"each step = {n_envs} envs x {N_RAYS} rays of that workload (bounded CPU sample)"},
-        "cpu_baseline": cpu,
+        "config": bench_config(args.warmup), "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -646,6 +794,7 @@ def main():
                     help="fused step through the single rover_mdp_step launch instead of rover_mdp_pre_step + rover_mdp_post_step")
     ap.add_argument("--variant", type=int, default=int(os.environ.get("ROVER_SCAN_VARIANT", "5")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg1", action="store_true", help="reference arm: skip the cfg-1 full-step leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the fused step kernel by kernel instead of replaying CUDA graphs")
     ap.add_argument("--init-on-cpu", action="store_true", help="build the init-time tables on the host (profiling)")
     args = ap.parse_args()
@@ -655,6 +804,8 @@ def main():
         with StdoutToStderr():
             line = run_ours(args)
         if line is not None:
+            if line.get("cpu_baseline"):
+                line["cpu_baseline"].pop("_mesh", None)
             print(json.dumps(line), flush=True)
 
 

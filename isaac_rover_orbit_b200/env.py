@@ -191,7 +191,7 @@ class RoverEnv:
     """
 
     def __init__(self, cfg: RoverEnvCfg, terrain: TerrainTables, device="cuda:0", physics=None, seed: int = 0,
-                 physics_needs_targets: bool = True):
+                 physics_needs_targets: bool = True, scan_grid: "ops.ScanGridHandle | None" = None):
         from .mdp.actions import AckermannAction2
         from .mdp.commands import TerrainBasedPositionCommand
         from .policy import alloc_obs
@@ -208,7 +208,9 @@ class RoverEnv:
         self._buf = ops.MdpBuffers.allocate(n, self.device)
         self._params = ops.mdp_params(cfg)
         self.episode_length_buf = self._buf.episode_length_buf
-        self.scan_grid = ops.ScanGridHandle.from_mesh(terrain.vertices, terrain.faces, self.device)
+        # the raycaster's acceleration structure (built from the mesh unless the caller shares one already on the device)
+        self.scan_grid = scan_grid if scan_grid is not None else ops.ScanGridHandle.from_mesh(
+            terrain.vertices, terrain.faces, self.device)
         robot = RobotArticulation(n, self.device)
         self.scene = Scene({"robot": robot}, {}, None)
         self.scene.terrain = RoverTerrainImporter(self, terrain)

@@ -23,6 +23,14 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 1e5 and d["ms_per_step"] > 0
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["unit"] == "rays/s" and cb["value"] == d["value"] and cb["sample"]
+    # cfg-1 (BASELINE.json configs[0]): the whole non-physics step at 256 envs on the host cores, >= 20 + >= 30 steps
+    c1 = cb["cfg1"]["cpu"]
+    assert c1["envs"] == 256 and c1["env_steps_per_s"] > 0 and c1["warmup_steps"] >= 20 and c1["timed_steps"] >= 30
+    # both arms print the SAME config dict (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.bench_config(1)
     e2e = d["e2e"]
     assert e2e["value"] == d["value"] and e2e["unit"] == "rays/s"
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
