@@ -562,28 +562,20 @@ def run_ours(args):
 
         n = STEP_ENVS_CFG3 if world == 1 else STEP_ENVS_CFG5
         gen4 = torch.Generator().manual_seed(5 + rank)
-        drift = torch.stack([(torch.rand(n, 3, generator=gen4) * torch.tensor([4.0, 4.0, 0.0]) - torch.tensor([2.0, 2.0, 0.0]))
-                             for _ in range(4)]).to(dev)
-        forces = torch.stack([synthetic.make_step(n, gen4, vt, TERRAIN["size_m"], TERRAIN["grid_res"],
-                                                  cfg3.num_contact_bodies, 1).force_matrix_w for _ in range(4)]).to(dev)
-        quats = torch.stack([synthetic.make_poses(n, gen4, vt, TERRAIN["size_m"], TERRAIN["grid_res"])[1] for _ in range(4)]).to(dev)
-        tick = torch.zeros((), dtype=torch.int64, device=dev)
+        drift = (torch.rand(n, 3, generator=gen4) * torch.tensor([4.0, 4.0, 0.0]) - torch.tensor([2.0, 2.0, 0.0])).to(dev)
+        st0 = synthetic.make_step(n, gen4, vt, TERRAIN["size_m"], TERRAIN["grid_res"], cfg3.num_contact_bodies, 1)
         out = {}
         for mode in ("eager", "cuda_graph"):
-            tick.zero_()
 
-            def physics(env):  # graph-safe stand-in for PhysX (a device-side counter picks the state set)
-                k = tick % 4
-                robot = env.scene["robot"].data
-                torch.add(env._buf.env_origins, drift.index_select(0, k.reshape(1))[0], out=robot.root_pos_w)
-                robot.root_quat_w.copy_(quats.index_select(0, k.reshape(1))[0])
-                env.scene.sensors["contact_sensor"].data.force_matrix_w.copy_(forces.index_select(0, k.reshape(1))[0])
-                tick.add_(1)
+            def physics(env):  # the same stand-in for PhysX as the ops.* figure: ONE torch kernel (pose = origin + drift)
+                torch.add(env._buf.env_origins, drift, out=env.scene["robot"].data.root_pos_w)
 
             sub = dataclasses.replace(tables, spawn_table=tables.spawn_table[: 2 * n])
             env = RoverEnv(RoverEnvCfg(num_envs=n), sub, dev, physics=physics, seed=3 + rank, physics_needs_targets=False,
                            scan_grid=grid)
             env.reset()
+            env.scene["robot"].data.root_quat_w.copy_(st0.root_quat_w)
+            env.scene.sensors["contact_sensor"].data.force_matrix_w.copy_(st0.force_matrix_w)  # 5 % of the envs in contact
             if mode == "cuda_graph":
                 env.enable_cuda_graph(warmup=2)
             acts = [(torch.rand(n, 2, generator=gen4) * 2 - 1).to(dev) for _ in range(4)]
@@ -606,9 +598,9 @@ def run_ours(args):
         out["ops_graph_us_per_step"] = ops_us
         if ops_us:
             out["api_over_ops"] = out["cuda_graph"]["us_per_step"] / ops_us
-        out["how"] = ("RoverEnv.step(action): action copy + pre_step(ACTIONS|TERMS) + post_step (variates and episode log in "
-                      "the kernel) + height scan; physics = synthetic pose/contact update (3 small torch kernels inside the "
-                      "timed region, as in the ops.* figure's 1)")
+        out["how"] = ("RoverEnv.step(action): copy of the action into the term's raw_actions + pre_step(ACTIONS|TERMS) + "
+                      "post_step (variates and episode log drawn / written in the kernel) + height scan; physics = one torch "
+                      "kernel (pose = env origin + drift), as in the ops.* figure")
         return out
 
     guarded("env_step", e2e, env_step)

@@ -74,13 +74,13 @@ typedef struct RoverPlaneCells {
  * ray_starts_local [n_rays,3]: ORBIT RayCaster.ray_starts (grid_pattern + offset.pos), env frame.
  * out_heights [n_envs,n_rays]: pos_w.z - hit.z - base_offset; a miss (no hit with 0 <= t < max_dist) is -inf.
  * out_hits_w [n_envs,n_rays,3] (optional, may be NULL): sensor.data.ray_hits_w, +inf on a miss.
- * pattern_box (HOST, 4 floats: xmin, xmax, ymin, ymax of ray_starts_local; required by variant 1).
- * cells (HOST struct, device pointers inside; required by variant 2, may be NULL otherwise).
- * variant: 0 = direct home-grid walk, 1 = shared-memory staged home-grid walk, 2 = plane-cell fast path with
- * home-grid fallback for general cells, 3 = variant 2 with the per-env table window staged through cp.async.bulk,
+ * pattern_box (HOST, 4 floats: xmin, xmax, ymin, ymax of ray_starts_local; required by variants 4 and 5).
+ * cells (HOST struct, device pointers inside; required by variants 2, 4, 5, may be NULL otherwise).
+ * variant: 0 = direct home-grid walk (any mesh), 2 = plane-cell fast path with home-grid fallback for general cells,
  * 4 = persistent warp-specialised pipeline (producer warp + 8-stage ring of 2-D tensor-map TMA loads on mbarriers +
- * consumer warps), 5 = variant 4's pipeline with 256-ray chunks dealt round-robin to the consumer warps and ray
- * pairs resolved with packed fp32 (FADD2 / FMUL2) -- the default of the Python binding.
+ * consumer warps; also serves out_hits_w), 5 = variant 4's pipeline with 256-ray chunks dealt round-robin to the
+ * consumer warps and ray pairs resolved with packed fp32 (FADD2 / FMUL2) -- the default of the Python binding.
+ * (1 and 3 were measured slower in round 1 and are retired: the call fails for them.)
  * All variants produce the same heights. */
 int rover_height_scan(const float* pos_w, const float* quat_w, int32_t n_envs, const float* ray_starts_local,
                       int32_t n_rays, const float* pattern_box /* host */, const RoverScanGrid* grid /* host */,

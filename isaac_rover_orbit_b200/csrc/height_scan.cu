@@ -162,15 +162,6 @@ static int make_dev_grid(const RoverScanGrid* grid, ScanGridDev& g) {
     return 0;
 }
 
-int launch_height_scan_staged(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local, int n_rays,
-                              const ScanGridDev& g, float4 pattern_box, float max_d, float base_offset, float* out,
-                              int out_stride, float* hits, cudaStream_t stream);  // height_scan_staged.cu
-
-int launch_height_scan_cells_tma(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local,
-                                 int n_rays, const ScanGridDev& g, const RoverPlaneCells* cells, float4 pattern_box,
-                                 float max_d, float base_offset, float* out, int out_stride, float* hits,
-                                 cudaStream_t stream);  // height_scan_cells_tma.cu
-
 int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local,
                                  int n_rays, const ScanGridDev& g, const RoverPlaneCells* cells, float4 pattern_box,
                                  float max_d, float base_offset, float* out, int out_stride, float* hits,
@@ -213,16 +204,11 @@ extern "C" int rover_height_scan(const float* pos_w, const float* quat_w, int32_
                                                                    out_hits_w);
         return check_launch("height_scan_direct_kernel");
     }
-    if (variant == 1) {
-        ROVER_CHECK(pattern_box != nullptr, "rover_height_scan: variant 1 needs pattern_box (host, 4 floats)");
-        ROVER_CHECK(pattern_box[0] <= pattern_box[1] && pattern_box[2] <= pattern_box[3],
-                    "rover_height_scan: pattern_box must be (xmin, xmax, ymin, ymax)");
-        const float4 box = make_float4(pattern_box[0], pattern_box[1], pattern_box[2], pattern_box[3]);
-        return launch_height_scan_staged(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, box, max_distance,
-                                         base_offset, out_heights, out_stride, out_hits_w, s);
-    }
-    if (variant >= 2 && variant <= 5) {
-        ROVER_CHECK(cells != nullptr, "rover_height_scan: variants 2..5 need the plane-cell table");
+    // variants 1 (window re-based into shared memory, home grid) and 3 (per-CTA cp.async.bulk window) were measured slower
+    // than their neighbours in round 1 and are retired; their numbers stay reserved
+    ROVER_CHECK(variant != 1 && variant != 3, "rover_height_scan: variant %d was retired (use 0, 2, 4 or 5)", variant);
+    if (variant == 2 || variant == 4 || variant == 5) {
+        ROVER_CHECK(cells != nullptr, "rover_height_scan: variants 2, 4, 5 need the plane-cell table");
         ROVER_CHECK(cells->xs && cells->ys && cells->entries && cells->nx > 0 && cells->ny > 0,
                     "rover_height_scan: bad plane-cell table");
         ROVER_CHECK((reinterpret_cast<uintptr_t>(cells->entries) & 15) == 0,
@@ -239,12 +225,7 @@ extern "C" int rover_height_scan(const float* pos_w, const float* quat_w, int32_
             return launch_height_scan_pipelined(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, cells, box,
                                                 max_distance, base_offset, out_heights, out_stride, out_hits_w, s);
         }
-        if (variant >= 3) {  // variants 4/5 with a pattern too large for their shared table -> variant 3
-            ROVER_CHECK(pattern_box != nullptr, "rover_height_scan: variant 3 needs pattern_box (host, 4 floats)");
-            const float4 box = make_float4(pattern_box[0], pattern_box[1], pattern_box[2], pattern_box[3]);
-            return launch_height_scan_cells_tma(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, cells, box,
-                                                max_distance, base_offset, out_heights, out_stride, out_hits_w, s);
-        }
+        // variant 2, and variants 4 / 5 with a pattern too large for their shared-memory tables
         PlaneCellsDev pc{cells->xs, cells->ys, reinterpret_cast<const float4*>(cells->entries), cells->nx, cells->ny,
                          cells->inv_dx, cells->inv_dy};
         height_scan_cells_kernel<<<n_envs, kScanThreads, 0, s>>>(pos_w, quat_w, ray_starts_local, n_rays, g, pc,
@@ -282,7 +263,7 @@ extern "C" int rover_height_scan_obs(const float* pos_w, const float* quat_w, in
                                          s);
     }
     // any other table / pattern: the best variant that applies, then one conversion pass
-    const int variant = cells != nullptr ? (pattern_box != nullptr ? 3 : 2) : 0;
+    const int variant = cells != nullptr ? 2 : 0;
     if (int rc = rover_height_scan(pos_w, quat_w, n_envs, ray_starts_local, n_rays, pattern_box, grid, cells, max_distance,
                                    base_offset, obs + head_cols, obs_stride, nullptr, variant, stream))
         return rc;

@@ -28,10 +28,12 @@ def shard_range(num_envs: int, rank: int, world: int) -> tuple:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def spawn_rows(num_envs_local: int, rank: int) -> tuple:
-    """Rows of the global spawn table a rank draws from: 2*N_local rows, disjoint between ranks, so that the
+def spawn_rows(num_envs: int, rank: int, world: int) -> tuple:
+    """Rows of the global spawn table (``2 * num_envs`` rows) a rank draws from: twice its env range, so the slices are
+    disjoint, cover the table and match ``shard_range`` also when ``num_envs`` does not divide evenly -- the
     without-replacement draw of mdp/randomizations.py:22 stays shard-local."""
-    return 2 * num_envs_local * rank, 2 * num_envs_local * (rank + 1)
+    lo, hi = shard_range(num_envs, rank, world)
+    return 2 * lo, 2 * hi
 
 
 def episode_log(stats: torch.Tensor, episode_length_s: float = 150.0) -> dict:

@@ -243,7 +243,9 @@ class RoverEnv:
         self._variates = None
         self._terms_current = False   # term columns (rewards / terminations) belong to the current state
         self._graph = None
-        self._action_in = torch.zeros(n, 2, device=self.device)
+        # input buffer of the captured step = the action term's raw_actions (the reference's ``_raw_actions[:] = actions``
+        # is then the one copy a step makes)
+        self._action_in = self.action_manager.get_term().raw_actions
         # rover_env.py:18-25: env origins are shifted by +100 m in x and y
         self._buf.env_origins[:, 0] += 100.0
         self._buf.env_origins[:, 1] += 100.0

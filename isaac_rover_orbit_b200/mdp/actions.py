@@ -54,7 +54,8 @@ class AckermannAction2:
         ``fused_terms_force`` (``RoverEnv.step`` when nothing has to run between the action term and the reward /
         termination terms): the contact forces -- the same launch then also advances the counters and computes the
         terminations and rewards."""
-        self._raw_actions[:] = actions
+        if actions is not self._raw_actions:  # (the captured step of RoverEnv writes its input straight into raw_actions)
+            self._raw_actions[:] = actions
         phases = _lib.PRE_ACTIONS | (_lib.PRE_TERMS if fused_terms_force is not None else 0)
         ops.mdp_pre_step(self._env._buf, self._params, self._raw_actions, fused_terms_force, phases=phases)
         self._env._terms_current = False  # the reward / termination columns describe the previous action until TERMS runs

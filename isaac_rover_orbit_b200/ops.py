@@ -122,8 +122,8 @@ def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridH
         raise RuntimeError("height_scan: bad shapes")
     if grid.device != dev:
         raise RuntimeError("height_scan: grid lives on another device")
-    if variant in (2, 3, 4, 5) and grid.cells_struct is None:
-        raise RuntimeError("height_scan: variants 2..5 need a ScanGridHandle built with plane_cells=True")
+    if variant in (2, 4, 5) and grid.cells_struct is None:
+        raise RuntimeError("height_scan: variants 2, 4, 5 need a ScanGridHandle built with plane_cells=True")
     args = (pos_w, quat_w, ray_starts_local, rays.box_t, grid.desc, grid.cells_desc, float(max_distance),
             float(base_offset), int(variant))
     if return_hits:

@@ -53,7 +53,14 @@ def test_shard_range_partitions_the_env_axis():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
-    assert RD.spawn_rows(8192, 3) == (2 * 8192 * 3, 2 * 8192 * 4)
+    assert RD.spawn_rows(8 * 8192, 3, 8) == (2 * 8192 * 3, 2 * 8192 * 4)
+    # uneven shards: the row ranges follow shard_range -- disjoint, gap-free, 2 rows per env
+    n, world = 1003, 8
+    rows = [RD.spawn_rows(n, r, world) for r in range(world)]
+    assert rows[0][0] == 0 and rows[-1][1] == 2 * n
+    for r in range(world):
+        lo, hi = RD.shard_range(n, r, world)
+        assert rows[r] == (2 * lo, 2 * hi) and (r == 0 or rows[r - 1][1] == rows[r][0])
 
 
 def test_episode_stats_sum_over_count_not_mean_of_means():

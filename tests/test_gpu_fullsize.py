@@ -34,7 +34,7 @@ def test_scan_cfg2_variants_determinism_and_symmetries(full):
     assert pos.shape[0] == 4096 and rays.n_rays == 961
     ref = ops.height_scan(pos, quat, rays, grid, variant=2)
     assert float(torch.isfinite(ref).float().mean()) > 0.99  # the bench poses keep (nearly) every ray over the terrain
-    for variant in (3, 4, 5):
+    for variant in (4, 5):
         assert torch.equal(ops.height_scan(pos, quat, rays, grid, variant=variant), ref), f"variant {variant}"
     h1 = ops.height_scan(pos, quat, rays, grid)
     h2 = ops.height_scan(pos, quat, rays, grid)

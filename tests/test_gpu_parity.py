@@ -43,7 +43,7 @@ def _scan_compare(h_gpu, h_ref, t_ref=10.0):
         assert err <= 1e-5 * max(t_ref, 1.0), f"height error {err}"
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 2, 4, 5])
 def test_height_scan_vs_oracle_small_terrain(world, variant):
     from oracle import step as OS
 
@@ -66,7 +66,7 @@ def test_height_scan_vs_oracle_small_terrain(world, variant):
     torch.testing.assert_close(hits[~miss], hits_ref[~miss], rtol=1e-6, atol=1e-4)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 2, 4, 5])
 def test_height_scan_analytic_plane(cuda_device, variant):
     """Independent of the oracle: on the plane z = 0.3x - 0.2y + 1 the scan equals body_z - z(x,y) - 0.26878 at the
     961 yaw-rotated grid points (SURVEY.md 8c invariant)."""
@@ -94,7 +94,7 @@ def test_height_scan_analytic_plane(cuda_device, variant):
     torch.testing.assert_close(h, expect, rtol=0, atol=2e-4)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 2, 4, 5])
 def test_height_scan_mixed_mesh_levels_and_degenerates(cuda_device, variant):
     """Ground of two huge triangles + small rock pyramids + vertical / zero-area / flipped triangles."""
     from oracle import raycast as oracle_raycast
@@ -172,7 +172,7 @@ def test_height_scan_pipelined_variants_fallback_paths(cuda_device, shape):
     pos, quat = pos.to(cuda_device), quat.to(cuda_device)
     ref = ops.height_scan(pos, quat, rays, grid, variant=2)
     assert torch.isfinite(ref).any() and torch.isinf(ref).any()  # hits and misses (rays beyond the border) both occur
-    for variant in (3, 4, 5):
+    for variant in (4, 5):
         h = ops.height_scan(pos, quat, rays, grid, variant=variant)
         assert torch.equal(h, ref), f"variant {variant} differs from variant 2 ({shape})"
 
@@ -233,7 +233,7 @@ def test_height_scan_obs_writes_fp32_heights_and_bf16_mirror(cuda_device, case):
     assert bool((obs_bf[:, 965:] == 9.0).all())
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 2, 4, 5])
 def test_height_scan_max_distance_and_empty(cuda_device, variant):
     v = np.array([[-5, -5, -95.0], [5, -5, -95.0], [0, 5, -95.0]], dtype=np.float32)
     f = np.array([[0, 1, 2]], dtype=np.int32)

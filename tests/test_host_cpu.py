@@ -77,7 +77,7 @@ def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "isaac_rover_orbit_b200")
     for dirpath, _, files in os.walk(pkg):
         for fn in files:
-            if fn.endswith(".py") and fn != "smoke.py":
+            if fn.endswith(".py"):  # no exception: the smoke checker lives in __graft_entry__.py, outside the package
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), fn
 
