@@ -78,11 +78,27 @@ class _RoverNetwork:
                 raise RuntimeError(f"size mismatch for {k}: {tuple(src.shape)} vs {tuple(dst.shape)}")
             dst.copy_(src)
         self._dirty = True
+        self._fused_dirty = True
 
     def _pack(self):
         torch.ops.rover_b200.policy_pack([self._params[k + ".weight"] for k in WEIGHT_KEYS],
                                          [self._params[k + ".bias"] for k in WEIGHT_KEYS], self._packed)
         self._dirty = False
+
+    def packed_fused(self) -> torch.Tensor:
+        """The weights as the fused scan + forward kernel reads them (``rover_policy_pack_fused``: every layer as the
+        A operand of a transposed MMA); packed on first use and after ``load_state_dict``."""
+        if self.__dict__.get("_packed_fused") is None or self.__dict__.get("_fused_dirty", True):
+            n_bytes = torch_ops.policy_packed_fused_bytes()
+            buf = self.__dict__.get("_packed_fused")
+            if buf is None:
+                raw = torch.zeros(n_bytes + 128, dtype=torch.uint8, device=self.device)
+                off = (-raw.data_ptr()) % 128
+                buf = self._packed_fused = raw[off: off + n_bytes]
+            torch.ops.rover_b200.policy_pack_fused([self._params[k + ".weight"] for k in WEIGHT_KEYS],
+                                                   [self._params[k + ".bias"] for k in WEIGHT_KEYS], buf)
+            self._fused_dirty = False
+        return self._packed_fused
 
     def _forward(self, states: torch.Tensor, value_head: bool) -> torch.Tensor:
         if not states.is_cuda or states.dtype != torch.float32 or states.dim() != 2 or states.shape[1] != OBS_COLS:
