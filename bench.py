@@ -520,6 +520,49 @@ def run_ours(args):
 
     guarded("policy_forward", roofline, policy_forward)
 
+    def fused_scan_policy():
+        # BASELINE.json configs[3]: the policy forward FUSED with the observation kernel -- one launch scans 65536 envs and
+        # runs the network on the heights as they are produced (rover_scan_policy_fused); the unfused pair beside it
+        n_pol = POLICY_ENVS
+        g5 = torch.Generator().manual_seed(31 + rank)
+        sets = [tuple(t.to(dev) for t in synthetic.make_poses(n_pol, g5, vt, TERRAIN["size_m"], TERRAIN["grid_res"]))
+                for _ in range(2)]
+        fobs = alloc_obs(n_pol, dev)
+        fobs[:, :4] = torch.rand(n_pol, 4, device=dev) * 2 - 1
+        fobs_bf = alloc_obs_bf16(n_pol, dev)
+        k = 100
+        res = {}
+        for tag, wr in (("inference (heights stay on chip)", False), ("rollout (heights also stored as fp32)", True)):
+            ms_f = time_steps(lambda i: ops.height_scan_policy(*sets[i % 2], rays, grid, fobs, net, write_obs=wr), k, 3, flush,
+                              stream)
+            t = max_over_ranks([ms_f.mean()])[0] * 1e-3
+            res[tag] = {"us_per_launch": t * 1e6, "env_steps_per_s": n_pol * world / t, "tflops": n_pol * POLICY_FLOP / t / 1e12,
+                        "rays_per_s": n_pol * N_RAYS * world / t}
+        t_scan = max_over_ranks([time_steps(lambda i: ops.height_scan(*sets[i % 2], rays, grid, out=fobs[:, 4:]), k, 3, flush,
+                                            stream).mean()])[0] * 1e-3
+        t_scan_bf = max_over_ranks([time_steps(lambda i: ops.height_scan_obs(*sets[i % 2], rays, grid, fobs, fobs_bf), k, 3,
+                                               flush, stream).mean()])[0] * 1e-3
+        t_p32 = max_over_ranks([time_steps(lambda i: net.compute({"states": fobs}), k, 3, flush, stream).mean()])[0] * 1e-3
+        t_p16 = max_over_ranks([time_steps(lambda i: net.compute({"states": fobs_bf}), k, 3, flush, stream).mean()])[0] * 1e-3
+        ref_mean = net.compute({"states": fobs})[0]
+        mean = ops.height_scan_policy(*sets[(3 + k - 1) % 2], rays, grid, fobs, net, write_obs=True)
+        ref_mean = net.compute({"states": fobs})[0]
+        fin = torch.isfinite(ref_mean).all(dim=1)
+        rec = ncu_record("fused_scan_policy_kernel")
+        res.update({
+            "workload": f"cfg-4 (fused): {n_pol} envs/GPU, height scan (961 rays/env) + policy forward in ONE launch; bf16 "
+                        "operands / fp32 accumulate on tcgen05, layers transposed (features x 16 envs per MMA)",
+            "unfused_us": {"scan": t_scan * 1e6, "scan_with_bf16_mirror": t_scan_bf * 1e6, "policy_fp32_obs": t_p32 * 1e6,
+                           "policy_bf16_obs": t_p16 * 1e6, "best_pair": min(t_scan + t_p32, t_scan_bf + t_p16) * 1e6},
+            "max_abs_diff_vs_unfused": float((mean[fin] - ref_mean[fin]).abs().max().item()),
+            "bit_identical_to_unfused": bool(torch.equal(mean[fin], ref_mean[fin])),
+            "tensor_pipe_active_pct_ncu": rec.get("tensor_pipe_active_pct"),
+            "hbm_bytes_saved_per_env": 3844 + 3860,
+        })
+        return res
+
+    guarded("fused_scan_policy", roofline, fused_scan_policy)
+
     def closed_loop():
         # obs -> policy -> action -> (stand-in physics) -> pre_step -> post_step -> height scan -> obs, one graph per step
         tag = "cfg3" if "cfg3" in worlds else "cfg5"
@@ -544,15 +587,28 @@ def run_ours(args):
             actions, _, _ = net.act({"states": loop_bf}, eps=eps_sets[i % 4])
             act_buf.copy_(actions)
 
+        def step_fused(i):  # scan + policy in one launch; the fp32 observation is still written (a rollout records it)
+            s = w.sets[i % 4]
+            w.physics(i)
+            w.mdp(i, act_buf)
+            mean = ops.height_scan_policy(s.root_pos_w, s.root_quat_w, rays, grid, w.obs, net, write_obs=True)
+            actions, _ = torch.ops.rover_b200.gaussian_act(mean, net.log_std_parameter, eps_sets[i % 4])
+            act_buf.copy_(actions)
+
         t32 = max_over_ranks([time_steps(graphed(step_fp32), ksteps, 3, flush, stream).mean()])[0] * 1e-3
         act_buf.zero_()
         t16 = max_over_ranks([time_steps(graphed(step_bf16), ksteps, 3, flush, stream).mean()])[0] * 1e-3
+        act_buf.zero_()
+        tfu = max_over_ranks([time_steps(graphed(step_fused), ksteps, 3, flush, stream).mean()])[0] * 1e-3
         return {"workload": f"{n} envs/GPU: pre_step + post_step + height scan + policy forward (tcgen05) + Gaussian act, "
                             "actions fed back to the next step; physics replaced by a synthetic pose update",
                 "env_steps_per_s": n * world / t32, "us_per_step": t32 * 1e6, "cuda_graph": not args.no_graph,
                 "finite_actions": bool(torch.isfinite(act_buf).all().item()),
                 "bf16_observation": {"env_steps_per_s": n * world / t16, "us_per_step": t16 * 1e6,
-                                     "how": "rover_height_scan_obs writes the bf16 mirror, rover_policy_forward_bf16 reads it"}}
+                                     "how": "rover_height_scan_obs writes the bf16 mirror, rover_policy_forward_bf16 reads it"},
+                "fused_scan_policy": {"env_steps_per_s": n * world / tfu, "us_per_step": tfu * 1e6, "gpu_launches_per_step": 4,
+                                      "how": "pre_step + post_step + rover_scan_policy_fused (scan and policy in one launch, "
+                                             "fp32 observation still stored) + Gaussian act"}}
 
     guarded("closed_loop", roofline, closed_loop)
 

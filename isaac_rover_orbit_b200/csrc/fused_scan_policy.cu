@@ -16,7 +16,9 @@
 // bf16 activations the epilogues write).  M is always 128: layers with fewer output rows let the MMA read past their
 // rows into whatever follows in the ring (finite garbage into TMEM lanes nobody reads).
 //
-// Roles (one persistent CTA per SM, 20 warps; registers re-balanced with setmaxnreg: 128 for the scan consumers, 64 else):
+// Roles (one persistent CTA per SM, 20 warps = 5 warpgroups).  The CTA is launched with 96 registers per thread (640 x 96 =
+// 61,440: setmaxnreg moves registers inside THAT pool, not inside the SM's file) and re-balances them per warpgroup: 120
+// for the three consumer groups, 64 for the producer / streamer / issuer group, 48 for the epilogue group (60,416 in all):
 //   warp 0       scan producer: poses -> window -> 3-D tensor-map TMA load per environment (4-stage ring), as variant 5
 //   warp 1       weight streamer: the 37 weight pieces of a batch, in order, through a 3-stage ring
 //   warp 2       MMA issuer: layer 0 when a batch of 16 environments is complete, then layers 1-5 as the epilogues publish
@@ -42,6 +44,9 @@ constexpr int kFuWStage = 10240, kFuWStages = 3, kFuWSlack = 1024;
 constexpr int kFuMaxPieces = 40;
 constexpr int kFuTmemCols = 128;
 constexpr int kFuBiasFloats = 80 + 64 + 256 + 160 + 128 + 16;
+constexpr int kFuRegsLaunch = 96, kFuRegsConsumer = 120, kFuRegsUtil = 64, kFuRegsEpilogue = 48;
+static_assert(128 * (3 * kFuRegsConsumer + kFuRegsUtil + kFuRegsEpilogue) <= kFuThreads * kFuRegsLaunch,
+              "setmaxnreg: the re-balanced budgets must fit the pool the CTA was launched with");
 // Phase aliasing (scan ring): environment E signals `full` barrier E % 8 with parity (E / 8) & 1; a waiter is fooled only if
 // E - 8 has not completed yet.  Chunks are handed out in order and at most 12 are outstanding, so when a warp holds a
 // chunk of E, at least 20 of the 32 chunks of E-8 .. E-1 are finished, hence one of E-4 .. E-1 -- whose load was issued
@@ -160,6 +165,7 @@ struct __align__(128) FuSmem {
     uint32_t tmem_base;
     int next_chunk;
     float vz0;
+    __nv_bfloat16 head[kFuBatch][4];  // observation head of the batch in the layer pipeline (kept across its layer 0 -> 1)
 };
 static_assert(sizeof(FuSmem) <= 227 * 1024, "FuSmem exceeds the shared memory of one SM");
 __device__ __forceinline__ float sm_vz(const FuSmem& sm, int) { return sm.vz0; }
@@ -190,17 +196,17 @@ __device__ __forceinline__ unsigned char* operand_at(unsigned char* base, int e,
 }
 
 // Epilogue of one accumulator block: feature `feat` (this thread's TMEM lane + row offset of the block), 16 envs.
-// kind 0: LeakyReLU(d + bias) -> act[k = feat]; kind 1: like 0 but `inject` replaces the value (observation head);
+// LeakyReLU(d + bias) -> act[k = feat] as bf16; `inject` (the observation head) replaces the value where given.
 __device__ __forceinline__ void fu_epilogue_block(uint32_t taddr, const float bias, unsigned char* act, int feat, bool store,
-                                                  const float* inject) {
+                                                  const __nv_bfloat16* inject /* [e * 4], or nullptr */) {
     uint32_t r[16];
     fu_tmem_ld16(taddr, r);
     if (store) {
 #pragma unroll
         for (int e = 0; e < kFuBatch; ++e) {
-            float v = leaky(__uint_as_float(r[e]) + bias);
-            if (inject != nullptr) v = inject[e];
-            *reinterpret_cast<__nv_bfloat16*>(operand_at(act, e, feat)) = __float2bfloat16_rn(v);
+            __nv_bfloat16 v = __float2bfloat16_rn(leaky(__uint_as_float(r[e]) + bias));
+            if (inject != nullptr) v = inject[4 * e];
+            *reinterpret_cast<__nv_bfloat16*>(operand_at(act, e, feat)) = v;
         }
     }
 }
@@ -308,7 +314,7 @@ fused_scan_policy_kernel(const float* __restrict__ pos_w, const float* __restric
     const uint32_t tmem = sm.tmem_base;
 
     if (warp < 4) {
-        reg_dec<64>();
+        reg_dec<kFuRegsUtil>();
         if (warp == 0) {
             // =============================== scan producer (as variant 5; 4 stages) ===============================
             for (int base = 0; base < n_iter; base += 32) {
@@ -389,7 +395,7 @@ fused_scan_policy_kernel(const float* __restrict__ pos_w, const float* __restric
             }
         }
     } else if (warp < 4 + kFuConsumerWarps) {
-        reg_inc<128>();
+        reg_inc<kFuRegsConsumer>();
         // =============================== scan consumers ===============================
         while (true) {
             int chunk_id = 0;
@@ -473,7 +479,7 @@ fused_scan_policy_kernel(const float* __restrict__ pos_w, const float* __restric
             }
         }
     } else {
-        reg_dec<64>();
+        reg_dec<kFuRegsEpilogue>();
         // =============================== epilogue group (TMEM lane = output feature) ===============================
         const int t = threadIdx.x - 32 * (4 + kFuConsumerWarps);
         const uint32_t t_lane = (uint32_t)((warp & 3) * 32) << 16;
@@ -502,17 +508,17 @@ fused_scan_policy_kernel(const float* __restrict__ pos_w, const float* __restric
             const int buf = b & 1;
             // ---- layer 0: D0 -> A1 (80 features); the observation head (k = 0..3 of the operand) is kept for layer 2
             wait_acc();
-            float head[kFuBatch];
+            if (t >= 60 && t < 64) {  // (threads 60..63 write rows k = 60..63 of A2 below: they carry the head across)
 #pragma unroll
-            for (int e = 0; e < kFuBatch; ++e)
-                head[e] = (t >= 60 && t < 64) ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
-                                                    operand_at(sm.obs[buf], e, t - 60)))
-                                              : 0.f;
+                for (int e = 0; e < kFuBatch; ++e)
+                    sm.head[e][t - 60] = *reinterpret_cast<const __nv_bfloat16*>(operand_at(sm.obs[buf], e, t - 60));
+            }
             fu_epilogue_block(tmem + t_lane + 0, t < 80 ? b0p[t] : 0.f, sm.act, t, t < 80, nullptr);
             publish(&sm.obs_empty[buf]);  // the observation operand of this batch may be refilled (batch b + 2)
             // ---- layer 1: -> A2 = [e(60), obs[:, 0:4]]
             wait_acc();
-            fu_epilogue_block(tmem + t_lane + 16, t < 60 ? b1p[t] : 0.f, sm.act, t, t < 64, (t >= 60 && t < 64) ? head : nullptr);
+            fu_epilogue_block(tmem + t_lane + 16, t < 60 ? b1p[t] : 0.f, sm.act, t, t < 64,
+                              (t >= 60 && t < 64) ? &sm.head[0][t - 60] : nullptr);
             publish(nullptr);
             // ---- layer 2: two blocks of 128 features -> A3 (256)
             wait_acc();
