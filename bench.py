@@ -153,8 +153,9 @@ def build_world(need_tables_for: int | None, build_device, device):
     t0 = time.time()
     v, f = TR.make_synthetic_terrain(**TERRAIN)
     grid = ops.ScanGridHandle.from_mesh(v, f, device)
-    log(f"terrain {v.shape[0]} verts / {f.shape[0]} tris, home grid {grid.grid.nbytes() / 1e6:.1f} MB, plane cells "
-        f"{grid.cells.nbytes() / 1e6:.1f} MB ({grid.cells.n_general} general cells) ({time.time() - t0:.1f}s)")
+    log(f"terrain {v.shape[0]} verts / {f.shape[0]} tris, home grid "
+        + (f"{grid.grid.nbytes() / 1e6:.1f} MB" if grid.has_home_grid else "deferred (no general cells: never read)")
+        + f", plane cells {grid.cells.nbytes() / 1e6:.1f} MB ({grid.cells.n_general} general cells) ({time.time() - t0:.1f}s)")
     tables = None
     if need_tables_for:
         t0 = time.time()

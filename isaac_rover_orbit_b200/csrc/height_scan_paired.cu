@@ -22,6 +22,10 @@
 // the same out-of-line global-memory helpers as variant 4, so the staging can never change a result.
 #include "scan_paired.cuh"
 
+#ifndef ROVER_PAIR_DYNAMIC
+#define ROVER_PAIR_DYNAMIC 1  // 0: the static round-robin deal of round 1 (kept for A/B timing)
+#endif
+
 namespace rover {
 
 // kBf16: rover_height_scan_obs -- `out` points at column head_cols of the fp32 observation rows; the kernel also
@@ -59,6 +63,7 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
             for (int s = 0; s < kPairFullBars; ++s) bar_init(&sm.full_bar[s], 2);  // TMA bytes + header published
             for (int s = 0; s < kPairStages; ++s) bar_init(&sm.empty_bar[s], (uint32_t)n_chunks);
+            sm.next_chunk = 0;
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -158,9 +163,26 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
         DBG_STAMP(2);
     } else {
         // =============================== consumers ===============================
+        // Work units (environment, chunk) are handed out in order from a shared counter: a warp that drew the short last
+        // chunk of an environment (961 rays = 3 x 256 + 193) or met a cheap environment simply comes back earlier -- a
+        // static deal (chunk K -> warp K mod 14) left ~1 us of imbalance per launch (profiles/r01_scan_v5_paired.md).
+        // The phase-aliasing argument above holds a fortiori: at most 14 units are outstanding, so when a warp holds a
+        // chunk of environment E at least 18 chunks of E-8 .. E-1 are finished, i.e. E-8 was issued and E-16 consumed.
+#if ROVER_PAIR_DYNAMIC
+        int it = 0, c = 0;
+        auto next_unit = [&]() {
+            int k = 0;
+            if (lane == 0) k = atomicAdd(&sm.next_chunk, 1);
+            k = __shfl_sync(0xffffffffu, k, 0);
+            it = k / n_chunks;
+            c = k - it * n_chunks;
+        };
+        next_unit();
+#else
         const int w = warp - 1;
         const int step_it = kPairConsumerWarps / n_chunks, step_c = kPairConsumerWarps % n_chunks;
         int it = w / n_chunks, c = w % n_chunks;
+#endif
 #if ROVER_SCAN_DBG == 3
         int dbg_j = 0;
 #endif
@@ -233,12 +255,16 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
             __syncwarp();
             DBG_STAMP(dbg_slot + 2);
             if (lane == 0) bar_arrive(&sm.empty_bar[s]);  // this chunk no longer reads the stage
+#if ROVER_PAIR_DYNAMIC
+            next_unit();
+#else
             it += step_it;
             c += step_c;
             if (c >= n_chunks) {
                 c -= n_chunks;
                 ++it;
             }
+#endif
         }
     }
 #if ROVER_SCAN_DBG == 3

@@ -105,6 +105,7 @@ struct PairSmem {
     LinePair2 xpair[kPairMaxLines], ypair[kPairMaxLines];
     unsigned long long full_bar[kPairFullBars];
     unsigned long long empty_bar[kPairStages];
+    int next_chunk;  // dynamic hand-out of (environment, chunk) work units, in order
 };
 // Phase aliasing: a consumer warp visits only every 3rd..4th environment, so it may reach environment E while the
 // TMA load of E - 8 (same stage) is still in flight (loads complete out of order); with one `full` barrier per stage

@@ -74,6 +74,9 @@ def test_height_scan_analytic_plane(cuda_device, variant):
     v[:, 2] = 0.3 * v[:, 0] - 0.2 * v[:, 1] + 1.0
     f = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32)
     grid = ops.ScanGridHandle.from_mesh(v, f, cuda_device)
+    # a 1 x 1 lattice with a closed-form cell: the home grid is deferred until variant 0 asks for it
+    assert grid.has_home_grid == (grid.cells.n_general != 0)
+    grid.ensure_home_grid()
     assert len(grid.grid.levels) == 1 and grid.grid.levels[0].cell > 50  # two giant triangles -> a coarse level
     gen = torch.Generator().manual_seed(5)
     n = 33
@@ -115,7 +118,7 @@ def test_height_scan_mixed_mesh_levels_and_degenerates(cuda_device, variant):
     faces += [[b, b + 1, b + 2], [b + 3, b + 4, b + 5]]
     v = np.array(verts, dtype=np.float32)
     f = np.array(faces, dtype=np.int32)
-    grid = ops.ScanGridHandle.from_mesh(v, f, cuda_device)
+    grid = ops.ScanGridHandle.from_mesh(v, f, cuda_device, home_grid=True)
     assert len(grid.grid.levels) >= 2 and grid.grid.n_dropped == 2
     gen = torch.Generator().manual_seed(9)
     n = 128
