@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librover_b200.so")
+# ROVER_B200_LIB: another build of the same library (A/B timing of compile-time experiments, profiles/); default in-tree
+LIB_PATH = os.environ.get("ROVER_B200_LIB") or os.path.join(_HERE, "librover_b200.so")
 
 MAX_LEVELS = 12
 NUM_REWARD_TERMS = 7

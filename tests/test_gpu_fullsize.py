@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def full(cuda_device):
-    v, f, grid, tables = bench.build_world(bench.STEP_ENVS_1GPU, cuda_device, cuda_device)
+    v, f, grid, tables = bench.build_world(bench.STEP_ENVS_CFG3, cuda_device, cuda_device)
     gen = torch.Generator().manual_seed(2024)
     vt = torch.from_numpy(v)
     pos, quat = synthetic.make_poses(bench.SCAN_ENVS_PER_GPU, gen, vt, bench.TERRAIN["size_m"], bench.TERRAIN["grid_res"])
@@ -106,7 +106,7 @@ def test_mdp_cfg3_steps_against_oracle(full):
     with the same checks as the small-terrain parity test -- masks and reset indices bit-exact, floats 1e-5 relative."""
     from mdp_parity import check_mdp_steps_vs_oracle
 
-    n = bench.STEP_ENVS_1GPU
+    n = bench.STEP_ENVS_CFG3
     assert n == 16384
     resets = check_mdp_steps_vs_oracle(full["dev"], n, full["v"], full["tables"].to("cpu"), bench.TERRAIN["size_m"],
                                        bench.TERRAIN["grid_res"], n_steps=3, margin=20.0, max_ambiguous=4)
@@ -114,7 +114,7 @@ def test_mdp_cfg3_steps_against_oracle(full):
 
 
 def test_mdp_cfg3_statistics_ranks_and_determinism(full):
-    dev, tables, n = full["dev"], full["tables"], bench.STEP_ENVS_1GPU
+    dev, tables, n = full["dev"], full["tables"], bench.STEP_ENVS_CFG3
     cfg = RoverEnvCfg(num_envs=n)
     params = ops.mdp_params(cfg)
     th = ops.TerrainTablesHandle(tables.heightmap, tables.safe_mask, tables.offset_xy, tables.spawn_table,
