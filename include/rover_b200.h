@@ -358,25 +358,33 @@ int rover_policy_forward_bf16(const uint16_t* obs_bf16, int32_t stride, int32_t 
                               void* stream);
 int rover_value_forward_bf16(const uint16_t* obs_bf16, int32_t stride, int32_t n_envs, const void* packed, float* value,
                              void* stream);
-/* Height scan FUSED with the policy (or value) forward -- BASELINE.json configs[3], "policy forward fused with the
- * observation kernel": replaces height_scan_rover (mdp/observations.py:35-45, over ORBIT RayCaster / warp raycast) and
- * GaussianNeuralNetwork.compute (learning/skrl/models.py:89-102) in ONE launch; the 961 heights of an environment go as
- * bf16 from the scan's consumer warps straight into the shared-memory operand of the layer-0 tcgen05.mma and never make
- * the HBM round trip (3844 B/env written + 3860 B/env read back in the unfused pair).
+/* Height scan FUSED with the heightmap encoder of the policy (or value) network -- BASELINE.json configs[3], "policy
+ * forward fused with the observation kernel".  rover_scan_encoder_fused replaces height_scan_rover
+ * (mdp/observations.py:35-45, over ORBIT RayCaster / warp raycast) and HeightmapEncoder (learning/skrl/models.py:24-36,
+ * called at :95-97) in ONE launch: the 961 heights of an environment go as bf16 from the scan's consumer warps straight
+ * into the shared-memory operand of the layer-0 tcgen05.mma -- whose other operand, W0 (80 x 961), stays in tensor
+ * memory for the whole launch -- and never make the round trip through L2 / HBM (3844 B/env written + 3860 B/env read
+ * back in the unfused pair).  rover_policy_mlp_forward then runs the MLP (64 -> 256 -> 160 -> 128 -> 2 | 1,
+ * models.py:97-102 / :151-162) on the encoder output.
  *   obs [N, obs_stride] fp32: columns 0..3 (written by rover_mdp_post_step) are READ; the heights are written to columns
  *     4..964 only when write_obs != 0 (a rollout that records its states needs them; pure inference does not) -- and,
  *     whatever write_obs says, for environments whose table window cannot be staged (they resolve through that row).
- *   packed_fused: image from rover_policy_pack_fused (size query: packed == NULL), 16-byte aligned; out [N,2] means
+ *   packed_fused: image from rover_policy_pack_fused (size query: packed == NULL; layers 0 and 1 of `weights`), 16-byte
+ *     aligned.  enc_bf16 [N, 64] bf16, 128-byte aligned: [LeakyReLU encoder output (60), obs[:, 0:4]] per environment.
+ *   rover_policy_mlp_forward: `packed` = the blob of rover_policy_pack (its layers 2..5 are read); out [N,2] means
  *     (value_head == 0; tanh applied) or [N] values (value_head != 0, weights packed with out_dim[5] == 1).
  * Needs n_rays == 961, a flat-z pattern and the planar plane-cell table.  Heights (when written) are exactly those of
- * rover_height_scan; means agree with rover_policy_forward within its bf16 tolerance (same operands, same K order). */
+ * rover_height_scan; the pair's output equals rover_policy_forward's bit for bit (same bf16 operands, same K order;
+ * tests/test_gpu_fused_policy.py). */
 int64_t rover_policy_pack_fused(const RoverPolicyWeights* weights /* host struct, device pointers */, void* packed,
                                 void* stream);
-int rover_scan_policy_fused(const float* pos_w, const float* quat_w, int32_t n_envs, const float* ray_starts_local,
-                            int32_t n_rays, const float* pattern_box /* host */, const RoverScanGrid* grid /* host */,
-                            const RoverPlaneCells* cells /* host */, float max_distance, float base_offset, float* obs,
-                            int32_t obs_stride, int32_t write_obs, const void* packed_fused, float* out,
-                            int32_t value_head, void* stream);
+int rover_scan_encoder_fused(const float* pos_w, const float* quat_w, int32_t n_envs, const float* ray_starts_local,
+                             int32_t n_rays, const float* pattern_box /* host */, const RoverScanGrid* grid /* host */,
+                             const RoverPlaneCells* cells /* host */, float max_distance, float base_offset, float* obs,
+                             int32_t obs_stride, int32_t write_obs, const void* packed_fused, uint16_t* enc_bf16,
+                             void* stream);
+int rover_policy_mlp_forward(const uint16_t* enc_bf16, int32_t n_envs, const void* packed, float* out, int32_t value_head,
+                             void* stream);
 /* actions = clamp(mean + exp(clamp(log_std,-20,2)) * eps, -1, 1); log_prob [N] = sum_j log N(a_j) */
 int rover_gaussian_act(const float* mean, const float* log_std, const float* eps, int32_t n_envs, float* actions,
                        float* log_prob, void* stream);

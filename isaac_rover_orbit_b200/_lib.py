@@ -28,7 +28,7 @@ SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_
            "rover_ackermann",
            "rover_policy_pack", "rover_policy_forward", "rover_value_forward", "rover_policy_forward_bf16",
            "rover_value_forward_bf16", "rover_gaussian_act", "rover_mesh_to_heightmap", "rover_steep_mask",
-           "rover_policy_pack_fused", "rover_scan_policy_fused")
+           "rover_policy_pack_fused", "rover_scan_encoder_fused", "rover_policy_mlp_forward")
 
 
 class ScanLevel(C.Structure):
@@ -184,9 +184,11 @@ def load() -> C.CDLL:
         fn.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.rover_policy_pack_fused.restype = C.c_int64
     lib.rover_policy_pack_fused.argtypes = [C.POINTER(PolicyWeights), vp, vp]
-    lib.rover_scan_policy_fused.restype = C.c_int
-    lib.rover_scan_policy_fused.argtypes = [vp, vp, i32, vp, i32, C.POINTER(C.c_float * 4), C.POINTER(ScanGrid),
-                                            C.POINTER(PlaneCells), f32, f32, vp, i32, i32, vp, vp, i32, vp]
+    lib.rover_scan_encoder_fused.restype = C.c_int
+    lib.rover_scan_encoder_fused.argtypes = [vp, vp, i32, vp, i32, C.POINTER(C.c_float * 4), C.POINTER(ScanGrid),
+                                             C.POINTER(PlaneCells), f32, f32, vp, i32, i32, vp, vp, vp]
+    lib.rover_policy_mlp_forward.restype = C.c_int
+    lib.rover_policy_mlp_forward.argtypes = [vp, i32, vp, vp, i32, vp]
     lib.rover_gaussian_act.restype = C.c_int
     lib.rover_gaussian_act.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     _lib = lib

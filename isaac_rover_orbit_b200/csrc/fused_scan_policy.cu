@@ -1,31 +1,38 @@
-// Height scan fused with the policy forward: the observation never leaves the SM.
+// Height scan fused with the heightmap encoder of the policy: the observation never leaves the SM.
 //
-// Replaces, in ONE launch, the pair the reference runs back to back every step (reference root relative):
+// Replaces, in one launch, the height scan and the part of the network that reads it (reference root relative):
 //   height_scan_rover                rover_envs/envs/navigation/mdp/observations.py:35-45  (+ ORBIT RayCaster / warp raycast)
-//   GaussianNeuralNetwork.compute    rover_envs/envs/navigation/learning/skrl/models.py:24-36, 89-102
+//   HeightmapEncoder (961 -> 80 -> 60, LeakyReLU)   rover_envs/envs/navigation/learning/skrl/models.py:24-36, called at :95-97
 // (BASELINE.json configs[3]: "policy forward ... fused with the observation kernel").  Unfused, the 961 heights of an
-// environment make an HBM round trip -- 3844 B written by the scan (+ 1930 B for the bf16 mirror), 3860 / 1930 B read
-// back by the policy -- and the stand-alone forward is HBM-bound at 83 FLOP/B.  Here the scan's consumer warps write
-// each height as bf16 straight into the shared-memory operand of the layer-0 MMA.
+// environment make a round trip through L2 / HBM -- 3844 B written by the scan (+ 1930 B for the bf16 mirror), 3860 /
+// 1930 B read back by the policy.  Here the scan's consumer warps write every height as bf16 straight into the
+// shared-memory operand of the layer-0 MMA; what leaves the SM is the encoder output, [e(60), obs[:, 0:4]] as 64 bf16 =
+// 128 B per environment -- the input of the MLP (64 -> 256 -> 160 -> 128 -> 2), which runs as a second, small launch
+// (policy_mlp.cu) on 128-environment tiles.
 //
 // Orientation.  The scan is environment-major (one environment = 961 rays at a time), so a 128-environment A tile as in
-// policy_ws.cu (247 KB of bf16) cannot be collected on chip.  Every layer therefore runs TRANSPOSED on tcgen05:
-//     D_l^T [features (M = 128 lanes) x envs (N = 16)] = W_l [features x K] * A_l^T [K x envs]
-// with the weights as the A operand (K-major, streamed from L2 through a ring of 10 KB pieces by bulk copies) and a batch
-// of 16 environments as the B operand (K-major rows of 16 B core matrices: the observation operand the scan fills, then the
-// bf16 activations the epilogues write).  M is always 128: layers with fewer output rows let the MMA read past their
-// rows into whatever follows in the ring (finite garbage into TMEM lanes nobody reads).
+// policy_ws.cu (247 KB of bf16) cannot be collected on chip.  The two encoder layers therefore run TRANSPOSED on tcgen05:
+//     D^T [features (M = 128 lanes) x envs (N = 16)] = W [features x K] * A^T [K x envs]
+// with a batch of 16 environments as the B operand (K-major rows of 16 B core matrices in shared memory: the operand
+// the scan fills) and the WEIGHTS as the A operand -- and W0, the only large matrix (80 x 961), is WEIGHT-STATIONARY IN
+// TENSOR MEMORY: 128 lanes x 488 columns (2 bf16 per 32-bit cell) of the SM's 512 TMEM columns hold it for the whole
+// launch (tcgen05.mma reads its A operand from TMEM), leaving 16 columns for the accumulator.  Nothing is streamed per
+// batch: a first version that streamed all six layers' weights from L2 per 16-environment batch (325 KB) ran 2.3x
+// SLOWER than the unfused pair -- 20 KB of weights per environment on top of the 22 KB table window, through a
+// latency-bound 30 KB ring (profiles/r02_fused_scan_policy.md).  W1 (60 x 80) sits in shared memory.
 //
 // Roles (one persistent CTA per SM, 20 warps = 5 warpgroups).  The CTA is launched with 96 registers per thread (640 x 96 =
 // 61,440: setmaxnreg moves registers inside THAT pool, not inside the SM's file) and re-balances them per warpgroup: 120
-// for the three consumer groups, 64 for the producer / streamer / issuer group, 48 for the epilogue group (60,416 in all):
+// for the three consumer groups, 64 for the producer / issuer group, 56 for the epilogue group (61,440 in all):
 //   warp 0       scan producer: poses -> window -> 3-D tensor-map TMA load per environment (4-stage ring), as variant 5
-//   warp 1       weight streamer: the 37 weight pieces of a batch, in order, through a 3-stage ring
-//   warp 2       MMA issuer: layer 0 when a batch of 16 environments is complete, then layers 1-5 as the epilogues publish
+//   warp 1       one bulk copy of W1 at start; TMEM allocation
+//   warp 2       MMA issuer: layer 0 (61 MMAs, A from TMEM) when a batch of 16 environments is complete, layer 1 after
+//                the epilogue has written its operand
 //   warps 4-15   scan consumers (variant 5's packed-fp32 ray pairs; 256-ray chunks handed out dynamically, in order)
-//   warps 16-19  epilogue group: TMEM lane = output feature; + bias, LeakyReLU, bf16 -> the next layer's operand; tanh.
-// The policy work of batch b runs while the consumers scan batch b+1 (two observation operands); only the last batch's
-// layers (a few microseconds) are exposed at the end of the launch.
+//   warps 16-19  epilogue group: loads W0 into TMEM while the first batch is being scanned; then TMEM lane = output
+//                feature: + bias, LeakyReLU, bf16 -> layer 1's operand / the encoder output.
+// The encoder work of batch b runs while the consumers scan batch b+1 (two observation operands); only the last batch's
+// two layers (~2 us) are exposed at the end of the launch.
 #include "policy_common.cuh"
 #include "scan_paired.cuh"
 
@@ -39,12 +46,19 @@ constexpr int kFuBatch = 16;                   // environments per batch = N of 
 constexpr int kFuRays = 961, kFuChunks = 4;    // 961 rays = 3 x 256 + 193
 constexpr int kFuK0 = 976;                     // layer-0 K: observation columns [0, 976); weights are zero outside [3, 964)
 constexpr int kFuObsBytes = (kFuK0 / 8) * kOperandLbo;   // 33,184
-constexpr int kFuActBytes = 32 * kOperandLbo;            // activations, K <= 256
-constexpr int kFuWStage = 10240, kFuWStages = 3, kFuWSlack = 1024;
-constexpr int kFuMaxPieces = 40;
-constexpr int kFuTmemCols = 128;
-constexpr int kFuBiasFloats = 80 + 64 + 256 + 160 + 128 + 16;
-constexpr int kFuRegsLaunch = 96, kFuRegsConsumer = 120, kFuRegsUtil = 64, kFuRegsEpilogue = 48;
+constexpr int kFuActBytes = (80 / 8) * kOperandLbo;      // layer 1's operand, K = 80
+constexpr int kFuW0Cols = kFuK0 / 2;           // 488 TMEM columns: W0 as the A operand, 2 bf16 per 32-bit cell
+constexpr int kFuAccCol = kFuW0Cols;           // accumulator (16 columns), used by layer 0 then layer 1 of a batch
+constexpr int kFuTmemCols = 512;
+constexpr int kFuEncCols = 64;                 // encoder output row: e(60), obs[:, 0:4]
+constexpr int kFuBiasFloats = 80 + 64;
+// packed image: [W0^T: kFuW0Cols x 128 lanes u32 (word j of lane t at j * 128 + t)] [W1 as an A operand: 10 planes x 64
+// rows x 16 B] [bias0 (80), bias1 (64) fp32]
+constexpr int kFuW0Bytes = kFuW0Cols * 128 * 4;
+constexpr int kFuW1Bytes = 10 * 64 * 16, kFuW1Lbo = 64 * 16, kFuW1Slack = 1024;  // (M = 128 reads 64 rows past W1's)
+constexpr int kFuW1Ofs = kFuW0Bytes, kFuBiasOfs = kFuW0Bytes + kFuW1Bytes;
+constexpr int kFuPackedBytes = kFuBiasOfs + kFuBiasFloats * 4;
+constexpr int kFuRegsLaunch = 96, kFuRegsConsumer = 120, kFuRegsUtil = 64, kFuRegsEpilogue = 56;
 static_assert(128 * (3 * kFuRegsConsumer + kFuRegsUtil + kFuRegsEpilogue) <= kFuThreads * kFuRegsLaunch,
               "setmaxnreg: the re-balanced budgets must fit the pool the CTA was launched with");
 // Phase aliasing (scan ring): environment E signals `full` barrier E % 8 with parity (E / 8) & 1; a waiter is fooled only if
@@ -53,101 +67,35 @@ static_assert(128 * (3 * kFuRegsConsumer + kFuRegsUtil + kFuRegsEpilogue) <= kFu
 // only after E-8 .. E-5 had been consumed (4 stages, in-order producer).
 static_assert(kFuFullBars == 2 * kFuStages && 8 * kFuChunks - kFuConsumerWarps > 4 * kFuChunks, "phase aliasing argument");
 
-struct FuPiece {
-    uint32_t gofs;       // byte offset inside the packed image
-    uint16_t bytes;      // size of the piece
-    uint16_t lbo;        // plane stride of the A operand = padded rows * 16
-    uint8_t layer, nk;   // nk MMAs of K = 16
-    uint8_t kstep0;      // first K step (units of 16) inside the layer's B operand
-    uint8_t tcol;        // TMEM column of the accumulator
-    uint8_t first;       // first piece of its accumulator (first MMA overwrites)
-    uint8_t last;        // last piece of the layer: commit to the epilogue
-    uint8_t row0;        // first output feature of the piece's block (0 or 128)
-    uint8_t pad;
-};
-struct FuPlan {
-    FuPiece p[kFuMaxPieces];
-    int n, bias_ofs, total_bytes, pad;
-};
-
-// The packed image: every piece is the A operand as the MMA reads it -- [K / 8 planes][rows_padded][8 bf16] -- followed by
-// the biases (fp32, padded layer widths 80, 64, 256, 160, 128, 16).
-struct FuLayerBlock {
-    int layer, row0, rows_real, rows_pad, k_len, k_piece, tcol;
-};
-inline FuPlan make_fused_plan() {
-    FuPlan plan{};
-    const FuLayerBlock blocks[] = {
-        {0, 0, 80, 80, kFuK0, 64, 0},    {1, 0, 60, 64, 80, 80, 16},    {2, 0, 128, 128, 64, 32, 32},
-        {2, 128, 128, 128, 64, 32, 48},  {3, 0, 128, 128, 256, 32, 64}, {3, 128, 32, 32, 256, 128, 80},
-        {4, 0, 128, 128, 160, 32, 96},   {5, 0, 2, 8, 128, 128, 112},
-    };
-    int n = 0, ofs = 0;
-    const int n_blocks = (int)(sizeof(blocks) / sizeof(blocks[0]));
-    for (int b = 0; b < n_blocks; ++b) {
-        const FuLayerBlock& B = blocks[b];
-        for (int k = 0; k < B.k_len; k += B.k_piece) {
-            const int len = (B.k_len - k) < B.k_piece ? (B.k_len - k) : B.k_piece;
-            FuPiece& P = plan.p[n++];
-            P.gofs = (uint32_t)ofs;
-            P.bytes = (uint16_t)((len / 8) * B.rows_pad * 16);
-            P.lbo = (uint16_t)(B.rows_pad * 16);
-            P.layer = (uint8_t)B.layer;
-            P.nk = (uint8_t)(len / 16);
-            P.kstep0 = (uint8_t)(k / 16);
-            P.tcol = (uint8_t)B.tcol;
-            P.first = k == 0;
-            P.last = (k + len == B.k_len) && (b + 1 == n_blocks || blocks[b + 1].layer != B.layer);
-            P.row0 = (uint8_t)B.row0;
-            ofs += P.bytes;
-        }
-    }
-    plan.n = n;
-    plan.bias_ofs = ofs;
-    plan.total_bytes = ofs + kFuBiasFloats * 4;
-    return plan;
-}
-
 struct FuPackArgs {
-    const float* w[6];
-    const float* b[6];
-    int in_dim[6], out_dim[6];
+    const float* w0;
+    const float* b0;
+    const float* w1;
+    const float* b1;
+    int in0, in1;  // row strides of the nn.Linear weights
 };
 
-// one thread per bf16 element of a piece
-__global__ void fused_pack_kernel(const __grid_constant__ FuPackArgs a, const __grid_constant__ FuPlan plan,
-                                  unsigned char* __restrict__ packed) {
-    for (int pi = blockIdx.y; pi < plan.n; pi += gridDim.y) {
-        const FuPiece P = plan.p[pi];
-        const int rows_pad = P.lbo / 16;
-        const int total = (P.bytes / 2);
-        const int row0 = P.row0;
-        const int l = P.layer;
-        const int k_real = layer_k_real(l), n_real = a.out_dim[l];
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(packed + P.gofs);
-        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-            const int j = idx & 7;
-            const int r = (idx >> 3) % rows_pad;
-            const int plane = (idx >> 3) / rows_pad;
-            const int k = P.kstep0 * 16 + plane * 8 + j;
-            int src_k = k;
-            if (l == 0) src_k = k - kEncInOffset;           // layer-0 K index = observation column
-            if (l == 2) src_k = (k < 60) ? k + 4 : k - 60;  // operand order [e(60), obs[:, 0:4]] -> reference [x(4), e(60)]
-            const int n = row0 + r;
-            float v = 0.f;
-            if (n < n_real && src_k >= 0 && src_k < k_real) v = a.w[l][(size_t)n * a.in_dim[l] + src_k];
-            dst[idx] = __float2bfloat16_rn(v);
+__global__ void fused_pack_kernel(const __grid_constant__ FuPackArgs a, unsigned char* __restrict__ packed) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    uint32_t* w0t = reinterpret_cast<uint32_t*>(packed);
+    for (int idx = tid; idx < kFuW0Cols * 128; idx += nthr) {
+        const int j = idx >> 7, t = idx & 127;  // TMEM column j (K = 2j, 2j + 1 = observation columns), lane t = feature
+        float v[2] = {0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int src_k = 2 * j + h - kEncInOffset;  // layer-0 K index = observation column
+            if (t < 80 && src_k >= 0 && src_k < kEncIn) v[h] = a.w0[(size_t)t * a.in0 + src_k];
         }
+        w0t[idx] = pack_bf16(v[0], v[1]);
     }
-    if (blockIdx.y == 0) {
-        float* bdst = reinterpret_cast<float*>(packed + plan.bias_ofs);
-        int ofs = 0;
-        for (int l = 0; l < 6; ++l) {
-            for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < layer_n(l); n += gridDim.x * blockDim.x)
-                bdst[ofs + n] = n < a.out_dim[l] ? a.b[l][n] : 0.f;
-            ofs += layer_n(l);
-        }
+    __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(packed + kFuW1Ofs);
+    for (int idx = tid; idx < kFuW1Bytes / 2; idx += nthr) {
+        const int jj = idx & 7, r = (idx >> 3) & 63, plane = idx >> 9;
+        const int k = plane * 8 + jj;
+        w1[idx] = __float2bfloat16_rn((r < 60 && k < 80) ? a.w1[(size_t)r * a.in1 + k] : 0.f);
     }
+    float* bias = reinterpret_cast<float*>(packed + kFuBiasOfs);
+    for (int n = tid; n < kFuBiasFloats; n += nthr) bias[n] = n < 80 ? a.b0[n] : (n - 80 < 60 ? a.b1[n - 80] : 0.f);
 }
 
 struct __align__(128) FuSmem {
@@ -155,13 +103,12 @@ struct __align__(128) FuSmem {
     float vx[kPairMaxRays], vy[kPairMaxRays];
     LinePair2 xpair[kPairMaxLines], ypair[kPairMaxLines];
     unsigned char obs[2][kFuObsBytes];   // observation operands of two batches: [k / 8][16 env rows x 16 B (+ 16 B skew)]
-    unsigned char act[kFuActBytes];      // activation operand of the layer being fed
-    unsigned char w[kFuWStages * kFuWStage + kFuWSlack];
+    unsigned char act[kFuActBytes];      // layer 1's operand
+    unsigned char w1[kFuW1Bytes + kFuW1Slack];
     float bias[kFuBiasFloats];
     unsigned long long full_bar[kFuFullBars], empty_bar[kFuStages];
     unsigned long long obs_full[2], obs_empty[2];
-    unsigned long long w_full[kFuWStages], w_empty[kFuWStages];
-    unsigned long long acc_full, act_ready, batch_done;
+    unsigned long long w1_full, w0_ready, acc_full, act_ready, batch_done;
     uint32_t tmem_base;
     int next_chunk;
     float vz0;
@@ -182,6 +129,19 @@ __device__ __forceinline__ void fu_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) 
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void fu_tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]: the A operand read from tensor memory (lane = row, 2 bf16 per 32-bit column)
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
 template <int kRegs>
 __device__ __forceinline__ void reg_dec() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
@@ -195,30 +155,13 @@ __device__ __forceinline__ unsigned char* operand_at(unsigned char* base, int e,
     return base + (k >> 3) * kOperandLbo + (e >> 3) * 128 + (e & 7) * 16 + (k & 7) * 2;
 }
 
-// Epilogue of one accumulator block: feature `feat` (this thread's TMEM lane + row offset of the block), 16 envs.
-// LeakyReLU(d + bias) -> act[k = feat] as bf16; `inject` (the observation head) replaces the value where given.
-__device__ __forceinline__ void fu_epilogue_block(uint32_t taddr, const float bias, unsigned char* act, int feat, bool store,
-                                                  const __nv_bfloat16* inject /* [e * 4], or nullptr */) {
-    uint32_t r[16];
-    fu_tmem_ld16(taddr, r);
-    if (store) {
-#pragma unroll
-        for (int e = 0; e < kFuBatch; ++e) {
-            __nv_bfloat16 v = __float2bfloat16_rn(leaky(__uint_as_float(r[e]) + bias));
-            if (inject != nullptr) v = inject[4 * e];
-            *reinterpret_cast<__nv_bfloat16*>(operand_at(act, e, feat)) = v;
-        }
-    }
-}
-
 template <bool kWriteObs>
 __global__ void __launch_bounds__(kFuThreads, 1)
-fused_scan_policy_kernel(const float* __restrict__ pos_w, const float* __restrict__ quat_w, int n_envs,
-                         const float* __restrict__ ray_local, const __grid_constant__ ScanGridDev g,
-                         const __grid_constant__ PlaneCellsDev pc, const __grid_constant__ CUtensorMap tmap,
-                         float pattern_radius, float max_d, float base_offset, float* __restrict__ obs, int obs_stride,
-                         const unsigned char* __restrict__ packed, const __grid_constant__ FuPlan plan,
-                         float* __restrict__ mean, int value_head) {
+fused_scan_encoder_kernel(const float* __restrict__ pos_w, const float* __restrict__ quat_w, int n_envs,
+                          const float* __restrict__ ray_local, const __grid_constant__ ScanGridDev g,
+                          const __grid_constant__ PlaneCellsDev pc, const __grid_constant__ CUtensorMap tmap,
+                          float pattern_radius, float max_d, float base_offset, float* __restrict__ obs, int obs_stride,
+                          const unsigned char* __restrict__ packed, __nv_bfloat16* __restrict__ enc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FuSmem& sm = *reinterpret_cast<FuSmem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -250,16 +193,16 @@ fused_scan_policy_kernel(const float* __restrict__ pos_w, const float* __restric
                 mb_init(&sm.obs_full[i], kFuBatch * kFuChunks);  // one arrival per finished chunk
                 mb_init(&sm.obs_empty[i], 1);                    // the epilogue group, after layer 0 of the batch
             }
-            for (int i = 0; i < kFuWStages; ++i) {
-                mb_init(&sm.w_full[i], 1);
-                mb_init(&sm.w_empty[i], 1);  // tcgen05.commit
-            }
+            mb_init(&sm.w1_full, 1);
+            mb_init(&sm.w0_ready, 1);
             mb_init(&sm.acc_full, 1);
             mb_init(&sm.act_ready, 1);
             mb_init(&sm.batch_done, 1);
             sm.next_chunk = 0;
             sm.vz0 = __ldg(ray_local + 2);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mb_expect_tx(&sm.w1_full, kFuW1Bytes);
+            bulk_g2s(sm.w1, packed + kFuW1Ofs, kFuW1Bytes, &sm.w1_full);
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sptr(&sm.tmem_base)),
@@ -305,7 +248,7 @@ fused_scan_policy_kernel(const float* __restrict__ pos_w, const float* __restric
         uint4* z = reinterpret_cast<uint4*>(&sm.obs[0][0]);
         for (int i = ct; i < 2 * kFuObsBytes / 16; i += kFill) z[i] = make_uint4(0u, 0u, 0u, 0u);
         for (int i = ct; i < kFuBiasFloats; i += kFill)
-            sm.bias[i] = __ldg(reinterpret_cast<const float*>(packed + plan.bias_ofs) + i);
+            sm.bias[i] = __ldg(reinterpret_cast<const float*>(packed + kFuBiasOfs) + i);
         fence_async_smem();  // the zeroed operands are read by the tensor core (async proxy)
     }
     tc_fence_before();
@@ -348,21 +291,13 @@ fused_scan_policy_kernel(const float* __restrict__ pos_w, const float* __restric
                     __syncwarp();  // environments are issued strictly in order
                 }
             }
-        } else if (warp == 1 && lane == 0) {
-            // =============================== weight streamer ===============================
-            uint32_t cnt = 0;
-            for (int b = 0; b < n_batches; ++b) {
-                for (int pi = 0; pi < plan.n; ++pi, ++cnt) {
-                    const uint32_t s = cnt % kFuWStages;
-                    if (cnt >= (uint32_t)kFuWStages) mb_wait(&sm.w_empty[s], ((cnt / kFuWStages) - 1u) & 1u);
-                    mb_expect_tx(&sm.w_full[s], plan.p[pi].bytes);
-                    bulk_g2s(sm.w + s * kFuWStage, packed + plan.p[pi].gofs, plan.p[pi].bytes, &sm.w_full[s]);
-                }
-            }
         } else if (warp == 2 && lane == 0) {
             // =============================== MMA issuer ===============================
             const uint32_t idesc = make_idesc(kFuBatch);
-            uint32_t cnt = 0, act_phase = 0;
+            const uint32_t acc = tmem + kFuAccCol;
+            mb_wait(&sm.w1_full, 0u);
+            mb_wait(&sm.w0_ready, 0u);  // W0 sits in TMEM columns [0, 488)
+            tc_fence_after();
             for (int b = 0; b < n_batches; ++b) {
                 const int buf = b & 1;
                 if (b == n_batches - 1) {  // a short last batch: stand in for the chunks of the environments that do not exist
@@ -372,26 +307,19 @@ fused_scan_policy_kernel(const float* __restrict__ pos_w, const float* __restric
                 if (b > 0) mb_wait(&sm.batch_done, (uint32_t)(b - 1) & 1u);  // the epilogues of batch b-1 have read TMEM
                 mb_wait(&sm.obs_full[buf], (uint32_t)(b >> 1) & 1u);
                 tc_fence_after();
-                int layer = 0;
-                for (int pi = 0; pi < plan.n; ++pi, ++cnt) {
-                    const FuPiece P = plan.p[pi];
-                    if (P.layer != layer) {  // the epilogue of the previous layer has written this layer's operand
-                        layer = P.layer;
-                        mb_wait(&sm.act_ready, act_phase);
-                        act_phase ^= 1u;
-                        tc_fence_after();
-                    }
-                    const uint32_t s = cnt % kFuWStages;
-                    mb_wait(&sm.w_full[s], (cnt / kFuWStages) & 1u);
-                    tc_fence_after();
-                    const uint32_t a0 = sptr(sm.w + s * kFuWStage);
-                    const uint32_t b0 = (layer == 0 ? sptr(sm.obs[buf]) : sptr(sm.act)) + (uint32_t)P.kstep0 * 2u * kOperandLbo;
-                    for (int j = 0; j < P.nk; ++j)
-                        umma(tmem + P.tcol, make_desc(a0 + j * 2 * P.lbo, P.lbo), make_desc(b0 + j * 2 * kOperandLbo, kOperandLbo),
-                             idesc, !(P.first && j == 0));
-                    umma_commit(&sm.w_empty[s]);  // the piece's ring stage is free once these MMAs retire
-                    if (P.last) umma_commit(&sm.acc_full);
-                }
+                // ---- layer 0: D = W0 (TMEM) x obs^T (shared), K = 976 in 61 steps of 16 (8 TMEM columns each)
+                const uint32_t b0 = sptr(sm.obs[buf]);
+                for (int ks = 0; ks < kFuK0 / 16; ++ks)
+                    umma_ts(acc, tmem + ks * 8, make_desc(b0 + ks * 2 * kOperandLbo, kOperandLbo), idesc, ks != 0);
+                umma_commit(&sm.acc_full);
+                // ---- layer 1: D = W1 (shared) x A1^T (shared), K = 80; the accumulator columns are re-used
+                mb_wait(&sm.act_ready, (uint32_t)b & 1u);
+                tc_fence_after();
+                const uint32_t a1 = sptr(sm.w1), b1 = sptr(sm.act);
+                for (int j = 0; j < 80 / 16; ++j)
+                    umma(acc, make_desc(a1 + j * 2 * kFuW1Lbo, kFuW1Lbo), make_desc(b1 + j * 2 * kOperandLbo, kOperandLbo), idesc,
+                         j != 0);
+                umma_commit(&sm.acc_full);
             }
         }
     } else if (warp < 4 + kFuConsumerWarps) {
@@ -483,72 +411,71 @@ fused_scan_policy_kernel(const float* __restrict__ pos_w, const float* __restric
         // =============================== epilogue group (TMEM lane = output feature) ===============================
         const int t = threadIdx.x - 32 * (4 + kFuConsumerWarps);
         const uint32_t t_lane = (uint32_t)((warp & 3) * 32) << 16;
-        const float* b0p = sm.bias;
-        const float* b1p = b0p + 80;
-        const float* b2p = b1p + 64;
-        const float* b3p = b2p + 256;
-        const float* b4p = b3p + 160;
-        const float* b5p = b4p + 128;
+        // ---- W0 -> tensor memory, while the consumers scan the first batch: lane t = feature t, column j = K pair j.
+        //      The image is column-major (word j of lane t at j * 128 + t): a warp's load is one 128-byte line.
+        {
+            const uint32_t* __restrict__ w0t = reinterpret_cast<const uint32_t*>(packed) + t;
+            static_assert(kFuW0Cols % 8 == 0, "W0 is stored 8 columns at a time");
+#pragma unroll 4
+            for (int c0 = 0; c0 < kFuW0Cols; c0 += 8) {
+                uint32_t r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = __ldg(w0t + (size_t)(c0 + i) * 128);
+                fu_tmem_st8(tmem + t_lane + c0, r);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            fu_epi_sync();
+            if (t == 0) fu_arrive(&sm.w0_ready);
+        }
+        const float bias0 = t < 80 ? sm.bias[t] : 0.f;
+        const float bias1 = t < 60 ? sm.bias[80 + t] : 0.f;
         uint32_t acc_phase = 0;
-        auto wait_acc = [&]() {
+        const uint32_t acc = tmem + t_lane + kFuAccCol;
+        for (int b = 0; b < n_batches; ++b) {
+            const int buf = b & 1;
+            // ---- layer 0: D0 -> A1 (80 features); the observation head (k = 0..3 of the operand) is kept for the output
             mb_wait(&sm.acc_full, acc_phase);
             acc_phase ^= 1u;
             tc_fence_after();
-        };
-        auto publish = [&](unsigned long long* also) {  // operand stores visible to the tensor core; TMEM reads done
-            tc_fence_before();
-            fence_async_smem();
-            fu_epi_sync();
-            if (t == 0) {
-                if (also != nullptr) fu_arrive(also);
-                fu_arrive(&sm.act_ready);
-            }
-        };
-        for (int b = 0; b < n_batches; ++b) {
-            const int buf = b & 1;
-            // ---- layer 0: D0 -> A1 (80 features); the observation head (k = 0..3 of the operand) is kept for layer 2
-            wait_acc();
-            if (t >= 60 && t < 64) {  // (threads 60..63 write rows k = 60..63 of A2 below: they carry the head across)
+            if (t >= 60 && t < 64) {  // (threads 60..63 write columns 60..63 of the encoder output below)
 #pragma unroll
                 for (int e = 0; e < kFuBatch; ++e)
                     sm.head[e][t - 60] = *reinterpret_cast<const __nv_bfloat16*>(operand_at(sm.obs[buf], e, t - 60));
             }
-            fu_epilogue_block(tmem + t_lane + 0, t < 80 ? b0p[t] : 0.f, sm.act, t, t < 80, nullptr);
-            publish(&sm.obs_empty[buf]);  // the observation operand of this batch may be refilled (batch b + 2)
-            // ---- layer 1: -> A2 = [e(60), obs[:, 0:4]]
-            wait_acc();
-            fu_epilogue_block(tmem + t_lane + 16, t < 60 ? b1p[t] : 0.f, sm.act, t, t < 64,
-                              (t >= 60 && t < 64) ? &sm.head[0][t - 60] : nullptr);
-            publish(nullptr);
-            // ---- layer 2: two blocks of 128 features -> A3 (256)
-            wait_acc();
-            fu_epilogue_block(tmem + t_lane + 32, b2p[t], sm.act, t, true, nullptr);
-            fu_epilogue_block(tmem + t_lane + 48, b2p[128 + t], sm.act, 128 + t, true, nullptr);
-            publish(nullptr);
-            // ---- layer 3: 128 + 32 features -> A4 (160)
-            wait_acc();
-            fu_epilogue_block(tmem + t_lane + 64, b3p[t], sm.act, t, true, nullptr);
-            fu_epilogue_block(tmem + t_lane + 80, t < 32 ? b3p[128 + t] : 0.f, sm.act, 128 + t, t < 32, nullptr);
-            publish(nullptr);
-            // ---- layer 4: -> A5 (128)
-            wait_acc();
-            fu_epilogue_block(tmem + t_lane + 96, b4p[t], sm.act, t, true, nullptr);
-            publish(nullptr);
-            // ---- layer 5: mean = tanh(D5 + b5) (policy, 2 rows) or the linear value (1 row)
-            wait_acc();
             {
                 uint32_t r[16];
-                fu_tmem_ld16(tmem + t_lane + 112, r);
-                const int n_out = value_head ? 1 : 2;
-                if (t < n_out) {
-                    const float bb = b5p[t];
+                fu_tmem_ld16(acc, r);
+                if (t < 80) {
+#pragma unroll
+                    for (int e = 0; e < kFuBatch; ++e)
+                        *reinterpret_cast<__nv_bfloat16*>(operand_at(sm.act, e, t)) =
+                            __float2bfloat16_rn(leaky(__uint_as_float(r[e]) + bias0));
+                }
+            }
+            tc_fence_before();   // TMEM reads done before layer 1 overwrites the accumulator
+            fence_async_smem();  // operand stores (generic proxy) -> visible to the tensor core (async proxy)
+            fu_epi_sync();
+            if (t == 0) {
+                fu_arrive(&sm.obs_empty[buf]);  // the observation operand of this batch may be refilled (batch b + 2)
+                fu_arrive(&sm.act_ready);
+            }
+            // ---- layer 1: -> encoder output row [e(60), obs[:, 0:4]] (bf16), the A operand of the MLP's first layer
+            mb_wait(&sm.acc_full, acc_phase);
+            acc_phase ^= 1u;
+            tc_fence_after();
+            {
+                uint32_t r[16];
+                fu_tmem_ld16(acc, r);
+                if (t < kFuEncCols) {
 #pragma unroll
                     for (int e = 0; e < kFuBatch; ++e) {
                         const int it = b * kFuBatch + e;
                         if (it < n_iter) {
                             const size_t env = (size_t)blockIdx.x + (size_t)it * gridDim.x;
-                            const float v = __uint_as_float(r[e]) + bb;
-                            mean[env * n_out + t] = value_head ? v : tanhf(v);
+                            const __nv_bfloat16 v = t < 60 ? __float2bfloat16_rn(leaky(__uint_as_float(r[e]) + bias1))
+                                                           : sm.head[e][t - 60];
+                            enc[env * kFuEncCols + t] = v;
                         }
                     }
                 }
@@ -570,59 +497,52 @@ fused_scan_policy_kernel(const float* __restrict__ pos_w, const float* __restric
 
 extern "C" int64_t rover_policy_pack_fused(const RoverPolicyWeights* weights, void* packed, void* stream) {
     using namespace rover;
-    static const FuPlan plan = make_fused_plan();
-    if (packed == nullptr) return plan.total_bytes;
+    if (packed == nullptr) return kFuPackedBytes;
     if (weights == nullptr) {
         fail("rover_policy_pack_fused: weights is NULL");
         return -1;
     }
-    FuPackArgs a;
-    for (int l = 0; l < 6; ++l) {
-        const bool out_ok = weights->out_dim[l] == layer_n_real(l) || (l == 5 && weights->out_dim[l] == 1);  // value head
-        if (!weights->w[l] || !weights->b[l] || weights->in_dim[l] < layer_k_real(l) || !out_ok) {
+    for (int l = 0; l < 2; ++l) {
+        if (!weights->w[l] || !weights->b[l] || weights->in_dim[l] < layer_k_real(l) || weights->out_dim[l] != layer_n_real(l)) {
             fail("rover_policy_pack_fused: layer %d has shape [%d,%d], expected [%d,%d]", l, weights->out_dim[l],
                  weights->in_dim[l], layer_n_real(l), layer_k_real(l));
             return -1;
         }
-        a.w[l] = weights->w[l];
-        a.b[l] = weights->b[l];
-        a.in_dim[l] = weights->in_dim[l];
-        a.out_dim[l] = weights->out_dim[l];
     }
-    fused_pack_kernel<<<dim3(8, plan.n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, plan, static_cast<unsigned char*>(packed));
-    return check_launch("fused_pack_kernel") ? -1 : plan.total_bytes;
+    FuPackArgs a{weights->w[0], weights->b[0], weights->w[1], weights->b[1], weights->in_dim[0], weights->in_dim[1]};
+    fused_pack_kernel<<<64, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, static_cast<unsigned char*>(packed));
+    return check_launch("fused_pack_kernel") ? -1 : kFuPackedBytes;
 }
 
-extern "C" int rover_scan_policy_fused(const float* pos_w, const float* quat_w, int32_t n_envs,
-                                       const float* ray_starts_local, int32_t n_rays, const float* pattern_box,
-                                       const RoverScanGrid* grid, const RoverPlaneCells* cells, float max_distance,
-                                       float base_offset, float* obs, int32_t obs_stride, int32_t write_obs,
-                                       const void* packed_fused, float* out, int32_t value_head, void* stream) {
+extern "C" int rover_scan_encoder_fused(const float* pos_w, const float* quat_w, int32_t n_envs,
+                                        const float* ray_starts_local, int32_t n_rays, const float* pattern_box,
+                                        const RoverScanGrid* grid, const RoverPlaneCells* cells, float max_distance,
+                                        float base_offset, float* obs, int32_t obs_stride, int32_t write_obs,
+                                        const void* packed_fused, uint16_t* enc_bf16, void* stream) {
     using namespace rover;
-    ROVER_CHECK(n_envs >= 0, "rover_scan_policy_fused: negative n_envs");
+    ROVER_CHECK(n_envs >= 0, "rover_scan_encoder_fused: negative n_envs");
     if (n_envs == 0) return 0;
-    ROVER_CHECK(pos_w && quat_w && ray_starts_local && pattern_box && grid && cells && obs && packed_fused && out,
-                "rover_scan_policy_fused: NULL argument");
-    ROVER_CHECK(n_rays == kFuRays, "rover_scan_policy_fused: the policy reads a 961-ray scan (31 x 31 grid), got %d rays", n_rays);
-    ROVER_CHECK(obs_stride >= kOperandHead + kFuRays, "rover_scan_policy_fused: obs_stride %d < 965", obs_stride);
+    ROVER_CHECK(pos_w && quat_w && ray_starts_local && pattern_box && grid && cells && obs && packed_fused && enc_bf16,
+                "rover_scan_encoder_fused: NULL argument");
+    ROVER_CHECK(n_rays == kFuRays, "rover_scan_encoder_fused: the encoder reads a 961-ray scan (31 x 31 grid), got %d rays", n_rays);
+    ROVER_CHECK(obs_stride >= kOperandHead + kFuRays, "rover_scan_encoder_fused: obs_stride %d < 965", obs_stride);
     ROVER_CHECK(cells->xs && cells->ys && cells->entries && cells->entries_planar && cells->nx > 0 && cells->ny > 0,
-                "rover_scan_policy_fused: needs the plane-cell table with its planar copy");
-    ROVER_CHECK((reinterpret_cast<uintptr_t>(packed_fused) & 15) == 0, "rover_scan_policy_fused: packed image not 16B aligned");
-    static const FuPlan plan = make_fused_plan();
+                "rover_scan_encoder_fused: needs the plane-cell table with its planar copy");
+    ROVER_CHECK((reinterpret_cast<uintptr_t>(packed_fused) & 15) == 0, "rover_scan_encoder_fused: packed image not 16B aligned");
     static int n_sms = 0;
     if (n_sms == 0) {
         int dev = 0;
         ROVER_CUDA(cudaGetDevice(&dev));
         ROVER_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-        ROVER_CUDA(cudaFuncSetAttribute(fused_scan_policy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ROVER_CUDA(cudaFuncSetAttribute(fused_scan_encoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(FuSmem)));
-        ROVER_CUDA(cudaFuncSetAttribute(fused_scan_policy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ROVER_CUDA(cudaFuncSetAttribute(fused_scan_encoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(FuSmem)));
     }
     ScanGridDev g;
     g.n_levels = grid->n_levels;
     g.span = grid->span;
-    ROVER_CHECK(grid->n_levels >= 0 && grid->n_levels <= ROVER_MAX_LEVELS, "rover_scan_policy_fused: bad grid");
+    ROVER_CHECK(grid->n_levels >= 0 && grid->n_levels <= ROVER_MAX_LEVELS, "rover_scan_encoder_fused: bad grid");
     for (int l = 0; l < grid->n_levels; ++l) {
         const RoverScanLevel& L = grid->level[l];
         g.level[l] = ScanLevelDev{L.ox, L.oy, L.cell, L.inv_cell, L.ncx, L.ncy, L.start_offset, 0};
@@ -630,20 +550,21 @@ extern "C" int rover_scan_policy_fused(const float* pos_w, const float* quat_w, 
     g.cell_start = grid->cell_start;
     g.rec = reinterpret_cast<const float4*>(grid->records);
     alignas(64) CUtensorMap tmap;
-    if (const int rc = encode_planar_tensor_map(&tmap, cells, kPairPitch, kPairWin, "rover_scan_policy_fused")) return rc;
+    if (const int rc = encode_planar_tensor_map(&tmap, cells, kPairPitch, kPairWin, "rover_scan_encoder_fused")) return rc;
     PlaneCellsDev pc{cells->xs, cells->ys, reinterpret_cast<const float4*>(cells->entries), cells->nx, cells->ny,
                      cells->inv_dx, cells->inv_dy};
     const float rx = fmaxf(fabsf(pattern_box[0]), fabsf(pattern_box[1])), ry = fmaxf(fabsf(pattern_box[2]), fabsf(pattern_box[3]));
     const float radius = sqrtf(rx * rx + ry * ry) * 1.0001f + 1.0e-3f;
     const int grid_dim = n_envs < n_sms ? n_envs : n_sms;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    __nv_bfloat16* enc = reinterpret_cast<__nv_bfloat16*>(enc_bf16);
     if (write_obs)
-        fused_scan_policy_kernel<true><<<grid_dim, kFuThreads, sizeof(FuSmem), s>>>(
+        fused_scan_encoder_kernel<true><<<grid_dim, kFuThreads, sizeof(FuSmem), s>>>(
             pos_w, quat_w, n_envs, ray_starts_local, g, pc, tmap, radius, max_distance, base_offset, obs, obs_stride,
-            static_cast<const unsigned char*>(packed_fused), plan, out, value_head);
+            static_cast<const unsigned char*>(packed_fused), enc);
     else
-        fused_scan_policy_kernel<false><<<grid_dim, kFuThreads, sizeof(FuSmem), s>>>(
+        fused_scan_encoder_kernel<false><<<grid_dim, kFuThreads, sizeof(FuSmem), s>>>(
             pos_w, quat_w, n_envs, ray_starts_local, g, pc, tmap, radius, max_distance, base_offset, obs, obs_stride,
-            static_cast<const unsigned char*>(packed_fused), plan, out, value_head);
-    return check_launch("fused_scan_policy_kernel");
+            static_cast<const unsigned char*>(packed_fused), enc);
+    return check_launch("fused_scan_encoder_kernel");
 }

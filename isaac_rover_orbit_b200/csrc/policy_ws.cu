@@ -43,7 +43,6 @@ constexpr int kWsChunks = 31;  // observation columns [0, 992) cover the encoder
 constexpr int kWsStagesF = 5;
 constexpr int kWsStagesA = 2;
 constexpr int kWsStagesW = 3;
-constexpr int kWsPlane = kTileM * 16;              // bytes between K-adjacent core matrices (A operands)
 constexpr int kWsW0Chunk = (kWsChunkK / 8) * 80 * 16;  // 5,120 B of the packed W0 image per chunk
 constexpr int kWsWBuf = 40 * 1024;                 // largest single weight load: W4, or one K half of W3
 constexpr uint32_t kWsColD0 = 0, kWsColD0Stride = 128, kWsColAcc = 256;
@@ -78,84 +77,6 @@ static_assert(offsetof(WsSmem, w0) == offsetof(WsSmem, a_bf16) + kWsStagesA * 4 
                   kBfStagesW * kW0ChunkBytes <= kWsStagesA * 4 * kWsPlane + kWsStagesW * kWsW0Chunk,
               "bf16-observation mode: W0 ring overlays a_bf16[] + w0[]");
 static_assert(kTileM * kBfChunkK * 2 == kTileM * kWsChunkK * 4, "both modes use the same 16 KB stages");
-
-// shared-memory matrix descriptor, K-major SWIZZLE_128B (the layout a 128-byte-wide SWIZZLE_128B TMA box lands in):
-// 8-row groups are 1024 B apart (SBO), LBO is not used by swizzled K-major layouts, layout type 2, version 1
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-__device__ __forceinline__ void mb_arrive(unsigned long long* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(b)) : "memory");
-}
-__device__ __forceinline__ void layer_group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-
-// Epilogue of one layer for one tile row: D[row, 0:n_cols] -> +bias -> LeakyReLU -> bf16 -> A planes of the next layer.
-// inject != nullptr: columns 60..63 are replaced by inject[0..3] (layer 2 consumes [e(60), obs[:, 0:4]]).
-__device__ __forceinline__ void epilogue_to_act(uint32_t taddr, int n_cols, const float* __restrict__ bias,
-                                                unsigned char* __restrict__ act, int row, const float* inject) {
-    // Software pipeline over batches of 16 columns: the tcgen05.ld of batch k+1 is in flight while batch k is converted.
-    // (Measured on the 256-column epilogue, ~3200 cycles: a build without the TMEM loads is only 14 % faster, one with
-    // the loads alone 2x faster, and a second group of four warps on the upper half of the columns changes nothing --
-    // the bound is the SM-wide rate of the conversion arithmetic (bias add, LeakyReLU, F2FP bf16 pack, STS), not TMEM.)
-    uint32_t raw[2][16];
-    tmem_ld16_nowait(taddr, raw[0]);
-    tmem_wait_ld();
-    const int n_batches = n_cols >> 4;
-#pragma unroll 2
-    for (int k = 0; k < n_batches; ++k) {
-        const int cur = k & 1;  // compile-time after the unroll by 2: raw[][] stays in registers
-        const int nq = 16 * k;
-        if (k + 1 < n_batches) tmem_ld16_nowait(taddr + nq + 16, raw[cur ^ 1]);
-        float v[16];
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + nq + 4 * j4);  // broadcast LDS.128
-            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int j = 0; j < 4; j += 2) {
-                // two columns per FADD2 / FMUL2 (per-lane IEEE fp32: same values as the scalar ops, half the issue slots)
-                unsigned long long acc2, b2, x2, t2;
-                const unsigned long long slope2 = 0x3c23d70a3c23d70aull;  // (0.01f, 0.01f)
-                asm("mov.b64 %0, {%1, %2};" : "=l"(acc2) : "r"(raw[cur][4 * j4 + j]), "r"(raw[cur][4 * j4 + j + 1]));
-                asm("mov.b64 %0, {%1, %2};" : "=l"(b2) : "f"(bb[j]), "f"(bb[j + 1]));
-                asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x2) : "l"(acc2), "l"(b2));
-                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t2) : "l"(x2), "l"(slope2));
-                const float x0 = __uint_as_float((unsigned)(x2 & 0xffffffffull)), x1 = __uint_as_float((unsigned)(x2 >> 32));
-                const float t0 = __uint_as_float((unsigned)(t2 & 0xffffffffull)), t1 = __uint_as_float((unsigned)(t2 >> 32));
-                v[4 * j4 + j] = fmaxf(x0, t0);  // == x > 0 ? x : 0.01 x (LeakyReLU, slope 0.01)
-                v[4 * j4 + j + 1] = fmaxf(x1, t1);
-            }
-        }
-        if (inject != nullptr && nq == 48) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[12 + j] = inject[j];
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint4 o;
-            o.x = pack_bf16(v[8 * h + 0], v[8 * h + 1]);
-            o.y = pack_bf16(v[8 * h + 2], v[8 * h + 3]);
-            o.z = pack_bf16(v[8 * h + 4], v[8 * h + 5]);
-            o.w = pack_bf16(v[8 * h + 6], v[8 * h + 7]);
-            *reinterpret_cast<uint4*>(act + ((nq >> 3) + h) * kWsPlane + row * 16) = o;
-        }
-        tmem_wait_ld();  // batch k+1 has landed
-    }
-}
 
 template <bool kBf16In>
 __global__ void __launch_bounds__(kWsThreads, 1)

@@ -191,24 +191,33 @@ def height_scan_obs(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanG
                                          float(max_distance), float(base_offset), obs, int(head_cols), obs_bf16)
 
 
-def height_scan_policy(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle, obs: torch.Tensor, net,
-                       write_obs: bool = True, max_distance: float = 100.0, base_offset: float = 0.26878) -> torch.Tensor:
-    """``height_scan_rover`` FUSED with ``net.compute`` (BASELINE.json configs[3]): one launch scans the terrain under every
-    environment and runs the policy (``GaussianNeuralNetwork`` -> means ``[N,2]``) or value network
-    (``DeterministicNeuralNetwork`` -> ``[N,1]``) on ``[obs[:, :4], heights]`` -- the heights go from the scan's warps
-    into the tensor-core operand in shared memory and never travel through HBM.  ``obs`` is the fp32 observation buffer
-    ``[N, >= 965]`` whose head columns the post-step kernel wrote; with ``write_obs`` the heights are also stored to
-    ``obs[:, 4:965]`` (a rollout that records its states needs them)."""
+def height_scan_encoder(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle, obs: torch.Tensor, net,
+                        write_obs: bool = True, max_distance: float = 100.0, base_offset: float = 0.26878) -> torch.Tensor:
+    """``height_scan_rover`` FUSED with the network's ``HeightmapEncoder`` (one launch): returns the encoder output
+    ``[N, 64]`` bf16 = ``[e(60), obs[:, 0:4]]``, the input of the MLP.  See ``height_scan_policy``."""
     if not isinstance(rays, RayPattern):
         rays = RayPattern(rays, pos_w.device)
     dev = _lib.require_cuda(pos_w, quat_w)
     if grid.device != dev or grid.cells_struct is None:
-        raise RuntimeError("height_scan_policy: needs a ScanGridHandle with plane cells on the tensors' device")
+        raise RuntimeError("height_scan_encoder: needs a ScanGridHandle with plane cells on the tensors' device")
     if not obs.is_cuda or obs.device != dev:
-        raise RuntimeError("height_scan_policy: obs on another device")
-    return torch.ops.rover_b200.scan_policy_fused(pos_w, quat_w, rays.starts, rays.box_t, grid.desc, grid.cells_desc,
-                                                  float(max_distance), float(base_offset), obs, bool(write_obs),
-                                                  net.packed_fused(), net._OUT_DIM == 1)
+        raise RuntimeError("height_scan_encoder: obs on another device")
+    return torch.ops.rover_b200.scan_encoder_fused(pos_w, quat_w, rays.starts, rays.box_t, grid.desc, grid.cells_desc,
+                                                   float(max_distance), float(base_offset), obs, bool(write_obs),
+                                                   net.packed_fused())
+
+
+def height_scan_policy(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle, obs: torch.Tensor, net,
+                       write_obs: bool = True, max_distance: float = 100.0, base_offset: float = 0.26878) -> torch.Tensor:
+    """``height_scan_rover`` FUSED with ``net.compute`` (BASELINE.json configs[3]).  Launch 1 scans the terrain under every
+    environment and runs the heightmap encoder on the heights as they are produced -- they go from the scan's warps into
+    the tensor-core operand in shared memory and never travel through L2 / HBM; launch 2 runs the MLP on the 128 B/env
+    encoder output.  Returns the policy means ``[N,2]`` (``GaussianNeuralNetwork``) or values ``[N,1]``
+    (``DeterministicNeuralNetwork``), bit-identical to ``net.compute`` on ``[obs[:, :4], heights]``.  ``obs`` is the fp32
+    observation buffer ``[N, >= 965]`` whose head columns the post-step kernel wrote; with ``write_obs`` the heights are
+    also stored to ``obs[:, 4:965]`` (a rollout that records its states needs them)."""
+    enc = height_scan_encoder(pos_w, quat_w, rays, grid, obs, net, write_obs, max_distance, base_offset)
+    return torch.ops.rover_b200.policy_mlp_forward(enc, net.packed(), net._OUT_DIM == 1)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -85,9 +85,16 @@ class _RoverNetwork:
                                          [self._params[k + ".bias"] for k in WEIGHT_KEYS], self._packed)
         self._dirty = False
 
+    def packed(self) -> torch.Tensor:
+        """The packed weight blob of ``rover_policy_pack`` (re-packed after ``load_state_dict``)."""
+        if self._dirty:
+            self._pack()
+        return self._packed
+
     def packed_fused(self) -> torch.Tensor:
-        """The weights as the fused scan + forward kernel reads them (``rover_policy_pack_fused``: every layer as the
-        A operand of a transposed MMA); packed on first use and after ``load_state_dict``."""
+        """The encoder weights as the fused scan + encoder kernel reads them (``rover_policy_pack_fused``: W0 as the
+        tensor-memory image of a transposed MMA's A operand, W1 as a shared-memory A operand); packed on first use and
+        after ``load_state_dict``."""
         if self.__dict__.get("_packed_fused") is None or self.__dict__.get("_fused_dirty", True):
             n_bytes = torch_ops.policy_packed_fused_bytes()
             buf = self.__dict__.get("_packed_fused")

@@ -50,10 +50,11 @@ _SCHEMAS = {
     # ---- policy / value forward (models.py:24-36, 89-102, 105-162) and GaussianMixin.act
     "policy_pack": "(Tensor[] weights, Tensor[] biases, Tensor(a!) packed) -> ()",
     "policy_pack_fused": "(Tensor[] weights, Tensor[] biases, Tensor(a!) packed) -> ()",
-    # ---- height scan fused with the policy / value forward (BASELINE.json configs[3])
-    "scan_policy_fused": "(Tensor pos_w, Tensor quat_w, Tensor ray_starts, Tensor pattern_box, Tensor grid, Tensor cells, "
-                         "float max_distance, float base_offset, Tensor(a!) obs, bool write_obs, Tensor packed_fused, "
-                         "bool value_head) -> Tensor",
+    # ---- height scan fused with the heightmap encoder, then the MLP on its output (BASELINE.json configs[3])
+    "scan_encoder_fused": "(Tensor pos_w, Tensor quat_w, Tensor ray_starts, Tensor pattern_box, Tensor grid, Tensor cells, "
+                          "float max_distance, float base_offset, Tensor(a!) obs, bool write_obs, Tensor packed_fused) "
+                          "-> Tensor",
+    "policy_mlp_forward": "(Tensor enc, Tensor packed, bool value_head) -> Tensor",
     "policy_forward": "(Tensor obs, Tensor packed, bool value_head) -> Tensor",
     "gaussian_act": "(Tensor mean, Tensor log_std, Tensor eps) -> (Tensor, Tensor)",
     # ---- init-time tables (terrain_utils.py:23-57, 265-279)
@@ -274,19 +275,29 @@ def policy_packed_fused_bytes() -> int:
     return int(_lib.load().rover_policy_pack_fused(None, None, None))
 
 
-def _scan_policy_fused(pos_w, quat_w, ray_starts, pattern_box, grid, cells, max_distance, base_offset, obs, write_obs,
-                       packed_fused, value_head):
-    _f32("scan_policy_fused", pos_w, quat_w, ray_starts)
+def _scan_encoder_fused(pos_w, quat_w, ray_starts, pattern_box, grid, cells, max_distance, base_offset, obs, write_obs,
+                        packed_fused):
+    _f32("scan_encoder_fused", pos_w, quat_w, ray_starts)
     n, r = pos_w.shape[0], ray_starts.shape[0]
     if pos_w.shape != (n, 3) or quat_w.shape != (n, 4) or ray_starts.shape != (r, 3):
-        raise RuntimeError("rover_b200::scan_policy_fused: pos_w [N,3], quat_w [N,4], ray_starts [R,3] expected")
+        raise RuntimeError("rover_b200::scan_encoder_fused: pos_w [N,3], quat_w [N,4], ray_starts [R,3] expected")
     if obs.dtype != torch.float32 or obs.dim() != 2 or obs.shape[0] != n or obs.shape[1] < 4 + r or obs.stride(1) != 1:
-        raise RuntimeError("rover_b200::scan_policy_fused: obs must be fp32 [N, >= 4 + R] with unit inner stride")
-    out = torch.empty(n, 1 if value_head else 2, dtype=torch.float32, device=pos_w.device)
-    _lib.check(_lib.load().rover_scan_policy_fused(
+        raise RuntimeError("rover_b200::scan_encoder_fused: obs must be fp32 [N, >= 4 + R] with unit inner stride")
+    enc = torch.empty(n + 1, 64, dtype=torch.bfloat16, device=pos_w.device)  # (+1 row: room to align rows to 128 bytes)
+    enc = enc.view(-1)[((-enc.data_ptr()) % 128) // 2:][: n * 64].view(n, 64)
+    _lib.check(_lib.load().rover_scan_encoder_fused(
         _p(pos_w), _p(quat_w), n, _p(ray_starts), r, C.cast(C.c_void_p(pattern_box.data_ptr()), C.POINTER(C.c_float * 4)),
         _desc(grid, _lib.ScanGrid, "grid"), _desc(cells, _lib.PlaneCells, "cells"), float(max_distance), float(base_offset),
-        _p(obs), int(obs.stride(0)), int(bool(write_obs)), _p(packed_fused), _p(out), int(bool(value_head)), _stream(pos_w)))
+        _p(obs), int(obs.stride(0)), int(bool(write_obs)), _p(packed_fused), _p(enc), _stream(pos_w)))
+    return enc
+
+
+def _policy_mlp_forward(enc, packed, value_head):
+    if enc.dtype != torch.bfloat16 or enc.dim() != 2 or enc.shape[1] != 64 or not enc.is_contiguous() or enc.data_ptr() % 128:
+        raise RuntimeError("rover_b200::policy_mlp_forward: enc must be a contiguous bf16 [N,64] tensor, 128-byte aligned")
+    n = enc.shape[0]
+    out = torch.empty(n, 1 if value_head else 2, dtype=torch.float32, device=enc.device)
+    _lib.check(_lib.load().rover_policy_mlp_forward(_p(enc), n, _p(packed), _p(out), int(bool(value_head)), _stream(enc)))
     return out
 
 
@@ -342,7 +353,7 @@ _IMPLS = {
     "height_scan_obs": _height_scan_obs, "ackermann": _ackermann, "mdp_pre_step": _mdp_pre_step,
     "mdp_post_step": _mdp_post_step, "mdp_step": _mdp_step, "stats_read": _stats_read, "policy_pack": _policy_pack,
     "policy_forward": _policy_forward, "gaussian_act": _gaussian_act, "policy_pack_fused": _policy_pack_fused,
-    "scan_policy_fused": _scan_policy_fused, "mesh_to_heightmap": _mesh_to_heightmap,
+    "scan_encoder_fused": _scan_encoder_fused, "policy_mlp_forward": _policy_mlp_forward, "mesh_to_heightmap": _mesh_to_heightmap,
     "steep_mask": _steep_mask,
 }
 for _name, _fn in _IMPLS.items():
@@ -376,10 +387,14 @@ def _(obs, packed, value_head):
     return obs.new_empty(obs.shape[0], 1 if value_head else 2, dtype=torch.float32)
 
 
-@_fake("scan_policy_fused")
-def _(pos_w, quat_w, ray_starts, pattern_box, grid, cells, max_distance, base_offset, obs, write_obs, packed_fused,
-      value_head):
-    return pos_w.new_empty(pos_w.shape[0], 1 if value_head else 2)
+@_fake("scan_encoder_fused")
+def _(pos_w, quat_w, ray_starts, pattern_box, grid, cells, max_distance, base_offset, obs, write_obs, packed_fused):
+    return pos_w.new_empty(pos_w.shape[0], 64, dtype=torch.bfloat16)
+
+
+@_fake("policy_mlp_forward")
+def _(enc, packed, value_head):
+    return enc.new_empty(enc.shape[0], 1 if value_head else 2, dtype=torch.float32)
 
 
 @_fake("gaussian_act")
