@@ -10,7 +10,7 @@ Headline metric (BASELINE.json): height-scan rays/s on cfg-2 -- 4096 envs x 961 
 The driver keeps only the contract's keys of the JSON line, so everything else this run measures lives INSIDE them:
   roofline.by_size          the scan at 16384 / 65536 envs (the 36 MB terrain term cannot carry the fraction there)
   roofline.fused_step       cfg-3 (16384 envs, N=1) and cfg-5 (8192 envs/GPU at EVERY N, so 1 -> 8 is a ratio):
-                            pre_step + post_step (reset variates drawn in the kernel) + height scan, one CUDA graph
+                            the MDP step in one launch (reset variates drawn in the kernel) + height scan, one CUDA graph
   roofline.mdp_only / policy_forward / fused_scan_policy / closed_loop    cfg-4 and the loop with the policy in it
   e2e.env_step              the reference-facing call, RoverEnv.step(), eager and graph-captured, beside the ops.* figure
   e2e.episode_stats         (N > 1) the P2P-mailbox totals against an NCCL all-reduce
@@ -397,7 +397,7 @@ def run_ours(args):
         def mdp(self, i, actions=None):
             s = self.sets[i % 4]
             a = s.actions if actions is None else actions
-            if args.single_launch_mdp:
+            if (not args.two_launch_mdp):
                 ops.mdp_step(self.buf, params, self.th, a, s.force_matrix_w, s.root_pos_w, s.root_quat_w, obs=self.obs,
                              rng=self.rng, xchg=self.xchg)
             else:
@@ -447,7 +447,7 @@ def run_ours(args):
         w.buf.stats.zero_()
         run(0)
         torch.cuda.synchronize()
-        d = fused_numbers(n, t_full, 2 if args.single_launch_mdp else 3)
+        d = fused_numbers(n, t_full, 2 if (not args.two_launch_mdp) else 3)
         d["resets_in_one_step"] = float(w.buf.stats[13].item())
         d["variates"] = "drawn in the post-step kernel (Philox4x32-10 keyed on seed, step, env)"
         if world > 1:
@@ -468,7 +468,8 @@ def run_ours(args):
         t = max_over_ranks([time_steps(graphed(w.mdp_only), ksteps, 3, flush, stream).mean()])[0] * 1e-3
         return {"envs_per_gpu": w.n, "env_steps_per_s": w.n * world / t, "us_per_step": t * 1e6,
                 "frac": w.n * 414.0 / t / 1e9 / peak,
-                "note": "414 B/env: launch-latency bound at this N (SURVEY.md 8d); pre + post launch"}
+                "launches": 1 if not args.two_launch_mdp else 2,
+                "note": "414 B/env: launch-latency bound at this N (SURVEY.md 8d)"}
 
     guarded("mdp_only", roofline, mdp_only)
 
@@ -523,7 +524,8 @@ def run_ours(args):
 
     def fused_scan_policy():
         # BASELINE.json configs[3]: the policy forward FUSED with the observation kernel -- one launch scans 65536 envs and
-        # runs the network on the heights as they are produced (rover_scan_policy_fused); the unfused pair beside it
+        # runs the heightmap encoder on the heights as they are produced (rover_scan_encoder_fused, W0 weight-stationary in
+        # tensor memory), a second launch runs the MLP on the 128 B/env encoder output; the unfused pairs beside it
         n_pol = POLICY_ENVS
         g5 = torch.Generator().manual_seed(31 + rank)
         sets = [tuple(t.to(dev) for t in synthetic.make_poses(n_pol, g5, vt, TERRAIN["size_m"], TERRAIN["grid_res"]))
@@ -549,10 +551,11 @@ def run_ours(args):
         mean = ops.height_scan_policy(*sets[(3 + k - 1) % 2], rays, grid, fobs, net, write_obs=True)
         ref_mean = net.compute({"states": fobs})[0]
         fin = torch.isfinite(ref_mean).all(dim=1)
-        rec = ncu_record("fused_scan_policy_kernel")
+        rec = ncu_record("fused_scan_encoder_kernel")
         res.update({
-            "workload": f"cfg-4 (fused): {n_pol} envs/GPU, height scan (961 rays/env) + policy forward in ONE launch; bf16 "
-                        "operands / fp32 accumulate on tcgen05, layers transposed (features x 16 envs per MMA)",
+            "workload": f"cfg-4 (fused): {n_pol} envs/GPU, height scan (961 rays/env) + heightmap encoder in one launch "
+                        "(transposed tcgen05 MMAs, features x 16 envs, W0 resident in tensor memory), MLP in a second; bf16 "
+                        "operands / fp32 accumulate",
             "unfused_us": {"scan": t_scan * 1e6, "scan_with_bf16_mirror": t_scan_bf * 1e6, "policy_fp32_obs": t_p32 * 1e6,
                            "policy_bf16_obs": t_p16 * 1e6, "best_pair": min(t_scan + t_p32, t_scan_bf + t_p16) * 1e6},
             "max_abs_diff_vs_unfused": float((mean[fin] - ref_mean[fin]).abs().max().item()),
@@ -607,9 +610,9 @@ def run_ours(args):
                 "finite_actions": bool(torch.isfinite(act_buf).all().item()),
                 "bf16_observation": {"env_steps_per_s": n * world / t16, "us_per_step": t16 * 1e6,
                                      "how": "rover_height_scan_obs writes the bf16 mirror, rover_policy_forward_bf16 reads it"},
-                "fused_scan_policy": {"env_steps_per_s": n * world / tfu, "us_per_step": tfu * 1e6, "gpu_launches_per_step": 4,
-                                      "how": "pre_step + post_step + rover_scan_policy_fused (scan and policy in one launch, "
-                                             "fp32 observation still stored) + Gaussian act"}}
+                "fused_scan_encoder": {"env_steps_per_s": n * world / tfu, "us_per_step": tfu * 1e6,
+                                       "how": "mdp step + rover_scan_encoder_fused (scan + heightmap encoder in one launch, "
+                                              "fp32 observation still stored) + rover_policy_mlp_forward + Gaussian act"}}
 
     guarded("closed_loop", roofline, closed_loop)
 
@@ -839,8 +842,8 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--single-launch-mdp", action="store_true",
-                    help="fused step through the single rover_mdp_step launch instead of rover_mdp_pre_step + rover_mdp_post_step")
+    ap.add_argument("--two-launch-mdp", action="store_true",
+                    help="fused step through rover_mdp_pre_step + rover_mdp_post_step instead of the single rover_mdp_step launch")
     ap.add_argument("--variant", type=int, default=int(os.environ.get("ROVER_SCAN_VARIANT", "5")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cfg1", action="store_true", help="reference arm: skip the cfg-1 full-step leg")

@@ -236,11 +236,13 @@ int rover_mdp_post_step(float* root_pos_w, float* root_quat_w, int32_t n_envs, c
 /* Where the random variates of the reset path come from (randomizations.py:22, 30; terrain_importer.py:94-95, 169).
  *   rng_state == NULL: explicit arrays, as documented above (parity tests feed the oracle the same numbers);
  *   rng_state != NULL: DEVICE uint64[2] = {seed, step}.  The kernel evaluates the counter-based generator of
- *     csrc/rng.cuh in registers -- Philox4x32-10, key = seed, counter = (env, step, stream); the spawn row of reset rank j
- *     is a keyed bijection of [0, n_spawns) at j (without replacement, like randperm(len)[:K]) -- and its last block
- *     advances `step`, so the launch is CUDA-graph safe and needs no torch generator call on the step path.
- *     rover_rng_variates() evaluates the same functions on the host: spawn_perm[j], yaw_u[i], heading_u[i],
- *     theta_u[i, r] for one (seed, step) -- what a kernel launched with that state consumes, bit for bit. */
+ *     csrc/rng.cuh in registers -- Philox4x32-10, key = seed, counter = (env, step, stream); the spawn row of env i is a
+ *     keyed bijection of [0, n_spawns) at i (K reset envs draw K distinct, uniformly random rows: the distribution of
+ *     randperm(len)[:K], without needing the reset rank) -- and its last block advances `step`, so the launch is
+ *     CUDA-graph safe and needs no torch generator call on the step path.
+ *     rover_rng_variates() evaluates the same functions on the host: spawn_by_env[i], yaw_u[i], heading_u[i],
+ *     theta_u[i, r] for one (seed, step) -- what a kernel launched with that state consumes, bit for bit (to feed them
+ *     through the explicit arrays: spawn_perm[j] = spawn_by_env[id of the j-th reset env]). */
 typedef struct RoverResetVariates {
     const int64_t* spawn_perm;
     const float* yaw_u;
@@ -264,9 +266,9 @@ int rover_mdp_post_step_v3(float* root_pos_w, float* root_quat_w, int32_t n_envs
                            float* scratch, float* log_out, float* obs, int32_t obs_stride, int32_t phases,
                            const struct RoverStatsExchange* xchg /* host, may be NULL */, void* stream);
 /* HOST function (no GPU work): the variates of one (seed, step) into host arrays; any output may be NULL.
- * spawn_perm [min(n_envs, n_spawns)], yaw_u [n_envs], heading_u [n_envs], theta_u [n_envs, n_rounds]. */
+ * spawn_by_env [min(n_envs, n_spawns)], yaw_u [n_envs], heading_u [n_envs], theta_u [n_envs, n_rounds]. */
 int rover_rng_variates(uint64_t seed, uint64_t step, int32_t n_envs, int32_t n_rounds, int32_t n_spawns,
-                       int64_t* spawn_perm, float* yaw_u, float* heading_u, float* theta_u);
+                       int64_t* spawn_by_env, float* yaw_u, float* heading_u, float* theta_u);
 /* HOST: one Philox4x32-10 block (Random123 known-answer vectors pin it: tests/test_rng_cpu.py) */
 int rover_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
 
@@ -275,6 +277,7 @@ int rover_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32
  * rank that the post-step needs comes from a decoupled look-back over the blocks' reset counts instead of a second
  * launch, and every env's pre-step outputs are consumed by the thread that produced them.  Same outputs, bit for bit.
  * lookback: DEVICE uint64 [ceil(N / ROVER_MDP_BLOCK) + 2], zeroed once; the kernel maintains it (CUDA-graph safe).
+ * (rover_mdp_step_v3 with the in-kernel generator needs neither a rank nor a look-back: lookback may be NULL there.)
  * Measured on a B200 at 16384 envs inside a CUDA graph: 34.4 us against 33.1 us for the two launches (the look-back
  * chain costs more than the launch boundary it removes), so the two-launch form stays the default in this package;
  * the entry is kept, parity-tested, for callers that launch kernel by kernel (that case is not measured). */

@@ -227,8 +227,9 @@ def current_stream(device) -> C.c_void_p:
 
 def rng_variates(seed: int, step: int, n_envs: int, n_rounds: int, n_spawns: int):
     """Host evaluation of the kernels' counter-based variates (``rover_rng_variates``; no GPU work): numpy arrays
-    ``(spawn_perm [min(N, n_spawns)] int64, yaw_u [N], heading_u [N], theta_u [N, n_rounds])`` -- exactly what a
-    launch whose ``rng_state`` holds ``{seed, step}`` consumes."""
+    ``(spawn_by_env [min(N, n_spawns)] int64, yaw_u [N], heading_u [N], theta_u [N, n_rounds])`` -- exactly what a
+    launch whose ``rng_state`` holds ``{seed, step}`` consumes; ``spawn_by_env[i]`` is the spawn row env ``i`` takes IF it
+    resets (a keyed permutation of the table evaluated at the env id)."""
     import numpy as np
 
     k = min(n_envs, n_spawns)

@@ -23,7 +23,10 @@
 #include "scan_paired.cuh"
 
 #ifndef ROVER_PAIR_DYNAMIC
-#define ROVER_PAIR_DYNAMIC 1  // 0: the static round-robin deal of round 1 (kept for A/B timing)
+#define ROVER_PAIR_DYNAMIC 0  // 1: work units handed out from a shared counter instead of the static round-robin deal.
+                              // Measured on a B200 (round 2, same box, profiles/time_scan_sizes.py): 22.5 / 59.4 / 200.7 us at
+                              // 4096 / 16384 / 65536 envs against 22.5 / 57.0 / 190.0 us for the static deal -- the atomic +
+                              // shuffle per unit costs more than the ~1 us of imbalance it removes, so the static deal stays.
 #endif
 
 namespace rover {
@@ -163,11 +166,10 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
         DBG_STAMP(2);
     } else {
         // =============================== consumers ===============================
-        // Work units (environment, chunk) are handed out in order from a shared counter: a warp that drew the short last
-        // chunk of an environment (961 rays = 3 x 256 + 193) or met a cheap environment simply comes back earlier -- a
-        // static deal (chunk K -> warp K mod 14) left ~1 us of imbalance per launch (profiles/r01_scan_v5_paired.md).
-        // The phase-aliasing argument above holds a fortiori: at most 14 units are outstanding, so when a warp holds a
-        // chunk of environment E at least 18 chunks of E-8 .. E-1 are finished, i.e. E-8 was issued and E-16 consumed.
+        // Work units (environment, chunk): chunk K of the CTA's run goes to warp K mod 14 (static deal).  With
+        // ROVER_PAIR_DYNAMIC they are handed out in order from a shared counter instead; the phase-aliasing argument above
+        // holds either way (at most 14 units are outstanding, so when a warp holds a chunk of environment E at least 18
+        // chunks of E-8 .. E-1 are finished, i.e. E-8 was issued and E-16 consumed).
 #if ROVER_PAIR_DYNAMIC
         int it = 0, c = 0;
         auto next_unit = [&]() {

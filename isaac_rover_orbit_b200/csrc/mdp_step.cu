@@ -455,58 +455,67 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
         }
     }
 
-    // ---- rank of this env among the reset envs in ascending env order (== reset_buf.nonzero() order)
-    const unsigned ballot = __ballot_sync(0xffffffffu, reset);
-    if (lane == 0) warp_cnt[wid] = __popc(ballot);
-    if (!kFused) {
-        if (wid == 0) {
-            int acc = 0;
-            for (int b = lane; b < bid; b += 32) acc += O.block_reset_counts[b];
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) block_base = acc;
-        }
-        __syncthreads();
-    } else {
-        __syncthreads();
-        if (wid == 0) {
-            // decoupled look-back (single pass): publish this block's count, walk back over the predecessors' descriptors
-            // until one carries an inclusive prefix, publish our own.  Logical block ids are tickets, so every
-            // predecessor has started; descriptors are tagged with the launch epoch, so nothing is re-zeroed.
-            int cnt = 0;
-            for (int w = 0; w < ROVER_MDP_BLOCK / 32; ++w) cnt += warp_cnt[w];
-            volatile unsigned long long* desc = lookback;
-            int base = 0;
-            if (bid > 0) {
-                if (lane == 0) desc[bid] = make_lookback(epoch, kDescAggregate, (unsigned)cnt);
-                int look = bid - 1;
-                while (true) {
-                    const int idx = look - lane;
-                    unsigned long long d = make_lookback(epoch, kDescPrefix, 0u);  // before block 0: prefix 0
-                    if (idx >= 0) {
-                        do {
-                            d = desc[idx];
-                        } while ((unsigned)(d >> 34) != (epoch & 0x3fffffffu) || ((d >> 32) & 3ull) == 0ull);
+    // ---- explicit variates: rank of this env among the reset envs in ascending env order (== reset_buf.nonzero() order),
+    //      the index into spawn_perm (randperm(len)[:K] assigned in that order, randomizations.py:22).  The in-kernel
+    //      generator needs no rank: its spawn draw is a keyed permutation of [0, n_spawns) evaluated at the ENV ID -- K
+    //      distinct envs get K distinct rows, and a uniformly random permutation evaluated at K distinct points has
+    //      exactly the distribution of randperm(len)[:K] -- so the cross-block prefix (a dependent load in front of the
+    //      reset chain; a look-back in the single-launch step) disappears.
+    int rank = 0;
+    if constexpr (!kRng) {
+        const unsigned ballot = __ballot_sync(0xffffffffu, reset);
+        if (lane == 0) warp_cnt[wid] = __popc(ballot);
+        if (!kFused) {
+            if (wid == 0) {
+                int acc = 0;
+                for (int b = lane; b < bid; b += 32) acc += O.block_reset_counts[b];
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) block_base = acc;
+            }
+            __syncthreads();
+        } else {
+            __syncthreads();
+            if (wid == 0) {
+                // decoupled look-back (single pass): publish this block's count, walk back over the predecessors' descriptors
+                // until one carries an inclusive prefix, publish our own.  Logical block ids are tickets, so every
+                // predecessor has started; descriptors are tagged with the launch epoch, so nothing is re-zeroed.
+                int cnt = 0;
+                for (int w = 0; w < ROVER_MDP_BLOCK / 32; ++w) cnt += warp_cnt[w];
+                volatile unsigned long long* desc = lookback;
+                int base = 0;
+                if (bid > 0) {
+                    if (lane == 0) desc[bid] = make_lookback(epoch, kDescAggregate, (unsigned)cnt);
+                    int look = bid - 1;
+                    while (true) {
+                        const int idx = look - lane;
+                        unsigned long long d = make_lookback(epoch, kDescPrefix, 0u);  // before block 0: prefix 0
+                        if (idx >= 0) {
+                            do {
+                                d = desc[idx];
+                            } while ((unsigned)(d >> 34) != (epoch & 0x3fffffffu) || ((d >> 32) & 3ull) == 0ull);
+                        }
+                        const bool is_prefix = ((d >> 32) & 3ull) == kDescPrefix;
+                        const unsigned pmask = __ballot_sync(0xffffffffu, is_prefix);
+                        const int first = pmask ? __ffs(pmask) - 1 : 32;  // closest predecessor with an inclusive prefix
+                        int v = (lane <= first) ? (int)(unsigned)(d & 0xffffffffull) : 0;
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        base += v;
+                        if (pmask) break;
+                        look -= 32;
                     }
-                    const bool is_prefix = ((d >> 32) & 3ull) == kDescPrefix;
-                    const unsigned pmask = __ballot_sync(0xffffffffu, is_prefix);
-                    const int first = pmask ? __ffs(pmask) - 1 : 32;  // closest predecessor with an inclusive prefix
-                    int v = (lane <= first) ? (int)(unsigned)(d & 0xffffffffull) : 0;
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    base += v;
-                    if (pmask) break;
-                    look -= 32;
+                }
+                if (lane == 0) {
+                    __threadfence();
+                    desc[bid] = make_lookback(epoch, kDescPrefix, (unsigned)(base + cnt));
+                    block_base = base;
                 }
             }
-            if (lane == 0) {
-                __threadfence();
-                desc[bid] = make_lookback(epoch, kDescPrefix, (unsigned)(base + cnt));
-                block_base = base;
-            }
+            __syncthreads();
         }
-        __syncthreads();
+        rank = block_base + __popc(ballot & ((1u << lane) - 1u));
+        for (int w = 0; w < wid; ++w) rank += warp_cnt[w];
+
     }
-    int rank = block_base + __popc(ballot & ((1u << lane) - 1u));
-    for (int w = 0; w < wid; ++w) rank += warp_cnt[w];
 
     float st[kStats];
 #pragma unroll
@@ -526,7 +535,7 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
         }
         if (reset && (phases & ROVER_PHASE_SPAWN)) {
             // -- reset_root_state_rover (randomizations.py:12-39)
-            if (kRng) spawn_idx = (long long)spawn_perm_at(make_spawn_perm_key(key, (uint32_t)T.n_spawns), (uint32_t)rank);
+            if (kRng) spawn_idx = (long long)spawn_perm_at(make_spawn_perm_key(key, (uint32_t)T.n_spawns), (uint32_t)i);
             else spawn_idx = __ldg(spawn_perm + rank);
             const float* sp = T.spawn + 3 * (size_t)spawn_idx;
             px = __ldg(sp);
@@ -702,7 +711,7 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
             if (threadIdx.x == 0) {
                 *done_counter = 0u;  // re-arm for the next launch
                 if (kRng) V.rng[1] = V.rng[1] + 1ull;  // next launch = next step of the variate streams
-                if (kFused) {        // fused step: next launch = next epoch, tickets from 0 again
+                if (kFused && !kRng) {  // fused step, explicit variates: next launch = next epoch, tickets from 0 again
                     lookback[n_blocks] = 0ull;
                     lookback[n_blocks + 1] = (unsigned long long)(epoch + 1u);
                 }
@@ -770,13 +779,17 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
     __shared__ int s_bid;
     __shared__ unsigned s_epoch;
     const int n_blocks = (int)gridDim.x;
-    if (threadIdx.x == 0) {
-        s_epoch = (unsigned)*reinterpret_cast<volatile unsigned long long*>(lookback + n_blocks + 1);
-        s_bid = (int)atomicAdd(lookback + n_blocks, 1ull);
+    int bid = (int)blockIdx.x;
+    unsigned epoch = 0u;
+    if constexpr (!kRng) {  // (the in-kernel generator needs no reset rank, hence no look-back and no ticket)
+        if (threadIdx.x == 0) {
+            s_epoch = (unsigned)*reinterpret_cast<volatile unsigned long long*>(lookback + n_blocks + 1);
+            s_bid = (int)atomicAdd(lookback + n_blocks, 1ull);
+        }
+        __syncthreads();
+        bid = s_bid;
+        epoch = s_epoch;
     }
-    __syncthreads();
-    const int bid = s_bid;
-    const unsigned epoch = s_epoch;
     const int i = bid * ROVER_MDP_BLOCK + threadIdx.x;
     if (i < n) {  // the post-step's rank-independent inputs: in flight while the pre-step part runs
         asm volatile("prefetch.global.L2 [%0];" ::"l"(root_pos_w + 3 * (size_t)i));
@@ -1005,8 +1018,9 @@ extern "C" int rover_mdp_step_v3(const float* new_actions, const float* force_ma
     ROVER_CHECK(n_envs >= 0, "rover_mdp_step: negative n_envs");
     if (n_envs == 0) return 0;
     ROVER_CHECK(params && (new_actions || !(pre_phases & ROVER_PRE_ACTIONS)) &&
-                    (force_matrix_w || !(pre_phases & ROVER_PRE_TERMS)) && lookback,
-                "rover_mdp_step: NULL argument");
+                    (force_matrix_w || !(pre_phases & ROVER_PRE_TERMS)) && variates &&
+                    (lookback || variates->rng_state),
+                "rover_mdp_step: NULL argument (lookback is needed with explicit variates)");
     ROVER_CHECK(params->num_bodies >= 0 && params->max_episode_length > 0, "rover_mdp_step: bad params");
     if (int rc = check_post_args(root_pos_w, root_quat_w, n_envs, params, tables, stats, scratch, obs, obs_stride, phases,
                                  "rover_mdp_step"))
@@ -1038,14 +1052,14 @@ extern "C" int rover_mdp_step_v3(const float* new_actions, const float* force_ma
 // The variates the kernels generate in registers, evaluated on the HOST by the same functions (rng.cuh): the oracle is
 // fed these, the kernel generates its own, and the two must agree bit for bit (tests/test_gpu_rng.py).
 extern "C" int rover_rng_variates(uint64_t seed, uint64_t step, int32_t n_envs, int32_t n_rounds, int32_t n_spawns,
-                                  int64_t* spawn_perm, float* yaw_u, float* heading_u, float* theta_u) {
+                                  int64_t* spawn_by_env, float* yaw_u, float* heading_u, float* theta_u) {
     using namespace rover;
     ROVER_CHECK(n_envs >= 0 && n_rounds >= 1 && n_spawns >= 1, "rover_rng_variates: bad sizes");
     const RngKey key = make_rng_key(seed, step);
-    if (spawn_perm != nullptr) {
+    if (spawn_by_env != nullptr) {
         const SpawnPermKey pk = make_spawn_perm_key(key, (uint32_t)n_spawns);
         const int k = n_envs < n_spawns ? n_envs : n_spawns;
-        for (int j = 0; j < k; ++j) spawn_perm[j] = (int64_t)spawn_perm_at(pk, (uint32_t)j);
+        for (int i = 0; i < k; ++i) spawn_by_env[i] = (int64_t)spawn_perm_at(pk, (uint32_t)i);
     }
     for (int i = 0; i < n_envs; ++i) {
         uint32_t w[4];

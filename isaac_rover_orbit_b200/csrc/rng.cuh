@@ -10,9 +10,12 @@
 // (seed, step, env, role): Philox4x32-10 (Salmon et al., SC'11; the generator behind curand / torch CUDA) with
 //   key     = (seed_lo, seed_hi)
 //   counter = (env, step_lo, step_hi, stream)      stream 0: {yaw, heading, -, -};  stream 1 + q: theta rounds 4q .. 4q+3
-// and the without-replacement spawn draw is a keyed bijection of [0, n_spawns) evaluated at the reset RANK (Kensler's
+// and the without-replacement spawn draw is a keyed bijection of [0, n_spawns) evaluated at the ENV ID (Kensler's
 // cycle-walking hash permutation: add key / multiply by an odd constant / xor-shift on the next power of two, repeated
 // until the value falls inside the range), keyed by Philox(counter = (0xffffffff, step_lo, step_hi, 0xffffffff)).
+// The reference assigns randperm(len)[:K] to the K reset envs in ascending order; a uniformly random permutation
+// evaluated at K distinct env ids has the same distribution (K distinct, uniformly drawn rows) and needs no reset rank --
+// no cross-block prefix sum in front of the reset chain.
 // The same functions are compiled for the host (rover_rng_variates) so that the oracle consumes identical numbers.
 #pragma once
 #include <stdint.h>
@@ -84,7 +87,7 @@ ROVER_HD SpawnPermKey make_spawn_perm_key(const RngKey& k, uint32_t n_spawns) {
     return p;
 }
 
-// row of the spawn table for reset rank j (j < n): a bijection of [0, n), so K ranks draw K distinct rows
+// row of the spawn table for env j (j < n): a bijection of [0, n), so K distinct envs draw K distinct rows
 ROVER_HD uint32_t spawn_perm_at(const SpawnPermKey& p, uint32_t j) {
     const uint32_t w = p.mask;
     uint32_t x = j;

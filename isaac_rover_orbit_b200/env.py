@@ -183,8 +183,8 @@ class RoverEnv:
     ``physics``: callable ``(env) -> None``, the stand-in for the PhysX stepping of rover_env.py:64-75.
     ``physics_needs_targets`` (default True): the callable reads the joint targets of this step, so the action term must
     have run before it -- ``step`` is then pre_step(ACTIONS), physics, pre_step(TERMS), post_step, scan (4 launches).
-    With ``False`` (a replayed / synthetic state source) or without physics the two pre-step phases run as ONE launch
-    after the state update: 3 launches per step.
+    With ``False`` (a replayed / synthetic state source) or without physics everything but the scan runs as ONE launch
+    after the state update (``rover_mdp_step_v3``): 2 launches per step.
     Random variates of the reset path come from the in-kernel counter-based generator keyed on ``seed`` (no torch
     generator call per step); ``set_variates`` feeds explicit arrays instead (parity tests).
     ``enable_cuda_graph()`` captures the whole step once; ``step`` then costs one action copy + one graph launch.
@@ -332,11 +332,22 @@ class RoverEnv:
             # -- counters, terminations, rewards (one launch; reads the PREVIOUS command like the reference)
             ops.mdp_pre_step(b, self._params, None, contact.force_matrix_w, phases=_lib.PRE_TERMS)
         else:
-            # the state source does not read the joint targets: action term + counters + terminations + rewards in ONE launch
+            # the state source does not read the joint targets: nothing has to run between the action term and the rest
             if self._physics is not None:
                 self._physics(self)
             term = self.action_manager.get_term()
-            term.process_actions(action, fused_terms_force=contact.force_matrix_w)
+            if self._variates is None:
+                # ONE launch: action term + counters + terminations + rewards + reset + command update + observation
+                # head + episode log.  The in-kernel spawn draw needs no reset rank, so nothing crosses blocks in front
+                # of the reset chain (rover_mdp_step_v3).
+                term.stage_actions(action)
+                ops.mdp_step(b, term._params, self.scene.terrain.handle, term.raw_actions, contact.force_matrix_w,
+                             robot.root_pos_w, robot.root_quat_w, obs=self.obs_buf, rng=self._rng,
+                             n_rounds=self.cfg.target_rounds)
+                self.action_manager.apply_action()
+                self._scan()
+                return
+            term.process_actions(action, fused_terms_force=contact.force_matrix_w)  # explicit variates: rank by pre-step
             self.action_manager.apply_action()
         # -- reset, command update, observation head, episode log (one launch; variates drawn in the kernel)
         self._post(_lib.PHASE_ALL, self.obs_buf)

@@ -49,6 +49,13 @@ class AckermannAction2:
     def processed_actions(self) -> torch.Tensor:
         return self._env._buf.processed_actions
 
+    def stage_actions(self, actions: torch.Tensor) -> None:
+        """``_raw_actions[:] = actions`` only (ackermann_actions.py:227): ``RoverEnv.step`` then runs the rest of
+        ``process_actions`` inside its single fused launch."""
+        if actions is not self._raw_actions:
+            self._raw_actions[:] = actions
+        self._env._terms_current = False
+
     def process_actions(self, actions: torch.Tensor, fused_terms_force: torch.Tensor | None = None):
         """ackermann_actions.py:226-229 (+ ORBIT ActionManager.process_action: prev_action <- action <- actions).
         ``fused_terms_force`` (``RoverEnv.step`` when nothing has to run between the action term and the reward /

@@ -386,7 +386,9 @@ class TerrainTablesHandle:
 class ResetRng:
     """``{seed, step}`` of the in-kernel variate generator (``RoverResetVariates.rng_state``): a CUDA int64[2] tensor the
     post-step launch reads and advances.  ``variates(n, rounds, n_spawns)`` evaluates, on the host, what the NEXT launch
-    will draw (``rover_rng_variates``; synchronises to read the step word) -- the parity tests feed that to the oracle."""
+    will draw (``rover_rng_variates``; synchronises to read the step word) -- ``(spawn_by_env, yaw_u, heading_u,
+    theta_u)``, all indexed by env id -- and the parity tests feed that to the oracle.  ``by_rank`` turns the spawn draw
+    into the rank-indexed ``spawn_perm`` of the explicit-variates interface for a given reset mask."""
 
     def __init__(self, seed: int, device, step: int = 0):
         self.device = torch.device(device)
@@ -402,6 +404,14 @@ class ResetRng:
         seed, step = self.peek()
         sp, yaw, head, theta = _lib.rng_variates(seed, step, n_envs, n_rounds, n_spawns)
         return torch.from_numpy(sp), torch.from_numpy(yaw), torch.from_numpy(head), torch.from_numpy(theta)
+
+    @staticmethod
+    def by_rank(spawn_by_env: torch.Tensor, reset_flags: torch.Tensor) -> torch.Tensor:
+        """``spawn_perm`` ``[N]`` of the explicit interface: entry j = the row of the j-th reset env (ascending ids)."""
+        ids = reset_flags.reshape(-1).bool().nonzero().squeeze(-1)
+        out = torch.zeros(reset_flags.numel(), dtype=torch.int64, device=spawn_by_env.device)
+        out[: ids.numel()] = spawn_by_env[ids.to(spawn_by_env.device)]
+        return out
 
 
 def mdp_pre_step(buf: MdpBuffers, params: _lib.MdpParams, actions: torch.Tensor | None,
@@ -469,10 +479,14 @@ def mdp_step(buf: MdpBuffers, params: _lib.MdpParams, tables: "TerrainTablesHand
              pre_phases: int = _lib.PRE_ACTIONS | _lib.PRE_TERMS, phases: int = _lib.PHASE_ALL, xchg=None,
              rng: ResetRng | None = None, n_rounds: int | None = None, log: bool = True):
     """``mdp_pre_step`` + ``mdp_post_step`` in ONE launch (``rover_mdp_step``): for loops whose physics does not sit
-    between the two.  Bit-identical to the two-launch sequence (``tests/test_gpu_parity.py``)."""
+    between the two.  Bit-identical to the two-launch sequence (``tests/test_gpu_parity.py``).  With ``rng=`` the spawn
+    draw needs no reset rank, so the launch has no cross-block dependency in front of the reset chain (explicit variates
+    keep the rank, by a decoupled look-back)."""
     dev = _lib.require_cuda(root_pos_w, root_quat_w, new_actions, force_matrix_w)
     if dev != buf.device or tables.device != dev:
         raise RuntimeError("mdp_step: tensors on different devices")
+    if (phases & _lib.PHASE_SPAWN) and tables.n_spawns < buf.n:
+        raise RuntimeError(f"mdp_step: spawn table has {tables.n_spawns} rows for {buf.n} envs")
     _require_f32("mdp_step", root_pos_w=root_pos_w, root_quat_w=root_quat_w, new_actions=new_actions,
                  force_matrix_w=force_matrix_w)
     n = buf.n

@@ -51,7 +51,8 @@ def _env_stream(seed: int, step: int, n_envs: int, stream: int) -> np.ndarray:
 
 
 def spawn_perm(seed: int, step: int, n_spawns: int, count: int) -> np.ndarray:
-    """Row of the spawn table for reset ranks ``0 .. count-1``: cycle-walking hash permutation of ``[0, n_spawns)``."""
+    """Row of the spawn table for envs ``0 .. count-1`` (taken if the env resets): cycle-walking hash permutation of
+    ``[0, n_spawns)`` evaluated at the env id."""
     ctr = np.array([[0xFFFFFFFF, step & 0xFFFFFFFF, (step >> 32) & 0xFFFFFFFF, 0xFFFFFFFF]], dtype=np.uint32)
     k = [int(v) for v in philox4x32_10(ctr, _key(seed))[0]]
     m = max(n_spawns - 1, 1)
@@ -74,7 +75,7 @@ def spawn_perm(seed: int, step: int, n_spawns: int, count: int) -> np.ndarray:
 
 
 def variates(seed: int, step: int, n_envs: int, n_rounds: int, n_spawns: int):
-    """``(spawn_perm [min(N, n_spawns)] int64, yaw_u [N], heading_u [N], theta_u [N, n_rounds])`` of one (seed, step)."""
+    """``(spawn_by_env [min(N, n_spawns)] int64, yaw_u [N], heading_u [N], theta_u [N, n_rounds])`` of one (seed, step)."""
     s0 = _env_stream(seed, step, n_envs, 0)
     theta = np.empty((n_envs, n_rounds), dtype=np.float32)
     for r0 in range(0, n_rounds, 4):

@@ -116,8 +116,11 @@ def resample_command(state: MdpState, ids, theta_u, heading_u, tables, c: RoverC
 
 
 def oracle_step(state: MdpState, actions, root_pos_w, root_quat_w, force_matrix_w, tables: TerrainTables,
-                spawn_perm, yaw_u, theta_u, heading_u, c: RoverConstants = AAU_ROVER) -> StepOutput:
-    """One env step; mutates ``state`` like the managers do.  Order = rover_env.py:61-102."""
+                spawn_perm, yaw_u, theta_u, heading_u, c: RoverConstants = AAU_ROVER, spawn_by_env=None) -> StepOutput:
+    """One env step; mutates ``state`` like the managers do.  Order = rover_env.py:61-102.
+    ``spawn_by_env`` (instead of ``spawn_perm``): the spawn row of env ``i`` if it resets -- a random permutation of the
+    table evaluated at the env ids; K reset envs draw K distinct uniformly random rows, the distribution of the
+    reference's ``randperm(len)[:K]`` (randomizations.py:22) without the dependence on the reset order."""
     n = actions.shape[0]
     max_len = c.max_episode_length
     dt = c.step_dt
@@ -164,7 +167,7 @@ def oracle_step(state: MdpState, actions, root_pos_w, root_quat_w, force_matrix_
     ids = reset.nonzero(as_tuple=False).squeeze(-1)
     k = len(ids)
     stats = {"num_resets": k, "target_rounds_exhausted": 0}
-    spawn_index = spawn_perm[:k].clone()
+    spawn_index = spawn_by_env[ids].clone() if spawn_by_env is not None else spawn_perm[:k].clone()
     if k > 0:
         # randomization "reset": reset_root_state_rover (randomizations.py:12-39)
         pos = tables.spawn_table[spawn_index].clone()

@@ -57,11 +57,10 @@ def test_kernel_rng_equals_explicit_variates_from_the_host_export(world, n, seed
         pa, qa = s.root_pos_w.clone(), s.root_quat_w.clone()
         pb, qb = s.root_pos_w.clone(), s.root_quat_w.clone()
         assert rng.peek() == (seed, 2 ** 32 - 2 + k)
-        sp, yaw, head, theta = (t.to(dev) for t in rng.variates(n, rounds, th.n_spawns))
-        sp_full = torch.zeros(n, dtype=torch.int64, device=dev)
-        sp_full[: sp.numel()] = sp
+        sp_env, yaw, head, theta = (t.to(dev) for t in rng.variates(n, rounds, th.n_spawns))
         for buf in (a, b):
             ops.mdp_pre_step(buf, params, s.actions, s.force_matrix_w)
+        sp_full = ops.ResetRng.by_rank(sp_env, b.reset_flags)  # explicit interface: rows by reset rank
         ops.mdp_post_step(a, params, th, pa, qa, obs=obs_a, rng=rng, n_rounds=rounds)
         ops.mdp_post_step(b, params, th, pb, qb, sp_full, yaw, head, theta, obs=obs_b)
         torch.cuda.synchronize()
@@ -104,8 +103,8 @@ def test_kernel_rng_against_the_oracle_and_single_launch(world):
     torch.cuda.synchronize()
     for name in STATE:
         assert torch.equal(getattr(bufs[0], name), getattr(bufs[1], name)), name
-    out = OS.oracle_step(ost, s.actions.cpu(), s.root_pos_w.cpu(), s.root_quat_w.cpu(), s.force_matrix_w.cpu(), otab, sp,
-                         yaw, theta, head)
+    out = OS.oracle_step(ost, s.actions.cpu(), s.root_pos_w.cpu(), s.root_quat_w.cpu(), s.force_matrix_w.cpu(), otab, None,
+                         yaw, theta, head, spawn_by_env=sp)
     ids = out.reset_ids
     assert len(ids) > 10
     got = bufs[0].spawn_index.cpu()

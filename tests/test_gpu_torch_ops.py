@@ -134,13 +134,13 @@ def test_env_step_graph_replay_equals_eager(world):
 
 
 def test_env_step_launch_count(world):
-    """``RoverEnv.step`` = 3 of our launches (pre_step(ACTIONS | TERMS), post_step, height scan) when nothing has to run
+    """``RoverEnv.step`` = 2 of our launches (the whole MDP step in one, then the height scan) when nothing has to run
     between the action term and the reward terms, 4 when the physics callable must see the joint targets -- plus ONE
     copy of the action into the term's ``raw_actions``; no generator, reduction or logging kernels."""
     from torch.profiler import ProfilerActivity, profile
 
     dev, tables = world["dev"], world["tables"]
-    for physics, want in ((None, 3), (lambda env: None, 4)):
+    for physics, want in ((None, 2), (lambda env: None, 4)):
         env = RoverEnv(RoverEnvCfg(num_envs=N), tables, dev, physics=physics, seed=1)
         env.reset()
         a = torch.zeros(N, 2, device=dev)

@@ -43,7 +43,7 @@ def test_host_export_equals_restatement(seed, step, n, rounds, spawns):
 def test_spawn_draw_is_a_permutation(spawns):
     for step in (0, 1, 12345):
         sp = _lib.rng_variates(11, step, spawns, 1, spawns)[0]
-        assert np.array_equal(np.sort(sp), np.arange(spawns)), "every row exactly once: sampling without replacement"
+        assert np.array_equal(np.sort(sp), np.arange(spawns)), "every row exactly once: distinct envs draw distinct rows"
     a = _lib.rng_variates(11, 0, spawns, 1, spawns)[0]
     b = _lib.rng_variates(11, 1, spawns, 1, spawns)[0]
     if spawns >= 31:
@@ -58,6 +58,6 @@ def test_variates_are_uniform_and_decorrelated():
     assert abs(float(np.corrcoef(theta[:, 0], theta[:, 1])[0, 1])) < 0.02
     _, yaw2, _, _ = _lib.rng_variates(5, 18, 65536, 8, 131072)
     assert abs(float(np.corrcoef(yaw, yaw2)[0, 1])) < 0.02, "consecutive steps"
-    # the first ranks of the spawn draw are spread over the table, not clustered
+    # the rows of the first envs are spread over the table, not clustered
     sp = _lib.rng_variates(5, 17, 4096, 1, 131072)[0]
     assert abs(float(sp.mean()) / 131072 - 0.5) < 0.03
