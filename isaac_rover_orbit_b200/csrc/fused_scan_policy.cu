@@ -121,6 +121,21 @@ __device__ __forceinline__ void fu_arrive(unsigned long long* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(b)) : "memory");
 }
 __device__ __forceinline__ void fu_epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// mbarrier wait of the roles that are NOT on the scan's critical path (issuer, epilogue group): poll, then sleep.  A
+// batch takes ~8 us to fill, their work ~2 us; a tight try_wait loop in 5 extra warps took issue slots from the scan
+// consumers sharing their schedulers (ncu, round 2: 46.0 M warp-instructions at 16384 envs against 32.3 M for the scan).
+__device__ __forceinline__ void fu_wait_relaxed(unsigned long long* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(sptr(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
 __device__ __forceinline__ void fu_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -295,8 +310,8 @@ fused_scan_encoder_kernel(const float* __restrict__ pos_w, const float* __restri
             // =============================== MMA issuer ===============================
             const uint32_t idesc = make_idesc(kFuBatch);
             const uint32_t acc = tmem + kFuAccCol;
-            mb_wait(&sm.w1_full, 0u);
-            mb_wait(&sm.w0_ready, 0u);  // W0 sits in TMEM columns [0, 488)
+            fu_wait_relaxed(&sm.w1_full, 0u);
+            fu_wait_relaxed(&sm.w0_ready, 0u);  // W0 sits in TMEM columns [0, 488)
             tc_fence_after();
             for (int b = 0; b < n_batches; ++b) {
                 const int buf = b & 1;
@@ -304,8 +319,8 @@ fused_scan_encoder_kernel(const float* __restrict__ pos_w, const float* __restri
                     const int missing = (n_batches * kFuBatch - n_iter) * kFuChunks;
                     for (int i = 0; i < missing; ++i) fu_arrive(&sm.obs_full[buf]);
                 }
-                if (b > 0) mb_wait(&sm.batch_done, (uint32_t)(b - 1) & 1u);  // the epilogues of batch b-1 have read TMEM
-                mb_wait(&sm.obs_full[buf], (uint32_t)(b >> 1) & 1u);
+                if (b > 0) fu_wait_relaxed(&sm.batch_done, (uint32_t)(b - 1) & 1u);  // the epilogues of batch b-1 have read TMEM
+                fu_wait_relaxed(&sm.obs_full[buf], (uint32_t)(b >> 1) & 1u);
                 tc_fence_after();
                 // ---- layer 0: D = W0 (TMEM) x obs^T (shared), K = 976 in 61 steps of 16 (8 TMEM columns each)
                 const uint32_t b0 = sptr(sm.obs[buf]);
@@ -313,7 +328,7 @@ fused_scan_encoder_kernel(const float* __restrict__ pos_w, const float* __restri
                     umma_ts(acc, tmem + ks * 8, make_desc(b0 + ks * 2 * kOperandLbo, kOperandLbo), idesc, ks != 0);
                 umma_commit(&sm.acc_full);
                 // ---- layer 1: D = W1 (shared) x A1^T (shared), K = 80; the accumulator columns are re-used
-                mb_wait(&sm.act_ready, (uint32_t)b & 1u);
+                fu_wait_relaxed(&sm.act_ready, (uint32_t)b & 1u);
                 tc_fence_after();
                 const uint32_t a1 = sptr(sm.w1), b1 = sptr(sm.act);
                 for (int j = 0; j < 80 / 16; ++j)
@@ -435,7 +450,7 @@ fused_scan_encoder_kernel(const float* __restrict__ pos_w, const float* __restri
         for (int b = 0; b < n_batches; ++b) {
             const int buf = b & 1;
             // ---- layer 0: D0 -> A1 (80 features); the observation head (k = 0..3 of the operand) is kept for the output
-            mb_wait(&sm.acc_full, acc_phase);
+            fu_wait_relaxed(&sm.acc_full, acc_phase);
             acc_phase ^= 1u;
             tc_fence_after();
             if (t >= 60 && t < 64) {  // (threads 60..63 write columns 60..63 of the encoder output below)
@@ -461,7 +476,7 @@ fused_scan_encoder_kernel(const float* __restrict__ pos_w, const float* __restri
                 fu_arrive(&sm.act_ready);
             }
             // ---- layer 1: -> encoder output row [e(60), obs[:, 0:4]] (bf16), the A operand of the MLP's first layer
-            mb_wait(&sm.acc_full, acc_phase);
+            fu_wait_relaxed(&sm.acc_full, acc_phase);
             acc_phase ^= 1u;
             tc_fence_after();
             {
