@@ -7,8 +7,8 @@
 //     up to one environment apart, and the per-ray store path recomputed a 64-bit address and a double select.
 //
 // What changes (same producer / mbarrier ring / 2-D tensor-map TMA loads as variant 4):
-//   * Work unit = chunk of 256 consecutive rays of one environment; the 14 consumer warps take chunks round-robin over
-//     the CTA's whole run (chunk K -> warp K mod 14), so lanes are 94 % used at 961 rays and every warp gets the same
+//   * Work unit = chunk of 256 consecutive rays of one environment; the 15 consumer warps take chunks round-robin over
+//     the CTA's whole run (chunk K -> warp K mod 15), so lanes are 94 % used at 961 rays and every warp gets the same
 //     number of chunks; a stage's `empty` barrier counts one arrival per chunk.
 //   * A lane resolves ray PAIRS (2k, 2k+1): the ray pattern sits in shared memory as three float arrays, so one LDS.64
 //     yields the same coordinate of both rays, and the whole ORBIT rotation chain, the window-relative cell coordinate
@@ -166,9 +166,9 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
         DBG_STAMP(2);
     } else {
         // =============================== consumers ===============================
-        // Work units (environment, chunk): chunk K of the CTA's run goes to warp K mod 14 (static deal).  With
+        // Work units (environment, chunk): chunk K of the CTA's run goes to warp K mod 15 (static deal).  With
         // ROVER_PAIR_DYNAMIC they are handed out in order from a shared counter instead; the phase-aliasing argument above
-        // holds either way (at most 14 units are outstanding, so when a warp holds a chunk of environment E at least 18
+        // holds either way (at most 15 units are outstanding, so when a warp holds a chunk of environment E at least 17
         // chunks of E-8 .. E-1 are finished, i.e. E-8 was issued and E-16 consumed).
 #if ROVER_PAIR_DYNAMIC
         int it = 0, c = 0;

@@ -42,9 +42,12 @@ __device__ __forceinline__ unsigned long long dbg_globaltimer() {
 #endif
 
 #ifndef ROVER_PAIR_WARPS
-#define ROVER_PAIR_WARPS 14
+#define ROVER_PAIR_WARPS 15
 #endif
-constexpr int kPairConsumerWarps = ROVER_PAIR_WARPS;  // 1 + 14 warps -> 16-warp register allocation -> 128 registers / thread
+// 1 producer + 15 consumer warps = 512 threads x 128 registers = the whole register file.  (Round 1 ran 14 consumers;
+// round 2, same box, profiles/time_scan_sizes.py: 15 consumers 21.5 / 56.3 / 184.3 us at 4096 / 16384 / 65536 envs against
+// 22.5 / 56.4 / 189.4 us for 14; 17 consumers at 96 registers spill and take 25.6 / 62.5 / 207.9 us.)
+constexpr int kPairConsumerWarps = ROVER_PAIR_WARPS;
 constexpr int kPairThreads = 32 * (1 + kPairConsumerWarps);
 constexpr int kPairStages = 8;          // ring depth (data)
 #ifndef ROVER_PAIR_EARLY
