@@ -411,6 +411,17 @@ int rover_mesh_to_heightmap(const float* vertices /* [V,3] */, const int32_t* fa
                             float* heightmap, int32_t* out_of_range, void* stream);
 int rover_steep_mask(const float* heightmap, int32_t rows, int32_t cols, double threshold, uint8_t* steep /* [rows, cols] */,
                      void* stream);
+/* The morphological clean-up that follows (terrain_utils.py:281-311; OpenCV + scipy in the reference):
+ * rover_morph_box = cv2.dilate / cv2.erode with a k x k box of ones on a 0/1 image (anchor k / 2, outside pixels neutral;
+ *   MORPH_CLOSE = dilate then erode, MORPH_OPEN = erode then dilate); src, tmp, dst [rows, cols] uint8, all distinct.
+ * rover_fill_holes = scipy.ndimage.binary_fill_holes (4-connected background flood from the border); `reach` [rows, cols]
+ *   uint8 and `changed` (1 int32) are device scratch.  This call synchronises the stream (it polls for convergence) -- it
+ *   is init-time code, not on the step path.  Both reproduce the library results bit for bit
+ *   (tests/test_gpu_terrain_build.py). */
+int rover_morph_box(const uint8_t* src, int32_t rows, int32_t cols, int32_t k, int32_t erode, uint8_t* tmp, uint8_t* dst,
+                    void* stream);
+int rover_fill_holes(const uint8_t* mask, int32_t rows, int32_t cols, uint8_t* reach, int32_t* changed, uint8_t* out,
+                     void* stream);
 
 #ifdef __cplusplus
 }

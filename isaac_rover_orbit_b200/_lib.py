@@ -28,7 +28,8 @@ SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_
            "rover_ackermann",
            "rover_policy_pack", "rover_policy_forward", "rover_value_forward", "rover_policy_forward_bf16",
            "rover_value_forward_bf16", "rover_gaussian_act", "rover_mesh_to_heightmap", "rover_steep_mask",
-           "rover_policy_pack_fused", "rover_scan_encoder_fused", "rover_policy_mlp_forward")
+           "rover_policy_pack_fused", "rover_scan_encoder_fused", "rover_policy_mlp_forward", "rover_morph_box",
+           "rover_fill_holes")
 
 
 class ScanLevel(C.Structure):
@@ -157,6 +158,10 @@ def load() -> C.CDLL:
     lib.rover_mesh_to_heightmap.argtypes = [vp, vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, i32, i32, vp, vp, vp]
     lib.rover_steep_mask.restype = C.c_int
     lib.rover_steep_mask.argtypes = [vp, i32, i32, C.c_double, vp, vp]
+    lib.rover_morph_box.restype = C.c_int
+    lib.rover_morph_box.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
+    lib.rover_fill_holes.restype = C.c_int
+    lib.rover_fill_holes.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     lib.rover_stats_read.restype = C.c_int
     lib.rover_stats_read.argtypes = [vp, i32, vp, vp]
     lib.rover_p2p_alloc.restype = C.c_int

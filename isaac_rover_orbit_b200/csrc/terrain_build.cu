@@ -68,6 +68,81 @@ steep_mask_kernel(const float* __restrict__ heightmap, int rows, int cols, doubl
     steep[(size_t)y * cols + x] = mag > threshold ? 1 : 0;
 }
 
+// terrain_utils.py:281-311: the morphological clean-up of the steep mask -- OpenCV box morphology and scipy
+// binary_fill_holes in the reference.  A k x k box is separable: one pass along x, one along y.  OpenCV semantics: the
+// anchor sits at k / 2, so the window covers offsets [-(k / 2), k - 1 - k / 2] (asymmetric for the 42 x 42 safety margin);
+// pixels outside the image never contribute (dilate) / never limit (erode).  Binary images: dilate = any, erode = all.
+__global__ void __launch_bounds__(256)
+morph_line_kernel(const uint8_t* __restrict__ src, int rows, int cols, int k, int vertical, int erode, uint8_t* __restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols) return;
+    const int lo = -(k / 2), hi = k - 1 - k / 2;
+    int hit = erode ? 1 : 0;
+    for (int o = lo; o <= hi; ++o) {
+        const int xx = vertical ? x : x + o, yy = vertical ? y + o : y;
+        if (xx < 0 || xx >= cols || yy < 0 || yy >= rows) continue;
+        const int v = __ldg(src + (size_t)yy * cols + xx) != 0;
+        hit = erode ? (hit & v) : (hit | v);
+    }
+    dst[(size_t)y * cols + x] = (uint8_t)hit;
+}
+
+// scipy.ndimage.binary_fill_holes: the complement of the background connected (4-neighbourhood) to the image border.
+// reach = 1 on background pixels already known to connect to the border.  One launch relaxes 32 x 32 tiles to their
+// local fixed point in shared memory (halo of one pixel) and raises *changed when a tile changed; the host repeats the
+// launch until nothing changes (path lengths are counted in tiles, not pixels).
+constexpr int kFillTile = 32;
+__global__ void __launch_bounds__(kFillTile * kFillTile)
+fill_reach_kernel(const uint8_t* __restrict__ mask, uint8_t* __restrict__ reach, int rows, int cols, int* __restrict__ changed) {
+    __shared__ uint8_t r[kFillTile + 2][kFillTile + 2];
+    __shared__ int tile_changed, any_changed;
+    const int tx = threadIdx.x % kFillTile, ty = threadIdx.x / kFillTile;
+    const int x = blockIdx.x * kFillTile + tx, y = blockIdx.y * kFillTile + ty;
+    const bool in = x < cols && y < rows;
+    const bool open = in && __ldg(mask + (size_t)y * cols + x) == 0;
+    auto load = [&](int yy, int xx) -> uint8_t {
+        return (xx >= 0 && xx < cols && yy >= 0 && yy < rows) ? reach[(size_t)yy * cols + xx] : (uint8_t)0;
+    };
+    r[ty + 1][tx + 1] = in ? reach[(size_t)y * cols + x] : (uint8_t)0;
+    if (ty == 0) r[0][tx + 1] = load(y - 1, x);
+    if (ty == kFillTile - 1) r[kFillTile + 1][tx + 1] = load(y + 1, x);
+    if (tx == 0) r[ty + 1][0] = load(y, x - 1);
+    if (tx == kFillTile - 1) r[ty + 1][kFillTile + 1] = load(y, x + 1);
+    if (threadIdx.x == 0) any_changed = 0;
+    __syncthreads();
+    const uint8_t before = r[ty + 1][tx + 1];
+    for (int it = 0; it < 2 * kFillTile * kFillTile; ++it) {
+        if (threadIdx.x == 0) tile_changed = 0;
+        __syncthreads();
+        if (open && !r[ty + 1][tx + 1] && (r[ty][tx + 1] | r[ty + 2][tx + 1] | r[ty + 1][tx] | r[ty + 1][tx + 2])) {
+            r[ty + 1][tx + 1] = 1;
+            tile_changed = 1;
+        }
+        __syncthreads();
+        if (!tile_changed) break;
+        __syncthreads();
+    }
+    if (in && r[ty + 1][tx + 1] != before) {
+        reach[(size_t)y * cols + x] = 1;
+        any_changed = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && any_changed) *changed = 1;
+}
+
+// reach seed: background pixels on the image border; and the final composition filled = !reach
+__global__ void fill_seed_kernel(const uint8_t* __restrict__ mask, uint8_t* __restrict__ reach, int rows, int cols) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * cols) return;
+    const int y = (int)(i / cols), x = (int)(i % cols);
+    const bool border = x == 0 || y == 0 || x == cols - 1 || y == rows - 1;
+    reach[i] = (border && mask[i] == 0) ? 1 : 0;
+}
+__global__ void fill_finish_kernel(const uint8_t* __restrict__ reach, uint8_t* __restrict__ out, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = reach[i] ? 0 : 1;
+}
+
 }  // namespace rover
 
 using namespace rover;
@@ -91,4 +166,38 @@ extern "C" int rover_steep_mask(const float* heightmap, int32_t rows, int32_t co
     steep_mask_kernel<<<dim3((cols + 255) / 256, rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(heightmap, rows, cols,
                                                                                                   threshold, steep);
     return check_launch("steep_mask_kernel");
+}
+
+extern "C" int rover_morph_box(const uint8_t* src, int32_t rows, int32_t cols, int32_t k, int32_t erode, uint8_t* tmp,
+                               uint8_t* dst, void* stream) {
+    using namespace rover;
+    ROVER_CHECK(src && tmp && dst && rows > 0 && cols > 0 && k >= 1, "rover_morph_box: bad arguments");
+    ROVER_CHECK(src != dst && src != tmp && tmp != dst, "rover_morph_box: src, tmp and dst must be distinct buffers");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const dim3 grid((cols + 255) / 256, rows);
+    morph_line_kernel<<<grid, 256, 0, s>>>(src, rows, cols, k, 0, erode, tmp);
+    morph_line_kernel<<<grid, 256, 0, s>>>(tmp, rows, cols, k, 1, erode, dst);
+    return check_launch("morph_line_kernel");
+}
+
+extern "C" int rover_fill_holes(const uint8_t* mask, int32_t rows, int32_t cols, uint8_t* reach /* scratch */,
+                                int32_t* changed /* device scratch, 1 int */, uint8_t* out, void* stream) {
+    using namespace rover;
+    ROVER_CHECK(mask && reach && changed && out && rows > 0 && cols > 0, "rover_fill_holes: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t n = (size_t)rows * cols;
+    fill_seed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mask, reach, rows, cols);
+    const dim3 grid((cols + kFillTile - 1) / kFillTile, (rows + kFillTile - 1) / kFillTile);
+    // init-time code: the host polls the convergence flag every 4 relaxation launches (a tile relaxes to its local fixed
+    // point per launch, so the launch count grows with the longest background path measured in tiles)
+    for (int round = 0; round < 100000; ++round) {
+        ROVER_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), s));
+        for (int rep = 0; rep < 4; ++rep) fill_reach_kernel<<<grid, kFillTile * kFillTile, 0, s>>>(mask, reach, rows, cols, changed);
+        int h = 0;
+        ROVER_CUDA(cudaMemcpyAsync(&h, changed, sizeof(int), cudaMemcpyDeviceToHost, s));
+        ROVER_CUDA(cudaStreamSynchronize(s));
+        if (!h) break;
+    }
+    fill_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reach, out, n);
+    return check_launch("fill_holes");
 }

@@ -192,7 +192,23 @@ def steep_mask(heightmap: np.ndarray, threshold: float = GRADIENT_THRESHOLD, dev
 def find_rocks_in_heightmap(heightmap: np.ndarray, threshold: float = GRADIENT_THRESHOLD, device="cpu"):
     """terrain_utils.py:265-311: Sobel gradient magnitude (wrap boundary) > threshold, then
     close 3x3 -> fill holes -> open 7x7 -> dilate 11x11 (= rock mask) -> dilate 42x42 (= safe mask).
-    ``device``: where the gradient stencil runs (``steep_mask``); the morphology is OpenCV / scipy on the host."""
+    On a CUDA ``device`` the whole chain runs on the GPU (``csrc/terrain_build.cu``: the gradient stencil, separable box
+    morphology with OpenCV's anchor convention, a tiled flood fill for ``binary_fill_holes``); on the host it is the
+    reference's own OpenCV / scipy calls.  Same masks bit for bit (tests/test_gpu_terrain_build.py)."""
+    dev = torch.device(device)
+    if dev.type == "cuda":
+        from . import torch_ops  # noqa: F401  (registers torch.ops.rover_b200)
+
+        R = torch.ops.rover_b200
+        with torch.cuda.device(dev):
+            hm = torch.from_numpy(np.ascontiguousarray(heightmap, dtype=np.float32)).to(dev)
+            m = R.steep_mask(hm, float(threshold))
+            m = R.morph_box(R.morph_box(m, 3, False), 3, True)      # MORPH_CLOSE = dilate, erode
+            m = R.fill_holes(m)
+            m = R.morph_box(R.morph_box(m, 7, True), 7, False)      # MORPH_OPEN = erode, dilate
+            rock = R.morph_box(m, 11, False)
+            safe = R.morph_box(rock, 42, False)
+            return rock.cpu().numpy(), safe.cpu().numpy()
     import cv2
     from scipy import ndimage
 
@@ -210,9 +226,11 @@ def random_rover_spawns(rock_mask: np.ndarray, heightmap: np.ndarray, min_x: flo
                         resolution: float = HEIGHTMAP_RESOLUTION, border_offset: float = SPAWN_BORDER_OFFSET,
                         seed: int | None = SPAWN_SEED) -> np.ndarray:
     """terrain_utils.py:330-385: legacy ``np.random.seed(seed)``; per spawn draw ``x, y = randint(lo, hi)``
-    until ``rock_mask[y, x] == 0``; row = ``(x*res + min_x, y*res + min_y, heightmap[y, x])`` in fp32."""
-    if seed is not None:
-        np.random.seed(seed)
+    until ``rock_mask[y, x] == 0``; row = ``(x*res + min_x, y*res + min_y, heightmap[y, x])`` in fp32.
+    The reference draws one candidate per Python iteration; here candidates are drawn in blocks -- the legacy
+    ``RandomState.randint`` stream is the same whether it is consumed by scalar calls or as an ``(M, 2)`` array
+    (checked in tests/test_oracle_golden.py against the reference's table) -- and the first ``n_spawns`` accepted
+    ones, in order, are kept.  The global generator is left exactly where the reference's loop would leave it."""
     height, width = rock_mask.shape
     lo = int(border_offset / resolution)
     hi = int(min(height, width) - lo)
@@ -220,17 +238,31 @@ def random_rover_spawns(rock_mask: np.ndarray, heightmap: np.ndarray, min_x: flo
         raise AssertionError(f"max_xy ({hi}) must be less than width/height ({width}, {height})")
     if hi <= lo:
         raise ValueError("terrain too small for the spawn border offset")
+    if seed is not None:
+        np.random.seed(seed)
+    state0 = np.random.get_state()
+    xs, ys, consumed, accepted = [], [], 0, 0
+    while accepted < n_spawns:
+        block = max(2 * (n_spawns - accepted), 1024)
+        cand = np.random.randint(lo, hi, size=(block, 2))
+        ok = rock_mask[cand[:, 1], cand[:, 0]] == 0
+        idx = np.nonzero(ok)[0][: n_spawns - accepted]
+        xs.append(cand[idx, 0])
+        ys.append(cand[idx, 1])
+        accepted += len(idx)
+        if accepted >= n_spawns:
+            consumed += int(idx[-1]) + 1 if len(idx) else block
+        else:
+            consumed += block
+            if not ok.any() and consumed > 50_000_000:
+                raise RuntimeError("no valid spawn location found (mask covers the spawn area)")
+    # leave the legacy generator where the reference's scalar loop would: `consumed` (x, y) pairs after the seed
+    np.random.set_state(state0)
+    if consumed:
+        np.random.randint(lo, hi, size=(consumed, 2))
+    x, y = np.concatenate(xs), np.concatenate(ys)
     out = np.zeros((n_spawns, 3), dtype=np.float32)
-    randint = np.random.randint
-    for i in range(n_spawns):
-        while True:
-            x = randint(lo, hi)
-            y = randint(lo, hi)
-            if rock_mask[y, x] == 0:
-                out[i, 0] = x
-                out[i, 1] = y
-                out[i, 2] = heightmap[y, x]
-                break
+    out[:, 0], out[:, 1], out[:, 2] = x, y, heightmap[y, x]
     out[:, 0] = out[:, 0] * resolution + min_x
     out[:, 1] = out[:, 1] * resolution + min_y
     return out

@@ -61,6 +61,9 @@ _SCHEMAS = {
     "mesh_to_heightmap": "(Tensor vertices, Tensor faces, float min_x, float min_y, float cell_x, float cell_y, "
                          "Tensor(a!) heightmap, Tensor(b!) out_of_range) -> ()",
     "steep_mask": "(Tensor heightmap, float threshold) -> Tensor",
+    # ---- morphology of the rock masks (terrain_utils.py:281-311)
+    "morph_box": "(Tensor mask, int k, bool erode) -> Tensor",
+    "fill_holes": "(Tensor mask) -> Tensor",
 }
 for _name, _schema in _SCHEMAS.items():
     _DEF.define(_name + _schema)
@@ -348,13 +351,35 @@ def _steep_mask(heightmap, threshold):
     return out
 
 
+def _u8_image(what, t):
+    if t.dtype != torch.uint8 or t.dim() != 2 or not t.is_contiguous():
+        raise RuntimeError(f"rover_b200::{what}: a contiguous uint8 [rows, cols] image is required")
+
+
+def _morph_box(mask, k, erode):
+    _u8_image("morph_box", mask)
+    tmp, out = torch.empty_like(mask), torch.empty_like(mask)
+    _lib.check(_lib.load().rover_morph_box(_p(mask), mask.shape[0], mask.shape[1], int(k), int(bool(erode)), _p(tmp), _p(out),
+                                            _stream(mask)))
+    return out
+
+
+def _fill_holes(mask):
+    _u8_image("fill_holes", mask)
+    reach, out = torch.empty_like(mask), torch.empty_like(mask)
+    changed = torch.zeros(1, dtype=torch.int32, device=mask.device)
+    _lib.check(_lib.load().rover_fill_holes(_p(mask), mask.shape[0], mask.shape[1], _p(reach), _p(changed), _p(out),
+                                             _stream(mask)))
+    return out
+
+
 _IMPLS = {
     "height_scan": _height_scan, "height_scan_out": _height_scan_out, "height_scan_hits": _height_scan_hits,
     "height_scan_obs": _height_scan_obs, "ackermann": _ackermann, "mdp_pre_step": _mdp_pre_step,
     "mdp_post_step": _mdp_post_step, "mdp_step": _mdp_step, "stats_read": _stats_read, "policy_pack": _policy_pack,
     "policy_forward": _policy_forward, "gaussian_act": _gaussian_act, "policy_pack_fused": _policy_pack_fused,
     "scan_encoder_fused": _scan_encoder_fused, "policy_mlp_forward": _policy_mlp_forward, "mesh_to_heightmap": _mesh_to_heightmap,
-    "steep_mask": _steep_mask,
+    "steep_mask": _steep_mask, "morph_box": _morph_box, "fill_holes": _fill_holes,
 }
 for _name, _fn in _IMPLS.items():
     _IMPL.impl(_name, _fn)
@@ -405,6 +430,16 @@ def _(mean, log_std, eps):
 @_fake("steep_mask")
 def _(heightmap, threshold):
     return heightmap.new_empty(heightmap.shape, dtype=torch.uint8)
+
+
+@_fake("morph_box")
+def _(mask, k, erode):
+    return torch.empty_like(mask)
+
+
+@_fake("fill_holes")
+def _(mask):
+    return torch.empty_like(mask)
 
 
 def _fake_none(*args, **kwargs):

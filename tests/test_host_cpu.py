@@ -342,3 +342,18 @@ def test_oracle_raycast_against_independent_float64_geometry():
     assert torch.isinf(h3).all()
     h4 = pm.raycast(torch.tensor(o32, dtype=torch.float32), torch.tensor(-d32, dtype=torch.float32), 100.0)
     assert torch.isinf(h4).all()
+
+
+def test_plane_cells_torch_port_equals_numpy_builder():
+    """The device builder of the plane-cell table (plane_cells.build_plane_cells_torch) is a line-by-line port of the host
+    builder: on the CPU device it must reproduce it bit for bit (the B200 run of the same check: test_gpu_terrain_build)."""
+    from isaac_rover_orbit_b200.plane_cells import build_plane_cells_torch
+
+    v, f = TR.make_synthetic_terrain(24.0, 0.2, seed=2)
+    f2 = np.delete(f, [3, 4, 500], axis=0)
+    f2[7] = f2[7][[0, 2, 1]]
+    plane = np.array([[-50, -50, 0], [50, -50, 1], [50, 50, 2], [-50, 50, 3]], dtype=np.float32)
+    for vv, ff in ((v, f), (v, f2), (plane, np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32))):
+        a, b = build_plane_cells(vv, ff), build_plane_cells_torch(vv, ff, "cpu")
+        assert b is not None and torch.equal(a.entries, b.entries) and torch.equal(a.xs, b.xs) and torch.equal(a.ys, b.ys)
+        assert (a.n_general, a.n_empty, a.inv_dx, a.inv_dy) == (b.n_general, b.n_empty, b.inv_dx, b.inv_dy)
