@@ -360,20 +360,9 @@ fused_scan_encoder_kernel(const float* __restrict__ pos_w, const float* __restri
             if (c == 0 && lane < kOperandHead)  // the head of the observation (written by the post-step kernel): k = lane
                 *reinterpret_cast<__nv_bfloat16*>(operand_row + lane * 2) = __float2bfloat16_rn(obs_row[lane]);
             if (h.mode == 1) {
-                PairCtx cx;
                 const float sz2 = __fmul_rn(h.sz, 2.f);
-                const float wx0 = sm.xpair[h.ic0].lo, wy0 = sm.ypair[h.jr0].lo;
-                cx.CW = dup(h.cw), cx.SZ = dup(h.sz), cx.NSZ = dup(-h.sz), cx.S2 = dup(sz2), cx.NS2 = dup(-sz2);
-                cx.PX = dup(h.px), cx.PY = dup(h.py), cx.PZ = dup(h.pz);
-                cx.NWX0 = dup(-wx0), cx.NWY0 = dup(-wy0), cx.IDX = dup(pc.inv_dx), cx.IDY = dup(pc.inv_dy);
-                cx.MAGIC = dup(kFloorMagic), cx.BASE = dup(base_offset);
-                cx.NEG0 = dup(__uint_as_float(0x80000000u | (unsigned)(n_envs >> 31)));  // -0.0, opaque to the compiler
-                cx.pz = h.pz, cx.max_d = max_d;
-                cx.ZFLAT = dup(__fadd_rn(sm.vz0, h.pz));
-                cx.cmax = (uint32_t)(h.ncols - 1), cx.rmax = (uint32_t)(h.nrows - 1);
-                cx.xoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.xpair + h.ic0) - smem_raw);
-                cx.yoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.ypair + h.jr0) - smem_raw);
-                cx.eoff = (uint32_t)(reinterpret_cast<const unsigned char*>(st.p) - smem_raw);
+                const PairCtx cx = make_pair_ctx(h, sm, st, smem_raw, pc.inv_dx, pc.inv_dy, base_offset, max_d, sm.vz0,
+                                                 n_envs >> 31);
                 constexpr int kSink = kWriteObs ? kSinkOperandAndGlobal : kSinkOperand;
                 for (int b0 = r_begin; b0 < r_end; b0 += kPairBatch) {
                     const int r = b0 + lane;  // rays r, r + 64 (slot 0) and r + 32, r + 96 (slot 1)

@@ -22,6 +22,9 @@
 // the same out-of-line global-memory helpers as variant 4, so the staging can never change a result.
 #include "scan_paired.cuh"
 
+#ifndef ROVER_PAIR_CTX_FROM_PRODUCER
+#define ROVER_PAIR_CTX_FROM_PRODUCER 1  // 0: every consumer warp rebuilds the per-environment constants per chunk (round 1)
+#endif
 #ifndef ROVER_PAIR_DYNAMIC
 #define ROVER_PAIR_DYNAMIC 0  // 1: work units handed out from a shared counter instead of the static round-robin deal.
                               // Measured on a B200 (round 2, same box, profiles/time_scan_sizes.py): 22.5 / 59.4 / 200.7 us at
@@ -156,7 +159,12 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
                     }
                     st.hdr = {cur.cw, cur.sz, cur.px, cur.py, cur.pz, cur.ic0, cur.jr0, cur.ncols, cur.nrows,
                               cur.ok ? 1 : 0, 0, 0};
-                    bar_arrive(full);  // header published (release)
+                    // the consumers' per-environment constants, ready to load (a staged window implies that the line
+                    // tables are in shared memory; vz[0] stands for every ray's z on flat patterns, the only users)
+                    if (cur.ok)
+                        st.ctx = make_pair_ctx(st.hdr, sm, st, smem_raw, pc.inv_dx, pc.inv_dy, base_offset, max_d, sm.vz[0],
+                                               n_envs >> 31);
+                    bar_arrive(full);  // header + context published (release)
                 }
                 // environments must be issued IN ORDER (the phase-aliasing argument above relies on it): without this
                 // the lanes run ahead independently and a later environment whose stage drains first overtakes
@@ -207,20 +215,13 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
                 bf_row[lane - head_cols] = __float2bfloat16_rn(out_row[lane - head_cols]);
             if (ROVER_SCAN_DBG == 1) {
             } else if (h.mode == 1) {
-                PairCtx cx;
-                const float sz2 = __fmul_rn(h.sz, 2.f);  // fl(fl(sz*v)*2) == fl(fl(2*sz)*v): scaling by 2 is exact
-                const float wx0 = sm.xpair[h.ic0].lo, wy0 = sm.ypair[h.jr0].lo;
-                cx.CW = dup(h.cw), cx.SZ = dup(h.sz), cx.NSZ = dup(-h.sz), cx.S2 = dup(sz2), cx.NS2 = dup(-sz2);
-                cx.PX = dup(h.px), cx.PY = dup(h.py), cx.PZ = dup(h.pz);
-                cx.NWX0 = dup(-wx0), cx.NWY0 = dup(-wy0), cx.IDX = dup(pc.inv_dx), cx.IDY = dup(pc.inv_dy);
-                cx.MAGIC = dup(kFloorMagic), cx.BASE = dup(base_offset);
-                cx.NEG0 = dup(__uint_as_float(0x80000000u | (unsigned)(n_envs >> 31)));  // -0.0, opaque to the compiler
-                cx.pz = h.pz, cx.max_d = max_d;
-                cx.ZFLAT = dup(__fadd_rn(sm.vz[0], h.pz));
-                cx.cmax = (uint32_t)(h.ncols - 1), cx.rmax = (uint32_t)(h.nrows - 1);
-                cx.xoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.xpair + h.ic0) - smem_raw);
-                cx.yoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.ypair + h.jr0) - smem_raw);
-                cx.eoff = (uint32_t)(reinterpret_cast<const unsigned char*>(st.p) - smem_raw);
+#if ROVER_PAIR_CTX_FROM_PRODUCER
+                const PairCtx cx = st.ctx;  // ten LDS.128: built once per environment by the producer
+#else
+                const PairCtx cx = make_pair_ctx(h, sm, st, smem_raw, pc.inv_dx, pc.inv_dy, base_offset, max_d, sm.vz[0],
+                                                 n_envs >> 31);
+#endif
+                const float sz2 = __fmul_rn(h.sz, 2.f);
                 for (int b0 = r_begin; b0 < r_end; b0 += kPairBatch) {
                     const int r = b0 + lane;  // rays r, r + 64 (slot 0) and r + 32, r + 96 (slot 1)
                     float* __restrict__ o = out_row + r;

@@ -92,6 +92,22 @@ struct PairHeader {
     int nrows, mode, pad0, pad1;  // mode 1: window staged in shared memory, 0: read the table from global memory
 };
 
+// ---- packed fp32 pairs (one 64-bit register pair; lo = ray 2k, hi = ray 2k+1)
+typedef unsigned long long f32x2;
+
+// The constants of the consumer loop for one environment, ready to load: (v, v) register pairs for the packed-fp32
+// chain and the shared-memory offsets of the window.  PUBLISHED BY THE PRODUCER with the header (variant 5): a consumer
+// warp used to rebuild them from the header for every 256-ray chunk -- 4 x ~70 of the ~2070 warp-instructions an
+// environment costs (13 %, profiles/r01_scan_v5_paired.md); now it is ten LDS.128.
+struct __align__(16) PairCtx {
+    f32x2 CW, SZ, NSZ, S2, NS2, PX, PY, PZ, NWX0, NWY0, IDX, IDY, MAGIC, BASE, NEG0, ZFLAT;
+    float pz, max_d;
+    uint32_t xoff, yoff, eoff;  // byte offsets into shared memory of the window's line pairs / p plane
+    uint32_t cmax, rmax;        // last column / row of the window
+    uint32_t pad;
+};
+static_assert(sizeof(PairCtx) == 160, "PairCtx is loaded as ten 16-byte words");
+
 // Planes of the window: p[row][col] = (a, b, c, k), q[row][col] = (A, B, C, tag) of cell (jr0 + row, ic0 + col).
 // (With the interleaved 32-byte entries of the other variants every LDS.128 of a quarter-warp could reach only the
 // even 16-byte bank groups: 2.5x the minimum number of shared-memory wavefronts, measured with ncu.)
@@ -99,6 +115,7 @@ struct __align__(128) PairStage {
     float4 p[kPairPlane];
     float4 q[kPairPlane];
     PairHeader hdr;
+    PairCtx ctx;  // valid when hdr.mode == 1 and the producer publishes it (variant 5)
 };
 static_assert(offsetof(PairStage, q) == kPairPlane * 16, "planes must be contiguous: one 3-D TMA box fills both");
 
@@ -147,9 +164,6 @@ __device__ __forceinline__ void tma_load_window_planar(void* dst, const CUtensor
         : "memory");
 }
 
-// ---- packed fp32 pairs (one 64-bit register pair; lo = ray 2k, hi = ray 2k+1)
-typedef unsigned long long f32x2;
-
 __device__ __forceinline__ f32x2 pk(float lo, float hi) {
     f32x2 r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -192,13 +206,29 @@ __device__ __forceinline__ f32x2 add2_rm(f32x2 a, f32x2 b) {  // round toward -i
     return r;
 }
 
-// per-chunk constants of the consumer loop
-struct PairCtx {
-    f32x2 CW, SZ, NSZ, S2, NS2, PX, PY, PZ, NWX0, NWY0, IDX, IDY, MAGIC, BASE, NEG0, ZFLAT;
-    float pz, max_d;
-    uint32_t xoff, yoff, eoff;  // byte offsets into shared memory of the window's line pairs / p plane
-    uint32_t cmax, rmax;        // last column / row of the window
-};
+// The context of one environment, built from its header (producer side of variant 5; per chunk in the fused kernel).
+// smem_base: address of the dynamic shared memory the offsets are relative to.
+template <class SM>
+__device__ __forceinline__ PairCtx make_pair_ctx(const PairHeader& h, const SM& sm, const PairStage& st,
+                                                 const unsigned char* smem_base, float inv_dx, float inv_dy, float base_offset,
+                                                 float max_d, float vz0, int opaque_zero) {
+    PairCtx cx;
+    const float sz2 = __fmul_rn(h.sz, 2.f);  // fl(fl(sz*v)*2) == fl(fl(2*sz)*v): scaling by 2 is exact
+    const float wx0 = sm.xpair[h.ic0].lo, wy0 = sm.ypair[h.jr0].lo;
+    cx.CW = dup(h.cw), cx.SZ = dup(h.sz), cx.NSZ = dup(-h.sz), cx.S2 = dup(sz2), cx.NS2 = dup(-sz2);
+    cx.PX = dup(h.px), cx.PY = dup(h.py), cx.PZ = dup(h.pz);
+    cx.NWX0 = dup(-wx0), cx.NWY0 = dup(-wy0), cx.IDX = dup(inv_dx), cx.IDY = dup(inv_dy);
+    cx.MAGIC = dup(kFloorMagic), cx.BASE = dup(base_offset);
+    cx.NEG0 = dup(__uint_as_float(0x80000000u | (unsigned)opaque_zero));  // -0.0, opaque to the compiler
+    cx.pz = h.pz, cx.max_d = max_d;
+    cx.ZFLAT = dup(__fadd_rn(vz0, h.pz));
+    cx.cmax = (uint32_t)(h.ncols - 1), cx.rmax = (uint32_t)(h.nrows - 1);
+    cx.xoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.xpair + h.ic0) - smem_base);
+    cx.yoff = (uint32_t)(reinterpret_cast<const unsigned char*>(sm.ypair + h.jr0) - smem_base);
+    cx.eoff = (uint32_t)(reinterpret_cast<const unsigned char*>(st.p) - smem_base);
+    cx.pad = 0u;
+    return cx;
+}
 
 // Rare path (a): a ray whose cell guess missed, that lies on the closed far border / outside the grid, or sits in a
 // general cell.  Out of line so that it does not raise the register pressure of the consumer loop.
