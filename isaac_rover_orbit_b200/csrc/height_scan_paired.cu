@@ -23,7 +23,12 @@
 #include "scan_paired.cuh"
 
 #ifndef ROVER_PAIR_CTX_FROM_PRODUCER
-#define ROVER_PAIR_CTX_FROM_PRODUCER 1  // 0: every consumer warp rebuilds the per-environment constants per chunk (round 1)
+#define ROVER_PAIR_CTX_FROM_PRODUCER 0  // 1: the producer publishes the consumers' per-environment constants (PairCtx) with
+                                        // the header and a consumer loads them (ten LDS.128) instead of rebuilding them per
+                                        // chunk (~13 % of an environment's instructions).  Measured on a B200 (round 2, same
+                                        // box): SLOWER, 25.4 / 63.4 / 209.8 us against 22.5 / 59.4 / 200.7 us at 4096 / 16384 /
+                                        // 65536 envs -- the loads sit on the chunk's critical path right after the barrier
+                                        // wait and the 40 live registers push the loop to 128 registers with spills.
 #endif
 #ifndef ROVER_PAIR_DYNAMIC
 #define ROVER_PAIR_DYNAMIC 0  // 1: work units handed out from a shared counter instead of the static round-robin deal.
@@ -161,9 +166,11 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
                               cur.ok ? 1 : 0, 0, 0};
                     // the consumers' per-environment constants, ready to load (a staged window implies that the line
                     // tables are in shared memory; vz[0] stands for every ray's z on flat patterns, the only users)
+#if ROVER_PAIR_CTX_FROM_PRODUCER
                     if (cur.ok)
                         st.ctx = make_pair_ctx(st.hdr, sm, st, smem_raw, pc.inv_dx, pc.inv_dy, base_offset, max_d, sm.vz[0],
                                                n_envs >> 31);
+#endif
                     bar_arrive(full);  // header + context published (release)
                 }
                 // environments must be issued IN ORDER (the phase-aliasing argument above relies on it): without this

@@ -95,10 +95,10 @@ struct PairHeader {
 // ---- packed fp32 pairs (one 64-bit register pair; lo = ray 2k, hi = ray 2k+1)
 typedef unsigned long long f32x2;
 
-// The constants of the consumer loop for one environment, ready to load: (v, v) register pairs for the packed-fp32
-// chain and the shared-memory offsets of the window.  PUBLISHED BY THE PRODUCER with the header (variant 5): a consumer
-// warp used to rebuild them from the header for every 256-ray chunk -- 4 x ~70 of the ~2070 warp-instructions an
-// environment costs (13 %, profiles/r01_scan_v5_paired.md); now it is ten LDS.128.
+// The constants of the consumer loop for one environment: (v, v) register pairs for the packed-fp32 chain and the
+// shared-memory offsets of the window.  A consumer warp builds them from the header for every 256-ray chunk (4 x ~70 of
+// the ~2070 warp-instructions an environment costs).  Having the PRODUCER publish them ready to load
+// (ROVER_PAIR_CTX_FROM_PRODUCER) was built and measured in round 2: slower (see height_scan_paired.cu).
 struct __align__(16) PairCtx {
     f32x2 CW, SZ, NSZ, S2, NS2, PX, PY, PZ, NWX0, NWY0, IDX, IDY, MAGIC, BASE, NEG0, ZFLAT;
     float pz, max_d;
@@ -115,7 +115,7 @@ struct __align__(128) PairStage {
     float4 p[kPairPlane];
     float4 q[kPairPlane];
     PairHeader hdr;
-    PairCtx ctx;  // valid when hdr.mode == 1 and the producer publishes it (variant 5)
+    PairCtx ctx;  // only with ROVER_PAIR_CTX_FROM_PRODUCER (valid when hdr.mode == 1)
 };
 static_assert(offsetof(PairStage, q) == kPairPlane * 16, "planes must be contiguous: one 3-D TMA box fills both");
 
