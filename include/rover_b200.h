@@ -295,6 +295,27 @@ int rover_mdp_step_v3(const float* new_actions, const float* force_matrix_w, flo
                       int32_t obs_stride, int32_t pre_phases, int32_t phases, const struct RoverStatsExchange* xchg,
                       void* stream);
 
+/* The WHOLE non-physics step in one launch: rover_mdp_step_v3 (in-kernel variates) + rover_height_scan (variant 5) as one
+ * persistent kernel.  One warp of every scan CTA runs the MDP step of the CTA's own environments, 32 at a time and one
+ * batch ahead of the scan, and hands each final root pose to the scan's producer warp through shared memory as soon as
+ * it is known; the MDP step's latency chain (three dependent cold misses, ~24 us as a launch of its own at 16384 envs)
+ * hides behind the scan.  Possible because the in-kernel spawn draw needs no reset rank: an env's step depends on that
+ * env only.  Replaces everything RoverEnv.step does outside PhysX (entrypoints/rover_env.py:61-102) when nothing has to
+ * run between the action term and the reward terms.
+ *   Same state / outputs / tables / rng_state as rover_mdp_step_v3; obs [N, obs_stride] receives the head (columns 0..3)
+ *   AND the heights (columns 4 .. 4 + n_rays).  scratch: DEVICE float [scratch_floats >= min(N, #SMs) * 16 + 1], zeroed
+ *   once, a buffer of its OWN (not the one passed to rover_mdp_post_step*).  Per-env results are bit-identical to
+ *   rover_mdp_step_v3 followed by rover_height_scan; the statistics are summed per CTA instead of per 64-env block
+ *   (same values up to fp32 summation order, still deterministic). */
+int rover_step_fused(const float* new_actions, const float* force_matrix_w, float* root_pos_w, float* root_quat_w,
+                     int32_t n_envs, const RoverMdpParams* params, const RoverMdpState* state, const RoverMdpOut* out,
+                     const RoverTerrainTables* tables, uint64_t* rng_state, int32_t n_rounds, int64_t* out_spawn_index,
+                     float* stats, float* scratch, int32_t scratch_floats, float* log_out, float* obs, int32_t obs_stride,
+                     int32_t pre_phases, int32_t phases, const struct RoverStatsExchange* xchg /* host, may be NULL */,
+                     const float* ray_starts_local, int32_t n_rays, const float* pattern_box /* host */,
+                     const RoverScanGrid* grid /* host */, const RoverPlaneCells* cells /* host */, float max_distance,
+                     float base_offset, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Multi-GPU episode statistics without a collective launch (the only cross-rank quantity on the path).
  * Each rank owns a MAILBOX with one slot per rank; the last block of rover_mdp_post_step_x adds the launch's 16

@@ -29,7 +29,7 @@ SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_
            "rover_policy_pack", "rover_policy_forward", "rover_value_forward", "rover_policy_forward_bf16",
            "rover_value_forward_bf16", "rover_gaussian_act", "rover_mesh_to_heightmap", "rover_steep_mask",
            "rover_policy_pack_fused", "rover_scan_encoder_fused", "rover_policy_mlp_forward", "rover_morph_box",
-           "rover_fill_holes")
+           "rover_fill_holes", "rover_step_fused")
 
 
 class ScanLevel(C.Structure):
@@ -146,6 +146,11 @@ def load() -> C.CDLL:
     lib.rover_mdp_step_v3.argtypes = [vp, vp, vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
                                       C.POINTER(TerrainTables), C.POINTER(ResetVariates), vp, vp, vp, vp, vp, vp, i32, i32,
                                       i32, C.POINTER(StatsExchange), vp]
+    lib.rover_step_fused.restype = C.c_int
+    lib.rover_step_fused.argtypes = [vp, vp, vp, vp, i32, C.POINTER(MdpParams), C.POINTER(MdpState), C.POINTER(MdpOut),
+                                     C.POINTER(TerrainTables), vp, i32, vp, vp, vp, i32, vp, vp, i32, i32, i32,
+                                     C.POINTER(StatsExchange), vp, i32, C.POINTER(C.c_float * 4), C.POINTER(ScanGrid),
+                                     C.POINTER(PlaneCells), f32, f32, vp]
     lib.rover_rng_variates.restype = C.c_int
     lib.rover_rng_variates.argtypes = [C.c_uint64, C.c_uint64, i32, i32, i32, vp, vp, vp, vp]
     lib.rover_philox4x32_10.restype = C.c_int

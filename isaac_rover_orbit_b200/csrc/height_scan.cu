@@ -142,7 +142,7 @@ height_scan_cells_kernel(const float* __restrict__ pos_w, const float* __restric
     }
 }
 
-static int make_dev_grid(const RoverScanGrid* grid, ScanGridDev& g) {
+int make_dev_grid(const RoverScanGrid* grid, ScanGridDev& g) {
     ROVER_CHECK(grid != nullptr, "rover_height_scan: grid is NULL");
     ROVER_CHECK(grid->n_levels >= 1 && grid->n_levels <= ROVER_MAX_LEVELS, "rover_height_scan: bad n_levels %d",
                 grid->n_levels);

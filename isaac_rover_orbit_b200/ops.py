@@ -340,6 +340,14 @@ class MdpBuffers:
                                                                                       device=device),
             f(_lib.STATS_LEN), f(max(blocks, 1) * _lib.STATS_LEN + 1), f(_lib.STATS_LEN))
 
+    @property
+    def scratch_fused(self) -> torch.Tensor:
+        """Scratch of ``step_fused`` (per-CTA statistics partials + completion counter): a buffer of its own."""
+        sc = self.__dict__.get("_scratch_fused")
+        if sc is None:
+            sc = self.__dict__["_scratch_fused"] = torch.zeros(256 * _lib.STATS_LEN + 1, dtype=torch.float32, device=self.device)
+        return sc
+
     def state_list(self) -> list:
         """The manager state as ``Tensor[]`` in ``RoverMdpState`` field order (argument of the custom ops)."""
         ls = self.__dict__.get("_state_list")
@@ -432,6 +440,29 @@ def mdp_pre_step(buf: MdpBuffers, params: _lib.MdpParams, actions: torch.Tensor 
         raise RuntimeError("mdp_pre_step: force_matrix_w must be fp32 [N,B,1,3]")
     torch.ops.rover_b200.mdp_pre_step(actions, force_matrix_w, params_desc(params), buf.state_list(), buf.out_list(),
                                       int(phases))
+
+
+def step_fused(buf: MdpBuffers, params: _lib.MdpParams, tables: "TerrainTablesHandle", new_actions: torch.Tensor | None,
+               force_matrix_w: torch.Tensor | None, root_pos_w: torch.Tensor, root_quat_w: torch.Tensor, rays,
+               grid: ScanGridHandle, obs: torch.Tensor, rng: "ResetRng", n_rounds: int = 16,
+               pre_phases: int = _lib.PRE_ACTIONS | _lib.PRE_TERMS, phases: int = _lib.PHASE_ALL, xchg=None, log: bool = True,
+               max_distance: float = 100.0, base_offset: float = 0.26878) -> None:
+    """The WHOLE non-physics step in ONE launch (``rover_step_fused``): ``mdp_step`` (in-kernel variates) + ``height_scan``
+    as one persistent kernel -- one warp of every scan CTA runs the MDP step of the CTA's environments a batch ahead of
+    the scan, so its latency hides behind the raycast.  ``obs`` ``[N, >= 4 + R]`` receives the head and the heights.
+    Per-env results are bit-identical to ``mdp_step(..., rng=)`` followed by ``height_scan``."""
+    if not isinstance(rays, RayPattern):
+        rays = RayPattern(rays, root_pos_w.device)
+    dev = _lib.require_cuda(root_pos_w, root_quat_w, new_actions, force_matrix_w)
+    if dev != buf.device or tables.device != dev or grid.device != dev or grid.cells_struct is None:
+        raise RuntimeError("step_fused: tensors / tables / grid (with plane cells) must live on one CUDA device")
+    if (phases & _lib.PHASE_SPAWN) and tables.n_spawns < buf.n:
+        raise RuntimeError(f"step_fused: spawn table has {tables.n_spawns} rows for {buf.n} envs")
+    torch.ops.rover_b200.step_fused(
+        new_actions, force_matrix_w, root_pos_w, root_quat_w, params_desc(params), buf.state_list(), buf.out_list(),
+        tables.desc, rng.state, int(n_rounds), buf.spawn_index, buf.stats, buf.scratch_fused, buf.log if log else None, obs,
+        int(pre_phases), int(phases), xchg.desc if xchg is not None else None, rays.starts, rays.box_t, grid.desc,
+        grid.cells_desc, float(max_distance), float(base_offset))
 
 
 def _check_variates(what, n, spawn_perm, yaw_u, heading_u, theta_u):

@@ -46,6 +46,11 @@ _SCHEMAS = {
                 "Tensor(c!)[] state, Tensor(d!)[] out, Tensor tables, Tensor[] variates, Tensor(e!)? rng_state, "
                 "int n_rounds, Tensor(f!) spawn_index, Tensor(g!) stats, Tensor(h!) scratch, Tensor(k!) lookback, "
                 "Tensor(i!)? log_out, Tensor(j!)? obs, int pre_phases, int phases, Tensor? xchg) -> ()",
+    "step_fused": "(Tensor? new_actions, Tensor? force_matrix_w, Tensor(a!) root_pos_w, Tensor(b!) root_quat_w, Tensor params, "
+                  "Tensor(c!)[] state, Tensor(d!)[] out, Tensor tables, Tensor(e!) rng_state, int n_rounds, "
+                  "Tensor(f!) spawn_index, Tensor(g!) stats, Tensor(h!) scratch, Tensor(i!)? log_out, Tensor(j!) obs, "
+                  "int pre_phases, int phases, Tensor? xchg, Tensor ray_starts, Tensor pattern_box, Tensor grid, Tensor cells, "
+                  "float max_distance, float base_offset) -> ()",
     "stats_read": "(Tensor mailbox, int world, Tensor(a!) out) -> ()",
     # ---- policy / value forward (models.py:24-36, 89-102, 105-162) and GaussianMixin.act
     "policy_pack": "(Tensor[] weights, Tensor[] biases, Tensor(a!) packed) -> ()",
@@ -248,6 +253,35 @@ def _mdp_step(new_actions, force_matrix_w, root_pos_w, root_quat_w, params, stat
         _desc(xchg, _lib.StatsExchange, "xchg") if xchg is not None else None, _stream(root_pos_w)))
 
 
+def _step_fused(new_actions, force_matrix_w, root_pos_w, root_quat_w, params, state, out, tables, rng_state, n_rounds,
+                spawn_index, stats, scratch, log_out, obs, pre_phases, phases, xchg, ray_starts, pattern_box, grid, cells,
+                max_distance, base_offset):
+    _f32("step_fused", new_actions, force_matrix_w, root_pos_w, root_quat_w, ray_starts)
+    n = _n_envs(state)
+    p = _desc(params, _lib.MdpParams, "params")
+    if root_pos_w.shape != (n, 3) or root_quat_w.shape != (n, 4):
+        raise RuntimeError("rover_b200::step_fused: bad root state shapes")
+    if (pre_phases & _lib.PRE_ACTIONS) and (new_actions is None or new_actions.shape != (n, 2)):
+        raise RuntimeError("rover_b200::step_fused: new_actions must be [N,2]")
+    if (pre_phases & _lib.PRE_TERMS) and (force_matrix_w is None or force_matrix_w.numel() != n * p.contents.num_bodies * 3):
+        raise RuntimeError("rover_b200::step_fused: force_matrix_w must be [N, num_bodies, 1, 3]")
+    if rng_state.dtype != torch.int64 or rng_state.numel() != 2 or not rng_state.is_cuda:
+        raise RuntimeError("rover_b200::step_fused: rng_state must be a CUDA int64 tensor {seed, step}")
+    r = ray_starts.shape[0]
+    if obs.dtype != torch.float32 or obs.dim() != 2 or obs.shape[0] != n or obs.shape[1] < 4 + r or obs.stride(1) != 1:
+        raise RuntimeError("rover_b200::step_fused: obs must be fp32 [N, >= 4 + R] with unit inner stride")
+    if scratch.dtype != torch.float32 or not scratch.is_contiguous():
+        raise RuntimeError("rover_b200::step_fused: scratch must be a contiguous fp32 tensor")
+    st, o = _state(state, _lib.MdpState, "state"), _state(out, _lib.MdpOut, "out")
+    _lib.check(_lib.load().rover_step_fused(
+        _p(new_actions), _p(force_matrix_w), _p(root_pos_w), _p(root_quat_w), n, p, C.byref(st), C.byref(o),
+        _desc(tables, _lib.TerrainTables, "tables"), _p(rng_state), int(n_rounds), _p(spawn_index), _p(stats), _p(scratch),
+        int(scratch.numel()), _p(log_out), _p(obs), int(obs.stride(0)), int(pre_phases), int(phases),
+        _desc(xchg, _lib.StatsExchange, "xchg") if xchg is not None else None, _p(ray_starts), r,
+        C.cast(C.c_void_p(pattern_box.data_ptr()), C.POINTER(C.c_float * 4)), _desc(grid, _lib.ScanGrid, "grid"),
+        _desc(cells, _lib.PlaneCells, "cells"), float(max_distance), float(base_offset), _stream(root_pos_w)))
+
+
 def _stats_read(mailbox, world, out):
     _lib.check(_lib.load().rover_stats_read(_p(mailbox), int(world), _p(out), _stream(out)))
 
@@ -376,7 +410,7 @@ def _fill_holes(mask):
 _IMPLS = {
     "height_scan": _height_scan, "height_scan_out": _height_scan_out, "height_scan_hits": _height_scan_hits,
     "height_scan_obs": _height_scan_obs, "ackermann": _ackermann, "mdp_pre_step": _mdp_pre_step,
-    "mdp_post_step": _mdp_post_step, "mdp_step": _mdp_step, "stats_read": _stats_read, "policy_pack": _policy_pack,
+    "mdp_post_step": _mdp_post_step, "mdp_step": _mdp_step, "step_fused": _step_fused, "stats_read": _stats_read, "policy_pack": _policy_pack,
     "policy_forward": _policy_forward, "gaussian_act": _gaussian_act, "policy_pack_fused": _policy_pack_fused,
     "scan_encoder_fused": _scan_encoder_fused, "policy_mlp_forward": _policy_mlp_forward, "mesh_to_heightmap": _mesh_to_heightmap,
     "steep_mask": _steep_mask, "morph_box": _morph_box, "fill_holes": _fill_holes,
@@ -446,7 +480,7 @@ def _fake_none(*args, **kwargs):
     return None
 
 
-for _name in ("height_scan_out", "height_scan_obs", "mdp_pre_step", "mdp_post_step", "mdp_step", "stats_read", "policy_pack",
+for _name in ("height_scan_out", "height_scan_obs", "mdp_pre_step", "mdp_post_step", "mdp_step", "step_fused", "stats_read", "policy_pack",
               "policy_pack_fused", "mesh_to_heightmap"):
     torch.library.register_fake(f"{NS}::{_name}", _fake_none, lib=_DEF)
 
