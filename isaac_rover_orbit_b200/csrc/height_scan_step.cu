@@ -7,22 +7,27 @@
 // Why: at 16384 envs the step was two launches, 24 us (MDP: once-through code, three dependent cold misses, 10 % issue
 // active -- profiles/r02_ncu_full.md) + 55 us (scan), strictly one after the other, although only the ~5 % of envs that
 // reset change the pose the scan reads.  With the reset variates drawn in the kernel the MDP work of an env depends on
-// nothing but that env (no reset rank), so any thread can do it: here WARP 1 of every scan CTA runs it for the CTA's own
-// envs, 32 at a time, one batch ahead of the scan; an env's final pose is handed to the scan's producer warp through
+// nothing but that env (no reset rank), so any thread can do it: here warps of every scan CTA run it for the CTA's own
+// envs, 32 at a time, ahead of the scan; an env's final pose is handed to the scan's producer warp through
 // shared memory as soon as it is known (right after the spawn, before the target rejection sampling and the stores).
 // The MDP step's latency chain hides behind the scan of the previous batch; only the first batch's (~4 us) is exposed.
 //
-// Roles: warp 0 scan producer (variant 5's, poses from shared memory), warp 1 MDP, warps 2-15 scan consumers (14; the
-// register file holds 16 warps at 128 registers).  Statistics: per-CTA partial sums (batches in order, fixed shuffle
-// tree), combined in CTA order by the last CTA's MDP warp, which also writes the episode log, advances the variate step
-// and publishes to the P2P mailboxes -- all of it long before the scan of that CTA ends.
+// One MDP warp per CTA is not enough: a batch of 32 envs is ~2800 dependent instructions + 3 cold misses, ~25 us in a
+// single warp, against the ~14 us the scan needs for 32 envs (first version: 104 us per step against 81 us for the two
+// launches).  So warps 1-4 are MDP warps: batch b goes to warp 1 + b % 4, each with its own pose buffer, and an MDP warp
+// that is ahead of the scan front JOINS THE SCAN CONSUMERS (work units come from a shared counter) until its next batch
+// is due.  Roles: warp 0 scan producer (variant 5's, poses from shared memory), warps 1-15 workers.  Statistics: per-warp
+// partials (batches in order, fixed shuffle tree) -> CTA partial -> combined in CTA order by the last CTA, which also
+// writes the episode log, advances the variate step and publishes to the P2P mailboxes.
 #include "mdp_env.cuh"
 #include "scan_paired.cuh"
 
 namespace rover {
 
-constexpr int kStepConsumerWarps = 14;
-constexpr int kStepThreads = 32 * (2 + kStepConsumerWarps);
+constexpr int kStepWorkerWarps = 15;  // warps 1..15: scan consumers; the first kStepMdpWarps of them run the MDP step first
+constexpr int kStepMdpWarps = 4;      // batches of 32 envs are dealt to them round-robin (batch b -> worker b % 4)
+constexpr int kStepThreads = 32 * (1 + kStepWorkerWarps);
+constexpr int kStepLead = 96;         // an MDP batch is started when the scan front is within this many envs of it
 static_assert(kStepThreads == 512, "16 warps x 128 registers = the register file");
 
 struct StepSmem {
@@ -31,20 +36,25 @@ struct StepSmem {
     LinePair2 xpair[kPairMaxLines], ypair[kPairMaxLines];
     unsigned long long full_bar[kPairFullBars];
     unsigned long long empty_bar[kPairStages];
-    unsigned long long pose_full[2], pose_empty[2];
-    float pose[2][32][8];  // final root pose of a batch of 32 envs: px, py, pz, qw, qx, qy, qz, -
+    unsigned long long pose_full[kStepMdpWarps], pose_empty[kStepMdpWarps];
+    float pose[kStepMdpWarps][32][8];  // final root pose of a batch of 32 envs: px, py, pz, qw, qx, qy, qz, -
+    float part[kStepMdpWarps][ROVER_STATS_LEN];  // statistics partials of the MDP warps
     int next_chunk;
+    int mdp_done;
 };
 static_assert(sizeof(StepSmem) <= 227 * 1024, "StepSmem exceeds the shared memory of one SM");
 __device__ __forceinline__ float sm_vz(const StepSmem& sm, int slot) { return sm.vz[slot]; }
 
 struct PoseToScan {
-    float* slot;              // this lane's row of the batch's pose buffer
-    unsigned long long* bar;  // the batch's `pose_full` barrier (32 arrivals)
+    float* slot;               // this lane's row of the batch's pose buffer
+    unsigned long long* full;  // the buffer's `pose_full` barrier (32 arrivals)
+    unsigned long long* empty; // ... and `pose_empty` (the producer took the previous batch that used the buffer)
+    int wait_parity;           // < 0: first use of the buffer, nothing to wait for
     __device__ __forceinline__ void operator()(float px, float py, float pz, const float4& q) const {
+        if (wait_parity >= 0) bar_wait(empty, (uint32_t)wait_parity);
         slot[0] = px, slot[1] = py, slot[2] = pz;
         slot[3] = q.x, slot[4] = q.y, slot[5] = q.z, slot[6] = q.w;  // (w, x, y, z)
-        bar_arrive(bar);  // release: the producer may read this row
+        bar_arrive(full);  // release: the producer may read this row
     }
 };
 
@@ -69,25 +79,26 @@ height_scan_step_kernel(const float* __restrict__ new_actions, const float* __re
     float* __restrict__ out = obs + 4;  // heights behind the observation head
     const int out_stride = obs_stride;
 
-    // ---- prologue: barriers (warp 0), pattern + line tables (consumer warps, loads before stores)
+    // ---- prologue: barriers (warp 0), pattern + line tables (worker warps, loads before stores)
     int my_flat_z = 1;
     if (warp == 0) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
             for (int s = 0; s < kPairFullBars; ++s) bar_init(&sm.full_bar[s], 2);  // TMA bytes + header published
             for (int s = 0; s < kPairStages; ++s) bar_init(&sm.empty_bar[s], (uint32_t)n_chunks);
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < kStepMdpWarps; ++s) {
                 bar_init(&sm.pose_full[s], 32);  // one arrival per lane of the MDP warp
                 bar_init(&sm.pose_empty[s], 1);  // the producer has read the batch
             }
             sm.next_chunk = 0;
+            sm.mdp_done = 0;
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-    } else if (warp >= 2) {
-        constexpr int kFill = 32 * kStepConsumerWarps;
+    } else {
+        constexpr int kFill = 32 * kStepWorkerWarps;
         constexpr int kPatLoads = (3 * kPairMaxRays + kFill - 1) / kFill;
         constexpr int kLineLoads = (kPairMaxLines + kFill - 1) / kFill;
-        const int ct = threadIdx.x - 64;
+        const int ct = threadIdx.x - 32;
         float* pat_flat = sm.vx;  // vx, vy, vz contiguous
         float pat[kPatLoads], xl[kLineLoads], xh[kLineLoads], yl[kLineLoads], yh[kLineLoads];
         const float vz0 = __ldg(ray_local + 2);
@@ -121,96 +132,14 @@ height_scan_step_kernel(const float* __restrict__ new_actions, const float* __re
     }
     const bool flat_z = __syncthreads_and(my_flat_z) != 0;
 
-    if (warp == 1) {
-        // =============================== MDP warp: one env per lane, one batch ahead of the scan ===============================
-        const RngKey key = make_rng_key(V.rng[0], *reinterpret_cast<volatile unsigned long long*>(V.rng + 1));
-        float acc = 0.f;  // lane k < 16 accumulates statistic k over the CTA's batches (in order)
-        for (int b = 0; b < n_batches; ++b) {
-            const int it = b * 32 + lane;
-            const bool valid = it < n_iter;
-            const int i = valid ? (int)blockIdx.x + it * (int)gridDim.x : n_envs;  // (n_envs: skipped by the i < n guards)
-            if (b >= 2) bar_wait(&sm.pose_empty[b & 1], (uint32_t)((b >> 1) - 1) & 1u);  // the producer took batch b - 2
-            if (valid) {  // the post-step's inputs: in flight while the pre-step part runs
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(root_pos_w + 3 * (size_t)i));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(root_quat_w + 4 * (size_t)i));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(S.pos_cmd_w + 3 * (size_t)i));
-            }
-            const bool reset = pre_step_env(i, new_actions, force, n_envs, P, S, O, pre_phases);
-            EnvRegs er;
-            post_env_load<true>(i, valid, root_pos_w, root_quat_w, S, V, er);
-            float st[kStats];
-            if (!valid) bar_arrive(&sm.pose_full[b & 1]);  // a lane without an env has no row to publish
-            post_env_work<true>(i, valid, valid && reset, 0, er, root_pos_w, root_quat_w, P, S, O, T, V, key, out_spawn_index, obs,
-                                obs_stride, phases, st, PoseToScan{&sm.pose[b & 1][lane][0], &sm.pose_full[b & 1]});
-            // the batch's statistics: fixed shuffle tree, then lane k keeps statistic k
-#pragma unroll
-            for (int k = 0; k < kStats; ++k) {
-                float v = st[k];
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                v = __shfl_sync(0xffffffffu, v, 0);
-                if (lane == k) acc += v;
-            }
-        }
-        // ---- CTA partial -> global; the last CTA combines them in CTA order (deterministic), writes the log, advances
-        //      the variate step and publishes to the other ranks' mailboxes
-        if (lane < kStats) cta_stats[(size_t)blockIdx.x * kStats + lane] = acc;
-        __threadfence();
-        __syncwarp();
-        unsigned ticket = 0;
-        if (lane == 0) ticket = atomicAdd(done_counter, 1u);
-        ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        if (ticket == gridDim.x - 1u) {
-            __threadfence();
-            float t = 0.f;
-            if (lane < kStats)
-                for (unsigned c = 0; c < gridDim.x; ++c) t += __ldcg(cta_stats + (size_t)c * kStats + lane);
-            const float cnt = __shfl_sync(0xffffffffu, t, 13);
-            double total = 0.0;
-            if (lane < kStats) {
-                stats[lane] += t;
-                if (log_out != nullptr && (phases & ROVER_PHASE_MANAGERS) && cnt > 0.f) {  // ORBIT manager.reset() log (A.2)
-                    float v = t;
-                    if (lane < ROVER_NUM_REWARD_TERMS) v = __fdiv_rn(__fdiv_rn(t, cnt), P.episode_length_s);
-                    else if (lane == 11 || lane == 12) v = __fdiv_rn(t, cnt);
-                    log_out[lane] = v;
-                }
-                if (X.world > 0) {
-                    total = X.cumulative[lane] + (double)t;
-                    X.cumulative[lane] = total;
-                }
-            }
-            if (lane == 0) {
-                *done_counter = 0u;           // re-arm for the next launch
-                V.rng[1] = V.rng[1] + 1ull;   // next launch = next step of the variate streams
-            }
-            if (X.world > 0) {  // P2P mailboxes: values into the idle buffer of every rank's slot, one fence, then the sequence
-                const unsigned long long seq = *X.sequence + 1ull;
-                for (int e0 = 0; e0 < X.world * kStats; e0 += 32) {
-                    const int e = e0 + lane;
-                    const double v = __shfl_sync(0xffffffffu, total, e % kStats);
-                    if (e < X.world * kStats) {
-                        unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[e / kStats]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
-                        reinterpret_cast<volatile double*>(slot + 8)[(seq & 1ull) * kStats + (e % kStats)] = v;
-                    }
-                }
-                __threadfence_system();
-                __syncwarp();
-                for (int p = lane; p < X.world; p += 32) {
-                    unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
-                    *reinterpret_cast<volatile unsigned long long*>(slot) = seq;
-                }
-                __syncwarp();
-                if (lane == 0) *X.sequence = seq;
-            }
-        }
-    } else if (warp == 0) {
-        // =============================== scan producer: variant 5's, poses from the MDP warp ===============================
+    if (warp == 0) {
+        // =============================== scan producer: variant 5's, poses from the MDP warps ===============================
         ProducerEnv cur;
         for (int b = 0; b < n_batches; ++b) {
-            const int base = b * 32;
-            bar_wait(&sm.pose_full[b & 1], (uint32_t)(b >> 1) & 1u);
+            const int base = b * 32, pb = b % kStepMdpWarps;
+            bar_wait(&sm.pose_full[pb], (uint32_t)(b / kStepMdpWarps) & 1u);
             {
-                const float* row = &sm.pose[b & 1][lane][0];
+                const float* row = &sm.pose[pb][lane][0];
                 cur.have = base + lane < n_iter;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) cur.pv[k] = cur.have ? row[k] : 0.f;
@@ -219,7 +148,7 @@ height_scan_step_kernel(const float* __restrict__ new_actions, const float* __re
                 cur.px = cur.pv[0], cur.py = cur.pv[1], cur.pz = cur.pv[2];
             }
             __syncwarp();
-            if (lane == 0) bar_arrive(&sm.pose_empty[b & 1]);
+            if (lane == 0) bar_arrive(&sm.pose_empty[pb]);
             producer_window(cur, pc, pattern_radius);
             producer_frame(cur);
             producer_verdict(cur, sm, pc, pattern_radius, lines_in_smem);
@@ -244,11 +173,141 @@ height_scan_step_kernel(const float* __restrict__ new_actions, const float* __re
             }
         }
     } else {
-        // =============================== scan consumers: variant 5's loop, 14 warps, static deal ===============================
-        const int w = warp - 2;
-        const int step_it = kStepConsumerWarps / n_chunks, step_c = kStepConsumerWarps % n_chunks;
-        int it = w / n_chunks, c = w % n_chunks;
-        while (it < n_iter) {
+        // =============================== workers: scan consumers; workers 0..3 run the MDP step of their batches first =========
+        // Work units of the scan are handed out in order from a shared counter (so that an MDP warp can join and leave the
+        // pool); an MDP warp starts its next batch when the scan front comes within kStepLead envs of it, and in any case
+        // before it touches a chunk of an env at or behind that batch (its own pending batch can never be what it waits for).
+        const int w = warp - 1;
+        const bool mdp_warp = w < kStepMdpWarps;
+        const int n_mdp_active = min(kStepMdpWarps, n_batches);
+        int my_next = mdp_warp ? w : n_batches;  // next batch this warp owes
+        RngKey key = make_rng_key(0ull, 0ull);
+        if (mdp_warp) key = make_rng_key(V.rng[0], *reinterpret_cast<volatile unsigned long long*>(V.rng + 1));
+        float acc = 0.f;  // lane k < 16 accumulates statistic k over this warp's batches (in order)
+        bool have_chunk = false, draining = false;
+        int it = 0, c = 0;
+        while (true) {
+            bool run_mdp = false;
+            if (my_next < n_batches) {
+                if (draining) run_mdp = true;
+                else if (have_chunk) run_mdp = my_next <= it / 32 + 1;
+                else run_mdp = my_next * 32 <= *reinterpret_cast<volatile int*>(&sm.next_chunk) / n_chunks + kStepLead;
+            }
+            if (run_mdp) {
+                // ------------------------------------------------ the MDP step of batch my_next: one env per lane
+                const int b = my_next;
+                const int eit = b * 32 + lane;
+                const bool valid = eit < n_iter;
+                const int i = valid ? (int)blockIdx.x + eit * (int)gridDim.x : n_envs;  // (n_envs: skipped by the i < n guards)
+                if (valid) {  // the post-step's inputs: in flight while the pre-step part runs
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(root_pos_w + 3 * (size_t)i));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(root_quat_w + 4 * (size_t)i));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(S.pos_cmd_w + 3 * (size_t)i));
+                }
+                const bool reset = pre_step_env(i, new_actions, force, n_envs, P, S, O, pre_phases);
+                EnvRegs er;
+                post_env_load<true>(i, valid, root_pos_w, root_quat_w, S, V, er);
+                float st[kStats];
+                const int use = b / kStepMdpWarps;  // w owns pose buffer w: use 0, 1, 2, ...
+                const PoseToScan hook{&sm.pose[w][lane][0], &sm.pose_full[w], &sm.pose_empty[w], use > 0 ? ((use - 1) & 1) : -1};
+                if (!valid) hook(0.f, 0.f, 0.f, make_float4(1.f, 0.f, 0.f, 0.f));  // a lane without an env still arrives
+                post_env_work<true>(i, valid, valid && reset, 0, er, root_pos_w, root_quat_w, P, S, O, T, V, key, out_spawn_index,
+                                    obs, obs_stride, phases, st, hook);
+                // the batch's statistics: fixed shuffle tree, then lane k keeps statistic k
+#pragma unroll
+                for (int k = 0; k < kStats; ++k) {
+                    float v = st[k];
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                    v = __shfl_sync(0xffffffffu, v, 0);
+                    if (lane == k) acc += v;
+                }
+                my_next += kStepMdpWarps;
+                if (my_next >= n_batches) {
+                    // ---- this warp's MDP work is done: its partial -> shared; the last MDP warp of the CTA combines them
+                    //      (fixed order) -> global; the last CTA combines the CTA partials in CTA order (deterministic),
+                    //      writes the log, advances the variate step and publishes to the other ranks' mailboxes
+                    if (lane < kStats) sm.part[w][lane] = acc;
+                    __threadfence_block();
+                    __syncwarp();
+                    int done = 0;
+                    if (lane == 0) done = atomicAdd(&sm.mdp_done, 1);
+                    done = __shfl_sync(0xffffffffu, done, 0);
+                    if (done == n_mdp_active - 1) {
+                        __threadfence_block();
+                        float cta = 0.f;
+                        if (lane < kStats)
+                            for (int q = 0; q < n_mdp_active; ++q) cta += *reinterpret_cast<volatile float*>(&sm.part[q][lane]);
+                        if (lane < kStats) cta_stats[(size_t)blockIdx.x * kStats + lane] = cta;
+                        __threadfence();
+                        __syncwarp();
+                        unsigned ticket = 0;
+                        if (lane == 0) ticket = atomicAdd(done_counter, 1u);
+                        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+                        if (ticket == gridDim.x - 1u) {
+                            __threadfence();
+                            float t = 0.f;
+                            if (lane < kStats)
+                                for (unsigned cc = 0; cc < gridDim.x; ++cc) t += __ldcg(cta_stats + (size_t)cc * kStats + lane);
+                            const float cnt = __shfl_sync(0xffffffffu, t, 13);
+                            double total = 0.0;
+                            if (lane < kStats) {
+                                stats[lane] += t;
+                                if (log_out != nullptr && (phases & ROVER_PHASE_MANAGERS) && cnt > 0.f) {  // ORBIT manager.reset() log
+                                    float v = t;
+                                    if (lane < ROVER_NUM_REWARD_TERMS) v = __fdiv_rn(__fdiv_rn(t, cnt), P.episode_length_s);
+                                    else if (lane == 11 || lane == 12) v = __fdiv_rn(t, cnt);
+                                    log_out[lane] = v;
+                                }
+                                if (X.world > 0) {
+                                    total = X.cumulative[lane] + (double)t;
+                                    X.cumulative[lane] = total;
+                                }
+                            }
+                            if (lane == 0) {
+                                *done_counter = 0u;          // re-arm for the next launch
+                                V.rng[1] = V.rng[1] + 1ull;  // next launch = next step of the variate streams
+                            }
+                            if (X.world > 0) {  // P2P mailboxes: values into the idle buffer of every slot, one fence, then the sequence
+                                const unsigned long long seq = *X.sequence + 1ull;
+                                for (int e0 = 0; e0 < X.world * kStats; e0 += 32) {
+                                    const int e = e0 + lane;
+                                    const double v = __shfl_sync(0xffffffffu, total, e % kStats);
+                                    if (e < X.world * kStats) {
+                                        unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[e / kStats]) +
+                                                              (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
+                                        reinterpret_cast<volatile double*>(slot + 8)[(seq & 1ull) * kStats + (e % kStats)] = v;
+                                    }
+                                }
+                                __threadfence_system();
+                                __syncwarp();
+                                for (int p = lane; p < X.world; p += 32) {
+                                    unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
+                                    *reinterpret_cast<volatile unsigned long long*>(slot) = seq;
+                                }
+                                __syncwarp();
+                                if (lane == 0) *X.sequence = seq;
+                            }
+                        }
+                    }
+                }
+                continue;
+            }
+            if (draining) break;
+            if (!have_chunk) {
+                int k = 0;
+                if (lane == 0) k = atomicAdd(&sm.next_chunk, 1);
+                k = __shfl_sync(0xffffffffu, k, 0);
+                it = k / n_chunks;
+                c = k - it * n_chunks;
+                if (it >= n_iter) {  // the scan is handed out; an MDP batch still owed (cannot be needed any more) is run, then out
+                    draining = true;
+                    continue;
+                }
+                have_chunk = true;
+                continue;  // re-check the MDP duty against the env just drawn
+            }
+            have_chunk = false;
+            // ------------------------------------------------ one 256-ray chunk of env `it` (variant 5's consumer body)
             const int env = (int)blockIdx.x + it * (int)gridDim.x;
             const int s = it % kPairStages;
             const PairStage& st = sm.stage[s];
@@ -290,12 +349,6 @@ height_scan_step_kernel(const float* __restrict__ new_actions, const float* __re
             }
             __syncwarp();
             if (lane == 0) bar_arrive(&sm.empty_bar[s]);  // this chunk no longer reads the stage
-            it += step_it;
-            c += step_c;
-            if (c >= n_chunks) {
-                c -= n_chunks;
-                ++it;
-            }
         }
     }
 }

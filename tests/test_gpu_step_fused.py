@@ -69,23 +69,21 @@ def test_step_fused_equals_mdp_step_then_scan(world, n):
         total_resets += float(bufs[1].stats[13])
     if n >= 148:
         assert total_resets > 0
-    # repeated launches are deterministic (statistics included)
-    a = ops.MdpBuffers.allocate(n, dev)
-    for name in ("pos_cmd_w", "heading_cmd_w", "episode_length_buf", "env_origins", "time_left", "pos_cmd_b", "action"):
-        getattr(a, name).copy_(getattr(bufs[1], name))
-    snap = {name: getattr(a, name).clone() for name in ("pos_cmd_w", "heading_cmd_w", "episode_length_buf", "env_origins",
-                                                          "time_left", "pos_cmd_b", "action")}
+    # repeated launches from the same state are deterministic (statistics and log included)
     res = []
     for _ in range(2):
-        for name, t in snap.items():
-            getattr(a, name).copy_(t)
-        a.stats.zero_()
-        a.episode_sums.zero_()
+        a = ops.MdpBuffers.allocate(n, dev)
+        a.pos_cmd_w.copy_(pc)
+        a.heading_cmd_w.copy_(hc)
+        a.episode_length_buf.copy_(ep)
+        a.env_origins.copy_(steps[0].root_pos_w)
+        a.time_left.fill_(150.0)
         o = alloc_obs(n, dev)
-        ops.step_fused(a, params, th, steps[0].actions, steps[0].force_matrix_w, steps[0].root_pos_w.clone(),
-                       steps[0].root_quat_w.clone(), rays, grid, o, ops.ResetRng(3, dev))
+        r3 = ops.ResetRng(3, dev)
+        for s in steps[:2]:
+            ops.step_fused(a, params, th, s.actions, s.force_matrix_w, s.root_pos_w.clone(), s.root_quat_w.clone(), rays, grid, o, r3)
         torch.cuda.synchronize()
-        res.append((a.stats.clone(), o.clone(), a.reward.clone()))
+        res.append((a.stats.clone(), a.log.clone(), o.clone(), a.reward.clone(), a.pos_cmd_w.clone()))
     assert all(torch.equal(x, y) for x, y in zip(res[0], res[1]))
 
 
