@@ -9,13 +9,6 @@
 
 namespace rover {
 
-// The accurate sinf / cosf / atan2f each inline a large-argument slow path; inlined at ~25 call sites they made the step
-// 8,000 instructions (128 KB) of once-through code, fetched cold by every SM -- 44 % of the launch's stalls were
-// instruction fetch (profiles/r01_mdp_v1.md).  One out-of-line copy of each: same functions, same results.
-static __device__ __noinline__ float mdp_sinf(float x) { return sinf(x); }
-static __device__ __noinline__ float mdp_cosf(float x) { return cosf(x); }
-static __device__ __noinline__ float mdp_atan2f(float y, float x) { return atan2f(y, x); }
-
 __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
 // torch.remainder(a, 2pi) followed by the (a > pi) fold  (ORBIT wrap_to_pi, A.1)
@@ -35,8 +28,8 @@ struct YawQuat {
 __device__ __forceinline__ YawQuat yaw_quat(float w, float x, float y, float z) {
     const float siny = __fmul_rn(2.f, __fadd_rn(__fmul_rn(w, z), __fmul_rn(x, y)));
     const float cosy = __fsub_rn(1.f, __fmul_rn(2.f, __fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z))));
-    const float half = __fdiv_rn(mdp_atan2f(siny, cosy), 2.f);
-    const float s = mdp_sinf(half), c = mdp_cosf(half);
+    const float half = __fdiv_rn(atan2f(siny, cosy), 2.f);
+    const float s = sinf(half), c = cosf(half);
     const float n = fmaxf(sqrtf(__fadd_rn(__fmul_rn(c, c), __fmul_rn(s, s))), 1e-9f);
     return {__fdiv_rn(c, n), __fdiv_rn(s, n)};
 }
@@ -48,7 +41,7 @@ __device__ __forceinline__ float heading_w(float w, float x, float y, float z) {
     const float cy = __fsub_rn(0.f, __fmul_rn(x, tz));  // z*t.x - x*t.z with t.x = 0
     const float fx = __fadd_rn(1.f, cx);
     const float fy = __fadd_rn(__fmul_rn(w, ty), cy);
-    return mdp_atan2f(fy, fx);
+    return atan2f(fy, fx);
 }
 
 __device__ __forceinline__ float norm2(float x, float y) {
@@ -103,7 +96,7 @@ __device__ __forceinline__ void ackermann_v2(const RoverMdpParams& P, float lin_
     const float v_r = point ? spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_r, w), dir);
     const float v_ml = point ? -spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_ml, w), dir);
     const float v_mr = point ? spin : __fmul_rn((w == 0.f) ? v : __fmul_rn(r_mr, w), dir);
-    const float ack = __fmul_rn(mdp_atan2f(P.wheelbase_length, r_l), turn);         // :305 (FL radius for all four)
+    const float ack = __fmul_rn(atan2f(P.wheelbase_length, r_l), turn);         // :305 (FL radius for all four)
     const float q = 0.78539816339744830962f;
     jv[0] = __fdiv_rn(v_ml, P.wheel_radius);                                    // [ML,FL,RL,RR,MR,FR] :316
     jv[1] = __fdiv_rn(v_l, P.wheel_radius);
@@ -135,7 +128,7 @@ __device__ __forceinline__ void ackermann_v1(float lin, float ang, float* jp, fl
         float vel = __fmul_rn(dist, av);                                        // :141
         vel = (dist > 1000.f) ? lin2 : vel;                                     // :144
         jv[k] = __fdiv_rn(vel, 0.2f);                                           // :147
-        float s = mdp_atan2f(wy[k], __fsub_rn(wx[k], p));                           // :149-154
+        float s = atan2f(wy[k], __fsub_rn(wx[k], p));                           // :149-154
         if (s < -1.57f) s = __fadd_rn(s, 3.1415927f);                           // :155
         if (s > 1.57f) s = __fsub_rn(s, 3.1415927f);                            // :156
         steer[k] = s;
@@ -166,10 +159,10 @@ __device__ __forceinline__ void ackermann_v3(const RoverMdpParams& P, float lin_
     const float half_wl = P.wheelbase_length / 2.f;
     const float y_front = __fsub_rn(half_wl, P.offset_lin), y_rear = __fadd_rn(half_wl, P.offset_lin);  // :488-497
     const float q = 0.78539816339744830962f;
-    jp[0] = point ? -q : __fmul_rn(mdp_atan2f(y_front, r_l), turn);                 // FL
-    jp[1] = point ? q : __fmul_rn(mdp_atan2f(y_front, r_r), turn);                  // FR
-    jp[2] = point ? q : __fmul_rn(mdp_atan2f(y_rear, r_l), -turn);                  // RL
-    jp[3] = point ? -q : __fmul_rn(mdp_atan2f(y_rear, r_r), -turn);                 // RR
+    jp[0] = point ? -q : __fmul_rn(atan2f(y_front, r_l), turn);                 // FL
+    jp[1] = point ? q : __fmul_rn(atan2f(y_front, r_r), turn);                  // FR
+    jp[2] = point ? q : __fmul_rn(atan2f(y_rear, r_l), -turn);                  // RL
+    jp[3] = point ? -q : __fmul_rn(atan2f(y_rear, r_r), -turn);                 // RR
     const float diam = P.wheel_diameter;                                        // :503 (float)(wheel_radius * 2)
     jv[0] = __fdiv_rn(v_l, diam);
     jv[1] = __fdiv_rn(v_r, diam);
@@ -216,7 +209,7 @@ __device__ __forceinline__ bool pre_step_env(int i, const float* __restrict__ ne
         // ---- shared quantities of the PREVIOUS command (rover_env.py:82-86 run before the command update)
         const float bx = S.pos_cmd_b[3 * (size_t)i], by = S.pos_cmd_b[3 * (size_t)i + 1];
         const float d = norm2(bx, by);
-        const float ang = mdp_atan2f(by, bx);
+        const float ang = atan2f(by, bx);
         const bool coll = collision_active(force + (size_t)i * P.num_bodies * 3, P.num_bodies);
         const float max_len = (float)P.max_episode_length;
 
@@ -306,7 +299,7 @@ struct VariatesDev {
 };
 
 template <bool kRng>
-static __device__ __noinline__ bool resample_command(int i, const RoverMdpParams& P, const RoverMdpState& S, const Tables& T,
+__device__ __forceinline__ bool resample_command(int i, const RoverMdpParams& P, const RoverMdpState& S, const Tables& T,
                                                  float ox, float oy, const float* __restrict__ theta_u,
                                                  const float (&theta0)[8], const RngKey& key, int n_rounds,
                                                  float heading_u, float& cx, float& cy, float& cz, float& chead) {
@@ -335,8 +328,8 @@ static __device__ __noinline__ bool resample_command(int i, const RoverMdpParams
 #pragma unroll
         for (int k = 0; k < kBatch; ++k) {
             const float th = __fmul_rn(__fmul_rn(u[k], 2.f), pi_f);                      // :169
-            xs[k] = __fadd_rn(__fmul_rn(mdp_cosf(th), P.target_distance), ox);               // :172
-            ys[k] = __fadd_rn(__fmul_rn(mdp_sinf(th), P.target_distance), oy);               // :173
+            xs[k] = __fadd_rn(__fmul_rn(cosf(th), P.target_distance), ox);               // :172
+            ys[k] = __fadd_rn(__fmul_rn(sinf(th), P.target_distance), oy);               // :173
             terrain_cell(T, xs[k], ys[k], cols[k], rows[k]);
             m[k] = __ldg(T.safe_mask + (size_t)rows[k] * T.W + cols[k]);                 // :220
             hz[k] = __ldg(T.heightmap + (size_t)rows[k] * T.W + cols[k]);                // :154, used if round k wins
@@ -458,7 +451,7 @@ __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int
             pz = __fadd_rn(__ldg(sp + 2), P.spawn_z_offset);
             const float angle = __fmul_rn(__fmul_rn(yaw_var, 2.f), 3.1415927f);
             const float half = __fdiv_rn(angle, 2.f);
-            q = make_float4(mdp_cosf(half), 0.f, 0.f, mdp_sinf(half));
+            q = make_float4(cosf(half), 0.f, 0.f, sinf(half));
             org_x = px, org_y = py, origin_known = true;
             S.env_origins[3 * (size_t)i] = px;
             S.env_origins[3 * (size_t)i + 1] = py;
@@ -562,7 +555,7 @@ __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int
             o[0] = act.x;
             o[1] = act.y;
             o[2] = __fmul_rn(norm2(pbx, pby), P.obs_distance_scale);
-            o[3] = __fmul_rn(mdp_atan2f(pby, pbx), P.obs_heading_scale);
+            o[3] = __fmul_rn(atan2f(pby, pbx), P.obs_heading_scale);
         }
     }
 
