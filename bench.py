@@ -455,8 +455,25 @@ def run_ours(args):
                                        else "NCCL all_reduce per step")
         return d
 
+    def one_launch():
+        # the whole step as ONE launch (rover_step_fused: MDP warps inside the persistent scan kernel) -- measured slower
+        # than the two launches; reported so that the record shows it
+        w = worlds["cfg3"]
+
+        def step(i):
+            s = w.sets[i % 4]
+            w.physics(i)
+            ops.step_fused(w.buf, params, w.th, s.actions, s.force_matrix_w, s.root_pos_w, s.root_quat_w, rays, grid, w.obs,
+                           w.rng)
+
+        t = max_over_ranks([time_steps(graphed(step), ksteps, 3, flush, stream).mean()])[0]
+        d = fused_numbers(w.n, t, 1)
+        d["what"] = "rover_step_fused: MDP step run by 4 warps of every scan CTA, scan in the same persistent kernel"
+        return d
+
     if world == 1:
         guarded("cfg3", fused, lambda: run_fused(STEP_ENVS_CFG3, "cfg3", False))
+        guarded("cfg3_one_launch", fused, one_launch)
     guarded("cfg5", fused, lambda: run_fused(STEP_ENVS_CFG5, "cfg5", p2p is not None))
     fused["note"] = ("cfg5 = 8192 envs/GPU at every N (weak scaling: the ratio of its env_steps_per_s across N is the "
                      "scaling of the fused step); cfg3 = 16384 envs on one GPU")

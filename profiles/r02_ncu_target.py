@@ -1,11 +1,11 @@
 """Round-2 ncu target: one warm-up launch and one profiled launch (L2 flushed before it) of every hot kernel.
 
     python profiles/r02_ncu_target.py && ncu --set full --clock-control none --import-source on \
-        -k regex:'height_scan_paired|fused_scan_encoder|policy_mlp|mdp_fused_step|policy_forward_ws' -s 8 -c 8 \
+        -k regex:'height_scan_paired|fused_scan_encoder|policy_mlp|mdp_fused_step|height_scan_step|policy_forward_ws' -s 9 -c 9 \
         -o gpurun_out/r02_full python profiles/r02_ncu_target.py
 
 Launch order of the matching kernels (the same in both passes): scan @ 4096, 16384, 65536 envs; fused scan + encoder and
-the MLP @ 16384; the single-launch MDP step @ 16384; policy forward on fp32 / bf16 observations @ 65536.
+the MLP @ 16384; the single-launch MDP step and the whole-step launch @ 16384; policy forward on fp32 / bf16 observations @ 65536.
 """
 import os
 import sys
@@ -54,6 +54,9 @@ for rep in range(2):
     flush_buf.fill_(1)
     ops.mdp_step(buf, params, th, st.actions, st.force_matrix_w, st.root_pos_w.clone(), st.root_quat_w.clone(), obs=mdp_obs,
                  rng=rng)
+    flush_buf.fill_(1)
+    ops.step_fused(buf, params, th, st.actions, st.force_matrix_w, st.root_pos_w.clone(), st.root_quat_w.clone(), rays, grid,
+                   mdp_obs, rng)
     flush_buf.fill_(1)
     net.compute({"states": pol32})
     flush_buf.fill_(1)
