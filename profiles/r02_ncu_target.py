@@ -43,6 +43,7 @@ th = ops.TerrainTablesHandle(tables.heightmap, tables.safe_mask, tables.offset_x
 buf.env_origins.copy_(st.root_pos_w)
 buf.time_left.fill_(150.0)
 buf.pos_cmd_w.copy_(st.root_pos_w + torch.tensor([9.0, 0.0, 0.0], device=dev))
+buf.pos_cmd_b.copy_(torch.tensor([9.0, 0.0, 0.0], device=dev).expand(16384, 3))  # 9 m from the target: resets come from contacts (5 %)
 rng = ops.ResetRng(5, dev)
 mdp_obs = alloc_obs(16384, dev)
 for rep in range(2):
