@@ -274,18 +274,19 @@ struct Tables {
 __device__ __forceinline__ void terrain_cell(const Tables& T, float x, float y, int& col, int& row) {
     const float sx = __fadd_rn(__fdiv_rn(x, T.res), T.offx);
     const float sy = __fadd_rn(__fdiv_rn(y, T.res), T.offy);
-    const long long cx = (long long)fminf(fmaxf(sx, -1.0e18f), 1.0e18f);  // .long(): truncation toward zero
-    const long long cy = (long long)fminf(fmaxf(sy, -1.0e18f), 1.0e18f);
-    col = (int)min(max(cx, 0LL), (long long)(T.W - 1));
-    row = (int)min(max(cy, 0LL), (long long)(T.H - 1));
+    // .long() truncates toward zero, then clamp(0, W - 1): truncation is monotone and the bounds are integers, so
+    // clamping the float first gives the same cell (NaN -> 0 either way) without 64-bit integer min / max
+    col = (int)fminf(fmaxf(sx, 0.f), (float)(T.W - 1));
+    row = (int)fminf(fmaxf(sy, 0.f), (float)(T.H - 1));
 }
 
 // CommandTerm._resample + _resample_command + sample_new_targets (terrain_importer.py:74-95, 134-175).
-// The reference's rejection loop is sequential (one host sync per round); here the candidates of a batch of 8 rounds
-// are generated together and their mask bytes fetched concurrently (one memory round trip per batch instead of per
-// round), then the first valid round wins -- the same candidate the sequential loop would have accepted.  The height
-// under every candidate is fetched in the same round trip (speculatively: 8 loads for the ~5 % of envs that resample),
-// which takes the heightmap lookup off the dependent chain rank -> spawn row -> mask -> height.
+// The reference's rejection loop is sequential (one host sync per round).  Here it is WARP-COOPERATIVE: the few envs of
+// a warp that resample this step (~5 %: 1.6 per warp) are served four at a time, eight lanes per env, lane k of a group
+// evaluating round r0 + k -- its variate, sin / cos, the terrain cell, the mask byte and (speculatively) the height
+// under the candidate -- so a warp pays ONE candidate's instruction chain and one memory round trip per pass instead of
+// eight unrolled candidates in every lane's instruction stream (that was 40 % of the step kernel's instructions).  The
+// first valid round wins, else the last one tried: the same candidate the sequential loop accepts.
 // The random variates of the reset path: explicit arrays (parity tests: oracle and kernel read the same numbers) or the
 // counter-based generator of rng.cuh evaluated in registers (rng != nullptr: {seed, step} in device memory, the step
 // counter advanced by the launch itself, so the launch can sit in a CUDA graph).
@@ -298,55 +299,70 @@ struct VariatesDev {
     int n_rounds;
 };
 
+// Must be called by all 32 lanes of a converged warp.  need: this lane's env resamples around (ox, oy).  Lanes with
+// `need` get the accepted candidate in (cx, cy, cz) and return true if every round was rejected.
 template <bool kRng>
-__device__ __forceinline__ bool resample_command(int i, const RoverMdpParams& P, const RoverMdpState& S, const Tables& T,
-                                                 float ox, float oy, const float* __restrict__ theta_u,
-                                                 const float (&theta0)[8], const RngKey& key, int n_rounds,
-                                                 float heading_u, float& cx, float& cy, float& cz, float& chead) {
+__device__ __forceinline__ bool resample_warp(int i, bool need, const RoverMdpParams& P, const Tables& T, float ox, float oy,
+                                              const float* __restrict__ theta_u, const RngKey& key, int n_rounds,
+                                              float& cx, float& cy, float& cz) {
+    constexpr unsigned kFull = 0xffffffffu;
     const float pi_f = 3.1415927f;  // torch.pi as fp32; the reference computes rand * 2 * pi left to right
-    constexpr int kBatch = 8;
-    float x = 0.f, y = 0.f, z = 0.f;
-    bool bad = true;
-    for (int r0 = 0; r0 < n_rounds && bad; r0 += kBatch) {
-        float u[kBatch], xs[kBatch], ys[kBatch];
-        int cols[kBatch], rows[kBatch];
-        uint8_t m[kBatch];
-        float hz[kBatch];
-        if (kRng) {  // rounds 4q .. 4q+3 = Philox stream 1 + q of this env
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned grp = lane >> 3, k = lane & 7u;
+    bool bad = need;
+    for (int r0 = 0; r0 < n_rounds; r0 += 8) {
+        unsigned pending = __ballot_sync(kFull, bad);
+        while (pending) {
+            // owners of this pass: the four lowest lanes still pending; group g serves the g-th of them
+            unsigned rest = pending;
+            int owner = -1;
 #pragma unroll
-            for (int q = 0; q < kBatch / 4; ++q) {
-                uint32_t w[4];
-                rng_env_stream(key, (uint32_t)i, 1u + (uint32_t)(r0 / 4 + q), w);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) u[4 * q + k] = u01(w[k]);
+            for (unsigned g = 0; g < 4; ++g) {
+                const int b = rest ? __ffs(rest) - 1 : -1;
+                if (g == grp) owner = b;
+                rest &= rest - 1u;
             }
-        } else {
-#pragma unroll
-            for (int k = 0; k < kBatch; ++k)  // the first batch was prefetched by the caller
-                u[k] = (r0 == 0) ? theta0[k] : ((r0 + k < n_rounds) ? __ldg(theta_u + (size_t)i * n_rounds + r0 + k) : 0.f);
-        }
-#pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
-            const float th = __fmul_rn(__fmul_rn(u[k], 2.f), pi_f);                      // :169
-            xs[k] = __fadd_rn(__fmul_rn(cosf(th), P.target_distance), ox);               // :172
-            ys[k] = __fadd_rn(__fmul_rn(sinf(th), P.target_distance), oy);               // :173
-            terrain_cell(T, xs[k], ys[k], cols[k], rows[k]);
-            m[k] = __ldg(T.safe_mask + (size_t)rows[k] * T.W + cols[k]);                 // :220
-            hz[k] = __ldg(T.heightmap + (size_t)rows[k] * T.W + cols[k]);                // :154, used if round k wins
-        }
-#pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
-            if (bad && r0 + k < n_rounds) {  // sequential semantics: the first valid round, else the last tried
-                x = xs[k], y = ys[k], z = hz[k];
-                bad = m[k] == 1;
+            const bool active = owner >= 0 && r0 + (int)k < n_rounds;
+            const int src = owner >= 0 ? owner : (int)lane;
+            const int si = __shfl_sync(kFull, i, src);
+            const float sox = __shfl_sync(kFull, ox, src), soy = __shfl_sync(kFull, oy, src);
+            float xk = 0.f, yk = 0.f, zk = 0.f;
+            bool good = false;
+            if (active) {
+                float u;
+                if (kRng) {  // rounds 4q .. 4q+3 = Philox stream 1 + q of the env
+                    uint32_t w[4];
+                    rng_env_stream(key, (uint32_t)si, 1u + (uint32_t)(r0 + (int)k) / 4u, w);
+                    const uint32_t lo = (k & 1u) ? w[1] : w[0], hi = (k & 1u) ? w[3] : w[2];
+                    u = u01((k & 2u) ? hi : lo);
+                } else {
+                    u = __ldg(theta_u + (size_t)si * n_rounds + r0 + (int)k);
+                }
+                const float th = __fmul_rn(__fmul_rn(u, 2.f), pi_f);                  // :169
+                xk = __fadd_rn(__fmul_rn(cosf(th), P.target_distance), sox);          // :172
+                yk = __fadd_rn(__fmul_rn(sinf(th), P.target_distance), soy);          // :173
+                int col, row;
+                terrain_cell(T, xk, yk, col, row);
+                const uint8_t m = __ldg(T.safe_mask + (size_t)row * T.W + col);       // :220
+                zk = __ldg(T.heightmap + (size_t)row * T.W + col);                    // :154, used if this round wins
+                good = m != 1;
             }
+            const unsigned good_b = __ballot_sync(kFull, good), act_b = __ballot_sync(kFull, active);
+            // an owner finds its group: the number of pending lanes below it
+            const unsigned my_g = (unsigned)__popc(pending & ((1u << lane) - 1u));
+            const bool served = ((pending >> lane) & 1u) != 0u && my_g < 4u;  // (a lane served earlier may still be `bad`)
+            const unsigned sh = served ? 8u * my_g : 0u;
+            const unsigned g_good = (good_b >> sh) & 0xffu, g_act = (act_b >> sh) & 0xffu;
+            const int pick = g_good ? __ffs(g_good) - 1 : 31 - __clz(g_act | 1u);  // first valid round, else the last tried
+            const int from = served ? (int)sh + pick : (int)lane;
+            const float nx = __shfl_sync(kFull, xk, from), ny = __shfl_sync(kFull, yk, from), nz = __shfl_sync(kFull, zk, from);
+            if (served) {
+                cx = nx, cy = ny, cz = nz;                                            // :154 (+ default_root_state z = 0)
+                bad = g_good == 0u;
+            }
+            pending = rest;
         }
     }
-    cx = x;
-    cy = y;
-    cz = z;                                                                  // :154 (+ default_root_state z = 0)
-    chead = __fadd_rn(__fmul_rn(heading_u, __fsub_rn(P.heading_hi, P.heading_lo)), P.heading_lo);  // uniform_(lo, hi)
-    S.time_left[i] = P.resampling_time;
     return bad;
 }
 
@@ -372,7 +388,6 @@ __device__ __forceinline__ unsigned long long make_lookback(unsigned epoch, unsi
 // launch pays one memory round trip for them instead of one per dependent stage (the step is latency-bound).
 struct EnvRegs {
     float px, py, pz, cwx, cwy, cwz, chead, time_left, yaw_var, heading_var;
-    float theta0[8];
     float4 q;
     float2 act;
 };
@@ -382,8 +397,6 @@ __device__ __forceinline__ void post_env_load(int i, bool valid, const float* __
                                               const float* __restrict__ root_quat_w, const RoverMdpState& S,
                                               const VariatesDev& V, EnvRegs& r) {
     r.px = r.py = r.pz = r.cwx = r.cwy = r.cwz = r.chead = r.time_left = r.yaw_var = r.heading_var = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r.theta0[k] = 0.f;
     r.q = make_float4(1.f, 0.f, 0.f, 0.f);
     r.act = make_float2(0.f, 0.f);
     if (valid) {
@@ -396,8 +409,6 @@ __device__ __forceinline__ void post_env_load(int i, bool valid, const float* __
         if (!kRng) {
             r.yaw_var = __ldg(V.yaw_u + i);
             r.heading_var = __ldg(V.heading_u + i);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) r.theta0[k] = (k < V.n_rounds) ? __ldg(V.theta_u + (size_t)i * V.n_rounds + k) : 0.f;
         }
     }
 }
@@ -424,23 +435,27 @@ __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int
     const int n_rounds = V.n_rounds;
     float &px = r.px, &py = r.py, &pz = r.pz, &cwx = r.cwx, &cwy = r.cwy, &cwz = r.cwz, &chead = r.chead;
     float &time_left = r.time_left, &yaw_var = r.yaw_var, &heading_var = r.heading_var;
-    float(&theta0)[8] = r.theta0;
     float4& q = r.q;
     float2& act = r.act;
 #pragma unroll
     for (int k = 0; k < kStats; ++k) st[k] = 0.f;
+    long long spawn_idx = -1;
+    bool cmd_dirty = false;
+    // Which envs draw a new target this step is known up front: a reset env (CommandTerm.reset -> _resample), or one whose
+    // timer runs out in CommandManager.compute below.  The two never meet in one env: the reset sets time_left =
+    // resampling_time, which the launcher requires to exceed step_dt -- so one cooperative draw serves both, and sharing
+    // the env's variates between them is safe.
+    const bool rs_reset = valid && reset && (phases & ROVER_PHASE_RESAMPLE);
+    const bool rs_timer = valid && !rs_reset && (phases & ROVER_PHASE_TIME) && __fsub_rn(time_left, P.step_dt) <= 0.f;
+    float org_x = 0.f, org_y = 0.f;  // env origin of a freshly spawned env stays in registers (no store -> load round trip)
     if (valid) {
-        long long spawn_idx = -1;
-        bool cmd_dirty = false;
-        bool origin_known = false;  // env origin of a freshly spawned env stays in registers (no store -> load round trip)
-        float org_x = 0.f, org_y = 0.f;
-
-        if (kRng && (reset || time_left <= P.step_dt)) {  // the only envs that consume variates this step
+        if (kRng && (reset || rs_timer)) {  // the only envs that consume variates this step
             uint32_t w[4];
             rng_env_stream(key, (uint32_t)i, 0u, w);
             yaw_var = u01(w[0]);
             heading_var = u01(w[1]);
         }
+        bool origin_known = false;
         if (reset && (phases & ROVER_PHASE_SPAWN)) {
             // -- reset_root_state_rover (randomizations.py:12-39)
             if (kRng) spawn_idx = (long long)spawn_perm_at(make_spawn_perm_key(key, (uint32_t)T.n_spawns), (uint32_t)i);
@@ -462,6 +477,15 @@ __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int
             reinterpret_cast<float4*>(root_quat_w)[i] = q;
         }
         on_pose(px, py, pz, q);
+        if ((rs_reset || rs_timer) && !origin_known) {
+            org_x = S.env_origins[3 * (size_t)i];
+            org_y = S.env_origins[3 * (size_t)i + 1];
+        }
+    }
+    // -- _resample_command around the (new) env origin, all lanes of the warp together
+    float nwx = 0.f, nwy = 0.f, nwz = 0.f;
+    const bool exhausted = resample_warp<kRng>(i, rs_reset || rs_timer, P, T, org_x, org_y, theta_u, key, n_rounds, nwx, nwy, nwz);
+    if (valid) {
         if (reset && (phases & ROVER_PHASE_MANAGERS)) {
             // -- ActionManager.reset
             act = make_float2(0.f, 0.f);
@@ -489,12 +513,10 @@ __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int
             S.command_counter[i] = 0;
             S.episode_length_buf[i] = 0;
         }
-        if (reset && (phases & ROVER_PHASE_RESAMPLE)) {
-            // -- CommandTerm._resample: time_left, counter += 1, _resample_command around the (new) env origin
-            const float ox = origin_known ? org_x : S.env_origins[3 * (size_t)i];
-            const float oy = origin_known ? org_y : S.env_origins[3 * (size_t)i + 1];
-            const bool exhausted = resample_command<kRng>(i, P, S, T, ox, oy, theta_u, theta0, key, n_rounds, heading_var,
-                                                          cwx, cwy, cwz, chead);
+        if (rs_reset) {
+            // -- CommandTerm._resample: time_left, counter += 1, the new command
+            cwx = nwx, cwy = nwy, cwz = nwz;
+            chead = __fadd_rn(__fmul_rn(heading_var, __fsub_rn(P.heading_hi, P.heading_lo)), P.heading_lo);  // uniform_(lo, hi)
             st[14] = exhausted ? 1.f : 0.f;
             S.command_counter[i] += 1;
             time_left = P.resampling_time;
@@ -510,13 +532,9 @@ __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int
             S.err_heading[i] = fabsf(wrap_to_pi(__fsub_rn(chead, hw)));
         }
         if (phases & ROVER_PHASE_TIME) time_left = __fsub_rn(time_left, P.step_dt);
-        if ((phases & ROVER_PHASE_TIME) && time_left <= 0.f) {
-            const float ox = origin_known ? org_x : S.env_origins[3 * (size_t)i];
-            const float oy = origin_known ? org_y : S.env_origins[3 * (size_t)i + 1];
-            // (a reset resample above and this one never meet in one step: the reset sets time_left = resampling_time,
-            // which the launcher requires to exceed step_dt -- so sharing the env's variates between them is safe)
-            const bool exhausted = resample_command<kRng>(i, P, S, T, ox, oy, theta_u, theta0, key, n_rounds, heading_var,
-                                                          cwx, cwy, cwz, chead);
+        if (rs_timer) {  // (time_left <= 0 after the decrement, decided above)
+            cwx = nwx, cwy = nwy, cwz = nwz;
+            chead = __fadd_rn(__fmul_rn(heading_var, __fsub_rn(P.heading_hi, P.heading_lo)), P.heading_lo);
             st[14] += exhausted ? 1.f : 0.f;
             st[15] = 1.f;
             S.command_counter[i] += 1;

@@ -159,3 +159,69 @@ def test_post_step_argument_errors(world):
     bad.resampling_time = 0.1
     with pytest.raises(RuntimeError, match="resampling_time"):
         ops.mdp_post_step(buf, bad, th, s.root_pos_w, s.root_quat_w, rng=ops.ResetRng(0, dev))
+
+
+@pytest.mark.parametrize("n,rounds,unsafe", [(96, 16, 0.85), (333, 9, 0.7), (64, 3, 0.5), (1024, 16, 0.97)])
+def test_cooperative_target_draw_under_dense_rejections_against_the_oracle(world, n, rounds, unsafe):
+    """The target rejection loop is warp-cooperative (four resampling envs per pass, eight rounds side by side).  Worst
+    case for that scheme: EVERY env resets (32 owners per warp = 8 passes), most candidates are rejected (several batches
+    of 8 rounds, exhausted envs keep the last candidate tried) and ``n_rounds`` is not a multiple of 8.  Explicit variates
+    and in-kernel variates, two launches and one launch, all against the oracle's sequential loop."""
+    from oracle import step as OS
+    from oracle import terms as OT
+
+    dev, seed = world["dev"], 1234 + n
+    cfg, params, th0, steps, init, tables = _setup(world, n, seed)
+    g = torch.Generator().manual_seed(seed)
+    mask = torch.as_tensor(tables.safe_mask).clone()
+    mask[torch.rand(mask.shape, generator=g) < unsafe] = 1          # 1 = not a valid target cell (terrain_utils.py:220)
+    th = ops.TerrainTablesHandle(tables.heightmap, mask, tables.offset_xy, tables.spawn_table, tables.resolution, dev)
+    otab = OS.TerrainTables(tables.heightmap, mask, tables.offset_xy, tables.spawn_table)
+    s = steps[0]
+
+    def oracle_state():
+        ost = OS.MdpState.zeros(n)
+        ost.pos_cmd_w[:], ost.heading_cmd_w[:], ost.episode_length_buf[:] = init
+        ost.env_origins[:] = s.root_pos_w.cpu()
+        ost.time_left[:] = 150.0
+        ost.pos_cmd_b[:] = torch.tensor([20.0, 0.0, 0.0])           # far_from_target: every env resets
+        return ost
+
+    ost = oracle_state()
+    rngs = [ops.ResetRng(seed, dev, step=7) for _ in range(2)]
+    sp, yaw, head, theta = rngs[0].variates(n, rounds, th.n_spawns)
+    out = OS.oracle_step(ost, s.actions.cpu(), s.root_pos_w.cpu(), s.root_quat_w.cpu(), s.force_matrix_w.cpu(), otab, None,
+                         yaw, theta, head, spawn_by_env=sp)
+    assert len(out.reset_ids) == n
+    if unsafe > 0.9:
+        assert out.stats["target_rounds_exhausted"] > 0, "the fixture must exhaust some envs"
+
+    def fresh():
+        buf = ops.MdpBuffers.allocate(n, dev)
+        src = oracle_state()
+        for k in ("pos_cmd_w", "heading_cmd_w", "pos_cmd_b", "episode_length_buf", "env_origins", "time_left"):
+            getattr(buf, k).copy_(getattr(src, k))
+        return buf
+
+    results = []
+    # (a) in-kernel variates, two launches; (b) in-kernel variates, one launch; (c) explicit arrays, two launches
+    for mode in ("rng2", "rng1", "explicit"):
+        buf, p, q = fresh(), s.root_pos_w.clone(), s.root_quat_w.clone()
+        if mode == "rng1":
+            ops.mdp_step(buf, params, th, s.actions, s.force_matrix_w, p, q, rng=rngs[1], n_rounds=rounds)
+        else:
+            ops.mdp_pre_step(buf, params, s.actions, s.force_matrix_w)
+            if mode == "rng2":
+                ops.mdp_post_step(buf, params, th, p, q, rng=rngs[0], n_rounds=rounds)
+            else:
+                ops.mdp_post_step(buf, params, th, p, q, ops.ResetRng.by_rank(sp.to(dev), buf.reset_flags), yaw.to(dev),
+                                  head.to(dev), theta.to(dev))
+        torch.cuda.synchronize()
+        results.append((buf, p))
+        assert int(buf.stats[13]) == n and int(buf.stats[14]) == out.stats["target_rounds_exhausted"], mode
+        torch.testing.assert_close(buf.pos_cmd_w.cpu(), ost.pos_cmd_w, rtol=1e-6, atol=2e-5)
+        torch.testing.assert_close(buf.heading_cmd_w.cpu(), ost.heading_cmd_w, rtol=1e-6, atol=1e-6)
+        assert torch.equal(p.cpu(), out.root_pos_w)
+    for buf, p in results[1:]:
+        for name in ("pos_cmd_w", "heading_cmd_w", "pos_cmd_b", "time_left", "command_counter", "env_origins"):
+            assert torch.equal(getattr(buf, name), getattr(results[0][0], name)), name
