@@ -68,8 +68,10 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
     // Consumer warps: pattern + line tables, every global load issued before the first shared store.
     ProducerEnv cur, nxt;
     int my_flat_z = 1;
+    // The launch may overlap the tail of the kernel in front of it on the stream (the MDP step that moves reset envs:
+    // common.cuh, launch_overlapped): everything up to grid_dependency_wait() reads only launch-invariant data (barriers,
+    // tensor map, ray pattern, lattice lines); the poses are read after it.
     if (warp == 0) {
-        producer_load(cur, lane, n_iter, pos_w, quat_w);  // cold misses: in flight while the barriers are set up
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
             for (int s = 0; s < kPairFullBars; ++s) bar_init(&sm.full_bar[s], 2);  // TMA bytes + header published
@@ -77,6 +79,8 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
             sm.next_chunk = 0;
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
+        grid_dependency_wait();
+        producer_load(cur, lane, n_iter, pos_w, quat_w);  // cold misses
         __syncwarp();
         producer_window(cur, pc, pattern_radius);
         if (lane < n_iter && lane < kPairEarly && ROVER_SCAN_DBG != 4) {
@@ -128,6 +132,7 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
         }
     }
     if (warp == 1) DBG_STAMP(3);
+    if (warp != 0) grid_dependency_wait();  // (the consumers' stores into `out` come after the producer's anyway)
     const bool flat_z = __syncthreads_and(my_flat_z) != 0;  // also publishes the tables / barriers to every warp
     if (warp == 0) DBG_STAMP(0);
 
@@ -323,12 +328,13 @@ int launch_height_scan_paired(const float* pos_w, const float* quat_w, int n_env
     const float radius = sqrtf(rx * rx + ry * ry) * 1.0001f + 1.0e-3f;
     const int grid = n_envs < n_sms ? n_envs : n_sms;
     if (obs_bf16 != nullptr)
-        height_scan_paired_kernel<true><<<grid, kPairThreads, sizeof(PairSmem), stream>>>(
-            pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, tmap, radius, max_d, base_offset, out, out_stride,
-            reinterpret_cast<__nv_bfloat16*>(obs_bf16), bf16_stride, head_cols);
+        ROVER_CUDA(launch_overlapped(height_scan_paired_kernel<true>, dim3(grid), dim3(kPairThreads), sizeof(PairSmem), stream,
+                                     pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, tmap, radius, max_d, base_offset, out,
+                                     out_stride, reinterpret_cast<__nv_bfloat16*>(obs_bf16), bf16_stride, head_cols));
     else
-        height_scan_paired_kernel<false><<<grid, kPairThreads, sizeof(PairSmem), stream>>>(
-            pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, tmap, radius, max_d, base_offset, out, out_stride, nullptr, 0, 0);
+        ROVER_CUDA(launch_overlapped(height_scan_paired_kernel<false>, dim3(grid), dim3(kPairThreads), sizeof(PairSmem), stream,
+                                     pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, tmap, radius, max_d, base_offset, out,
+                                     out_stride, nullptr, 0, 0));
     return check_launch("height_scan_paired_kernel");
 }
 

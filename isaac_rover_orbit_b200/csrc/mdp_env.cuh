@@ -375,6 +375,33 @@ struct StatsExchangeDev {
     int rank, world;  // world == 0: no exchange
 };
 
+// Sum of each of the 16 statistics over the 32 lanes of a warp, written to out[0..15].  Transposing reduction: every
+// butterfly stage halves the number of values a lane still carries (8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5),
+// a fixed summation tree (deterministic).  Only envs that reset or re-drew their target contribute, so most lanes hold
+// zeros and a warp without such an env skips the shuffles.
+__device__ __forceinline__ void warp_stats_reduce(float (&st)[kStats], int lane, float* __restrict__ out) {
+    static_assert(kStats == 16, "reduction layout");
+    constexpr unsigned kFull = 0xffffffffu;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < kStats; ++k) any |= st[k] != 0.f;
+    if (__ballot_sync(kFull, any) == 0u) {
+        if (lane < kStats) out[lane] = 0.f;
+        return;
+    }
+#pragma unroll
+    for (int width = 8; width >= 1; width >>= 1) {  // lanes' bit (4, 3, 2, 1) picks the half it keeps
+        const bool up = (lane & (2 * width)) != 0;
+#pragma unroll
+        for (int j = 0; j < width; ++j) {
+            const float send = up ? st[j] : st[j + width], keep = up ? st[j + width] : st[j];
+            st[j] = keep + __shfl_xor_sync(kFull, send, 2 * width);
+        }
+    }
+    st[0] += __shfl_xor_sync(kFull, st[0], 1);
+    if ((lane & 1) == 0) out[lane >> 1] = st[0];  // statistic index = lane bits 4..1
+}
+
 // look-back descriptor of the fused step: [epoch : 30 | status : 2 | value : 32]
 constexpr unsigned long long kDescAggregate = 1ull, kDescPrefix = 2ull;
 __device__ __forceinline__ unsigned long long make_lookback(unsigned epoch, unsigned long long status, unsigned value) {

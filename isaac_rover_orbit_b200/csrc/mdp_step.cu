@@ -138,12 +138,7 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
                         phases, st);
 
     // ---- deterministic episode statistics: warp shuffle -> block -> last block sums the partials in order
-#pragma unroll
-    for (int k = 0; k < kStats; ++k) {
-        float v = st[k];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) red[wid][k] = v;
-    }
+    warp_stats_reduce(st, lane, red[wid]);
     __syncthreads();
     if (threadIdx.x < kStats) {
         float v = 0.f;
@@ -242,6 +237,7 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
                      float* __restrict__ block_stats, unsigned int* __restrict__ done_counter, float* __restrict__ stats,
                      float* __restrict__ log_out, float* __restrict__ obs, int obs_stride, int phases,
                      const __grid_constant__ StatsExchangeDev X) {
+    grid_dependency_trigger();  // (see mdp_fused_step_kernel)
     post_step_block<false, kRng>((int)blockIdx.x, (int)gridDim.x, false, root_pos_w, root_quat_w, n, P, S, O, T, V,
                                  out_spawn_index, block_stats, done_counter, stats, log_out, obs, obs_stride, phases, X,
                                  nullptr, 0u);
@@ -277,8 +273,23 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
         bid = s_bid;
         epoch = s_epoch;
     }
+    // the kernel behind this one on the stream (the height scan) may bring its CTAs up as SMs become free: it waits for
+    // this grid's completion before it reads a pose (common.cuh, launch_overlapped)
+    grid_dependency_trigger();
     const int i = bid * ROVER_MDP_BLOCK + threadIdx.x;
-    if (i < n) {  // the post-step's rank-independent inputs: in flight while the pre-step part runs
+    if (i < n) {
+        // every line this env reads, requested before the first dependent use: the launch then pays ONE cold-miss latency
+        // for them instead of one per stage (the compiler cannot hoist the loads over the stores in between).  First the
+        // pre-step's inputs (the actions are loaded right away and lead the way) ...
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.pos_cmd_b + 3 * (size_t)i));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(S.episode_sums + ROVER_NUM_REWARD_TERMS * (size_t)i));
+        {
+            const float* f = force + (size_t)i * P.num_bodies * 3;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(f));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(f + P.num_bodies * 3 - 1));
+        }
+        if ((threadIdx.x & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(S.episode_length_buf + i));
+        // ... then the post-step's rank-independent inputs: in flight while the pre-step part runs
         asm volatile("prefetch.global.L2 [%0];" ::"l"(root_pos_w + 3 * (size_t)i));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(root_quat_w + 4 * (size_t)i));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(S.pos_cmd_w + 3 * (size_t)i));
