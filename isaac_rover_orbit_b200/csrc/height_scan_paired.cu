@@ -68,6 +68,7 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
     // Consumer warps: pattern + line tables, every global load issued before the first shared store.
     ProducerEnv cur, nxt;
     int my_flat_z = 1;
+    grid_dependency_trigger();  // the policy kernel behind this one sets itself up on SMs as this grid's CTAs retire
     // The launch may overlap the tail of the kernel in front of it on the stream (the MDP step that moves reset envs:
     // common.cuh, launch_overlapped): everything up to grid_dependency_wait() reads only launch-invariant data (barriers,
     // tensor map, ray pattern, lattice lines); the poses are read after it.

@@ -265,6 +265,7 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
     int bid = (int)blockIdx.x;
     unsigned epoch = 0u;
     if constexpr (!kRng) {  // (the in-kernel generator needs no reset rank, hence no look-back and no ticket)
+        grid_dependency_wait();  // the ticket counter is re-armed by the previous launch of this kernel
         if (threadIdx.x == 0) {
             s_epoch = (unsigned)*reinterpret_cast<volatile unsigned long long*>(lookback + n_blocks + 1);
             s_bid = (int)atomicAdd(lookback + n_blocks, 1ull);
@@ -305,6 +306,9 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
             asm volatile("prefetch.global.L2 [%0];" ::"l"(S.err_heading + i));
         }
     }
+    // this launch may itself be a programmatic dependent of whatever produced the actions / root state / contacts: the
+    // prefetches above carry no data, everything below reads what the predecessor wrote
+    if constexpr (kRng) grid_dependency_wait();
     const bool reset = pre_step_env(i, new_actions, force, n, P, S, O, pre_phases);
     if ((pre_phases & ROVER_PRE_TERMS) && threadIdx.x == 0) O.block_reset_counts[bid] = 0;  // unused by this path
     post_step_block<true, kRng>(bid, n_blocks, reset, root_pos_w, root_quat_w, n, P, S, O, T, V, out_spawn_index, block_stats,
@@ -535,15 +539,17 @@ extern "C" int rover_mdp_step_v3(const float* new_actions, const float* force_ma
     unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + (size_t)blocks * ROVER_STATS_LEN);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (V.rng != nullptr)
-        mdp_fused_step_kernel<true><<<blocks, ROVER_MDP_BLOCK, 0, st>>>(
-            new_actions, force_matrix_w, root_pos_w, root_quat_w, n_envs, *params, *state, *out, T, V,
-            reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats, log_out, obs, obs_stride, pre_phases,
-            phases, X, reinterpret_cast<unsigned long long*>(lookback));
+        ROVER_CUDA(launch_overlapped(mdp_fused_step_kernel<true>, dim3(blocks), dim3(ROVER_MDP_BLOCK), 0, st, new_actions,
+                                     force_matrix_w, root_pos_w, root_quat_w, (int)n_envs, *params, *state, *out, T, V,
+                                     reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats, log_out, obs,
+                                     (int)obs_stride, (int)pre_phases, (int)phases, X,
+                                     reinterpret_cast<unsigned long long*>(lookback)));
     else
-        mdp_fused_step_kernel<false><<<blocks, ROVER_MDP_BLOCK, 0, st>>>(
-            new_actions, force_matrix_w, root_pos_w, root_quat_w, n_envs, *params, *state, *out, T, V,
-            reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats, log_out, obs, obs_stride, pre_phases,
-            phases, X, reinterpret_cast<unsigned long long*>(lookback));
+        ROVER_CUDA(launch_overlapped(mdp_fused_step_kernel<false>, dim3(blocks), dim3(ROVER_MDP_BLOCK), 0, st, new_actions,
+                                     force_matrix_w, root_pos_w, root_quat_w, (int)n_envs, *params, *state, *out, T, V,
+                                     reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats, log_out, obs,
+                                     (int)obs_stride, (int)pre_phases, (int)phases, X,
+                                     reinterpret_cast<unsigned long long*>(lookback)));
     return check_launch("mdp_fused_step_kernel");
 }
 

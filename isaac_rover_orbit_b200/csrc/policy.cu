@@ -317,6 +317,7 @@ __global__ void policy_pack_kernel(const __grid_constant__ PackArgs a, unsigned 
 __global__ void gaussian_act_kernel(const float* __restrict__ mean, const float* __restrict__ log_std,
                                     const float* __restrict__ eps, int n, float* __restrict__ actions,
                                     float* __restrict__ log_prob) {
+    grid_dependency_wait();  // launched as a programmatic dependent of the forward pass (common.cuh)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float lp = 0.f;
@@ -452,7 +453,7 @@ extern "C" int rover_gaussian_act(const float* mean, const float* log_std, const
     ROVER_CHECK(n_envs >= 0, "rover_gaussian_act: negative n_envs");
     if (n_envs == 0) return 0;
     ROVER_CHECK(mean && log_std && eps && actions, "rover_gaussian_act: NULL argument");
-    gaussian_act_kernel<<<(n_envs + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(mean, log_std, eps, n_envs,
-                                                                                            actions, log_prob);
+    ROVER_CUDA(launch_overlapped(gaussian_act_kernel, dim3((n_envs + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                 mean, log_std, eps, (int)n_envs, actions, log_prob));
     return check_launch("gaussian_act_kernel");
 }

@@ -115,6 +115,9 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
             mb_init(&sm.f_empty[i], kBf16In ? 1 : 4);  // converter warps, or the commit of the MMAs that read the stage
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the observation is what the kernel in front of this one writes: under a programmatic dependent launch
+        // (common.cuh) everything above -- and the weight loads, the TMEM allocation of the other warps -- overlaps its tail
+        grid_dependency_wait();
         if ((int)blockIdx.x < n_tiles)
             for (int c = 0; c < kWsStagesF; ++c) {
                 mb_expect_tx(&sm.f_full[c], chunk_bytes);
@@ -147,6 +150,8 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    grid_dependency_wait();     // every thread, before anything of the predecessor's is read or `mean` is written
+    grid_dependency_trigger();  // (the sampling kernel behind this one only saves its launch latency)
 
     if (warp == 8) {
         // =============================================================== TMA producer
@@ -479,13 +484,13 @@ int launch_policy_forward_ws(const void* obs, int obs_stride, int n_envs, const 
     const int n_tiles = (n_envs + tile_rows - 1) / tile_rows;
     const int grid = n_tiles < n_sms ? n_tiles : n_sms;
     if (bf16_in)
-        policy_forward_ws_kernel<true><<<grid, kWsThreads, kSmemBytes, stream>>>(
-            map, static_cast<const float*>(obs), obs_stride, n_envs, tile_rows, static_cast<const unsigned char*>(packed), mean,
-            value_head ? 1 : 0);
+        ROVER_CUDA(launch_overlapped(policy_forward_ws_kernel<true>, dim3(grid), dim3(kWsThreads), (size_t)kSmemBytes, stream, map,
+                                     static_cast<const float*>(obs), obs_stride, n_envs, tile_rows,
+                                     static_cast<const unsigned char*>(packed), mean, value_head ? 1 : 0));
     else
-        policy_forward_ws_kernel<false><<<grid, kWsThreads, kSmemBytes, stream>>>(
-            map, static_cast<const float*>(obs), obs_stride, n_envs, tile_rows, static_cast<const unsigned char*>(packed), mean,
-            value_head ? 1 : 0);
+        ROVER_CUDA(launch_overlapped(policy_forward_ws_kernel<false>, dim3(grid), dim3(kWsThreads), (size_t)kSmemBytes, stream, map,
+                                     static_cast<const float*>(obs), obs_stride, n_envs, tile_rows,
+                                     static_cast<const unsigned char*>(packed), mean, value_head ? 1 : 0));
     return check_launch("policy_forward_ws_kernel");
 }
 
