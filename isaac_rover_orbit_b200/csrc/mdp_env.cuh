@@ -178,17 +178,67 @@ __device__ __forceinline__ void ackermann_dispatch(const RoverMdpParams& P, floa
     else ackermann_v2(P, lin_p, ang_p, jp, jv);
 }
 
+// collision_active on values already in registers (the AAU rover's 14 bodies); accumulation order = body order
+template <int kBodies>
+__device__ __forceinline__ bool collision_active_regs(const float (&v)[3 * kBodies]) {
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+    for (int b = 0; b < kBodies; ++b) {
+        sx = __fadd_rn(sx, __fmul_rn(v[3 * b], v[3 * b]));
+        sy = __fadd_rn(sy, __fmul_rn(v[3 * b + 1], v[3 * b + 1]));
+        sz = __fadd_rn(sz, __fmul_rn(v[3 * b + 2], v[3 * b + 2]));
+    }
+    return __fadd_rn(__fadd_rn(sqrtf(sx), sqrtf(sy)), sqrtf(sz)) > 1.f;
+}
+
+struct NoMidHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
 // The per-env work of the pre-step (one thread per env); returns the env's reset flag.
+// The step is bound by the latency of ONE warp's dependent chain, so the function is laid out for that: every global
+// load of the env is issued first (the compiler cannot hoist loads over the stores in between -- each late load was
+// another L2 round trip in the chain), then the action term's kinematics, then `mid()` -- a hook in which the caller
+// may start loads of its own that the rest of the pre-step hides (the fused step: variate state -> spawn row) -- then
+// terminations and rewards.
+template <class Mid = NoMidHook>
 __device__ __forceinline__ bool pre_step_env(int i, const float* __restrict__ new_actions, const float* __restrict__ force,
                                              int n, const RoverMdpParams& P, const RoverMdpState& S, const RoverMdpOut& O,
-                                             int phases) {
+                                             int phases, Mid mid = Mid()) {
+    constexpr int kFixedBodies = 14;  // AAU rover: 6 Drive + 4 Steer + 3 Boogie + Body
+    const bool valid = i < n;
+    const bool terms = valid && (phases & ROVER_PRE_TERMS);
+    const bool fixed_bodies = P.num_bodies == kFixedBodies;
     bool reset = false;
-    if (i < n) {
-        float2 a_old, a;
+    // ---- loads
+    float2 a_old = make_float2(0.f, 0.f), a = a_old;
+    long long ep = 0;
+    float bx = 0.f, by = 0.f;
+    float fv[3 * kFixedBodies];
+    float sums_in[ROVER_NUM_REWARD_TERMS];
+    if (valid) {
         if (phases & ROVER_PRE_ACTIONS) {
+            a_old = reinterpret_cast<const float2*>(S.action)[i];
+            a = reinterpret_cast<const float2*>(new_actions)[i];
+        } else {
+            a = reinterpret_cast<const float2*>(S.action)[i];
+            a_old = reinterpret_cast<const float2*>(S.prev_action)[i];
+        }
+    }
+    if (terms) {
+        ep = S.episode_length_buf[i] + 1;
+        bx = S.pos_cmd_b[3 * (size_t)i], by = S.pos_cmd_b[3 * (size_t)i + 1];
+        if (fixed_bodies) {
+            const float* f = force + (size_t)i * kFixedBodies * 3;
+#pragma unroll
+            for (int k = 0; k < 3 * kFixedBodies; ++k) fv[k] = __ldg(f + k);
+        }
+        const float* sums = S.episode_sums + ROVER_NUM_REWARD_TERMS * (size_t)i;
+#pragma unroll
+        for (int k = 0; k < ROVER_NUM_REWARD_TERMS; ++k) sums_in[k] = sums[k];
+    }
+    if (valid && (phases & ROVER_PRE_ACTIONS)) {
         // ---- ActionManager.process_action: prev <- action <- new; term.process_actions (ackermann_actions.py:226-229)
-        a_old = reinterpret_cast<const float2*>(S.action)[i];
-        a = reinterpret_cast<const float2*>(new_actions)[i];
         reinterpret_cast<float2*>(S.prev_action)[i] = a_old;
         reinterpret_cast<float2*>(S.action)[i] = a;
         const float lin_p = __fadd_rn(__fmul_rn(a.x, P.scale_lin), P.offset_lin);
@@ -196,21 +246,17 @@ __device__ __forceinline__ bool pre_step_env(int i, const float* __restrict__ ne
         reinterpret_cast<float2*>(O.processed_actions)[i] = make_float2(lin_p, ang_p);
 
         ackermann_dispatch(P, lin_p, ang_p, O.joint_pos + 4 * (size_t)i, O.joint_vel + 6 * (size_t)i);
-        } else {
-            a = reinterpret_cast<const float2*>(S.action)[i];
-            a_old = reinterpret_cast<const float2*>(S.prev_action)[i];
-        }
-
-        if (phases & ROVER_PRE_TERMS) {
+    }
+    mid();
+    if (terms) {
         // ---- counters (rover_env.py:79)
-        const long long ep = S.episode_length_buf[i] + 1;
         S.episode_length_buf[i] = ep;
 
         // ---- shared quantities of the PREVIOUS command (rover_env.py:82-86 run before the command update)
-        const float bx = S.pos_cmd_b[3 * (size_t)i], by = S.pos_cmd_b[3 * (size_t)i + 1];
         const float d = norm2(bx, by);
         const float ang = atan2f(by, bx);
-        const bool coll = collision_active(force + (size_t)i * P.num_bodies * 3, P.num_bodies);
+        const bool coll = fixed_bodies ? collision_active_regs<kFixedBodies>(fv)
+                                       : collision_active(force + (size_t)i * P.num_bodies * 3, P.num_bodies);
         const float max_len = (float)P.max_episode_length;
 
         // ---- terminations (terminations.py:14-64, ORBIT mdp.time_out)
@@ -249,12 +295,11 @@ __device__ __forceinline__ bool pre_step_env(int i, const float* __restrict__ ne
         for (int k = 0; k < ROVER_NUM_REWARD_TERMS; ++k) {
             const float c = __fmul_rn(__fmul_rn(val[k], P.weight[k]), P.step_dt);
             total = __fadd_rn(total, c);
-            sums[k] = __fadd_rn(sums[k], c);
+            sums[k] = __fadd_rn(sums_in[k], c);
             tr[k] = c;
             tv[k] = val[k];
         }
         O.reward[i] = total;
-        }
     }
     return reset;
 }
@@ -443,6 +488,15 @@ __device__ __forceinline__ void post_env_load(int i, bool valid, const float* __
 // The per-env work of the post-step (one thread per env): spawn / manager resets / resample / command update /
 // observation head; `st` receives the env's contribution to the 16 episode statistics.  On return r.px .. r.q hold the
 // env's FINAL root pose (the spawn pose if it reset).
+// The spawn row an env WOULD get if it reset this step, fetched before the reset decision exists (fused step, in-kernel
+// variates: the row is a function of {seed, step, env} alone).  The chain  rng state -> Philox -> spawn row  -- two cold
+// misses -- then runs beside the pre-step instead of behind it; the 95 % of the lanes that do not reset ignore the row.
+struct SpawnEarly {
+    bool have = false;
+    long long idx = -1;
+    float x = 0.f, y = 0.f, z = 0.f;
+};
+
 struct NoPoseHook {
     __device__ __forceinline__ void operator()(float, float, float, const float4&) const {}
 };
@@ -456,7 +510,8 @@ __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int
                                               const RoverMdpParams& P, const RoverMdpState& S, const RoverMdpOut& O,
                                               const Tables& T, const VariatesDev& V, const RngKey& key,
                                               long long* __restrict__ out_spawn_index, float* __restrict__ obs,
-                                              int obs_stride, int phases, float (&st)[kStats], OnPose on_pose = OnPose()) {
+                                              int obs_stride, int phases, float (&st)[kStats], OnPose on_pose = OnPose(),
+                                              const SpawnEarly early = SpawnEarly()) {
     const long long* __restrict__ spawn_perm = V.spawn_perm;
     const float* __restrict__ theta_u = V.theta_u;
     const int n_rounds = V.n_rounds;
@@ -485,12 +540,18 @@ __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int
         bool origin_known = false;
         if (reset && (phases & ROVER_PHASE_SPAWN)) {
             // -- reset_root_state_rover (randomizations.py:12-39)
-            if (kRng) spawn_idx = (long long)spawn_perm_at(make_spawn_perm_key(key, (uint32_t)T.n_spawns), (uint32_t)i);
-            else spawn_idx = __ldg(spawn_perm + rank);
-            const float* sp = T.spawn + 3 * (size_t)spawn_idx;
-            px = __ldg(sp);
-            py = __ldg(sp + 1);
-            pz = __fadd_rn(__ldg(sp + 2), P.spawn_z_offset);
+            if (kRng && early.have) {
+                spawn_idx = early.idx;
+                px = early.x, py = early.y;
+                pz = __fadd_rn(early.z, P.spawn_z_offset);
+            } else {
+                if (kRng) spawn_idx = (long long)spawn_perm_at(make_spawn_perm_key(key, (uint32_t)T.n_spawns), (uint32_t)i);
+                else spawn_idx = __ldg(spawn_perm + rank);
+                const float* sp = T.spawn + 3 * (size_t)spawn_idx;
+                px = __ldg(sp);
+                py = __ldg(sp + 1);
+                pz = __fadd_rn(__ldg(sp + 2), P.spawn_z_offset);
+            }
             const float angle = __fmul_rn(__fmul_rn(yaw_var, 2.f), 3.1415927f);
             const float half = __fdiv_rn(angle, 2.f);
             q = make_float4(cosf(half), 0.f, 0.f, sinf(half));

@@ -18,6 +18,26 @@
 
 namespace rover {
 
+#ifndef ROVER_MDP_DBG
+#define ROVER_MDP_DBG 0  // 1: globaltimer (ns) stamps of every block of the single-launch step (profiles/mdp_timeline.py)
+#endif
+#if ROVER_MDP_DBG
+__device__ unsigned long long g_mdp_dbg[8][1024];
+#define MDP_STAMP(slot)                                                                  \
+    do {                                                                                 \
+        if (threadIdx.x == 0 && blockIdx.x < 1024) {                                     \
+            unsigned long long t__;                                                      \
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t__));                       \
+            g_mdp_dbg[slot][blockIdx.x] = t__;                                           \
+        }                                                                                \
+    } while (0)
+#else
+#define MDP_STAMP(slot) \
+    do {                \
+    } while (0)
+#endif
+
+
 __global__ void ackermann_kernel(const float* __restrict__ actions, int n, const __grid_constant__ RoverMdpParams P,
                                  float* __restrict__ processed, float* __restrict__ jp, float* __restrict__ jv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -44,6 +64,14 @@ mdp_pre_step_kernel(const float* __restrict__ new_actions, const float* __restri
 }
 
 
+// {seed, step}: one uniform load per thread (L2 / L1 hit after the first); the step word is advanced by the last block
+// of the launch, after every block has read it
+template <bool kRng>
+__device__ __forceinline__ RngKey load_rng_key(const VariatesDev& V) {
+    if (!kRng) return make_rng_key(0ull, 0ull);
+    return make_rng_key(V.rng[0], *reinterpret_cast<volatile unsigned long long*>(V.rng + 1));
+}
+
 template <bool kFused, bool kRng>
 __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool reset_in, float* __restrict__ root_pos_w,
                                                 float* __restrict__ root_quat_w, int n, const RoverMdpParams& P,
@@ -53,11 +81,7 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
                                                 float* __restrict__ stats, float* __restrict__ log_out,
                                                 float* __restrict__ obs, int obs_stride, int phases,
                                                 const StatsExchangeDev& X, unsigned long long* __restrict__ lookback,
-                                                unsigned epoch) {
-    // {seed, step}: one uniform load per thread (L2 / L1 hit after the first); the step word is advanced by the last
-    // block of the launch, after every block has read it
-    RngKey key = make_rng_key(0ull, 0ull);
-    if (kRng) key = make_rng_key(V.rng[0], *reinterpret_cast<volatile unsigned long long*>(V.rng + 1));
+                                                unsigned epoch, const RngKey key, const SpawnEarly early = SpawnEarly()) {
     __shared__ int warp_cnt[ROVER_MDP_BLOCK / 32];
     __shared__ int block_base;
     constexpr int kRedRows = ROVER_MDP_BLOCK / 4;  // 16 row groups of the last-block reduction (>= warps per block)
@@ -135,7 +159,8 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
 
     float st[kStats];
     post_env_work<kRng>(i, valid, reset, rank, er, root_pos_w, root_quat_w, P, S, O, T, V, key, out_spawn_index, obs, obs_stride,
-                        phases, st);
+                        phases, st, NoPoseHook(), early);
+    MDP_STAMP(3);
 
     // ---- deterministic episode statistics: warp shuffle -> block -> last block sums the partials in order
     warp_stats_reduce(st, lane, red[wid]);
@@ -147,8 +172,10 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
     }
     __threadfence();
     __syncthreads();
+    MDP_STAMP(4);
     if (threadIdx.x == 0) is_last = (atomicAdd(done_counter, 1u) == (unsigned)n_blocks - 1u);
     __syncthreads();
+    MDP_STAMP(5);
     if (is_last) {
         // Fixed summation tree (deterministic, same result for the same inputs whatever the block schedule): thread t
         // owns the statistics quad c = t % 4 of the block rows g, g + 16, ... (g = t / 4): float4 loads, kUnroll of them
@@ -225,6 +252,7 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
             }
             if (threadIdx.x == 0) *X.sequence = seq;
         }
+        MDP_STAMP(6);
     }
 }
 
@@ -240,7 +268,7 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
     grid_dependency_trigger();  // (see mdp_fused_step_kernel)
     post_step_block<false, kRng>((int)blockIdx.x, (int)gridDim.x, false, root_pos_w, root_quat_w, n, P, S, O, T, V,
                                  out_spawn_index, block_stats, done_counter, stats, log_out, obs, obs_stride, phases, X,
-                                 nullptr, 0u);
+                                 nullptr, 0u, load_rng_key<kRng>(V));
 }
 
 // rover_mdp_step: pre-step + post-step of one env block in ONE launch (the reset rank comes from a look-back instead of a
@@ -277,6 +305,7 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
     // the kernel behind this one on the stream (the height scan) may bring its CTAs up as SMs become free: it waits for
     // this grid's completion before it reads a pose (common.cuh, launch_overlapped)
     grid_dependency_trigger();
+    MDP_STAMP(0);
     const int i = bid * ROVER_MDP_BLOCK + threadIdx.x;
     if (i < n) {
         // every line this env reads, requested before the first dependent use: the launch then pays ONE cold-miss latency
@@ -309,10 +338,23 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
     // this launch may itself be a programmatic dependent of whatever produced the actions / root state / contacts: the
     // prefetches above carry no data, everything below reads what the predecessor wrote
     if constexpr (kRng) grid_dependency_wait();
-    const bool reset = pre_step_env(i, new_actions, force, n, P, S, O, pre_phases);
+    const RngKey key = load_rng_key<kRng>(V);  // (a cold miss: first consumed in the hook below, after the kinematics)
+    SpawnEarly early;
+    MDP_STAMP(1);
+    const bool reset = pre_step_env(i, new_actions, force, n, P, S, O, pre_phases, [&]() {
+        if constexpr (kRng) {
+            if (i < n && (phases & ROVER_PHASE_SPAWN)) {  // (see SpawnEarly) consumed after the rest of the pre-step
+                early.have = true;
+                early.idx = (long long)spawn_perm_at(make_spawn_perm_key(key, (uint32_t)T.n_spawns), (uint32_t)i);
+                const float* sp = T.spawn + 3 * (size_t)early.idx;
+                early.x = __ldg(sp), early.y = __ldg(sp + 1), early.z = __ldg(sp + 2);
+            }
+        }
+    });
+    MDP_STAMP(2);
     if ((pre_phases & ROVER_PRE_TERMS) && threadIdx.x == 0) O.block_reset_counts[bid] = 0;  // unused by this path
     post_step_block<true, kRng>(bid, n_blocks, reset, root_pos_w, root_quat_w, n, P, S, O, T, V, out_spawn_index, block_stats,
-                                done_counter, stats, log_out, obs, obs_stride, phases, X, lookback, epoch);
+                                done_counter, stats, log_out, obs, obs_stride, phases, X, lookback, epoch, key, early);
 }
 
 // one block: thread (p, k) = (threadIdx.x / 16, threadIdx.x % 16) reads statistic k of rank p's slot consistently
@@ -628,3 +670,9 @@ extern "C" int rover_p2p_close(void* ptr) {
     ROVER_CUDA(cudaIpcCloseMemHandle(ptr));
     return 0;
 }
+
+#if ROVER_MDP_DBG
+extern "C" int rover_debug_mdp_timeline(unsigned long long* host_dst) {
+    return (int)cudaMemcpyFromSymbol(host_dst, rover::g_mdp_dbg, sizeof(rover::g_mdp_dbg));
+}
+#endif
