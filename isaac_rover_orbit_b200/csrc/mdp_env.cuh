@@ -201,13 +201,16 @@ struct NoMidHook {
 // another L2 round trip in the chain), then the action term's kinematics, then `mid()` -- a hook in which the caller
 // may start loads of its own that the rest of the pre-step hides (the fused step: variate state -> spawn row) -- then
 // terminations and rewards.
-template <class Mid = NoMidHook>
+// kParts: kPreState = action-manager shift + terminations + rewards, kPreKinematics = the action term's kinematics (a
+// pure function of the new action: the single-launch step gives it to a second warp, off the env's critical path).
+constexpr int kPreState = 1, kPreKinematics = 2, kPreAll = 3;
+template <int kParts = kPreAll, class Mid = NoMidHook>
 __device__ __forceinline__ bool pre_step_env(int i, const float* __restrict__ new_actions, const float* __restrict__ force,
                                              int n, const RoverMdpParams& P, const RoverMdpState& S, const RoverMdpOut& O,
                                              int phases, Mid mid = Mid()) {
     constexpr int kFixedBodies = 14;  // AAU rover: 6 Drive + 4 Steer + 3 Boogie + Body
     const bool valid = i < n;
-    const bool terms = valid && (phases & ROVER_PRE_TERMS);
+    const bool terms = valid && (phases & ROVER_PRE_TERMS) && (kParts & kPreState);
     const bool fixed_bodies = P.num_bodies == kFixedBodies;
     bool reset = false;
     // ---- loads
@@ -218,9 +221,9 @@ __device__ __forceinline__ bool pre_step_env(int i, const float* __restrict__ ne
     float sums_in[ROVER_NUM_REWARD_TERMS];
     if (valid) {
         if (phases & ROVER_PRE_ACTIONS) {
-            a_old = reinterpret_cast<const float2*>(S.action)[i];
+            if (kParts & kPreState) a_old = reinterpret_cast<const float2*>(S.action)[i];
             a = reinterpret_cast<const float2*>(new_actions)[i];
-        } else {
+        } else if (kParts & kPreState) {
             a = reinterpret_cast<const float2*>(S.action)[i];
             a_old = reinterpret_cast<const float2*>(S.prev_action)[i];
         }
@@ -239,13 +242,17 @@ __device__ __forceinline__ bool pre_step_env(int i, const float* __restrict__ ne
     }
     if (valid && (phases & ROVER_PRE_ACTIONS)) {
         // ---- ActionManager.process_action: prev <- action <- new; term.process_actions (ackermann_actions.py:226-229)
-        reinterpret_cast<float2*>(S.prev_action)[i] = a_old;
-        reinterpret_cast<float2*>(S.action)[i] = a;
-        const float lin_p = __fadd_rn(__fmul_rn(a.x, P.scale_lin), P.offset_lin);
-        const float ang_p = __fadd_rn(__fmul_rn(a.y, P.scale_ang), P.offset_ang);
-        reinterpret_cast<float2*>(O.processed_actions)[i] = make_float2(lin_p, ang_p);
+        if (kParts & kPreState) {
+            reinterpret_cast<float2*>(S.prev_action)[i] = a_old;
+            reinterpret_cast<float2*>(S.action)[i] = a;
+        }
+        if (kParts & kPreKinematics) {
+            const float lin_p = __fadd_rn(__fmul_rn(a.x, P.scale_lin), P.offset_lin);
+            const float ang_p = __fadd_rn(__fmul_rn(a.y, P.scale_ang), P.offset_ang);
+            reinterpret_cast<float2*>(O.processed_actions)[i] = make_float2(lin_p, ang_p);
 
-        ackermann_dispatch(P, lin_p, ang_p, O.joint_pos + 4 * (size_t)i, O.joint_vel + 6 * (size_t)i);
+            ackermann_dispatch(P, lin_p, ang_p, O.joint_pos + 4 * (size_t)i, O.joint_vel + 6 * (size_t)i);
+        }
     }
     mid();
     if (terms) {
@@ -497,6 +504,10 @@ struct SpawnEarly {
     float x = 0.f, y = 0.f, z = 0.f;
 };
 
+struct NoStatsHook {
+    __device__ __forceinline__ void operator()(float (&)[kStats]) const {}
+};
+
 struct NoPoseHook {
     __device__ __forceinline__ void operator()(float, float, float, const float4&) const {}
 };
@@ -504,14 +515,16 @@ struct NoPoseHook {
 // on_pose(px, py, pz, q) is called (valid envs only) as soon as the env's FINAL root pose is known -- right after the
 // spawn -- so that a consumer of the pose (the height scan fused behind this step, height_scan_step.cu) can start while
 // the rest of the env's work (target rejection sampling, command update, stores) is still running.
-template <bool kRng, class OnPose = NoPoseHook>
+// on_stats(st) is called by ALL lanes (warp-converged, valid or not) once the env's 16 statistics are final -- after the
+// target draw, before metrics / command update / observation head.
+template <bool kRng, class OnPose = NoPoseHook, class OnStats = NoStatsHook>
 __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int rank, EnvRegs& r,
                                               float* __restrict__ root_pos_w, float* __restrict__ root_quat_w,
                                               const RoverMdpParams& P, const RoverMdpState& S, const RoverMdpOut& O,
                                               const Tables& T, const VariatesDev& V, const RngKey& key,
                                               long long* __restrict__ out_spawn_index, float* __restrict__ obs,
                                               int obs_stride, int phases, float (&st)[kStats], OnPose on_pose = OnPose(),
-                                              const SpawnEarly early = SpawnEarly()) {
+                                              const SpawnEarly early = SpawnEarly(), OnStats on_stats = OnStats()) {
     const long long* __restrict__ spawn_perm = V.spawn_perm;
     const float* __restrict__ theta_u = V.theta_u;
     const int n_rounds = V.n_rounds;
@@ -610,6 +623,13 @@ __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int
             time_left = P.resampling_time;
             cmd_dirty = true;
         }
+        if (rs_timer) {  // (applied below, after the metrics; its statistics are known now)
+            st[14] += exhausted ? 1.f : 0.f;
+            st[15] = 1.f;
+        }
+    }
+    on_stats(st);
+    if (valid) {
         if (out_spawn_index) out_spawn_index[i] = spawn_idx;
 
         // -- CommandManager.compute(dt): metrics, time_left, time-based resample, _update_command
@@ -623,8 +643,6 @@ __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int
         if (rs_timer) {  // (time_left <= 0 after the decrement, decided above)
             cwx = nwx, cwy = nwy, cwz = nwz;
             chead = __fadd_rn(__fmul_rn(heading_var, __fsub_rn(P.heading_hi, P.heading_lo)), P.heading_lo);
-            st[14] += exhausted ? 1.f : 0.f;
-            st[15] = 1.f;
             S.command_counter[i] += 1;
             time_left = P.resampling_time;
             cmd_dirty = true;

@@ -72,8 +72,132 @@ __device__ __forceinline__ RngKey load_rng_key(const VariatesDev& V) {
     return make_rng_key(V.rng[0], *reinterpret_cast<volatile unsigned long long*>(V.rng + 1));
 }
 
-template <bool kFused, bool kRng>
-__device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool reset_in, float* __restrict__ root_pos_w,
+// barrier of the ROVER_MDP_BLOCK threads that own an env (the single-launch step runs extra kinematics warps in the CTA
+// that are gone by then: a named barrier with an explicit count instead of __syncthreads())
+__device__ __forceinline__ void mdp_block_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ROVER_MDP_BLOCK) : "memory"); }
+
+// shared memory of one MDP CTA
+struct MdpShared {
+    int warp_cnt[ROVER_MDP_BLOCK / 32];
+    int block_base;
+    float red[ROVER_MDP_BLOCK / 4][kStats];  // 16 row groups of the last-block reduction (>= warps per block)
+    double pub[kStats];
+    int is_last;
+};
+
+// barrier among 64 threads on hardware barrier kId
+template <int kId>
+__device__ __forceinline__ void sync64() { asm volatile("bar.sync %0, 64;" ::"n"(kId) : "memory"); }
+
+// The block's share of the 16 episode statistics -> its row of block_stats, then a ticket: the CTA that takes the last
+// one owns the launch-wide reduction (sh.is_last).  Called by the ROVER_MDP_BLOCK threads that own an env.
+__device__ __forceinline__ void publish_block_stats(float (&st)[kStats], MdpShared& sh, int bid, int n_blocks,
+                                                    float* __restrict__ block_stats, unsigned int* __restrict__ done_counter) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    warp_stats_reduce(st, lane, sh.red[wid]);
+    mdp_block_sync();
+    if (threadIdx.x < kStats) {
+        float v = 0.f;
+        for (int w = 0; w < ROVER_MDP_BLOCK / 32; ++w) v += sh.red[w][threadIdx.x];
+        block_stats[(size_t)bid * kStats + threadIdx.x] = v;
+    }
+    __threadfence();
+    mdp_block_sync();
+    MDP_STAMP(4);
+    if (threadIdx.x == 0) sh.is_last = (atomicAdd(done_counter, 1u) == (unsigned)n_blocks - 1u) ? 1 : 0;
+}
+
+// Launch-wide reduction by the CTA that took the last ticket; `tid` in [0, 64), the 64 callers synchronise on hardware
+// barrier kBar.  Fixed summation tree (deterministic, same result for the same inputs whatever the block schedule): thread
+// t owns the statistics quad c = t % 4 of the block rows g, g + 16, ... (g = t / 4): float4 loads, kUnroll of them in
+// flight per thread, so the 16 KB of partials (L2) cost one or two round trips instead of a chain of them; the 16 row
+// groups are then combined in order of g.
+template <bool kFused, bool kRng, int kBar>
+__device__ __forceinline__ void final_stats_reduce(int tid, MdpShared& sh, int n_blocks, const RoverMdpParams& P,
+                                                   const VariatesDev& V, const float* __restrict__ block_stats,
+                                                   unsigned int* __restrict__ done_counter, float* __restrict__ stats,
+                                                   float* __restrict__ log_out, int phases, const StatsExchangeDev& X,
+                                                   unsigned long long* __restrict__ lookback, unsigned epoch) {
+    static_assert(ROVER_MDP_BLOCK == 64 && kStats == 16, "last-block reduction layout");
+    constexpr int kGroups = ROVER_MDP_BLOCK / 4, kUnroll = 16;
+    const int c4 = tid & 3, g = tid >> 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (unsigned b0 = g; b0 < (unsigned)n_blocks; b0 += kGroups * kUnroll) {
+        float4 x[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const unsigned bb = b0 + u * kGroups;
+            x[u] = bb < (unsigned)n_blocks ? __ldcg(reinterpret_cast<const float4*>(block_stats + (size_t)bb * kStats) + c4)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) acc.x += x[u].x, acc.y += x[u].y, acc.z += x[u].z, acc.w += x[u].w;
+    }
+    sync64<kBar>();  // sh.red[] is free: every thread of the CTA passed the block-level reduction
+    sh.red[g][4 * c4 + 0] = acc.x, sh.red[g][4 * c4 + 1] = acc.y, sh.red[g][4 * c4 + 2] = acc.z, sh.red[g][4 * c4 + 3] = acc.w;
+    sync64<kBar>();
+    double total = 0.0;
+    if (tid < kStats) {
+        float t = 0.f;
+        for (int q = 0; q < kGroups; ++q) t += sh.red[q][tid];
+        stats[tid] += t;
+        // extras["log"] of the ORBIT managers' reset() (A.2), refreshed only by a launch that reset something -- the
+        // reference calls _reset_idx only then (rover_env.py:89-91), so the previous values stay visible otherwise:
+        //   Episode Reward/<term> = mean(episode_sums[ids]) / max_episode_length_s, Episode Termination/<term> =
+        //   count, Metrics/target_pose/<m> = mean over ids; [13] = number of resets, [14], [15] as in stats
+        const float cnt = __shfl_sync(0xffffu, t, 13);  // the 16 statistics live in lanes 0..15 of one warp
+        if (log_out != nullptr && (phases & ROVER_PHASE_MANAGERS) && cnt > 0.f) {
+            float v = t;
+            if (tid < ROVER_NUM_REWARD_TERMS) v = __fdiv_rn(__fdiv_rn(t, cnt), P.episode_length_s);
+            else if (tid == 11 || tid == 12) v = __fdiv_rn(t, cnt);
+            log_out[tid] = v;
+        }
+        if (tid == 0) {
+            *done_counter = 0u;  // re-arm for the next launch
+            if (kRng) V.rng[1] = V.rng[1] + 1ull;  // next launch = next step of the variate streams
+            if (kFused && !kRng) {  // fused step, explicit variates: next launch = next epoch, tickets from 0 again
+                lookback[n_blocks] = 0ull;
+                lookback[n_blocks + 1] = (unsigned long long)(epoch + 1u);
+            }
+        }
+        if (X.world > 0) {
+            total = X.cumulative[tid] + (double)t;
+            X.cumulative[tid] = total;
+        }
+    }
+    // ---- multi-GPU: publish the running totals into this rank's slot of every rank's mailbox (peer stores over
+    //      NVLink).  A slot holds a sequence number and two value buffers; the writer fills buffer (seq + 1) & 1 in
+    //      every mailbox, fences once, then stores seq + 1 everywhere -- one system-scope fence per step, all peers
+    //      in flight together.  No collective, no extra launch.
+    if (X.world > 0) {
+        if (tid < kStats) sh.pub[tid] = total;
+        sync64<kBar>();
+        const unsigned long long seq = *X.sequence + 1ull;
+        for (int e = tid; e < X.world * kStats; e += ROVER_MDP_BLOCK) {
+            const int p = e / kStats, k = e % kStats;
+            unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
+            reinterpret_cast<volatile double*>(slot + 8)[(seq & 1ull) * kStats + k] = sh.pub[k];
+        }
+        __threadfence_system();
+        sync64<kBar>();
+        for (int p = tid; p < X.world; p += ROVER_MDP_BLOCK) {
+            unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
+            *reinterpret_cast<volatile unsigned long long*>(slot) = seq;
+        }
+        if (tid == 0) *X.sequence = seq;
+    }
+}
+
+// hardware barrier 2: the env warps of a split CTA announce the ticket (arrive), its kinematics warps wait for it (sync)
+__device__ __forceinline__ void split_ticket_arrive() { asm volatile("bar.arrive 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void split_ticket_wait() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+// kSplit (single-launch step with in-kernel variates): the statistics leave the env warps as soon as they are complete --
+// after the target draw, before metrics / command update / observation head -- where the fence in front of the ticket
+// finds no recent stores to wait for, and the launch-wide reduction of the last CTA is done by its kinematics warps
+// while the env warps finish their envs.
+template <bool kFused, bool kRng, bool kSplit = false>
+__device__ __forceinline__ void post_step_block(MdpShared& sh, int bid, int n_blocks, bool reset_in, float* __restrict__ root_pos_w,
                                                 float* __restrict__ root_quat_w, int n, const RoverMdpParams& P,
                                                 const RoverMdpState& S, const RoverMdpOut& O, const Tables& T,
                                                 const VariatesDev& V, long long* __restrict__ out_spawn_index,
@@ -82,11 +206,8 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
                                                 float* __restrict__ obs, int obs_stride, int phases,
                                                 const StatsExchangeDev& X, unsigned long long* __restrict__ lookback,
                                                 unsigned epoch, const RngKey key, const SpawnEarly early = SpawnEarly()) {
-    __shared__ int warp_cnt[ROVER_MDP_BLOCK / 32];
-    __shared__ int block_base;
-    constexpr int kRedRows = ROVER_MDP_BLOCK / 4;  // 16 row groups of the last-block reduction (>= warps per block)
-    __shared__ float red[kRedRows][kStats];
-    __shared__ bool is_last;
+    int(&warp_cnt)[ROVER_MDP_BLOCK / 32] = sh.warp_cnt;
+    int& block_base = sh.block_base;
     const int i = bid * ROVER_MDP_BLOCK + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool valid = i < n;
@@ -112,9 +233,9 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 if (lane == 0) block_base = acc;
             }
-            __syncthreads();
+            mdp_block_sync();
         } else {
-            __syncthreads();
+            mdp_block_sync();
             if (wid == 0) {
                 // decoupled look-back (single pass): publish this block's count, walk back over the predecessors' descriptors
                 // until one carries an inclusive prefix, publish our own.  Logical block ids are tickets, so every
@@ -150,7 +271,7 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
                     block_base = base;
                 }
             }
-            __syncthreads();
+            mdp_block_sync();
         }
         rank = block_base + __popc(ballot & ((1u << lane) - 1u));
         for (int w = 0; w < wid; ++w) rank += warp_cnt[w];
@@ -158,101 +279,28 @@ __device__ __forceinline__ void post_step_block(int bid, int n_blocks, bool rese
     }
 
     float st[kStats];
-    post_env_work<kRng>(i, valid, reset, rank, er, root_pos_w, root_quat_w, P, S, O, T, V, key, out_spawn_index, obs, obs_stride,
-                        phases, st, NoPoseHook(), early);
-    MDP_STAMP(3);
-
-    // ---- deterministic episode statistics: warp shuffle -> block -> last block sums the partials in order
-    warp_stats_reduce(st, lane, red[wid]);
-    __syncthreads();
-    if (threadIdx.x < kStats) {
-        float v = 0.f;
-        for (int w = 0; w < ROVER_MDP_BLOCK / 32; ++w) v += red[w][threadIdx.x];
-        block_stats[(size_t)bid * kStats + threadIdx.x] = v;
-    }
-    __threadfence();
-    __syncthreads();
-    MDP_STAMP(4);
-    if (threadIdx.x == 0) is_last = (atomicAdd(done_counter, 1u) == (unsigned)n_blocks - 1u);
-    __syncthreads();
-    MDP_STAMP(5);
-    if (is_last) {
-        // Fixed summation tree (deterministic, same result for the same inputs whatever the block schedule): thread t
-        // owns the statistics quad c = t % 4 of the block rows g, g + 16, ... (g = t / 4): float4 loads, kUnroll of them
-        // in flight per thread, so the 16 KB of partials (L2) cost one or two round trips instead of a chain of them;
-        // the 16 row groups are then combined in order of g.
-        static_assert(ROVER_MDP_BLOCK == 64 && kStats == 16, "last-block reduction layout");
-        constexpr int kGroups = ROVER_MDP_BLOCK / 4, kUnroll = 16;
-        const int c4 = threadIdx.x & 3, g = threadIdx.x >> 2;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (unsigned b0 = g; b0 < (unsigned)n_blocks; b0 += kGroups * kUnroll) {
-            float4 x[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const unsigned bb = b0 + u * kGroups;
-                x[u] = bb < (unsigned)n_blocks ? __ldcg(reinterpret_cast<const float4*>(block_stats + (size_t)bb * kStats) + c4)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) acc.x += x[u].x, acc.y += x[u].y, acc.z += x[u].z, acc.w += x[u].w;
+    if constexpr (kSplit) {
+        post_env_work<kRng>(i, valid, reset, rank, er, root_pos_w, root_quat_w, P, S, O, T, V, key, out_spawn_index, obs,
+                            obs_stride, phases, st, NoPoseHook(), early, [&](float(&stv)[kStats]) {
+                                publish_block_stats(stv, sh, bid, n_blocks, block_stats, done_counter);
+                                __threadfence_block();
+                                split_ticket_arrive();
+                            });
+        MDP_STAMP(3);
+        return;
+    } else {
+        post_env_work<kRng>(i, valid, reset, rank, er, root_pos_w, root_quat_w, P, S, O, T, V, key, out_spawn_index, obs,
+                            obs_stride, phases, st, NoPoseHook(), early);
+        MDP_STAMP(3);
+        // ---- deterministic episode statistics: warp shuffle -> block -> last block sums the partials in order
+        publish_block_stats(st, sh, bid, n_blocks, block_stats, done_counter);
+        mdp_block_sync();
+        MDP_STAMP(5);
+        if (sh.is_last) {
+            final_stats_reduce<kFused, kRng, 1>((int)threadIdx.x, sh, n_blocks, P, V, block_stats, done_counter, stats, log_out,
+                                                phases, X, lookback, epoch);
+            MDP_STAMP(6);
         }
-        __syncthreads();  // red[] is free: every thread passed the block-level reduction above
-        red[g][4 * c4 + 0] = acc.x, red[g][4 * c4 + 1] = acc.y, red[g][4 * c4 + 2] = acc.z, red[g][4 * c4 + 3] = acc.w;
-        __syncthreads();
-        constexpr int G = kGroups;
-        double total = 0.0;
-        if (threadIdx.x < kStats) {
-            float t = 0.f;
-            for (int q = 0; q < G; ++q) t += red[q][threadIdx.x];
-            stats[threadIdx.x] += t;
-            // extras["log"] of the ORBIT managers' reset() (A.2), refreshed only by a launch that reset something -- the
-            // reference calls _reset_idx only then (rover_env.py:89-91), so the previous values stay visible otherwise:
-            //   Episode Reward/<term> = mean(episode_sums[ids]) / max_episode_length_s, Episode Termination/<term> =
-            //   count, Metrics/target_pose/<m> = mean over ids; [13] = number of resets, [14], [15] as in stats
-            const float cnt = __shfl_sync(0xffffu, t, 13);  // the 16 statistics live in lanes 0..15 of warp 0
-            if (log_out != nullptr && (phases & ROVER_PHASE_MANAGERS) && cnt > 0.f) {
-                const int k = (int)threadIdx.x;
-                float v = t;
-                if (k < ROVER_NUM_REWARD_TERMS) v = __fdiv_rn(__fdiv_rn(t, cnt), P.episode_length_s);
-                else if (k == 11 || k == 12) v = __fdiv_rn(t, cnt);
-                log_out[k] = v;
-            }
-            if (threadIdx.x == 0) {
-                *done_counter = 0u;  // re-arm for the next launch
-                if (kRng) V.rng[1] = V.rng[1] + 1ull;  // next launch = next step of the variate streams
-                if (kFused && !kRng) {  // fused step, explicit variates: next launch = next epoch, tickets from 0 again
-                    lookback[n_blocks] = 0ull;
-                    lookback[n_blocks + 1] = (unsigned long long)(epoch + 1u);
-                }
-            }
-            if (X.world > 0) {
-                total = X.cumulative[threadIdx.x] + (double)t;
-                X.cumulative[threadIdx.x] = total;
-            }
-        }
-        // ---- multi-GPU: publish the running totals into this rank's slot of every rank's mailbox (peer stores over
-        //      NVLink).  A slot holds a sequence number and two value buffers; the writer fills buffer (seq + 1) & 1 in
-        //      every mailbox, fences once, then stores seq + 1 everywhere -- one system-scope fence per step, all peers
-        //      in flight together.  No collective, no extra launch.
-        if (X.world > 0) {
-            __shared__ double pub[kStats];
-            if (threadIdx.x < kStats) pub[threadIdx.x] = total;
-            __syncthreads();
-            const unsigned long long seq = *X.sequence + 1ull;
-            for (int e = threadIdx.x; e < X.world * kStats; e += ROVER_MDP_BLOCK) {
-                const int p = e / kStats, k = e % kStats;
-                unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
-                reinterpret_cast<volatile double*>(slot + 8)[(seq & 1ull) * kStats + k] = pub[k];
-            }
-            __threadfence_system();
-            __syncthreads();
-            for (int p = threadIdx.x; p < X.world; p += ROVER_MDP_BLOCK) {
-                unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
-                *reinterpret_cast<volatile unsigned long long*>(slot) = seq;
-            }
-            if (threadIdx.x == 0) *X.sequence = seq;
-        }
-        MDP_STAMP(6);
     }
 }
 
@@ -265,8 +313,9 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
                      float* __restrict__ block_stats, unsigned int* __restrict__ done_counter, float* __restrict__ stats,
                      float* __restrict__ log_out, float* __restrict__ obs, int obs_stride, int phases,
                      const __grid_constant__ StatsExchangeDev X) {
+    __shared__ MdpShared sh;
     grid_dependency_trigger();  // (see mdp_fused_step_kernel)
-    post_step_block<false, kRng>((int)blockIdx.x, (int)gridDim.x, false, root_pos_w, root_quat_w, n, P, S, O, T, V,
+    post_step_block<false, kRng>(sh, (int)blockIdx.x, (int)gridDim.x, false, root_pos_w, root_quat_w, n, P, S, O, T, V,
                                  out_spawn_index, block_stats, done_counter, stats, log_out, obs, obs_stride, phases, X,
                                  nullptr, 0u, load_rng_key<kRng>(V));
 }
@@ -277,8 +326,8 @@ mdp_post_step_kernel(float* __restrict__ root_pos_w, float* __restrict__ root_qu
 // Logical block ids are ALWAYS tickets: the look-back spins on predecessors, which is only safe if every predecessor
 // has started -- blockIdx order guarantees that on an idle GPU only, a ticket taken at block start guarantees it under
 // MPS, concurrent kernels or a partitioned device as well (one atomic per block).
-template <bool kRng>
-__global__ void __launch_bounds__(ROVER_MDP_BLOCK)
+template <bool kRng, bool kSplit = false>
+__global__ void __launch_bounds__(kSplit ? 2 * ROVER_MDP_BLOCK : ROVER_MDP_BLOCK)
 mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __restrict__ force,
                       float* __restrict__ root_pos_w, float* __restrict__ root_quat_w, int n,
                       const __grid_constant__ RoverMdpParams P, const __grid_constant__ RoverMdpState S,
@@ -289,6 +338,7 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
                       const __grid_constant__ StatsExchangeDev X, unsigned long long* __restrict__ lookback) {
     __shared__ int s_bid;
     __shared__ unsigned s_epoch;
+    __shared__ MdpShared sh;
     const int n_blocks = (int)gridDim.x;
     int bid = (int)blockIdx.x;
     unsigned epoch = 0u;
@@ -306,6 +356,31 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
     // this grid's completion before it reads a pose (common.cuh, launch_overlapped)
     grid_dependency_trigger();
     MDP_STAMP(0);
+    if constexpr (kSplit) {
+        // warps 2, 3 of the CTA: the action term's kinematics of the CTA's envs (AckermannAction2: ~25 % of the pre-step's
+        // dependent chain, a function of the new action only) beside the warps that own the envs, then gone
+        static_assert(kRng, "the split CTA is the in-kernel-variates step");
+        if (threadIdx.x >= ROVER_MDP_BLOCK) {
+            grid_dependency_wait();
+            pre_step_env<kPreKinematics>(bid * ROVER_MDP_BLOCK + (int)threadIdx.x - ROVER_MDP_BLOCK, new_actions, force, n, P, S,
+                                         O, pre_phases);
+            // ... then they wait for the CTA's ticket: if it was the launch's last one, the launch-wide reduction of the
+            // statistics is theirs (the env warps are still busy with metrics / command update / observation head)
+            split_ticket_wait();
+            if (sh.is_last) {
+                final_stats_reduce<true, kRng, 3>((int)threadIdx.x - ROVER_MDP_BLOCK, sh, n_blocks, P, V, block_stats,
+                                                  done_counter, stats, log_out, phases, X, lookback, 0u);
+#if ROVER_MDP_DBG
+                if (threadIdx.x == ROVER_MDP_BLOCK) {
+                    unsigned long long t__;
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t__));
+                    g_mdp_dbg[6][blockIdx.x] = t__;
+                }
+#endif
+            }
+            return;
+        }
+    }
     const int i = bid * ROVER_MDP_BLOCK + threadIdx.x;
     if (i < n) {
         // every line this env reads, requested before the first dependent use: the launch then pays ONE cold-miss latency
@@ -341,7 +416,7 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
     const RngKey key = load_rng_key<kRng>(V);  // (a cold miss: first consumed in the hook below, after the kinematics)
     SpawnEarly early;
     MDP_STAMP(1);
-    const bool reset = pre_step_env(i, new_actions, force, n, P, S, O, pre_phases, [&]() {
+    const bool reset = pre_step_env<kSplit ? kPreState : kPreAll>(i, new_actions, force, n, P, S, O, pre_phases, [&]() {
         if constexpr (kRng) {
             if (i < n && (phases & ROVER_PHASE_SPAWN)) {  // (see SpawnEarly) consumed after the rest of the pre-step
                 early.have = true;
@@ -353,7 +428,7 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
     });
     MDP_STAMP(2);
     if ((pre_phases & ROVER_PRE_TERMS) && threadIdx.x == 0) O.block_reset_counts[bid] = 0;  // unused by this path
-    post_step_block<true, kRng>(bid, n_blocks, reset, root_pos_w, root_quat_w, n, P, S, O, T, V, out_spawn_index, block_stats,
+    post_step_block<true, kRng, kSplit>(sh, bid, n_blocks, reset, root_pos_w, root_quat_w, n, P, S, O, T, V, out_spawn_index, block_stats,
                                 done_counter, stats, log_out, obs, obs_stride, phases, X, lookback, epoch, key, early);
 }
 
@@ -580,7 +655,15 @@ extern "C" int rover_mdp_step_v3(const float* new_actions, const float* force_ma
     float* block_stats = scratch;
     unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + (size_t)blocks * ROVER_STATS_LEN);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (V.rng != nullptr)
+    // ROVER_MDP_SPLIT=0: the in-kernel-variates step without the kinematics warps (A/B timing, profiles/r02_step.md)
+    static const bool split = !(std::getenv("ROVER_MDP_SPLIT") && std::getenv("ROVER_MDP_SPLIT")[0] == '0');
+    if (V.rng != nullptr && split)
+        ROVER_CUDA(launch_overlapped(mdp_fused_step_kernel<true, true>, dim3(blocks), dim3(2 * ROVER_MDP_BLOCK), 0, st, new_actions,
+                                     force_matrix_w, root_pos_w, root_quat_w, (int)n_envs, *params, *state, *out, T, V,
+                                     reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats, log_out, obs,
+                                     (int)obs_stride, (int)pre_phases, (int)phases, X,
+                                     reinterpret_cast<unsigned long long*>(lookback)));
+    else if (V.rng != nullptr)
         ROVER_CUDA(launch_overlapped(mdp_fused_step_kernel<true>, dim3(blocks), dim3(ROVER_MDP_BLOCK), 0, st, new_actions,
                                      force_matrix_w, root_pos_w, root_quat_w, (int)n_envs, *params, *state, *out, T, V,
                                      reinterpret_cast<long long*>(out_spawn_index), block_stats, counter, stats, log_out, obs,

@@ -43,11 +43,11 @@ for rep in range(4):
     nb = (n + 63) // 64
     t = t[:, :nb].astype(np.int64)
     t0 = t[0].min()
-    names = ["block start", "prefetch+early issued", "pre-step done", "post work done", "partials stored+fenced", "ticket taken", "last block done"]
+    names = ["block start", "prefetches issued", "pre-step done", "post work done", "partials stored+fenced"]
     print(f"rep {rep}: event time {a.elapsed_time(b) * 1e3:.1f} us, resets {int(buf.stats[13])}")
-    for k, nm in enumerate(names[:6]):
+    for k, nm in enumerate(names):
         d = t[k] - t0
         print(f"  {nm:26s} min {d.min():6d}  median {int(np.median(d)):6d}  p90 {int(np.percentile(d, 90)):6d}  max {d.max():6d} ns")
     last = t[6].max() - t0
-    print(f"  last block done            {last} ns;   block lifetime (start -> ticket) median {int(np.median(t[5] - t[0]))} max {int((t[5] - t[0]).max())} ns")
+    print(f"  launch-wide reduction done {last} ns;   env warps' lifetime (start -> post work done) median {int(np.median(t[3] - t[0]))} max {int((t[3] - t[0]).max())} ns")
     buf.stats.zero_()
