@@ -616,7 +616,37 @@ def run_ours(args):
             actions, _ = torch.ops.rover_b200.gaussian_act(mean, net.log_std_parameter, eps_sets[i % 4])
             act_buf.copy_(actions)
 
+        # the PPO rollout evaluates the value network on the same observation every step (skrl PPO.record_transition):
+        # as two forward passes, and as ONE pass over the observation (rover_policy_value_forward)
+        from isaac_rover_orbit_b200.policy import DeterministicNeuralNetwork, policy_value_forward
+
+        vnet = DeterministicNeuralNetwork(device=dev)
+        gv = torch.Generator().manual_seed(4)
+        vnet.load_state_dict({k: torch.randn(t.shape, generator=gv) * (0.05 if t.dim() == 2 else 0.01)
+                              for k, t in vnet.state_dict().items()})
+        values = [None]
+
+        def step_value_separate(i):
+            w.physics(i)
+            w.mdp(i, act_buf)
+            w.scan(i)
+            actions, _, _ = net.act({"states": w.obs}, eps=eps_sets[i % 4])
+            values[0] = vnet.compute({"states": w.obs})[0]
+            act_buf.copy_(actions)
+
+        def step_value_one_pass(i):
+            w.physics(i)
+            w.mdp(i, act_buf)
+            w.scan(i)
+            mean, values[0] = policy_value_forward(net, vnet, w.obs)
+            actions, _ = torch.ops.rover_b200.gaussian_act(mean, net.log_std_parameter, eps_sets[i % 4])
+            act_buf.copy_(actions)
+
         t32 = max_over_ranks([time_steps(graphed(step_fp32), ksteps, 3, flush, stream).mean()])[0] * 1e-3
+        act_buf.zero_()
+        tv2 = max_over_ranks([time_steps(graphed(step_value_separate), ksteps, 3, flush, stream).mean()])[0] * 1e-3
+        act_buf.zero_()
+        tv1 = max_over_ranks([time_steps(graphed(step_value_one_pass), ksteps, 3, flush, stream).mean()])[0] * 1e-3
         act_buf.zero_()
         t16 = max_over_ranks([time_steps(graphed(step_bf16), ksteps, 3, flush, stream).mean()])[0] * 1e-3
         act_buf.zero_()
@@ -625,6 +655,10 @@ def run_ours(args):
                             "actions fed back to the next step; physics replaced by a synthetic pose update",
                 "env_steps_per_s": n * world / t32, "us_per_step": t32 * 1e6, "cuda_graph": not args.no_graph,
                 "finite_actions": bool(torch.isfinite(act_buf).all().item()),
+                "rollout_with_value": {"two_passes_us_per_step": tv2 * 1e6, "one_pass_us_per_step": tv1 * 1e6,
+                                       "env_steps_per_s": n * world / tv1,
+                                       "how": "the closed loop + the value network on the same observation (PPO rollout): "
+                                              "rover_policy_forward + rover_value_forward vs rover_policy_value_forward"},
                 "bf16_observation": {"env_steps_per_s": n * world / t16, "us_per_step": t16 * 1e6,
                                      "how": "rover_height_scan_obs writes the bf16 mirror, rover_policy_forward_bf16 reads it"},
                 "fused_scan_encoder": {"env_steps_per_s": n * world / tfu, "us_per_step": tfu * 1e6,

@@ -374,6 +374,12 @@ int rover_policy_forward(const float* obs, int32_t obs_stride, int32_t n_envs, c
  * linear output, no tanh.  `packed` comes from rover_policy_pack with out_dim[5] == 1; value [N] fp32. */
 int rover_value_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed, float* value,
                         void* stream);
+/* Policy AND value network in ONE pass over the observation -- what a PPO rollout evaluates every step (skrl PPO:
+ * policy.act in the trainer loop, skrl_utils.py:139-142, value.act in record_transition; models.py:89-102 + :151-162).
+ * The observation tile streams through the SM once and meets both heightmap encoders; mean [N,2] and value [N] are
+ * bit-identical to rover_policy_forward / rover_value_forward on the same blobs. */
+int rover_policy_value_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed_policy,
+                               const void* packed_value, float* mean, float* value, void* stream);
 /* The same two networks on a bf16 copy of the observation, obs_bf16 [N, stride] (stride % 8 == 0, rows 16-byte
  * aligned; columns 0..963 are read), as rover_height_scan_obs writes it.  A TMA tile of that buffer is the MMA operand
  * as it lands (no conversion stage, half the bytes); results are bit-identical to the fp32 entry points fed with

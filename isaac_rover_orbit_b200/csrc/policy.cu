@@ -339,7 +339,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int launch_policy_forward_ws(const void* obs, int obs_stride, int n_envs, const void* packed, float* out,
-                             bool value_head, bool bf16_in, cudaStream_t stream);  // policy_ws.cu
+                             bool value_head, bool bf16_in, cudaStream_t stream, const void* packed2 = nullptr,
+                             float* value2 = nullptr);  // policy_ws.cu
 
 }  // namespace rover
 
@@ -418,6 +419,21 @@ static int policy_or_value_forward(const float* obs, int32_t obs_stride, int32_t
 extern "C" int rover_policy_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed,
                                     float* mean, void* stream) {
     return policy_or_value_forward(obs, obs_stride, n_envs, packed, mean, stream, false);
+}
+
+extern "C" int rover_policy_value_forward(const float* obs, int32_t obs_stride, int32_t n_envs, const void* packed_policy,
+                                          const void* packed_value, float* mean, float* value, void* stream) {
+    using namespace rover;
+    ROVER_CHECK(n_envs >= 0, "rover_policy_value_forward: negative n_envs");
+    if (n_envs == 0) return 0;
+    ROVER_CHECK(obs && packed_policy && packed_value && mean && value, "rover_policy_value_forward: NULL argument");
+    ROVER_CHECK(obs_stride >= kObsCols && obs_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0,
+                "rover_policy_value_forward: obs rows must be 16-byte aligned (obs_stride %% 4 == 0, got %d); allocate the "
+                "observation buffer with ops.alloc_obs()", obs_stride);
+    ROVER_CHECK((reinterpret_cast<uintptr_t>(packed_policy) & 127) == 0 && (reinterpret_cast<uintptr_t>(packed_value) & 127) == 0,
+                "rover_policy_value_forward: packed blob not 128B aligned");
+    return launch_policy_forward_ws(obs, obs_stride, n_envs, packed_policy, mean, false, false, static_cast<cudaStream_t>(stream),
+                                    packed_value, value);
 }
 
 static int forward_bf16(const uint16_t* obs_bf16, int32_t stride, int32_t n_envs, const void* packed, float* out,

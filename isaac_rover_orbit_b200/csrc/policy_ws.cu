@@ -16,6 +16,12 @@
 //               layer l+1; its thread 0 streams W1..W5 (bulk copies into one 40 KB buffer; W3 in two K halves) and
 //               issues the MMAs of layers 1-5 into one 256-column accumulator.
 // Same arithmetic as v1 (bf16 operands, fp32 accumulation, same K order inside a layer), so the means are identical.
+//
+// kDual (fp32 observations): policy AND value network in one pass over the observation (models.py:89-102 + :151-162; the
+// rollout needs both every step).  The tile's A operand meets both W0 images (two 80-column accumulators per D0 buffer),
+// the layer group then runs layers 1-5 once per network.  TMEM: 2 x 160 D0 columns + a 192-column accumulator, so layer 2
+// (N = 256) runs as two N halves and its input operand sits in planes 24-31, which the first half's output (planes
+// 0-15) does not touch.  Same arithmetic per network, so both outputs equal the two single passes bit for bit.
 #include "policy_common.cuh"
 
 #ifndef ROVER_POLICY_DBG
@@ -41,11 +47,14 @@ constexpr int kWsThreads = 352;
 constexpr int kWsChunkK = 32;
 constexpr int kWsChunks = 31;  // observation columns [0, 992) cover the encoder input [3, 964)
 constexpr int kWsStagesF = 5;
+constexpr int kWsStagesFDual = 4;  // the second W0 image takes the shared memory of one observation stage
 constexpr int kWsStagesA = 2;
 constexpr int kWsStagesW = 3;
 constexpr int kWsW0Chunk = (kWsChunkK / 8) * 80 * 16;  // 5,120 B of the packed W0 image per chunk
 constexpr int kWsWBuf = 40 * 1024;                 // largest single weight load: W4, or one K half of W3
 constexpr uint32_t kWsColD0 = 0, kWsColD0Stride = 128, kWsColAcc = 256;
+constexpr uint32_t kWsColD0StrideDual = 160, kWsColAccDual = 320;  // D0[buf] = [policy 80 | value 80]; accumulator: 192 columns
+constexpr int kWsBiasFloats = 80 + 64 + 256 + 160 + 128 + 16;
 
 static_assert(weight_bytes(1) <= kWsWBuf && weight_bytes(2) <= kWsWBuf && weight_bytes(3) == 2 * kWsWBuf &&
                   weight_bytes(4) <= kWsWBuf && weight_bytes(5) <= kWsWBuf,
@@ -58,13 +67,16 @@ constexpr int kBfChunkK = 64;
 constexpr int kBfChunks = 16;                 // columns [0, 1024); beyond column 963 the tensor map zero-fills
 constexpr int kBfStagesW = 3;                 // 10 KB W0 chunks in the space of a_bf16[] + w0[]
 
-struct WsSmem {
-    float stage_f[kWsStagesF][kTileM * kWsChunkK];        // 5 x 16 KB, TMA destinations (1024-byte aligned)
+template <bool kDual>
+struct WsSmemT {
+    static constexpr int kNets = kDual ? 2 : 1;
+    static constexpr int kStagesFT = kDual ? kWsStagesFDual : kWsStagesF;
+    float stage_f[kStagesFT][kTileM * kWsChunkK];         // 5 (4) x 16 KB, TMA destinations (1024-byte aligned)
     unsigned char a_bf16[kWsStagesA][4 * kWsPlane];       // 2 x 8 KB   } bf16-observation mode: three 10 KB W0
-    unsigned char w0[kWsStagesW][kWsW0Chunk];             // 3 x 5 KB   } chunks live in these two arrays
+    unsigned char w0[kWsStagesW][kNets * kWsW0Chunk];     // 3 x 5 KB   } chunks live in these two arrays
     unsigned char act[32 * kWsPlane];                     // A operand of layers 1..5 (K <= 256): 64 KB
     unsigned char w[kWsWBuf];                             // weights of the current layer
-    float bias[80 + 64 + 256 + 160 + 128 + 16];
+    float bias[kNets][kWsBiasFloats];
     unsigned long long f_full[kWsStagesF], f_empty[kWsStagesF];
     unsigned long long a_full[kWsStagesA], a_empty[kWsStagesA];
     unsigned long long w0_full[kWsStagesW], w0_empty[kWsStagesW];
@@ -72,21 +84,30 @@ struct WsSmem {
     unsigned long long w_full, acc_done;
     uint32_t tmem_base;
 };
-static_assert(sizeof(WsSmem) + 1024 <= 227 * 1024, "WsSmem exceeds the shared memory of one SM");
+using WsSmem = WsSmemT<false>;
+static_assert(sizeof(WsSmem) + 1024 <= 227 * 1024 && sizeof(WsSmemT<true>) + 1024 <= 227 * 1024,
+              "WsSmem exceeds the shared memory of one SM");
+static_assert(kWsBiasFloats * 4 == kPackedBytes - kBiasOffset, "bias block of the packed blob");
 static_assert(offsetof(WsSmem, w0) == offsetof(WsSmem, a_bf16) + kWsStagesA * 4 * kWsPlane &&
                   kBfStagesW * kW0ChunkBytes <= kWsStagesA * 4 * kWsPlane + kWsStagesW * kWsW0Chunk,
               "bf16-observation mode: W0 ring overlays a_bf16[] + w0[]");
 static_assert(kTileM * kBfChunkK * 2 == kTileM * kWsChunkK * 4, "both modes use the same 16 KB stages");
 
-template <bool kBf16In>
+// kDual: `packed` = policy, `packed2` = value network, outputs `mean` [N, 2] and `value2` [N]; else one network
+// (value_head: linear [N] output instead of tanh [N, 2]).
+template <bool kBf16In, bool kDual = false>
 __global__ void __launch_bounds__(kWsThreads, 1)
 policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const float* __restrict__ obs, int obs_stride,
                          int n_envs, int tile_rows, const unsigned char* __restrict__ packed, float* __restrict__ mean,
-                         int value_head) {
+                         int value_head, const unsigned char* __restrict__ packed2, float* __restrict__ value2) {
+    static_assert(!(kDual && kBf16In), "the two-network pass reads fp32 observations");
+    using Smem = WsSmemT<kDual>;
+    constexpr int kNets = Smem::kNets, kStagesFK = Smem::kStagesFT;
+    constexpr uint32_t kColD0Stride = kDual ? kWsColD0StrideDual : kWsColD0Stride, kColAcc = kDual ? kWsColAccDual : kWsColAcc;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic on the __shared__ array, so that the compiler keeps
     // the address space (an integer round-trip turns every access into a generic LD/ST)
-    WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_dyn + ((1024u - (sptr(smem_dyn) & 1023u)) & 1023u));
+    Smem& sm = *reinterpret_cast<Smem*>(smem_dyn + ((1024u - (sptr(smem_dyn) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // A tile holds tile_rows <= 128 environments (multiple of 8, chosen by the launcher so that the tiles fill whole
     // rounds of the grid: 65536 envs on 148 SMs -> 586 tiles of 112 instead of 512 of 128 = 3.96 instead of 3.46 -> 4
@@ -95,7 +116,8 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
     constexpr int kChunks = kBf16In ? kBfChunks : kWsChunks;
     constexpr int kChunkK = kBf16In ? kBfChunkK : kWsChunkK;        // observation columns per chunk
     constexpr int kStagesW = kBf16In ? kBfStagesW : kWsStagesW;
-    constexpr int kW0Chunk = kBf16In ? kW0ChunkBytes : kWsW0Chunk;  // bytes of the packed W0 image per chunk
+    constexpr int kW0Chunk = kBf16In ? kW0ChunkBytes : kWsW0Chunk;  // bytes of ONE packed W0 image per chunk
+    constexpr int kW0Stage = kNets * kW0Chunk;                      // bytes of a W0 ring stage
     const uint32_t chunk_bytes = (uint32_t)tile_rows * 128u;        // 32 fp32 or 64 bf16 columns per row
     unsigned char* const w0_ring = kBf16In ? &sm.a_bf16[0][0] : &sm.w0[0][0];
 #if ROVER_POLICY_DBG
@@ -110,7 +132,7 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
     if (tid == 8 * 32) {
         // the producer sets up its own ring and starts the first loads before the CTA-wide barrier below
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&obs_map)) : "memory");
-        for (int i = 0; i < kWsStagesF; ++i) {
+        for (int i = 0; i < kStagesFK; ++i) {
             mb_init(&sm.f_full[i], 1);
             mb_init(&sm.f_empty[i], kBf16In ? 1 : 4);  // converter warps, or the commit of the MMAs that read the stage
         }
@@ -119,7 +141,7 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
         // (common.cuh) everything above -- and the weight loads, the TMEM allocation of the other warps -- overlaps its tail
         grid_dependency_wait();
         if ((int)blockIdx.x < n_tiles)
-            for (int c = 0; c < kWsStagesF; ++c) {
+            for (int c = 0; c < kStagesFK; ++c) {
                 mb_expect_tx(&sm.f_full[c], chunk_bytes);
                 tma_2d(sm.stage_f[c], &obs_map, c * kChunkK, blockIdx.x * tile_rows, &sm.f_full[c]);
             }
@@ -159,18 +181,18 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
             int sf = 0;
             uint32_t pf = 0;  // completed passes over the ring (parity)
             int dbg_g = 0;
-            bool first = true;  // chunks 0 .. kWsStagesF-1 of the first tile were issued in the prologue
+            bool first = true;  // chunks 0 .. kStagesFK-1 of the first tile were issued in the prologue
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int row0 = tile * tile_rows;
                 for (int c = 0; c < kChunks; ++c) {
-                    if (!(first && c < kWsStagesF)) {
+                    if (!(first && c < kStagesFK)) {
                         mb_wait(&sm.f_empty[sf], (pf & 1u) ^ 1u);
                         mb_expect_tx(&sm.f_full[sf], chunk_bytes);
                         tma_2d(sm.stage_f[sf], &obs_map, c * kChunkK, row0, &sm.f_full[sf]);
                     }
                     if (dbg_g < 128) PDBG(dbg_g);
                     ++dbg_g;
-                    if (++sf == kWsStagesF) sf = 0, ++pf;
+                    if (++sf == kStagesFK) sf = 0, ++pf;
                 }
                 first = false;
             }
@@ -183,8 +205,10 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int c = 0; c < kChunks; ++c) {
                     mb_wait(&sm.w0_empty[sw], (pw & 1u) ^ 1u);
-                    mb_expect_tx(&sm.w0_full[sw], kW0Chunk);
-                    bulk_g2s(w0_ring + sw * kW0Chunk, packed + (size_t)c * kW0Chunk, kW0Chunk, &sm.w0_full[sw]);
+                    mb_expect_tx(&sm.w0_full[sw], kW0Stage);
+                    bulk_g2s(w0_ring + sw * kW0Stage, packed + (size_t)c * kW0Chunk, kW0Chunk, &sm.w0_full[sw]);
+                    if (kDual)
+                        bulk_g2s(w0_ring + sw * kW0Stage + kW0Chunk, packed2 + (size_t)c * kW0Chunk, kW0Chunk, &sm.w0_full[sw]);
                     if (++sw == kStagesW) sw = 0, ++pw;
                 }
             }
@@ -200,13 +224,13 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
                 const int buf = i & 1;
                 mb_wait(&sm.d0_empty[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);  // the layer group has drained D0[buf]
                 tc_fence_after();
-                const uint32_t d0 = tmem + kWsColD0 + buf * kWsColD0Stride;
+                const uint32_t d0 = tmem + kWsColD0 + buf * kColD0Stride;
                 for (int c = 0; c < kChunks; ++c) {
                     if (kBf16In) mb_wait(&sm.f_full[sa], pa & 1u);  // sa / pa walk the 5-stage TMA ring in this mode
                     else mb_wait(&sm.a_full[sa], pa & 1u);
                     mb_wait(&sm.w0_full[sw], pw & 1u);
                     tc_fence_after();
-                    const uint32_t b0 = sptr(w0_ring + sw * kW0Chunk);
+                    const uint32_t b0 = sptr(w0_ring + sw * kW0Stage);
                     if (kBf16In) {
                         const uint32_t a0 = sptr(sm.stage_f[sa]);
 #pragma unroll
@@ -216,15 +240,17 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
                     } else {
                         const uint32_t a0 = sptr(sm.a_bf16[sa]);
 #pragma unroll
-                        for (int j = 0; j < kWsChunkK / 16; ++j)
-                            umma(d0, make_desc(a0 + j * 2 * kWsPlane, kWsPlane), make_desc(b0 + j * 2 * 80 * 16, 80 * 16), idesc0,
-                                 (c | j) != 0);
+                        for (int net = 0; net < kNets; ++net)
+#pragma unroll
+                            for (int j = 0; j < kWsChunkK / 16; ++j)
+                                umma(d0 + net * 80, make_desc(a0 + j * 2 * kWsPlane, kWsPlane),
+                                     make_desc(b0 + net * kW0Chunk + j * 2 * 80 * 16, 80 * 16), idesc0, (c | j) != 0);
                         umma_commit(&sm.a_empty[sa]);  // A stage and W0 stage are free once these MMAs retire
                     }
                     if (dbg_g < 128) PDBG(512 + dbg_g);
                     ++dbg_g;
                     umma_commit(&sm.w0_empty[sw]);
-                    if (++sa == (kBf16In ? kWsStagesF : kWsStagesA)) sa = 0, ++pa;
+                    if (++sa == (kBf16In ? kStagesFK : kWsStagesA)) sa = 0, ++pa;
                     if (++sw == kStagesW) sw = 0, ++pw;
                 }
                 umma_commit(&sm.d0_full[buf]);
@@ -238,8 +264,10 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
         // =============================================================== converters: fp32 stage -> bf16 A operand
         // first the packed weights into L2 (326 KB; after an L2 flush every layer's first load was a cold miss that the
         // layer group waited for: 21 k instead of 13 k cycles for the first tile)
-        for (int off = (tid - 128) * 128; off < kPackedBytes; off += 128 * 128)
+        for (int off = (tid - 128) * 128; off < kPackedBytes; off += 128 * 128) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(packed + off));
+            if (kDual) asm volatile("prefetch.global.L2 [%0];" ::"l"(packed2 + off));
+        }
         const int row = tid - 128;  // tile row
         const int sx = row & 7;     // SWIZZLE_128B: 16-byte unit u of row r sits at unit u ^ (r & 7)
         int sf = 0, sa = 0;
@@ -281,7 +309,7 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
                 }
                 if (tid == 128 && dbg_g < 128) PDBG(384 + dbg_g);
                 ++dbg_g;
-                if (++sf == kWsStagesF) sf = 0, ++pf;
+                if (++sf == kStagesFK) sf = 0, ++pf;
                 if (++sa == kWsStagesA) sa = 0, ++pa;
             }
         }
@@ -289,22 +317,24 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
         // =============================================================== layer group (warps 0-3): layers 1..5
         const int row = tid;  // TMEM lane == tile row; warp w may touch lanes 32w .. 32w+31
         const uint32_t t_lane = (uint32_t)(warp * 32) << 16;
-        const uint32_t acc = tmem + kWsColAcc;
+        const uint32_t acc = tmem + kColAcc;
         const uint32_t a0 = sptr(sm.act), b0 = sptr(sm.w);
         uint32_t ph_w = 0, ph_acc = 0;
-        // weights of layer l (or one K half of layer 3) into the single weight buffer; only thread 0 calls these
-        auto load_w = [&](int byte_offset, int bytes) {
+        // weights of layer l (or one K half of layer 3) of network `net` into the single weight buffer; only thread 0
+        // calls these
+        auto load_w = [&](int net, int byte_offset, int bytes) {
             mb_expect_tx(&sm.w_full, (uint32_t)bytes);
-            bulk_g2s(sm.w, packed + byte_offset, (uint32_t)bytes, &sm.w_full);
+            bulk_g2s(sm.w, (kDual && net ? packed2 : packed) + byte_offset, (uint32_t)bytes, &sm.w_full);
         };
-        // D[128 x nn] (+)= A[planes plane0 ..] x W^T, k_steps MMAs of K = 16; then commit to acc_done
-        auto issue_mma = [&](int plane0, int k_steps, int nn, bool accumulate) {
+        // D[128 x nn] (+)= A[planes plane0 ..] x W^T, k_steps MMAs of K = 16; then commit to acc_done.  The weight image in
+        // the buffer has n_image rows per plane; the MMA uses rows n_row0 .. n_row0 + nn - 1 of it.
+        auto issue_mma = [&](int plane0, int k_steps, int nn, bool accumulate, int n_image, int n_row0) {
             tc_fence_after();
             mb_wait(&sm.w_full, ph_w);
             const uint32_t idesc = make_idesc(nn);
             for (int j = 0; j < k_steps; ++j)
-                umma(acc, make_desc(a0 + (plane0 + 2 * j) * kWsPlane, kWsPlane), make_desc(b0 + j * 2 * nn * 16, nn * 16), idesc,
-                     accumulate || j != 0);
+                umma(acc, make_desc(a0 + (plane0 + 2 * j) * kWsPlane, kWsPlane),
+                     make_desc(b0 + j * 2 * n_image * 16 + n_row0 * 16, n_image * 16), idesc, accumulate || j != 0);
             umma_commit(&sm.acc_done);
         };
         auto wait_acc = [&]() {
@@ -317,19 +347,28 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
             fence_async_smem();
             layer_group_sync();
         };
-        if (tid == 0) load_w(weight_offset(1), weight_bytes(1));
+        if (tid == 0) load_w(0, weight_offset(1), weight_bytes(1));
         {   // biases: cold global loads that only this group needs (and only ~one tile-time from now), so they stay out
             // of the CTA-wide prologue that the observation stream waits for
-            constexpr int kBiasFloats = (kPackedBytes - kBiasOffset) / 4;
-            float b[(kBiasFloats + 127) / 128];
+            constexpr int kPer = (kWsBiasFloats + 127) / 128;
+            float b[kNets][kPer];
 #pragma unroll
-            for (int k = 0; k < (kBiasFloats + 127) / 128; ++k)
-                b[k] = tid + 128 * k < kBiasFloats ? __ldg(reinterpret_cast<const float*>(packed + kBiasOffset) + tid + 128 * k) : 0.f;
+            for (int net = 0; net < kNets; ++net)
 #pragma unroll
-            for (int k = 0; k < (kBiasFloats + 127) / 128; ++k)
-                if (tid + 128 * k < kBiasFloats) sm.bias[tid + 128 * k] = b[k];
+                for (int k = 0; k < kPer; ++k)
+                    b[net][k] = tid + 128 * k < kWsBiasFloats
+                                    ? __ldg(reinterpret_cast<const float*>((kDual && net ? packed2 : packed) + kBiasOffset) + tid + 128 * k)
+                                    : 0.f;
+#pragma unroll
+            for (int net = 0; net < kNets; ++net)
+#pragma unroll
+                for (int k = 0; k < kPer; ++k)
+                    if (tid + 128 * k < kWsBiasFloats) sm.bias[net][tid + 128 * k] = b[net][k];
             layer_group_sync();
         }
+        // layer 2's input operand: planes 0.. (one network), planes 24..31 in the two-network pass, where layer 2 runs
+        // as two N halves and the first half's output (planes 0..15) must not overwrite it
+        constexpr int kA2Plane = kDual ? 24 : 0;
         int i = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
             const int buf = i & 1;
@@ -344,86 +383,120 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
                 else
                     inject[j] = live ? __ldg(obs + (size_t)grow * obs_stride + j) : 0.f;
             }
-            // ---- layer 0 epilogue: D0[buf] -> A1 (80 columns)
-#define LDBG(k)                                        \
-    do {                                               \
-        if (tid == 0 && i < 8) PDBG(1024 + 16 * i + (k)); \
+#define LDBG(k)                                                       \
+    do {                                                              \
+        if (tid == 0 && i < 8 && net == 0) PDBG(1024 + 16 * i + (k)); \
     } while (0)
-            LDBG(0);
-            mb_wait(&sm.d0_full[buf], ((uint32_t)i >> 1) & 1u);
-            tc_fence_after();
-            LDBG(1);
-            epilogue_to_act(tmem + t_lane + kWsColD0 + buf * kWsColD0Stride, layer_n(0), sm.bias, sm.act, row, nullptr);
-            publish_act();
-            if (tid == 0) {
-                mb_arrive(&sm.d0_empty[buf]);  // the layer-0 issuer may start tile i+2 into D0[buf]
-                issue_mma(0, layer_k(1) / 16, layer_n(1), false);
-            }
-            ph_w ^= 1u;
-            LDBG(2);
-            wait_acc();
-            LDBG(3);
-            if (tid == 0) load_w(weight_offset(2), weight_bytes(2));
-            // ---- layer 1 epilogue -> A2 = [e(60), obs[:, 0:4]]
-            epilogue_to_act(acc + t_lane, layer_n(1), sm.bias + (bias_offset(1) - kBiasOffset) / 4, sm.act, row, inject);
-            publish_act();
-            if (tid == 0) issue_mma(0, layer_k(2) / 16, layer_n(2), false);
-            ph_w ^= 1u;
-            LDBG(4);
-            wait_acc();
-            LDBG(5);
-            if (tid == 0) load_w(weight_offset(3), kWsWBuf);  // W3, K planes 0..15
-            // ---- layer 2 epilogue -> A3 (256 columns); layer 3 in two K halves through the 40 KB weight buffer
-            epilogue_to_act(acc + t_lane, layer_n(2), sm.bias + (bias_offset(2) - kBiasOffset) / 4, sm.act, row, nullptr);
-            publish_act();
-            if (tid == 0) issue_mma(0, 8, layer_n(3), false);
-            ph_w ^= 1u;
-            LDBG(6);
-            wait_acc();
-            LDBG(7);
-            if (tid == 0) {
-                load_w(weight_offset(3) + kWsWBuf, kWsWBuf);  // W3, K planes 16..31
-                issue_mma(16, 8, layer_n(3), true);
-            }
-            ph_w ^= 1u;
-            wait_acc();
-            LDBG(8);
-            if (tid == 0) load_w(weight_offset(4), weight_bytes(4));
-            // ---- layer 3 epilogue -> A4
-            epilogue_to_act(acc + t_lane, layer_n(3), sm.bias + (bias_offset(3) - kBiasOffset) / 4, sm.act, row, nullptr);
-            publish_act();
-            if (tid == 0) issue_mma(0, layer_k(4) / 16, layer_n(4), false);
-            ph_w ^= 1u;
-            LDBG(9);
-            wait_acc();
-            LDBG(10);
-            if (tid == 0) load_w(weight_offset(5), weight_bytes(5));
-            // ---- layer 4 epilogue -> A5
-            epilogue_to_act(acc + t_lane, layer_n(4), sm.bias + (bias_offset(4) - kBiasOffset) / 4, sm.act, row, nullptr);
-            publish_act();
-            if (tid == 0) issue_mma(0, layer_k(5) / 16, layer_n(5), false);
-            ph_w ^= 1u;
-            LDBG(11);
-            wait_acc();
-            LDBG(12);
-            if (tid == 0 && tile + (int)gridDim.x < n_tiles) load_w(weight_offset(1), weight_bytes(1));  // next tile's W1
-            // ---- last layer: mean = tanh(D5 + b5), two real columns
-            {
-                float v[8];
-                tmem_ld8(acc + t_lane, v);
-                const float* b5 = sm.bias + (bias_offset(5) - kBiasOffset) / 4;
-                if (live && value_head) {
-                    mean[grow] = v[0] + b5[0];  // DeterministicNeuralNetwork (models.py:151-162): linear output, no tanh
-                } else if (live) {
-                    float2 m;
-                    m.x = tanhf(v[0] + b5[0]);
-                    m.y = tanhf(v[1] + b5[1]);
-                    *reinterpret_cast<float2*>(mean + 2 * (size_t)grow) = m;
+#pragma unroll
+            for (int net = 0; net < kNets; ++net) {
+                const float* bias = sm.bias[net];
+                const bool last_net = net == kNets - 1;
+                // ---- layer 0 epilogue: D0[buf][net] -> A1 (80 columns)
+                LDBG(0);
+                if (net == 0) {
+                    mb_wait(&sm.d0_full[buf], ((uint32_t)i >> 1) & 1u);
+                    tc_fence_after();
                 }
+                LDBG(1);
+                epilogue_to_act(tmem + t_lane + kWsColD0 + buf * kColD0Stride + net * 80, layer_n(0), bias, sm.act, row, nullptr);
+                publish_act();
+                if (tid == 0) {
+                    if (last_net) mb_arrive(&sm.d0_empty[buf]);  // the layer-0 issuer may start tile i+2 into D0[buf]
+                    issue_mma(0, layer_k(1) / 16, layer_n(1), false, layer_n(1), 0);
+                }
+                ph_w ^= 1u;
+                LDBG(2);
+                wait_acc();
+                LDBG(3);
+                if (tid == 0) load_w(net, weight_offset(2), weight_bytes(2));
+                // ---- layer 1 epilogue -> A2 = [e(60), obs[:, 0:4]]
+                epilogue_to_act(acc + t_lane, layer_n(1), bias + (bias_offset(1) - kBiasOffset) / 4, sm.act + kA2Plane * kWsPlane, row,
+                                inject);
+                publish_act();
+                if (!kDual) {
+                    if (tid == 0) issue_mma(0, layer_k(2) / 16, layer_n(2), false, layer_n(2), 0);
+                    ph_w ^= 1u;
+                    LDBG(4);
+                    wait_acc();
+                    LDBG(5);
+                    if (tid == 0) load_w(net, weight_offset(3), kWsWBuf);  // W3, K planes 0..15
+                    // ---- layer 2 epilogue -> A3 (256 columns); layer 3 in two K halves through the 40 KB weight buffer
+                    epilogue_to_act(acc + t_lane, layer_n(2), bias + (bias_offset(2) - kBiasOffset) / 4, sm.act, row, nullptr);
+                    publish_act();
+                } else {
+                    // ---- layer 2 as two N halves through the 192-column accumulator (W2 stays in the weight buffer)
+                    constexpr int kHalf = layer_n(2) / 2;
+                    if (tid == 0) issue_mma(kA2Plane, layer_k(2) / 16, kHalf, false, layer_n(2), 0);
+                    ph_w ^= 1u;
+                    wait_acc();
+                    epilogue_to_act(acc + t_lane, kHalf, bias + (bias_offset(2) - kBiasOffset) / 4, sm.act, row, nullptr);
+                    publish_act();
+                    if (tid == 0) {  // (w_full completed its phase above: the second half must not wait on it again)
+                        tc_fence_after();
+                        const uint32_t idesc = make_idesc(kHalf);
+                        for (int j = 0; j < layer_k(2) / 16; ++j)
+                            umma(acc, make_desc(a0 + (kA2Plane + 2 * j) * kWsPlane, kWsPlane),
+                                 make_desc(b0 + j * 2 * layer_n(2) * 16 + kHalf * 16, layer_n(2) * 16), idesc, j != 0);
+                        umma_commit(&sm.acc_done);
+                    }
+                    wait_acc();
+                    if (tid == 0) load_w(net, weight_offset(3), kWsWBuf);  // W3, K planes 0..15
+                    epilogue_to_act(acc + t_lane, kHalf, bias + (bias_offset(2) - kBiasOffset) / 4 + kHalf,
+                                    sm.act + (kHalf / 8) * kWsPlane, row, nullptr);
+                    publish_act();
+                }
+                if (tid == 0) issue_mma(0, 8, layer_n(3), false, layer_n(3), 0);
+                ph_w ^= 1u;
+                LDBG(6);
+                wait_acc();
+                LDBG(7);
+                if (tid == 0) {
+                    load_w(net, weight_offset(3) + kWsWBuf, kWsWBuf);  // W3, K planes 16..31
+                    issue_mma(16, 8, layer_n(3), true, layer_n(3), 0);
+                }
+                ph_w ^= 1u;
+                wait_acc();
+                LDBG(8);
+                if (tid == 0) load_w(net, weight_offset(4), weight_bytes(4));
+                // ---- layer 3 epilogue -> A4
+                epilogue_to_act(acc + t_lane, layer_n(3), bias + (bias_offset(3) - kBiasOffset) / 4, sm.act, row, nullptr);
+                publish_act();
+                if (tid == 0) issue_mma(0, layer_k(4) / 16, layer_n(4), false, layer_n(4), 0);
+                ph_w ^= 1u;
+                LDBG(9);
+                wait_acc();
+                LDBG(10);
+                if (tid == 0) load_w(net, weight_offset(5), weight_bytes(5));
+                // ---- layer 4 epilogue -> A5
+                epilogue_to_act(acc + t_lane, layer_n(4), bias + (bias_offset(4) - kBiasOffset) / 4, sm.act, row, nullptr);
+                publish_act();
+                if (tid == 0) issue_mma(0, layer_k(5) / 16, layer_n(5), false, layer_n(5), 0);
+                ph_w ^= 1u;
+                LDBG(11);
+                wait_acc();
+                LDBG(12);
+                // the next W1: the other network's for this tile, or the first network's for the next tile
+                if (tid == 0 && (!last_net || tile + (int)gridDim.x < n_tiles)) load_w(last_net ? 0 : net + 1, weight_offset(1), weight_bytes(1));
+                // ---- last layer: mean = tanh(D5 + b5), two real columns; value = D5 + b5, one real column
+                {
+                    float v[8];
+                    tmem_ld8(acc + t_lane, v);
+                    const float* b5 = bias + (bias_offset(5) - kBiasOffset) / 4;
+                    const bool linear = kDual ? net == 1 : value_head != 0;
+                    float* dst = kDual && net == 1 ? value2 : mean;
+                    if (live && linear) {
+                        dst[grow] = v[0] + b5[0];  // DeterministicNeuralNetwork (models.py:151-162): linear output, no tanh
+                    } else if (live) {
+                        float2 m;
+                        m.x = tanhf(v[0] + b5[0]);
+                        m.y = tanhf(v[1] + b5[1]);
+                        *reinterpret_cast<float2*>(dst + 2 * (size_t)grow) = m;
+                    }
+                }
+                LDBG(13);
+                tc_fence_before();
+                layer_group_sync();  // every TMEM read of this pass is done before the next layer-1 MMA overwrites acc
             }
-            LDBG(13);
-            tc_fence_before();
-            layer_group_sync();  // every TMEM read of this tile is done before the next tile's layer-1 MMA overwrites acc
         }
     }
 
@@ -445,18 +518,24 @@ typedef CUresult (*WsEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// obs: fp32 [N, obs_stride] (bf16_in == false) or bf16 [N, obs_stride] (bf16_in == true; strides in elements)
+// obs: fp32 [N, obs_stride] (bf16_in == false) or bf16 [N, obs_stride] (bf16_in == true; strides in elements).
+// packed2 != nullptr (fp32 observations only): policy (`packed` -> mean [N, 2]) and value network (`packed2` -> value2 [N])
+// in one pass over the observation.
 int launch_policy_forward_ws(const void* obs, int obs_stride, int n_envs, const void* packed, float* mean,
-                             bool value_head, bool bf16_in, cudaStream_t stream) {
+                             bool value_head, bool bf16_in, cudaStream_t stream, const void* packed2, float* value2) {
     static WsEncodeTiledFn encode = nullptr;
     static int n_sms = 0;
-    constexpr int kSmemBytes = (int)sizeof(WsSmem) + 1024;
+    constexpr int kSmemBytes = (int)sizeof(WsSmem) + 1024, kSmemBytesDual = (int)sizeof(WsSmemT<true>) + 1024;
+    const bool dual = packed2 != nullptr;
+    ROVER_CHECK(!(dual && (bf16_in || value2 == nullptr || value_head)), "policy + value pass: fp32 observations, two outputs");
     if (!encode) {
         int dev = 0;
         ROVER_CUDA(cudaGetDevice(&dev));
         ROVER_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
         ROVER_CUDA(cudaFuncSetAttribute(policy_forward_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         ROVER_CUDA(cudaFuncSetAttribute(policy_forward_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        ROVER_CUDA(cudaFuncSetAttribute(policy_forward_ws_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kSmemBytesDual));
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
         ROVER_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
@@ -483,14 +562,21 @@ int launch_policy_forward_ws(const void* obs, int obs_stride, int n_envs, const 
     ROVER_CHECK(rc == CUDA_SUCCESS, "rover_policy_forward: cuTensorMapEncodeTiled failed (%d)", (int)rc);
     const int n_tiles = (n_envs + tile_rows - 1) / tile_rows;
     const int grid = n_tiles < n_sms ? n_tiles : n_sms;
-    if (bf16_in)
+    const unsigned char* no_net = nullptr;
+    float* no_out = nullptr;
+    if (dual)
+        ROVER_CUDA(launch_overlapped(policy_forward_ws_kernel<false, true>, dim3(grid), dim3(kWsThreads), (size_t)kSmemBytesDual,
+                                     stream, map, static_cast<const float*>(obs), obs_stride, n_envs, tile_rows,
+                                     static_cast<const unsigned char*>(packed), mean, 0,
+                                     static_cast<const unsigned char*>(packed2), value2));
+    else if (bf16_in)
         ROVER_CUDA(launch_overlapped(policy_forward_ws_kernel<true>, dim3(grid), dim3(kWsThreads), (size_t)kSmemBytes, stream, map,
                                      static_cast<const float*>(obs), obs_stride, n_envs, tile_rows,
-                                     static_cast<const unsigned char*>(packed), mean, value_head ? 1 : 0));
+                                     static_cast<const unsigned char*>(packed), mean, value_head ? 1 : 0, no_net, no_out));
     else
         ROVER_CUDA(launch_overlapped(policy_forward_ws_kernel<false>, dim3(grid), dim3(kWsThreads), (size_t)kSmemBytes, stream, map,
                                      static_cast<const float*>(obs), obs_stride, n_envs, tile_rows,
-                                     static_cast<const unsigned char*>(packed), mean, value_head ? 1 : 0));
+                                     static_cast<const unsigned char*>(packed), mean, value_head ? 1 : 0, no_net, no_out));
     return check_launch("policy_forward_ws_kernel");
 }
 

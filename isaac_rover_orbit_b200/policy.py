@@ -156,6 +156,23 @@ class GaussianNeuralNetwork(_RoverNetwork):
         return actions, log_prob.unsqueeze(-1), outputs
 
 
+def policy_value_forward(policy: "GaussianNeuralNetwork", value: "DeterministicNeuralNetwork", states: torch.Tensor):
+    """Policy mean ``[N,2]`` and value ``[N,1]`` of ``states [N,965]`` (fp32) in ONE pass over the observation
+    (``rover_policy_value_forward``): what a PPO rollout evaluates every step -- ``policy.act`` in the trainer loop
+    (skrl_utils.py:139-142) and ``value.act`` in ``record_transition`` (models.py:89-102 + :151-162).  Bit-identical to
+    ``policy.compute`` / ``value.compute``."""
+    if not states.is_cuda or states.dtype != torch.float32 or states.dim() != 2 or states.shape[1] != OBS_COLS:
+        raise RuntimeError("policy_value_forward: states must be a CUDA fp32 [N,965] tensor")
+    if states.stride(1) != 1 or states.stride(0) % 4 != 0 or states.data_ptr() % 16 != 0:
+        buf = alloc_obs(states.shape[0], states.device)
+        buf.copy_(states)
+        states = buf
+    for net in (policy, value):
+        if net._dirty:
+            net._pack()
+    return torch.ops.rover_b200.policy_value_forward(states, policy._packed, value._packed)
+
+
 class DeterministicNeuralNetwork(_RoverNetwork):
     """The value network: rover_envs/envs/navigation/learning/skrl/models.py:105-162 (same encoder + MLP with its own
     weights -- the ``value`` entry of ``best_agent.pt`` -- one linear output, no tanh), ``compute -> (value [N,1], {})``

@@ -61,6 +61,7 @@ _SCHEMAS = {
                           "-> Tensor",
     "policy_mlp_forward": "(Tensor enc, Tensor packed, bool value_head) -> Tensor",
     "policy_forward": "(Tensor obs, Tensor packed, bool value_head) -> Tensor",
+    "policy_value_forward": "(Tensor obs, Tensor packed_policy, Tensor packed_value) -> (Tensor, Tensor)",
     "gaussian_act": "(Tensor mean, Tensor log_std, Tensor eps) -> (Tensor, Tensor)",
     # ---- init-time tables (terrain_utils.py:23-57, 265-279)
     "mesh_to_heightmap": "(Tensor vertices, Tensor faces, float min_x, float min_y, float cell_x, float cell_y, "
@@ -358,6 +359,18 @@ def _policy_forward(obs, packed, value_head):
     return out
 
 
+def _policy_value_forward(obs, packed_policy, packed_value):
+    if (obs.dtype != torch.float32 or obs.dim() != 2 or obs.shape[1] != 965 or obs.stride(1) != 1
+            or obs.stride(0) % 4 != 0 or obs.data_ptr() % 16 != 0):
+        raise RuntimeError("rover_b200::policy_value_forward: states must be fp32 [N,965] with 16-byte aligned rows")
+    n = obs.shape[0]
+    mean = torch.empty(n, 2, dtype=torch.float32, device=obs.device)
+    value = torch.empty(n, 1, dtype=torch.float32, device=obs.device)
+    _lib.check(_lib.load().rover_policy_value_forward(_p(obs), int(obs.stride(0)), n, _p(packed_policy), _p(packed_value),
+                                                      _p(mean), _p(value), _stream(obs)))
+    return mean, value
+
+
 def _gaussian_act(mean, log_std, eps):
     _f32("gaussian_act", mean, log_std, eps)
     n = mean.shape[0]
@@ -411,7 +424,7 @@ _IMPLS = {
     "height_scan": _height_scan, "height_scan_out": _height_scan_out, "height_scan_hits": _height_scan_hits,
     "height_scan_obs": _height_scan_obs, "ackermann": _ackermann, "mdp_pre_step": _mdp_pre_step,
     "mdp_post_step": _mdp_post_step, "mdp_step": _mdp_step, "step_fused": _step_fused, "stats_read": _stats_read, "policy_pack": _policy_pack,
-    "policy_forward": _policy_forward, "gaussian_act": _gaussian_act, "policy_pack_fused": _policy_pack_fused,
+    "policy_forward": _policy_forward, "policy_value_forward": _policy_value_forward, "gaussian_act": _gaussian_act, "policy_pack_fused": _policy_pack_fused,
     "scan_encoder_fused": _scan_encoder_fused, "policy_mlp_forward": _policy_mlp_forward, "mesh_to_heightmap": _mesh_to_heightmap,
     "steep_mask": _steep_mask, "morph_box": _morph_box, "fill_holes": _fill_holes,
 }
@@ -444,6 +457,11 @@ def _(actions, params):
 @_fake("policy_forward")
 def _(obs, packed, value_head):
     return obs.new_empty(obs.shape[0], 1 if value_head else 2, dtype=torch.float32)
+
+
+@_fake("policy_value_forward")
+def _(obs, packed_policy, packed_value):
+    return obs.new_empty(obs.shape[0], 2, dtype=torch.float32), obs.new_empty(obs.shape[0], 1, dtype=torch.float32)
 
 
 @_fake("scan_encoder_fused")

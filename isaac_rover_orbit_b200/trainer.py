@@ -134,11 +134,19 @@ class RolloutAgent(BaseAgent):
     (sampling + log-prob) and ``record_transition`` = the ``RandomMemory`` rollout write.  The
     hooks the trainer calls around them exist and do what skrl's base ``Agent`` does (tracking), nothing more."""
 
-    def __init__(self, policy, memory: RolloutMemory | None = None, observation_size: int = 965, action_size: int = 2):
+    def __init__(self, policy, memory: RolloutMemory | None = None, observation_size: int = 965, action_size: int = 2,
+                 value=None):
+        """``value``: the PPO value network (``DeterministicNeuralNetwork``).  skrl's PPO evaluates it in
+        ``record_transition`` on the states ``act`` just saw; here both networks run in ONE pass over the observation
+        (``policy.policy_value_forward``) and the values are written to the memory's ``values`` tensor."""
         super().__init__()
         self.policy = policy
+        self.value = value
         self.memory = memory
         self._log_prob = None
+        self._values = None
+        if memory is not None and value is not None:
+            memory.create_tensor("values", 1)
         if memory is not None:
             memory.create_tensor("states", observation_size)
             memory.create_tensor("actions", action_size)
@@ -147,7 +155,18 @@ class RolloutAgent(BaseAgent):
             memory.create_tensor("log_prob", 1)
 
     def act(self, states: torch.Tensor, timestep: int, timesteps: int):
-        actions, log_prob, outputs = self.policy.act({"states": states}, role="policy")
+        if self.value is None or states.dtype != torch.float32:
+            actions, log_prob, outputs = self.policy.act({"states": states}, role="policy")
+            if self.value is not None:
+                self._values = self.value.act({"states": states}, role="value")[0]
+        else:
+            from .policy import policy_value_forward
+
+            mean, self._values = policy_value_forward(self.policy, self.value, states)
+            eps = torch.randn(mean.shape[0], 2, device=mean.device)  # (the same draw GaussianNeuralNetwork.act makes)
+            actions, log_prob = torch.ops.rover_b200.gaussian_act(mean, self.policy.log_std_parameter, eps)
+            log_prob = log_prob.unsqueeze(-1)
+            outputs = {"mean_actions": mean}
         self._log_prob = log_prob
         return actions, log_prob, outputs
 
@@ -156,7 +175,7 @@ class RolloutAgent(BaseAgent):
         super().record_transition(states, actions, rewards, next_states, terminated, truncated, infos, timestep, timesteps)
         if self.memory is not None:
             self.memory.add_samples(states=states, actions=actions, rewards=rewards, terminated=terminated,
-                                    log_prob=self._log_prob)
+                                    log_prob=self._log_prob, **({"values": self._values} if self.value is not None else {}))
 
 
 class SkrlSequentialLogTrainer:

@@ -193,3 +193,36 @@ def test_bf16_observation_path_is_bit_identical(cuda_device, golden, golden_dir,
         assert torch.equal(a, b) and torch.isfinite(b).all(), type(net).__name__
     with pytest.raises(RuntimeError):
         pol.compute_bf16({"states": obs})  # fp32 tensor on the bf16 entry point
+
+
+@pytest.mark.parametrize("n", [1, 129, 3000, 18944 + 5, 40000])
+def test_policy_and_value_in_one_pass_are_bit_identical(cuda_device, golden, golden_dir, n):
+    """rover_policy_value_forward (one pass for policy + value, models.py:89-102 + :151-162): the
+    observation tile meets both heightmap encoders, the layer group runs once per network (layer 2 as two N halves
+    through a 192-column accumulator).  Same arithmetic per network, so mean and value equal the two single passes bit
+    for bit -- with the weights of best_agent.pt, one tile, ragged tiles, several tiles per SM, a non-aligned tensor."""
+    from oracle import policy as OP
+    from isaac_rover_orbit_b200.policy import policy_value_forward
+
+    _, sd = golden
+    pol = GaussianNeuralNetwork(device=cuda_device)
+    pol.load_state_dict(sd)
+    val = DeterministicNeuralNetwork(device=cuda_device)
+    val.load_state_dict(OP.load_golden_weights(np.load(os.path.join(golden_dir, "value.npz"))))
+    g = torch.Generator().manual_seed(300 + n)
+    obs = alloc_obs(n, cuda_device)
+    obs.copy_((torch.randn(n, 965, generator=g) * 0.4).to(cuda_device))
+    obs[:, 964] = float("-inf")  # the column the reference's slicing drops (a missed ray) must not matter
+    mean, value = policy_value_forward(pol, val, obs)
+    torch.cuda.synchronize()
+    assert mean.shape == (n, 2) and value.shape == (n, 1)
+    assert torch.equal(mean, pol.compute({"states": obs})[0]) and torch.equal(value, val.compute({"states": obs})[0])
+    assert torch.isfinite(mean).all() and torch.isfinite(value).all()
+    if n == 129:
+        packed_dense = obs.contiguous()  # [N, 965] rows are not 16-byte aligned: re-homed once, like compute()
+        m2, v2 = policy_value_forward(pol, val, packed_dense[:, :965].clone())
+        assert torch.equal(m2, mean) and torch.equal(v2, value)
+        with pytest.raises(RuntimeError):
+            policy_value_forward(pol, val, obs.cpu())
+        with pytest.raises(RuntimeError):
+            torch.ops.rover_b200.policy_value_forward(obs.double(), pol._packed, val._packed)

@@ -50,6 +50,7 @@ def test_opcheck_height_scan_and_policy(world):
     obs.copy_(torch.randn(40, 965, device=dev) * 0.1)
     for tests in ("test_schema", "test_faketensor"):
         torch.library.opcheck(torch.ops.rover_b200.policy_forward.default, (obs, net._packed, False), test_utils=tests)
+        torch.library.opcheck(torch.ops.rover_b200.policy_value_forward.default, (obs, net._packed, net._packed), test_utils=tests)
         torch.library.opcheck(torch.ops.rover_b200.gaussian_act.default,
                               (torch.zeros(40, 2, device=dev), torch.zeros(2, device=dev), torch.randn(40, 2, device=dev)),
                               test_utils=tests)

@@ -56,6 +56,33 @@ def test_train_loop_records_the_rollout(cuda_device):
     assert any(k.startswith("EpisodeInfo / ") for k in agent.tracking_data)
 
 
+def test_rollout_agent_with_value_network_records_the_values(cuda_device):
+    """skrl PPO.record_transition evaluates the value network on the states ``act`` saw and stores ``values``; the agent
+    does both networks in one pass over the observation.  The recorded values equal ``value.compute(states)`` bit for
+    bit, and the actions equal those of the policy-only agent under the same torch seed."""
+    from isaac_rover_orbit_b200.policy import DeterministicNeuralNetwork
+
+    n, steps = 200, 4
+    g2 = torch.Generator().manual_seed(4)
+    net, vnet = GaussianNeuralNetwork(device=cuda_device), DeterministicNeuralNetwork(device=cuda_device)
+    for m in (net, vnet):
+        m.load_state_dict({k: torch.randn(t.shape, generator=g2) * (0.05 if t.dim() == 2 else 0.01)
+                           for k, t in m.state_dict().items()})
+    mem = RolloutMemory(memory_size=steps, num_envs=n, device=cuda_device)
+    agent, plain = RolloutAgent(net, mem, value=vnet), RolloutAgent(net)
+    assert "values" in mem.get_tensor_names()
+    for t in range(steps):
+        states = torch.randn(n, 965, generator=g2).to(cuda_device) * 0.3
+        torch.manual_seed(100 + t)
+        a1, lp1, out1 = agent.act(states, t, steps)
+        torch.manual_seed(100 + t)
+        a0, lp0, out0 = plain.act(states, t, steps)
+        assert torch.equal(a1, a0) and torch.equal(lp1, lp0) and torch.equal(out1["mean_actions"], out0["mean_actions"])
+        agent.record_transition(states, a1, torch.zeros(n, device=cuda_device), states, torch.zeros(n, dtype=torch.bool, device=cuda_device),
+                                torch.zeros(n, dtype=torch.bool, device=cuda_device), {}, t, steps)
+        assert torch.equal(mem.get_tensor_by_name("values")[t], vnet.compute({"states": states})[0])
+
+
 def test_eval_loop_runs_on_the_real_env_and_agent(cuda_device):
     """``SkrlSequentialLogTrainer.eval()`` (the reference's eval.py path, skrl_utils.py:150-206) with the
     shipped ``RoverEnv`` + ``RolloutAgent``: records through the base agent (tracking only, no rollout write) and calls
