@@ -303,19 +303,35 @@ def run_ours(args):
         ops.height_scan(p_d, q_d, rays, grid, out=out, variant=args.variant)
         host_out.copy_(out, non_blocking=True)
 
+    host_work = ops.HostScanWork(n_scan, N_RAYS, dev)
+    E2E_SLICES = 1  # (8 slices: 357 us/step against 345: the step is the D2H copy, profiles/time_e2e_slices.py)
+
+    def e2e_step_host(i):  # the C-ABI call with HOST buffers: rover_height_scan_host (copies + sliced scan inside)
+        p, q = pin[i % POSE_SETS]
+        ops.height_scan_host(p, q, rays, grid, host_out, host_work, n_slices=E2E_SLICES, variant=args.variant)
+
+    def time_e2e(step_fn):
+        for i in range(3):
+            step_fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            step_fn(i)
+            torch.cuda.synchronize()  # the caller reads the heights of step i before issuing step i+1
+        return n_scan * N_RAYS * e2e_steps * world / max_over_ranks([time.perf_counter() - t0])[0]
+
     e2e_steps = max(min(args.steps, 200), 3)
-    for i in range(3):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(i)
-        torch.cuda.synchronize()  # the caller reads the heights of step i before issuing step i+1
-    e2e_value = n_scan * N_RAYS * e2e_steps * world / max_over_ranks([time.perf_counter() - t0])[0]
+    e2e_unsliced = time_e2e(e2e_step)
+    e2e_value = time_e2e(e2e_step_host)
+    host_equals_device = bool(torch.equal(host_out, out.cpu()))  # (e2e_step left the same pose set's heights in `out`)
     e2e = {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_scan * 28, "d2h_bytes_per_step": n_scan * N_RAYS * 4,
-           "steps": e2e_steps, "how": "pinned host poses -> H2D -> rover_height_scan -> D2H heights, synchronised per step"}
+           "steps": e2e_steps,
+           "how": "rover_height_scan_host (the C-ABI call with host buffers): pinned host poses -> H2D -> rover_height_scan -> "
+                  "D2H heights, all inside the call; the host synchronises after every step",
+           "torch_copies": {"value": e2e_unsliced, "how": "the same step as torch copies around rover_height_scan (round-1 figure)"},
+           "host_heights_equal_device_heights": host_equals_device}
 
     def pipelined():
         # the same calls double-buffered on two streams: step i+1's H2D and kernel overlap step i's D2H; the host waits

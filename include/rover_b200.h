@@ -87,6 +87,20 @@ int rover_height_scan(const float* pos_w, const float* quat_w, int32_t n_envs, c
                       const RoverPlaneCells* cells /* host */, float max_distance, float base_offset,
                       float* out_heights, int32_t out_stride, float* out_hits_w, int32_t variant, void* stream);
 
+/* The height scan for a caller whose poses and heights live in HOST memory (a CPU-side simulator; bench.py's `e2e`):
+ * pos_host [n_envs,3], quat_host [n_envs,4] and out_host [n_envs,out_stride] are host pointers (page-locked for the
+ * copies to be asynchronous), everything else as in rover_height_scan.  The poses are copied in, the environments are
+ * scanned in `n_slices` slices on `stream`, and slice k's heights travel to the host on an internal copy stream while
+ * slice k + 1 is scanned; `stream` is complete when all heights are in out_host.  (On a B200 behind PCIe Gen5 the step is
+ * the 15.7 MB device-to-host copy -- 300 of 340 us at cfg-2 -- and slicing does not pay: 1 slice 344.6 us, 8 slices 357 us,
+ * profiles/time_e2e_slices.py; n_slices = 1 runs everything on `stream`.)  `work`: device scratch of
+ * rover_height_scan_host_work_bytes(n_envs, out_stride) bytes, 256-byte aligned.  Replaces the same reference lines as
+ * rover_height_scan (rover_env_cfg.py:78-86 + observations.py:35-45) plus the .cpu() / .to(device) round trip around them. */
+int64_t rover_height_scan_host_work_bytes(int32_t n_envs, int32_t out_stride);
+int rover_height_scan_host(const float* pos_host, const float* quat_host, int32_t n_envs, const float* ray_starts_local,
+                           int32_t n_rays, const float* pattern_box, const RoverScanGrid* grid, const RoverPlaneCells* cells,
+                           float max_distance, float base_offset, float* out_host, int32_t out_stride, void* work,
+                           int64_t work_bytes, int32_t n_slices, int32_t variant, void* stream);
 /* The observation variant of the height scan (B200-native addition, no counterpart in the reference): obs is the fp32
  * observation buffer [n_envs, obs_stride] whose columns [0, head_cols) were written by rover_mdp_post_step; the heights
  * go to columns [head_cols, head_cols + n_rays), and obs_bf16 [n_envs, bf16_stride] receives the bf16 (round to nearest

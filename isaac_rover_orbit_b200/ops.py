@@ -177,6 +177,42 @@ def height_scan(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridH
     return out
 
 
+class HostScanWork:
+    """Device work area of ``height_scan_host`` for up to ``n_envs`` environments (poses in, heights out)."""
+
+    def __init__(self, n_envs: int, n_rays: int, device):
+        self.device = torch.device(device)
+        self.n_envs, self.n_rays = int(n_envs), int(n_rays)
+        n_bytes = int(_lib.load().rover_height_scan_host_work_bytes(self.n_envs, self.n_rays))
+        raw = torch.empty(n_bytes + 256, dtype=torch.uint8, device=self.device)
+        off = (-raw.data_ptr()) % 256
+        self.buffer = raw[off: off + n_bytes]
+
+
+def height_scan_host(pos_host: torch.Tensor, quat_host: torch.Tensor, rays: "RayPattern", grid: ScanGridHandle,
+                     out_host: torch.Tensor, work: HostScanWork, n_slices: int = 1, max_distance: float = 100.0,
+                     base_offset: float = 0.26878, variant: int | None = None) -> torch.Tensor:
+    """``height_scan`` for a caller whose poses and heights live in HOST memory (page-locked tensors): copies the poses
+    in, scans the environments in ``n_slices`` slices and sends slice k's heights to the host while slice k+1 is scanned
+    (``rover_height_scan_host``; on a PCIe-attached B200 the device-to-host copy is 90 % of the step and slicing does not
+    pay, hence the default of one slice).  Asynchronous: ``out_host`` is valid once the current stream of ``work.device`` is
+    synchronised."""
+    variant = DEFAULT_SCAN_VARIANT if variant is None else variant
+    if variant == 0:
+        grid.ensure_home_grid()
+    n = pos_host.shape[0]
+    if n > work.n_envs or rays.starts.shape[0] != work.n_rays:
+        raise RuntimeError("height_scan_host: work area was sized for fewer environments / another ray pattern")
+    if grid.device != work.device or rays.starts.device != work.device:
+        raise RuntimeError("height_scan_host: grid / rays / work area live on different devices")
+    if variant in (2, 4, 5) and grid.cells_struct is None:
+        raise RuntimeError("height_scan_host: variants 2, 4, 5 need a ScanGridHandle built with plane_cells=True")
+    torch.ops.rover_b200.height_scan_host(pos_host, quat_host, rays.starts, rays.box_t, grid.desc, grid.cells_desc,
+                                          float(max_distance), float(base_offset), int(variant), int(n_slices), work.buffer,
+                                          out_host)
+    return out_host
+
+
 def height_scan_obs(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle, obs: torch.Tensor,
                     obs_bf16: torch.Tensor, head_cols: int = 4, max_distance: float = 100.0,
                     base_offset: float = 0.26878) -> None:

@@ -34,6 +34,9 @@ _SCHEMAS = {
                         "float max_distance, float base_offset, int variant) -> (Tensor, Tensor)",
     "height_scan_obs": "(Tensor pos_w, Tensor quat_w, Tensor ray_starts, Tensor pattern_box, Tensor grid, Tensor? cells, "
                        "float max_distance, float base_offset, Tensor(a!) obs, int head_cols, Tensor(b!) obs_bf16) -> ()",
+    "height_scan_host": "(Tensor pos_host, Tensor quat_host, Tensor ray_starts, Tensor pattern_box, Tensor grid, "
+                        "Tensor? cells, float max_distance, float base_offset, int variant, int n_slices, Tensor(a!) work, "
+                        "Tensor(b!) out_host) -> ()",
     # ---- fused MDP step (ackermann_actions.py:226-322, rewards.py:14-137, terminations.py:14-64, ...)
     "ackermann": "(Tensor actions, Tensor params) -> (Tensor, Tensor, Tensor)",
     "mdp_pre_step": "(Tensor? new_actions, Tensor? force_matrix_w, Tensor params, Tensor(a!)[] state, Tensor(b!)[] out, "
@@ -141,6 +144,30 @@ def _height_scan_hits(pos_w, quat_w, ray_starts, pattern_box, grid, cells, max_d
     hits = torch.empty(n, r, 3, dtype=torch.float32, device=pos_w.device)
     _scan_call(pos_w, quat_w, ray_starts, pattern_box, grid, cells, max_distance, base_offset, variant, out, hits)
     return out, hits
+
+
+def _height_scan_host(pos_host, quat_host, ray_starts, pattern_box, grid, cells, max_distance, base_offset, variant, n_slices,
+                      work, out_host):
+    """Poses and heights in HOST memory (page-locked tensors), ray pattern / tables / work area on the device."""
+    n, r = pos_host.shape[0], ray_starts.shape[0]
+    for t, shape, what in ((pos_host, (n, 3), "pos_host"), (quat_host, (n, 4), "quat_host")):
+        if t.device.type != "cpu" or t.dtype != torch.float32 or t.shape != shape or not t.is_contiguous():
+            raise RuntimeError(f"rover_b200::height_scan_host: {what} must be a contiguous CPU fp32 {list(shape)} tensor")
+    if (out_host.device.type != "cpu" or out_host.dtype != torch.float32 or out_host.dim() != 2 or out_host.shape[0] != n
+            or out_host.shape[1] != r or out_host.stride(1) != 1):
+        raise RuntimeError("rover_b200::height_scan_host: out_host must be a CPU fp32 [N,R] tensor with unit inner stride")
+    if not (pos_host.is_pinned() and quat_host.is_pinned() and out_host.is_pinned()):
+        raise RuntimeError("rover_b200::height_scan_host: host tensors must be page-locked (tensor.pin_memory())")
+    _f32("height_scan_host", ray_starts)
+    if not work.is_cuda or work.dtype != torch.uint8 or not work.is_contiguous() or ray_starts.device != work.device:
+        raise RuntimeError("rover_b200::height_scan_host: work must be a contiguous CUDA uint8 tensor on the rays' device")
+    if pattern_box.device.type != "cpu" or pattern_box.dtype != torch.float32 or pattern_box.numel() != 4:
+        raise RuntimeError("rover_b200::height_scan_host: pattern_box must be a CPU fp32 tensor of 4 values")
+    _lib.check(_lib.load().rover_height_scan_host(
+        _p(pos_host), _p(quat_host), n, _p(ray_starts), r, C.cast(C.c_void_p(pattern_box.data_ptr()), C.POINTER(C.c_float * 4)),
+        _desc(grid, _lib.ScanGrid, "grid"), _desc(cells, _lib.PlaneCells, "cells") if cells is not None else None,
+        float(max_distance), float(base_offset), _p(out_host), int(out_host.stride(0)) if n > 0 else r, _p(work),
+        int(work.numel()), int(n_slices), int(variant), _stream(work)))
 
 
 def _height_scan_obs(pos_w, quat_w, ray_starts, pattern_box, grid, cells, max_distance, base_offset, obs, head_cols,
@@ -422,7 +449,7 @@ def _fill_holes(mask):
 
 _IMPLS = {
     "height_scan": _height_scan, "height_scan_out": _height_scan_out, "height_scan_hits": _height_scan_hits,
-    "height_scan_obs": _height_scan_obs, "ackermann": _ackermann, "mdp_pre_step": _mdp_pre_step,
+    "height_scan_obs": _height_scan_obs, "height_scan_host": _height_scan_host, "ackermann": _ackermann, "mdp_pre_step": _mdp_pre_step,
     "mdp_post_step": _mdp_post_step, "mdp_step": _mdp_step, "step_fused": _step_fused, "stats_read": _stats_read, "policy_pack": _policy_pack,
     "policy_forward": _policy_forward, "policy_value_forward": _policy_value_forward, "gaussian_act": _gaussian_act, "policy_pack_fused": _policy_pack_fused,
     "scan_encoder_fused": _scan_encoder_fused, "policy_mlp_forward": _policy_mlp_forward, "mesh_to_heightmap": _mesh_to_heightmap,
@@ -498,7 +525,7 @@ def _fake_none(*args, **kwargs):
     return None
 
 
-for _name in ("height_scan_out", "height_scan_obs", "mdp_pre_step", "mdp_post_step", "mdp_step", "step_fused", "stats_read", "policy_pack",
+for _name in ("height_scan_out", "height_scan_obs", "height_scan_host", "mdp_pre_step", "mdp_post_step", "mdp_step", "step_fused", "stats_read", "policy_pack",
               "policy_pack_fused", "mesh_to_heightmap"):
     torch.library.register_fake(f"{NS}::{_name}", _fake_none, lib=_DEF)
 

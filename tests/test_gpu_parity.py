@@ -407,3 +407,32 @@ def test_ackermann_variants_against_reference_golden(cuda_device, golden_dir):
     ctl.apply_actions()
     torch.testing.assert_close(robot.joint_pos_target.cpu(), torch.from_numpy(z["ref_v3_joint_pos"]), rtol=1e-5, atol=2e-6)
     assert ctl.action_dim == 2 and torch.equal(ctl.processed_actions.cpu(), torch.from_numpy(z["ref_processed"]))
+
+
+@pytest.mark.parametrize("n,slices", [(1, 8), (7, 3), (257, 1), (1000, 8), (1000, 64)])
+def test_height_scan_host_buffers_equal_the_device_call(world, n, slices):
+    """rover_height_scan_host (poses and heights in page-locked HOST memory, the scan in slices whose heights travel back
+    while the next slice runs) returns exactly what rover_height_scan returns for the same poses, whatever the slicing;
+    a work area that is too small, unpinned host tensors and CUDA tensors in the host slots are refused."""
+    dev = world["dev"]
+    rays = ops.RayPattern.grid(dev)
+    grid = world["grid"]
+    gen = torch.Generator().manual_seed(900 + n)
+    p, q = synthetic.make_poses(n, gen, torch.from_numpy(world["v"]), SIZE, RES, margin=4.0)
+    ref = ops.height_scan(p.to(dev), q.to(dev), rays, grid)
+    work = ops.HostScanWork(n, rays.starts.shape[0], dev)
+    out = torch.full((n, rays.starts.shape[0]), float("nan")).pin_memory()
+    for rep in range(2):  # the second call reuses the work area and the internal stream / events
+        ops.height_scan_host(p.pin_memory(), q.pin_memory(), rays, grid, out, work, n_slices=slices)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref.cpu())
+        out.fill_(float("nan"))
+    if n == 7:
+        with pytest.raises(RuntimeError, match="page-locked"):
+            ops.height_scan_host(p, q, rays, grid, out, work)
+        with pytest.raises(RuntimeError):
+            ops.height_scan_host(p.to(dev), q.to(dev), rays, grid, out, work)
+        with pytest.raises(RuntimeError, match="work area"):
+            ops.height_scan_host(p.pin_memory(), q.pin_memory(), rays, grid, out, ops.HostScanWork(3, rays.starts.shape[0], dev))
+        with pytest.raises(RuntimeError, match="n_slices"):
+            ops.height_scan_host(p.pin_memory(), q.pin_memory(), rays, grid, out, work, n_slices=0)
