@@ -149,57 +149,76 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
         : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+// 16 accumulator columns nq .. nq + 15 of one tile row: +bias -> LeakyReLU -> bf16 -> two A planes of the next layer
+__device__ __forceinline__ void epilogue_16(const uint32_t* raw, int nq, const float* __restrict__ bias,
+                                            unsigned char* __restrict__ act, int row, const float* inject) {
+    float v[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + nq + 4 * j4);  // broadcast LDS.128
+        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+            // two columns per FADD2 / FMUL2 (per-lane IEEE fp32: same values as the scalar ops, half the issue slots)
+            unsigned long long acc2, b2, x2, t2;
+            const unsigned long long slope2 = 0x3c23d70a3c23d70aull;  // (0.01f, 0.01f)
+            asm("mov.b64 %0, {%1, %2};" : "=l"(acc2) : "r"(raw[4 * j4 + j]), "r"(raw[4 * j4 + j + 1]));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(b2) : "f"(bb[j]), "f"(bb[j + 1]));
+            asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x2) : "l"(acc2), "l"(b2));
+            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t2) : "l"(x2), "l"(slope2));
+            const float x0 = __uint_as_float((unsigned)(x2 & 0xffffffffull)), x1 = __uint_as_float((unsigned)(x2 >> 32));
+            const float t0 = __uint_as_float((unsigned)(t2 & 0xffffffffull)), t1 = __uint_as_float((unsigned)(t2 >> 32));
+            v[4 * j4 + j] = fmaxf(x0, t0);  // == x > 0 ? x : 0.01 x (LeakyReLU, slope 0.01)
+            v[4 * j4 + j + 1] = fmaxf(x1, t1);
+        }
+    }
+    if (inject != nullptr && nq == 48) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[12 + j] = inject[j];
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint4 o;
+        o.x = pack_bf16(v[8 * h + 0], v[8 * h + 1]);
+        o.y = pack_bf16(v[8 * h + 2], v[8 * h + 3]);
+        o.z = pack_bf16(v[8 * h + 4], v[8 * h + 5]);
+        o.w = pack_bf16(v[8 * h + 6], v[8 * h + 7]);
+        *reinterpret_cast<uint4*>(act + ((nq >> 3) + h) * kWsPlane + row * 16) = o;
+    }
+}
+
 // Epilogue of one layer for one tile row: D[row, 0:n_cols] -> +bias -> LeakyReLU -> bf16 -> A planes of the next layer.
 // inject != nullptr: columns 60..63 are replaced by inject[0..3] (layer 2 consumes [e(60), obs[:, 0:4]]).
+// Batches of 32 columns per tcgen05.ld (then a 16-column tail): the load's latency (~50 cycles before the first value can
+// be used; ptxas schedules every load directly in front of its first use, so a source-level double buffer does not overlap
+// it with the previous batch's arithmetic) is paid once per 32 columns.  profiles/microbench/tmem_read.cu: TMEM delivers
+// 160-250 B/cycle/SM, the conversion arithmetic is what an epilogue costs.
 __device__ __forceinline__ void epilogue_to_act(uint32_t taddr, int n_cols, const float* __restrict__ bias,
                                                 unsigned char* __restrict__ act, int row, const float* inject) {
-    // Software pipeline over batches of 16 columns: the tcgen05.ld of batch k+1 is in flight while batch k is converted.
-    // (Measured on the 256-column epilogue, ~3200 cycles: a build without the TMEM loads is only 14 % faster, one with
-    // the loads alone 2x faster, and a second group of four warps on the upper half of the columns changes nothing --
-    // the bound is the SM-wide rate of the conversion arithmetic (bias add, LeakyReLU, F2FP bf16 pack, STS), not TMEM.)
-    uint32_t raw[2][16];
-    tmem_ld16_nowait(taddr, raw[0]);
-    tmem_wait_ld();
-    const int n_batches = n_cols >> 4;
-#pragma unroll 2
-    for (int k = 0; k < n_batches; ++k) {
-        const int cur = k & 1;  // compile-time after the unroll by 2: raw[][] stays in registers
-        const int nq = 16 * k;
-        if (k + 1 < n_batches) tmem_ld16_nowait(taddr + nq + 16, raw[cur ^ 1]);
-        float v[16];
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + nq + 4 * j4);  // broadcast LDS.128
-            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int j = 0; j < 4; j += 2) {
-                // two columns per FADD2 / FMUL2 (per-lane IEEE fp32: same values as the scalar ops, half the issue slots)
-                unsigned long long acc2, b2, x2, t2;
-                const unsigned long long slope2 = 0x3c23d70a3c23d70aull;  // (0.01f, 0.01f)
-                asm("mov.b64 %0, {%1, %2};" : "=l"(acc2) : "r"(raw[cur][4 * j4 + j]), "r"(raw[cur][4 * j4 + j + 1]));
-                asm("mov.b64 %0, {%1, %2};" : "=l"(b2) : "f"(bb[j]), "f"(bb[j + 1]));
-                asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x2) : "l"(acc2), "l"(b2));
-                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t2) : "l"(x2), "l"(slope2));
-                const float x0 = __uint_as_float((unsigned)(x2 & 0xffffffffull)), x1 = __uint_as_float((unsigned)(x2 >> 32));
-                const float t0 = __uint_as_float((unsigned)(t2 & 0xffffffffull)), t1 = __uint_as_float((unsigned)(t2 >> 32));
-                v[4 * j4 + j] = fmaxf(x0, t0);  // == x > 0 ? x : 0.01 x (LeakyReLU, slope 0.01)
-                v[4 * j4 + j + 1] = fmaxf(x1, t1);
-            }
-        }
-        if (inject != nullptr && nq == 48) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[12 + j] = inject[j];
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint4 o;
-            o.x = pack_bf16(v[8 * h + 0], v[8 * h + 1]);
-            o.y = pack_bf16(v[8 * h + 2], v[8 * h + 3]);
-            o.z = pack_bf16(v[8 * h + 4], v[8 * h + 5]);
-            o.w = pack_bf16(v[8 * h + 6], v[8 * h + 7]);
-            *reinterpret_cast<uint4*>(act + ((nq >> 3) + h) * kWsPlane + row * 16) = o;
-        }
-        tmem_wait_ld();  // batch k+1 has landed
+    int nq = 0;
+    for (; nq + 32 <= n_cols; nq += 32) {
+        uint32_t raw[32];
+        tmem_ld32_nowait(taddr + nq, raw);
+        tmem_wait_ld();
+        epilogue_16(raw, nq, bias, act, row, inject);
+        epilogue_16(raw + 16, nq + 16, bias, act, row, inject);
+    }
+    if (nq < n_cols) {
+        uint32_t raw[16];
+        tmem_ld16_nowait(taddr + nq, raw);
+        tmem_wait_ld();
+        epilogue_16(raw, nq, bias, act, row, inject);
     }
 }
 
