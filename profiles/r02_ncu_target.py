@@ -1,11 +1,11 @@
 """Round-2 ncu target: one warm-up launch and one profiled launch (L2 flushed before it) of every hot kernel.
 
     python profiles/r02_ncu_target.py && ncu --set full --clock-control none --import-source on \
-        -k regex:'height_scan_paired|fused_scan_encoder|policy_mlp|mdp_fused_step|height_scan_step|policy_forward_ws' -s 9 -c 9 \
+        -k regex:'height_scan_paired|fused_scan_encoder|policy_mlp|mdp_fused_step|height_scan_step|policy_forward_ws' -s 10 -c 10 \
         -o gpurun_out/r02_full python profiles/r02_ncu_target.py
 
 Launch order of the matching kernels (the same in both passes): scan @ 4096, 16384, 65536 envs; fused scan + encoder and
-the MLP @ 16384; the single-launch MDP step and the whole-step launch @ 16384; policy forward on fp32 / bf16 observations @ 65536.
+the MLP @ 16384; the single-launch MDP step and the whole-step launch @ 16384; policy forward on fp32 / bf16 observations and the policy + value pass @ 65536.
 """
 import os
 import sys
@@ -16,7 +16,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from isaac_rover_orbit_b200 import ops, synthetic  # noqa: E402
 from isaac_rover_orbit_b200.config import RoverEnvCfg  # noqa: E402
-from isaac_rover_orbit_b200.policy import GaussianNeuralNetwork, alloc_obs, alloc_obs_bf16  # noqa: E402
+from isaac_rover_orbit_b200.policy import (DeterministicNeuralNetwork, GaussianNeuralNetwork, alloc_obs, alloc_obs_bf16,  # noqa: E402
+                                            policy_value_forward)
 
 dev = torch.device("cuda:0")
 v, f, grid, tables = bench.build_world(16384, dev, dev)
@@ -29,6 +30,8 @@ outs = {n: torch.empty(n, 961, device=dev) for n in poses}
 net = GaussianNeuralNetwork(device=dev)
 g = torch.Generator().manual_seed(1)
 net.load_state_dict({k: torch.randn(t.shape, generator=g) * (0.05 if t.dim() == 2 else 0.01) for k, t in net.state_dict().items()})
+vnet = DeterministicNeuralNetwork(device=dev)
+vnet.load_state_dict({k: torch.randn(t.shape, generator=g) * (0.05 if t.dim() == 2 else 0.01) for k, t in vnet.state_dict().items()})
 obs16 = alloc_obs(16384, dev)
 obs16[:, :4] = torch.rand(16384, 4, device=dev)
 pol32 = alloc_obs(65536, dev)
@@ -62,5 +65,7 @@ for rep in range(2):
     net.compute({"states": pol32})
     flush_buf.fill_(1)
     net.compute({"states": pol16})
+    flush_buf.fill_(1)
+    policy_value_forward(net, vnet, pol32)
     torch.cuda.synchronize()
 print("ok")
