@@ -115,3 +115,49 @@ def test_capture_steps_replays_the_enqueued_work(cuda_device):
         replay(i)
     torch.cuda.synchronize()
     assert torch.equal(acc, base + 12.0)
+
+
+def test_recorder_collects_from_the_real_env_on_the_gpu(cuda_device):
+    """f-4: recorder/orbit.py:24-36 over RoverEnv with CUDA tensors -- staging ring on the device, page-locked transfer
+    every `chunk_steps` steps; the rows equal what a per-step `.cpu()` copy (the reference's way) collects."""
+    import types
+
+    import numpy as np
+    from isaac_rover_orbit_b200.recorder import HDF5DataRecorder, SequentialCollector
+    from oracle.recorder import FakeH5, reference_recorder_run
+
+    n, steps = 96, 11
+    v, f = TR.make_synthetic_terrain(48.0, 0.2, seed=5)
+    tables = TR.build_terrain_tables(v, f, n)
+    gen = torch.Generator().manual_seed(8)
+    drift = [(torch.rand(n, 3, generator=gen) * torch.tensor([9.0, 9.0, 0.0])).to(cuda_device) for _ in range(steps)]
+
+    def physics(env):
+        pos = env.scene["robot"].data.root_pos_w
+        pos.copy_(env._buf.env_origins + drift[env.common_step_counter % steps])
+        pos[:, 2] = 0.3
+
+    env = RoverEnv(RoverEnvCfg(num_envs=n), tables, cuda_device, physics=physics, seed=4)
+    net = GaussianNeuralNetwork(device=cuda_device)
+    seen = []
+    step0 = env.step
+
+    def spy_step(action):  # what the reference's recorder would have been handed, copied to the host per step
+        obs_before = env.obs_buf.clone()
+        out = step0(action)
+        seen.append((obs_before.cpu().numpy(), action.cpu().numpy(), out[1].cpu().numpy(), out[2].cpu().numpy(), {}))
+        return out
+
+    env.step = spy_step
+    spaces = types.SimpleNamespace(observation_space=types.SimpleNamespace(shape=(965,), dtype=np.float32),
+                                   action_space=types.SimpleNamespace(shape=(2,), dtype=np.float32))
+    h5, ref = FakeH5(), FakeH5()
+    rec = HDF5DataRecorder("roll", n, spaces, max_rows=400, chunk_steps=4, backend=h5)
+    SequentialCollector(env, net, rec, predict_fn=lambda m, o: m.compute({"states": o})[0], num_episodes=steps).collect()
+    rec.close()
+    reference_recorder_run(ref, "roll", n, 965, 2, np.float32, np.float32, {}, 400, seen)
+    assert list(h5.files) == list(ref.files) and len(h5.files) >= 2
+    for name in ref.files:
+        assert h5.files[name]["__attrs__"] == ref.files[name]["__attrs__"]
+        for k in ("observations", "actions", "rewards", "terminated"):
+            assert np.array_equal(h5.files[name][k].data, ref.files[name][k].data), (name, k)
