@@ -511,11 +511,12 @@ def run_ours(args):
         # outside the timed regions: the mailbox totals equal an NCCL all-reduce of the ranks' running totals
         dist.barrier()
         torch.cuda.synchronize()
-        mine = p2p._cumulative.clone()
+        mine = p2p.local_totals().clone()
         dist.all_reduce(mine, op=dist.ReduceOp.SUM)
-        got = p2p.read().clone()
+        got = p2p.totals().clone()  # flush (the step publishes one launch behind) + barrier + read
         torch.cuda.synchronize()
-        stats_check = {"exchange": "p2p mailbox stores from mdp_post_step (no collective launch on the step path)",
+        stats_check = {"exchange": "p2p mailbox stores from the MDP step's idle kinematics warps at launch start (totals of the "
+                                   "launches before it): no collective launch and no NVLink round trip on the step path",
                        "equals_nccl_all_reduce": bool(torch.equal(got, mine)), "global_resets": float(got[13].item())}
     elif world > 1:
         stats_check = {"exchange": "nccl all_reduce per step"}

@@ -361,6 +361,13 @@ int rover_mdp_post_step_x(float* root_pos_w, float* root_quat_w, int32_t n_envs,
                           const int64_t* spawn_perm, const float* yaw_u, const float* heading_u, const float* theta_u,
                           int32_t n_rounds, int64_t* out_spawn_index, float* stats, float* scratch, float* obs,
                           int32_t obs_stride, int32_t phases, const RoverStatsExchange* xchg /* host */, void* stream);
+/* Publish this rank's running totals to every mailbox now (one small launch).  The single-launch step with in-kernel
+ * variates (rover_mdp_step_v3 / rover_mdp_step with rng_state) publishes at the START of a launch, from warps that would
+ * otherwise idle, the totals as of the PREVIOUS launch -- the two NVLink round trips of a publication then cost the step
+ * nothing (they sat between the launch-wide reduction and the end of the kernel: 5 us per step at 2 GPUs) -- so the
+ * mailboxes run one launch behind.  For exact totals: rover_stats_publish on every rank, synchronise, barrier, then
+ * rover_stats_read.  (The other step entry points publish at the end of each launch, as before.) */
+int rover_stats_publish(const struct RoverStatsExchange* xchg /* host */, void* stream);
 /* out [16] f64 (device): sum over the world's slots of the local mailbox, in rank order; a slot that is being written is
  * re-read (sequence lock), so every addend is one rank's totals after some whole number of its steps */
 int rover_stats_read(const void* mailbox_local, int32_t world, double* out, void* stream);

@@ -92,7 +92,8 @@ __device__ __forceinline__ void sync64() { asm volatile("bar.sync %0, 64;" ::"n"
 // The block's share of the 16 episode statistics -> its row of block_stats, then a ticket: the CTA that takes the last
 // one owns the launch-wide reduction (sh.is_last).  Called by the ROVER_MDP_BLOCK threads that own an env.
 __device__ __forceinline__ void publish_block_stats(float (&st)[kStats], MdpShared& sh, int bid, int n_blocks,
-                                                    float* __restrict__ block_stats, unsigned int* __restrict__ done_counter) {
+                                                    float* __restrict__ block_stats, unsigned int* __restrict__ done_counter,
+                                                    bool after_snapshot = false) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     warp_stats_reduce(st, lane, sh.red[wid]);
     mdp_block_sync();
@@ -104,6 +105,9 @@ __device__ __forceinline__ void publish_block_stats(float (&st)[kStats], MdpShar
     __threadfence();
     mdp_block_sync();
     MDP_STAMP(4);
+    // (split CTA 0 of a multi-GPU run: its kinematics warps have read the totals they publish -- hardware barrier 4 -- before
+    // this CTA's ticket can make the launch-wide reduction, which rewrites those totals, possible)
+    if (after_snapshot) asm volatile("bar.sync 4, 128;" ::: "memory");
     if (threadIdx.x == 0) sh.is_last = (atomicAdd(done_counter, 1u) == (unsigned)n_blocks - 1u) ? 1 : 0;
 }
 
@@ -112,7 +116,32 @@ __device__ __forceinline__ void publish_block_stats(float (&st)[kStats], MdpShar
 // t owns the statistics quad c = t % 4 of the block rows g, g + 16, ... (g = t / 4): float4 loads, kUnroll of them in
 // flight per thread, so the 16 KB of partials (L2) cost one or two round trips instead of a chain of them; the 16 row
 // groups are then combined in order of g.
-template <bool kFused, bool kRng, int kBar>
+// ---- multi-GPU: store this rank's running totals `total` (threads 0..15 of the 64 callers hold one each) into the rank's
+//      slot of every rank's mailbox (peer stores over NVLink).  A slot holds a sequence number and two value buffers; the
+//      writer fills buffer (seq + 1) & 1 in every mailbox, fences once, then stores seq + 1 everywhere -- one system-scope
+//      fence per publication, all peers in flight together.  No collective, no extra launch.
+template <int kBar>
+__device__ __forceinline__ void publish_totals(int tid, double total, MdpShared& sh, const StatsExchangeDev& X) {
+    if (tid < kStats) sh.pub[tid] = total;
+    sync64<kBar>();
+    const unsigned long long seq = *X.sequence + 1ull;
+    for (int e = tid; e < X.world * kStats; e += ROVER_MDP_BLOCK) {
+        const int p = e / kStats, k = e % kStats;
+        unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
+        reinterpret_cast<volatile double*>(slot + 8)[(seq & 1ull) * kStats + k] = sh.pub[k];
+    }
+    __threadfence_system();
+    sync64<kBar>();
+    for (int p = tid; p < X.world; p += ROVER_MDP_BLOCK) {
+        unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
+        *reinterpret_cast<volatile unsigned long long*>(slot) = seq;
+    }
+    if (tid == 0) *X.sequence = seq;
+}
+
+// kPublish = false (the split single-launch step): the totals are only accumulated here; they were / will be published by
+// CTA 0's kinematics warps at the START of a launch (mdp_fused_step_kernel), off the step's critical path.
+template <bool kFused, bool kRng, int kBar, bool kPublish = true>
 __device__ __forceinline__ void final_stats_reduce(int tid, MdpShared& sh, int n_blocks, const RoverMdpParams& P,
                                                    const VariatesDev& V, const float* __restrict__ block_stats,
                                                    unsigned int* __restrict__ done_counter, float* __restrict__ stats,
@@ -165,27 +194,7 @@ __device__ __forceinline__ void final_stats_reduce(int tid, MdpShared& sh, int n
             X.cumulative[tid] = total;
         }
     }
-    // ---- multi-GPU: publish the running totals into this rank's slot of every rank's mailbox (peer stores over
-    //      NVLink).  A slot holds a sequence number and two value buffers; the writer fills buffer (seq + 1) & 1 in
-    //      every mailbox, fences once, then stores seq + 1 everywhere -- one system-scope fence per step, all peers
-    //      in flight together.  No collective, no extra launch.
-    if (X.world > 0) {
-        if (tid < kStats) sh.pub[tid] = total;
-        sync64<kBar>();
-        const unsigned long long seq = *X.sequence + 1ull;
-        for (int e = tid; e < X.world * kStats; e += ROVER_MDP_BLOCK) {
-            const int p = e / kStats, k = e % kStats;
-            unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
-            reinterpret_cast<volatile double*>(slot + 8)[(seq & 1ull) * kStats + k] = sh.pub[k];
-        }
-        __threadfence_system();
-        sync64<kBar>();
-        for (int p = tid; p < X.world; p += ROVER_MDP_BLOCK) {
-            unsigned char* slot = static_cast<unsigned char*>(X.peer_mailbox[p]) + (size_t)X.rank * ROVER_MAILBOX_SLOT_BYTES;
-            *reinterpret_cast<volatile unsigned long long*>(slot) = seq;
-        }
-        if (tid == 0) *X.sequence = seq;
-    }
+    if (kPublish && X.world > 0) publish_totals<kBar>(tid, total, sh, X);
 }
 
 // hardware barrier 2: the env warps of a split CTA announce the ticket (arrive), its kinematics warps wait for it (sync)
@@ -282,7 +291,7 @@ __device__ __forceinline__ void post_step_block(MdpShared& sh, int bid, int n_bl
     if constexpr (kSplit) {
         post_env_work<kRng>(i, valid, reset, rank, er, root_pos_w, root_quat_w, P, S, O, T, V, key, out_spawn_index, obs,
                             obs_stride, phases, st, NoPoseHook(), early, [&](float(&stv)[kStats]) {
-                                publish_block_stats(stv, sh, bid, n_blocks, block_stats, done_counter);
+                                publish_block_stats(stv, sh, bid, n_blocks, block_stats, done_counter, X.world > 0 && bid == 0);
                                 __threadfence_block();
                                 split_ticket_arrive();
                             });
@@ -361,15 +370,26 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
         // dependent chain, a function of the new action only) beside the warps that own the envs, then gone
         static_assert(kRng, "the split CTA is the in-kernel-variates step");
         if (threadIdx.x >= ROVER_MDP_BLOCK) {
+            const int ht = (int)threadIdx.x - ROVER_MDP_BLOCK;
             grid_dependency_wait();
-            pre_step_env<kPreKinematics>(bid * ROVER_MDP_BLOCK + (int)threadIdx.x - ROVER_MDP_BLOCK, new_actions, force, n, P, S,
-                                         O, pre_phases);
+            // multi-GPU: CTA 0's kinematics warps publish the rank's running totals AS OF THE PREVIOUS LAUNCH to the peers'
+            // mailboxes -- two NVLink round trips (values, fence, sequence number) that would otherwise sit between the
+            // launch-wide reduction and the end of the kernel (5 us per step at 2 GPUs), here beside ~10 us of env work.
+            // The mailboxes therefore run one launch behind; rover_stats_publish (P2PStats.flush) brings them up to date.
+            const bool publisher = X.world > 0 && bid == 0;
+            double snapshot = 0.0;
+            if (publisher) {
+                if (ht < kStats) snapshot = X.cumulative[ht];
+                asm volatile("bar.arrive 4, 128;" ::: "memory");  // read before this CTA's ticket (publish_block_stats)
+            }
+            pre_step_env<kPreKinematics>(bid * ROVER_MDP_BLOCK + ht, new_actions, force, n, P, S, O, pre_phases);
+            if (publisher) publish_totals<3>(ht, snapshot, sh, X);
             // ... then they wait for the CTA's ticket: if it was the launch's last one, the launch-wide reduction of the
             // statistics is theirs (the env warps are still busy with metrics / command update / observation head)
             split_ticket_wait();
             if (sh.is_last) {
-                final_stats_reduce<true, kRng, 3>((int)threadIdx.x - ROVER_MDP_BLOCK, sh, n_blocks, P, V, block_stats,
-                                                  done_counter, stats, log_out, phases, X, lookback, 0u);
+                final_stats_reduce<true, kRng, 3, false>(ht, sh, n_blocks, P, V, block_stats, done_counter, stats, log_out, phases,
+                                                         X, lookback, 0u);
 #if ROVER_MDP_DBG
                 if (threadIdx.x == ROVER_MDP_BLOCK) {
                     unsigned long long t__;
@@ -710,6 +730,21 @@ extern "C" int rover_philox4x32_10(const uint32_t counter[4], const uint32_t key
     rover::philox4x32_10(counter[0], counter[1], counter[2], counter[3], key[0], key[1], o);
     for (int k = 0; k < 4; ++k) out[k] = o[k];
     return 0;
+}
+
+__global__ void __launch_bounds__(ROVER_MDP_BLOCK) stats_publish_kernel(const __grid_constant__ rover::StatsExchangeDev X) {
+    __shared__ rover::MdpShared sh;
+    const int tid = (int)threadIdx.x;
+    rover::publish_totals<1>(tid, tid < rover::kStats ? X.cumulative[tid] : 0.0, sh, X);
+}
+
+extern "C" int rover_stats_publish(const RoverStatsExchange* xchg, void* stream) {
+    using namespace rover;
+    StatsExchangeDev X;
+    if (int rc = make_exchange(xchg, X, "rover_stats_publish")) return rc;
+    ROVER_CHECK(X.world > 0, "rover_stats_publish: xchg is NULL");
+    stats_publish_kernel<<<1, ROVER_MDP_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(X);
+    return check_launch("stats_publish_kernel");
 }
 
 extern "C" int rover_stats_read(const void* mailbox_local, int32_t world, double* out, void* stream) {

@@ -144,8 +144,28 @@ class P2PStats:
         if self.world > 1:
             dist.barrier(group=group)  # every mailbox is mapped everywhere before anyone publishes
 
+    def flush(self) -> None:
+        """Publish this rank's running totals now (``rover_stats_publish``).  The single-launch step with in-kernel
+        variates publishes at the START of a launch the totals of the launches before it (off the step's critical path),
+        so the mailboxes run one launch behind; for exact totals every rank calls ``flush()``, synchronises, and the
+        ranks meet at a barrier before ``read()`` (``totals()`` does all of that)."""
+        self._lib.check(self._lib.load().rover_stats_publish(C.byref(self.struct), self._lib.current_stream(self.device)))
+
+    def totals(self, group=None) -> torch.Tensor:
+        """Exact global running totals ``[16]`` f64 as of the last launch of EVERY rank (collective: flush, barrier, read)."""
+        self.flush()
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=group)
+        return self.read()
+
+    def local_totals(self) -> torch.Tensor:
+        """This rank's own running totals ``[16]`` f64."""
+        return self._cumulative
+
     def read(self) -> torch.Tensor:
-        """Global running totals ``[16]`` f64 (device tensor, enqueued on the current stream)."""
+        """Global running totals ``[16]`` f64 (device tensor, enqueued on the current stream) as of each rank's latest
+        PUBLISHED launch (see ``flush``)."""
         self._lib.check(self._lib.load().rover_stats_read(C.c_void_p(self._mailbox), self.world,
                                                           C.c_void_p(self._out.data_ptr()),
                                                           self._lib.current_stream(self.device)))

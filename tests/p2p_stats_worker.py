@@ -56,6 +56,29 @@ def main():
     got = p2p.read().clone()
     torch.cuda.synchronize()
     ok = bool(torch.equal(got.cpu(), want.cpu())) and float(got[13]) > 0
+    # ---- second phase: the single-launch step with in-kernel variates publishes at the START of a launch the totals of
+    #      the launches before it (CTA 0's kinematics warps), so the mailboxes run one launch behind until a flush;
+    #      mixed here with an end-of-launch publisher in between
+    rng = ops.ResetRng(7 + rank, dev)
+    steps2 = 9 + 2 * rank
+    for k in range(steps2):
+        st = synthetic.make_step(n, gen, vt, 48.0, 0.2, margin=4.0).to(dev)
+        buf.stats.zero_()
+        if k == 4:
+            ops.mdp_pre_step(buf, params, st.actions, st.force_matrix_w)
+            ops.mdp_post_step(buf, params, th, st.root_pos_w, st.root_quat_w, rng=rng, xchg=p2p)
+        else:
+            ops.mdp_step(buf, params, th, st.actions, st.force_matrix_w, st.root_pos_w, st.root_quat_w, rng=rng, xchg=p2p)
+        mine += buf.stats.double()
+        p2p.read()
+    torch.cuda.synchronize()
+    assert torch.equal(p2p.local_totals(), mine), "the rank's own running totals"
+    want2 = mine.cpu() if same_device else mine.clone()
+    dist.all_reduce(want2, op=dist.ReduceOp.SUM)
+    got2 = p2p.totals().clone()  # flush + barrier + read
+    torch.cuda.synchronize()
+    ok = ok and bool(torch.equal(got2.cpu(), want2.cpu())) and float(got2[13]) > float(got[13])
+    got, want = got2, want2
     flag = torch.tensor([1.0 if ok else 0.0], device="cpu" if same_device else dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -45,6 +45,18 @@ def test_p2p_stats_world1_equals_accumulator(cuda_device):
     assert torch.equal(p2p.read().cpu(), total) and total[13] > 0
     log = episode_log(p2p.interval())
     assert log["num_resets"] == int(total[13] - first[13])
+    # the single-launch step with in-kernel variates publishes one launch behind (at the START of the next launch)
+    rng = ops.ResetRng(5, cuda_device)
+    for step in range(3):
+        st = synthetic.make_step(n, gen, vt, 48.0, 0.2, margin=4.0).to(cuda_device)
+        buf.stats.zero_()
+        before = total.clone()
+        ops.mdp_step(buf, params, th, st.actions, st.force_matrix_w, st.root_pos_w, st.root_quat_w, rng=rng, xchg=p2p)
+        total += buf.stats.double().cpu()
+        torch.cuda.synchronize()
+        assert torch.equal(p2p.read().cpu(), before), "mailbox = totals of the launches before this one"
+        assert torch.equal(p2p.local_totals().cpu(), total)
+    assert torch.equal(p2p.totals().cpu(), total)  # flush + read
     p2p.close()
 
 
