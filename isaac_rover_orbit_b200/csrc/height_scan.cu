@@ -244,6 +244,10 @@ struct HostScanStreams {
     cudaEvent_t done = nullptr;
     int device = -1;
 };
+// the poses' share of the work area, rounded up so that the heights start on a 64 KB boundary (the device-to-host DMA of
+// 15.7 MB per step is what the end-to-end step costs; keep it on large-page-aligned source addresses)
+static inline int64_t host_scan_pose_bytes(int64_t n_envs) { return ((7 * n_envs * 4 + 65535) / 65536) * 65536; }
+
 static int host_scan_streams(HostScanStreams*& out) {
     static HostScanStreams per_device[64];
     int dev = 0;
@@ -281,7 +285,7 @@ extern "C" int rover_height_scan_host(const float* pos_host, const float* quat_h
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     float* d_pos = static_cast<float*>(work);
     float* d_quat = d_pos + 3 * (size_t)n_envs;
-    float* d_out = reinterpret_cast<float*>(static_cast<unsigned char*>(work) + ((7 * (size_t)n_envs * 4 + 255) / 256) * 256);
+    float* d_out = reinterpret_cast<float*>(static_cast<unsigned char*>(work) + host_scan_pose_bytes(n_envs));
     ROVER_CUDA(cudaMemcpyAsync(d_pos, pos_host, 12 * (size_t)n_envs, cudaMemcpyHostToDevice, s));
     ROVER_CUDA(cudaMemcpyAsync(d_quat, quat_host, 16 * (size_t)n_envs, cudaMemcpyHostToDevice, s));
     const int slices = n_slices < n_envs ? n_slices : n_envs;
@@ -312,7 +316,7 @@ extern "C" int rover_height_scan_host(const float* pos_host, const float* quat_h
 
 extern "C" int64_t rover_height_scan_host_work_bytes(int32_t n_envs, int32_t out_stride) {
     if (n_envs < 0 || out_stride < 0) return -1;
-    return ((7 * (int64_t)n_envs * 4 + 255) / 256) * 256 + (int64_t)n_envs * out_stride * 4;
+    return rover::host_scan_pose_bytes(n_envs) + (int64_t)n_envs * out_stride * 4;
 }
 
 extern "C" int rover_height_scan_obs(const float* pos_w, const float* quat_w, int32_t n_envs,

@@ -184,8 +184,8 @@ class HostScanWork:
         self.device = torch.device(device)
         self.n_envs, self.n_rays = int(n_envs), int(n_rays)
         n_bytes = int(_lib.load().rover_height_scan_host_work_bytes(self.n_envs, self.n_rays))
-        raw = torch.empty(n_bytes + 256, dtype=torch.uint8, device=self.device)
-        off = (-raw.data_ptr()) % 256
+        raw = torch.empty(n_bytes + 65536, dtype=torch.uint8, device=self.device)
+        off = (-raw.data_ptr()) % 65536
         self.buffer = raw[off: off + n_bytes]
 
 
@@ -207,10 +207,32 @@ def height_scan_host(pos_host: torch.Tensor, quat_host: torch.Tensor, rays: "Ray
         raise RuntimeError("height_scan_host: grid / rays / work area live on different devices")
     if variant in (2, 4, 5) and grid.cells_struct is None:
         raise RuntimeError("height_scan_host: variants 2, 4, 5 need a ScanGridHandle built with plane_cells=True")
-    torch.ops.rover_b200.height_scan_host(pos_host, quat_host, rays.starts, rays.box_t, grid.desc, grid.cells_desc,
-                                          float(max_distance), float(base_offset), int(variant), int(n_slices), work.buffer,
-                                          out_host)
+    # A synchronous host loop pays every microsecond in front of the first copy: the validated call (the same one
+    # torch.ops.rover_b200.height_scan_host makes) is prepared once per set of buffers and replayed as one ctypes call.
+    key = (pos_host.data_ptr(), quat_host.data_ptr(), out_host.data_ptr(), n, out_host.stride(0), id(rays), id(grid), id(work),
+           int(n_slices), int(variant), float(max_distance), float(base_offset))
+    call = _HOST_SCAN_CALLS.get(key)
+    if call is None:
+        torch.ops.rover_b200.height_scan_host(pos_host, quat_host, rays.starts, rays.box_t, grid.desc, grid.cells_desc,
+                                              float(max_distance), float(base_offset), int(variant), int(n_slices),
+                                              work.buffer, out_host)  # first use: the operator, with all its checks
+        fn = _lib.load().rover_height_scan_host
+        cargs = (C.c_void_p(pos_host.data_ptr()), C.c_void_p(quat_host.data_ptr()), n, C.c_void_p(rays.starts.data_ptr()),
+                 rays.starts.shape[0], C.cast(C.c_void_p(rays.box_t.data_ptr()), C.POINTER(C.c_float * 4)),
+                 C.byref(grid.struct), C.byref(grid.cells_struct) if grid.cells_struct is not None else None,
+                 float(max_distance), float(base_offset), C.c_void_p(out_host.data_ptr()), int(out_host.stride(0)),
+                 C.c_void_p(work.buffer.data_ptr()), int(work.buffer.numel()), int(n_slices), int(variant))
+        keep = (pos_host, quat_host, out_host, rays, grid, work)  # the pointers above stay valid while the entry lives
+        if len(_HOST_SCAN_CALLS) >= 64:
+            _HOST_SCAN_CALLS.clear()
+        _HOST_SCAN_CALLS[key] = (fn, cargs, keep)
+        return out_host
+    fn, cargs, _ = call
+    _lib.check(fn(*cargs, C.c_void_p(torch.cuda.current_stream(work.device).cuda_stream)))
     return out_host
+
+
+_HOST_SCAN_CALLS: dict = {}
 
 
 def height_scan_obs(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle, obs: torch.Tensor,

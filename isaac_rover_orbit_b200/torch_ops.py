@@ -146,6 +146,9 @@ def _height_scan_hits(pos_w, quat_w, ray_starts, pattern_box, grid, cells, max_d
     return out, hits
 
 
+_PINNED_SEEN: set = set()
+
+
 def _height_scan_host(pos_host, quat_host, ray_starts, pattern_box, grid, cells, max_distance, base_offset, variant, n_slices,
                       work, out_host):
     """Poses and heights in HOST memory (page-locked tensors), ray pattern / tables / work area on the device."""
@@ -156,8 +159,14 @@ def _height_scan_host(pos_host, quat_host, ray_starts, pattern_box, grid, cells,
     if (out_host.device.type != "cpu" or out_host.dtype != torch.float32 or out_host.dim() != 2 or out_host.shape[0] != n
             or out_host.shape[1] != r or out_host.stride(1) != 1):
         raise RuntimeError("rover_b200::height_scan_host: out_host must be a CPU fp32 [N,R] tensor with unit inner stride")
-    if not (pos_host.is_pinned() and quat_host.is_pinned() and out_host.is_pinned()):
-        raise RuntimeError("rover_b200::height_scan_host: host tensors must be page-locked (tensor.pin_memory())")
+    for t in (pos_host, quat_host, out_host):  # is_pinned() asks the driver (~2 us): once per buffer, not once per step
+        key = (t.data_ptr(), t.numel())
+        if key not in _PINNED_SEEN:
+            if not t.is_pinned():
+                raise RuntimeError("rover_b200::height_scan_host: host tensors must be page-locked (tensor.pin_memory())")
+            if len(_PINNED_SEEN) > 4096:
+                _PINNED_SEEN.clear()
+            _PINNED_SEEN.add(key)
     _f32("height_scan_host", ray_starts)
     if not work.is_cuda or work.dtype != torch.uint8 or not work.is_contiguous() or ray_starts.device != work.device:
         raise RuntimeError("rover_b200::height_scan_host: work must be a contiguous CUDA uint8 tensor on the rays' device")
