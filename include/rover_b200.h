@@ -11,7 +11,12 @@
  *   - tensors are dense row-major fp32 unless stated; quaternions are (w, x, y, z);
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it, nothing synchronises;
  *   - every function returns 0 on success, non-zero on error; rover_last_error() gives the message
- *     (thread-local).  No function falls back to a CPU path.
+ *     (thread-local).  No function falls back to a CPU path;
+ *   - the step kernels (MDP step, height scan, policy forward, Gaussian act) are launched with programmatic stream
+ *     serialisation: one of them may begin while the kernel in front of it on the stream retires, and waits for that
+ *     kernel's completion before it reads the per-step inputs.  Launch-invariant inputs -- ray pattern, scan tables,
+ *     packed network weights -- are read before that wait: do not let the kernel that writes them be the one directly
+ *     in front of a step call on the same stream (synchronise once after building them).  ROVER_PDL=0 disables it.
  */
 #ifndef ROVER_B200_H
 #define ROVER_B200_H

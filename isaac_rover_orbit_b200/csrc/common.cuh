@@ -44,6 +44,10 @@ inline int check_launch(const char* what) {
 // grid_dependency_wait() before it touches anything that kernel writes (the wait returns when the predecessor has
 // completed and its memory is visible; immediately if there is none).  The predecessor may call
 // grid_dependency_trigger() to let the dependents start before it exits (otherwise they start when it does).
+// What a kernel may read BEFORE the wait is launch-invariant data only (ray pattern, lattice lines, tensor maps, packed
+// network weights): data that was complete before the kernel in front of it on the stream was launched.  The Python layer
+// guarantees that by synchronising the stream after it builds such data (ScanGridHandle, policy._pack); a C-ABI caller
+// that rebuilds tables or weights must not let the kernel that writes them be the one directly in front of a step kernel.
 // Works under stream capture (a programmatic edge in the graph).  ROVER_PDL=0 in the environment turns it off.
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dependency_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -56,6 +56,9 @@ class ScanGridHandle:
         # descriptor tensors of the torch custom ops: CPU uint8 views of the host structs (no copy)
         self.desc = torch_ops.descriptor(self.struct)
         self.cells_desc = torch_ops.descriptor(self.cells_struct) if self.cells_struct is not None else None
+        # The scan starts under programmatic dependent launch and reads the lattice lines / ray pattern BEFORE it waits for
+        # the kernel in front of it (csrc/common.cuh): launch-invariant tables must be complete before that kernel starts.
+        torch.cuda.current_stream(self.device).synchronize()
 
     def _upload_home_grid(self, grid: ScanGrid) -> None:
         self.grid = grid

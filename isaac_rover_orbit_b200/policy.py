@@ -83,6 +83,9 @@ class _RoverNetwork:
     def _pack(self):
         torch.ops.rover_b200.policy_pack([self._params[k + ".weight"] for k in WEIGHT_KEYS],
                                          [self._params[k + ".bias"] for k in WEIGHT_KEYS], self._packed)
+        # the forward kernels start under programmatic dependent launch and read the blob BEFORE they wait for the kernel
+        # in front of them (csrc/common.cuh): launch-invariant data must be complete before that kernel is launched
+        torch.cuda.current_stream(self.device).synchronize()
         self._dirty = False
 
     def packed(self) -> torch.Tensor:
@@ -104,6 +107,7 @@ class _RoverNetwork:
                 buf = self._packed_fused = raw[off: off + n_bytes]
             torch.ops.rover_b200.policy_pack_fused([self._params[k + ".weight"] for k in WEIGHT_KEYS],
                                                    [self._params[k + ".bias"] for k in WEIGHT_KEYS], buf)
+            torch.cuda.current_stream(self.device).synchronize()  # (see _pack)
             self._fused_dirty = False
         return self._packed_fused
 
