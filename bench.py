@@ -609,29 +609,27 @@ def run_ours(args):
         act_buf = torch.zeros(n, 2, device=dev)
         eps_sets = [torch.randn(n, 2, generator=gen3).to(dev) for _ in range(4)]
         loop_bf = alloc_obs_bf16(n, dev)
+        lp_buf = torch.zeros(n, device=dev)
 
-        def step_fp32(i):
+        def step_fp32(i):  # (the sampled actions land in the buffer the next step's MDP launch reads: no copy)
             w.physics(i)
             w.mdp(i, act_buf)
             w.scan(i)
-            actions, _, _ = net.act({"states": w.obs}, eps=eps_sets[i % 4])
-            act_buf.copy_(actions)
+            net.act({"states": w.obs}, eps=eps_sets[i % 4], out_actions=act_buf)
 
         def step_bf16(i):  # the scan also writes the bf16 observation; the policy reads only that
             s = w.sets[i % 4]
             w.physics(i)
             w.mdp(i, act_buf)
             ops.height_scan_obs(s.root_pos_w, s.root_quat_w, rays, grid, w.obs, loop_bf)
-            actions, _, _ = net.act({"states": loop_bf}, eps=eps_sets[i % 4])
-            act_buf.copy_(actions)
+            net.act({"states": loop_bf}, eps=eps_sets[i % 4], out_actions=act_buf)
 
         def step_fused(i):  # scan + policy in one launch; the fp32 observation is still written (a rollout records it)
             s = w.sets[i % 4]
             w.physics(i)
             w.mdp(i, act_buf)
             mean = ops.height_scan_policy(s.root_pos_w, s.root_quat_w, rays, grid, w.obs, net, write_obs=True)
-            actions, _ = torch.ops.rover_b200.gaussian_act(mean, net.log_std_parameter, eps_sets[i % 4])
-            act_buf.copy_(actions)
+            torch.ops.rover_b200.gaussian_act_out(mean, net.log_std_parameter, eps_sets[i % 4], act_buf, lp_buf)
 
         # the PPO rollout evaluates the value network on the same observation every step (skrl PPO.record_transition):
         # as two forward passes, and as ONE pass over the observation (rover_policy_value_forward)
@@ -647,17 +645,15 @@ def run_ours(args):
             w.physics(i)
             w.mdp(i, act_buf)
             w.scan(i)
-            actions, _, _ = net.act({"states": w.obs}, eps=eps_sets[i % 4])
+            net.act({"states": w.obs}, eps=eps_sets[i % 4], out_actions=act_buf)
             values[0] = vnet.compute({"states": w.obs})[0]
-            act_buf.copy_(actions)
 
         def step_value_one_pass(i):
             w.physics(i)
             w.mdp(i, act_buf)
             w.scan(i)
             mean, values[0] = policy_value_forward(net, vnet, w.obs)
-            actions, _ = torch.ops.rover_b200.gaussian_act(mean, net.log_std_parameter, eps_sets[i % 4])
-            act_buf.copy_(actions)
+            torch.ops.rover_b200.gaussian_act_out(mean, net.log_std_parameter, eps_sets[i % 4], act_buf, lp_buf)
 
         t32 = max_over_ranks([time_steps(graphed(step_fp32), ksteps, 3, flush, stream).mean()])[0] * 1e-3
         act_buf.zero_()

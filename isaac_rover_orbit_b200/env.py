@@ -374,6 +374,13 @@ class RoverEnv:
         self._graph = g  # (capturing does not execute: the first replay is the next step)
         return self
 
+    @property
+    def action_input(self) -> torch.Tensor:
+        """The buffer the step reads its actions from (the action term's ``raw_actions``, ``[N, 2]`` fp32).  A producer that
+        writes its actions straight into it (``policy.act(..., out_actions=env.action_input)``) and then calls
+        ``env.step(env.action_input)`` saves the copy of the action tensor, also under ``enable_cuda_graph()``."""
+        return self._action_in
+
     def step(self, action: torch.Tensor):
         """rover_env.py:42-102."""
         if self._graph is not None:

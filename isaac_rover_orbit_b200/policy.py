@@ -148,14 +148,21 @@ class GaussianNeuralNetwork(_RoverNetwork):
         """``compute`` on the bf16 observation mirror; identical means (the fp32 path rounds to the same bf16)."""
         return self._forward_bf16(inputs["states"], False), self.log_std_parameter, {}
 
-    def act(self, inputs: dict, role: str = "actor", eps: torch.Tensor | None = None):
+    def act(self, inputs: dict, role: str = "actor", eps: torch.Tensor | None = None,
+            out_actions: torch.Tensor | None = None):
         """skrl 1.1.0 ``GaussianMixin.act``: returns ``(actions [N,2], log_prob [N,1], outputs)``.
-        ``eps`` (standard-normal draws) may be supplied for reproducible parity checks."""
+        ``eps`` (standard-normal draws) may be supplied for reproducible parity checks; ``out_actions`` (fp32 ``[N,2]``,
+        e.g. the env's action input buffer) receives the actions in place of a new tensor (no copy on the way to the env)."""
         mean, log_std, outputs = self.compute(inputs, role)
         n = mean.shape[0]
         if eps is None:
             eps = torch.randn(n, 2, device=mean.device)
-        actions, log_prob = torch.ops.rover_b200.gaussian_act(mean, log_std, eps.contiguous())
+        if out_actions is not None:
+            log_prob = torch.empty(n, dtype=torch.float32, device=mean.device)
+            torch.ops.rover_b200.gaussian_act_out(mean, log_std, eps.contiguous(), out_actions, log_prob)
+            actions = out_actions
+        else:
+            actions, log_prob = torch.ops.rover_b200.gaussian_act(mean, log_std, eps.contiguous())
         outputs["mean_actions"] = mean
         return actions, log_prob.unsqueeze(-1), outputs
 

@@ -66,6 +66,7 @@ _SCHEMAS = {
     "policy_forward": "(Tensor obs, Tensor packed, bool value_head) -> Tensor",
     "policy_value_forward": "(Tensor obs, Tensor packed_policy, Tensor packed_value) -> (Tensor, Tensor)",
     "gaussian_act": "(Tensor mean, Tensor log_std, Tensor eps) -> (Tensor, Tensor)",
+    "gaussian_act_out": "(Tensor mean, Tensor log_std, Tensor eps, Tensor(a!) actions, Tensor(b!) log_prob) -> ()",
     # ---- init-time tables (terrain_utils.py:23-57, 265-279)
     "mesh_to_heightmap": "(Tensor vertices, Tensor faces, float min_x, float min_y, float cell_x, float cell_y, "
                          "Tensor(a!) heightmap, Tensor(b!) out_of_range) -> ()",
@@ -407,6 +408,14 @@ def _policy_value_forward(obs, packed_policy, packed_value):
     return mean, value
 
 
+def _gaussian_act_out(mean, log_std, eps, actions, log_prob):
+    _f32("gaussian_act_out", mean, log_std, eps, actions, log_prob)
+    n = mean.shape[0]
+    if actions.shape != mean.shape or log_prob.numel() != n:
+        raise RuntimeError("rover_b200::gaussian_act_out: actions [N,2] and log_prob [N] expected")
+    _lib.check(_lib.load().rover_gaussian_act(_p(mean), _p(log_std), _p(eps), n, _p(actions), _p(log_prob), _stream(mean)))
+
+
 def _gaussian_act(mean, log_std, eps):
     _f32("gaussian_act", mean, log_std, eps)
     n = mean.shape[0]
@@ -460,7 +469,8 @@ _IMPLS = {
     "height_scan": _height_scan, "height_scan_out": _height_scan_out, "height_scan_hits": _height_scan_hits,
     "height_scan_obs": _height_scan_obs, "height_scan_host": _height_scan_host, "ackermann": _ackermann, "mdp_pre_step": _mdp_pre_step,
     "mdp_post_step": _mdp_post_step, "mdp_step": _mdp_step, "step_fused": _step_fused, "stats_read": _stats_read, "policy_pack": _policy_pack,
-    "policy_forward": _policy_forward, "policy_value_forward": _policy_value_forward, "gaussian_act": _gaussian_act, "policy_pack_fused": _policy_pack_fused,
+    "policy_forward": _policy_forward, "policy_value_forward": _policy_value_forward, "gaussian_act": _gaussian_act,
+    "gaussian_act_out": _gaussian_act_out, "policy_pack_fused": _policy_pack_fused,
     "scan_encoder_fused": _scan_encoder_fused, "policy_mlp_forward": _policy_mlp_forward, "mesh_to_heightmap": _mesh_to_heightmap,
     "steep_mask": _steep_mask, "morph_box": _morph_box, "fill_holes": _fill_holes,
 }
@@ -534,7 +544,7 @@ def _fake_none(*args, **kwargs):
     return None
 
 
-for _name in ("height_scan_out", "height_scan_obs", "height_scan_host", "mdp_pre_step", "mdp_post_step", "mdp_step", "step_fused", "stats_read", "policy_pack",
+for _name in ("height_scan_out", "height_scan_obs", "height_scan_host", "gaussian_act_out", "mdp_pre_step", "mdp_post_step", "mdp_step", "step_fused", "stats_read", "policy_pack",
               "policy_pack_fused", "mesh_to_heightmap"):
     torch.library.register_fake(f"{NS}::{_name}", _fake_none, lib=_DEF)
 

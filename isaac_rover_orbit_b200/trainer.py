@@ -135,13 +135,14 @@ class RolloutAgent(BaseAgent):
     hooks the trainer calls around them exist and do what skrl's base ``Agent`` does (tracking), nothing more."""
 
     def __init__(self, policy, memory: RolloutMemory | None = None, observation_size: int = 965, action_size: int = 2,
-                 value=None):
+                 value=None, action_out: torch.Tensor | None = None):
         """``value``: the PPO value network (``DeterministicNeuralNetwork``).  skrl's PPO evaluates it in
         ``record_transition`` on the states ``act`` just saw; here both networks run in ONE pass over the observation
         (``policy.policy_value_forward``) and the values are written to the memory's ``values`` tensor."""
         super().__init__()
         self.policy = policy
         self.value = value
+        self.action_out = action_out  # e.g. ``env.action_input``: the sampled actions land where the env's step reads them
         self.memory = memory
         self._log_prob = None
         self._values = None
@@ -156,7 +157,8 @@ class RolloutAgent(BaseAgent):
 
     def act(self, states: torch.Tensor, timestep: int, timesteps: int):
         if self.value is None or states.dtype != torch.float32:
-            actions, log_prob, outputs = self.policy.act({"states": states}, role="policy")
+            extra = {"out_actions": self.action_out} if self.action_out is not None else {}  # (any skrl-style policy works)
+            actions, log_prob, outputs = self.policy.act({"states": states}, role="policy", **extra)
             if self.value is not None:
                 self._values = self.value.act({"states": states}, role="value")[0]
         else:
@@ -164,7 +166,11 @@ class RolloutAgent(BaseAgent):
 
             mean, self._values = policy_value_forward(self.policy, self.value, states)
             eps = torch.randn(mean.shape[0], 2, device=mean.device)  # (the same draw GaussianNeuralNetwork.act makes)
-            actions, log_prob = torch.ops.rover_b200.gaussian_act(mean, self.policy.log_std_parameter, eps)
+            if self.action_out is not None:
+                actions, log_prob = self.action_out, torch.empty(mean.shape[0], device=mean.device)
+                torch.ops.rover_b200.gaussian_act_out(mean, self.policy.log_std_parameter, eps, actions, log_prob)
+            else:
+                actions, log_prob = torch.ops.rover_b200.gaussian_act(mean, self.policy.log_std_parameter, eps)
             log_prob = log_prob.unsqueeze(-1)
             outputs = {"mean_actions": mean}
         self._log_prob = log_prob

@@ -115,6 +115,10 @@ def test_gaussian_act(cuda_device, golden):
     torch.testing.assert_close(actions.cpu(), a_ref, rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(log_prob.cpu(), lp_ref, rtol=1e-4, atol=1e-4)
     assert actions.abs().max() <= 1.0 and (actions.abs() == 1.0).any()
+    # the same sample written straight into a caller's buffer (the env's action input): no new tensor, same numbers
+    buf = torch.full_like(actions, 7.0)
+    a2, lp2, _ = net.act({"states": obs}, eps=eps.to(cuda_device), out_actions=buf)
+    assert a2 is buf and torch.equal(buf, actions) and torch.equal(lp2, log_prob)
 
 
 def test_policy_rejects_other_shapes(cuda_device):

@@ -28,7 +28,8 @@ def test_every_abi_entry_point_is_a_registered_operator():
         op = getattr(torch.ops.rover_b200, name)
         assert op.default._schema.name == f"rover_b200::{name}"
     mutated = {n for n in torch_ops.OPS if getattr(torch.ops.rover_b200, n).default._schema.is_mutable}
-    assert {"height_scan_out", "height_scan_obs", "mdp_pre_step", "mdp_post_step", "mdp_step", "policy_pack"} <= mutated
+    assert {"height_scan_out", "height_scan_obs", "height_scan_host", "gaussian_act_out", "mdp_pre_step", "mdp_post_step",
+            "mdp_step", "policy_pack"} <= mutated
 
 
 def test_opcheck_height_scan_and_policy(world):

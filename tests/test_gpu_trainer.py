@@ -69,7 +69,8 @@ def test_rollout_agent_with_value_network_records_the_values(cuda_device):
         m.load_state_dict({k: torch.randn(t.shape, generator=g2) * (0.05 if t.dim() == 2 else 0.01)
                            for k, t in m.state_dict().items()})
     mem = RolloutMemory(memory_size=steps, num_envs=n, device=cuda_device)
-    agent, plain = RolloutAgent(net, mem, value=vnet), RolloutAgent(net)
+    action_in = torch.zeros(n, 2, device=cuda_device)  # stands for env.action_input
+    agent, plain = RolloutAgent(net, mem, value=vnet, action_out=action_in), RolloutAgent(net)
     assert "values" in mem.get_tensor_names()
     for t in range(steps):
         states = torch.randn(n, 965, generator=g2).to(cuda_device) * 0.3
@@ -78,6 +79,7 @@ def test_rollout_agent_with_value_network_records_the_values(cuda_device):
         torch.manual_seed(100 + t)
         a0, lp0, out0 = plain.act(states, t, steps)
         assert torch.equal(a1, a0) and torch.equal(lp1, lp0) and torch.equal(out1["mean_actions"], out0["mean_actions"])
+        assert a1 is action_in  # sampled in place: nothing to copy on the way to the env
         agent.record_transition(states, a1, torch.zeros(n, device=cuda_device), states, torch.zeros(n, dtype=torch.bool, device=cuda_device),
                                 torch.zeros(n, dtype=torch.bool, device=cuda_device), {}, t, steps)
         assert torch.equal(mem.get_tensor_by_name("values")[t], vnet.compute({"states": states})[0])
