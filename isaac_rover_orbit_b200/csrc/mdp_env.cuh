@@ -502,6 +502,8 @@ struct SpawnEarly {
     bool have = false;
     long long idx = -1;
     float x = 0.f, y = 0.f, z = 0.f;
+    bool have_variates = false;  // yaw_u / heading_u of the env's variate stream 0 computed by someone else as well
+    float yaw_u = 0.f, heading_u = 0.f;
 };
 
 struct NoStatsHook {
@@ -544,7 +546,9 @@ __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int
     const bool rs_timer = valid && !rs_reset && (phases & ROVER_PHASE_TIME) && __fsub_rn(time_left, P.step_dt) <= 0.f;
     float org_x = 0.f, org_y = 0.f;  // env origin of a freshly spawned env stays in registers (no store -> load round trip)
     if (valid) {
-        if (kRng && (reset || rs_timer)) {  // the only envs that consume variates this step
+        if (kRng && early.have_variates) {
+            yaw_var = early.yaw_u, heading_var = early.heading_u;
+        } else if (kRng && (reset || rs_timer)) {  // the only envs that consume variates this step
             uint32_t w[4];
             rng_env_stream(key, (uint32_t)i, 0u, w);
             yaw_var = u01(w[0]);

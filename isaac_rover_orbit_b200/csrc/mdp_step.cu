@@ -83,6 +83,10 @@ struct MdpShared {
     float red[ROVER_MDP_BLOCK / 4][kStats];  // 16 row groups of the last-block reduction (>= warps per block)
     double pub[kStats];
     int is_last;
+    // split CTA: what the kinematics warps hand to the env warps (hardware barrier 5) -- the spawn row and the stream-0
+    // variates each env WOULD use if it reset or re-drew its target this step
+    int hand_idx[ROVER_MDP_BLOCK];
+    float hand[5][ROVER_MDP_BLOCK];  // spawn x, y, z, yaw_u, heading_u
 };
 
 // barrier among 64 threads on hardware barrier kId
@@ -382,6 +386,27 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
                 if (ht < kStats) snapshot = X.cumulative[ht];
                 asm volatile("bar.arrive 4, 128;" ::: "memory");  // read before this CTA's ticket (publish_block_stats)
             }
+            {   // the env's variate stream 0 and its would-be spawn row: rng state -> Philox -> keyed permutation -> row, a
+                // chain of two cold misses and ~350 instructions that the env warps no longer carry
+                const int hi = bid * ROVER_MDP_BLOCK + ht;
+                const RngKey hkey = load_rng_key<kRng>(V);
+                int idx = -1;
+                float hx = 0.f, hy = 0.f, hz = 0.f, yaw_u = 0.f, heading_u = 0.f;
+                if (hi < n) {
+                    if (phases & ROVER_PHASE_SPAWN) {
+                        idx = (int)spawn_perm_at(make_spawn_perm_key(hkey, (uint32_t)T.n_spawns), (uint32_t)hi);
+                        const float* sp = T.spawn + 3 * (size_t)idx;
+                        hx = __ldg(sp), hy = __ldg(sp + 1), hz = __ldg(sp + 2);
+                    }
+                    uint32_t w[4];
+                    rng_env_stream(hkey, (uint32_t)hi, 0u, w);
+                    yaw_u = u01(w[0]), heading_u = u01(w[1]);
+                }
+                sh.hand_idx[ht] = idx;
+                sh.hand[0][ht] = hx, sh.hand[1][ht] = hy, sh.hand[2][ht] = hz, sh.hand[3][ht] = yaw_u, sh.hand[4][ht] = heading_u;
+                __threadfence_block();
+                asm volatile("bar.arrive 5, 128;" ::: "memory");
+            }
             pre_step_env<kPreKinematics>(bid * ROVER_MDP_BLOCK + ht, new_actions, force, n, P, S, O, pre_phases);
             if (publisher) publish_totals<3>(ht, snapshot, sh, X);
             // ... then they wait for the CTA's ticket: if it was the launch's last one, the launch-wide reduction of the
@@ -437,7 +462,7 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
     SpawnEarly early;
     MDP_STAMP(1);
     const bool reset = pre_step_env<kSplit ? kPreState : kPreAll>(i, new_actions, force, n, P, S, O, pre_phases, [&]() {
-        if constexpr (kRng) {
+        if constexpr (kRng && !kSplit) {
             if (i < n && (phases & ROVER_PHASE_SPAWN)) {  // (see SpawnEarly) consumed after the rest of the pre-step
                 early.have = true;
                 early.idx = (long long)spawn_perm_at(make_spawn_perm_key(key, (uint32_t)T.n_spawns), (uint32_t)i);
@@ -447,6 +472,15 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
         }
     });
     MDP_STAMP(2);
+    if constexpr (kSplit) {  // the kinematics warps' handoff (long there by now)
+        asm volatile("bar.sync 5, 128;" ::: "memory");
+        const int t = (int)threadIdx.x;
+        early.have = (i < n) && (phases & ROVER_PHASE_SPAWN);
+        early.idx = sh.hand_idx[t];
+        early.x = sh.hand[0][t], early.y = sh.hand[1][t], early.z = sh.hand[2][t];
+        early.have_variates = i < n;
+        early.yaw_u = sh.hand[3][t], early.heading_u = sh.hand[4][t];
+    }
     if ((pre_phases & ROVER_PRE_TERMS) && threadIdx.x == 0) O.block_reset_counts[bid] = 0;  // unused by this path
     post_step_block<true, kRng, kSplit>(sh, bid, n_blocks, reset, root_pos_w, root_quat_w, n, P, S, O, T, V, out_spawn_index, block_stats,
                                 done_counter, stats, log_out, obs, obs_stride, phases, X, lookback, epoch, key, early);
