@@ -370,8 +370,10 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
     grid_dependency_trigger();
     MDP_STAMP(0);
     if constexpr (kSplit) {
-        // warps 2, 3 of the CTA: the action term's kinematics of the CTA's envs (AckermannAction2: ~25 % of the pre-step's
-        // dependent chain, a function of the new action only) beside the warps that own the envs, then gone
+        // warps 2, 3 of the CTA work beside the warps that own the envs, on everything that does not depend on an env's
+        // reset decision: the variate stream / spawn row each env would use (handed over through shared memory), the
+        // action term's kinematics (AckermannAction2: ~25 % of the pre-step's dependent chain, a function of the new action
+        // only), on multi-GPU runs the publication of the rank's totals, and at the end the launch-wide reduction
         static_assert(kRng, "the split CTA is the in-kernel-variates step");
         if (threadIdx.x >= ROVER_MDP_BLOCK) {
             const int ht = (int)threadIdx.x - ROVER_MDP_BLOCK;
