@@ -204,10 +204,16 @@ struct NoMidHook {
 // kParts: kPreState = action-manager shift + terminations + rewards, kPreKinematics = the action term's kinematics (a
 // pure function of the new action: the single-launch step gives it to a second warp, off the env's critical path).
 constexpr int kPreState = 1, kPreKinematics = 2, kPreAll = 3;
-template <int kParts = kPreAll, class Mid = NoMidHook>
+struct NoResetHook {
+    __device__ __forceinline__ void operator()(bool) const {}
+};
+
+// on_reset(reset) is called by every thread (also those without an env) as soon as the env's reset decision exists --
+// after the terminations, before the rewards.
+template <int kParts = kPreAll, class Mid = NoMidHook, class OnReset = NoResetHook>
 __device__ __forceinline__ bool pre_step_env(int i, const float* __restrict__ new_actions, const float* __restrict__ force,
                                              int n, const RoverMdpParams& P, const RoverMdpState& S, const RoverMdpOut& O,
-                                             int phases, Mid mid = Mid()) {
+                                             int phases, Mid mid = Mid(), OnReset on_reset = OnReset()) {
     constexpr int kFixedBodies = 14;  // AAU rover: 6 Drive + 4 Steer + 3 Boogie + Body
     const bool valid = i < n;
     const bool terms = valid && (phases & ROVER_PRE_TERMS) && (kParts & kPreState);
@@ -255,28 +261,32 @@ __device__ __forceinline__ bool pre_step_env(int i, const float* __restrict__ ne
         }
     }
     mid();
+    float d = 0.f, ang = 0.f;
+    bool coll = false, t_succ = false, t_far = false;
+    const float max_len = (float)P.max_episode_length;
     if (terms) {
         // ---- counters (rover_env.py:79)
         S.episode_length_buf[i] = ep;
 
         // ---- shared quantities of the PREVIOUS command (rover_env.py:82-86 run before the command update)
-        const float d = norm2(bx, by);
-        const float ang = atan2f(by, bx);
-        const bool coll = fixed_bodies ? collision_active_regs<kFixedBodies>(fv)
-                                       : collision_active(force + (size_t)i * P.num_bodies * 3, P.num_bodies);
-        const float max_len = (float)P.max_episode_length;
+        d = norm2(bx, by);
+        coll = fixed_bodies ? collision_active_regs<kFixedBodies>(fv)
+                            : collision_active(force + (size_t)i * P.num_bodies * 3, P.num_bodies);
 
         // ---- terminations (terminations.py:14-64, ORBIT mdp.time_out)
         const bool t_out = ep >= (long long)P.max_episode_length;
-        const bool t_succ = d < P.reached_threshold;
-        const bool t_far = d > P.far_threshold;
+        t_succ = d < P.reached_threshold;
+        t_far = d > P.far_threshold;
         const bool terminated = t_succ || t_far || coll;
         reset = t_out || terminated;
         O.terminated[i] = terminated;
         O.truncated[i] = t_out;
         reinterpret_cast<uchar4*>(O.term_flags)[i] = make_uchar4(t_out, t_succ, t_far, coll);
         O.reset_flags[i] = reset;
-
+    }
+    on_reset(reset);
+    if (terms) {
+        ang = atan2f(by, bx);
         // ---- rewards (rewards.py:14-137), RewardManager: value * weight * dt, summed in declaration order
         float val[ROVER_NUM_REWARD_TERMS];
         val[0] = __fdiv_rn(__fdiv_rn(1.f, __fadd_rn(1.f, __fmul_rn(__fmul_rn(0.11f, d), d))), max_len);
@@ -353,23 +363,28 @@ struct VariatesDev {
 
 // Must be called by all 32 lanes of a converged warp.  need: this lane's env resamples around (ox, oy).  Lanes with
 // `need` get the accepted candidate in (cx, cy, cz) and return true if every round was rejected.
+// A pass serves the four lowest pending envs, eight lanes per env, lane k of a group evaluating round r0 + k; an env whose
+// eight candidates were all rejected goes on to rounds r0 + 8 .. in the next batch.  (kPer = 4 -- eight envs per pass, four
+// rounds each -- was measured slower, 71.4 against 70.6 us for the cfg-3 step: an env that needs a fifth round then pays
+// a second cold miss, and on the bench terrain some block of every launch holds one.)
 template <bool kRng>
 __device__ __forceinline__ bool resample_warp(int i, bool need, const RoverMdpParams& P, const Tables& T, float ox, float oy,
                                               const float* __restrict__ theta_u, const RngKey& key, int n_rounds,
                                               float& cx, float& cy, float& cz) {
     constexpr unsigned kFull = 0xffffffffu;
+    constexpr int kPer = 8, kGroups = 32 / kPer;  // rounds (= lanes) per env and envs per pass
     const float pi_f = 3.1415927f;  // torch.pi as fp32; the reference computes rand * 2 * pi left to right
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned grp = lane >> 3, k = lane & 7u;
+    const unsigned grp = lane / kPer, k = lane % kPer;
     bool bad = need;
-    for (int r0 = 0; r0 < n_rounds; r0 += 8) {
+    for (int r0 = 0; r0 < n_rounds; r0 += kPer) {
         unsigned pending = __ballot_sync(kFull, bad);
         while (pending) {
-            // owners of this pass: the four lowest lanes still pending; group g serves the g-th of them
+            // owners of this pass: the lowest lanes still pending; group g serves the g-th of them
             unsigned rest = pending;
             int owner = -1;
 #pragma unroll
-            for (unsigned g = 0; g < 4; ++g) {
+            for (unsigned g = 0; g < (unsigned)kGroups; ++g) {
                 const int b = rest ? __ffs(rest) - 1 : -1;
                 if (g == grp) owner = b;
                 rest &= rest - 1u;
@@ -402,9 +417,9 @@ __device__ __forceinline__ bool resample_warp(int i, bool need, const RoverMdpPa
             const unsigned good_b = __ballot_sync(kFull, good), act_b = __ballot_sync(kFull, active);
             // an owner finds its group: the number of pending lanes below it
             const unsigned my_g = (unsigned)__popc(pending & ((1u << lane) - 1u));
-            const bool served = ((pending >> lane) & 1u) != 0u && my_g < 4u;  // (a lane served earlier may still be `bad`)
-            const unsigned sh = served ? 8u * my_g : 0u;
-            const unsigned g_good = (good_b >> sh) & 0xffu, g_act = (act_b >> sh) & 0xffu;
+            const bool served = ((pending >> lane) & 1u) != 0u && my_g < (unsigned)kGroups;  // (a lane served earlier may still be `bad`)
+            const unsigned sh = served ? (unsigned)kPer * my_g : 0u;
+            const unsigned g_good = (good_b >> sh) & ((1u << kPer) - 1u), g_act = (act_b >> sh) & ((1u << kPer) - 1u);
             const int pick = g_good ? __ffs(g_good) - 1 : 31 - __clz(g_act | 1u);  // first valid round, else the last tried
             const int from = served ? (int)sh + pick : (int)lane;
             const float nx = __shfl_sync(kFull, xk, from), ny = __shfl_sync(kFull, yk, from), nz = __shfl_sync(kFull, zk, from);
@@ -506,6 +521,12 @@ struct SpawnEarly {
     float yaw_u = 0.f, heading_u = 0.f;
 };
 
+// get_target(x, y, z, exhausted) -> true if the env's new target was drawn elsewhere (the split CTA's kinematics warps run
+// the rejection sampling beside the env warps); false: post_env_work draws it itself.  Warp-uniform.
+struct NoTargetHook {
+    __device__ __forceinline__ bool operator()(float&, float&, float&, bool&) const { return false; }
+};
+
 struct NoStatsHook {
     __device__ __forceinline__ void operator()(float (&)[kStats]) const {}
 };
@@ -519,14 +540,15 @@ struct NoPoseHook {
 // the rest of the env's work (target rejection sampling, command update, stores) is still running.
 // on_stats(st) is called by ALL lanes (warp-converged, valid or not) once the env's 16 statistics are final -- after the
 // target draw, before metrics / command update / observation head.
-template <bool kRng, class OnPose = NoPoseHook, class OnStats = NoStatsHook>
+template <bool kRng, class OnPose = NoPoseHook, class OnStats = NoStatsHook, class GetTarget = NoTargetHook>
 __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int rank, EnvRegs& r,
                                               float* __restrict__ root_pos_w, float* __restrict__ root_quat_w,
                                               const RoverMdpParams& P, const RoverMdpState& S, const RoverMdpOut& O,
                                               const Tables& T, const VariatesDev& V, const RngKey& key,
                                               long long* __restrict__ out_spawn_index, float* __restrict__ obs,
                                               int obs_stride, int phases, float (&st)[kStats], OnPose on_pose = OnPose(),
-                                              const SpawnEarly early = SpawnEarly(), OnStats on_stats = OnStats()) {
+                                              const SpawnEarly early = SpawnEarly(), OnStats on_stats = OnStats(),
+                                              GetTarget get_target = GetTarget()) {
     const long long* __restrict__ spawn_perm = V.spawn_perm;
     const float* __restrict__ theta_u = V.theta_u;
     const int n_rounds = V.n_rounds;
@@ -589,7 +611,9 @@ __device__ __forceinline__ void post_env_work(int i, bool valid, bool reset, int
     }
     // -- _resample_command around the (new) env origin, all lanes of the warp together
     float nwx = 0.f, nwy = 0.f, nwz = 0.f;
-    const bool exhausted = resample_warp<kRng>(i, rs_reset || rs_timer, P, T, org_x, org_y, theta_u, key, n_rounds, nwx, nwy, nwz);
+    bool exhausted = false;
+    if (!get_target(nwx, nwy, nwz, exhausted))
+        exhausted = resample_warp<kRng>(i, rs_reset || rs_timer, P, T, org_x, org_y, theta_u, key, n_rounds, nwx, nwy, nwz);
     if (valid) {
         if (reset && (phases & ROVER_PHASE_MANAGERS)) {
             // -- ActionManager.reset

@@ -87,6 +87,11 @@ struct MdpShared {
     // variates each env WOULD use if it reset or re-drew its target this step
     int hand_idx[ROVER_MDP_BLOCK];
     float hand[5][ROVER_MDP_BLOCK];  // spawn x, y, z, yaw_u, heading_u
+    // ... what the env warps tell them (barrier 6: which envs reset) and get back (barrier 7: the new target of every env that
+    // resets or whose command timer ran out -- the rejection sampling, a cold miss and ~400 instructions, runs beside
+    // the env warps' reward / spawn / manager-reset work)
+    unsigned char reset_flag[ROVER_MDP_BLOCK];
+    float target[4][ROVER_MDP_BLOCK];  // x, y, z, exhausted
 };
 
 // barrier among 64 threads on hardware barrier kId
@@ -293,12 +298,20 @@ __device__ __forceinline__ void post_step_block(MdpShared& sh, int bid, int n_bl
 
     float st[kStats];
     if constexpr (kSplit) {
-        post_env_work<kRng>(i, valid, reset, rank, er, root_pos_w, root_quat_w, P, S, O, T, V, key, out_spawn_index, obs,
-                            obs_stride, phases, st, NoPoseHook(), early, [&](float(&stv)[kStats]) {
-                                publish_block_stats(stv, sh, bid, n_blocks, block_stats, done_counter, X.world > 0 && bid == 0);
-                                __threadfence_block();
-                                split_ticket_arrive();
-                            });
+        post_env_work<kRng>(
+            i, valid, reset, rank, er, root_pos_w, root_quat_w, P, S, O, T, V, key, out_spawn_index, obs, obs_stride, phases, st,
+            NoPoseHook(), early,
+            [&](float(&stv)[kStats]) {
+                publish_block_stats(stv, sh, bid, n_blocks, block_stats, done_counter, X.world > 0 && bid == 0);
+                __threadfence_block();
+                split_ticket_arrive();
+            },
+            [&](float& tx, float& ty, float& tz, bool& ex) {  // the targets the kinematics warps drew (barrier 7)
+                asm volatile("bar.sync 7, 128;" ::: "memory");
+                const int t = (int)threadIdx.x;
+                tx = sh.target[0][t], ty = sh.target[1][t], tz = sh.target[2][t], ex = sh.target[3][t] != 0.f;
+                return true;
+            });
         MDP_STAMP(3);
         return;
     } else {
@@ -408,6 +421,23 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
                 sh.hand[0][ht] = hx, sh.hand[1][ht] = hy, sh.hand[2][ht] = hz, sh.hand[3][ht] = yaw_u, sh.hand[4][ht] = heading_u;
                 __threadfence_block();
                 asm volatile("bar.arrive 5, 128;" ::: "memory");
+                // the target draw of the envs that reset (flag from the env warps) or whose timer runs out this step:
+                // the same rs_reset / rs_timer / origin rules as post_env_work, the same resample_warp
+                const float tl = (hi < n && (phases & ROVER_PHASE_TIME)) ? S.time_left[hi] : 0.f;
+                float ox = hx, oy = hy;
+                asm volatile("bar.sync 6, 128;" ::: "memory");
+                const bool h_reset = hi < n && sh.reset_flag[ht] != 0;
+                const bool rs_reset = h_reset && (phases & ROVER_PHASE_RESAMPLE);
+                const bool rs_timer = hi < n && !rs_reset && (phases & ROVER_PHASE_TIME) && __fsub_rn(tl, P.step_dt) <= 0.f;
+                if ((rs_reset || rs_timer) && !(h_reset && (phases & ROVER_PHASE_SPAWN))) {
+                    ox = S.env_origins[3 * (size_t)hi];
+                    oy = S.env_origins[3 * (size_t)hi + 1];
+                }
+                float tx = 0.f, ty = 0.f, tz = 0.f;
+                const bool ex = resample_warp<kRng>(hi, rs_reset || rs_timer, P, T, ox, oy, V.theta_u, hkey, V.n_rounds, tx, ty, tz);
+                sh.target[0][ht] = tx, sh.target[1][ht] = ty, sh.target[2][ht] = tz, sh.target[3][ht] = ex ? 1.f : 0.f;
+                __threadfence_block();
+                asm volatile("bar.arrive 7, 128;" ::: "memory");
             }
             pre_step_env<kPreKinematics>(bid * ROVER_MDP_BLOCK + ht, new_actions, force, n, P, S, O, pre_phases);
             if (publisher) publish_totals<3>(ht, snapshot, sh, X);
@@ -471,6 +501,12 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
                 const float* sp = T.spawn + 3 * (size_t)early.idx;
                 early.x = __ldg(sp), early.y = __ldg(sp + 1), early.z = __ldg(sp + 2);
             }
+        }
+    }, [&](bool reset_now) {
+        if constexpr (kSplit) {  // which envs reset -> the kinematics warps: they draw the new targets during the rewards
+            sh.reset_flag[threadIdx.x] = reset_now ? 1 : 0;
+            __threadfence_block();
+            asm volatile("bar.arrive 6, 128;" ::: "memory");
         }
     });
     MDP_STAMP(2);
