@@ -624,6 +624,13 @@ def run_ours(args):
             ops.height_scan_obs(s.root_pos_w, s.root_quat_w, rays, grid, w.obs, loop_bf)
             net.act({"states": loop_bf}, eps=eps_sets[i % 4], out_actions=act_buf)
 
+        def step_bf16_only(i):  # the policy is the heights' only consumer: the fp32 heights are not even stored
+            s = w.sets[i % 4]
+            w.physics(i)
+            w.mdp(i, act_buf)
+            ops.height_scan_obs(s.root_pos_w, s.root_quat_w, rays, grid, w.obs, loop_bf, bf16_only=True)
+            net.act({"states": loop_bf}, eps=eps_sets[i % 4], out_actions=act_buf)
+
         def step_fused(i):  # scan + policy in one launch; the fp32 observation is still written (a rollout records it)
             s = w.sets[i % 4]
             w.physics(i)
@@ -663,6 +670,8 @@ def run_ours(args):
         act_buf.zero_()
         t16 = max_over_ranks([time_steps(graphed(step_bf16), ksteps, 3, flush, stream).mean()])[0] * 1e-3
         act_buf.zero_()
+        t16o = max_over_ranks([time_steps(graphed(step_bf16_only), ksteps, 3, flush, stream).mean()])[0] * 1e-3
+        act_buf.zero_()
         tfu = max_over_ranks([time_steps(graphed(step_fused), ksteps, 3, flush, stream).mean()])[0] * 1e-3
         return {"workload": f"{n} envs/GPU: pre_step + post_step + height scan + policy forward (tcgen05) + Gaussian act, "
                             "actions fed back to the next step; physics replaced by a synthetic pose update",
@@ -674,6 +683,10 @@ def run_ours(args):
                                               "rover_policy_forward + rover_value_forward vs rover_policy_value_forward"},
                 "bf16_observation": {"env_steps_per_s": n * world / t16, "us_per_step": t16 * 1e6,
                                      "how": "rover_height_scan_obs writes the bf16 mirror, rover_policy_forward_bf16 reads it"},
+                "bf16_observation_only": {"env_steps_per_s": n * world / t16o, "us_per_step": t16o * 1e6,
+                                          "how": "rover_height_scan_obs_bf16: the scan stores only the bf16 observation (the policy "
+                                                 "forward rounds fp32 observations to these very values, so the trajectory is the "
+                                                 "same bit for bit: tests/test_gpu_policy.py); for inference loops that do not record fp32 observations"},
                 "fused_scan_encoder": {"env_steps_per_s": n * world / tfu, "us_per_step": tfu * 1e6,
                                        "how": "mdp step + rover_scan_encoder_fused (scan + heightmap encoder in one launch, "
                                               "fp32 observation still stored) + rover_policy_mlp_forward + Gaussian act"}}

@@ -116,6 +116,16 @@ int rover_height_scan_obs(const float* pos_w, const float* quat_w, int32_t n_env
                           int32_t n_rays, const float* pattern_box /* host */, const RoverScanGrid* grid /* host */,
                           const RoverPlaneCells* cells /* host */, float max_distance, float base_offset, float* obs,
                           int32_t obs_stride, int32_t head_cols, uint16_t* obs_bf16, int32_t bf16_stride, void* stream);
+/* The same with ONLY the bf16 observation written: for a loop in which the policy forward on bf16 observations
+ * (rover_policy_forward_bf16) is the heights' only consumer.  `obs_head` is the fp32 observation buffer, read for its
+ * head columns (written by the MDP step) and otherwise left alone on the variant-5 path -- its height columns keep
+ * whatever they held (a general table falls back to scan + conversion and does write them).  The policy rounds fp32
+ * observations to these very bf16 values, so means, actions and the whole trajectory are bit-identical to the fp32 loop;
+ * what is saved is the 3844 B/env fp32 store and the 3860 B/env fp32 read of the forward pass. */
+int rover_height_scan_obs_bf16(const float* pos_w, const float* quat_w, int32_t n_envs, const float* ray_starts_local,
+                               int32_t n_rays, const float* pattern_box /* host */, const RoverScanGrid* grid,
+                               const RoverPlaneCells* cells, float max_distance, float base_offset, const float* obs_head,
+                               int32_t obs_stride, int32_t head_cols, uint16_t* obs_bf16, int32_t bf16_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Fused MDP step.  Replaces, in one launch:

@@ -26,7 +26,7 @@ SYMBOLS = ("rover_abi_version", "rover_last_error", "rover_height_scan", "rover_
            "rover_rng_variates", "rover_philox4x32_10", "rover_stats_read", "rover_p2p_alloc", "rover_p2p_free",
            "rover_p2p_export", "rover_p2p_open", "rover_p2p_close",
            "rover_ackermann",
-           "rover_height_scan_host", "rover_height_scan_host_work_bytes", "rover_stats_publish", "rover_policy_pack", "rover_policy_forward", "rover_value_forward", "rover_policy_value_forward", "rover_policy_forward_bf16",
+           "rover_height_scan_host", "rover_height_scan_host_work_bytes", "rover_stats_publish", "rover_height_scan_obs_bf16", "rover_policy_pack", "rover_policy_forward", "rover_value_forward", "rover_policy_value_forward", "rover_policy_forward_bf16",
            "rover_value_forward_bf16", "rover_gaussian_act", "rover_mesh_to_heightmap", "rover_steep_mask",
            "rover_policy_pack_fused", "rover_scan_encoder_fused", "rover_policy_mlp_forward", "rover_morph_box",
            "rover_fill_holes", "rover_step_fused")
@@ -189,9 +189,10 @@ def load() -> C.CDLL:
     lib.rover_height_scan_host.restype = C.c_int
     lib.rover_height_scan_host.argtypes = [vp, vp, i32, vp, i32, C.POINTER(C.c_float * 4), C.POINTER(ScanGrid),
                                            C.POINTER(PlaneCells), f32, f32, vp, i32, vp, C.c_int64, i32, i32, vp]
-    lib.rover_height_scan_obs.restype = C.c_int
-    lib.rover_height_scan_obs.argtypes = [vp, vp, i32, vp, i32, C.POINTER(C.c_float * 4), C.POINTER(ScanGrid),
-                                          C.POINTER(PlaneCells), f32, f32, vp, i32, i32, vp, i32, vp]
+    for fn in (lib.rover_height_scan_obs, lib.rover_height_scan_obs_bf16):
+        fn.restype = C.c_int
+        fn.argtypes = [vp, vp, i32, vp, i32, C.POINTER(C.c_float * 4), C.POINTER(ScanGrid), C.POINTER(PlaneCells), f32, f32, vp,
+                       i32, i32, vp, i32, vp]
     lib.rover_policy_forward.restype = C.c_int
     lib.rover_policy_forward.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.rover_value_forward.restype = C.c_int

@@ -170,7 +170,8 @@ int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_
 int launch_height_scan_paired(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local, int n_rays,
                               const ScanGridDev& g, const RoverPlaneCells* cells, float4 pattern_box, float max_d,
                               float base_offset, float* out, int out_stride, float* hits, uint16_t* obs_bf16,
-                              int bf16_stride, int head_cols, cudaStream_t stream);  // height_scan_paired.cu
+                              int bf16_stride, int head_cols, cudaStream_t stream,
+                              bool bf16_only = false);  // height_scan_paired.cu
 
 // fallback of rover_height_scan_obs when variant 5 cannot run: mirror obs[:, 0:cols] into bf16
 __global__ void obs_to_bf16_kernel(const float* __restrict__ obs, int obs_stride, int n_envs, int cols,
@@ -319,11 +320,11 @@ extern "C" int64_t rover_height_scan_host_work_bytes(int32_t n_envs, int32_t out
     return rover::host_scan_pose_bytes(n_envs) + (int64_t)n_envs * out_stride * 4;
 }
 
-extern "C" int rover_height_scan_obs(const float* pos_w, const float* quat_w, int32_t n_envs,
-                                     const float* ray_starts_local, int32_t n_rays, const float* pattern_box,
-                                     const RoverScanGrid* grid, const RoverPlaneCells* cells, float max_distance,
-                                     float base_offset, float* obs, int32_t obs_stride, int32_t head_cols,
-                                     uint16_t* obs_bf16, int32_t bf16_stride, void* stream) {
+static int height_scan_obs_impl(const float* pos_w, const float* quat_w, int32_t n_envs, const float* ray_starts_local,
+                                int32_t n_rays, const float* pattern_box, const RoverScanGrid* grid,
+                                const RoverPlaneCells* cells, float max_distance, float base_offset, float* obs,
+                                int32_t obs_stride, int32_t head_cols, uint16_t* obs_bf16, int32_t bf16_stride, void* stream,
+                                bool bf16_only) {
     using namespace rover;
     ROVER_CHECK(n_envs >= 0 && n_rays >= 0 && head_cols >= 0, "rover_height_scan_obs: negative sizes");
     if (n_envs == 0) return 0;
@@ -343,9 +344,10 @@ extern "C" int rover_height_scan_obs(const float* pos_w, const float* quat_w, in
         const float4 box = make_float4(pattern_box[0], pattern_box[1], pattern_box[2], pattern_box[3]);
         return launch_height_scan_paired(pos_w, quat_w, n_envs, ray_starts_local, n_rays, g, cells, box, max_distance,
                                          base_offset, obs + head_cols, obs_stride, nullptr, obs_bf16, bf16_stride, head_cols,
-                                         s);
+                                         s, bf16_only);
     }
-    // any other table / pattern: the best variant that applies, then one conversion pass
+    // any other table / pattern: the best variant that applies, then one conversion pass (the fp32 heights are written
+    // on this path also in the bf16-only mode: it is the staging buffer of the conversion)
     const int variant = cells != nullptr ? 2 : 0;
     if (int rc = rover_height_scan(pos_w, quat_w, n_envs, ray_starts_local, n_rays, pattern_box, grid, cells, max_distance,
                                    base_offset, obs + head_cols, obs_stride, nullptr, variant, stream))
@@ -353,4 +355,23 @@ extern "C" int rover_height_scan_obs(const float* pos_w, const float* quat_w, in
     obs_to_bf16_kernel<<<1184, 256, 0, s>>>(obs, obs_stride, n_envs, head_cols + n_rays,
                                             reinterpret_cast<__nv_bfloat16*>(obs_bf16), bf16_stride);
     return check_launch("obs_to_bf16_kernel");
+}
+
+extern "C" int rover_height_scan_obs(const float* pos_w, const float* quat_w, int32_t n_envs,
+                                     const float* ray_starts_local, int32_t n_rays, const float* pattern_box,
+                                     const RoverScanGrid* grid, const RoverPlaneCells* cells, float max_distance,
+                                     float base_offset, float* obs, int32_t obs_stride, int32_t head_cols,
+                                     uint16_t* obs_bf16, int32_t bf16_stride, void* stream) {
+    return height_scan_obs_impl(pos_w, quat_w, n_envs, ray_starts_local, n_rays, pattern_box, grid, cells, max_distance,
+                                base_offset, obs, obs_stride, head_cols, obs_bf16, bf16_stride, stream, false);
+}
+
+extern "C" int rover_height_scan_obs_bf16(const float* pos_w, const float* quat_w, int32_t n_envs,
+                                          const float* ray_starts_local, int32_t n_rays, const float* pattern_box,
+                                          const RoverScanGrid* grid, const RoverPlaneCells* cells, float max_distance,
+                                          float base_offset, const float* obs_head, int32_t obs_stride, int32_t head_cols,
+                                          uint16_t* obs_bf16, int32_t bf16_stride, void* stream) {
+    return height_scan_obs_impl(pos_w, quat_w, n_envs, ray_starts_local, n_rays, pattern_box, grid, cells, max_distance,
+                                base_offset, const_cast<float*>(obs_head), obs_stride, head_cols, obs_bf16, bf16_stride,
+                                stream, true);
 }

@@ -42,7 +42,9 @@ namespace rover {
 // kBf16: rover_height_scan_obs -- `out` points at column head_cols of the fp32 observation rows; the kernel also
 // writes the bf16 mirror obs_bf16[env, 0 : head_cols + n_rays] (head columns converted from the fp32 row, heights
 // rounded from the values it stores).
-template <bool kBf16>
+// kBf16 = 2: the same, but the fp32 heights are NOT stored (the fp32 rows are only read for their head columns): an
+// inference loop whose only consumer of the heights is the bf16 policy forward (rover_height_scan_obs_bf16).
+template <int kBf16>
 __global__ void __launch_bounds__(kPairThreads, 1)
 height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restrict__ quat_w, int n_envs,
                           const float* __restrict__ ray_local, int n_rays, const __grid_constant__ ScanGridDev g,
@@ -260,13 +262,14 @@ height_scan_paired_kernel(const float* __restrict__ pos_w, const float* __restri
                             const float X = __fadd_rn(__fadd_rn(__fadd_rn(vx, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
                             const float Y = __fadd_rn(__fadd_rn(__fadd_rn(vy, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
                             pair_resolve_deferred_ray(&sm, &st, g, pc.inv_dx, pc.inv_dy, X, Y, __fadd_rn(sm.vz[sl], h.pz),
-                                                      h.pz, max_d, base_offset, out_row + rr,
+                                                      h.pz, max_d, base_offset, kBf16 == 2 ? nullptr : out_row + rr,
                                                       kBf16 ? bf_row + rr : nullptr);
                         }
                     }
                 }
             } else {
-                pair_resolve_chunk_from_global(&sm, lane, r_begin, r_end, h, g, pc, max_d, base_offset, out_row, bf_row);
+                pair_resolve_chunk_from_global(&sm, lane, r_begin, r_end, h, g, pc, max_d, base_offset,
+                                               kBf16 == 2 ? nullptr : out_row, bf_row);
             }
             __syncwarp();
             DBG_STAMP(dbg_slot + 2);
@@ -298,7 +301,7 @@ int launch_height_scan_pipelined(const float* pos_w, const float* quat_w, int n_
 int launch_height_scan_paired(const float* pos_w, const float* quat_w, int n_envs, const float* ray_local, int n_rays,
                               const ScanGridDev& g, const RoverPlaneCells* cells, float4 pattern_box, float max_d,
                               float base_offset, float* out, int out_stride, float* hits, uint16_t* obs_bf16,
-                              int bf16_stride, int head_cols, cudaStream_t stream) {
+                              int bf16_stride, int head_cols, cudaStream_t stream, bool bf16_only) {
     // hit positions are a debugging / test output: served by variant 4's kernel (same heights, same table); so is a
     // table without the planar copy
     if (obs_bf16 == nullptr && (hits != nullptr || cells->entries_planar == nullptr))
@@ -314,9 +317,11 @@ int launch_height_scan_paired(const float* pos_w, const float* quat_w, int n_env
         int dev = 0;
         ROVER_CUDA(cudaGetDevice(&dev));
         ROVER_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-        ROVER_CUDA(cudaFuncSetAttribute(height_scan_paired_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ROVER_CUDA(cudaFuncSetAttribute(height_scan_paired_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(PairSmem)));
-        ROVER_CUDA(cudaFuncSetAttribute(height_scan_paired_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ROVER_CUDA(cudaFuncSetAttribute(height_scan_paired_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(PairSmem)));
+        ROVER_CUDA(cudaFuncSetAttribute(height_scan_paired_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(PairSmem)));
         configured = true;
     }
@@ -328,12 +333,17 @@ int launch_height_scan_paired(const float* pos_w, const float* quat_w, int n_env
     const float rx = fmaxf(fabsf(pattern_box.x), fabsf(pattern_box.y)), ry = fmaxf(fabsf(pattern_box.z), fabsf(pattern_box.w));
     const float radius = sqrtf(rx * rx + ry * ry) * 1.0001f + 1.0e-3f;
     const int grid = n_envs < n_sms ? n_envs : n_sms;
-    if (obs_bf16 != nullptr)
-        ROVER_CUDA(launch_overlapped(height_scan_paired_kernel<true>, dim3(grid), dim3(kPairThreads), sizeof(PairSmem), stream,
+    ROVER_CHECK(!bf16_only || obs_bf16 != nullptr, "height_scan_paired: bf16-only output needs the bf16 buffer");
+    if (obs_bf16 != nullptr && bf16_only)
+        ROVER_CUDA(launch_overlapped(height_scan_paired_kernel<2>, dim3(grid), dim3(kPairThreads), sizeof(PairSmem), stream,
+                                     pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, tmap, radius, max_d, base_offset, out,
+                                     out_stride, reinterpret_cast<__nv_bfloat16*>(obs_bf16), bf16_stride, head_cols));
+    else if (obs_bf16 != nullptr)
+        ROVER_CUDA(launch_overlapped(height_scan_paired_kernel<1>, dim3(grid), dim3(kPairThreads), sizeof(PairSmem), stream,
                                      pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, tmap, radius, max_d, base_offset, out,
                                      out_stride, reinterpret_cast<__nv_bfloat16*>(obs_bf16), bf16_stride, head_cols));
     else
-        ROVER_CUDA(launch_overlapped(height_scan_paired_kernel<false>, dim3(grid), dim3(kPairThreads), sizeof(PairSmem), stream,
+        ROVER_CUDA(launch_overlapped(height_scan_paired_kernel<0>, dim3(grid), dim3(kPairThreads), sizeof(PairSmem), stream,
                                      pos_w, quat_w, n_envs, ray_local, n_rays, g, pc, tmap, radius, max_d, base_offset, out,
                                      out_stride, nullptr, 0, 0));
     return check_launch("height_scan_paired_kernel");

@@ -255,8 +255,10 @@ static __device__ __noinline__ void pair_resolve_deferred_ray(const SM* sm, cons
         zhit = (q.w == 0.f) ? eval_cell(st->p[e], q, __fsub_rn(X, xp[ci].lo), __fsub_rn(Y, yp[cj].lo), Z, max_d)
                             : walk_home_grid(g, X, Y, Z, max_d);
     }
-    store_result(pz, X, Y, Z, zhit, base_offset, out, nullptr);
-    if (out_bf != nullptr) *out_bf = __float2bfloat16_rn(*out);
+    float height;
+    store_result(pz, X, Y, Z, zhit, base_offset, &height, nullptr);
+    if (out != nullptr) *out = height;  // (out == nullptr: the bf16-only observation mode)
+    if (out_bf != nullptr) *out_bf = __float2bfloat16_rn(height);
 }
 
 // Rare path (b): a chunk of an environment whose window is not staged (too large, not covered on a non-uniform
@@ -275,8 +277,10 @@ static __device__ __noinline__ void pair_resolve_chunk_from_global(const SM* sm,
         const float X = __fadd_rn(__fadd_rn(__fadd_rn(vx, __fmul_rn(h.cw, tx)), -__fmul_rn(h.sz, ty)), h.px);
         const float Y = __fadd_rn(__fadd_rn(__fadd_rn(vy, __fmul_rn(h.cw, ty)), __fmul_rn(h.sz, tx)), h.py);
         const float Z = __fadd_rn(sm_vz(*sm, sl), h.pz);
-        store_result(h.pz, X, Y, Z, resolve_from_global(g, pc, X, Y, Z, max_d), base_offset, out_row + r, nullptr);
-        if (bf_row != nullptr) bf_row[r] = __float2bfloat16_rn(out_row[r]);
+        float height;
+        store_result(h.pz, X, Y, Z, resolve_from_global(g, pc, X, Y, Z, max_d), base_offset, &height, nullptr);
+        if (out_row != nullptr) out_row[r] = height;
+        if (bf_row != nullptr) bf_row[r] = __float2bfloat16_rn(height);
     }
 }
 
@@ -284,9 +288,9 @@ static __device__ __noinline__ void pair_resolve_chunk_from_global(const SM* sm,
 // Returns a 2-bit mask of the rays that need the rare path.
 // kFull: the whole batch lies inside the pattern (no per-ray validity predicates); kFlatZ: every ray starts at the
 // same local z (grid patterns), so Z is a per-environment constant.
-// kBf: the heights are also stored as bf16 (round to nearest even) at ob[0] / ob[64] -- the observation mirror that
-// feeds rover_policy_forward_bf16.
-template <bool kFull, bool kFlatZ, bool kBf, int kSink = kSinkGlobal, class SM = PairSmem>
+// kBf = 1: the heights are also stored as bf16 (round to nearest even) at ob[0] / ob[64] -- the observation mirror that
+// feeds rover_policy_forward_bf16; kBf = 2: ONLY the bf16 mirror is stored (the fp32 row is not written).
+template <bool kFull, bool kFlatZ, int kBf, int kSink = kSinkGlobal, class SM = PairSmem>
 __device__ __forceinline__ unsigned resolve_pair(const unsigned char* __restrict__ smem, const SM& sm,
                                                  const PairCtx& c, int slot, int ray_a, int n_rays,
                                                  float* __restrict__ o, __nv_bfloat16* __restrict__ ob,
@@ -341,7 +345,7 @@ __device__ __forceinline__ unsigned resolve_pair(const unsigned char* __restrict
     const float t0 = lo_of(T), t1 = hi_of(T);
     const float h0 = (t0 >= 0.f && t0 < c.max_d) ? lo_of(H) : -INFINITY;
     const float h1 = (t1 >= 0.f && t1 < c.max_d) ? hi_of(H) : -INFINITY;
-    if (kSink != kSinkOperand) {
+    if (kSink != kSinkOperand && kBf != 2) {
         if (keep[0]) o[0] = h0;
         if (keep[1]) o[64] = h1;
     }

@@ -240,10 +240,13 @@ _HOST_SCAN_CALLS: dict = {}
 
 def height_scan_obs(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle, obs: torch.Tensor,
                     obs_bf16: torch.Tensor, head_cols: int = 4, max_distance: float = 100.0,
-                    base_offset: float = 0.26878) -> None:
+                    base_offset: float = 0.26878, bf16_only: bool = False) -> None:
     """Height scan into the observation buffers of the closed loop: heights -> ``obs[:, head_cols:head_cols + R]``
     (fp32) and the bf16 mirror of ``obs[:, :head_cols + R]`` -> ``obs_bf16`` (``policy.alloc_obs_bf16``), the operand
-    of ``GaussianNeuralNetwork.compute_bf16``.  One launch (variant 5 with the extra stores)."""
+    of ``GaussianNeuralNetwork.compute_bf16``.  One launch (variant 5 with the extra stores).
+    ``bf16_only``: only the mirror is written (``rover_height_scan_obs_bf16``) -- ``obs`` is read for its head columns and
+    its height columns keep what they held; for loops in which the bf16 policy forward is the heights' only consumer.
+    The policy rounds fp32 observations to exactly these bf16 values, so actions and trajectory do not change."""
     if not isinstance(rays, RayPattern):
         rays = RayPattern(rays, pos_w.device)
     _lib.require_cuda(pos_w, quat_w)  # obs / obs_bf16 are row-strided views: checked below
@@ -253,7 +256,7 @@ def height_scan_obs(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanG
             or obs_bf16.shape[1] < head_cols + rays.n_rays or not obs_bf16.is_cuda):
         raise RuntimeError("height_scan_obs: obs must be fp32 and obs_bf16 bf16, both [N, >= head_cols + R] with unit inner stride")
     torch.ops.rover_b200.height_scan_obs(pos_w, quat_w, rays.starts, rays.box_t, grid.desc, grid.cells_desc,
-                                         float(max_distance), float(base_offset), obs, int(head_cols), obs_bf16)
+                                         float(max_distance), float(base_offset), obs, int(head_cols), obs_bf16, bool(bf16_only))
 
 
 def height_scan_encoder(pos_w: torch.Tensor, quat_w: torch.Tensor, rays, grid: ScanGridHandle, obs: torch.Tensor, net,

@@ -33,7 +33,8 @@ _SCHEMAS = {
     "height_scan_hits": "(Tensor pos_w, Tensor quat_w, Tensor ray_starts, Tensor pattern_box, Tensor grid, Tensor? cells, "
                         "float max_distance, float base_offset, int variant) -> (Tensor, Tensor)",
     "height_scan_obs": "(Tensor pos_w, Tensor quat_w, Tensor ray_starts, Tensor pattern_box, Tensor grid, Tensor? cells, "
-                       "float max_distance, float base_offset, Tensor(a!) obs, int head_cols, Tensor(b!) obs_bf16) -> ()",
+                       "float max_distance, float base_offset, Tensor(a!) obs, int head_cols, Tensor(b!) obs_bf16, "
+                       "bool bf16_only=False) -> ()",
     "height_scan_host": "(Tensor pos_host, Tensor quat_host, Tensor ray_starts, Tensor pattern_box, Tensor grid, "
                         "Tensor? cells, float max_distance, float base_offset, int variant, int n_slices, Tensor(a!) work, "
                         "Tensor(b!) out_host) -> ()",
@@ -181,7 +182,7 @@ def _height_scan_host(pos_host, quat_host, ray_starts, pattern_box, grid, cells,
 
 
 def _height_scan_obs(pos_w, quat_w, ray_starts, pattern_box, grid, cells, max_distance, base_offset, obs, head_cols,
-                     obs_bf16):
+                     obs_bf16, bf16_only=False):
     _f32("height_scan_obs", pos_w, quat_w, ray_starts)
     n, r = pos_w.shape[0], ray_starts.shape[0]
     if (obs.dtype != torch.float32 or obs.shape[0] != n or obs.stride(1) != 1 or obs.shape[1] < head_cols + r
@@ -189,7 +190,8 @@ def _height_scan_obs(pos_w, quat_w, ray_starts, pattern_box, grid, cells, max_di
             or obs_bf16.shape[1] < head_cols + r):
         raise RuntimeError("rover_b200::height_scan_obs: obs must be fp32 and obs_bf16 bf16, both [N, >= head_cols + R] "
                            "with unit inner stride")
-    _lib.check(_lib.load().rover_height_scan_obs(
+    entry = _lib.load().rover_height_scan_obs_bf16 if bf16_only else _lib.load().rover_height_scan_obs
+    _lib.check(entry(
         _p(pos_w), _p(quat_w), n, _p(ray_starts), r, C.cast(C.c_void_p(pattern_box.data_ptr()), C.POINTER(C.c_float * 4)),
         _desc(grid, _lib.ScanGrid, "grid"), _desc(cells, _lib.PlaneCells, "cells") if cells is not None else None,
         float(max_distance), float(base_offset), _p(obs), int(obs.stride(0)), int(head_cols), _p(obs_bf16),

@@ -230,3 +230,35 @@ def test_policy_and_value_in_one_pass_are_bit_identical(cuda_device, golden, gol
             policy_value_forward(pol, val, obs.cpu())
         with pytest.raises(RuntimeError):
             torch.ops.rover_b200.policy_value_forward(obs.double(), pol._packed, val._packed)
+
+
+def test_bf16_only_observation_scan_changes_nothing_downstream(cuda_device, golden):
+    """rover_height_scan_obs_bf16: the scan stores only the bf16 observation.  The mirror equals the one the fp32 + bf16
+    scan writes, the fp32 height columns are left alone, and the policy's means equal those on the fp32 observation
+    bit for bit (it rounds fp32 observations to these very bf16 values)."""
+    from isaac_rover_orbit_b200 import ops, synthetic
+    from isaac_rover_orbit_b200 import terrain as TR
+
+    _, sd = golden
+    net = GaussianNeuralNetwork(device=cuda_device)
+    net.load_state_dict(sd)
+    v, f = TR.make_synthetic_terrain(48.0, 0.2, seed=3)
+    grid = ops.ScanGridHandle.from_mesh(v, f, cuda_device)
+    rays = ops.RayPattern.grid(cuda_device)
+    n = 777
+    g = torch.Generator().manual_seed(12)
+    p, q = (t.to(cuda_device) for t in synthetic.make_poses(n, g, torch.from_numpy(v), 48.0, 0.2, margin=4.0))
+    head = (torch.rand(n, 4, generator=g) * 2 - 1).to(cuda_device)
+    obs_a, obs_b = alloc_obs(n, cuda_device), alloc_obs(n, cuda_device)
+    bf_a, bf_b = alloc_obs_bf16(n, cuda_device), alloc_obs_bf16(n, cuda_device)
+    for o in (obs_a, obs_b):
+        o.fill_(123.0)
+        o[:, :4] = head
+    ops.height_scan_obs(p, q, rays, grid, obs_a, bf_a)
+    ops.height_scan_obs(p, q, rays, grid, obs_b, bf_b, bf16_only=True)
+    torch.cuda.synchronize()
+    assert torch.equal(bf_a[:, :965].view(torch.int16), bf_b[:, :965].view(torch.int16))
+    assert bool((obs_b[:, 4:] == 123.0).all()) and torch.equal(obs_b[:, :4], head)  # fp32 heights never written
+    m_fp32 = net.compute({"states": obs_a})[0]
+    m_bf16 = net.compute_bf16({"states": bf_b})[0]
+    assert torch.equal(m_fp32, m_bf16)
