@@ -43,7 +43,8 @@ __device__ unsigned long long g_pol_cta[2][256];  // globaltimer (ns) at CTA sta
     } while (0)
 #endif
 
-constexpr int kWsThreads = 352;
+constexpr int kWsThreads = 352;        // bf16 observations: warps 0-10
+constexpr int kWsThreadsF32 = 480;     // fp32 observations: + warps 11-14, a second converter warpgroup
 constexpr int kWsChunkK = 32;
 constexpr int kWsChunks = 31;  // observation columns [0, 992) cover the encoder input [3, 964)
 constexpr int kWsStagesF = 5;
@@ -96,7 +97,7 @@ static_assert(kTileM * kBfChunkK * 2 == kTileM * kWsChunkK * 4, "both modes use 
 // kDual: `packed` = policy, `packed2` = value network, outputs `mean` [N, 2] and `value2` [N]; else one network
 // (value_head: linear [N] output instead of tanh [N, 2]).
 template <bool kBf16In, bool kDual = false>
-__global__ void __launch_bounds__(kWsThreads, 1)
+__global__ void __launch_bounds__(kBf16In ? kWsThreads : kWsThreadsF32, 1)
 policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const float* __restrict__ obs, int obs_stride,
                          int n_envs, int tile_rows, const unsigned char* __restrict__ packed, float* __restrict__ mean,
                          int value_head, const unsigned char* __restrict__ packed2, float* __restrict__ value2) {
@@ -134,7 +135,7 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&obs_map)) : "memory");
         for (int i = 0; i < kStagesFK; ++i) {
             mb_init(&sm.f_full[i], 1);
-            mb_init(&sm.f_empty[i], kBf16In ? 1 : 4);  // converter warps, or the commit of the MMAs that read the stage
+            mb_init(&sm.f_empty[i], kBf16In ? 1 : 8);  // converter warps, or the commit of the MMAs that read the stage
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the observation is what the kernel in front of this one writes: under a programmatic dependent launch
@@ -148,7 +149,7 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
     }
     if (tid == 0) {
         for (int i = 0; i < kWsStagesA; ++i) {
-            mb_init(&sm.a_full[i], 4);
+            mb_init(&sm.a_full[i], 8);  // the eight converter warps
             mb_init(&sm.a_empty[i], 1);  // tcgen05.commit
         }
         for (int i = 0; i < kWsStagesW; ++i) {
@@ -264,11 +265,15 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
         // =============================================================== converters: fp32 stage -> bf16 A operand
         // first the packed weights into L2 (326 KB; after an L2 flush every layer's first load was a cold miss that the
         // layer group waited for: 21 k instead of 13 k cycles for the first tile)
-        for (int off = (tid - 128) * 128; off < kPackedBytes; off += 128 * 128) {
+        // Two warpgroups (warps 4-7 and 11-14): a thread converts HALF of its row's chunk (planes 2 * half, 2 * half + 1).
+        // With one warpgroup a chunk took 506 cycles -- the wait -> LDS -> pack -> STS -> fence -> arrive chain of one warp
+        // per scheduler -- which bounds the stream whenever the observation comes from L2 (the closed loop: 8.2 us per tile).
+        const int half = warp >= 11 ? 1 : 0;
+        const int row = half ? tid - kWsThreads : tid - 128;  // tile row
+        for (int off = (half * 128 + row) * 128; off < kPackedBytes; off += 256 * 128) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(packed + off));
             if (kDual) asm volatile("prefetch.global.L2 [%0];" ::"l"(packed2 + off));
         }
-        const int row = tid - 128;  // tile row
         const int sx = row & 7;     // SWIZZLE_128B: 16-byte unit u of row r sits at unit u ^ (r & 7)
         int sf = 0, sa = 0;
         uint32_t pf = 0, pa = 0;
@@ -282,7 +287,8 @@ policy_forward_ws_kernel(const __grid_constant__ CUtensorMap obs_map, const floa
                 const unsigned char* src = reinterpret_cast<const unsigned char*>(sm.stage_f[sf]) + row * (kWsChunkK * 4);
                 unsigned char* dst = sm.a_bf16[sa] + row * 16;
 #pragma unroll
-                for (int plane = 0; plane < kWsChunkK / 8; ++plane) {
+                for (int pl = 0; pl < kWsChunkK / 16; ++pl) {
+                    const int plane = 2 * half + pl;
                     if (row >= tile_rows) break;  // rows beyond the tile: never loaded, never stored
                     const float4 lo = *reinterpret_cast<const float4*>(src + (((2 * plane) ^ sx) << 4));
                     const float4 hi = *reinterpret_cast<const float4*>(src + (((2 * plane + 1) ^ sx) << 4));
@@ -565,7 +571,7 @@ int launch_policy_forward_ws(const void* obs, int obs_stride, int n_envs, const 
     const unsigned char* no_net = nullptr;
     float* no_out = nullptr;
     if (dual)
-        ROVER_CUDA(launch_overlapped(policy_forward_ws_kernel<false, true>, dim3(grid), dim3(kWsThreads), (size_t)kSmemBytesDual,
+        ROVER_CUDA(launch_overlapped(policy_forward_ws_kernel<false, true>, dim3(grid), dim3(kWsThreadsF32), (size_t)kSmemBytesDual,
                                      stream, map, static_cast<const float*>(obs), obs_stride, n_envs, tile_rows,
                                      static_cast<const unsigned char*>(packed), mean, 0,
                                      static_cast<const unsigned char*>(packed2), value2));
@@ -574,7 +580,7 @@ int launch_policy_forward_ws(const void* obs, int obs_stride, int n_envs, const 
                                      static_cast<const float*>(obs), obs_stride, n_envs, tile_rows,
                                      static_cast<const unsigned char*>(packed), mean, value_head ? 1 : 0, no_net, no_out));
     else
-        ROVER_CUDA(launch_overlapped(policy_forward_ws_kernel<false>, dim3(grid), dim3(kWsThreads), (size_t)kSmemBytes, stream, map,
+        ROVER_CUDA(launch_overlapped(policy_forward_ws_kernel<false>, dim3(grid), dim3(kWsThreadsF32), (size_t)kSmemBytes, stream, map,
                                      static_cast<const float*>(obs), obs_stride, n_envs, tile_rows,
                                      static_cast<const unsigned char*>(packed), mean, value_head ? 1 : 0, no_net, no_out));
     return check_launch("policy_forward_ws_kernel");
