@@ -4,12 +4,13 @@
 // behind a CTA-wide barrier -- issue slots 15 % busy, tensor pipe 8 %, HBM idle during layers 1-5; 130 us at cfg-4
 // where the 254 MB of fp32 observations alone take 39 us at the measured HBM rate.
 //
-// Roles (one persistent CTA per SM, 10 warps, all 512 TMEM columns):
+// Roles (one persistent CTA per SM, 11 warps -- 15 with fp32 observations --, all 512 TMEM columns):
 //   warp 8      TMA producer: obs chunks (128 envs x 32 columns fp32, SWIZZLE_128B) into a 5-stage ring, running ahead
 //               across tiles (up to 80 KB of HBM reads in flight per SM).
 //   warp 10     W0 producer: the matching 5 KB slice of the packed W0 image into a 3-stage ring.  (A single producer
 //               thread serving both rings stalled the observation stream on the shallower W0 ring: 84 us.)
-//   warps 4-7   converters: fp32 stage -> bf16 A operand (K-major core-matrix layout), 2-stage ring.
+//   warps 4-7   converters: fp32 stage -> bf16 A operand (K-major core-matrix layout), 2-stage ring; warps 11-14: the
+//               second converter warpgroup (each thread converts half of its row's chunk).
 //   warp 9      layer-0 MMA issuer: 2 tcgen05.mma per chunk into D0[tile parity] (two 80-column accumulators);
 //               tcgen05.commit frees the A / W0 stages and, after the last chunk, publishes D0.
 //   warps 0-3   layer group: epilogue of layer l (tcgen05.ld -> +bias -> LeakyReLU -> bf16) writes the A operand of
