@@ -76,6 +76,21 @@ __device__ __forceinline__ RngKey load_rng_key(const VariatesDev& V) {
 // that are gone by then: a named barrier with an explicit count instead of __syncthreads())
 __device__ __forceinline__ void mdp_block_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ROVER_MDP_BLOCK) : "memory"); }
 
+// Hardware barriers of the split CTA (2 env warps + 2 kinematics warps = 128 threads; 0 is __syncthreads, 1 the env warps'
+// own barrier above).  One side arrives, the other waits: producer / consumer hand-offs through shared memory.
+enum SplitBarrier : int {
+    kBarTicket = 2,      // env warps took the CTA's ticket            -> kinematics warps (launch-wide reduction if it was the last)
+    kBarKinematics = 3,  // the 64 kinematics threads among themselves (publication, reduction)
+    kBarSnapshot = 4,    // kinematics warps of CTA 0 read the totals they publish -> env warps (before their ticket)
+    kBarHandoff = 5,     // kinematics warps: variates + would-be spawn rows       -> env warps
+    kBarResetFlags = 6,  // env warps: which envs reset                              -> kinematics warps
+    kBarTargets = 7,     // kinematics warps: the new targets                        -> env warps
+};
+template <int kId>
+__device__ __forceinline__ void split_arrive() { asm volatile("bar.arrive %0, 128;" ::"n"(kId) : "memory"); }
+template <int kId>
+__device__ __forceinline__ void split_wait() { asm volatile("bar.sync %0, 128;" ::"n"(kId) : "memory"); }
+
 // shared memory of one MDP CTA
 struct MdpShared {
     int warp_cnt[ROVER_MDP_BLOCK / 32];
@@ -116,7 +131,7 @@ __device__ __forceinline__ void publish_block_stats(float (&st)[kStats], MdpShar
     MDP_STAMP(4);
     // (split CTA 0 of a multi-GPU run: its kinematics warps have read the totals they publish -- hardware barrier 4 -- before
     // this CTA's ticket can make the launch-wide reduction, which rewrites those totals, possible)
-    if (after_snapshot) asm volatile("bar.sync 4, 128;" ::: "memory");
+    if (after_snapshot) split_wait<kBarSnapshot>();
     if (threadIdx.x == 0) sh.is_last = (atomicAdd(done_counter, 1u) == (unsigned)n_blocks - 1u) ? 1 : 0;
 }
 
@@ -207,8 +222,8 @@ __device__ __forceinline__ void final_stats_reduce(int tid, MdpShared& sh, int n
 }
 
 // hardware barrier 2: the env warps of a split CTA announce the ticket (arrive), its kinematics warps wait for it (sync)
-__device__ __forceinline__ void split_ticket_arrive() { asm volatile("bar.arrive 2, 128;" ::: "memory"); }
-__device__ __forceinline__ void split_ticket_wait() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void split_ticket_arrive() { split_arrive<kBarTicket>(); }
+__device__ __forceinline__ void split_ticket_wait() { split_wait<kBarTicket>(); }
 
 // kSplit (single-launch step with in-kernel variates): the statistics leave the env warps as soon as they are complete --
 // after the target draw, before metrics / command update / observation head -- where the fence in front of the ticket
@@ -307,7 +322,7 @@ __device__ __forceinline__ void post_step_block(MdpShared& sh, int bid, int n_bl
                 split_ticket_arrive();
             },
             [&](float& tx, float& ty, float& tz, bool& ex) {  // the targets the kinematics warps drew (barrier 7)
-                asm volatile("bar.sync 7, 128;" ::: "memory");
+                split_wait<kBarTargets>();
                 const int t = (int)threadIdx.x;
                 tx = sh.target[0][t], ty = sh.target[1][t], tz = sh.target[2][t], ex = sh.target[3][t] != 0.f;
                 return true;
@@ -399,7 +414,7 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
             double snapshot = 0.0;
             if (publisher) {
                 if (ht < kStats) snapshot = X.cumulative[ht];
-                asm volatile("bar.arrive 4, 128;" ::: "memory");  // read before this CTA's ticket (publish_block_stats)
+                split_arrive<kBarSnapshot>();  // read before this CTA's ticket (publish_block_stats)
             }
             {   // the env's variate stream 0 and its would-be spawn row: rng state -> Philox -> keyed permutation -> row, a
                 // chain of two cold misses and ~350 instructions that the env warps no longer carry
@@ -420,12 +435,12 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
                 sh.hand_idx[ht] = idx;
                 sh.hand[0][ht] = hx, sh.hand[1][ht] = hy, sh.hand[2][ht] = hz, sh.hand[3][ht] = yaw_u, sh.hand[4][ht] = heading_u;
                 __threadfence_block();
-                asm volatile("bar.arrive 5, 128;" ::: "memory");
+                split_arrive<kBarHandoff>();
                 // the target draw of the envs that reset (flag from the env warps) or whose timer runs out this step:
                 // the same rs_reset / rs_timer / origin rules as post_env_work, the same resample_warp
                 const float tl = (hi < n && (phases & ROVER_PHASE_TIME)) ? S.time_left[hi] : 0.f;
                 float ox = hx, oy = hy;
-                asm volatile("bar.sync 6, 128;" ::: "memory");
+                split_wait<kBarResetFlags>();
                 const bool h_reset = hi < n && sh.reset_flag[ht] != 0;
                 const bool rs_reset = h_reset && (phases & ROVER_PHASE_RESAMPLE);
                 const bool rs_timer = hi < n && !rs_reset && (phases & ROVER_PHASE_TIME) && __fsub_rn(tl, P.step_dt) <= 0.f;
@@ -437,15 +452,15 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
                 const bool ex = resample_warp<kRng>(hi, rs_reset || rs_timer, P, T, ox, oy, V.theta_u, hkey, V.n_rounds, tx, ty, tz);
                 sh.target[0][ht] = tx, sh.target[1][ht] = ty, sh.target[2][ht] = tz, sh.target[3][ht] = ex ? 1.f : 0.f;
                 __threadfence_block();
-                asm volatile("bar.arrive 7, 128;" ::: "memory");
+                split_arrive<kBarTargets>();
             }
             pre_step_env<kPreKinematics>(bid * ROVER_MDP_BLOCK + ht, new_actions, force, n, P, S, O, pre_phases);
-            if (publisher) publish_totals<3>(ht, snapshot, sh, X);
+            if (publisher) publish_totals<kBarKinematics>(ht, snapshot, sh, X);
             // ... then they wait for the CTA's ticket: if it was the launch's last one, the launch-wide reduction of the
             // statistics is theirs (the env warps are still busy with metrics / command update / observation head)
             split_ticket_wait();
             if (sh.is_last) {
-                final_stats_reduce<true, kRng, 3, false>(ht, sh, n_blocks, P, V, block_stats, done_counter, stats, log_out, phases,
+                final_stats_reduce<true, kRng, kBarKinematics, false>(ht, sh, n_blocks, P, V, block_stats, done_counter, stats, log_out, phases,
                                                          X, lookback, 0u);
 #if ROVER_MDP_DBG
                 if (threadIdx.x == ROVER_MDP_BLOCK) {
@@ -506,12 +521,12 @@ mdp_fused_step_kernel(const float* __restrict__ new_actions, const float* __rest
         if constexpr (kSplit) {  // which envs reset -> the kinematics warps: they draw the new targets during the rewards
             sh.reset_flag[threadIdx.x] = reset_now ? 1 : 0;
             __threadfence_block();
-            asm volatile("bar.arrive 6, 128;" ::: "memory");
+            split_arrive<kBarResetFlags>();
         }
     });
     MDP_STAMP(2);
     if constexpr (kSplit) {  // the kinematics warps' handoff (long there by now)
-        asm volatile("bar.sync 5, 128;" ::: "memory");
+        split_wait<kBarHandoff>();
         const int t = (int)threadIdx.x;
         early.have = (i < n) && (phases & ROVER_PHASE_SPAWN);
         early.idx = sh.hand_idx[t];
