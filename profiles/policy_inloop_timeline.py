@@ -29,6 +29,10 @@ for mode in ("cold obs (flushed)", "obs just written by the scan"):
              "W3hi+MMA3b done", "epi3+MMA4 issued", "MMA4 done", "epi4+MMA5 issued", "MMA5 done", "epi5 done"]
     row = t[1024:1024 + 14]
     print(mode, ": producer issue", t[0:31:6].tolist(), "MMA issued", t[512:543:6].tolist())
+    c = np.arange(8, 30)
+    print("   steady state per chunk (cycles): TMA issue -> data landed", int((t[128 + c] - t[c]).mean()), "| landed -> A slot free", int((t[256 + c] - t[128 + c]).mean()),
+          "| convert", int((t[384 + c] - t[256 + c]).mean()), "| converted -> MMA issued", int((t[512 + c] - t[384 + c]).mean()),
+          "| chunk period", int(np.diff(t[512 + c]).mean()))
     print("   layer group tile 0:", {nm: int(v) for nm, v in zip(names, row)})
     cta = np.zeros((2, 256), dtype=np.uint64)
     assert lib.rover_debug_policy_ctas(cta.ctypes.data_as(C.c_void_p)) == 0
